@@ -1,0 +1,261 @@
+"""Pin the oracle against the UNMODIFIED reference and write golden fixtures.
+
+Runs only in the build container (needs ``/root/reference``).  For every case it
+  1. builds the reference modules with a fixed seed (default PyTorch init, the
+     construction order of ``train_mask_grid_sample.py:38-61``: coarse, decoder, fine),
+  2. runs the reference's own ``render_rays_cross_ray`` / ``sample_pdf`` /
+     ``PosEmbedding`` / ``NeRF_sigma`` / ``style_net`` on CPU,
+  3. runs ``oracle/crnerf_oracle.py`` on the same inputs and asserts the outputs
+     are bit-identical (``torch.equal``) - that is the pin,
+  4. saves inputs + reference outputs (+ the random draws of train-mode cases)
+     to ``tests/golden/<case>.pt``.
+
+Weights are NOT stored (2 x 2.5 MB): they are regenerated from the seed by the
+product's own module mirror, and each fixture carries a checksum of every
+parameter so a drift in init order or RNG is caught.
+
+    python oracle/make_golden.py            # writes tests/golden/*.pt
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import types
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("CRNERF_REFERENCE", "/root/reference")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+sys.path.insert(0, HERE)
+import crnerf_oracle as oracle  # noqa: E402
+
+
+def import_reference():
+    """Import the reference's model files unmodified.  ``kornia`` is not
+    installed; ``nerf_decoder_stylenerf.py:104`` only needs the *name*
+    ``kornia.filters.filter2d`` at import time (``Blur`` is never constructed at
+    n_blocks == 0), so an empty stub module satisfies it."""
+    if "kornia" not in sys.modules:
+        k = types.ModuleType("kornia")
+        kf = types.ModuleType("kornia.filters")
+        kf.filter2d = lambda *a, **k_: (_ for _ in ()).throw(RuntimeError("kornia stub"))
+        k.filters = kf
+        sys.modules["kornia"] = k
+        sys.modules["kornia.filters"] = kf
+    sys.path.insert(0, REF)
+    import importlib
+    rendering = importlib.import_module("models.rendering")
+    nerf = importlib.import_module("models.nerf")
+    lst = importlib.import_module("models.linearStyleTransfer")
+    sys.path.remove(REF)
+    return rendering, nerf, lst
+
+
+def ref_args():
+    return types.SimpleNamespace(nerf_out_dim=64, pertubeCord=False, img_wh=[32, 32],
+                                 N_emb_xyz=15, N_emb_dir=4)
+
+
+def build_reference_models(nerf, lst, seed=0, peaky=False):
+    torch.manual_seed(seed)
+    args = ref_args()
+    coarse = nerf.NeRF_sigma("coarse", args, in_channels_xyz=93, in_channels_dir=27)
+    decoder = lst.style_net(args)
+    fine = nerf.NeRF_sigma("fine", args, in_channels_xyz=93, in_channels_dir=27,
+                           encode_appearance=True, in_channels_a=48, encode_random=True)
+    if peaky:
+        sharpen(coarse, seed + 100)
+        sharpen(fine, seed + 101)
+    return {"coarse": coarse.eval(), "fine": fine.eval(), "decoder": decoder.eval()}, args
+
+
+def sharpen(model, seed):
+    """'Peaky' variant: scale the sigma head so ray weights
+    concentrate and sample_pdf's search / empty-bin branches are exercised."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        w = model.static_sigma[0].weight
+        w.mul_(30.0)
+        w.add_(0.05 * torch.randn(w.shape, generator=g))
+        model.static_sigma[0].bias.sub_(2.0)
+
+
+def checksums(module):
+    return {k: (float(v.double().sum()), float(v.double().abs().sum()))
+            for k, v in module.state_dict().items()}
+
+
+def sd(module):
+    return {k: v.detach().clone() for k, v in module.state_dict().items()}
+
+
+def make_rays(n, seed, hw=(24, 32), near_far=(0.0, 5.0), per_ray_nf=False):
+    h, w = hw
+    rays = oracle.pinhole_rays(h, w, oracle.synthetic_pose(seed), *near_far)
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randperm(rays.shape[0], generator=g)[:n].sort()[0]
+    rays = rays[idx].clone()
+    if per_ray_nf:
+        rays[:, 6] = 0.05 + 0.45 * torch.rand(n, generator=g)
+        rays[:, 7] = 2.0 + 3.0 * torch.rand(n, generator=g)
+    return rays.contiguous()
+
+
+def assert_equal(name, a, b):
+    if not torch.equal(a, b):
+        d = (a.double() - b.double()).abs().max().item()
+        raise SystemExit(f"ORACLE != REFERENCE for {name}: max abs diff {d:g}")
+
+
+def case_render(rendering, nerf, lst, name, n_rays, ns, ni, train, peaky=False, seed=0,
+                per_ray_nf=False, use_disp=False):
+    models, args = build_reference_models(nerf, lst, seed=seed, peaky=peaky)
+    emb = {"xyz": nerf.PosEmbedding(14, 15), "dir": nerf.PosEmbedding(3, 4)}
+    rays = make_rays(n_rays, seed + 7, per_ray_nf=per_ray_nf or use_disp)
+    perturb, noise_std = (1.0, 1.0) if train else (0, 0)
+    with torch.no_grad():
+        torch.manual_seed(1234)
+        ref = rendering.render_rays_cross_ray(models, emb, rays, None, ns, use_disp, perturb,
+                                              noise_std, ni, 8192, False, test_time=not train,
+                                              args=args)
+        torch.manual_seed(1234)
+        rec = {}
+        mine = oracle.render_rays(sd(models["coarse"]), sd(models["fine"]), rays, n_samples=ns,
+                                  n_importance=ni, use_disp=use_disp, perturb=perturb,
+                                  noise_std=noise_std, chunk=8192, record=rec)
+    for k, v in mine.items():
+        assert_equal(f"{name}:{k}", v, ref[k])
+    if ni > 0:
+        assert ref["feature_fine_random"] is ref["feature_fine"]
+    out = {
+        "kind": "render", "seed": seed, "peaky": peaky, "n_samples": ns, "n_importance": ni,
+        "perturb": perturb, "noise_std": noise_std, "use_disp": use_disp, "rays": rays,
+        "rng": {k: v for k, v in rec.items() if k in ("perturb_rand", "noise_coarse", "noise_fine")},
+        "z_coarse": rec["z_coarse"], "z_fine": rec.get("z_fine"),
+        "ref": {k: v.clone() for k, v in ref.items() if k != "feature_fine_random"},
+        "checksum_coarse": checksums(models["coarse"]), "checksum_fine": checksums(models["fine"]),
+    }
+    if train and ni > 0:
+        # the uniform draws of sample_pdf: replay the generator to capture them
+        torch.manual_seed(1234)
+        z0 = torch.rand_like(rec["z_coarse"])
+        _ = torch.randn(n_rays, ns)
+        out["rng"]["u"] = torch.rand(n_rays, ni)
+        assert torch.equal(perturb * z0, rec["perturb_rand"])
+        with torch.no_grad():
+            again = oracle.render_rays(sd(models["coarse"]), sd(models["fine"]), rays, n_samples=ns,
+                                       n_importance=ni, perturb=perturb, noise_std=noise_std,
+                                       chunk=8192, rng=out["rng"])
+        for k, v in again.items():
+            assert_equal(f"{name}:replay:{k}", v, ref[k])
+    torch.save(out, os.path.join(GOLD, f"{name}.pt"))
+    print(f"  {name}: pinned ({', '.join(ref.keys())})")
+
+
+def case_posenc_mlp(nerf, lst):
+    models, args = build_reference_models(nerf, lst, seed=0)
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(96, 3, generator=g) - 0.5) * 8.0
+    d = torch.nn.functional.normalize(torch.randn(96, 3, generator=g), dim=-1)
+    e_x, e_d = nerf.PosEmbedding(14, 15), nerf.PosEmbedding(3, 4)
+    with torch.no_grad():
+        ex, ed = e_x(x), e_d(d)
+        assert_equal("posenc:xyz", oracle.pos_embed(x, 15), ex)
+        assert_equal("posenc:dir", oracle.pos_embed(d, 4), ed)
+        inp = torch.cat([ex, ed], 1)
+        ref_out = models["fine"](inp)
+        ref_sig = models["fine"](ex, sigma_only=True)
+        assert_equal("mlp", oracle.nerf_sigma_forward(sd(models["fine"]), inp), ref_out)
+        assert_equal("mlp:sigma_only",
+                     oracle.nerf_sigma_forward(sd(models["fine"]), ex, sigma_only=True), ref_sig)
+    torch.save({"kind": "posenc_mlp", "seed": 0, "xyz": x, "dir": d, "emb_xyz": ex, "emb_dir": ed,
+                "mlp_out": ref_out, "sigma_only": ref_sig,
+                "checksum_fine": checksums(models["fine"])},
+               os.path.join(GOLD, "posenc_mlp.pt"))
+    print("  posenc_mlp: pinned")
+
+
+def case_sample_pdf(rendering):
+    g = torch.Generator().manual_seed(11)
+    n, m = 48, 62
+    bins = torch.sort(torch.rand(n, m + 1, generator=g) * 5.0, dim=-1)[0]
+    w = torch.rand(n, m, generator=g) ** 4
+    w[:8] = 0.0                       # all-empty rays: pdf is uniform through eps
+    w[8:16, 10:40] = 0.0              # empty interior bins -> denom < eps branch
+    w[16:24] = 0.0
+    w[16:24, 30] = 1.0                # a single spike
+    out = {"kind": "sample_pdf", "bins": bins, "weights": w, "cases": []}
+    for ni, det in ((128, True), (64, True), (33, True), (128, False), (64, False)):
+        torch.manual_seed(99)
+        ref = rendering.sample_pdf(bins, w, ni, det=det)
+        torch.manual_seed(99)
+        mine = oracle.sample_pdf(bins, w, ni, det=det)
+        assert_equal(f"sample_pdf:{ni}:{det}", mine, ref)
+        u = None
+        if not det:
+            torch.manual_seed(99)
+            u = torch.rand(n, ni)
+            assert_equal("sample_pdf:u", oracle.sample_pdf(bins, w, ni, det=False, u=u), ref)
+        out["cases"].append({"n_importance": ni, "det": det, "u": u, "ref": ref})
+    torch.save(out, os.path.join(GOLD, "sample_pdf.pt"))
+    print("  sample_pdf: pinned (5 cases)")
+
+
+def case_style(nerf, lst):
+    models, args = build_reference_models(nerf, lst, seed=0)
+    dec = models["decoder"]
+    g = torch.Generator().manual_seed(21)
+    out = {"kind": "style", "seed": 0, "cases": [], "checksum_decoder": checksums(dec)}
+    for (h, w) in ((32, 32), (24, 40), (7, 9)):
+        feat = torch.rand(h * w, 64, generator=g) * 0.3 + 0.35      # (N,64) as the renderer emits
+        content = feat.t().reshape(1, 64, h, w)                      # caller's rearrange: a view
+        style = torch.rand(1, 64, 32, 32, generator=g)
+        with torch.no_grad():
+            ref = dec(content, style)
+            ref_c = dec(content, None, type="content")
+            fused, trans = dec.multi_net(content, style)
+            p = sd(dec)
+            assert_equal("style:fused", oracle.style_net_forward(p, content, style), ref)
+            assert_equal("style:content", oracle.style_net_forward(p, content, None, type="content"),
+                         ref_c)
+            f2, t2 = oracle.mul_layer_forward(p, content, style)
+            assert_equal("style:mullayer", f2, fused)
+            assert_equal("style:trans", t2, trans)
+        out["cases"].append({"h": h, "w": w, "feature": feat, "style": style, "rgb": ref,
+                             "rgb_content": ref_c, "fused": fused, "trans": trans})
+    torch.save(out, os.path.join(GOLD, "style.pt"))
+    print("  style_net: pinned (3 sizes)")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.parse_args()
+    if not os.path.isdir(REF):
+        raise SystemExit(f"reference not found at {REF}; golden vectors can only be made in the "
+                         "build container")
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(8)
+    rendering, nerf, lst = import_reference()
+    print("pinning oracle against", REF)
+    case_posenc_mlp(nerf, lst)
+    case_sample_pdf(rendering)
+    case_style(nerf, lst)
+    # config[0]-shaped (coarse only), eval and train mode, fine pass, peaky weights
+    case_render(rendering, nerf, lst, "render_c64_eval", 64, 64, 0, train=False)
+    case_render(rendering, nerf, lst, "render_64p128_eval", 96, 64, 128, train=False)
+    case_render(rendering, nerf, lst, "render_64p128_eval_peaky", 96, 64, 128, train=False,
+                peaky=True, per_ray_nf=True)
+    case_render(rendering, nerf, lst, "render_64p64_train", 64, 64, 64, train=True, seed=3)
+    case_render(rendering, nerf, lst, "render_32p24_train_peaky", 40, 32, 24, train=True,
+                peaky=True, seed=4, per_ray_nf=True)
+    case_render(rendering, nerf, lst, "render_48p48_disp", 32, 48, 48, train=False, seed=5,
+                use_disp=True)
+    print("done ->", GOLD)
+
+
+if __name__ == "__main__":
+    main()
