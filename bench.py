@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py - ray-samples/s of the CR-NeRF volume-rendering hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one eval-mode pass of ``render_rays_cross_ray`` over a batch of
+4096 synthetic Phototourism-shaped rays with 64 coarse + 128 fine samples
+(coarse pass -> inverse-CDF resampling -> fine pass), the configuration
+BASELINE.json's metric is quoted on.  One "ray-sample" = one of the
+4096*(64+128) = 786,432 fine-pass sample slots; each step
+evaluates the MLP at 4096*(64+192) = 1,048,576 points = 1.29306 TFLOP.
+
+  value : device-timed (CUDA events, max over ranks), inputs resident in HBM, L2
+          flushed between timed steps.
+  e2e   : same call through the public API with the rays in pinned HOST memory:
+          H2D copy + render + D2H read of the result inside the wall-clock region.
+  roofline : the dominant kernel (fused fine pass) timed alone, algorithmic
+          FLOPs / duration against the measured bf16 peak of MEASURED_PEAKS.json.
+  cpu_baseline : the oracle (torch-CPU port of the reference path) on the host cores.
+
+``--impl reference`` times that same CPU port alone (the reference is pure
+PyTorch; its own files cannot travel to the GPU box, the oracle is pinned
+bit-exact against them - oracle/make_golden.py).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "cr-nerf-pytorch_b200"), ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+N_RAYS, NS, NI = 4096, 64, 128
+FLOP_PER_POINT = 1233152                      # 2 * 616,576 MAC
+RAY_SAMPLES_PER_STEP = N_RAYS * (NS + NI)     # 786,432
+POINTS_PER_STEP = N_RAYS * (NS + NS + NI)     # 1,048,576
+METRIC = "ray-samples/sec at 4096 rays x (64+128) samples"
+UNIT = "ray-samples/s"
+WORKLOAD = ("configs[1]: 4096-ray eval batches (slices of a 320x256 synthetic Brandenburg-Gate-shaped "
+            "frame), 64 coarse + 128 fine samples, N_emb_xyz=15, N_emb_dir=4, nerf_out_dim=64, "
+            "default-init weights seed 0")
+
+
+def load_oracle():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import crnerf_oracle
+    return crnerf_oracle
+
+
+def make_args():
+    return types.SimpleNamespace(nerf_out_dim=64, pertubeCord=False, img_wh=[320, 256])
+
+
+def build_models():
+    from models.nerf import NeRF_sigma
+    from models.linearStyleTransfer import style_net
+    torch.manual_seed(0)
+    args = make_args()
+    coarse = NeRF_sigma('coarse', args, in_channels_xyz=93, in_channels_dir=27)
+    decoder = style_net(args)
+    fine = NeRF_sigma('fine', args, in_channels_xyz=93, in_channels_dir=27, encode_appearance=True,
+                      in_channels_a=48, encode_random=True)
+    return {"coarse": coarse.eval(), "fine": fine.eval(), "decoder": decoder.eval()}, args
+
+
+def frame_rays(oracle):
+    """A 320x256 frame = 20 batches of 4096 rays, fov 60 deg, near 0 / far 5."""
+    return oracle.pinhole_rays(256, 320, oracle.synthetic_pose(0), 0.0, 5.0)
+
+
+def cpu_state(models):
+    sd = lambda m: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    return sd(models["coarse"]), sd(models["fine"])
+
+
+def cpu_reference_throughput(oracle, state, rays, reps, warm=1):
+    """ray-samples/s of the CPU port on all host threads; each rep = one 4096-ray batch."""
+    pc, pf = state
+    times = []
+    with torch.no_grad():
+        for i in range(warm + reps):
+            batch = rays[(i % 20) * N_RAYS:(i % 20 + 1) * N_RAYS]
+            t0 = time.perf_counter()
+            oracle.render_rays(pc, pf, batch, n_samples=NS, n_importance=NI, perturb=0, noise_std=0,
+                               chunk=8192)
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append(dt)
+    return RAY_SAMPLES_PER_STEP / statistics.mean(times), times
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    oracle = load_oracle()
+    models, _ = build_models()
+    rays = frame_rays(oracle)
+    cores = torch.get_num_threads()
+    value, times = cpu_reference_throughput(oracle, cpu_state(models), rays, reps=max(1, args.steps),
+                                            warm=max(1, min(args.warmup, 2)))
+    sample = f"{len(times)} x one 4096-ray batch (786,432 ray-samples each) on {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(times), "warmup": max(1, min(args.warmup, 2)),
+        "ms_per_step": 1e3 * statistics.mean(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "device": "cpu", "chunk": 8192,
+                   "host_cpus": os.cpu_count()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from models.nerf import PosEmbedding
+    from models.rendering import render_rays_cross_ray
+    from crnerf_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    oracle = load_oracle()
+    models, margs = build_models()
+    rays_cpu = frame_rays(oracle)
+    state_cpu = cpu_state(models)          # nn.Module.to() moves in place: keep a CPU copy
+    models_gpu = {k: v.to(dev) for k, v in models.items()}
+    emb = {"xyz": PosEmbedding(14, 15), "dir": PosEmbedding(3, 4)}
+    # every rank renders its own 4096-ray batches of the frame (weak scaling)
+    n_batches = rays_cpu.shape[0] // N_RAYS
+    rays_dev = rays_cpu.to(dev)
+    batch = lambda i: rays_dev[((i * world + rank) % n_batches) * N_RAYS:
+                               ((i * world + rank) % n_batches + 1) * N_RAYS]
+    gather_buf = torch.empty(world * N_RAYS, 64, device=dev) if world > 1 else None
+
+    def step(rays):
+        with torch.no_grad():
+            res = render_rays_cross_ray(models_gpu, emb, rays, None, NS, False, 0, 0, NI, 32768, False,
+                                        test_time=True, args=margs)
+        if world > 1:  # the sharded frame's single collective: gather the rendered features
+            dist.all_gather_into_tensor(gather_buf, res["feature_fine"])
+        return res
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(3, args.warmup)):
+        step(batch(i))
+    barrier()
+
+    # ---- value: device-timed steps, inputs resident, L2 flushed between steps
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    n0 = ops.launch_count()
+    barrier()
+    for i, (e0, e1) in enumerate(evs):
+        flush.fill_(float(i))
+        e0.record()
+        step(batch(i))
+        e1.record()
+    barrier()
+    launches = ops.launch_count() - n0
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = world * RAY_SAMPLES_PER_STEP * args.steps / (dev_ms * 1e-3)
+
+    # ---- e2e: rays in pinned host memory, result read back, wall clock
+    host_rays = [rays_cpu[((i * world + rank) % n_batches) * N_RAYS:
+                          ((i * world + rank) % n_batches + 1) * N_RAYS].clone().pin_memory()
+                 for i in range(min(args.steps, n_batches))]
+    host_out = torch.empty(N_RAYS, 64).pin_memory()
+    host_depth = torch.empty(N_RAYS).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        r = host_rays[i % len(host_rays)].to(dev, non_blocking=True)
+        res = step(r)
+        host_out.copy_(res["feature_fine"], non_blocking=True)
+        host_depth.copy_(res["depth_fine"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()    # the caller consumes the result each step
+    barrier()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([wall], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * RAY_SAMPLES_PER_STEP * args.steps / float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel: the fused fine pass, timed alone
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        with torch.no_grad():
+            res = render_rays_cross_ray(models_gpu, emb, batch(0), None, NS, False, 0, 0, NI, 32768,
+                                        False, test_time=True, args=margs)
+            t_steps = torch.linspace(0, 1, NS, device=dev)
+            zc = ops.coarse_z(batch(0), t_steps)
+            zf = ops.sample_pdf_merge(zc, res["weights_coarse"], torch.linspace(0, 1, NI, device=dev), NI)
+            packed = models_gpu["fine"].packed()
+            for _ in range(3):
+                ops.render_pass(packed, batch(0), zf)
+            reps = 20
+            kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                   for _ in range(reps)]
+            torch.cuda.synchronize()
+            for e0, e1 in kev:
+                flush.fill_(1.0)
+                e0.record()
+                ops.render_pass(packed, batch(0), zf)
+                e1.record()
+            torch.cuda.synchronize()
+        k_ms = statistics.mean(e0.elapsed_time(e1) for e0, e1 in kev)
+        flop = N_RAYS * (NS + NI) * FLOP_PER_POINT
+        achieved = flop / (k_ms * 1e-3) / 1e12
+        peak, peak_src = 1590.0, "fallback (B200_PROFILING.md)"
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak, peak_src = float(mp["bf16_tflops"]), "measured burst (MEASURED_PEAKS.json bf16_tflops)"
+        except (OSError, KeyError, ValueError):
+            pass
+        roof = {"bound": "tensor", "kernel": "render_fused_kernel<fp16> fine pass, 4096x192 points",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                "flop_per_launch": flop}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = torch.get_num_threads()
+            v, times = cpu_reference_throughput(oracle, state_cpu, rays_cpu, reps=5, warm=1)
+            cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"5 x one 4096-ray batch (786,432 ray-samples each), "
+                                  f"{sum(times):.1f} s of CPU work on {cores} threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16 operands, fp32 accumulate (tcgen05 kind::f16); fp32 everywhere else",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": N_RAYS,
+                       "parallelism": f"rays sharded x{world}" + (", all_gather(feature_fine)" if world > 1 else ""),
+                       "l2": "256 MiB buffer written between timed steps (outside the event pairs)",
+                       "timing": "CUDA events per step on the launch stream, summed, max over ranks"},
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": N_RAYS * 8 * 4, "d2h_bytes_per_step": N_RAYS * 65 * 4,
+                    "timing": "wall clock, pinned host rays -> H2D -> render -> D2H feature+depth, "
+                              "stream sync every step"},
+            "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu_base, "clocks": clocks,
+            "points_per_step": POINTS_PER_STEP,
+            "tflops_per_step_device": POINTS_PER_STEP * FLOP_PER_POINT / (dev_ms / args.steps * 1e-3) / 1e12,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 8:      # keep the CPU arm bounded: ~1.5-3 s per step
+            args.steps = 8
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

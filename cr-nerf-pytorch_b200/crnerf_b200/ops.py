@@ -1,0 +1,381 @@
+"""Tensor-level wrappers over the C ABI.
+
+PyTorch is used for device memory and streams only: every function validates
+its tensors, allocates outputs with ``torch.empty`` on the input's device and
+enqueues the library's kernels on ``torch.cuda.current_stream()``.  CPU tensors
+are rejected - there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import CrnerfError, check
+
+OPERAND_FP16 = 0
+OPERAND_BF16 = 1
+_OPERANDS = {"fp16": 0, "bf16": 1, 0: 0, 1: 1}
+
+# order of the 12 NeRF_sigma layers in crnerf_mlp_weights (reference state_dict prefixes)
+MLP_LAYER_KEYS = tuple([f"xyz_encoding_{i}.0" for i in range(1, 9)] +
+                       ["xyz_encoding_final", "dir_encoding.0", "static_rgb.0", "static_sigma.0"])
+
+
+def operand_id(op) -> int:
+    try:
+        return _OPERANDS[op]
+    except KeyError:
+        raise ValueError(f"unknown operand format {op!r} (use 'fp16' or 'bf16')") from None
+
+
+def _need(t: torch.Tensor, name: str, dims: Optional[int] = None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a tensor")
+    if not t.is_cuda:
+        raise CrnerfError(f"{name} is on {t.device}: crnerf_b200 runs on CUDA (sm_100) only and has "
+                          "no CPU fallback")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if dims is not None and t.dim() != dims:
+        raise ValueError(f"{name} must have {dims} dims, got shape {tuple(t.shape)}")
+    return t
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count() -> int:
+    return int(_lib.load().crnerf_launch_count())
+
+
+def device_ok() -> bool:
+    return bool(_lib.load().crnerf_device_ok())
+
+
+# --------------------------------------------------------------------------
+class PackedMLP:
+    """Tensor-core-ready image of one NeRF_sigma's weights (see csrc/nerf_layout.h)."""
+
+    def __init__(self, buf: torch.Tensor, operand: int, e_xyz: int, e_dir: int):
+        self.buf, self.operand, self.e_xyz, self.e_dir = buf, operand, e_xyz, e_dir
+
+    @property
+    def device(self):
+        return self.buf.device
+
+
+def pack_mlp(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], e_xyz: int,
+             e_dir: int, operand="fp16", check_range: bool = True) -> PackedMLP:
+    """weights/biases: the 12 nn.Linear tensors in ``MLP_LAYER_KEYS`` order."""
+    lib = _lib.load()
+    op = operand_id(operand)
+    if len(weights) != 12 or len(biases) != 12:
+        raise ValueError("expected 12 weight and 12 bias tensors")
+    dev = weights[0].device
+    keep = []
+    w = _lib.MlpWeights()
+    in_f = [e_xyz] + [256] * 3 + [e_xyz + 256] + [256] * 3 + [256, 256 + e_dir, 128, 256]
+    out_f = [256] * 9 + [128, 64, 1]
+    for i in range(12):
+        wi = _c(_need(weights[i].detach(), f"weight[{i}]", 2))
+        bi = _c(_need(biases[i].detach(), f"bias[{i}]", 1))
+        if tuple(wi.shape) != (out_f[i], in_f[i]) or tuple(bi.shape) != (out_f[i],):
+            raise ValueError(
+                f"layer {MLP_LAYER_KEYS[i]}: got weight {tuple(wi.shape)} bias {tuple(bi.shape)}, the "
+                f"fused kernel is specialised for D=8, W=256, skips=[4], out_dim=64 and expects "
+                f"({out_f[i]}, {in_f[i]})")
+        if wi.device != dev or bi.device != dev:
+            raise ValueError("all weights must live on one device")
+        keep += [wi, bi]
+        w.weight[i] = wi.data_ptr()
+        w.bias[i] = bi.data_ptr()
+    w.e_xyz, w.e_dir = e_xyz, e_dir
+    nbytes = lib.crnerf_mlp_packed_bytes(e_xyz, e_dir)
+    with torch.cuda.device(dev):
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev) if check_range else None
+        check(lib.crnerf_mlp_pack(C.byref(w), op, buf.data_ptr(), nbytes, _p(status), _stream(dev)))
+        if check_range and int(status.item()) != 0:
+            raise CrnerfError("a NeRF weight exceeds the fp16 finite range (|w| > 65504); "
+                              "pack with operand='bf16'")
+    del keep
+    return PackedMLP(buf, op, e_xyz, e_dir)
+
+
+def render_pass(packed: PackedMLP, rays: torch.Tensor, z_vals: torch.Tensor,
+                noise: Optional[torch.Tensor] = None, view_dir: Optional[torch.Tensor] = None,
+                n_freq_xyz: int = 15, n_freq_dir: int = 4):
+    """One fused pass: embed -> MLP -> composite.  Returns (weights, feature, depth)."""
+    lib = _lib.load()
+    rays = _c(_need(rays, "rays", 2))
+    z_vals = _c(_need(z_vals, "z_vals", 2))
+    n, s = z_vals.shape
+    if rays.shape != (n, 8):
+        raise ValueError(f"rays must be ({n}, 8), got {tuple(rays.shape)}")
+    if 3 + 6 * n_freq_xyz != packed.e_xyz or 3 + 6 * n_freq_dir != packed.e_dir:
+        raise ValueError("weights were packed for a different embedding width")
+    if noise is not None:
+        noise = _c(_need(noise, "noise", 2))
+        if noise.shape != (n, s):
+            raise ValueError("noise must match z_vals")
+    if view_dir is not None:
+        view_dir = _c(_need(view_dir, "view_dir", 2))
+        if view_dir.shape != (n, 3):
+            raise ValueError("view_dir must be (n_rays, 3)")
+    dev = rays.device
+    with torch.cuda.device(dev):
+        weights = torch.empty((n, s), dtype=torch.float32, device=dev)
+        feature = torch.empty((n, 64), dtype=torch.float32, device=dev)
+        depth = torch.empty((n,), dtype=torch.float32, device=dev)
+        if n == 0:
+            return weights, feature, depth
+        check(lib.crnerf_render_pass(packed.buf.data_ptr(), packed.operand, rays.data_ptr(),
+                                     _p(view_dir), z_vals.data_ptr(), _p(noise), n, s, n_freq_xyz,
+                                     n_freq_dir, weights.data_ptr(), feature.data_ptr(),
+                                     depth.data_ptr(), _stream(dev)))
+    return weights, feature, depth
+
+
+def mlp_forward(packed: PackedMLP, x: torch.Tensor, sigma_only: bool = False) -> torch.Tensor:
+    """NeRF_sigma.forward on embedded rows: (B, e_xyz+e_dir) -> (B, 65) (or (B,1))."""
+    lib = _lib.load()
+    x = _c(_need(x, "x", 2))
+    need = packed.e_xyz if sigma_only else packed.e_xyz + packed.e_dir
+    if x.shape[1] != need:
+        raise ValueError(f"x must have {need} columns, got {x.shape[1]}")
+    dev = x.device
+    with torch.cuda.device(dev):
+        out = torch.empty((x.shape[0], 1 if sigma_only else 65), dtype=torch.float32, device=dev)
+        if x.shape[0] == 0:
+            return out
+        check(lib.crnerf_mlp_forward(packed.buf.data_ptr(), packed.operand, packed.e_xyz,
+                                     packed.e_dir, x.data_ptr(), x.shape[0], x.shape[1],
+                                     int(sigma_only), out.data_ptr(), _stream(dev)))
+    return out
+
+
+def pos_embed(x: torch.Tensor, n_freqs: int) -> torch.Tensor:
+    lib = _lib.load()
+    x = _c(_need(x, "x", 2))
+    if x.shape[1] != 3:
+        raise ValueError("PosEmbedding input must be (B, 3)")
+    dev = x.device
+    with torch.cuda.device(dev):
+        out = torch.empty((x.shape[0], 3 + 6 * n_freqs), dtype=torch.float32, device=dev)
+        if x.shape[0] == 0:
+            return out
+        check(lib.crnerf_pos_embed(x.data_ptr(), x.shape[0], n_freqs, out.data_ptr(), _stream(dev)))
+    return out
+
+
+def coarse_z(rays: torch.Tensor, t_steps: torch.Tensor, perturb_rand: Optional[torch.Tensor] = None,
+             use_disp: bool = False) -> torch.Tensor:
+    lib = _lib.load()
+    rays = _c(_need(rays, "rays", 2))
+    t_steps = _c(_need(t_steps, "t_steps", 1))
+    n, s = rays.shape[0], t_steps.shape[0]
+    if perturb_rand is not None:
+        perturb_rand = _c(_need(perturb_rand, "perturb_rand", 2))
+        if perturb_rand.shape != (n, s):
+            raise ValueError("perturb_rand must be (n_rays, n_samples)")
+    dev = rays.device
+    with torch.cuda.device(dev):
+        z = torch.empty((n, s), dtype=torch.float32, device=dev)
+        if n == 0:
+            return z
+        check(lib.crnerf_coarse_z(rays.data_ptr(), t_steps.data_ptr(), _p(perturb_rand), n, s,
+                                  int(use_disp), z.data_ptr(), _stream(dev)))
+    return z
+
+
+def _u_args(u: torch.Tensor, n: int, n_imp: int):
+    u = _c(_need(u, "u"))
+    if u.dim() == 1 and u.shape[0] == n_imp:
+        return u, 0
+    if u.dim() == 2 and u.shape == (n, n_imp):
+        return u, n_imp
+    raise ValueError(f"u must be ({n_imp},) or ({n}, {n_imp}), got {tuple(u.shape)}")
+
+
+def sample_pdf_merge(z_coarse: torch.Tensor, weights_coarse: torch.Tensor, u: torch.Tensor,
+                     n_importance: int, eps: float = 1e-5, return_new: bool = False):
+    """z_fine = sort(cat(z_coarse, sample_pdf(mid(z_coarse), weights_coarse[:,1:-1], u)))."""
+    lib = _lib.load()
+    z_coarse = _c(_need(z_coarse, "z_coarse", 2))
+    weights_coarse = _c(_need(weights_coarse.detach(), "weights_coarse", 2))
+    n, s = z_coarse.shape
+    if weights_coarse.shape != (n, s):
+        raise ValueError("weights_coarse must match z_coarse")
+    u, u_stride = _u_args(u, n, n_importance)
+    dev = z_coarse.device
+    with torch.cuda.device(dev):
+        z_fine = torch.empty((n, s + n_importance), dtype=torch.float32, device=dev)
+        z_new = torch.empty((n, n_importance), dtype=torch.float32, device=dev) if return_new else None
+        if n == 0:
+            return (z_fine, z_new) if return_new else z_fine
+        check(lib.crnerf_sample_pdf_merge(z_coarse.data_ptr(), weights_coarse.data_ptr(),
+                                          u.data_ptr(), u_stride, n, s, n_importance, eps,
+                                          z_fine.data_ptr(), _p(z_new), _stream(dev)))
+    return (z_fine, z_new) if return_new else z_fine
+
+
+def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, u: torch.Tensor, n_importance: int,
+               eps: float = 1e-5) -> torch.Tensor:
+    lib = _lib.load()
+    bins = _c(_need(bins, "bins", 2))
+    weights = _c(_need(weights.detach(), "weights", 2))
+    n, m = weights.shape
+    if bins.shape != (n, m + 1):
+        raise ValueError("bins must be (n_rays, n_bins+1)")
+    u, u_stride = _u_args(u, n, n_importance)
+    dev = bins.device
+    with torch.cuda.device(dev):
+        out = torch.empty((n, n_importance), dtype=torch.float32, device=dev)
+        if n == 0:
+            return out
+        check(lib.crnerf_sample_pdf(bins.data_ptr(), weights.data_ptr(), u.data_ptr(), u_stride, n,
+                                    m, n_importance, eps, out.data_ptr(), _stream(dev)))
+    return out
+
+
+# --------------------------------------------------------------------------
+class StyleWeightsRef:
+    """Pointers to (a subset of) a style_net's parameters, kept alive by the
+    tensors it holds.  ``params`` maps the reference's state_dict keys
+    (``multi_net.cnet.convs.0.weight`` ... ``decoder.feat_2_rgb_list.0.bias``) to
+    tensors; groups that are absent stay NULL (e.g. a bare NeuralRenderer only
+    has the decoder keys, a bare MulLayer has no decoder)."""
+
+    _SHAPES = {"convs.0.weight": (128, 64, 1, 1), "convs.0.bias": (128,),
+               "convs.2.weight": (64, 128, 1, 1), "convs.2.bias": (64,),
+               "convs.4.weight": (32, 64, 1, 1), "convs.4.bias": (32,),
+               "fc.weight": (1024, 1024), "fc.bias": (1024,)}
+    _TOP = {"multi_net.compress.weight": (32, 64, 1, 1), "multi_net.compress.bias": (32,),
+            "multi_net.unzip.weight": (64, 32, 1, 1), "multi_net.unzip.bias": (64,),
+            "decoder.feat_2_rgb_list.0.weight": (3, 64, 1, 1),
+            "decoder.feat_2_rgb_list.0.bias": (3,)}
+
+    def __init__(self, params: dict):
+        self.tensors = {}
+        self.device = None
+        s = _lib.StyleWeights()
+
+        def g(key, shape):
+            t = params.get(key)
+            if t is None:
+                return None
+            t = _c(_need(t.detach(), key))
+            if tuple(t.shape) != shape:
+                raise ValueError(f"{key}: expected {shape}, got {tuple(t.shape)} "
+                                 "(the cross-ray kernels need nerf_out_dim == 64, matrixSize == 32)")
+            if self.device is None:
+                self.device = t.device
+            elif t.device != self.device:
+                raise ValueError("style_net parameters must live on one device")
+            self.tensors[key] = t
+            return t.data_ptr()
+
+        for name, cw in (("cnet", s.cnet), ("snet", s.snet)):
+            pre = f"multi_net.{name}."
+            for i, j in enumerate((0, 2, 4)):
+                cw.conv_w[i] = g(f"{pre}convs.{j}.weight", self._SHAPES[f"convs.{j}.weight"])
+                cw.conv_b[i] = g(f"{pre}convs.{j}.bias", self._SHAPES[f"convs.{j}.bias"])
+            cw.fc_w = g(f"{pre}fc.weight", self._SHAPES["fc.weight"])
+            cw.fc_b = g(f"{pre}fc.bias", self._SHAPES["fc.bias"])
+        s.compress_w = g("multi_net.compress.weight", self._TOP["multi_net.compress.weight"])
+        s.compress_b = g("multi_net.compress.bias", self._TOP["multi_net.compress.bias"])
+        s.unzip_w = g("multi_net.unzip.weight", self._TOP["multi_net.unzip.weight"])
+        s.unzip_b = g("multi_net.unzip.bias", self._TOP["multi_net.unzip.bias"])
+        s.rgb_w = g("decoder.feat_2_rgb_list.0.weight", self._TOP["decoder.feat_2_rgb_list.0.weight"])
+        s.rgb_b = g("decoder.feat_2_rgb_list.0.bias", self._TOP["decoder.feat_2_rgb_list.0.bias"])
+        self.has_fusion = all(k in self.tensors for k in
+                              ["multi_net.cnet.fc.weight", "multi_net.snet.fc.weight",
+                               "multi_net.compress.weight", "multi_net.unzip.weight"])
+        self.has_decoder = "decoder.feat_2_rgb_list.0.weight" in self.tensors
+        self.struct = s
+
+    @staticmethod
+    def version_key(params: dict):
+        return tuple((k, t.data_ptr(), t._version) for k, t in sorted(params.items()))
+
+
+def _feat_strides(t: torch.Tensor, name: str):
+    """(1,64,H,W) feature map (any strides that keep H*W flat) -> (n_pixels, pix_stride, ch_stride).
+
+    Accepts both a contiguous NCHW tensor and the transposed view the reference's
+    callers build from the renderer's (N,64) rows (train_mask_grid_sample.py:133-134,
+    eval.py:291-292), which is read in place."""
+    _need(t, name, 4)
+    if t.shape[0] != 1 or t.shape[1] != 64:
+        raise ValueError(f"{name} must be (1, 64, H, W), got {tuple(t.shape)}")
+    _, _, h, w = t.shape
+    sb, sc, sh, sw = t.stride()
+    if h * w > 0 and (h == 1 or sh == sw * w):
+        return t, h * w, sw, sc
+    t = t.contiguous()
+    return t, h * w, 1, h * w
+
+
+def style_forward(sw: StyleWeightsRef, content: torch.Tensor, style: Optional[torch.Tensor],
+                  want_trans: bool = False, want_fused: bool = False):
+    """style_net.forward: content (1,64,H,W), style (1,64,h,w) or None -> rgb (1,3,H,W)."""
+    lib = _lib.load()
+    content, n, cps, ccs = _feat_strides(content, "content")
+    h, w = content.shape[2], content.shape[3]
+    dev = content.device
+    if dev != sw.device:
+        raise ValueError("content and style_net parameters are on different devices")
+    if not sw.has_decoder or (style is not None and not sw.has_fusion):
+        raise ValueError("style weights are missing the parameters this call needs")
+    ns = sps = scs = 0
+    if style is not None:
+        style, ns, sps, scs = _feat_strides(style, "style")
+        if style.device != dev:
+            raise ValueError("content and style are on different devices")
+    with torch.cuda.device(dev):
+        rgb = torch.empty((1, 3, h, w), dtype=torch.float32, device=dev)
+        trans = torch.empty((1, 32, 32), dtype=torch.float32, device=dev) if want_trans else None
+        fused = torch.empty((1, 64, h, w), dtype=torch.float32, device=dev) if want_fused else None
+        scratch = torch.empty(lib.crnerf_style_scratch_floats(n), dtype=torch.float32, device=dev)
+        check(lib.crnerf_style_forward(C.byref(sw.struct), content.data_ptr(), n, cps, ccs,
+                                       _p(style), ns, sps, scs, rgb.data_ptr(), _p(trans),
+                                       _p(fused), scratch.data_ptr(), _stream(dev)))
+    out = [rgb]
+    if want_trans:
+        out.append(trans)
+    if want_fused:
+        out.append(fused)
+    return out[0] if len(out) == 1 else tuple(out)
+
+
+def cnn_forward(sw: StyleWeightsRef, which: str, x: torch.Tensor) -> torch.Tensor:
+    """CNN.forward (linearStyleTransfer.py:28-37): (1,64,H,W) -> (1,1024)."""
+    lib = _lib.load()
+    x, n, ps, cs = _feat_strides(x, "x")
+    dev = x.device
+    cw = sw.struct.cnet if which == "cnet" else sw.struct.snet
+    if not cw.fc_w:
+        raise ValueError("CNN weights missing")
+    with torch.cuda.device(dev):
+        out = torch.empty((1, 1024), dtype=torch.float32, device=dev)
+        scratch = torch.empty(lib.crnerf_style_scratch_floats(n), dtype=torch.float32, device=dev)
+        check(lib.crnerf_cnn_forward(C.byref(cw), x.data_ptr(), n, ps, cs, out.data_ptr(),
+                                     scratch.data_ptr(), _stream(dev)))
+    return out
+
+
+def debug_set(buf: Optional[torch.Tensor], layer: int = -1):
+    """Tests only: dump post-activation values of `layer` for every point into buf (P,256)."""
+    check(_lib.load().crnerf_debug_set(_p(buf), layer))

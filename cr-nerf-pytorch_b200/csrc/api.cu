@@ -1,0 +1,258 @@
+// extern "C" surface of libcrnerf_b200.so (declared in include/crnerf_b200.h).
+// Argument validation lives here; kernels live in nerf_mlp.cu / sample.cu /
+// crossray.cu.  No torch types, no allocation, no host synchronisation.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include "common.h"
+
+namespace crnerf {
+
+static thread_local char t_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+float* g_dbg_buf = nullptr;
+int g_dbg_layer = -1;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error '%s' in %s", cudaGetErrorString(e), what);
+  return CRNERF_ERR_DEVICE;
+}
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static std::mutex mu;
+  static int cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cache[dev] = v;
+  }
+  return cache[dev];
+}
+
+static int device_check() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+  if (major != 10) {
+    set_error("crnerf_b200 kernels are built for sm_100a only; device %d has compute capability %d.x "
+              "(there is no fallback path)", dev, major);
+    return CRNERF_ERR_DEVICE;
+  }
+  return CRNERF_OK;
+}
+
+// implemented in sample.cu / crossray.cu
+int pos_embed(const float* x, int64_t n, int n_freqs, float* out, cudaStream_t st);
+int coarse_z(const float* rays, const float* t_steps, const float* perturb_rand, int n_rays,
+             int n_samples, int use_disp, float* z, cudaStream_t st);
+int sample_pdf(const float* bins_or_z, const float* weights, const float* u, int64_t u_stride,
+               int n_rays, int m, int n_imp, float eps, float* samples, float* sorted, bool merge,
+               cudaStream_t st);
+size_t style_scratch_floats(int64_t);
+int style_stats1(const float* content, int64_t n, int64_t ps, int64_t cs, float* sums,
+                 float* partial, cudaStream_t st);
+int style_stats2(const crnerf_cnn_weights& cw, const float* content, int64_t n, int64_t ps,
+                 int64_t cs, const float* mean, float* gram, float* partial, float scale,
+                 cudaStream_t st);
+int style_finish(const crnerf_style_weights* w, const float* content, int64_t n, int64_t ps,
+                 int64_t cs, const float* mean_c, const float* gram_c_normalised,
+                 const float* style, int64_t ns, int64_t sps, int64_t scs, float* rgb,
+                 float* transmatrix, float* fused, float* scratch, cudaStream_t st);
+int style_forward(const crnerf_style_weights* w, const float* content, int64_t n, int64_t ps,
+                  int64_t cs, const float* style, int64_t ns, int64_t sps, int64_t scs, float* rgb,
+                  float* transmatrix, float* fused, float* scratch, cudaStream_t st);
+int cnn_forward(const crnerf_cnn_weights* cw, const float* x, int64_t n, int64_t ps, int64_t cs,
+                float* out, float* scratch, cudaStream_t st);
+
+}  // namespace crnerf
+
+using namespace crnerf;
+
+extern "C" {
+
+const char* crnerf_last_error(void) { return t_err; }
+int crnerf_abi_version(void) { return CRNERF_ABI_VERSION; }
+int crnerf_device_ok(void) { return device_check() == CRNERF_OK ? 1 : 0; }
+uint64_t crnerf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int crnerf_debug_set(float* dbg_buf, int layer) {
+  g_dbg_buf = dbg_buf;
+  g_dbg_layer = layer;
+  return CRNERF_OK;
+}
+
+int crnerf_debug_program(int e_xyz, int e_dir, int32_t* out_host, int cap) {
+  return debug_program(e_xyz, e_dir, out_host, cap);
+}
+
+size_t crnerf_mlp_packed_bytes(int e_xyz, int e_dir) { return mlp_packed_bytes(e_xyz, e_dir); }
+
+int crnerf_mlp_pack(const crnerf_mlp_weights* w, int operand, void* packed, size_t packed_bytes,
+                    int32_t* status_dev, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return mlp_pack(w, operand, packed, packed_bytes, status_dev, (cudaStream_t)stream);
+}
+
+int crnerf_render_pass(const void* packed, int operand, const float* rays, const float* view_dir,
+                       const float* z_vals, const float* noise, int n_rays, int n_samples,
+                       int n_freq_xyz, int n_freq_dir, float* weights, float* feature,
+                       float* depth, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  CRNERF_REQUIRE(packed && rays && z_vals && weights && feature && depth, "null argument");
+  CRNERF_REQUIRE(operand == 0 || operand == 1, "operand must be 0 (fp16) or 1 (bf16)");
+  CRNERF_REQUIRE(n_rays >= 0, "n_rays must be non-negative");
+  CRNERF_REQUIRE(n_samples >= 16 && n_samples <= 4096,
+                 "n_samples=%d unsupported (16 <= n_samples <= 4096)", n_samples);
+  CRNERF_REQUIRE(n_freq_xyz >= 0 && n_freq_xyz <= 15 && n_freq_dir >= 0 && n_freq_dir <= 4,
+                 "positional-encoding bands out of range (xyz <= 15, dir <= 4)");
+  CRNERF_REQUIRE((reinterpret_cast<uintptr_t>(rays) & 15) == 0, "rays must be 16-byte aligned");
+  if (n_rays == 0) return CRNERF_OK;
+  RenderArgs a{};
+  a.packed = packed;
+  a.operand = operand;
+  a.e_xyz = 3 + 6 * n_freq_xyz;
+  a.e_dir = 3 + 6 * n_freq_dir;
+  a.rays = rays;
+  a.view_dir = view_dir;
+  a.z_vals = z_vals;
+  a.noise = noise;
+  a.n_points = (int64_t)n_rays * n_samples;
+  a.n_rays = n_rays;
+  a.n_samples = n_samples;
+  a.n_freq_xyz = n_freq_xyz;
+  a.n_freq_dir = n_freq_dir;
+  a.weights = weights;
+  a.feature = feature;
+  a.depth = depth;
+  return launch_render(a, (cudaStream_t)stream);
+}
+
+int crnerf_mlp_forward(const void* packed, int operand, int e_xyz, int e_dir, const float* x,
+                       int64_t n, int x_stride, int sigma_only, float* out, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  CRNERF_REQUIRE(packed && x && out, "null argument");
+  CRNERF_REQUIRE(operand == 0 || operand == 1, "operand must be 0 (fp16) or 1 (bf16)");
+  CRNERF_REQUIRE(n >= 0, "n must be non-negative");
+  CRNERF_REQUIRE(x_stride >= (sigma_only ? e_xyz : e_xyz + e_dir), "x_stride smaller than the row width");
+  if (n == 0) return CRNERF_OK;
+  RenderArgs a{};
+  a.packed = packed;
+  a.operand = operand;
+  a.e_xyz = e_xyz;
+  a.e_dir = e_dir;
+  a.x = x;
+  a.x_stride = x_stride;
+  a.sigma_only = sigma_only;
+  a.n_points = n;
+  a.n_samples = 1;
+  a.raw = out;
+  return launch_render(a, (cudaStream_t)stream);
+}
+
+int crnerf_pos_embed(const float* x, int64_t n, int n_freqs, float* out, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return pos_embed(x, n, n_freqs, out, (cudaStream_t)stream);
+}
+
+int crnerf_coarse_z(const float* rays, const float* t_steps, const float* perturb_rand, int n_rays,
+                    int n_samples, int use_disp, float* z_vals, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return coarse_z(rays, t_steps, perturb_rand, n_rays, n_samples, use_disp, z_vals,
+                  (cudaStream_t)stream);
+}
+
+int crnerf_sample_pdf_merge(const float* z_coarse, const float* weights_coarse, const float* u,
+                            int64_t u_stride, int n_rays, int n_samples, int n_importance,
+                            float eps, float* z_fine, float* z_new, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  CRNERF_REQUIRE(n_samples >= 3, "sample_pdf needs at least 3 coarse samples");
+  return sample_pdf(z_coarse, weights_coarse, u, u_stride, n_rays, n_samples - 2, n_importance, eps,
+                    z_new, z_fine, true, (cudaStream_t)stream);
+}
+
+int crnerf_sample_pdf(const float* bins, const float* weights, const float* u, int64_t u_stride,
+                      int n_rays, int m, int n_importance, float eps, float* samples,
+                      void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return sample_pdf(bins, weights, u, u_stride, n_rays, m, n_importance, eps, samples, nullptr,
+                    false, (cudaStream_t)stream);
+}
+
+size_t crnerf_style_scratch_floats(int64_t n_pixels) { return style_scratch_floats(n_pixels); }
+
+int crnerf_style_forward(const crnerf_style_weights* w, const float* content, int64_t n_pixels,
+                         int64_t c_pix_stride, int64_t c_ch_stride, const float* style,
+                         int64_t n_style_pixels, int64_t s_pix_stride, int64_t s_ch_stride,
+                         float* rgb, float* transmatrix, float* fused, float* scratch,
+                         void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return style_forward(w, content, n_pixels, c_pix_stride, c_ch_stride, style, n_style_pixels,
+                       s_pix_stride, s_ch_stride, rgb, transmatrix, fused, scratch,
+                       (cudaStream_t)stream);
+}
+
+int crnerf_cnn_forward(const crnerf_cnn_weights* w, const float* x, int64_t n_pixels,
+                       int64_t pix_stride, int64_t ch_stride, float* out, float* scratch,
+                       void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return cnn_forward(w, x, n_pixels, pix_stride, ch_stride, out, scratch, (cudaStream_t)stream);
+}
+
+int crnerf_style_stats1(const float* content, int64_t n_pixels, int64_t pix_stride,
+                        int64_t ch_stride, float* sums, float* scratch, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  CRNERF_REQUIRE(content && sums && scratch && n_pixels >= 1, "bad argument");
+  return style_stats1(content, n_pixels, pix_stride, ch_stride, sums, scratch, (cudaStream_t)stream);
+}
+
+int crnerf_style_stats2(const crnerf_style_weights* w, const float* content, int64_t n_pixels,
+                        int64_t pix_stride, int64_t ch_stride, const float* mean, float* gram,
+                        float* scratch, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  CRNERF_REQUIRE(w && content && mean && gram && scratch && n_pixels >= 1, "bad argument");
+  // partials go to the Gram-partial region of the scratch buffer (offset = kMaxBlocks*64 floats)
+  return style_stats2(w->cnet, content, n_pixels, pix_stride, ch_stride, mean, gram,
+                      scratch + 296 * 64, 1.f, (cudaStream_t)stream);
+}
+
+int crnerf_style_apply(const crnerf_style_weights* w, const float* content, int64_t n_pixels,
+                       int64_t pix_stride, int64_t ch_stride, const float* mean,
+                       const float* gram_normalised, const float* style, int64_t n_style_pixels,
+                       int64_t s_pix_stride, int64_t s_ch_stride, float* rgb, float* transmatrix,
+                       float* scratch, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  CRNERF_REQUIRE(w && content && mean && gram_normalised && style && rgb && scratch, "null argument");
+  return style_finish(w, content, n_pixels, pix_stride, ch_stride, mean, gram_normalised, style,
+                      n_style_pixels, s_pix_stride, s_ch_stride, rgb, transmatrix, nullptr, scratch,
+                      (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,18 @@
+#!/bin/bash
+# Builds libcrnerf_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU).
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/../crnerf_b200/libcrnerf_b200.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
+       -Xcompiler -fvisibility=hidden --use_fast_math=false)
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC)
+mkdir -p "$HERE/_obj"
+pids=()
+for f in api nerf_mlp sample crossray; do
+  "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" ${CRNERF_PTXAS_V:+-Xptxas -v} &
+  pids+=($!)
+done
+for p in "${pids[@]}"; do wait "$p"; done
+"$NVCC" -shared -o "$OUT" "$HERE"/_obj/{api,nerf_mlp,sample,crossray}.o -lcudart
+echo "built $OUT"

@@ -1,0 +1,58 @@
+// Internal helpers shared by the translation units of libcrnerf_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/crnerf_b200.h"
+
+namespace crnerf {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);  // records message, returns CRNERF_ERR_DEVICE
+void count_launch(int n = 1);
+int num_sms();  // SM count of the current device (cached per device)
+
+// debug hook (tests): per-layer activation dump of the fused kernel
+extern float* g_dbg_buf;
+extern int g_dbg_layer;
+
+// ---- internal entry points implemented in the kernel translation units ----
+struct RenderArgs {
+  const void* packed;
+  int operand;       // crnerf_operand
+  int e_xyz, e_dir;  // embedding widths the weights were packed for
+  const float* rays;
+  const float* view_dir;
+  const float* z_vals;
+  const float* noise;
+  const float* x;  // pre-embedded rows (mlp_forward) or nullptr
+  int x_stride;
+  int sigma_only;
+  int64_t n_points;  // rays * samples, or rows of x
+  int n_rays, n_samples;
+  int n_freq_xyz, n_freq_dir;
+  float* weights;
+  float* feature;
+  float* depth;
+  float* raw;  // (n,65) or (n,1) output of mlp_forward
+};
+int launch_render(const RenderArgs& a, cudaStream_t st);
+size_t mlp_packed_bytes(int e_xyz, int e_dir);
+int debug_program(int e_xyz, int e_dir, int32_t* out, int cap);
+int mlp_pack(const crnerf_mlp_weights* w, int operand, void* packed, size_t packed_bytes,
+             int32_t* status_dev, cudaStream_t st);
+
+}  // namespace crnerf
+
+#define CRNERF_CUDA(x)                                          \
+  do {                                                          \
+    cudaError_t e_ = (x);                                       \
+    if (e_ != cudaSuccess) return crnerf::cuda_fail(e_, #x);    \
+  } while (0)
+
+#define CRNERF_REQUIRE(cond, ...)        \
+  do {                                   \
+    if (!(cond)) {                       \
+      crnerf::set_error(__VA_ARGS__);    \
+      return CRNERF_ERR_ARG;             \
+    }                                    \
+  } while (0)

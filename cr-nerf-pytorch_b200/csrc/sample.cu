@@ -1,0 +1,236 @@
+// Depth sampling kernels: PosEmbedding, stratified coarse depths, and the
+// inverse-CDF importance sampler fused with the coarse/fine merge.
+//   pos_embed        <- PosEmbedding.forward        (reference models/nerf.py:17-30)
+//   coarse_z         <- render_rays_cross_ray       (reference models/rendering.py:161-176)
+//   sample_pdf(+sort)<- sample_pdf + cat + sort     (reference models/rendering.py:7-46, 183-187)
+// These are latency/HBM-bound (< 1% of the path); the design goals are one
+// launch each, coalesced row access, and the reference's rounding order
+// (explicit __f*_rn so nvcc does not contract mul+add into FMA).
+#include <math_constants.h>
+#include "common.h"
+
+namespace crnerf {
+namespace {
+
+// ---------------------------------------------------------------------------
+__global__ void pos_embed_kernel(const float* __restrict__ x, long long n, int n_freqs,
+                                 float* __restrict__ out) {
+  const int width = 3 + 6 * n_freqs;
+  const long long total = n * (n_freqs + 1);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / (n_freqs + 1);
+    const int k = (int)(i - row * (n_freqs + 1));  // 0: identity, k>=1: band k-1
+    const float* xr = x + row * 3;
+    float* o = out + row * width;
+    if (k == 0) {
+      o[0] = xr[0];
+      o[1] = xr[1];
+      o[2] = xr[2];
+    } else {
+      const float f = __int_as_float((127 + (k - 1)) << 23);  // 2^(k-1), exact
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float s, cs;
+        sincosf(__fmul_rn(f, xr[c]), &s, &cs);
+        o[3 + 6 * (k - 1) + c] = s;
+        o[6 + 6 * (k - 1) + c] = cs;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float z_at(float near, float far, float t, int use_disp) {
+  const float omt = __fsub_rn(1.f, t);
+  if (!use_disp) return __fadd_rn(__fmul_rn(near, omt), __fmul_rn(far, t));
+  const float a = __fmul_rn(__fdiv_rn(1.f, near), omt);
+  const float b = __fmul_rn(__fdiv_rn(1.f, far), t);
+  return __fdiv_rn(1.f, __fadd_rn(a, b));
+}
+
+__global__ void coarse_z_kernel(const float* __restrict__ rays, const float* __restrict__ t_steps,
+                                const float* __restrict__ perturb_rand, int n_rays, int S,
+                                int use_disp, float* __restrict__ z_out) {
+  const long long total = (long long)n_rays * S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ray = (int)(i / S);
+    const int s = (int)(i - (long long)ray * S);
+    const float near = __ldg(rays + (long long)ray * 8 + 6), far = __ldg(rays + (long long)ray * 8 + 7);
+    const float z = z_at(near, far, __ldg(t_steps + s), use_disp);
+    if (!perturb_rand) {
+      z_out[i] = z;
+      continue;
+    }
+    // stratified jitter: lower + (upper - lower) * rand  (rendering.py:169-176)
+    const float zp = s > 0 ? z_at(near, far, __ldg(t_steps + s - 1), use_disp) : z;
+    const float zn = s + 1 < S ? z_at(near, far, __ldg(t_steps + s + 1), use_disp) : z;
+    const float lower = s > 0 ? __fmul_rn(0.5f, __fadd_rn(zp, z)) : z;
+    const float upper = s + 1 < S ? __fmul_rn(0.5f, __fadd_rn(z, zn)) : z;
+    z_out[i] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), __ldg(perturb_rand + i)));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// One warp per ray.  Shared memory per warp: cdf[m+1] | sort buffer[pow2(n_coarse+n_imp)].
+// kMerge: bins are the midpoints of z (n_coarse = m+2 depths), weights =
+// weights_coarse[:, 1:-1]; output is sort(cat(z, samples)).
+template <bool kMerge>
+__global__ void __launch_bounds__(128)
+sample_pdf_kernel(const float* __restrict__ bins_or_z, const float* __restrict__ weights,
+                  const float* __restrict__ u, long long u_stride, int n_rays, int m,
+                  int n_imp, float eps, float* __restrict__ samples_out,
+                  float* __restrict__ sorted_out, int cdf_pad, int sort_pad) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ray = blockIdx.x * 4 + warp;
+  if (ray >= n_rays) return;
+  float* cdf = sm + warp * (cdf_pad + sort_pad);
+  float* buf = cdf + cdf_pad;
+  const int n_coarse = m + 2;
+  const float* wrow = kMerge ? weights + (long long)ray * n_coarse + 1 : weights + (long long)ray * m;
+  const float* brow = kMerge ? bins_or_z + (long long)ray * n_coarse : bins_or_z + (long long)ray * (m + 1);
+
+  // pdf normaliser.  torch sums/accumulates in higher precision on the CPU
+  // (cumsum uses a double accumulator); doing the same here keeps the cdf
+  // order-independent to the last bit in nearly every case.
+  double part = 0.0;
+  for (int j = lane; j < m; j += 32) part += (double)__fadd_rn(wrow[j], eps);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+  const float total = (float)part;
+
+  // cdf[0] = 0, cdf[j+1] = sum_{i<=j} pdf_i  (warp scan over 32-wide blocks)
+  double carry = 0.0;
+  if (lane == 0) cdf[0] = 0.f;
+  for (int base = 0; base < m; base += 32) {
+    const int j = base + lane;
+    double v = j < m ? (double)__fdiv_rn(__fadd_rn(wrow[j], eps), total) : 0.0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double o = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += o;
+    }
+    v += carry;
+    if (j < m) cdf[j + 1] = (float)v;
+    carry = __shfl_sync(0xffffffffu, v, 31);
+  }
+  __syncwarp();
+
+  for (int i = lane; i < n_imp; i += 32) {
+    const float ui = __ldg(u + (long long)ray * u_stride + i);
+    // searchsorted(cdf, u, right=True): first index with cdf[idx] > u, over m+1 entries
+    int lo = 0, hi = m + 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= ui) lo = mid + 1; else hi = mid;
+    }
+    const int below = max(lo - 1, 0), above = min(lo, m);
+    const float c0 = cdf[below], c1 = cdf[above];
+    float b0, b1;
+    if (kMerge) {
+      b0 = __fmul_rn(0.5f, __fadd_rn(brow[below], brow[below + 1]));
+      b1 = __fmul_rn(0.5f, __fadd_rn(brow[above], brow[above + 1]));
+    } else {
+      b0 = brow[below];
+      b1 = brow[above];
+    }
+    float denom = __fsub_rn(c1, c0);
+    if (denom < eps) denom = 1.f;
+    const float smp =
+        __fadd_rn(b0, __fmul_rn(__fdiv_rn(__fsub_rn(ui, c0), denom), __fsub_rn(b1, b0)));
+    if (samples_out) samples_out[(long long)ray * n_imp + i] = smp;
+    if (kMerge) buf[n_coarse + i] = smp;
+  }
+  if (!kMerge) return;
+
+  const int n_tot = n_coarse + n_imp;
+  for (int i = lane; i < n_coarse; i += 32) buf[i] = brow[i];
+  for (int i = n_tot + lane; i < sort_pad; i += 32) buf[i] = CUDART_INF_F;
+  __syncwarp();
+  // bitonic sort of sort_pad (power of two) values held in shared memory
+  for (int k = 2; k <= sort_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < sort_pad; i += 32) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const float a = buf[i], b = buf[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            buf[i] = b;
+            buf[ixj] = a;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < n_tot; i += 32) sorted_out[(long long)ray * n_tot + i] = buf[i];
+}
+
+int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)num_sms() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+int pos_embed(const float* x, int64_t n, int n_freqs, float* out, cudaStream_t st) {
+  CRNERF_REQUIRE(x && out, "null argument");
+  CRNERF_REQUIRE(n_freqs >= 0 && n_freqs <= 32, "n_freqs out of range");
+  if (n == 0) return CRNERF_OK;
+  pos_embed_kernel<<<grid_for(n * (n_freqs + 1), 256), 256, 0, st>>>(x, n, n_freqs, out);
+  count_launch();
+  CRNERF_CUDA(cudaGetLastError());
+  return CRNERF_OK;
+}
+
+int coarse_z(const float* rays, const float* t_steps, const float* perturb_rand, int n_rays,
+             int n_samples, int use_disp, float* z, cudaStream_t st) {
+  CRNERF_REQUIRE(rays && t_steps && z, "null argument");
+  CRNERF_REQUIRE(n_samples >= 1, "n_samples must be positive");
+  if (n_rays == 0) return CRNERF_OK;
+  coarse_z_kernel<<<grid_for((long long)n_rays * n_samples, 256), 256, 0, st>>>(
+      rays, t_steps, perturb_rand, n_rays, n_samples, use_disp, z);
+  count_launch();
+  CRNERF_CUDA(cudaGetLastError());
+  return CRNERF_OK;
+}
+
+int sample_pdf(const float* bins_or_z, const float* weights, const float* u, int64_t u_stride,
+               int n_rays, int m, int n_imp, float eps, float* samples, float* sorted, bool merge,
+               cudaStream_t st) {
+  CRNERF_REQUIRE(bins_or_z && weights && u, "null argument");
+  CRNERF_REQUIRE(m >= 1 && n_imp >= 1, "need at least one bin and one sample");
+  CRNERF_REQUIRE(!merge || sorted, "merge needs an output buffer");
+  CRNERF_REQUIRE(merge || samples, "samples output is null");
+  if (n_rays == 0) return CRNERF_OK;
+  const int cdf_pad = (m + 1 + 3) & ~3;
+  const int sort_pad = merge ? next_pow2(m + 2 + n_imp) : 0;
+  CRNERF_REQUIRE(sort_pad <= 4096 && cdf_pad <= 4096, "too many samples per ray (max 4096)");
+  const size_t smem = 4 * (size_t)(cdf_pad + sort_pad) * sizeof(float);
+  const int grid = (n_rays + 3) / 4;
+  if (merge) {
+    if (smem > 48 * 1024)
+      CRNERF_CUDA(cudaFuncSetAttribute(sample_pdf_kernel<true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sample_pdf_kernel<true><<<grid, 128, smem, st>>>(bins_or_z, weights, u, u_stride, n_rays, m,
+                                                     n_imp, eps, samples, sorted, cdf_pad, sort_pad);
+  } else {
+    sample_pdf_kernel<false><<<grid, 128, smem, st>>>(bins_or_z, weights, u, u_stride, n_rays, m,
+                                                      n_imp, eps, samples, sorted, cdf_pad, sort_pad);
+  }
+  count_launch();
+  CRNERF_CUDA(cudaGetLastError());
+  return CRNERF_OK;
+}
+
+}  // namespace crnerf

@@ -1,0 +1,171 @@
+"""``models.linearStyleTransfer`` of the reference, backed by sm_100a kernels.
+
+Hot-path classes (reference file:line): ``CNN`` (:6-37), ``MulLayer`` (:43-94) and
+``style_net`` (:278-291) hold the same parameters under the same names
+(``multi_net.{snet,cnet}.convs.{0,2,4}``, ``.fc``, ``multi_net.compress``,
+``multi_net.unzip``, ``decoder.feat_2_rgb_list.0``) and run the cross-ray fusion +
+decoder as three streaming passes over the feature map (csrc/crossray.cu)
+instead of ~40 library launches.  The feature map is read in place whether it is
+contiguous NCHW or the transposed view of the renderer's (N,64) rows that the
+reference's callers build.
+
+``encoder_sameoutputsize`` (:208-276, the style/content encoder ``enc_a``) sits
+outside the render path ("next"); it is provided as a plain module
+with the reference's parameter names so checkpoints load and callers run.
+"""
+import torch
+import torch.nn as nn
+
+from crnerf_b200 import ops
+from models.nerf_decoder_stylenerf import NeuralRenderer
+
+
+def _no_autograd(module, *tensors):
+    if torch.is_grad_enabled() and (any(t is not None and t.requires_grad for t in tensors) or
+                                    any(p.requires_grad for p in module.parameters())):
+        raise NotImplementedError(
+            "crnerf_b200 implements the inference path (torch.no_grad()); the fused backward is "
+            "not built yet - wrap the call in torch.no_grad() or freeze the parameters")
+
+
+class _StyleParamsMixin:
+    """Caches the C struct of parameter pointers; rebuilt when a parameter moves or changes."""
+
+    def _style_ref(self, prefix_map):
+        params = {}
+        for name, p in self.named_parameters():
+            for src, dst in prefix_map:
+                if name.startswith(src):
+                    params[dst + name[len(src):]] = p
+                    break
+        key = ops.StyleWeightsRef.version_key(params)
+        if getattr(self, '_sw_key', None) != key:
+            self._sw = ops.StyleWeightsRef(params)
+            self._sw_key = key
+        return self._sw
+
+
+class CNN(nn.Module, _StyleParamsMixin):
+    def __init__(self, matrixSize=32, in_channel=64):
+        """Three 1x1 convs + Gram + fc, reference linearStyleTransfer.py:7-25."""
+        super(CNN, self).__init__()
+        self.convs = nn.Sequential(nn.Conv2d(in_channel, 128, 1, 1, 0),
+                                   nn.LeakyReLU(0.2, inplace=True),
+                                   nn.Conv2d(128, 64, 1, 1, 0),
+                                   nn.LeakyReLU(0.2, inplace=True),
+                                   nn.Conv2d(64, matrixSize, 1, 1, 0))
+        self.fc = nn.Linear(matrixSize * matrixSize, matrixSize * matrixSize)
+
+    def forward(self, x):
+        """(1,64,H,W) -> (1,1024), reference linearStyleTransfer.py:28-37."""
+        _no_autograd(self, x)
+        return ops.cnn_forward(self._style_ref([("", "multi_net.cnet.")]), "cnet", x)
+
+
+class MulLayer(nn.Module, _StyleParamsMixin):
+    def __init__(self, matrixSize=32, in_channel=64):
+        """Reference linearStyleTransfer.py:44-56 (snet/cnet use the default in_channel=64)."""
+        super(MulLayer, self).__init__()
+        self.snet = CNN(matrixSize)
+        self.cnet = CNN(matrixSize)
+        self.matrixSize = matrixSize
+        self.compress = nn.Conv2d(in_channel, matrixSize, 1, 1, 0)
+        self.unzip = nn.Conv2d(matrixSize, in_channel, 1, 1, 0)
+        self.transmatrix = None
+
+    def forward(self, cF, sF, trans=True):
+        """content (1,64,H,W), style (1,64,h,w) -> (fused (1,64,H,W), transmatrix (1,32,32)),
+        reference linearStyleTransfer.py:58-90."""
+        if not trans:
+            # the reference's trans=False branch returns None (bare `return`, :91-93)
+            return None
+        _no_autograd(self, cF, sF)
+        sw = self._style_ref([("", "multi_net.")])
+        if not sw.has_decoder:
+            # stand-alone MulLayer: the kernel still needs a 64->3 head to write; use zeros
+            dev = cF.device
+            params = dict(sw.tensors)
+            params["decoder.feat_2_rgb_list.0.weight"] = torch.zeros(3, 64, 1, 1, device=dev)
+            params["decoder.feat_2_rgb_list.0.bias"] = torch.zeros(3, device=dev)
+            sw = ops.StyleWeightsRef(params)
+        _, trans_m, fused = ops.style_forward(sw, cF, sF, want_trans=True, want_fused=True)
+        return fused, trans_m
+
+
+class style_net(nn.Module, _StyleParamsMixin):
+    def __init__(self, args, residual_blocks=2):
+        """Reference linearStyleTransfer.py:279-283."""
+        super(style_net, self).__init__()
+        nerf_channel = args.nerf_out_dim
+        self.multi_net = MulLayer(in_channel=nerf_channel)
+        self.decoder = NeuralRenderer(img_size=(args.img_wh[0], args.img_wh[1]),
+                                      featmap_size=(args.img_wh[0], args.img_wh[1]),
+                                      feat_nc=args.nerf_out_dim, out_dim=3, args_here=args)
+
+    def forward(self, content_feature, style_feature, type=None):
+        """content (1,64,H,W), style (1,64,32,32) or None -> rgb (1,3,H,W),
+        reference linearStyleTransfer.py:284-291."""
+        _no_autograd(self, content_feature, style_feature)
+        sw = self._style_ref([("", "")])
+        if style_feature is None and type == "content":
+            return ops.style_forward(sw, content_feature, None)
+        return ops.style_forward(sw, content_feature, style_feature)
+
+
+class encoder_sameoutputsize(nn.Module):
+    """Style/content encoder ``enc_a`` / ``enc_cont`` (reference :208-276): six
+    reflection-padded 3x3 convs with LeakyReLU(0.2), two 2x2 max-pools, adaptive
+    average pool to 32x32 and a 1x1 conv.  Outside the render path (it runs once
+    per reference photo); kept as library ops - see DESIGN.md "out of scope"."""
+
+    def __init__(self, out_channel=64):
+        super(encoder_sameoutputsize, self).__init__()
+        self.conv1 = nn.Conv2d(3, 3, 1, 1, 0)
+        self.reflecPad1 = nn.ReflectionPad2d((1, 1, 1, 1))
+        self.conv2 = nn.Conv2d(3, 64, 3, 1, 0)
+        self.relu2 = nn.LeakyReLU(0.2, inplace=True)
+        self.reflecPad3 = nn.ReflectionPad2d((1, 1, 1, 1))
+        self.conv3 = nn.Conv2d(64, 64, 3, 1, 0)
+        self.relu3 = nn.LeakyReLU(0.2, inplace=True)
+        self.maxPool = nn.MaxPool2d(kernel_size=2, stride=2, return_indices=True)
+        self.reflecPad4 = nn.ReflectionPad2d((1, 1, 1, 1))
+        self.conv4 = nn.Conv2d(64, 128, 3, 1, 0)
+        self.relu4 = nn.LeakyReLU(0.2, inplace=True)
+        self.reflecPad5 = nn.ReflectionPad2d((1, 1, 1, 1))
+        self.conv5 = nn.Conv2d(128, 128, 3, 1, 0)
+        self.relu5 = nn.LeakyReLU(0.2, inplace=True)
+        self.maxPool2 = nn.MaxPool2d(kernel_size=2, stride=2, return_indices=True)
+        self.reflecPad6 = nn.ReflectionPad2d((1, 1, 1, 1))
+        self.conv6 = nn.Conv2d(128, 128, 3, 1, 0)
+        self.relu6 = nn.LeakyReLU(0.2, inplace=True)
+        self.adppool = nn.AdaptiveAvgPool2d(32)
+        self.conv7 = nn.Conv2d(128, out_channel, 1, 1, 0)
+        self.relu7 = nn.LeakyReLU(0.2, inplace=True)
+
+    def forward(self, x):
+        h = self.relu2(self.conv2(self.reflecPad1(self.conv1(x))))
+        h = self.relu3(self.conv3(self.reflecPad3(h)))
+        h, _ = self.maxPool(h)
+        h = self.relu4(self.conv4(self.reflecPad4(h)))
+        h = self.relu5(self.conv5(self.reflecPad5(h)))
+        h, _ = self.maxPool2(h)
+        h = self.relu6(self.conv6(self.reflecPad6(h)))
+        return self.relu7(self.conv7(self.adppool(h)))
+
+
+class _NotOnHotPath(nn.Module):
+    _why = ""
+
+    def __init__(self, *a, **k):
+        super().__init__()
+        raise NotImplementedError(self._why)
+
+
+class encoder3(_NotOnHotPath):
+    """Importable placeholder for reference linearStyleTransfer.py:97-150 (unused there)."""
+    _why = "models.linearStyleTransfer.encoder3 is imported but never instantiated by the reference"
+
+
+class decoder3(_NotOnHotPath):
+    """Importable placeholder for reference linearStyleTransfer.py:152-206 (unused there)."""
+    _why = "models.linearStyleTransfer.decoder3 is never instantiated by the reference"

@@ -1,0 +1,111 @@
+"""``models.rendering`` of the reference (models/rendering.py), backed by sm_100a kernels.
+
+``render_rays_cross_ray`` keeps the reference's positional signature
+(rendering.py:50-63) and result dictionary.  The per-chunk Python loop over
+``embedding -> cat -> model -> cat`` and the ~200 small launches of the
+reference collapse into, per call: one depth-sampling kernel, one fused
+embed+MLP+composite kernel per pass, and one inverse-CDF+sort kernel.
+
+Random numbers stay on the host side of the boundary: they are drawn with the
+same torch calls, in the same order and on the same device as the reference
+(rand_like(z) :175, randn_like(sigma) :125, rand(N,Ni) :30, randn_like :125) and
+handed to the kernels, so seeded CUDA runs consume the generator identically.
+"""
+import torch
+
+from crnerf_b200 import ops
+
+__all__ = ['render_rays_cross_ray']
+
+
+def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5):
+    """Inverse-CDF sampling, reference models/rendering.py:7-46.
+
+    bins (N_rays, N_samples_+1), weights (N_rays, N_samples_) -> (N_rays, N_importance).
+    """
+    N_rays = weights.shape[0]
+    if det:
+        u = torch.linspace(0, 1, N_importance, device=bins.device)
+    else:
+        u = torch.rand(N_rays, N_importance, device=bins.device)
+    return ops.sample_pdf(bins, weights, u, N_importance, eps)
+
+
+def _n_freqs(embedding):
+    n = getattr(embedding, 'N_freqs', None)
+    return int(n if n is not None else len(embedding.freqs))
+
+
+def render_rays_cross_ray(models,
+                          embeddings,
+                          rays,
+                          ts,
+                          N_samples=64,
+                          use_disp=False,
+                          perturb=0,
+                          noise_std=1,
+                          N_importance=0,
+                          chunk=1024 * 32,
+                          white_back=False,
+                          test_time=False,
+                          **kwargs):
+    """Render rays: coarse pass, importance resampling, fine pass.
+
+    Same contract as reference models/rendering.py:50-196.  ``ts``, ``chunk``,
+    ``white_back`` and ``test_time`` are accepted and unused, as in the reference
+    (point chunking is unnecessary because no per-point tensor is
+    materialised).  Returns ``weights_{typ} (N,S)``, ``feature_{typ} (N,64)``,
+    ``depth_{typ} (N,)`` for the coarse model and, if ``N_importance > 0``, the
+    fine model, plus the ``feature_fine_random`` alias (rendering.py:140-141).
+    """
+    args = kwargs['args']
+    if getattr(args, 'pertubeCord', False):
+        raise NotImplementedError("args.pertubeCord (xyz jitter, rendering.py:102-104) is off in every "
+                                  "reference command and has no kernel")
+    if not rays.is_cuda:
+        raise ops.CrnerfError(f"rays are on {rays.device}: crnerf_b200 renders on CUDA (sm_100) only "
+                              "and has no CPU fallback")
+    coarse = models['coarse']
+    coarse._no_autograd(rays)
+    n_fx, n_fd = _n_freqs(embeddings['xyz']), _n_freqs(embeddings['dir'])
+    rays = rays.contiguous().float()
+    N_rays = rays.shape[0]
+    view_dir = kwargs.get('view_dir', None)
+    dev = rays.device
+
+    # depths: z = near*(1-t)+far*t (+ stratified jitter), rendering.py:161-176
+    t_steps = torch.linspace(0, 1, N_samples, device=dev)
+    perturb_rand = None
+    if perturb > 0:
+        perturb_rand = perturb * torch.rand(N_rays, N_samples, device=dev)
+    z_vals = ops.coarse_z(rays, t_steps, perturb_rand, use_disp)
+
+    results = {}
+
+    def run(model, z):
+        # the reference always draws the noise tensor, even when noise_std == 0 (:125)
+        noise = torch.randn(z.shape, device=dev) * noise_std
+        w, f, d = ops.render_pass(model.packed(), rays, z, noise if noise_std != 0 else None,
+                                  view_dir, n_fx, n_fd)
+        typ = model.typ
+        results[f'weights_{typ}'] = w
+        results[f'feature_{typ}'] = f
+        results[f'depth_{typ}'] = d
+        return w, f
+
+    w_coarse, _ = run(coarse, z_vals)
+
+    if N_importance > 0:
+        fine = models['fine']
+        if perturb == 0:     # det: u = linspace(0,1,N_importance) shared by all rays (:26-28)
+            u = torch.linspace(0, 1, N_importance, device=dev)
+        else:                # :30
+            u = torch.rand(N_rays, N_importance, device=dev)
+        # sample_pdf on the coarse mid-points with weights_coarse[:,1:-1] (detached),
+        # then sort(cat(z, z_new)) - one kernel (rendering.py:183-187)
+        z_fine = ops.sample_pdf_merge(z_vals, w_coarse, u, N_importance)
+        _, f_fine = run(fine, z_fine)
+        if kwargs.get('output_random', True) and fine.encode_random:
+            results['feature_fine_random'] = f_fine   # same tensor object, as the reference
+
+    return results

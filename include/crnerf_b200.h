@@ -1,0 +1,212 @@
+/* crnerf_b200 - C ABI of the B200-native CR-NeRF volume-rendering path.
+ *
+ * Drop-in boundary for the hot path of YifYang993/CR-NeRF-PyTorch
+ * (models/rendering.py::render_rays_cross_ray and the NeRF_sigma / style_net /
+ * NeuralRenderer forwards it feeds).  The reference is pure Python/PyTorch and has
+ * no FFI of its own, so these entry points are what a ctypes binding placed at
+ * the reference's call sites would bind; the repo's own
+ * Python mirror (cr-nerf-pytorch_b200/models/) is exactly such a binding.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers on the current CUDA device unless the
+ *     name ends in _host; tensors are dense row-major fp32 unless stated.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Every call only enqueues work on that stream: no host synchronisation, no
+ *     internal streams, no allocation (callers own every buffer; scratch sizes
+ *     are queryable).
+ *   - Return value: 0 on success, negative crnerf_status on error;
+ *     crnerf_last_error() returns a thread-local message.  There is NO CPU
+ *     fallback: on a machine without an sm_100 GPU every compute call fails with
+ *     CRNERF_ERR_DEVICE.
+ *   - Thread safety: calls may be made from any host thread; a packed-weights
+ *     buffer may be shared by concurrent calls (read-only).
+ */
+#ifndef CRNERF_B200_H_
+#define CRNERF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRNERF_ABI_VERSION 1
+
+typedef enum {
+  CRNERF_OK = 0,
+  CRNERF_ERR_ARG = -1,     /* bad shape / null pointer / unsupported configuration */
+  CRNERF_ERR_DEVICE = -2,  /* no sm_100 device, or a CUDA runtime error */
+  CRNERF_ERR_RANGE = -3,   /* a weight does not fit the operand format (see pack) */
+  CRNERF_ERR_KERNEL = -4   /* device-side protocol timeout (internal error) */
+} crnerf_status;
+
+/* Operand format of the tensor-core MLP.  Accumulation is always fp32.
+ *   FP16: 10-bit mantissa (same as TF32) - meets the 1e-4 parity bar; |w| must be < 65504.
+ *   BF16: 7-bit mantissa, fp32 range - PSNR-level parity only. */
+typedef enum { CRNERF_OPERAND_FP16 = 0, CRNERF_OPERAND_BF16 = 1 } crnerf_operand;
+
+const char* crnerf_last_error(void);
+int crnerf_abi_version(void);
+/* 1 if the current device can run the kernels (compute capability 10.x). */
+int crnerf_device_ok(void);
+/* number of kernels this library has launched since load (all threads) */
+uint64_t crnerf_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * NeRF_sigma weights (reference models/nerf.py:116-154, state_dict keys
+ * xyz_encoding_{1..8}.0, xyz_encoding_final, dir_encoding.0, static_rgb.0,
+ * static_sigma.0).  nn.Linear layout: weight (out,in) row-major, bias (out).
+ * Index: 0..7 trunk, 8 final, 9 dir, 10 rgb, 11 sigma.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* weight[12];
+  const float* bias[12];
+  int32_t e_xyz; /* in_channels_xyz, <= 96 (93 for N_emb_xyz=15) */
+  int32_t e_dir; /* in_channels_dir, <= 32 (27 for N_emb_dir=4)  */
+} crnerf_mlp_weights;
+
+/* Bytes of the packed form (16-bit swizzled weight image + fp32 bias blob). */
+size_t crnerf_mlp_packed_bytes(int e_xyz, int e_dir);
+/* Pack once per weight version.  `status_dev` (int32, device, may be NULL)
+ * receives 1 if some |w| exceeded the operand format's finite range (the value
+ * is clamped); the Python mirror turns that into an error. */
+int crnerf_mlp_pack(const crnerf_mlp_weights* w, int operand, void* packed, size_t packed_bytes,
+                    int32_t* status_dev, void* stream);
+
+/* ------------------------------------------------------------------------
+ * One volume-rendering pass = the reference's `inference` closure
+ * (models/rendering.py:82-145) with PosEmbedding (models/nerf.py:17-30) and
+ * NeRF_sigma.forward (models/nerf.py:157-182) fused in: for every ray,
+ * embed xyz = o + d*z and the view direction, run the MLP on every sample,
+ * alpha-composite.  No per-point intermediate is written to memory.
+ *   rays      (n_rays, 8)  [o3, d3, near, far]   (rendering.py:151-153)
+ *   view_dir  (n_rays, 3) or NULL -> rays[:,3:6]  (kwargs['view_dir'], :155)
+ *   z_vals    (n_rays, n_samples) sorted depths
+ *   noise     (n_rays, n_samples) already scaled by noise_std, or NULL (:125)
+ * outputs
+ *   weights   (n_rays, n_samples), feature (n_rays, 64), depth (n_rays)
+ * `operand` must be the crnerf_operand the weights were packed with, and the
+ * weights must have been packed for e_xyz = 3+6*n_freq_xyz, e_dir = 3+6*n_freq_dir.
+ * 16 <= n_samples <= 4096.  n_freq_xyz <= 15, n_freq_dir <= 4 (PosEmbedding(L-1, L)).
+ * ---------------------------------------------------------------------- */
+int crnerf_render_pass(const void* packed, int operand, const float* rays, const float* view_dir,
+                       const float* z_vals, const float* noise, int n_rays, int n_samples,
+                       int n_freq_xyz, int n_freq_dir, float* weights, float* feature,
+                       float* depth, void* stream);
+
+/* NeRF_sigma.forward on pre-embedded rows (models/nerf.py:157-182):
+ *   x (n, x_stride) with [0,e_xyz) xyz embedding, [e_xyz, e_xyz+e_dir) dir
+ *   embedding; out (n, 65) = [sigmoid features(64) | softplus sigma].
+ * If sigma_only != 0, x holds only the xyz embedding and out is (n, 1). */
+int crnerf_mlp_forward(const void* packed, int operand, int e_xyz, int e_dir, const float* x,
+                       int64_t n, int x_stride, int sigma_only, float* out, void* stream);
+
+/* PosEmbedding.forward (models/nerf.py:17-30): x (n,3) -> out (n, 3+6*n_freqs),
+ * [x, sin(2^0 x), cos(2^0 x), ...]. */
+int crnerf_pos_embed(const float* x, int64_t n, int n_freqs, float* out, void* stream);
+
+/* Coarse depths (models/rendering.py:161-176): z = near*(1-t)+far*t (or the
+ * disparity form).  t_steps (n_samples) is the caller's linspace(0,1,n_samples)
+ * (rendering.py:161; passed in so the grid is bit-identical to the one the
+ * reference builds on the same device).  If perturb_rand != NULL (n_rays,
+ * n_samples, already multiplied by `perturb`) applies the stratified jitter
+ * lower + (upper-lower)*perturb_rand. */
+int crnerf_coarse_z(const float* rays, const float* t_steps, const float* perturb_rand, int n_rays,
+                    int n_samples, int use_disp, float* z_vals, void* stream);
+
+/* sample_pdf + merge (models/rendering.py:7-46 and :183-187):
+ *   bins = midpoints of z_coarse, weights = weights_coarse[:,1:-1]; draws
+ *   n_importance samples by inverse CDF at the uniforms u[ray*u_stride + i]
+ *   (u_stride = n_importance for per-ray draws, rendering.py:30; u_stride = 0
+ *   to share one row, the det case u = linspace(0,1,n_importance), :27-28) and
+ *   writes z_fine (n_rays, n_samples+n_importance) = sort(cat(z_coarse, samples)).
+ *   z_new (n_rays, n_importance), optional, receives the unsorted samples.
+ *   n_samples + n_importance <= 4096. */
+int crnerf_sample_pdf_merge(const float* z_coarse, const float* weights_coarse, const float* u,
+                            int64_t u_stride, int n_rays, int n_samples, int n_importance,
+                            float eps, float* z_fine, float* z_new, void* stream);
+
+/* Stand-alone sample_pdf (models/rendering.py:7-46): bins (n, m+1), weights (n, m). */
+int crnerf_sample_pdf(const float* bins, const float* weights, const float* u, int64_t u_stride,
+                      int n_rays, int m, int n_importance, float eps, float* samples,
+                      void* stream);
+
+/* ------------------------------------------------------------------------
+ * Cross-ray fusion + decoder = style_net.forward
+ * (models/linearStyleTransfer.py:284-291 -> MulLayer.forward :58-90 ->
+ *  CNN.forward :28-37 -> NeuralRenderer.forward nerf_decoder_stylenerf.py:279-291).
+ * Feature maps are addressed as element (pixel p, channel c) at
+ *   base[p * pix_stride + c * ch_stride]
+ * so both the renderer's (N,64) rows (pix_stride 64, ch_stride 1: what the
+ * callers' rearrange produces as a view) and contiguous NCHW
+ * (pix_stride 1, ch_stride H*W) are read in place.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* conv_w[3]; /* convs.0 (128,64) convs.2 (64,128) convs.4 (32,64) */
+  const float* conv_b[3];
+  const float* fc_w; /* (1024,1024) */
+  const float* fc_b; /* (1024)      */
+} crnerf_cnn_weights;
+
+typedef struct {
+  crnerf_cnn_weights cnet, snet;
+  const float* compress_w; /* (32,64) */
+  const float* compress_b;
+  const float* unzip_w; /* (64,32) */
+  const float* unzip_b;
+  const float* rgb_w; /* decoder.feat_2_rgb_list.0 (3,64) */
+  const float* rgb_b;
+} crnerf_style_weights;
+
+/* scratch floats needed by crnerf_style_forward */
+size_t crnerf_style_scratch_floats(int64_t n_pixels);
+/* content (n_pixels x 64), style (n_style_pixels x 64) or NULL (type=="content":
+ * decoder only) -> rgb written as (3, n_pixels) planar (= (1,3,H,W) contiguous).
+ * Optionally writes transmatrix (32x32) and fused (64 x n_pixels planar). */
+int crnerf_style_forward(const crnerf_style_weights* w, const float* content,
+                         int64_t n_pixels, int64_t c_pix_stride, int64_t c_ch_stride,
+                         const float* style, int64_t n_style_pixels, int64_t s_pix_stride,
+                         int64_t s_ch_stride, float* rgb, float* transmatrix, float* fused,
+                         float* scratch, void* stream);
+
+/* CNN.forward alone (models/linearStyleTransfer.py:28-37): x (n_pixels x 64) ->
+ * out (1024) = fc(flatten(convs(x) convs(x)^T / n_pixels)).  Same scratch buffer. */
+int crnerf_cnn_forward(const crnerf_cnn_weights* w, const float* x, int64_t n_pixels,
+                       int64_t pix_stride, int64_t ch_stride, float* out, float* scratch,
+                       void* stream);
+
+/* The sharded (multi-GPU) form of the same block, SURVEY.md 8(e) scheme B:
+ *   stats1: per-channel sums of this rank's pixels          -> sums (64)
+ *   [all-reduce sums; mean = sums / total_pixels]
+ *   stats2: un-normalised Gram of cnet.convs(content - mean) -> gram (32x32)
+ *   [all-reduce gram]
+ *   apply : build the fused 64->3 map from gram / total_pixels and the style
+ *           branch, apply it to this rank's pixels            -> rgb (3, n_pixels)
+ * `scratch` is the same buffer crnerf_style_forward takes. */
+int crnerf_style_stats1(const float* content, int64_t n_pixels, int64_t pix_stride,
+                        int64_t ch_stride, float* sums, float* scratch, void* stream);
+int crnerf_style_stats2(const crnerf_style_weights* w, const float* content, int64_t n_pixels,
+                        int64_t pix_stride, int64_t ch_stride, const float* mean, float* gram,
+                        float* scratch, void* stream);
+/* gram_normalised = (all-reduced gram) / total_pixels, computed by the caller */
+int crnerf_style_apply(const crnerf_style_weights* w, const float* content, int64_t n_pixels,
+                       int64_t pix_stride, int64_t ch_stride, const float* mean,
+                       const float* gram_normalised, const float* style, int64_t n_style_pixels,
+                       int64_t s_pix_stride, int64_t s_ch_stride, float* rgb, float* transmatrix,
+                       float* scratch, void* stream);
+
+/* debug (tests only): dump the post-activation values of `layer` (0..10) for every
+ * point of later fused launches into dbg_buf (n_points x 256 floats); NULL disables. */
+int crnerf_debug_set(float* dbg_buf, int layer);
+/* debug (tests only, host-only, no GPU needed): the weight-chunk program of the
+ * fused kernel as flat int32: [n_chunks, n_units, image_bytes, 10 ints per chunk
+ * (offset, bytes, layer, rows, row0, wcol0, wcols, a_src, a_k0, nk), 7 ints per
+ * unit (layer, half, n, chunk0, nchunks, first_of_layer, last_of_layer)].
+ * Returns the number of ints written, or a negative crnerf_status. */
+int crnerf_debug_program(int e_xyz, int e_dir, int32_t* out_host, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRNERF_B200_H_ */

@@ -1,0 +1,85 @@
+"""Shared fixtures.  GPU tests are marked ``@pytest.mark.gpu``; everything else runs on CPU.
+
+Only tests (and smoke / bench's CPU-baseline leg) may import ``oracle/``; the
+product package under ``cr-nerf-pytorch_b200/`` never does.
+"""
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "cr-nerf-pytorch_b200")
+for p in (os.path.join(ROOT, "oracle"), PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA (sm_100) device")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLD, name + ".pt"), map_location="cpu", weights_only=False)
+
+
+def make_args(**kw):
+    d = dict(nerf_out_dim=64, pertubeCord=False, img_wh=[32, 32], N_emb_xyz=15, N_emb_dir=4)
+    d.update(kw)
+    return types.SimpleNamespace(**d)
+
+
+def sharpen(model, seed):
+    """Same 'peaky' transform as oracle/make_golden.py::sharpen."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        w = model.static_sigma[0].weight
+        w.mul_(30.0)
+        w.add_(0.05 * torch.randn(w.shape, generator=g))
+        model.static_sigma[0].bias.sub_(2.0)
+
+
+def build_mirror_models(seed=0, peaky=False):
+    """The product's module mirror, built in the reference's order (coarse, decoder,
+    fine - train_mask_grid_sample.py:38-61) so seeded default init equals the reference's."""
+    from models.nerf import NeRF_sigma
+    from models.linearStyleTransfer import style_net
+    torch.manual_seed(seed)
+    args = make_args()
+    coarse = NeRF_sigma('coarse', args, in_channels_xyz=93, in_channels_dir=27)
+    decoder = style_net(args)
+    fine = NeRF_sigma('fine', args, in_channels_xyz=93, in_channels_dir=27, encode_appearance=True,
+                      in_channels_a=48, encode_random=True)
+    if peaky:
+        sharpen(coarse, seed + 100)
+        sharpen(fine, seed + 101)
+    return {"coarse": coarse.eval(), "fine": fine.eval(), "decoder": decoder.eval()}, args
+
+
+def state(module):
+    return {k: v.detach().clone() for k, v in module.state_dict().items()}
+
+
+def check_checksums(module, sums):
+    sd = module.state_dict()
+    assert set(sd.keys()) == set(sums.keys()), (sorted(sd.keys()), sorted(sums.keys()))
+    for k, (s, a) in sums.items():
+        v = sd[k].double()
+        assert float(v.sum()) == s and float(v.abs().sum()) == a, f"init drift in {k}"
+
+
+@pytest.fixture(scope="session")
+def mirror_default():
+    return build_mirror_models(0, False)

@@ -1,0 +1,93 @@
+"""CPU: the oracle reproduces every golden vector bit-for-bit, and the product's
+module mirror has the reference's state_dict keys and seeded default init.
+
+The goldens were produced by the UNMODIFIED reference (oracle/make_golden.py), so
+this pins oracle == reference on every machine, without /root/reference."""
+import pytest
+import torch
+
+import crnerf_oracle as oracle
+from conftest import build_mirror_models, check_checksums, load_golden, state
+
+RENDER_CASES = ["render_c64_eval", "render_64p128_eval", "render_64p128_eval_peaky",
+                "render_64p64_train", "render_32p24_train_peaky", "render_48p48_disp"]
+
+
+@pytest.mark.parametrize("name", RENDER_CASES)
+def test_render_matches_reference(name):
+    g = load_golden(name)
+    models, _ = build_mirror_models(g["seed"], g["peaky"])
+    check_checksums(models["coarse"], g["checksum_coarse"])
+    check_checksums(models["fine"], g["checksum_fine"])
+    rng = dict(g["rng"])
+    if g["perturb"] > 0 and g["n_importance"] > 0:
+        assert "u" in rng
+    with torch.no_grad():
+        out = oracle.render_rays(state(models["coarse"]), state(models["fine"]), g["rays"],
+                                 n_samples=g["n_samples"], n_importance=g["n_importance"],
+                                 use_disp=g["use_disp"], perturb=g["perturb"],
+                                 noise_std=g["noise_std"], chunk=8192, rng=rng, record=(rec := {}))
+    for k, v in g["ref"].items():
+        assert torch.equal(out[k], v), k
+    assert torch.equal(rec["z_coarse"], g["z_coarse"])
+    if g["z_fine"] is not None:
+        assert torch.equal(rec["z_fine"], g["z_fine"])
+
+
+def test_posenc_and_mlp():
+    g = load_golden("posenc_mlp")
+    models, _ = build_mirror_models(0)
+    check_checksums(models["fine"], g["checksum_fine"])
+    assert torch.equal(oracle.pos_embed(g["xyz"], 15), g["emb_xyz"])
+    assert torch.equal(oracle.pos_embed(g["dir"], 4), g["emb_dir"])
+    x = torch.cat([g["emb_xyz"], g["emb_dir"]], 1)
+    with torch.no_grad():
+        assert torch.equal(oracle.nerf_sigma_forward(state(models["fine"]), x), g["mlp_out"])
+        assert torch.equal(oracle.nerf_sigma_forward(state(models["fine"]), g["emb_xyz"],
+                                                     sigma_only=True), g["sigma_only"])
+
+
+def test_sample_pdf():
+    g = load_golden("sample_pdf")
+    for c in g["cases"]:
+        u = c["u"]
+        if u is None:
+            u = torch.linspace(0, 1, c["n_importance"]).expand(g["bins"].shape[0], -1)
+        out = oracle.sample_pdf(g["bins"], g["weights"], c["n_importance"], det=c["det"], u=u)
+        assert torch.equal(out, c["ref"])
+    # edge cases the reference's formula defines: all-zero weights -> uniform pdf through eps
+    s = oracle.sample_pdf(g["bins"][:8], g["weights"][:8], 16, det=True)
+    assert torch.isfinite(s).all()
+    assert (s >= g["bins"][:8, :1] - 1e-6).all() and (s <= g["bins"][:8, -1:] + 1e-6).all()
+
+
+def test_style_net():
+    g = load_golden("style")
+    models, _ = build_mirror_models(0)
+    dec = models["decoder"]
+    check_checksums(dec, g["checksum_decoder"])
+    p = state(dec)
+    for c in g["cases"]:
+        content = c["feature"].t().reshape(1, 64, c["h"], c["w"])
+        with torch.no_grad():
+            assert torch.equal(oracle.style_net_forward(p, content, c["style"]), c["rgb"])
+            assert torch.equal(oracle.style_net_forward(p, content, None, type="content"),
+                               c["rgb_content"])
+            fused, trans = oracle.mul_layer_forward(p, content, c["style"])
+            assert torch.equal(fused, c["fused"]) and torch.equal(trans, c["trans"])
+
+
+def test_operand_emulation_meets_tolerance():
+    """fp16 operands (10-bit mantissa, the CUDA path's parity mode) keep the rendered
+    features within the north-star tolerance of the fp32 reference; bf16 does not.
+    Documents why fp16 is the parity mode."""
+    g = load_golden("render_64p128_eval")
+    models, _ = build_mirror_models(0)
+    pc, pf = state(models["coarse"]), state(models["fine"])
+    kw = dict(n_samples=64, n_importance=128, perturb=0, noise_std=0, chunk=8192)
+    with torch.no_grad():
+        h = oracle.render_rays(pc, pf, g["rays"], operand_dtype=torch.float16, **kw)
+        b = oracle.render_rays(pc, pf, g["rays"], operand_dtype=torch.bfloat16, **kw)
+    ref = g["ref"]["feature_fine"]
+    assert torch.allclose(h["feature_fine"], ref, rtol=1e-4, atol=1e-6)
+    assert not torch.allclose(b["feature_fine"], ref, rtol=1e-4, atol=1e-6)
