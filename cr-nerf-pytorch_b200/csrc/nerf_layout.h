@@ -11,9 +11,16 @@
 //
 // A-operand sources of a chunk:
 //   kSrcEmb : the tile's embedding buffer in shared memory (SS MMA). 128 columns:
-//             [0,e_xyz) xyz embedding, zero pad to 96, [96,96+e_dir) dir embedding,
-//             zero pad to 128; two SW128 slabs of 64 columns.
+//             [0,e_xyz) xyz embedding, zero pad, columns 93 and 94 hold the constant 1.0,
+//             [96,96+e_dir) dir embedding, zero pad to 128; two SW128 slabs of 64 columns.
 //   kSrcAct : the previous layer's activations in TMEM (TS MMA), 2 values per column.
+//
+// Biases ride on the tensor core: every unit ends with a BIAS chunk, one 16-column
+// k-step whose A operand is embedding columns 80..95 (ones at 93, 94) and whose B
+// operand holds fp16(b) at K index 13 and fp16(b - fp16(b)) at K index 14 (zero
+// elsewhere), so D = W x + b to ~22 bits of b without a single epilogue instruction.
+// Bias chunks use the un-swizzled K-major "interleaved" layout (8x8 core matrices,
+// LBO 128 B between the two K halves, SBO 256 B between 8-row groups): rows*32 bytes.
 //
 // build_program() is the single source of truth; host code runs it once and
 // uploads the tables to __constant__ memory for both kernels.
@@ -35,7 +42,10 @@ constexpr int kDirWidth = 128;   // W/2
 constexpr int kOutDim = 64;      // nerf_out_dim
 constexpr int kEmbCols = 128;    // embedding buffer columns (2 slabs of 64)
 constexpr int kDirCol0 = 96;     // first dir-embedding column in the buffer
-constexpr int kMaxExyz = 96, kMaxEdir = 32;
+constexpr int kMaxExyz = 93, kMaxEdir = 32;
+constexpr int kOnesCol = 93;     // embedding columns kOnesCol, kOnesCol+1 are the constant 1.0
+constexpr int kBiasKstep = 5;    // k-step (16 columns) of the embedding buffer that holds them
+constexpr int kBiasKhi = kOnesCol - 16 * kBiasKstep;  // K index of fp16(b) inside a bias chunk (13)
 
 enum LayerId : int {
   kL1 = 0,  // .. kL8 = 7
@@ -46,6 +56,7 @@ enum LayerId : int {
   kLSigma = 11  // not a tensor-core layer; index into the weight pointer array only
 };
 enum ASrc : int { kSrcEmb = 0, kSrcAct = 1 };
+enum ChunkKind : int { kKindWeights = 0, kKindBias = 1 };
 
 struct Chunk {
   int32_t offset;   // byte offset in the packed image
@@ -58,6 +69,8 @@ struct Chunk {
   int16_t a_src;    // ASrc
   int16_t a_k0;     // first k-step (16 columns) in the A source
   int16_t nk;       // k-steps to issue = ceil(wcols / 16)
+  int16_t kind;     // ChunkKind
+  int16_t pad;
 };
 
 struct Unit {
@@ -71,7 +84,7 @@ struct Unit {
   int16_t pad;
 };
 
-constexpr int kMaxChunks = 80;
+constexpr int kMaxChunks = 104;
 constexpr int kMaxUnits = 20;
 
 struct Program {
@@ -123,6 +136,24 @@ inline void build_program(int e_xyz, int e_dir, Program* p) {
     c.a_src = (int16_t)a_src;
     c.a_k0 = (int16_t)a_k0;
     c.nk = (int16_t)((wcols + 15) / 16);
+    c.kind = kKindWeights;
+    c.pad = 0;
+    off += c.bytes;
+  };
+  auto add_bias_chunk = [&](int layer, int row0, int rows) {
+    Chunk& c = p->chunks[nc++];
+    c.offset = off;
+    c.bytes = rows * 32;
+    c.layer = (int16_t)layer;
+    c.rows = (int16_t)rows;
+    c.row0 = (int16_t)row0;
+    c.wcol0 = 0;
+    c.wcols = 0;
+    c.a_src = (int16_t)kSrcEmb;
+    c.a_k0 = (int16_t)kBiasKstep;
+    c.nk = 1;
+    c.kind = kKindBias;
+    c.pad = 0;
     off += c.bytes;
   };
   auto emb_chunks = [&](int layer, int row0, int rows, int wcol0, int cols, int bufcol0) {
@@ -165,20 +196,24 @@ inline void build_program(int e_xyz, int e_dir, Program* p) {
       } else {
         act_chunks(l, h * 128, 128, 0, kWidth);
       }
+      add_bias_chunk(l, h * 128, 128);
       end_unit();
     }
   }
   for (int h = 0; h < 2; ++h) {
     begin_unit(kLFinal, h, 128, h == 0, h == 1);
     act_chunks(kLFinal, h * 128, 128, 0, kWidth);
+    add_bias_chunk(kLFinal, h * 128, 128);
     end_unit();
   }
   begin_unit(kLDir, 0, 128, 1, 1);
   act_chunks(kLDir, 0, 128, 0, kWidth);
   emb_chunks(kLDir, 0, 128, kWidth, e_dir, kDirCol0);
+  add_bias_chunk(kLDir, 0, 128);
   end_unit();
   begin_unit(kLRgb, 0, 64, 1, 1);
   act_chunks(kLRgb, 0, 64, 0, kDirWidth);
+  add_bias_chunk(kLRgb, 0, 64);
   end_unit();
   p->n_chunks = nc;
   p->n_units = nu;

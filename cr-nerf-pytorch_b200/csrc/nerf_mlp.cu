@@ -8,9 +8,10 @@
 // Structure (one CTA per SM, 384 threads):
 //   warp 0      producer : streams the packed weight image L2 -> smem ring with
 //                          cp.async.bulk (TMA engine), mbarrier complete_tx
-//   warp 1      issuer   : one thread issues tcgen05.mma (kind::f16, M=128,
-//                          N=128/64, K=16); activations are the A operand read
-//                          from TMEM (TS form), the embedding is read from smem
+//   warps 1, 3  issuers  : one per tile stream (X, Y); an elected thread issues
+//                          tcgen05.mma (kind::f16, M=128, N=128/64, K=16); activations
+//                          are the A operand read from TMEM (TS form), the embedding is
+//                          read from smem (SS form)
 //   warp 2      TMEM allocator
 //   warps 4-7   epilogue group X, warps 8-11 epilogue group Y: each group owns
 //               one 128-point tile (one point per thread = one TMEM lane):
@@ -18,9 +19,9 @@
 //               cvt.f16x2 -> tcgen05.st back as next layer's A operand; sigma
 //               head as an fp32 dot in the layer-8 epilogue; segmented
 //               warp-shuffle transmittance scan; weighted feature reduction.
-// Two tiles (X, Y) are in flight per CTA and share every weight chunk; the
-// issuer alternates X/Y per 128-wide output half so each epilogue runs under
-// the other tile's MMAs.  TMEM: X {A: cols 0-127, D: 128-255}, Y {A: 256-383,
+// Two tiles (X, Y) are in flight per CTA and share every weight chunk; their
+// MMA streams are issued by separate warps so each stream's epilogues and
+// barrier waits run under the other stream's MMAs.  TMEM: X {A: cols 0-127, D: 128-255}, Y {A: 256-383,
 // D: 384-511}; the first output half is held in registers until the layer's
 // second half has been issued, so A needs no double buffer.
 #include <cuda_bf16.h>
@@ -36,6 +37,8 @@ namespace crnerf {
 
 __constant__ Chunk c_chunks[kMaxChunks];
 __constant__ Unit c_units[kMaxUnits];
+// per chunk, for the issuer: a_src | a_k0 << 8 | nk << 16 (one uniform load)
+__constant__ uint32_t c_meta[kMaxChunks];
 
 namespace {
 
@@ -83,6 +86,9 @@ struct RenderParams {
   float* depth;
   float* raw;
   float* dbg;
+  long long* prof;  // optional cycle counters of CTA 0 (tests / profiling only)
+  int exp;          // profiling experiments (debug instantiation only): 1 = epilogue skips TMEM
+                    // traffic and math, 2 = producer skips the weight copies
   long long n_points;
   long long pts_per_cta;
   int x_stride;
@@ -92,6 +98,24 @@ struct RenderParams {
   int n_chunks, n_units;
   int mode;
 };
+
+// mbar_wait that adds the blocked cycles to a counter when profiling is on
+__device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, uint32_t tag, bool prof,
+                                           long long& acc) {
+  if (!prof) {
+    mbar_wait(bar, parity, tag);
+    return;
+  }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity, tag);
+  acc += clock64() - t0;
+}
+
+// one arrival on behalf of a converged warp
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 
 __device__ __forceinline__ void group_sync(int b) {
   asm volatile("bar.sync %0, 128;" ::"r"(1 + b) : "memory");
@@ -116,48 +140,78 @@ __device__ __forceinline__ void emb_put(uint8_t* buf, int row, int col, float v)
   *reinterpret_cast<uint16_t*>(buf + off) = to_operand<kFmt>(v);
 }
 
-// sin/cos of 2^k * x with x/(2*pi) supplied as an unevaluated sum hi+lo.
-// The argument 2^k*x is exact in fp32 (power-of-two scale), so the only error
-// is in the range reduction - done here to ~2^-45 of a revolution in
-// double-float arithmetic - and the SFU evaluation on |a| <= pi (~5e-7 abs),
-// far below the 16-bit operand rounding (2^-11) applied right after.
-__device__ __forceinline__ void sincos_band(float x, float hi, float lo, int k, float& s, float& c) {
-  const float sc = __int_as_float((127 + k) << 23);
-  const float hk = hi * sc, lk = lo * sc;
-  if (fabsf(hk) < 4194304.f) {
-    const float n = rintf(hk);
-    const float r = (hk - n) + lk;
-    const float a = r * 6.283185307179586f;
-    s = __sinf(a);
-    c = __cosf(a);
-  } else {  // |x| beyond any scene scale: full-range library path
-    sincosf(x * sc, &s, &c);
-  }
-}
-
-// [v, sin(2^0 v), cos(2^0 v), ...] for a 3-vector, written at buffer column col0
-// (reference column order, models/nerf.py:25-30).
-template <int kFmt>
-__device__ __forceinline__ void embed3(uint8_t* buf, int row, int col0, const float (&v)[3],
-                                       int n_freqs) {
-  float hi[3], lo[3];
+// ---------------------------------------------------------------------------
+// Positional encoding (reference models/nerf.py:17-30).
+// sin/cos of 2^k * x with x/(2*pi) held as an unevaluated sum hi+lo.  The
+// argument 2^k*x is exact in fp32 (power-of-two scale), so the only error is in
+// the range reduction - done to ~2^-45 of a revolution in double-float
+// arithmetic - and the SFU evaluation on |a| <= pi (~5e-7 abs), far below the
+// 16-bit operand rounding (2^-11) applied right after.
+// ---------------------------------------------------------------------------
+struct EmbIn {
+  float v[3], hi[3], lo[3];
+};
+__device__ __forceinline__ void emb_prepare(EmbIn& e) {
+  const float chi = 0.15915493667125702f;    // fl32(1/2pi)
+  const float clo = 6.420638316725915e-09f;  // 1/2pi - chi
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    emb_put<kFmt>(buf, row, col0 + i, v[i]);
-    const float chi = 0.15915493667125702f;  // fl32(1/2pi)
-    const float clo = 6.420638316725915e-09f;  // 1/2pi - chi
-    hi[i] = v[i] * chi;
-    lo[i] = fmaf(v[i], clo, fmaf(v[i], chi, -hi[i]));
+    e.hi[i] = e.v[i] * chi;
+    e.lo[i] = fmaf(e.v[i], clo, fmaf(e.v[i], chi, -e.hi[i]));
   }
+}
+// fast path is valid while 2^14 |x| / 2pi < 2^22
+__device__ __forceinline__ bool emb_fast_ok(const EmbIn& e) {
+  return fmaxf(fmaxf(fabsf(e.v[0]), fabsf(e.v[1])), fabsf(e.v[2])) < 1024.f;
+}
+// column c of [v, sin(2^0 v), cos(2^0 v), ...]; c is a constant after unrolling, and the
+// reduced argument of a (band, coordinate) pair is shared by its sin and cos columns (CSE)
+template <int kNFreq, bool kOnes>
+__device__ __forceinline__ float emb_col(const EmbIn& e, int c) {
+  if (c < 3) return e.v[c];
+  if (kOnes && (c == kOnesCol || c == kOnesCol + 1)) return 1.f;  // bias lanes (nerf_layout.h)
+  if (c >= 3 + 6 * kNFreq) return 0.f;
+  const int k = (c - 3) / 6, r = (c - 3) % 6, i = r % 3;
+  const float sc = __int_as_float((127 + k) << 23);
+  const float hk = e.hi[i] * sc, lk = e.lo[i] * sc;
+  const float a = ((hk - rintf(hk)) + lk) * 6.283185307179586f;
+  return r < 3 ? __sinf(a) : __cosf(a);
+}
+// 8*kNChunks consecutive columns -> kNChunks 16-byte stores into the swizzled buffer
+template <int kFmt, int kNFreq, int kChunk0, int kNChunks>
+__device__ __forceinline__ void emb_write(uint8_t* buf, uint32_t row_off, uint32_t row_xor,
+                                          const EmbIn& e) {
+#pragma unroll
+  for (int m = 0; m < kNChunks; ++m) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      w[q] = pack2<kFmt, false>(emb_col<kNFreq, kChunk0 == 0>(e, 8 * m + 2 * q),
+                                emb_col<kNFreq, kChunk0 == 0>(e, 8 * m + 2 * q + 1));
+    const uint32_t cm = kChunk0 + m;
+    const uint32_t off = (cm >> 3) * 16384u + row_off + (((cm & 7u) << 4) ^ row_xor);
+    *reinterpret_cast<uint4*>(buf + off) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+// any band count / any magnitude: library sincos, element stores (rare path, kept out of line)
+template <int kFmt>
+__device__ __noinline__ void embed3_generic(uint8_t* buf, int row, int col0, int col_end, float v0,
+                                            float v1, float v2, int n_freqs) {
+  const float v[3] = {v0, v1, v2};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) emb_put<kFmt>(buf, row, col0 + i, v[i]);
   for (int k = 0; k < n_freqs; ++k) {
+    const float sc = __int_as_float((127 + k) << 23);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       float s, c;
-      sincos_band(v[i], hi[i], lo[i], k, s, c);
+      sincosf(v[i] * sc, &s, &c);
       emb_put<kFmt>(buf, row, col0 + 3 + 6 * k + i, s);
       emb_put<kFmt>(buf, row, col0 + 6 + 6 * k + i, c);
     }
   }
+  for (int c = col0 + 3 + 6 * n_freqs; c < col_end; ++c)
+    emb_put<kFmt>(buf, row, c, (col0 == 0 && (c == kOnesCol || c == kOnesCol + 1)) ? 1.f : 0.f);
 }
 
 __device__ __forceinline__ float softplus_ref(float x) {
@@ -175,26 +229,95 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
       : "memory");
 }
 
-// One 32-column slice of an accumulator: +bias, optional ReLU, pack to 16 words.
-// kSigma additionally accumulates the fp32 sigma-head dot product.
+// One 16-column slice of an accumulator (bias already inside, see nerf_layout.h):
+// optional ReLU + pack to 8 words.  kSigma additionally accumulates the fp32
+// sigma-head dot product of the layer-8 activations.
 template <int kFmt, bool kRelu, bool kSigma>
-__device__ __forceinline__ void bias_act_pack(const uint32_t (&v)[32], const float* bias,
-                                              const float* wsig, uint32_t* out, float& sig_acc) {
+__device__ __forceinline__ void act_pack16(const uint32_t (&v)[16], const float* wsig, uint32_t* out,
+                                           float& sig_acc) {
+  if constexpr (kSigma) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float2 bb = *reinterpret_cast<const float2*>(bias + 2 * j);
-    const float2 a =
-        add2(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bb);
-    if constexpr (kSigma) {
-      const float2 ws = *reinterpret_cast<const float2*>(wsig + 2 * j);
-      sig_acc = fmaf(fmaxf(a.x, 0.f), ws.x, sig_acc);
-      sig_acc = fmaf(fmaxf(a.y, 0.f), ws.y, sig_acc);
+    for (int j = 0; j < 4; ++j) {
+      const float4 ws = *reinterpret_cast<const float4*>(wsig + 4 * j);
+      sig_acc = fmaf(fmaxf(__uint_as_float(v[4 * j]), 0.f), ws.x, sig_acc);
+      sig_acc = fmaf(fmaxf(__uint_as_float(v[4 * j + 1]), 0.f), ws.y, sig_acc);
+      sig_acc = fmaf(fmaxf(__uint_as_float(v[4 * j + 2]), 0.f), ws.z, sig_acc);
+      sig_acc = fmaf(fmaxf(__uint_as_float(v[4 * j + 3]), 0.f), ws.w, sig_acc);
     }
-    out[j] = pack2<kFmt, kRelu>(a.x, a.y);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    out[j] = pack2<kFmt, kRelu>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+}
+
+// Epilogue of one 128-wide accumulator.  kMode 0: first half of a 256-wide layer - keep
+// the packed result in `staged` (A is still being read by the layer's second half);
+// kMode 1: second half - write the staged half and this one to A columns [0,128);
+// kMode 2: dir layer - write straight to A columns [0,64).
+// The accumulator is drained in eight 16-column slices, software-pipelined over two
+// register buffers: the tcgen05.ld of slice c+1 is in flight while slice c is processed.
+enum : int { kEpiStage = 0, kEpiFlush = 1, kEpiDirect = 2 };
+
+template <int kFmt, bool kRelu, bool kSigma, bool kDbg>
+__device__ __forceinline__ void epi_128(int mode, uint32_t tD, uint32_t tA, const float* wsig,
+                                        uint32_t (&staged)[64], float& sig_acc, uint64_t* d_empty,
+                                        float* dbg_row, bool skip, int exp = 0) {
+  if (kDbg && skip) {
+    tc_fence_before_sync();
+    warp_arrive(d_empty);
+    return;
+  }
+  uint32_t va[16], vb[16];
+  if (kDbg && (exp & 16)) {  // experiment: no TMEM loads at all
+#pragma unroll
+    for (int j = 0; j < 16; ++j) va[j] = vb[j] = 0;
+  } else {
+    tmem_ld_x16(tD, va);
+  }
+  if (mode == kEpiFlush) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_st16(tA + 16 * c, &staged[16 * c]);
+  }
+  const uint32_t a_col0 = mode == kEpiFlush ? 64u : 0u;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (!(kDbg && (exp & 16))) tmem_ld_wait();
+    if (c < 7) {
+      if (!(kDbg && (exp & 16))) {
+        if (c & 1)
+          tmem_ld_x16(tD + 16 * (c + 1), va);
+        else
+          tmem_ld_x16(tD + 16 * (c + 1), vb);
+      }
+    } else {  // accumulator drained: the issuer may overwrite it
+      tc_fence_before_sync();
+      warp_arrive(d_empty);
+    }
+    uint32_t(&v)[16] = (c & 1) ? vb : va;
+    if constexpr (kDbg) {
+      if (dbg_row) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = __uint_as_float(v[j]);
+          dbg_row[16 * c + j] = kRelu ? fmaxf(a, 0.f) : a;
+        }
+      }
+    }
+    if (kDbg && (exp & 8)) {  // experiment: loads only
+      sig_acc += __uint_as_float(v[0]);
+      continue;
+    }
+    if (mode == kEpiStage) {
+      act_pack16<kFmt, kRelu, kSigma>(v, wsig + 16 * c, &staged[8 * c], sig_acc);
+    } else {
+      uint32_t cur[8];
+      act_pack16<kFmt, kRelu, kSigma>(v, wsig + 16 * c, cur, sig_acc);
+      tmem_st_x8(tA + a_col0 + 8 * c, cur);
+    }
   }
 }
 
-template <int kFmt>
+template <int kFmt, bool kDbg>
 __global__ void __launch_bounds__(kThreads, 1)
 render_fused_kernel(const __grid_constant__ RenderParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -213,15 +336,17 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
   if (tid == 0) {
     for (int i = 0; i < kSlots; ++i) {
       mbar_init(&M->ring_full[i], 1);
-      mbar_init(&M->ring_empty[i], 1);
+      mbar_init(&M->ring_empty[i], 2);  // released by both tile streams
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&M->emb_full[b], 128);
-      mbar_init(&M->a_full[b], 128);
+      // epilogue-side barriers take ONE arrival per warp (an elected lane after the warp's
+      // collective tcgen05.wait / __syncwarp): a 32-lane arrive is 32 serialized smem atomics
+      mbar_init(&M->emb_full[b], 4);
+      mbar_init(&M->a_full[b], 4);
       mbar_init(&M->d_full[b], 1);
-      mbar_init(&M->d_empty[b], 128);
+      mbar_init(&M->d_empty[b], 4);
       mbar_init(&M->carry_a[b], 1);
-      mbar_init(&M->carry_b[b], 64);
+      mbar_init(&M->carry_b[b], 2);
     }
     fence_mbar_init();
   }
@@ -242,6 +367,10 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
           const uint32_t slot = g % kSlots, n = g / kSlots;
           mbar_wait(&M->ring_empty[slot], (n & 1) ^ 1, 1);
           const uint32_t bytes = (uint32_t)c_chunks[c].bytes;
+          if (kDbg && (P.exp & 2)) {
+            mbar_arrive(&M->ring_full[slot]);
+            continue;
+          }
           mbar_arrive_expect_tx(&M->ring_full[slot], bytes);
           bulk_g2s_hint(ring + slot * kSlotBytes, P.wimg + c_chunks[c].offset, bytes,
                         &M->ring_full[slot], pol);
@@ -249,63 +378,126 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // -------------------------------------------------------------------- issuer
-    if (elect_one()) {
-      const uint32_t ring_addr = smem_u32(ring);
-      const uint32_t emb_addr = smem_u32(emb);
-      uint32_t ucount[2] = {0, 0}, acount[2] = {0, 0}, tcount[2] = {0, 0};
-      uint32_t g_base = 0;
-      for (int pair = 0; pair < n_pairs; ++pair) {
-        const bool valid1 = (2 * pair + 1) < n_tiles;
-        const int last_b = valid1 ? 1 : 0;
-        for (int u = 0; u < P.n_units; ++u) {
-          const Unit un = c_units[u];
-          const uint32_t idesc = make_idesc_f16(128, (uint32_t)un.n, kFmt);
-          for (int b = 0; b <= last_b; ++b) {
-            const uint32_t tA = tmem + (b ? 256u : 0u);
-            const uint32_t tD = tmem + (b ? 384u : 128u);
-            if (un.first_of_layer) {
-              if (un.layer == 0) {
-                mbar_wait(&M->emb_full[b], tcount[b] & 1, 2);
-              } else {
-                mbar_wait(&M->a_full[b], acount[b] & 1, 3);
-                acount[b]++;
-              }
-            }
-            mbar_wait(&M->d_empty[b], (ucount[b] & 1) ^ 1, 4);
-            tc_fence_after_sync();
-            for (int j = 0; j < un.nchunks; ++j) {
-              const uint32_t g = g_base + (uint32_t)(un.chunk0 + j);
-              const uint32_t slot = g % kSlots, n = g / kSlots;
-              const Chunk ch = c_chunks[un.chunk0 + j];
-              if (b == 0) {
-                mbar_wait(&M->ring_full[slot], n & 1, 5);
-                tc_fence_after_sync();
-              }
-              const uint32_t bslot = ring_addr + slot * kSlotBytes;
-              for (int k = 0; k < ch.nk; ++k) {
-                const uint64_t bdesc = make_sdesc_k_sw128(bslot + (uint32_t)k * 32u, 1024);
-                const uint32_t acc = (j | k) ? 1u : 0u;
-                const int ak = ch.a_k0 + k;
-                if (ch.a_src == kSrcEmb) {
-                  const uint32_t a_smem = emb_addr + (uint32_t)b * kEmbBufBytes +
-                                          (uint32_t)(ak >> 2) * 16384u + (uint32_t)(ak & 3) * 32u;
-                  umma_ss(tD, make_sdesc_k_sw128(a_smem, 1024), bdesc, idesc, acc);
-                } else {
-                  umma_ts(tD, tA + (uint32_t)ak * 8u, bdesc, idesc, acc);
-                }
-              }
-              if (b == last_b) umma_commit(&M->ring_empty[slot]);
-            }
-            umma_commit(&M->d_full[b]);
-            ucount[b]++;
+  } else if (warp == 1 || warp == 3) {
+    // ------------------------------------------------------------------- issuers
+    // One issuer warp per tile stream (warp 1 -> X, warp 3 -> Y).  The tcgen05 issue
+    // queue is only 1-2 instructions deep (measured: tools/umma_probe issue timestamps),
+    // so the tensor pipe runs only while some thread is actually issuing; with two
+    // independent streams one warp's barrier waits and bookkeeping hide under the other
+    // warp's MMAs.  X and Y touch disjoint TMEM regions, so no ordering between the two
+    // streams is needed; a ring slot is released when BOTH streams have committed it.
+    // The whole warp walks the (warp-uniform) program so table loads and descriptor
+    // arithmetic stay in uniform registers; tcgen05 instructions run under elect_one().
+    const int b = warp == 1 ? 0 : 1;
+    constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO | version | SW128
+    const uint32_t ring_lo = ((smem_u32(ring) & 0x3ffffu) >> 4) | (1u << 16);
+    const uint32_t emb_lo = ((smem_u32(emb) & 0x3ffffu) >> 4) | (1u << 16);
+    auto desc = [](uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; };
+    const uint32_t tA = tmem + (b ? 256u : 0u);
+    const uint32_t tD = tmem + (b ? 384u : 128u);
+    uint32_t ucount = 0, acount = 0;
+    uint32_t g_base = 0;
+    const bool prof = kDbg && P.prof != nullptr && blockIdx.x == 0;
+    long long w_emb = 0, w_a = 0, w_d = 0, w_ring = 0;
+    const long long t_start = clock64();
+    for (int pair = 0; pair < n_pairs; ++pair) {
+      if (2 * pair + b >= n_tiles) {
+        // odd tile count: this stream has no tile in the last pair, but it still owes the
+        // producer one arrival per ring slot
+        for (int c = 0; c < P.n_chunks; ++c) {
+          const uint32_t g = g_base + (uint32_t)c;
+          mbar_wait(&M->ring_full[g % kSlots], (g / kSlots) & 1, 6);
+          if (elect_one()) mbar_arrive(&M->ring_empty[g % kSlots]);
+        }
+        break;
+      }
+      for (int u = 0; u < P.n_units; ++u) {
+        const Unit un = c_units[u];
+        const uint32_t idesc = make_idesc_f16(128, (uint32_t)un.n, kFmt);
+        if (un.first_of_layer) {
+          if (un.layer == 0) {
+            timed_wait(&M->emb_full[b], (uint32_t)pair & 1, 2, prof, w_emb);
+          } else {
+            timed_wait(&M->a_full[b], acount & 1, 3, prof, w_a);
+            acount++;
           }
         }
-        tcount[0]++;
-        tcount[1]++;
-        g_base += (uint32_t)P.n_chunks;
+        timed_wait(&M->d_empty[b], (ucount & 1) ^ 1, 4, prof, w_d);
+        tc_fence_after_sync();
+        int j = 0;
+        while (j < un.nchunks) {
+          const uint32_t g = g_base + (uint32_t)(un.chunk0 + j);
+          const uint32_t meta = c_meta[un.chunk0 + j];
+          const int blk = (int)(meta >> 24);  // 4 / 2: first chunk of a run of full TS slabs
+          if (blk) {
+            // ---- fast path: `blk` consecutive 64-wide activation slabs = 4*blk MMAs issued
+            // as straight-line code (no table lookups or waits between them)
+            for (int jj = 0; jj < blk; ++jj)
+              timed_wait(&M->ring_full[(g + jj) % kSlots], ((g + jj) / kSlots) & 1, 5, prof, w_ring);
+            tc_fence_after_sync();
+            if (elect_one()) {
+              const uint32_t a_t = tA + ((meta >> 8) & 0xffu) * 8u;
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                if (jj < blk) {
+                  const uint32_t slot = (g + jj) % kSlots;
+                  const uint32_t b_lo = ring_lo + slot * (kSlotBytes >> 4);
+                  umma_ts(tD, a_t + 32u * jj, desc(b_lo), idesc, (j + jj) ? 1u : 0u);
+                  umma_ts(tD, a_t + 32u * jj + 8u, desc(b_lo + 2u), idesc, 1u);
+                  umma_ts(tD, a_t + 32u * jj + 16u, desc(b_lo + 4u), idesc, 1u);
+                  umma_ts(tD, a_t + 32u * jj + 24u, desc(b_lo + 6u), idesc, 1u);
+                  umma_commit(&M->ring_empty[slot]);
+                }
+              }
+            }
+            j += blk;
+            continue;
+          }
+          // ---- generic path: partial / embedding chunks (4 of the 79 chunks of a tile)
+          const uint32_t slot = g % kSlots;
+          const int a_src = (int)(meta & 0x7fu);
+          const bool is_bias = (meta & 0x80u) != 0;
+          const int a_k0 = (int)((meta >> 8) & 0xffu);
+          const int nk = (int)((meta >> 16) & 0xffu);
+          timed_wait(&M->ring_full[slot], (g / kSlots) & 1, 5, prof, w_ring);
+          tc_fence_after_sync();
+          const uint32_t b_lo = ring_lo + slot * (kSlotBytes >> 4);
+          if (elect_one()) {
+            const uint32_t acc0 = j ? 1u : 0u;
+            if (is_bias) {
+              // one k-step: ones columns of the embedding x [fp16(b), fp16(b - fp16(b))]
+              const uint32_t a_lo = emb_lo + (uint32_t)b * (kEmbBufBytes >> 4) +
+                                    (uint32_t)(a_k0 >> 2) * 1024u + (uint32_t)(a_k0 & 3) * 2u;
+              constexpr uint32_t kBiasHi = (256u >> 4) | (1u << 14);          // SBO 256 B | version | no swizzle
+              const uint32_t bb_lo = ((b_lo & 0xffffu)) | ((128u >> 4) << 16);  // LBO 128 B
+              umma_ss(tD, desc(a_lo), (static_cast<uint64_t>(kBiasHi) << 32) | bb_lo, idesc, acc0);
+            } else if (a_src == kSrcEmb) {
+              const uint32_t a_lo = emb_lo + (uint32_t)b * (kEmbBufBytes >> 4) +
+                                    (uint32_t)(a_k0 >> 2) * 1024u + (uint32_t)(a_k0 & 3) * 2u;
+              for (int k = 0; k < nk; ++k)
+                umma_ss(tD, desc(a_lo + 2u * k), desc(b_lo + 2u * k), idesc, k ? 1u : acc0);
+            } else {
+              const uint32_t a_t = tA + (uint32_t)a_k0 * 8u;
+              for (int k = 0; k < nk; ++k)
+                umma_ts(tD, a_t + 8u * k, desc(b_lo + 2u * k), idesc, k ? 1u : acc0);
+            }
+            umma_commit(&M->ring_empty[slot]);
+          }
+          ++j;
+        }
+        if (elect_one()) umma_commit(&M->d_full[b]);
+        ucount++;
       }
+      g_base += (uint32_t)P.n_chunks;
+    }
+    if (prof && lane == 0) {
+      long long* o = P.prof + (b ? 24 : 0);
+      o[0] = clock64() - t_start;  // issuer lifetime
+      o[1] = w_emb;
+      o[2] = w_a;
+      o[3] = w_d;
+      o[4] = w_ring;
+      o[5] = n_pairs;
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -320,9 +512,15 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
     uint8_t* my_emb = emb + b * kEmbBufBytes;
     float* staging = reinterpret_cast<float*>(my_emb);
     const bool ray_mode = !(P.mode & kModeEmbedded);
-    const bool raw_mode = (P.mode & kModeRaw) != 0;
+    const bool skip = kDbg && (P.exp & 1);
+    const bool raw_mode = (P.mode & kModeRaw) != 0 || skip;
+    const bool fast_emb = P.n_freq_xyz == 15 && P.n_freq_dir == 4;
     const float* wsig = blob + kSigmaWOff;
+    const uint32_t row_off = (uint32_t)row * 128u, row_xor = (uint32_t)(row & 7) << 4;
     uint32_t ud = 0;
+    const bool prof = kDbg && P.prof != nullptr && blockIdx.x == 0 && gtid == 0;
+    long long w_dfull = 0, t_emb = 0, t_comp = 0, t_red = 0, t_units = 0, t_stage = 0, t_flush = 0;
+    const long long t_start = clock64();
 
     for (int pair = 0; pair < n_pairs; ++pair) {
       const int t = 2 * pair + b;
@@ -333,11 +531,14 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       const bool valid = row < nvalid;
 
       // ---- tile inputs + embedding -> smem (A operand of layers 1, 5 and dir)
+      const long long t_e0 = prof ? clock64() : 0;
       float z = 0.f, delta = 0.f, nz = 0.f;
       int s = 0;
       long long ray = 0;
       if (ray_mode) {
-        float xyz[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
+        EmbIn ex, ed;
+        ex.v[0] = ex.v[1] = ex.v[2] = 0.f;
+        ed.v[0] = ed.v[1] = ed.v[2] = 0.f;
         if (valid) {
           ray = p / P.S;
           s = (int)(p - ray * P.S);
@@ -348,201 +549,157 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
           const float4 r1 = __ldg(reinterpret_cast<const float4*>(P.rays + ray * 8) + 1);
           // xyz = o + d*z with separate roundings, as the reference's broadcast
           // mul then add (rendering.py:178)
-          xyz[0] = __fadd_rn(r0.x, __fmul_rn(r0.w, z));
-          xyz[1] = __fadd_rn(r0.y, __fmul_rn(r1.x, z));
-          xyz[2] = __fadd_rn(r0.z, __fmul_rn(r1.y, z));
+          ex.v[0] = __fadd_rn(r0.x, __fmul_rn(r0.w, z));
+          ex.v[1] = __fadd_rn(r0.y, __fmul_rn(r1.x, z));
+          ex.v[2] = __fadd_rn(r0.z, __fmul_rn(r1.y, z));
           if (P.view_dir) {
-            vd[0] = __ldg(P.view_dir + ray * 3 + 0);
-            vd[1] = __ldg(P.view_dir + ray * 3 + 1);
-            vd[2] = __ldg(P.view_dir + ray * 3 + 2);
+            ed.v[0] = __ldg(P.view_dir + ray * 3 + 0);
+            ed.v[1] = __ldg(P.view_dir + ray * 3 + 1);
+            ed.v[2] = __ldg(P.view_dir + ray * 3 + 2);
           } else {
-            vd[0] = r0.w;
-            vd[1] = r1.x;
-            vd[2] = r1.y;
+            ed.v[0] = r0.w;
+            ed.v[1] = r1.x;
+            ed.v[2] = r1.y;
           }
         }
-        embed3<kFmt>(my_emb, row, 0, xyz, P.n_freq_xyz);
-        embed3<kFmt>(my_emb, row, kDirCol0, vd, P.n_freq_dir);
+        if (fast_emb && emb_fast_ok(ex) && emb_fast_ok(ed)) {
+          emb_prepare(ex);
+          emb_prepare(ed);
+          emb_write<kFmt, 15, 0, 12>(my_emb, row_off, row_xor, ex);   // columns 0..95
+          emb_write<kFmt, 4, 12, 4>(my_emb, row_off, row_xor, ed);    // columns 96..127
+        } else {
+          embed3_generic<kFmt>(my_emb, row, 0, kDirCol0, ex.v[0], ex.v[1], ex.v[2], P.n_freq_xyz);
+          embed3_generic<kFmt>(my_emb, row, kDirCol0, kEmbCols, ed.v[0], ed.v[1], ed.v[2],
+                               P.n_freq_dir);
+        }
       } else {
         const float* xr = P.x + p * P.x_stride;
         for (int c = 0; c < P.e_xyz; ++c) emb_put<kFmt>(my_emb, row, c, valid ? __ldg(xr + c) : 0.f);
+        for (int c = P.e_xyz; c < kDirCol0; ++c)
+          emb_put<kFmt>(my_emb, row, c, (c == kOnesCol || c == kOnesCol + 1) ? 1.f : 0.f);
         for (int c = 0; c < P.e_dir; ++c)
           emb_put<kFmt>(my_emb, row, kDirCol0 + c,
                         (valid && !(P.mode & kModeSigmaOnly)) ? __ldg(xr + P.e_xyz + c) : 0.f);
+        for (int c = kDirCol0 + P.e_dir; c < kEmbCols; ++c) emb_put<kFmt>(my_emb, row, c, 0.f);
       }
-      for (int c = P.e_xyz; c < kDirCol0; ++c) emb_put<kFmt>(my_emb, row, c, 0.f);
-      for (int c = kDirCol0 + P.e_dir; c < kEmbCols; ++c) emb_put<kFmt>(my_emb, row, c, 0.f);
       fence_proxy_async_smem();
-      mbar_arrive(&M->emb_full[b]);
+      warp_arrive(&M->emb_full[b]);
+      if (prof) t_emb += clock64() - t_e0;
 
       uint32_t staged[64];
       float sig_acc = 0.f, sigma = 0.f, w_ray = 0.f;
 
       for (int u = 0; u < P.n_units; ++u) {
-        const Unit un = c_units[u];
-        mbar_wait(&M->d_full[b], ud & 1, 16 + u);
+        const int layer = c_units[u].layer, half = c_units[u].half;
+        timed_wait(&M->d_full[b], ud & 1, 16 + u, prof, w_dfull);
         ud++;
         tc_fence_after_sync();
-        const float* bias = blob + kBiasOff(un.layer) + un.half * 128;
-        const bool dump = P.dbg != nullptr && P.dbg_layer == un.layer && valid;
+        const long long t_u0 = prof ? clock64() : 0;
+        float* dbg_row = nullptr;
+        if constexpr (kDbg) {
+          if (P.dbg != nullptr && P.dbg_layer == layer && valid) dbg_row = P.dbg + p * 256 + half * 128;
+        }
 
-        if (un.layer <= kLFinal) {
-          // ------------------------------------------------ 256-wide layers
-          if (un.half == 0) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t v[32];
-              tmem_ld_x32(tD + 32 * c, v);
-              tmem_ld_wait();
-              if (c == 3) {
-                tc_fence_before_sync();
-                mbar_arrive(&M->d_empty[b]);
-              }
-              if (dump) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  float a = __uint_as_float(v[j]) + bias[32 * c + j];
-                  P.dbg[p * 256 + 32 * c + j] = un.layer < 8 ? fmaxf(a, 0.f) : a;
-                }
-              }
-              if (un.layer == 7)
-                bias_act_pack<kFmt, true, true>(v, bias + 32 * c, wsig + 32 * c, &staged[16 * c],
-                                                sig_acc);
-              else if (un.layer < 8)
-                bias_act_pack<kFmt, true, false>(v, bias + 32 * c, wsig, &staged[16 * c], sig_acc);
-              else
-                bias_act_pack<kFmt, false, false>(v, bias + 32 * c, wsig, &staged[16 * c], sig_acc);
-            }
-          } else {
-            // every MMA of this layer has retired: A may be overwritten
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_st16(tA + 16 * c, &staged[16 * c]);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t v[32], cur[16];
-              tmem_ld_x32(tD + 32 * c, v);
-              tmem_ld_wait();
-              if (c == 3) {
-                tc_fence_before_sync();
-                mbar_arrive(&M->d_empty[b]);
-              }
-              if (dump) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  float a = __uint_as_float(v[j]) + bias[32 * c + j];
-                  P.dbg[p * 256 + 128 + 32 * c + j] = un.layer < 8 ? fmaxf(a, 0.f) : a;
-                }
-              }
-              if (un.layer == 7)
-                bias_act_pack<kFmt, true, true>(v, bias + 32 * c, wsig + 128 + 32 * c, cur, sig_acc);
-              else if (un.layer < 8)
-                bias_act_pack<kFmt, true, false>(v, bias + 32 * c, wsig, cur, sig_acc);
-              else
-                bias_act_pack<kFmt, false, false>(v, bias + 32 * c, wsig, cur, sig_acc);
-              tmem_st16(tA + 64 + 16 * c, cur);
-            }
+        if (layer <= kLDir) {
+          // ------------------------------------------------ 256-wide layers and the dir layer
+          const int mode = layer == kLDir ? kEpiDirect : (half == 0 ? kEpiStage : kEpiFlush);
+          if (layer == 7)
+            epi_128<kFmt, true, true, kDbg>(mode, tD, tA, wsig + half * 128, staged, sig_acc,
+                                            &M->d_empty[b], dbg_row, skip, kDbg ? P.exp : 0);
+          else if (layer == kLFinal)
+            epi_128<kFmt, false, false, kDbg>(mode, tD, tA, wsig, staged, sig_acc, &M->d_empty[b],
+                                              dbg_row, skip, kDbg ? P.exp : 0);
+          else
+            epi_128<kFmt, true, false, kDbg>(mode, tD, tA, wsig, staged, sig_acc, &M->d_empty[b],
+                                             dbg_row, skip, kDbg ? P.exp : 0);
+          if (mode != kEpiStage) {
+            // A holds the next layer's full input
             tmem_st_wait();
             tc_fence_before_sync();
-            mbar_arrive(&M->a_full[b]);
+            warp_arrive(&M->a_full[b]);
+          }
+          if (prof) {
+            const long long dt = clock64() - t_u0;
+            t_units += dt;
+            if (mode == kEpiStage) t_stage += dt; else t_flush += dt;
+          }
 
-            if (un.layer == 7) {
-              // ---------------- sigma head + alpha composite (rendering.py:121-143)
-              sigma = softplus_ref(sig_acc + blob[kSigmaBOff]);
-              if (!raw_mode) {
-                const int s_first = (int)(tile_p0 % P.S);
-                const float alpha =
-                    valid ? 1.f - expf(-(delta * fmaxf(sigma + nz, 0.f))) : 0.f;
-                const float om = 1.f - alpha;
-                const int f0 = (valid && s == 0) ? 1 : 0;
-                // inclusive segmented product over the warp's 32 rows
-                float Pp = om;
-                int F = f0;
+          if (layer == 7 && half == 1) {
+            // ---------------- sigma head + alpha composite (rendering.py:121-143)
+            sigma = softplus_ref(sig_acc + blob[kSigmaBOff]);
+            const long long t_c0 = prof ? clock64() : 0;
+            if (!raw_mode) {
+              const int s_first = (int)(tile_p0 % P.S);
+              const float alpha = valid ? 1.f - expf(-(delta * fmaxf(sigma + nz, 0.f))) : 0.f;
+              const float om = 1.f - alpha;
+              const int f0 = (valid && s == 0) ? 1 : 0;
+              // inclusive segmented product over the warp's 32 rows
+              float Pp = om;
+              int F = f0;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                  const float pn = __shfl_up_sync(0xffffffffu, Pp, d);
-                  const int fn = __shfl_up_sync(0xffffffffu, F, d);
-                  if (lane >= d) {
-                    if (!F) Pp *= pn;
-                    F |= fn;
-                  }
-                }
-                float Pe = __shfl_up_sync(0xffffffffu, Pp, 1);
-                int Fe = __shfl_up_sync(0xffffffffu, F, 1);
-                if (lane == 0) {
-                  Pe = 1.f;
-                  Fe = 0;
-                }
-                if (lane == 31) {
-                  M->scan_p[b][q] = Pp;
-                  M->scan_f[b][q] = F;
-                }
-                group_sync(b);
-                // carry of the ray that straddles the previous tile boundary
-                float cin_T = 1.f, cin_d = 0.f;
-                if (t > 0) {
-                  const uint32_t par = b ? (uint32_t)(pair & 1) : (uint32_t)((pair - 1) & 1);
-                  mbar_wait(&M->carry_a[1 - b], par, 40);
-                  if (s_first != 0) {
-                    cin_T = M->carry_T[1 - b];
-                    cin_d = M->carry_depth[1 - b];
-                  }
-                }
-                float pre = cin_T;
-                for (int w2 = 0; w2 < q; ++w2)
-                  pre = M->scan_f[b][w2] ? M->scan_p[b][w2] : pre * M->scan_p[b][w2];
-                const float T = f0 ? 1.f : (Fe ? Pe : pre * Pe);
-                w_ray = alpha * T;
-                if (valid) P.weights[p] = w_ray;
-                // inclusive segmented sum of w*z for the depth map
-                float Sd = w_ray * z;
-                int F2 = f0;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                  const float sn = __shfl_up_sync(0xffffffffu, Sd, d);
-                  const int fn = __shfl_up_sync(0xffffffffu, F2, d);
-                  if (lane >= d) {
-                    if (!F2) Sd += sn;
-                    F2 |= fn;
-                  }
-                }
-                if (lane == 31) M->scan_d[b][q] = Sd;
-                group_sync(b);
-                float pre_d = cin_d;
-                for (int w2 = 0; w2 < q; ++w2)
-                  pre_d = M->scan_f[b][w2] ? M->scan_d[b][w2] : pre_d + M->scan_d[b][w2];
-                const float D_incl = F2 ? Sd : pre_d + Sd;
-                const bool ray_end = valid && (s == P.S - 1);
-                if (ray_end) P.depth[ray] = D_incl;
-                if (row == nvalid - 1) {
-                  M->carry_T[b] = ray_end ? 1.f : T * om;
-                  M->carry_depth[b] = ray_end ? 0.f : D_incl;
-                  mbar_arrive(&M->carry_a[b]);
+              for (int d = 1; d < 32; d <<= 1) {
+                const float pn = __shfl_up_sync(0xffffffffu, Pp, d);
+                const int fn = __shfl_up_sync(0xffffffffu, F, d);
+                if (lane >= d) {
+                  if (!F) Pp *= pn;
+                  F |= fn;
                 }
               }
-            }
-          }
-        } else if (un.layer == kLDir) {
-          // ------------------------------------------------ dir layer (128, ReLU)
+              float Pe = __shfl_up_sync(0xffffffffu, Pp, 1);
+              int Fe = __shfl_up_sync(0xffffffffu, F, 1);
+              if (lane == 0) {
+                Pe = 1.f;
+                Fe = 0;
+              }
+              if (lane == 31) {
+                M->scan_p[b][q] = Pp;
+                M->scan_f[b][q] = F;
+              }
+              group_sync(b);
+              // carry of the ray that straddles the previous tile boundary
+              float cin_T = 1.f, cin_d = 0.f;
+              if (t > 0) {
+                const uint32_t par = b ? (uint32_t)(pair & 1) : (uint32_t)((pair - 1) & 1);
+                mbar_wait(&M->carry_a[1 - b], par, 40);
+                if (s_first != 0) {
+                  cin_T = M->carry_T[1 - b];
+                  cin_d = M->carry_depth[1 - b];
+                }
+              }
+              float pre = cin_T;
+              for (int w2 = 0; w2 < q; ++w2)
+                pre = M->scan_f[b][w2] ? M->scan_p[b][w2] : pre * M->scan_p[b][w2];
+              const float T = f0 ? 1.f : (Fe ? Pe : pre * Pe);
+              w_ray = alpha * T;
+              if (valid) P.weights[p] = w_ray;
+              // inclusive segmented sum of w*z for the depth map
+              float Sd = w_ray * z;
+              int F2 = f0;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t v[32], cur[16];
-            tmem_ld_x32(tD + 32 * c, v);
-            tmem_ld_wait();
-            if (c == 3) {
-              tc_fence_before_sync();
-              mbar_arrive(&M->d_empty[b]);
+              for (int d = 1; d < 32; d <<= 1) {
+                const float sn = __shfl_up_sync(0xffffffffu, Sd, d);
+                const int fn = __shfl_up_sync(0xffffffffu, F2, d);
+                if (lane >= d) {
+                  if (!F2) Sd += sn;
+                  F2 |= fn;
+                }
+              }
+              if (lane == 31) M->scan_d[b][q] = Sd;
+              group_sync(b);
+              float pre_d = cin_d;
+              for (int w2 = 0; w2 < q; ++w2)
+                pre_d = M->scan_f[b][w2] ? M->scan_d[b][w2] : pre_d + M->scan_d[b][w2];
+              const float D_incl = F2 ? Sd : pre_d + Sd;
+              const bool ray_end = valid && (s == P.S - 1);
+              if (ray_end) P.depth[ray] = D_incl;
+              if (row == nvalid - 1) {
+                M->carry_T[b] = ray_end ? 1.f : T * om;
+                M->carry_depth[b] = ray_end ? 0.f : D_incl;
+                mbar_arrive(&M->carry_a[b]);
+              }
             }
-            if (dump) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                P.dbg[p * 256 + 32 * c + j] = fmaxf(__uint_as_float(v[j]) + bias[32 * c + j], 0.f);
-            }
-            bias_act_pack<kFmt, true, false>(v, bias + 32 * c, wsig, cur, sig_acc);
-            tmem_st16(tA + 16 * c, cur);
+            if (prof) t_comp += clock64() - t_c0;
           }
-          tmem_st_wait();
-          tc_fence_before_sync();
-          mbar_arrive(&M->a_full[b]);
         } else {
           // ------------------------------------------------ rgb layer (64, sigmoid)
           // the embedding buffer is dead (dir layer retired): reuse it as the
@@ -551,34 +708,41 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t v[32];
-            tmem_ld_x32(tD + 32 * c, v);
-            tmem_ld_wait();
+            if (!skip) {
+              tmem_ld_x32(tD + 32 * c, v);
+              tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0;
+            }
             if (c == 1) {
               tc_fence_before_sync();
-              mbar_arrive(&M->d_empty[b]);
+              warp_arrive(&M->d_empty[b]);
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float a = __uint_as_float(v[j]) + bias[32 * c + j];
+              const float a = __uint_as_float(v[j]);
               const float f = __fdividef(1.f, 1.f + __expf(-a));
               const int ch = 32 * c + j;
               if (raw_mode) {
-                if (valid && !(P.mode & kModeSigmaOnly)) P.raw[p * 65 + ch] = f;
+                if (valid && !skip && !(P.mode & kModeSigmaOnly)) P.raw[p * 65 + ch] = f;
               } else {
                 staging[row * 64 + (ch ^ (row & 31))] = w_ray * f;
               }
-              if (dump) P.dbg[p * 256 + ch] = f;
+              if constexpr (kDbg) {
+                if (dbg_row) dbg_row[ch] = f;
+              }
             }
           }
           if (raw_mode) {
-            if (valid) {
+            if (valid && !skip) {
               if (P.mode & kModeSigmaOnly)
                 P.raw[p] = sigma;
               else
                 P.raw[p * 65 + 64] = sigma;
             }
-            group_sync(b);  // staging/embedding buffer hand-over is uniform in both modes
           } else {
+            const long long t_r0 = prof ? clock64() : 0;
             group_sync(b);
             const int s_first = (int)(tile_p0 % P.S);
             const long long ray_first = tile_p0 / P.S;
@@ -610,11 +774,23 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
                   carry_out = tot;
               }
               M->carry_feat[b][cc] = carry_out;
-              mbar_arrive(&M->carry_b[b]);
+              warp_arrive(&M->carry_b[b]);
             }
+            if (prof) t_red += clock64() - t_r0;
           }
         }
       }
+    }
+    if (prof) {
+      long long* o = P.prof + 8 + 8 * b;
+      o[0] = clock64() - t_start;  // epilogue-thread lifetime
+      o[1] = w_dfull;              // blocked waiting for accumulators
+      o[2] = t_emb;                // embedding phases
+      o[3] = t_comp;               // sigma/alpha scan
+      o[4] = t_red;                // feature reduction
+      o[5] = t_units;              // all 128-wide layer epilogues (wake-up -> a_full/d_empty arrive)
+      o[6] = t_stage;              // ... of which first halves (drain to registers)
+      o[7] = t_flush;              // ... of which second halves / dir (drain + write A)
     }
   }
 
@@ -643,6 +819,30 @@ __global__ void pack_kernel(const __grid_constant__ PackParams P) {
     while (ci + 1 < P.n_chunks && c_chunks[ci + 1].offset <= byte) ++ci;
     const Chunk ch = c_chunks[ci];
     const int within = byte - ch.offset;
+    if (ch.kind == kKindBias) {
+      // interleaved K-major: [8-row group][K half][row in group] x 16 bytes
+      const int grp = within >> 8, khalf = (within >> 7) & 1, r = (within >> 4) & 7;
+      uint32_t out[4] = {0u, 0u, 0u, 0u};
+      if (khalf == (kBiasKhi >> 3)) {
+        const float bv = P.b[ch.layer][ch.row0 + grp * 8 + r];
+        float hi, lo;
+        if (P.fmt == 0) {
+          if (fabsf(bv) > 65504.f && P.status) atomicExch(P.status, 1);
+          hi = __half2float(__float2half_rn(fminf(fmaxf(bv, -65504.f), 65504.f)));
+          lo = __half2float(__float2half_rn(bv - hi));
+        } else {
+          hi = __bfloat162float(__float2bfloat16_rn(bv));
+          lo = __bfloat162float(__float2bfloat16_rn(bv - hi));
+        }
+        static_assert((kBiasKhi & 7) == 5, "bias hi/lo sit at elements 5 and 6 of the second K half");
+        const uint32_t w2 = P.fmt == 0 ? pack2<0, false>(0.f, hi) : pack2<1, false>(0.f, hi);  // elements 4,5
+        const uint32_t w3 = P.fmt == 0 ? pack2<0, false>(lo, 0.f) : pack2<1, false>(lo, 0.f);  // elements 6,7
+        out[2] = w2;
+        out[3] = w3;
+      }
+      *reinterpret_cast<uint4*>(P.img + byte) = make_uint4(out[0], out[1], out[2], out[3]);
+      continue;
+    }
     const int row = within >> 7;
     const int pos = (within & 127) >> 4;
     const int k0 = ((pos ^ (row & 7)) & 7) * 8;
@@ -698,6 +898,31 @@ int ensure_program(int e_xyz, int e_dir, cudaStream_t st, const Program** out) {
                                         cudaMemcpyHostToDevice, st));
     CRNERF_CUDA(cudaMemcpyToSymbolAsync(c_units, g_prog.units, sizeof(Unit) * kMaxUnits, 0,
                                         cudaMemcpyHostToDevice, st));
+    static uint32_t meta[kMaxChunks];
+    for (int i = 0; i < kMaxChunks; ++i)
+      meta[i] = i < g_prog.n_chunks ? ((uint32_t)g_prog.chunks[i].a_src | ((uint32_t)g_prog.chunks[i].a_k0 << 8) |
+                                       ((uint32_t)g_prog.chunks[i].nk << 16) |
+                                       (g_prog.chunks[i].kind == kKindBias ? 0x80u : 0u))
+                                    : 0u;
+    // mark the first chunk of each run of full activation slabs inside a unit (bits 24+: run length 4 or 2)
+    for (int u = 0; u < g_prog.n_units; ++u) {
+      const Unit& un = g_prog.units[u];
+      int j = 0;
+      while (j < un.nchunks) {
+        int run = 0;
+        while (j + run < un.nchunks && g_prog.chunks[un.chunk0 + j + run].a_src == kSrcAct &&
+               g_prog.chunks[un.chunk0 + j + run].nk == 4)
+          ++run;
+        const int take = run >= 4 ? 4 : (run >= 2 ? 2 : 0);
+        if (take) {
+          meta[un.chunk0 + j] |= (uint32_t)take << 24;
+          j += take;
+        } else {
+          ++j;
+        }
+      }
+    }
+    CRNERF_CUDA(cudaMemcpyToSymbolAsync(c_meta, meta, sizeof(meta), 0, cudaMemcpyHostToDevice, st));
     // the tables are read by every later launch on any stream of this device
     CRNERF_CUDA(cudaStreamSynchronize(st));
     g_prog_dev = dev;
@@ -753,7 +978,7 @@ int debug_program(int e_xyz, int e_dir, int32_t* out, int cap) {
   CRNERF_REQUIRE(out && e_xyz >= 3 && e_xyz <= kMaxExyz && e_dir >= 0 && e_dir <= kMaxEdir, "bad argument");
   Program p;
   build_program(e_xyz, e_dir, &p);
-  const int need = 3 + p.n_chunks * 10 + p.n_units * 7;
+  const int need = 3 + p.n_chunks * 11 + p.n_units * 7;
   CRNERF_REQUIRE(cap >= need, "buffer too small: need %d ints", need);
   int k = 0;
   out[k++] = p.n_chunks;
@@ -761,8 +986,8 @@ int debug_program(int e_xyz, int e_dir, int32_t* out, int cap) {
   out[k++] = p.image_bytes;
   for (int i = 0; i < p.n_chunks; ++i) {
     const Chunk& c = p.chunks[i];
-    const int v[10] = {c.offset, c.bytes, c.layer, c.rows, c.row0, c.wcol0, c.wcols, c.a_src, c.a_k0, c.nk};
-    for (int j = 0; j < 10; ++j) out[k++] = v[j];
+    const int v[11] = {c.offset, c.bytes, c.layer, c.rows, c.row0, c.wcol0, c.wcols, c.a_src, c.a_k0, c.nk, c.kind};
+    for (int j = 0; j < 11; ++j) out[k++] = v[j];
   }
   for (int i = 0; i < p.n_units; ++i) {
     const Unit& u = p.units[i];
@@ -793,8 +1018,10 @@ int launch_render(const RenderArgs& a, cudaStream_t st) {
   P.feature = a.feature;
   P.depth = a.depth;
   P.raw = a.raw;
-  P.dbg = g_dbg_buf;
+  P.dbg = g_dbg_layer >= 0 ? g_dbg_buf : nullptr;
   P.dbg_layer = g_dbg_layer;
+  P.prof = g_dbg_layer <= -2 ? reinterpret_cast<long long*>(g_dbg_buf) : nullptr;
+  P.exp = g_dbg_layer <= -2 ? (-2 - g_dbg_layer) : 0;  // -2: profile, -3: exp 1, -4: exp 2, -5: both
   P.n_points = a.n_points;
   P.S = a.n_samples > 0 ? a.n_samples : 1;
   P.n_freq_xyz = a.n_freq_xyz;
@@ -821,7 +1048,9 @@ int launch_render(const RenderArgs& a, cudaStream_t st) {
     P.pts_per_cta = rpc * S;
     grid = (int)((a.n_rays + rpc - 1) / rpc);
   }
-  auto kern = operand == 0 ? render_fused_kernel<0> : render_fused_kernel<1>;
+  const bool dbg = P.dbg != nullptr || P.prof != nullptr;
+  auto kern = operand == 0 ? (dbg ? render_fused_kernel<0, true> : render_fused_kernel<0, false>)
+                           : (dbg ? render_fused_kernel<1, true> : render_fused_kernel<1, false>);
   CRNERF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   kern<<<grid, kThreads, kSmemBytes, st>>>(P);
   count_launch();

@@ -200,8 +200,8 @@ int crnerf_style_apply(const crnerf_style_weights* w, const float* content, int6
  * point of later fused launches into dbg_buf (n_points x 256 floats); NULL disables. */
 int crnerf_debug_set(float* dbg_buf, int layer);
 /* debug (tests only, host-only, no GPU needed): the weight-chunk program of the
- * fused kernel as flat int32: [n_chunks, n_units, image_bytes, 10 ints per chunk
- * (offset, bytes, layer, rows, row0, wcol0, wcols, a_src, a_k0, nk), 7 ints per
+ * fused kernel as flat int32: [n_chunks, n_units, image_bytes, 11 ints per chunk
+ * (offset, bytes, layer, rows, row0, wcol0, wcols, a_src, a_k0, nk, kind), 7 ints per
  * unit (layer, half, n, chunk0, nchunks, first_of_layer, last_of_layer)].
  * Returns the number of ints written, or a negative crnerf_status. */
 int crnerf_debug_program(int e_xyz, int e_dir, int32_t* out_host, int cap);

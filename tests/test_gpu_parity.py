@@ -187,11 +187,16 @@ def test_sample_pdf_merge_matches_golden(name):
     u = g["rng"]["u"] if "u" in g["rng"] else torch.linspace(0, 1, ni)
     z_fine, z_new = ops().sample_pdf_merge(g["z_coarse"].cuda(), g["ref"]["weights_coarse"].cuda(),
                                            u.cuda(), ni, return_new=True)
-    zc, wc = g["z_coarse"].double(), g["ref"]["weights_coarse"].double()
+    # compare the UNSORTED draws element by element (a shifted draw may swap places with a
+    # neighbour in the merged array); the merge itself is checked exactly below
+    zc, wc = g["z_coarse"], g["ref"]["weights_coarse"]
     u2 = u if u.dim() == 2 else u.expand(zc.shape[0], ni)
-    new64 = oracle.sample_pdf(0.5 * (zc[:, :-1] + zc[:, 1:]), wc[:, 1:-1], ni, u=u2.double())
-    fine64 = torch.sort(torch.cat([zc, new64], 1), 1)[0]
-    close_where_conditioned(z_fine, g["z_fine"], fine64, "z_fine", rtol=2e-6, atol=2e-6)
+    new32 = oracle.sample_pdf(0.5 * (zc[:, :-1] + zc[:, 1:]), wc[:, 1:-1], ni, u=u2)
+    new64 = oracle.sample_pdf(0.5 * (zc.double()[:, :-1] + zc.double()[:, 1:]), wc.double()[:, 1:-1],
+                              ni, u=u2.double())
+    assert torch.equal(torch.sort(torch.cat([zc, new32], 1), 1)[0], g["z_fine"])   # oracle == golden
+    close_where_conditioned(z_new, new32, new64, "z_new", rtol=2e-6, atol=2e-6)
+    close(z_fine, g["z_fine"], "z_fine (loose: conditioning of near-empty bins)", rtol=0, atol=1e-3)
     # sortedness + multiset identity (exact): the merge is sort(cat(z_coarse, z_new))
     assert (z_fine[:, 1:] >= z_fine[:, :-1]).all()
     want = torch.sort(torch.cat([g["z_coarse"].cuda(), z_new], 1), 1)[0]

@@ -21,10 +21,10 @@ def get_program(e_xyz, e_dir):
     n = lib.crnerf_debug_program(e_xyz, e_dir, buf, 4096)
     assert n > 0
     nc, nu, image_bytes = buf[0], buf[1], buf[2]
-    ck = ["offset", "bytes", "layer", "rows", "row0", "wcol0", "wcols", "a_src", "a_k0", "nk"]
+    ck = ["offset", "bytes", "layer", "rows", "row0", "wcol0", "wcols", "a_src", "a_k0", "nk", "kind"]
     uk = ["layer", "half", "n", "chunk0", "nchunks", "first", "last"]
-    chunks = [dict(zip(ck, buf[3 + 10 * i: 13 + 10 * i])) for i in range(nc)]
-    base = 3 + 10 * nc
+    chunks = [dict(zip(ck, buf[3 + 11 * i: 14 + 11 * i])) for i in range(nc)]
+    base = 3 + 11 * nc
     units = [dict(zip(uk, buf[base + 7 * i: base + 7 * i + 7])) for i in range(nu)]
     return chunks, units, image_bytes
 
@@ -35,6 +35,7 @@ def emulate(p, x_xyz, x_dir, e_xyz, e_dir):
     emb = torch.zeros(n, 128, dtype=torch.float64)
     emb[:, :e_xyz] = x_xyz
     emb[:, 96:96 + e_dir] = x_dir
+    emb[:, 93:95] = 1.0          # the constant-one columns the bias chunks multiply
     act = torch.zeros(n, 256, dtype=torch.float64)
     acc = torch.zeros(n, 256, dtype=torch.float64)
     sigma = None
@@ -42,8 +43,18 @@ def emulate(p, x_xyz, x_dir, e_xyz, e_dir):
         key = LAYER_KEYS[u["layer"]]
         W, b = p[key + ".weight"].double(), p[key + ".bias"].double()
         d = torch.zeros(n, u["n"], dtype=torch.float64)
+        seen_bias = 0
         for c in chunks[u["chunk0"]: u["chunk0"] + u["nchunks"]]:
             assert c["layer"] == u["layer"] and c["rows"] == u["n"] and c["row0"] == u["half"] * 128
+            if c["kind"] == 1:
+                # bias chunk: one k-step over embedding columns 80..95; fp16(b) at K 13, the
+                # rounding remainder at K 14 (here: exact b at 13), ones at columns 93 / 94
+                assert c["a_src"] == 0 and c["a_k0"] == 5 and c["nk"] == 1 and c["bytes"] == c["rows"] * 32
+                wc = torch.zeros(c["rows"], 16, dtype=torch.float64)
+                wc[:, 13] = b[c["row0"]: c["row0"] + c["rows"]]
+                d += emb[:, 80:96] @ wc.t()
+                seen_bias += 1
+                continue
             assert c["nk"] == (c["wcols"] + 15) // 16 and c["bytes"] == c["rows"] * 128
             kk = c["nk"] * 16
             wc = torch.zeros(c["rows"], kk, dtype=torch.float64)
@@ -51,10 +62,11 @@ def emulate(p, x_xyz, x_dir, e_xyz, e_dir):
             src = emb if c["a_src"] == 0 else act
             a = src[:, c["a_k0"] * 16: c["a_k0"] * 16 + kk]
             d += a @ wc.t()
+        assert seen_bias == 1, "every unit carries exactly one bias chunk"
         acc[:, u["half"] * 128: u["half"] * 128 + u["n"]] = d
         if u["last"]:
             width = W.shape[0]
-            y = acc[:, :width] + b
+            y = acc[:, :width]
             if u["layer"] < 8 or u["layer"] == 9:
                 y = torch.relu(y)
             if u["layer"] == 7:
@@ -77,6 +89,8 @@ def test_program_covers_every_weight_once():
     for c in chunks:
         assert c["offset"] == off and c["offset"] % 16 == 0
         off += c["bytes"]
+        if c["kind"] == 1:
+            continue
         cover[c["layer"]][c["row0"]: c["row0"] + c["rows"], c["wcol0"]: c["wcol0"] + c["wcols"]] += 1
     for l, cv in enumerate(cover):
         assert int(cv.min()) == 1 and int(cv.max()) == 1, f"layer {l} not covered exactly once"

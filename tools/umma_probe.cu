@@ -37,6 +37,9 @@ struct Params {
   float* d_out;           // 128 x N fp32 row-major
   long long* cycles;      // [0] = cycles for the timed MMA loop
   int mode, N, K, fmt, reps, dcol;
+  int grid;
+  int commit_every;  // extra tcgen05.commit to a scratch mbarrier every n MMAs (0 = never)
+  int alt;           // alternate between two accumulators every 16 MMAs
 };
 
 __global__ void __launch_bounds__(160, 1) probe_kernel(Params p) {
@@ -53,6 +56,7 @@ __global__ void __launch_bounds__(160, 1) probe_kernel(Params p) {
   if (threadIdx.x == 0) {
     mbar_init(&bars[0], 1);  // bulk copy landed
     mbar_init(&bars[1], 1);  // MMA done
+    mbar_init(&bars[2], 1);  // scratch target of the extra commits
     fence_mbar_init();
   }
   if (warp == 4) tmem_alloc<512>(tmem_slot);
@@ -95,7 +99,9 @@ __global__ void __launch_bounds__(160, 1) probe_kernel(Params p) {
       const uint32_t idesc = make_idesc_f16(128, p.N, p.fmt);
       const uint32_t sbo = 1024;
       long long t0 = clock64();
+      int issued = 0;
       for (int r = 0; r < p.reps; ++r) {
+        const uint32_t d_tmem = (p.alt && (r & 1)) ? tmem + p.dcol + 128 : tmem + p.dcol;
         for (int ks = 0; ks < p.K / 16; ++ks) {
           const int slab = ks / 4, kin = ks % 4;
           uint64_t bdesc = make_sdesc_k_sw128(smem_u32(sB + slab * p.N * 128) + kin * 32, sbo);
@@ -107,12 +113,14 @@ __global__ void __launch_bounds__(160, 1) probe_kernel(Params p) {
             uint64_t adesc = make_sdesc_k_sw128(smem_u32(sA + slab * 16384) + kin * 32, sbo);
             umma_ss(d_tmem, adesc, bdesc, idesc, acc);
           }
+          if (++issued == p.commit_every) { umma_commit(&bars[2]); issued = 0; }
+          if (blockIdx.x == 0 && r < 3) p.cycles[256 + r * 16 + ks] = clock64() - t0;
         }
       }
       umma_commit(&bars[1]);
       mbar_wait(&bars[1], 0, 2);
       long long t1 = clock64();
-      p.cycles[0] = t1 - t0;
+      p.cycles[blockIdx.x] = t1 - t0;
     }
     __syncwarp();
   }
@@ -124,8 +132,10 @@ __global__ void __launch_bounds__(160, 1) probe_kernel(Params p) {
       uint32_t v[32];
       tmem_ld_x32(d_tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
       tmem_ld_wait();
+      if (blockIdx.x == 0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) p.d_out[row * p.N + c0 + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) p.d_out[row * p.N + c0 + j] = __uint_as_float(v[j]);
+      }
     }
   }
   tc_fence_before_sync();
@@ -169,6 +179,9 @@ int main(int argc, char** argv) {
   int fmt = argc > 4 ? atoi(argv[4]) : 0;
   int reps = argc > 5 ? atoi(argv[5]) : 1;
   int dcol = argc > 6 ? atoi(argv[6]) : 0;
+  int grid = argc > 7 ? atoi(argv[7]) : 1;
+  int commit_every = argc > 8 ? atoi(argv[8]) : 0;
+  int alt = argc > 9 ? atoi(argv[9]) : 0;
   const int M = 128;
   if (K % 64 || K > 256 || N % 16 || N > 256 || dcol + N > 384) {
     printf("bad args\n");
@@ -213,7 +226,7 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&db, b_img.size()));
   CK(cudaMalloc(&darm, a_rm.size() * 2));
   CK(cudaMalloc(&dd, M * N * 4));
-  CK(cudaMalloc(&dc, 64));
+  CK(cudaMalloc(&dc, 8 * 1024));
   CK(cudaMemcpy(da, a_img.data(), a_img.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(db, b_img.data(), b_img.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(darm, a_rm.data(), a_rm.size() * 2, cudaMemcpyHostToDevice));
@@ -229,9 +242,12 @@ int main(int argc, char** argv) {
   p.fmt = fmt;
   p.reps = reps;
   p.dcol = dcol;
+  p.grid = grid;
+  p.commit_every = commit_every;
+  p.alt = alt;
   size_t smem = kslabs * 16384 + kslabs * N * 128 + 1024;
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  probe_kernel<<<1, 160, smem>>>(p);
+  probe_kernel<<<grid, 160, smem>>>(p);
   CK(cudaGetLastError());
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
@@ -244,7 +260,11 @@ int main(int argc, char** argv) {
   std::vector<float> out(M * N);
   long long cyc = 0;
   CK(cudaMemcpy(out.data(), dd, M * N * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost));
+  {
+    std::vector<long long> cy(grid);
+    CK(cudaMemcpy(cy.data(), dc, 8 * grid, cudaMemcpyDeviceToHost));
+    for (auto v : cy) cyc = v > cyc ? v : cyc;   // slowest CTA
+  }
   double maxerr = 0;
   int bad = 0;
   for (int i = 0; i < M * N; ++i) {
@@ -253,8 +273,15 @@ int main(int argc, char** argv) {
     if (!(d == 0)) bad++;
   }
   int nmma = reps * (K / 16);
-  printf("probe mode=%d N=%d K=%d fmt=%d dcol=%d reps=%d: max_abs_err=%g mismatches=%d/%d  cycles=%lld (%.1f per MMA)  %s\n",
-         mode, N, K, fmt, dcol, reps, maxerr, bad, M * N, cyc, double(cyc) / nmma,
+  if (reps >= 3 && K == 256) {
+    std::vector<long long> ts(48);
+    CK(cudaMemcpy(ts.data(), dc + 256, 8 * 48, cudaMemcpyDeviceToHost));
+    printf("issue timestamps (cycles since start) of the first 48 MMAs:");
+    for (int i = 0; i < 48; ++i) printf(" %lld", ts[i]);
+    printf("\n");
+  }
+  printf("probe commit_every=%d alt=%d grid=%d mode=%d N=%d K=%d fmt=%d dcol=%d reps=%d: max_abs_err=%g mismatches=%d/%d  cycles=%lld (%.1f per MMA)  %s\n",
+         commit_every, alt, grid, mode, N, K, fmt, dcol, reps, maxerr, bad, M * N, cyc, double(cyc) / nmma,
          bad == 0 ? "OK" : "FAIL");
   if (bad && bad < M * N) {
     int shown = 0;
