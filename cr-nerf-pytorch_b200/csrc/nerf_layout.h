@@ -96,13 +96,10 @@ struct Program {
   int32_t e_xyz, e_dir;
 };
 
-// fp32 side blob: biases of the 11 tensor-core layers, sigma head weights + bias
-CRNERF_HD constexpr int kBiasOff(int layer) {
-  return layer < 8 ? layer * 256 : layer == kLFinal ? 2048 : layer == kLDir ? 2304 : 2432;
-}
-constexpr int kSigmaWOff = 2496;
-constexpr int kSigmaBOff = 2752;
-constexpr int kBlobFloats = 2760;
+// fp32 side blob: sigma head weights (256) + bias; everything else is in the weight image
+constexpr int kSigmaWOff = 0;
+constexpr int kSigmaBOff = 256;
+constexpr int kBlobFloats = 264;
 
 // Index of each layer's tensors in the caller-provided pointer arrays
 // (crnerf_mlp_weights_t): xyz_encoding_1..8, xyz_encoding_final, dir_encoding,

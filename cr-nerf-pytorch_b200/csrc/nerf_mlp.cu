@@ -45,7 +45,7 @@ namespace {
 constexpr int kSlots = 8;
 constexpr int kSlotBytes = 16384;
 constexpr int kEmbBufBytes = 32768;
-constexpr int kThreads = 384;
+constexpr int kThreads = 640;        // 4 control warps + 2 tile groups x 8 epilogue warps
 constexpr int kMaxSeg = 10;  // ray segments per 128-row tile (n_samples >= 16)
 
 constexpr int kRingOff = 0;
@@ -65,7 +65,9 @@ struct Misc {
   float carry_T[2];
   float carry_depth[2];
   float carry_feat[2][64];
-  float part[2][2][kMaxSeg][64];
+  float sig_part[2][128];  // sigma-head partial sums of the second column-half warps
+  float wray[2][128];      // per-row composite weights for the second column-half warps
+  float part[2][4][kMaxSeg][64];
 };
 constexpr int kSmemBytes = kMiscOff + (int)sizeof(Misc);
 static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
@@ -117,8 +119,19 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
   if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
 
+// named barriers: 1+b all 256 threads of tile group b; 3+b its 128 "column-half 0" threads;
+// 5+b / 7+b producer-consumer pairs between the two column halves (arrive + sync = 256)
 __device__ __forceinline__ void group_sync(int b) {
-  asm volatile("bar.sync %0, 128;" ::"r"(1 + b) : "memory");
+  asm volatile("bar.sync %0, 256;" ::"r"(1 + b) : "memory");
+}
+__device__ __forceinline__ void half_sync(int b) {
+  asm volatile("bar.sync %0, 128;" ::"r"(3 + b) : "memory");
+}
+__device__ __forceinline__ void pc_arrive(int id) {
+  asm volatile("bar.arrive %0, 256;" ::"r"(id) : "memory");
+}
+__device__ __forceinline__ void pc_sync(int id) {
+  asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory");
 }
 
 template <int kFmt>
@@ -178,7 +191,8 @@ __device__ __forceinline__ float emb_col(const EmbIn& e, int c) {
   return r < 3 ? __sinf(a) : __cosf(a);
 }
 // 8*kNChunks consecutive columns -> kNChunks 16-byte stores into the swizzled buffer
-template <int kFmt, int kNFreq, int kChunk0, int kNChunks>
+// embedding-column chunks [kSrc0, kSrc0+kNChunks) -> buffer chunks [kDst0, ...)
+template <int kFmt, int kNFreq, bool kOnes, int kSrc0, int kDst0, int kNChunks>
 __device__ __forceinline__ void emb_write(uint8_t* buf, uint32_t row_off, uint32_t row_xor,
                                           const EmbIn& e) {
 #pragma unroll
@@ -186,9 +200,9 @@ __device__ __forceinline__ void emb_write(uint8_t* buf, uint32_t row_off, uint32
     uint32_t w[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      w[q] = pack2<kFmt, false>(emb_col<kNFreq, kChunk0 == 0>(e, 8 * m + 2 * q),
-                                emb_col<kNFreq, kChunk0 == 0>(e, 8 * m + 2 * q + 1));
-    const uint32_t cm = kChunk0 + m;
+      w[q] = pack2<kFmt, false>(emb_col<kNFreq, kOnes>(e, 8 * (kSrc0 + m) + 2 * q),
+                                emb_col<kNFreq, kOnes>(e, 8 * (kSrc0 + m) + 2 * q + 1));
+    const uint32_t cm = kDst0 + m;
     const uint32_t off = (cm >> 3) * 16384u + row_off + (((cm & 7u) << 4) ^ row_xor);
     *reinterpret_cast<uint4*>(buf + off) = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -219,25 +233,28 @@ __device__ __forceinline__ float softplus_ref(float x) {
   return x > 20.f ? x : log1pf(expf(x));
 }
 
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
-      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),
-      "r"(v[15])
-      : "memory");
-}
+// Epilogue of one warp's 64 accumulator columns (bias already inside, see nerf_layout.h):
+// one tcgen05.ld.x64, optional ReLU, pack to 32 words.  kSigma additionally accumulates
+// this warp's share of the fp32 sigma-head dot product of the layer-8 activations.
+//   kEpiStage : first half of a 256-wide layer - keep the packed words in `staged`
+//               (A is still being read by the layer's second half);
+//   kEpiFlush : second half - write the staged words and this half's words to A;
+//   kEpiDirect: dir layer - write straight to A columns [0,64).
+enum : int { kEpiStage = 0, kEpiFlush = 1, kEpiDirect = 2 };
 
-// One 16-column slice of an accumulator (bias already inside, see nerf_layout.h):
-// optional ReLU + pack to 8 words.  kSigma additionally accumulates the fp32
-// sigma-head dot product of the layer-8 activations.
-template <int kFmt, bool kRelu, bool kSigma>
-__device__ __forceinline__ void act_pack16(const uint32_t (&v)[16], const float* wsig, uint32_t* out,
-                                           float& sig_acc) {
+template <int kFmt, bool kRelu, bool kSigma, bool kDbg, int kOff, int kN>
+__device__ __forceinline__ void epi_slice32(const uint32_t (&v)[32], const float* wsig,
+                                            uint32_t (&out)[kN], float& sig_acc, float* dbg) {
+  if constexpr (kDbg) {
+    if (dbg) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        dbg[j] = kRelu ? fmaxf(__uint_as_float(v[j]), 0.f) : __uint_as_float(v[j]);
+    }
+  }
   if constexpr (kSigma) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 8; ++j) {
       const float4 ws = *reinterpret_cast<const float4*>(wsig + 4 * j);
       sig_acc = fmaf(fmaxf(__uint_as_float(v[4 * j]), 0.f), ws.x, sig_acc);
       sig_acc = fmaf(fmaxf(__uint_as_float(v[4 * j + 1]), 0.f), ws.y, sig_acc);
@@ -246,75 +263,53 @@ __device__ __forceinline__ void act_pack16(const uint32_t (&v)[16], const float*
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    out[j] = pack2<kFmt, kRelu>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+  for (int j = 0; j < 16; ++j)
+    out[kOff + j] = pack2<kFmt, kRelu>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
 }
 
-// Epilogue of one 128-wide accumulator.  kMode 0: first half of a 256-wide layer - keep
-// the packed result in `staged` (A is still being read by the layer's second half);
-// kMode 1: second half - write the staged half and this one to A columns [0,128);
-// kMode 2: dir layer - write straight to A columns [0,64).
-// The accumulator is drained in eight 16-column slices, software-pipelined over two
-// register buffers: the tcgen05.ld of slice c+1 is in flight while slice c is processed.
-enum : int { kEpiStage = 0, kEpiFlush = 1, kEpiDirect = 2 };
-
 template <int kFmt, bool kRelu, bool kSigma, bool kDbg>
-__device__ __forceinline__ void epi_128(int mode, uint32_t tD, uint32_t tA, const float* wsig,
-                                        uint32_t (&staged)[64], float& sig_acc, uint64_t* d_empty,
-                                        float* dbg_row, bool skip, int exp = 0) {
+__device__ __forceinline__ void epi_64(int mode, int ch, uint32_t tD, uint32_t tA, const float* wsig,
+                                       uint32_t (&staged)[32], float& sig_acc, uint64_t* d_empty,
+                                       float* dbg_row, bool skip) {
   if (kDbg && skip) {
     tc_fence_before_sync();
     warp_arrive(d_empty);
     return;
   }
-  uint32_t va[16], vb[16];
-  if (kDbg && (exp & 16)) {  // experiment: no TMEM loads at all
-#pragma unroll
-    for (int j = 0; j < 16; ++j) va[j] = vb[j] = 0;
-  } else {
-    tmem_ld_x16(tD, va);
+  // Two 32-column loads, the second in flight while the first slice is packed (one x64
+  // load next to the 32 staged words does not fit the epilogue warps' register budget).
+  // In flush mode every MMA of the layer has retired, so the staged first half may
+  // overwrite A right away.
+  float* dbg = kDbg && dbg_row ? dbg_row + 64 * ch : nullptr;
+  if (mode == kEpiStage) {
+    // the 32 staged words stay live, so use one 32-register buffer sequentially
+    uint32_t v[32];
+    tmem_ld_x32(tD + 64 * ch, v);
+    tmem_ld_wait();
+    epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 32>(v, wsig + 64 * ch, staged, sig_acc, dbg);
+    tmem_ld_x32(tD + 64 * ch + 32, v);
+    tmem_ld_wait();
+    tc_fence_before_sync();
+    warp_arrive(d_empty);  // accumulator drained: the issuer may overwrite it
+    epi_slice32<kFmt, kRelu, kSigma, kDbg, 16, 32>(v, wsig + 64 * ch + 32, staged, sig_acc,
+                                                   dbg ? dbg + 32 : nullptr);
+    return;
   }
-  if (mode == kEpiFlush) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) tmem_st16(tA + 16 * c, &staged[16 * c]);
-  }
-  const uint32_t a_col0 = mode == kEpiFlush ? 64u : 0u;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    if (!(kDbg && (exp & 16))) tmem_ld_wait();
-    if (c < 7) {
-      if (!(kDbg && (exp & 16))) {
-        if (c & 1)
-          tmem_ld_x16(tD + 16 * (c + 1), va);
-        else
-          tmem_ld_x16(tD + 16 * (c + 1), vb);
-      }
-    } else {  // accumulator drained: the issuer may overwrite it
-      tc_fence_before_sync();
-      warp_arrive(d_empty);
-    }
-    uint32_t(&v)[16] = (c & 1) ? vb : va;
-    if constexpr (kDbg) {
-      if (dbg_row) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = __uint_as_float(v[j]);
-          dbg_row[16 * c + j] = kRelu ? fmaxf(a, 0.f) : a;
-        }
-      }
-    }
-    if (kDbg && (exp & 8)) {  // experiment: loads only
-      sig_acc += __uint_as_float(v[0]);
-      continue;
-    }
-    if (mode == kEpiStage) {
-      act_pack16<kFmt, kRelu, kSigma>(v, wsig + 16 * c, &staged[8 * c], sig_acc);
-    } else {
-      uint32_t cur[8];
-      act_pack16<kFmt, kRelu, kSigma>(v, wsig + 16 * c, cur, sig_acc);
-      tmem_st_x8(tA + a_col0 + 8 * c, cur);
-    }
-  }
+  // flush / direct: the staged words leave first (frees their registers), then two loads
+  // with the second in flight while the first slice is packed and stored
+  if (mode == kEpiFlush) tmem_st_x32(tA + 32 * ch, staged);
+  const uint32_t a_dst = tA + (mode == kEpiFlush ? 64 : 0) + 32 * ch;
+  uint32_t va[32], vb[32], out[16];
+  tmem_ld_x32(tD + 64 * ch, va);
+  tmem_ld_wait();
+  tmem_ld_x32(tD + 64 * ch + 32, vb);
+  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 16>(va, wsig + 64 * ch, out, sig_acc, dbg);
+  tmem_st_x16p(a_dst, out);
+  tmem_ld_wait();
+  tc_fence_before_sync();
+  warp_arrive(d_empty);  // accumulator drained: the issuer may overwrite it
+  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 16>(vb, wsig + 64 * ch + 32, out, sig_acc, dbg ? dbg + 32 : nullptr);
+  tmem_st_x16p(a_dst + 16, out);
 }
 
 template <int kFmt, bool kDbg>
@@ -341,10 +336,10 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
     for (int b = 0; b < 2; ++b) {
       // epilogue-side barriers take ONE arrival per warp (an elected lane after the warp's
       // collective tcgen05.wait / __syncwarp): a 32-lane arrive is 32 serialized smem atomics
-      mbar_init(&M->emb_full[b], 4);
-      mbar_init(&M->a_full[b], 4);
+      mbar_init(&M->emb_full[b], 8);
+      mbar_init(&M->a_full[b], 8);
       mbar_init(&M->d_full[b], 1);
-      mbar_init(&M->d_empty[b], 4);
+      mbar_init(&M->d_empty[b], 8);
       mbar_init(&M->carry_a[b], 1);
       mbar_init(&M->carry_b[b], 2);
     }
@@ -356,6 +351,11 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = M->tmem_base;
+
+  // register rebalancing inside the CTA's launch allocation (640 threads x 96 registers =
+  // 61,440; setmaxnreg cannot draw from outside it): 4 control warps x 64 + 16 epilogue
+  // warps x 104 = 61,440 exactly
+  if (warp < 4) setmaxnreg_dec_64(); else setmaxnreg_inc_104();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
@@ -502,10 +502,13 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
     __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int b = (warp - 4) >> 2;
-    const int q = warp & 3;
+    // tile group b (8 warps): warp gw owns TMEM lane quarter q = gw & 3 (rows 32q..32q+31,
+    // one row per lane) and column half ch = gw >> 2 of every 128-wide accumulator.
+    const int b = (warp - 4) >> 3;
+    const int gw = (warp - 4) & 7;
+    const int q = gw & 3, ch = gw >> 2;
     const int row = q * 32 + lane;
-    const int gtid = tid - 128 - b * 128;  // 0..127 inside the group (== row)
+    const int gtid = gw * 32 + lane;  // 0..255 inside the group
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t tA = tmem + (b ? 256u : 0u) + lane_off;
     const uint32_t tD = tmem + (b ? 384u : 128u) + lane_off;
@@ -530,21 +533,16 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       const long long p = tile_p0 + row;
       const bool valid = row < nvalid;
 
-      // ---- tile inputs + embedding -> smem (A operand of layers 1, 5 and dir)
+      // ---- tile inputs + embedding -> smem (A operand of layers 1, 5, dir and of every
+      // bias k-step).  Column half 0 writes buffer columns 0..63, half 1 columns 64..127.
       const long long t_e0 = prof ? clock64() : 0;
-      float z = 0.f, delta = 0.f, nz = 0.f;
-      int s = 0;
-      long long ray = 0;
       if (ray_mode) {
         EmbIn ex, ed;
         ex.v[0] = ex.v[1] = ex.v[2] = 0.f;
         ed.v[0] = ed.v[1] = ed.v[2] = 0.f;
         if (valid) {
-          ray = p / P.S;
-          s = (int)(p - ray * P.S);
-          z = __ldg(P.z_vals + p);
-          delta = (s + 1 < P.S) ? __fsub_rn(__ldg(P.z_vals + p + 1), z) : 1e2f;
-          nz = P.noise ? __ldg(P.noise + p) : 0.f;
+          const long long ray = p / P.S;
+          const float z = __ldg(P.z_vals + p);
           const float4 r0 = __ldg(reinterpret_cast<const float4*>(P.rays + ray * 8));
           const float4 r1 = __ldg(reinterpret_cast<const float4*>(P.rays + ray * 8) + 1);
           // xyz = o + d*z with separate roundings, as the reference's broadcast
@@ -562,31 +560,41 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
             ed.v[2] = r1.y;
           }
         }
-        if (fast_emb && emb_fast_ok(ex) && emb_fast_ok(ed)) {
+        // warp-uniform choice so both halves of a row agree on the path
+        const bool fast = fast_emb && __all_sync(0xffffffffu, emb_fast_ok(ex) && emb_fast_ok(ed));
+        if (fast) {
           emb_prepare(ex);
-          emb_prepare(ed);
-          emb_write<kFmt, 15, 0, 12>(my_emb, row_off, row_xor, ex);   // columns 0..95
-          emb_write<kFmt, 4, 12, 4>(my_emb, row_off, row_xor, ed);    // columns 96..127
-        } else {
+          if (ch == 0) {
+            emb_write<kFmt, 15, true, 0, 0, 8>(my_emb, row_off, row_xor, ex);    // columns 0..63
+          } else {
+            emb_prepare(ed);
+            emb_write<kFmt, 15, true, 8, 8, 4>(my_emb, row_off, row_xor, ex);    // columns 64..95
+            emb_write<kFmt, 4, false, 0, 12, 4>(my_emb, row_off, row_xor, ed);   // columns 96..127
+          }
+        } else if (ch == 0) {
           embed3_generic<kFmt>(my_emb, row, 0, kDirCol0, ex.v[0], ex.v[1], ex.v[2], P.n_freq_xyz);
+        } else {
           embed3_generic<kFmt>(my_emb, row, kDirCol0, kEmbCols, ed.v[0], ed.v[1], ed.v[2],
                                P.n_freq_dir);
         }
       } else {
         const float* xr = P.x + p * P.x_stride;
-        for (int c = 0; c < P.e_xyz; ++c) emb_put<kFmt>(my_emb, row, c, valid ? __ldg(xr + c) : 0.f);
-        for (int c = P.e_xyz; c < kDirCol0; ++c)
-          emb_put<kFmt>(my_emb, row, c, (c == kOnesCol || c == kOnesCol + 1) ? 1.f : 0.f);
-        for (int c = 0; c < P.e_dir; ++c)
-          emb_put<kFmt>(my_emb, row, kDirCol0 + c,
-                        (valid && !(P.mode & kModeSigmaOnly)) ? __ldg(xr + P.e_xyz + c) : 0.f);
-        for (int c = kDirCol0 + P.e_dir; c < kEmbCols; ++c) emb_put<kFmt>(my_emb, row, c, 0.f);
+        if (ch == 0) {
+          for (int c = 0; c < P.e_xyz; ++c) emb_put<kFmt>(my_emb, row, c, valid ? __ldg(xr + c) : 0.f);
+          for (int c = P.e_xyz; c < kDirCol0; ++c)
+            emb_put<kFmt>(my_emb, row, c, (c == kOnesCol || c == kOnesCol + 1) ? 1.f : 0.f);
+        } else {
+          for (int c = 0; c < P.e_dir; ++c)
+            emb_put<kFmt>(my_emb, row, kDirCol0 + c,
+                          (valid && !(P.mode & kModeSigmaOnly)) ? __ldg(xr + P.e_xyz + c) : 0.f);
+          for (int c = kDirCol0 + P.e_dir; c < kEmbCols; ++c) emb_put<kFmt>(my_emb, row, c, 0.f);
+        }
       }
       fence_proxy_async_smem();
       warp_arrive(&M->emb_full[b]);
       if (prof) t_emb += clock64() - t_e0;
 
-      uint32_t staged[64];
+      uint32_t staged[32];
       float sig_acc = 0.f, sigma = 0.f, w_ray = 0.f;
 
       for (int u = 0; u < P.n_units; ++u) {
@@ -604,14 +612,14 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
           // ------------------------------------------------ 256-wide layers and the dir layer
           const int mode = layer == kLDir ? kEpiDirect : (half == 0 ? kEpiStage : kEpiFlush);
           if (layer == 7)
-            epi_128<kFmt, true, true, kDbg>(mode, tD, tA, wsig + half * 128, staged, sig_acc,
-                                            &M->d_empty[b], dbg_row, skip, kDbg ? P.exp : 0);
+            epi_64<kFmt, true, true, kDbg>(mode, ch, tD, tA, wsig + half * 128, staged, sig_acc,
+                                           &M->d_empty[b], dbg_row, skip);
           else if (layer == kLFinal)
-            epi_128<kFmt, false, false, kDbg>(mode, tD, tA, wsig, staged, sig_acc, &M->d_empty[b],
-                                              dbg_row, skip, kDbg ? P.exp : 0);
+            epi_64<kFmt, false, false, kDbg>(mode, ch, tD, tA, wsig, staged, sig_acc, &M->d_empty[b],
+                                             dbg_row, skip);
           else
-            epi_128<kFmt, true, false, kDbg>(mode, tD, tA, wsig, staged, sig_acc, &M->d_empty[b],
-                                             dbg_row, skip, kDbg ? P.exp : 0);
+            epi_64<kFmt, true, false, kDbg>(mode, ch, tD, tA, wsig, staged, sig_acc, &M->d_empty[b],
+                                            dbg_row, skip);
           if (mode != kEpiStage) {
             // A holds the next layer's full input
             tmem_st_wait();
@@ -625,133 +633,151 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
           }
 
           if (layer == 7 && half == 1) {
-            // ---------------- sigma head + alpha composite (rendering.py:121-143)
-            sigma = softplus_ref(sig_acc + blob[kSigmaBOff]);
+            // ---------------- sigma head + alpha composite (rendering.py:121-143), done by
+            // the column-half-0 warps (one thread per row); half 1 hands over its partial dot
             const long long t_c0 = prof ? clock64() : 0;
-            if (!raw_mode) {
-              const int s_first = (int)(tile_p0 % P.S);
-              const float alpha = valid ? 1.f - expf(-(delta * fmaxf(sigma + nz, 0.f))) : 0.f;
-              const float om = 1.f - alpha;
-              const int f0 = (valid && s == 0) ? 1 : 0;
-              // inclusive segmented product over the warp's 32 rows
-              float Pp = om;
-              int F = f0;
+            if (ch == 1) {
+              M->sig_part[b][row] = sig_acc;
+              pc_arrive(7 + b);
+            } else {
+              pc_sync(7 + b);
+              sigma = softplus_ref(sig_acc + M->sig_part[b][row] + blob[kSigmaBOff]);
+              if (!raw_mode) {
+                // per-row ray state is (re)loaded here rather than carried through the layers
+                const long long ray = valid ? p / P.S : 0;
+                const int s = valid ? (int)(p - ray * P.S) : 0;
+                const float z = valid ? __ldg(P.z_vals + p) : 0.f;
+                const float delta =
+                    valid ? ((s + 1 < P.S) ? __fsub_rn(__ldg(P.z_vals + p + 1), z) : 1e2f) : 0.f;
+                const float nz = (valid && P.noise) ? __ldg(P.noise + p) : 0.f;
+                const int s_first = (int)(tile_p0 % P.S);
+                const float alpha = valid ? 1.f - expf(-(delta * fmaxf(sigma + nz, 0.f))) : 0.f;
+                const float om = 1.f - alpha;
+                const int f0 = (valid && s == 0) ? 1 : 0;
+                // inclusive segmented product over the warp's 32 rows
+                float Pp = om;
+                int F = f0;
 #pragma unroll
-              for (int d = 1; d < 32; d <<= 1) {
-                const float pn = __shfl_up_sync(0xffffffffu, Pp, d);
-                const int fn = __shfl_up_sync(0xffffffffu, F, d);
-                if (lane >= d) {
-                  if (!F) Pp *= pn;
-                  F |= fn;
+                for (int d = 1; d < 32; d <<= 1) {
+                  const float pn = __shfl_up_sync(0xffffffffu, Pp, d);
+                  const int fn = __shfl_up_sync(0xffffffffu, F, d);
+                  if (lane >= d) {
+                    if (!F) Pp *= pn;
+                    F |= fn;
+                  }
                 }
-              }
-              float Pe = __shfl_up_sync(0xffffffffu, Pp, 1);
-              int Fe = __shfl_up_sync(0xffffffffu, F, 1);
-              if (lane == 0) {
-                Pe = 1.f;
-                Fe = 0;
-              }
-              if (lane == 31) {
-                M->scan_p[b][q] = Pp;
-                M->scan_f[b][q] = F;
-              }
-              group_sync(b);
-              // carry of the ray that straddles the previous tile boundary
-              float cin_T = 1.f, cin_d = 0.f;
-              if (t > 0) {
-                const uint32_t par = b ? (uint32_t)(pair & 1) : (uint32_t)((pair - 1) & 1);
-                mbar_wait(&M->carry_a[1 - b], par, 40);
-                if (s_first != 0) {
-                  cin_T = M->carry_T[1 - b];
-                  cin_d = M->carry_depth[1 - b];
+                float Pe = __shfl_up_sync(0xffffffffu, Pp, 1);
+                int Fe = __shfl_up_sync(0xffffffffu, F, 1);
+                if (lane == 0) {
+                  Pe = 1.f;
+                  Fe = 0;
                 }
-              }
-              float pre = cin_T;
-              for (int w2 = 0; w2 < q; ++w2)
-                pre = M->scan_f[b][w2] ? M->scan_p[b][w2] : pre * M->scan_p[b][w2];
-              const float T = f0 ? 1.f : (Fe ? Pe : pre * Pe);
-              w_ray = alpha * T;
-              if (valid) P.weights[p] = w_ray;
-              // inclusive segmented sum of w*z for the depth map
-              float Sd = w_ray * z;
-              int F2 = f0;
+                if (lane == 31) {
+                  M->scan_p[b][q] = Pp;
+                  M->scan_f[b][q] = F;
+                }
+                half_sync(b);
+                // carry of the ray that straddles the previous tile boundary
+                float cin_T = 1.f, cin_d = 0.f;
+                if (t > 0) {
+                  const uint32_t par = b ? (uint32_t)(pair & 1) : (uint32_t)((pair - 1) & 1);
+                  mbar_wait(&M->carry_a[1 - b], par, 40);
+                  if (s_first != 0) {
+                    cin_T = M->carry_T[1 - b];
+                    cin_d = M->carry_depth[1 - b];
+                  }
+                }
+                float pre = cin_T;
+                for (int w2 = 0; w2 < q; ++w2)
+                  pre = M->scan_f[b][w2] ? M->scan_p[b][w2] : pre * M->scan_p[b][w2];
+                const float T = f0 ? 1.f : (Fe ? Pe : pre * Pe);
+                w_ray = alpha * T;
+                if (valid) P.weights[p] = w_ray;
+                M->wray[b][row] = w_ray;
+                // inclusive segmented sum of w*z for the depth map
+                float Sd = w_ray * z;
+                int F2 = f0;
 #pragma unroll
-              for (int d = 1; d < 32; d <<= 1) {
-                const float sn = __shfl_up_sync(0xffffffffu, Sd, d);
-                const int fn = __shfl_up_sync(0xffffffffu, F2, d);
-                if (lane >= d) {
-                  if (!F2) Sd += sn;
-                  F2 |= fn;
+                for (int d = 1; d < 32; d <<= 1) {
+                  const float sn = __shfl_up_sync(0xffffffffu, Sd, d);
+                  const int fn = __shfl_up_sync(0xffffffffu, F2, d);
+                  if (lane >= d) {
+                    if (!F2) Sd += sn;
+                    F2 |= fn;
+                  }
                 }
-              }
-              if (lane == 31) M->scan_d[b][q] = Sd;
-              group_sync(b);
-              float pre_d = cin_d;
-              for (int w2 = 0; w2 < q; ++w2)
-                pre_d = M->scan_f[b][w2] ? M->scan_d[b][w2] : pre_d + M->scan_d[b][w2];
-              const float D_incl = F2 ? Sd : pre_d + Sd;
-              const bool ray_end = valid && (s == P.S - 1);
-              if (ray_end) P.depth[ray] = D_incl;
-              if (row == nvalid - 1) {
-                M->carry_T[b] = ray_end ? 1.f : T * om;
-                M->carry_depth[b] = ray_end ? 0.f : D_incl;
-                mbar_arrive(&M->carry_a[b]);
+                if (lane == 31) M->scan_d[b][q] = Sd;
+                half_sync(b);
+                float pre_d = cin_d;
+                for (int w2 = 0; w2 < q; ++w2)
+                  pre_d = M->scan_f[b][w2] ? M->scan_d[b][w2] : pre_d + M->scan_d[b][w2];
+                const float D_incl = F2 ? Sd : pre_d + Sd;
+                const bool ray_end = valid && (s == P.S - 1);
+                if (ray_end) P.depth[ray] = D_incl;
+                if (row == nvalid - 1) {
+                  M->carry_T[b] = ray_end ? 1.f : T * om;
+                  M->carry_depth[b] = ray_end ? 0.f : D_incl;
+                  mbar_arrive(&M->carry_a[b]);
+                }
+                pc_arrive(5 + b);  // wray[] is published for the half-1 warps
               }
             }
             if (prof) t_comp += clock64() - t_c0;
           }
         } else {
           // ------------------------------------------------ rgb layer (64, sigmoid)
-          // the embedding buffer is dead (dir layer retired): reuse it as the
-          // (row, channel) staging area, XOR-swizzled so both the row-wise
-          // writes and the channel-wise reads are bank-conflict free
+          // the embedding buffer is dead (dir layer and every bias k-step of this tile have
+          // retired... except this unit's own bias k-step, which has retired too since the
+          // accumulator is complete): reuse it as the (row, channel) staging area,
+          // XOR-swizzled so both the row-wise writes and the channel-wise reads are
+          // bank-conflict free.  Each column half handles 32 of the 64 channels.
+          if (!raw_mode && ch == 1) {
+            pc_sync(5 + b);
+            w_ray = M->wray[b][row];
+          }
+          uint32_t v[32];
+          if (!skip) {
+            tmem_ld_x32(tD + 32 * ch, v);
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            if (!skip) {
-              tmem_ld_x32(tD + 32 * c, v);
-              tmem_ld_wait();
+            for (int j = 0; j < 32; ++j) v[j] = 0;
+          }
+          tc_fence_before_sync();
+          warp_arrive(&M->d_empty[b]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float a = __uint_as_float(v[j]);
+            const float f = __fdividef(1.f, 1.f + __expf(-a));
+            const int chn = 32 * ch + j;
+            if (raw_mode) {
+              if (valid && !skip && !(P.mode & kModeSigmaOnly)) P.raw[p * 65 + chn] = f;
             } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = 0;
+              staging[row * 64 + (chn ^ (row & 31))] = w_ray * f;
             }
-            if (c == 1) {
-              tc_fence_before_sync();
-              warp_arrive(&M->d_empty[b]);
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float a = __uint_as_float(v[j]);
-              const float f = __fdividef(1.f, 1.f + __expf(-a));
-              const int ch = 32 * c + j;
-              if (raw_mode) {
-                if (valid && !skip && !(P.mode & kModeSigmaOnly)) P.raw[p * 65 + ch] = f;
-              } else {
-                staging[row * 64 + (ch ^ (row & 31))] = w_ray * f;
-              }
-              if constexpr (kDbg) {
-                if (dbg_row) dbg_row[ch] = f;
-              }
+            if constexpr (kDbg) {
+              if (dbg_row) dbg_row[chn] = f;
             }
           }
           if (raw_mode) {
-            if (valid && !skip) {
+            if (valid && !skip && ch == 0) {
               if (P.mode & kModeSigmaOnly)
                 P.raw[p] = sigma;
               else
                 P.raw[p * 65 + 64] = sigma;
             }
+            group_sync(b);  // the next tile's embedding overwrites the buffer both halves use
           } else {
             const long long t_r0 = prof ? clock64() : 0;
             group_sync(b);
             const int s_first = (int)(tile_p0 % P.S);
             const long long ray_first = tile_p0 / P.S;
             const int n_seg = (s_first + nvalid + P.S - 1) / P.S;
-            const int cc = gtid & 63, hh = gtid >> 6;
+            const int cc = gtid & 63, hh = gtid >> 6;  // channel, row quarter
             for (int sg = 0; sg < n_seg; ++sg) {
               const int r_beg = max(0, sg * P.S - s_first);
               const int r_end = min(nvalid, (sg + 1) * P.S - s_first);
-              const int lo = max(r_beg, 64 * hh), hi = min(r_end, 64 * hh + 64);
+              const int lo = max(r_beg, 32 * hh), hi = min(r_end, 32 * hh + 32);
               float acc = 0.f;
               for (int r = lo; r < hi; ++r) acc += staging[r * 64 + (cc ^ (r & 31))];
               M->part[b][hh][sg][cc] = acc;
@@ -767,6 +793,8 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
                 float tot = (sg == 0 && s_first != 0) ? M->carry_feat[1 - b][cc] : 0.f;
                 tot += M->part[b][0][sg][cc];
                 tot += M->part[b][1][sg][cc];
+                tot += M->part[b][2][sg][cc];
+                tot += M->part[b][3][sg][cc];
                 const bool ends = ((sg + 1) * P.S - s_first) <= nvalid;
                 if (ends)
                   P.feature[(ray_first + sg) * 64 + cc] = tot;
@@ -788,7 +816,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       o[2] = t_emb;                // embedding phases
       o[3] = t_comp;               // sigma/alpha scan
       o[4] = t_red;                // feature reduction
-      o[5] = t_units;              // all 128-wide layer epilogues (wake-up -> a_full/d_empty arrive)
+      o[5] = t_units;              // all layer epilogues (wake-up -> a_full/d_empty arrive)
       o[6] = t_stage;              // ... of which first halves (drain to registers)
       o[7] = t_flush;              // ... of which second halves / dir (drain + write A)
     }
@@ -866,15 +894,10 @@ __global__ void pack_kernel(const __grid_constant__ PackParams P) {
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kBlobFloats; i += gridDim.x * blockDim.x) {
     float v = 0.f;
-    if (i < kSigmaWOff) {
-      const int layer = i < 2048 ? i / 256 : i < 2304 ? kLFinal : i < 2432 ? kLDir : kLRgb;
-      const int j = i - kBiasOff(layer);
-      if (j < layer_out_features(layer)) v = P.b[layer][j];
-    } else if (i < kSigmaBOff) {
+    if (i < kSigmaBOff)
       v = P.w[kLSigma][i - kSigmaWOff];
-    } else if (i == kSigmaBOff) {
+    else if (i == kSigmaBOff)
       v = P.b[kLSigma][0];
-    }
     P.blob[i] = v;
   }
 }

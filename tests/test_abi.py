@@ -39,8 +39,8 @@ def test_host_only_entry_points():
     from crnerf_b200 import _lib
     lib = _lib.load()
     # weights: 77 chunks of 16 KB + 2 of 8 KB; biases: 19 chunks of 4 KB + 1 of 2 KB;
-    # + 2760 fp32 side blob (sigma head)
-    assert lib.crnerf_mlp_packed_bytes(93, 27) == 77 * 16384 + 2 * 8192 + 19 * 4096 + 2048 + 2760 * 4
+    # + 264 fp32 side blob (sigma head)
+    assert lib.crnerf_mlp_packed_bytes(93, 27) == 77 * 16384 + 2 * 8192 + 19 * 4096 + 2048 + 264 * 4
     assert lib.crnerf_style_scratch_floats(1024) > 296 * 1088
     buf = (ctypes.c_int32 * 4096)()
     n = lib.crnerf_debug_program(93, 27, buf, 4096)

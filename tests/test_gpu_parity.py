@@ -30,23 +30,46 @@ def ops():
     return o
 
 
-def close_where_conditioned(got, ref32, ref64, what, rtol, atol):
+def sample_pdf_conditioning(bins, weights, u, eps=1e-5):
+    """Per-sample amplification d(sample)/d(cdf) = bin width / cdf mass of the selected bin,
+    evaluated in float64 with the steps of rendering.py:20-45, and a flag for samples whose
+    bin sits on the `denom < eps -> 1` switch (rendering.py:41-42)."""
+    bins, weights, u = bins.double(), weights.double(), u.double().contiguous()
+    m = weights.shape[1]
+    w = weights + eps
+    pdf = w / w.sum(1, keepdim=True)
+    cdf = torch.cat([torch.zeros_like(pdf[:, :1]), torch.cumsum(pdf, -1)], -1)
+    idx = torch.searchsorted(cdf, u, right=True)
+    lo, hi = (idx - 1).clamp_min(0), idx.clamp_max(m)
+    denom = cdf.gather(1, hi) - cdf.gather(1, lo)
+    width = (bins.gather(1, hi) - bins.gather(1, lo)).abs()
+    on_switch = (denom - eps).abs() < 1e-6
+    # a draw within a few ulp of a cdf knot may also land in the neighbouring bin
+    near_knot = torch.minimum((u - cdf.gather(1, lo)).abs(), (cdf.gather(1, hi) - u).abs()) < 4e-7
+    amp = width / torch.where(denom < eps, torch.ones_like(denom), denom)
+    return amp, width, on_switch | near_knot
+
+
+def close_where_conditioned(got, ref32, ref64, what, rtol, atol, cond):
     """sample_pdf divides by the bin's cdf mass: in a nearly empty bin (pdf ~ eps) one ulp of
-    the cdf moves the sample by ~ulp/pdf * bin width (1e-5 .. a whole bin where the
-    reference's `denom < eps -> 1` rule, rendering.py:41-42, flips), and the fp32
-    reference disagrees with its own float64 evaluation by that much.  Criterion: within
-    tolerance of the fp32 reference, OR at least as close to the float64 result as the
-    fp32 reference is (x2 slack)."""
+    the cdf moves the sample by ulp/mass * bin width, and torch's own fp32 result depends on
+    the host's summation order by that much (the pdf normaliser `w.sum()` is a vectorised
+    cascade sum whose shape follows the CPU's SIMD width).  Tolerance per element:
+    atol + rtol*|ref| + 8 ulp(cdf) * amplification; elements on the `denom < eps` switch or
+    on a cdf knot may differ by up to the bin width.  At most 1 % of the elements may need
+    more than the plain atol/rtol part."""
+    amp, width, loose = cond
     got, ref32, ref64 = got.detach().cpu().double(), ref32.double(), ref64.double()
     tol32 = atol + rtol * ref32.abs()
-    ok32 = (got - ref32).abs() <= tol32
-    ok64 = (got - ref64).abs() <= torch.maximum(tol32, 2 * (ref32 - ref64).abs())
-    bad = ~(ok32 | ok64)
-    assert (~ok32).float().mean() < 0.01, f"{what}: too many elements off the fp32 reference"
+    tol = tol32 + 8 * 2.0 ** -24 * amp + torch.where(loose, width, torch.zeros_like(width))
+    err = torch.minimum((got - ref32).abs(), (got - ref64).abs())
+    bad = err > tol
+    assert ((got - ref32).abs() > tol32).float().mean() < 0.01, f"{what}: too many elements off the fp32 reference"
     if bad.any():
-        i = torch.argmax(((got - ref32).abs() * bad).flatten())
+        i = torch.argmax((err * bad).flatten())
         raise AssertionError(f"{what}: {int(bad.sum())}/{bad.numel()} outside tolerance; worst got "
-                             f"{got.flatten()[i]:.8g} want {ref32.flatten()[i]:.8g} (fp64 ref {ref64.flatten()[i]:.8g})")
+                             f"{got.flatten()[i]:.8g} want {ref32.flatten()[i]:.8g} (fp64 ref {ref64.flatten()[i]:.8g}, "
+                             f"tol {tol.flatten()[i]:.3g})")
 
 
 def close(a, b, what, rtol, atol):
@@ -168,12 +191,13 @@ def test_sample_pdf_matches_golden():
         u2 = u if u.dim() == 2 else u.expand(bins.shape[0], ni)
         ref64 = oracle.sample_pdf(g["bins"].double(), g["weights"].double(), ni, u=u2.double())
         close_where_conditioned(out, c["ref"], ref64, f"sample_pdf ni={ni} det={c['det']}",
-                                rtol=2e-6, atol=2e-6)
+                                rtol=2e-6, atol=2e-6, cond=sample_pdf_conditioning(g["bins"], g["weights"], u2))
     out = rendering.sample_pdf(bins, w, 64, det=True)
     ref64 = oracle.sample_pdf(g["bins"].double(), g["weights"].double(), 64,
                               u=torch.linspace(0, 1, 64).expand(48, 64).double())
     close_where_conditioned(out, g["cases"][1]["ref"], ref64, "models.rendering.sample_pdf",
-                            rtol=2e-6, atol=2e-6)
+                            rtol=2e-6, atol=2e-6,
+                            cond=sample_pdf_conditioning(g["bins"], g["weights"], torch.linspace(0, 1, 64).expand(48, 64)))
     torch.manual_seed(5)
     out = rendering.sample_pdf(bins, w, 32, det=False)
     assert out.shape == (48, 32) and torch.isfinite(out).all()
@@ -195,7 +219,8 @@ def test_sample_pdf_merge_matches_golden(name):
     new64 = oracle.sample_pdf(0.5 * (zc.double()[:, :-1] + zc.double()[:, 1:]), wc.double()[:, 1:-1],
                               ni, u=u2.double())
     assert torch.equal(torch.sort(torch.cat([zc, new32], 1), 1)[0], g["z_fine"])   # oracle == golden
-    close_where_conditioned(z_new, new32, new64, "z_new", rtol=2e-6, atol=2e-6)
+    close_where_conditioned(z_new, new32, new64, "z_new", rtol=2e-6, atol=2e-6,
+                            cond=sample_pdf_conditioning(0.5 * (zc[:, :-1] + zc[:, 1:]), wc[:, 1:-1], u2))
     close(z_fine, g["z_fine"], "z_fine (loose: conditioning of near-empty bins)", rtol=0, atol=1e-3)
     # sortedness + multiset identity (exact): the merge is sort(cat(z_coarse, z_new))
     assert (z_fine[:, 1:] >= z_fine[:, :-1]).all()

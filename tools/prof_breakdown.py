@@ -13,7 +13,7 @@ args = types.SimpleNamespace(nerf_out_dim=64, pertubeCord=False, img_wh=[64, 64]
 fine = NeRF_sigma('fine', args, in_channels_xyz=93, in_channels_dir=27).cuda()
 rays = oracle.pinhole_rays(64, 64, oracle.synthetic_pose(0)).cuda()
 EXPS = [(-2, "normal"), (-3, "EXP1: epilogue skips TMEM traffic + math"),
-        (-4, "EXP2: producer skips weight copies"), (-10, "EXP8: epilogue = TMEM loads only"), (-18, "EXP16: epilogue = convert+store only (no loads)")]
+        (-4, "EXP2: producer skips weight copies"), (-5, "EXP1+EXP2")]
 if len(sys.argv) > 1 and sys.argv[1] == "quick":
     EXPS = EXPS[:1]
 for code, label in EXPS:

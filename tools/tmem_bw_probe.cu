@@ -53,6 +53,24 @@ __global__ void __launch_bounds__(320, 1) k(P p) {
       } else if (p.shape == 64) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) { uint32_t v[64]; ld64(base + 64 * c, v); tmem_ld_wait(); acc += v[0] + v[63]; }
+      } else if (p.shape == 100) {  // store test: 64 words per iteration (2 x st.x32) + wait::st
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = acc + j;
+        tmem_st_x32(base, v);
+        tmem_st_x32(base + 32, v);
+        tmem_st_wait();
+        acc += 1;
+      } else if (p.shape == 101) {  // ld x32 + st x16 + wait::st (the flush pattern)
+        uint32_t v[32];
+        tmem_ld_x32(base, v);
+        tmem_ld_wait();
+        tmem_st_x16p(base + 64, v);
+        tmem_ld_x32(base + 32, v);
+        tmem_ld_wait();
+        tmem_st_x16p(base + 80, v);
+        tmem_st_wait();
+        acc += v[0];
       } else {  // 32 columns, two loads in flight before each wait
 #pragma unroll
         for (int c = 0; c < 2; ++c) { uint32_t v[32], w[32]; tmem_ld_x32(base + 64 * c, v); tmem_ld_x32(base + 64 * c + 32, w); tmem_ld_wait(); acc += v[0] + w[31]; }
