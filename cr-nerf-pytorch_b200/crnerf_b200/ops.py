@@ -379,3 +379,67 @@ def cnn_forward(sw: StyleWeightsRef, which: str, x: torch.Tensor) -> torch.Tenso
 def debug_set(buf: Optional[torch.Tensor], layer: int = -1):
     """Tests only: dump post-activation values of `layer` for every point into buf (P,256)."""
     check(_lib.load().crnerf_debug_set(_p(buf), layer))
+
+
+# --------------------------------------------------------------------------
+# Sharded form of the cross-ray block (SURVEY.md 8e scheme B): the three phases of
+# style_forward as separate calls so a collective can run between them.
+def _rows64(t: torch.Tensor, name: str):
+    """(n, 64) row-major features (what render_pass returns) -> (tensor, n, pix_stride, ch_stride)."""
+    t = _c(_need(t, name, 2))
+    if t.shape[1] != 64:
+        raise ValueError(f"{name} must be (n_pixels, 64), got {tuple(t.shape)}")
+    return t, t.shape[0], 64, 1
+
+
+def _style_scratch(dev, n):
+    return torch.empty(_lib.load().crnerf_style_scratch_floats(n), dtype=torch.float32, device=dev)
+
+
+def style_stats1(content_rows: torch.Tensor) -> torch.Tensor:
+    """Per-channel SUMS over this rank's pixels: (n,64) -> (64,)."""
+    lib = _lib.load()
+    x, n, ps, cs = _rows64(content_rows, "content_rows")
+    dev = x.device
+    with torch.cuda.device(dev):
+        sums = torch.zeros(64, dtype=torch.float32, device=dev)
+        if n == 0:
+            return sums
+        check(lib.crnerf_style_stats1(x.data_ptr(), n, ps, cs, sums.data_ptr(),
+                                      _style_scratch(dev, n).data_ptr(), _stream(dev)))
+    return sums
+
+
+def style_stats2(sw: StyleWeightsRef, content_rows: torch.Tensor, mean: torch.Tensor) -> torch.Tensor:
+    """Un-normalised Gram of cnet.convs(content - mean) over this rank's pixels -> (32,32)."""
+    lib = _lib.load()
+    x, n, ps, cs = _rows64(content_rows, "content_rows")
+    mean = _c(_need(mean, "mean", 1))
+    dev = x.device
+    with torch.cuda.device(dev):
+        gram = torch.zeros((32, 32), dtype=torch.float32, device=dev)
+        if n == 0:
+            return gram
+        check(lib.crnerf_style_stats2(C.byref(sw.struct), x.data_ptr(), n, ps, cs, mean.data_ptr(),
+                                      gram.data_ptr(), _style_scratch(dev, n).data_ptr(), _stream(dev)))
+    return gram
+
+
+def style_apply(sw: StyleWeightsRef, content_rows: torch.Tensor, mean: torch.Tensor,
+                gram_normalised: torch.Tensor, style: torch.Tensor) -> torch.Tensor:
+    """Fused cross-ray map + decoder on this rank's pixels -> rgb (3, n) planar."""
+    lib = _lib.load()
+    x, n, ps, cs = _rows64(content_rows, "content_rows")
+    mean = _c(_need(mean, "mean", 1))
+    gram_normalised = _c(_need(gram_normalised, "gram_normalised", 2))
+    style, ns, sps, scs = _feat_strides(style, "style")
+    dev = x.device
+    with torch.cuda.device(dev):
+        rgb = torch.empty((3, n), dtype=torch.float32, device=dev)
+        if n == 0:
+            return rgb
+        check(lib.crnerf_style_apply(C.byref(sw.struct), x.data_ptr(), n, ps, cs, mean.data_ptr(),
+                                     gram_normalised.data_ptr(), style.data_ptr(), ns, sps, scs,
+                                     rgb.data_ptr(), None, _style_scratch(dev, n).data_ptr(),
+                                     _stream(dev)))
+    return rgb
