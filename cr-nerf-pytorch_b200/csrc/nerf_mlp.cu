@@ -46,6 +46,7 @@ constexpr int kSlots = 8;
 constexpr int kSlotBytes = 16384;
 constexpr int kEmbBufBytes = 32768;
 constexpr int kThreads = 640;        // 4 control warps + 2 tile groups x 8 epilogue warps
+constexpr int kCtrlRegs = 32, kEpiRegs = 112;  // 4*32*32 + 16*32*112 = 61,440 = 640*96
 constexpr int kMaxSeg = 10;  // ray segments per 128-row tile (n_samples >= 16)
 
 constexpr int kRingOff = 0;
@@ -58,7 +59,14 @@ struct Misc {
   uint64_t ring_empty[kSlots];
   uint64_t emb_full[2], a_full[2], d_full[2], d_empty[2], carry_a[2], carry_b[2];
   uint32_t tmem_base;
-  uint32_t pad0;
+  uint32_t pipe_turn;  // whose unit goes down the tensor pipe next (even: stream X, odd: Y)
+  // the issuers' copy of the program: constant-bank lookups indexed by a run-time value are
+  // slow (tens to hundreds of cycles each), shared-memory loads are not
+  //   unit_tab: n | first_of_layer << 8 | (layer == 0) << 9 | standard << 10 | chunk0 << 16 |
+  //             nchunks << 24; "standard" = four full activation slabs and a bias chunk
+  //   meta_tab: c_meta
+  uint32_t unit_tab[kMaxUnits];
+  uint32_t meta_tab[kMaxChunks];
   float scan_p[2][4];
   float scan_d[2][4];
   int scan_f[2][4];
@@ -111,6 +119,19 @@ __device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, uint3
   const long long t0 = clock64();
   mbar_wait(bar, parity, tag);
   acc += clock64() - t0;
+}
+
+// bounded spin on the pipe-turn word (same policy as mbar_wait: trap instead of hanging;
+// a shared-memory load spins ~30 cycles per iteration, so 2^27 spins is seconds)
+__device__ __forceinline__ void turn_wait(const uint32_t* turn, uint32_t want) {
+  const volatile uint32_t* t = turn;
+  uint32_t spins = 0;
+  while (*t != want) {
+    if (++spins == (1u << 27)) {
+      g_wait_timeout_tag = 0x80000000u | (50u << 16) | (blockIdx.x & 0xffff);
+      __trap();
+    }
+  }
 }
 
 // one arrival on behalf of a converged warp
@@ -236,11 +257,7 @@ __device__ __forceinline__ float softplus_ref(float x) {
 // Epilogue of one warp's 64 accumulator columns (bias already inside, see nerf_layout.h):
 // one tcgen05.ld.x64, optional ReLU, pack to 32 words.  kSigma additionally accumulates
 // this warp's share of the fp32 sigma-head dot product of the layer-8 activations.
-//   kEpiStage : first half of a 256-wide layer - keep the packed words in `staged`
-//               (A is still being read by the layer's second half);
-//   kEpiFlush : second half - write the staged words and this half's words to A;
-//   kEpiDirect: dir layer - write straight to A columns [0,64).
-enum : int { kEpiStage = 0, kEpiFlush = 1, kEpiDirect = 2 };
+// epi_stage / epi_flush below combine two slices into a layer-half epilogue.
 
 template <int kFmt, bool kRelu, bool kSigma, bool kDbg, int kOff, int kN>
 __device__ __forceinline__ void epi_slice32(const uint32_t (&v)[32], const float* wsig,
@@ -267,49 +284,57 @@ __device__ __forceinline__ void epi_slice32(const uint32_t (&v)[32], const float
     out[kOff + j] = pack2<kFmt, kRelu>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
 }
 
+// First half of a 256-wide layer: drain this warp's 64 accumulator columns into 32 packed
+// words that stay in registers (A is still being read by the layer's second half).
 template <int kFmt, bool kRelu, bool kSigma, bool kDbg>
-__device__ __forceinline__ void epi_64(int mode, int ch, uint32_t tD, uint32_t tA, const float* wsig,
-                                       uint32_t (&staged)[32], float& sig_acc, uint64_t* d_empty,
-                                       float* dbg_row, bool skip) {
+__device__ __forceinline__ void epi_stage(uint32_t tD_ch, const float* wsig_ch, uint32_t (&staged)[32],
+                                          float& sig_acc, uint64_t* d_empty, float* dbg, bool skip) {
   if (kDbg && skip) {
     tc_fence_before_sync();
     warp_arrive(d_empty);
     return;
   }
-  // Two 32-column loads, the second in flight while the first slice is packed (one x64
-  // load next to the 32 staged words does not fit the epilogue warps' register budget).
-  // In flush mode every MMA of the layer has retired, so the staged first half may
-  // overwrite A right away.
-  float* dbg = kDbg && dbg_row ? dbg_row + 64 * ch : nullptr;
-  if (mode == kEpiStage) {
-    // the 32 staged words stay live, so use one 32-register buffer sequentially
-    uint32_t v[32];
-    tmem_ld_x32(tD + 64 * ch, v);
-    tmem_ld_wait();
-    epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 32>(v, wsig + 64 * ch, staged, sig_acc, dbg);
-    tmem_ld_x32(tD + 64 * ch + 32, v);
-    tmem_ld_wait();
+  uint32_t va[32], vb[32];
+  tmem_ld_x32(tD_ch, va);
+  tmem_ld_wait();
+  tmem_ld_x32(tD_ch + 32, vb);  // in flight while the first slice is packed
+  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 32>(va, wsig_ch, staged, sig_acc, dbg);
+  tmem_ld_wait();
+  tc_fence_before_sync();
+  warp_arrive(d_empty);  // accumulator drained: the issuer may overwrite it
+  epi_slice32<kFmt, kRelu, kSigma, kDbg, 16, 32>(vb, wsig_ch + 32, staged, sig_acc, dbg ? dbg + 32 : nullptr);
+}
+
+// Second half (kDirect == false): every MMA of the layer has retired, so the staged first
+// half goes to A columns [32ch, 32ch+32) and this half's 64 columns to [64+32ch, ...).
+// kDirect (dir layer, 128 wide): this warp's 64 columns go to A columns [32ch, 32ch+32).
+template <int kFmt, bool kRelu, bool kSigma, bool kDbg, bool kDirect>
+__device__ __forceinline__ void epi_flush(uint32_t tD_ch, uint32_t tA_ch, const float* wsig_ch,
+                                          const uint32_t (&staged)[32], float& sig_acc,
+                                          uint64_t* d_empty, uint64_t* a_full, float* dbg, bool skip) {
+  if (kDbg && skip) {
     tc_fence_before_sync();
-    warp_arrive(d_empty);  // accumulator drained: the issuer may overwrite it
-    epi_slice32<kFmt, kRelu, kSigma, kDbg, 16, 32>(v, wsig + 64 * ch + 32, staged, sig_acc,
-                                                   dbg ? dbg + 32 : nullptr);
+    warp_arrive(d_empty);
+    warp_arrive(a_full);
     return;
   }
-  // flush / direct: the staged words leave first (frees their registers), then two loads
-  // with the second in flight while the first slice is packed and stored
-  if (mode == kEpiFlush) tmem_st_x32(tA + 32 * ch, staged);
-  const uint32_t a_dst = tA + (mode == kEpiFlush ? 64 : 0) + 32 * ch;
+  if constexpr (!kDirect) tmem_st_x32(tA_ch, staged);
+  const uint32_t a_dst = tA_ch + (kDirect ? 0u : 64u);
   uint32_t va[32], vb[32], out[16];
-  tmem_ld_x32(tD + 64 * ch, va);
+  tmem_ld_x32(tD_ch, va);
   tmem_ld_wait();
-  tmem_ld_x32(tD + 64 * ch + 32, vb);
-  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 16>(va, wsig + 64 * ch, out, sig_acc, dbg);
+  tmem_ld_x32(tD_ch + 32, vb);
+  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 16>(va, wsig_ch, out, sig_acc, dbg);
   tmem_st_x16p(a_dst, out);
   tmem_ld_wait();
   tc_fence_before_sync();
   warp_arrive(d_empty);  // accumulator drained: the issuer may overwrite it
-  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 16>(vb, wsig + 64 * ch + 32, out, sig_acc, dbg ? dbg + 32 : nullptr);
+  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 16>(vb, wsig_ch + 32, out, sig_acc, dbg ? dbg + 32 : nullptr);
   tmem_st_x16p(a_dst + 16, out);
+  // A holds the next layer's full input
+  tmem_st_wait();
+  tc_fence_before_sync();
+  warp_arrive(a_full);
 }
 
 template <int kFmt, bool kDbg>
@@ -331,7 +356,9 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
   if (tid == 0) {
     for (int i = 0; i < kSlots; ++i) {
       mbar_init(&M->ring_full[i], 1);
-      mbar_init(&M->ring_empty[i], 2);  // released by both tile streams
+      // released by stream Y alone: the turn order puts X's use of a chunk ahead of Y's on the
+      // in-order tensor pipe, so Y's commit covers both (X commits only when it runs solo)
+      mbar_init(&M->ring_empty[i], 1);
     }
     for (int b = 0; b < 2; ++b) {
       // epilogue-side barriers take ONE arrival per warp (an elected lane after the warp's
@@ -343,22 +370,38 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       mbar_init(&M->carry_a[b], 1);
       mbar_init(&M->carry_b[b], 2);
     }
+    M->pipe_turn = 0u;
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(&M->tmem_base);
   for (int i = tid; i < kBlobFloats; i += kThreads) blob[i] = P.blob[i];
+  for (int i = tid; i < P.n_units; i += kThreads) {
+    const Unit un = c_units[i];
+    bool standard = un.nchunks == 5;
+    for (int j = 0; standard && j < 4; ++j) {
+      const uint32_t m = c_meta[un.chunk0 + j];  // a_src | a_k0 << 8 | nk << 16 | bias flag 0x80
+      standard = (m & 0xffu) == (uint32_t)kSrcAct && ((m >> 8) & 0xffu) == 4u * j && ((m >> 16) & 0xffu) == 4u;
+    }
+    standard = standard && (c_meta[un.chunk0 + 4] & 0x80u) != 0;
+    M->unit_tab[i] = (uint32_t)un.n | ((uint32_t)(un.first_of_layer != 0) << 8) |
+                     ((uint32_t)(un.layer == 0) << 9) | ((uint32_t)standard << 10) |
+                     ((uint32_t)un.chunk0 << 16) | ((uint32_t)un.nchunks << 24);
+  }
+  for (int i = tid; i < P.n_chunks; i += kThreads) M->meta_tab[i] = c_meta[i];
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = M->tmem_base;
 
-  // register rebalancing inside the CTA's launch allocation (640 threads x 96 registers =
-  // 61,440; setmaxnreg cannot draw from outside it): 4 control warps x 64 + 16 epilogue
-  // warps x 104 = 61,440 exactly
-  if (warp < 4) setmaxnreg_dec_64(); else setmaxnreg_inc_104();
-
+  // Register rebalancing inside the CTA's launch allocation (640 threads x 96 registers =
+  // 61,440; setmaxnreg cannot draw from outside it): the 4 control warps drop to kCtrlRegs,
+  // the 16 epilogue warps rise to kEpiRegs.  setmaxnreg is a warpgroup-wide instruction:
+  // warps 0-3 (one warpgroup) must all use the same value.  Each call sits at the top of
+  // its role branch - ptxas only raises a region's register budget when the instruction
+  // dominates it.
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
+    setmaxnreg_dec<kCtrlRegs>();
     if (elect_one()) {
       const uint64_t pol = l2_policy_evict_last();
       uint32_t g = 0;
@@ -378,8 +421,11 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       }
     }
     __syncwarp();
+  } else if (warp == 2) {
+    setmaxnreg_dec<kCtrlRegs>();  // TMEM allocator warp: idle until teardown
   } else if (warp == 1 || warp == 3) {
     // ------------------------------------------------------------------- issuers
+    setmaxnreg_dec<kCtrlRegs>();
     // One issuer warp per tile stream (warp 1 -> X, warp 3 -> Y).  The tcgen05 issue
     // queue is only 1-2 instructions deep (measured: tools/umma_probe issue timestamps),
     // so the tensor pipe runs only while some thread is actually issuing; with two
@@ -397,25 +443,23 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
     const uint32_t tD = tmem + (b ? 384u : 128u);
     uint32_t ucount = 0, acount = 0;
     uint32_t g_base = 0;
+    uint32_t my_turn = (uint32_t)b;  // pipe_turn value at which this stream may issue its next unit
     const bool prof = kDbg && P.prof != nullptr && blockIdx.x == 0;
-    long long w_emb = 0, w_a = 0, w_d = 0, w_ring = 0;
+    long long w_emb = 0, w_a = 0, w_d = 0, w_ring = 0, w_lock = 0, t_burst = 0;
     const long long t_start = clock64();
     for (int pair = 0; pair < n_pairs; ++pair) {
-      if (2 * pair + b >= n_tiles) {
-        // odd tile count: this stream has no tile in the last pair, but it still owes the
-        // producer one arrival per ring slot
-        for (int c = 0; c < P.n_chunks; ++c) {
-          const uint32_t g = g_base + (uint32_t)c;
-          mbar_wait(&M->ring_full[g % kSlots], (g / kSlots) & 1, 6);
-          if (elect_one()) mbar_arrive(&M->ring_empty[g % kSlots]);
-        }
-        break;
-      }
+      if (2 * pair + b >= n_tiles) break;  // odd tile count: X finishes the last pair solo
+      const bool solo = 2 * pair + 2 > n_tiles;  // odd tile count: X owns the last pair alone
       for (int u = 0; u < P.n_units; ++u) {
-        const Unit un = c_units[u];
-        const uint32_t idesc = make_idesc_f16(128, (uint32_t)un.n, kFmt);
-        if (un.first_of_layer) {
-          if (un.layer == 0) {
+        const uint32_t ut = M->unit_tab[u];
+        const uint32_t idesc = make_idesc_f16(128, ut & 0xffu, kFmt);
+        const int chunk0 = (int)((ut >> 16) & 0xffu), nch = (int)(ut >> 24);
+        const uint32_t g0 = g_base + (uint32_t)chunk0;
+        // ---- everything this unit depends on is awaited BEFORE the pipe turn, so the turn
+        // holder issues one uninterrupted burst: the tcgen05 queue is only 1-2 MMAs deep and
+        // the pipe idles whenever the issuing thread does anything else for long.
+        if (ut & 0x100u) {
+          if (ut & 0x200u) {
             timed_wait(&M->emb_full[b], (uint32_t)pair & 1, 2, prof, w_emb);
           } else {
             timed_wait(&M->a_full[b], acount & 1, 3, prof, w_a);
@@ -423,69 +467,86 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
           }
         }
         timed_wait(&M->d_empty[b], (ucount & 1) ^ 1, 4, prof, w_d);
-        tc_fence_after_sync();
-        int j = 0;
-        while (j < un.nchunks) {
-          const uint32_t g = g_base + (uint32_t)(un.chunk0 + j);
-          const uint32_t meta = c_meta[un.chunk0 + j];
-          const int blk = (int)(meta >> 24);  // 4 / 2: first chunk of a run of full TS slabs
-          if (blk) {
-            // ---- fast path: `blk` consecutive 64-wide activation slabs = 4*blk MMAs issued
-            // as straight-line code (no table lookups or waits between them)
-            for (int jj = 0; jj < blk; ++jj)
-              timed_wait(&M->ring_full[(g + jj) % kSlots], ((g + jj) / kSlots) & 1, 5, prof, w_ring);
-            tc_fence_after_sync();
-            if (elect_one()) {
-              const uint32_t a_t = tA + ((meta >> 8) & 0xffu) * 8u;
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                if (jj < blk) {
-                  const uint32_t slot = (g + jj) % kSlots;
-                  const uint32_t b_lo = ring_lo + slot * (kSlotBytes >> 4);
-                  umma_ts(tD, a_t + 32u * jj, desc(b_lo), idesc, (j + jj) ? 1u : 0u);
-                  umma_ts(tD, a_t + 32u * jj + 8u, desc(b_lo + 2u), idesc, 1u);
-                  umma_ts(tD, a_t + 32u * jj + 16u, desc(b_lo + 4u), idesc, 1u);
-                  umma_ts(tD, a_t + 32u * jj + 24u, desc(b_lo + 6u), idesc, 1u);
-                  umma_commit(&M->ring_empty[slot]);
-                }
-              }
-            }
-            j += blk;
-            continue;
-          }
-          // ---- generic path: partial / embedding chunks (4 of the 79 chunks of a tile)
-          const uint32_t slot = g % kSlots;
-          const int a_src = (int)(meta & 0x7fu);
-          const bool is_bias = (meta & 0x80u) != 0;
-          const int a_k0 = (int)((meta >> 8) & 0xffu);
-          const int nk = (int)((meta >> 16) & 0xffu);
-          timed_wait(&M->ring_full[slot], (g / kSlots) & 1, 5, prof, w_ring);
-          tc_fence_after_sync();
-          const uint32_t b_lo = ring_lo + slot * (kSlotBytes >> 4);
-          if (elect_one()) {
-            const uint32_t acc0 = j ? 1u : 0u;
-            if (is_bias) {
-              // one k-step: ones columns of the embedding x [fp16(b), fp16(b - fp16(b))]
-              const uint32_t a_lo = emb_lo + (uint32_t)b * (kEmbBufBytes >> 4) +
-                                    (uint32_t)(a_k0 >> 2) * 1024u + (uint32_t)(a_k0 & 3) * 2u;
-              constexpr uint32_t kBiasHi = (256u >> 4) | (1u << 14);          // SBO 256 B | version | no swizzle
-              const uint32_t bb_lo = ((b_lo & 0xffffu)) | ((128u >> 4) << 16);  // LBO 128 B
-              umma_ss(tD, desc(a_lo), (static_cast<uint64_t>(kBiasHi) << 32) | bb_lo, idesc, acc0);
-            } else if (a_src == kSrcEmb) {
-              const uint32_t a_lo = emb_lo + (uint32_t)b * (kEmbBufBytes >> 4) +
-                                    (uint32_t)(a_k0 >> 2) * 1024u + (uint32_t)(a_k0 & 3) * 2u;
-              for (int k = 0; k < nk; ++k)
-                umma_ss(tD, desc(a_lo + 2u * k), desc(b_lo + 2u * k), idesc, k ? 1u : acc0);
-            } else {
-              const uint32_t a_t = tA + (uint32_t)a_k0 * 8u;
-              for (int k = 0; k < nk; ++k)
-                umma_ts(tD, a_t + 8u * k, desc(b_lo + 2u * k), idesc, k ? 1u : acc0);
-            }
-            umma_commit(&M->ring_empty[slot]);
-          }
-          ++j;
+        // every weight chunk of the unit as well: they were requested when the partner's
+        // previous unit freed their slots and have normally landed by now
+        for (int j = 0; j < nch; ++j)
+          timed_wait(&M->ring_full[(g0 + j) % kSlots], ((g0 + j) / kSlots) & 1, 5, prof, w_ring);
+        // Take the tensor pipe for this whole unit, strictly alternating X, Y, X, ...
+        // Left alone the two streams issue MMA by MMA in lock step, finish their units
+        // together and then both sit in their epilogues with the pipe idle; with unit-sized
+        // turns one tile's epilogue runs under the other tile's MMAs.  (Strict order, not a
+        // free-for-all lock: the weight ring holds two units, so a stream that got a whole
+        // unit ahead while holding the pipe would wait for a slot its partner can only free
+        // after taking the pipe.)
+        {
+          const long long t_l0 = prof ? clock64() : 0;
+          if (lane == 0) turn_wait(&M->pipe_turn, my_turn);
+          __syncwarp();
+          if (prof) w_lock += clock64() - t_l0;
         }
-        if (elect_one()) umma_commit(&M->d_full[b]);
+        tc_fence_after_sync();
+        const long long t_b0 = prof ? clock64() : 0;
+        // ring slots are released by stream Y's commits (see ring_empty init)
+        const bool release = b == 1 || solo;
+        const uint32_t a_bias = emb_lo + (uint32_t)b * (kEmbBufBytes >> 4) + (uint32_t)(kBiasKstep >> 2) * 1024u +
+                                (uint32_t)(kBiasKstep & 3) * 2u;
+        constexpr uint32_t kBiasHi = (256u >> 4) | (1u << 14);  // SBO 256 B | version | no swizzle
+        if (elect_one()) {
+          if (ut & 0x400u) {
+            // ---- standard unit: 16 TS MMAs over the four activation slabs + the bias k-step,
+            // straight-line
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t slot = (g0 + (uint32_t)j) % kSlots;
+              const uint32_t b_lo = ring_lo + slot * (kSlotBytes >> 4);
+              const uint32_t a_t = tA + 32u * j;
+              umma_ts(tD, a_t, desc(b_lo), idesc, j ? 1u : 0u);
+              umma_ts(tD, a_t + 8u, desc(b_lo + 2u), idesc, 1u);
+              umma_ts(tD, a_t + 16u, desc(b_lo + 4u), idesc, 1u);
+              umma_ts(tD, a_t + 24u, desc(b_lo + 6u), idesc, 1u);
+              if (release) umma_commit(&M->ring_empty[slot]);
+            }
+            {
+              const uint32_t slot = (g0 + 4u) % kSlots;
+              const uint32_t b_lo = ring_lo + slot * (kSlotBytes >> 4);
+              const uint32_t bb_lo = (b_lo & 0xffffu) | ((128u >> 4) << 16);  // LBO 128 B
+              umma_ss(tD, desc(a_bias), (static_cast<uint64_t>(kBiasHi) << 32) | bb_lo, idesc, 1u);
+              if (release) umma_commit(&M->ring_empty[slot]);
+            }
+          } else {
+            // ---- embedding-fed and narrow units (layer 1, skip layer, dir, rgb): table-driven
+            for (int j = 0; j < nch; ++j) {
+              const uint32_t slot = (g0 + (uint32_t)j) % kSlots;
+              const uint32_t meta = M->meta_tab[chunk0 + j];
+              const uint32_t b_lo = ring_lo + slot * (kSlotBytes >> 4);
+              const uint32_t a_k0 = (meta >> 8) & 0xffu;
+              const uint32_t acc0 = j ? 1u : 0u;
+              const int nk = (int)((meta >> 16) & 0xffu);
+              if (kDbg && (meta & 0x80u) && (P.exp & 4)) {
+                // profiling experiment 4: no bias MMA (results are wrong, timing only)
+              } else if (meta & 0x80u) {
+                // bias: one k-step, ones columns of the embedding x [fp16(b), fp16(b - fp16(b))]
+                const uint32_t bb_lo = (b_lo & 0xffffu) | ((128u >> 4) << 16);  // LBO 128 B
+                umma_ss(tD, desc(a_bias), (static_cast<uint64_t>(kBiasHi) << 32) | bb_lo, idesc, acc0);
+              } else if ((meta & 0x7fu) == (uint32_t)kSrcEmb) {
+                const uint32_t a_lo = emb_lo + (uint32_t)b * (kEmbBufBytes >> 4) + (a_k0 >> 2) * 1024u +
+                                      (a_k0 & 3u) * 2u;
+                for (int k = 0; k < nk; ++k)
+                  umma_ss(tD, desc(a_lo + 2u * k), desc(b_lo + 2u * k), idesc, k ? 1u : acc0);
+              } else {
+                const uint32_t a_t = tA + a_k0 * 8u;
+                for (int k = 0; k < nk; ++k)
+                  umma_ts(tD, a_t + 8u * k, desc(b_lo + 2u * k), idesc, k ? 1u : acc0);
+              }
+              if (release) umma_commit(&M->ring_empty[slot]);
+            }
+          }
+          umma_commit(&M->d_full[b]);
+        }
+        __syncwarp();
+        if (prof) t_burst += clock64() - t_b0;
+        my_turn += 2u;
+        if (lane == 0) *(volatile uint32_t*)&M->pipe_turn = my_turn - (solo ? 0u : 1u);
         ucount++;
       }
       g_base += (uint32_t)P.n_chunks;
@@ -498,10 +559,13 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       o[3] = w_d;
       o[4] = w_ring;
       o[5] = n_pairs;
+      o[6] = w_lock;
+      o[7] = t_burst;  // turn acquired -> unit committed (includes the ring waits inside)
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  } else {
     // ------------------------------------------------------------------ epilogue
+    setmaxnreg_inc<kEpiRegs>();
     // tile group b (8 warps): warp gw owns TMEM lane quarter q = gw & 3 (rows 32q..32q+31,
     // one row per lane) and column half ch = gw >> 2 of every 128-wide accumulator.
     const int b = (warp - 4) >> 3;
@@ -522,7 +586,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
     const uint32_t row_off = (uint32_t)row * 128u, row_xor = (uint32_t)(row & 7) << 4;
     uint32_t ud = 0;
     const bool prof = kDbg && P.prof != nullptr && blockIdx.x == 0 && gtid == 0;
-    long long w_dfull = 0, t_emb = 0, t_comp = 0, t_red = 0, t_units = 0, t_stage = 0, t_flush = 0;
+    long long w_dfull = 0, t_emb = 0, t_comp = 0, t_red = 0, t_stage = 0, t_flush = 0;
     const long long t_start = clock64();
 
     for (int pair = 0; pair < n_pairs; ++pair) {
@@ -596,216 +660,245 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
 
       uint32_t staged[32];
       float sig_acc = 0.f, sigma = 0.f, w_ray = 0.f;
-
-      for (int u = 0; u < P.n_units; ++u) {
-        const int layer = c_units[u].layer, half = c_units[u].half;
-        timed_wait(&M->d_full[b], ud & 1, 16 + u, prof, w_dfull);
+      const uint32_t tD_ch = tD + 64u * ch, tA_ch = tA + 32u * ch;
+      uint64_t* const d_full = &M->d_full[b];
+      uint64_t* const d_empty = &M->d_empty[b];
+      uint64_t* const a_full = &M->a_full[b];
+      // wait for the next accumulator of this tile (units arrive in program order)
+      auto wait_d = [&]() {
+        timed_wait(d_full, ud & 1, 16, prof, w_dfull);
         ud++;
         tc_fence_after_sync();
-        const long long t_u0 = prof ? clock64() : 0;
+      };
+      // debug dump target of (layer, half) for this warp's 64 columns, or nullptr
+      auto dbg_at = [&](int layer, int half) -> float* {
+        if constexpr (kDbg) {
+          if (P.dbg != nullptr && P.dbg_layer == layer && valid) return P.dbg + p * 256 + half * 128 + 64 * ch;
+        }
+        return nullptr;
+      };
+      long long t_a = 0;
+
+      // ---- trunk layers 1..7: ReLU.  The layer structure is spelled out here (the issuer
+      // walks the same program from the tables) so that the 32 staged words live in
+      // registers between a layer's two halves and nothing is indexed at run time.
+#pragma unroll 1
+      for (int layer = 0; layer < 7; ++layer) {
+        wait_d();
+        if (prof) t_a = clock64();
+        epi_stage<kFmt, true, false, kDbg>(tD_ch, wsig, staged, sig_acc, d_empty, dbg_at(layer, 0), skip);
+        if (prof) t_stage += clock64() - t_a;
+        wait_d();
+        if (prof) t_a = clock64();
+        epi_flush<kFmt, true, false, kDbg, false>(tD_ch, tA_ch, wsig, staged, sig_acc, d_empty, a_full,
+                                                  dbg_at(layer, 1), skip);
+        if (prof) t_flush += clock64() - t_a;
+      }
+      // ---- layer 8: ReLU + this warp's share of the fp32 sigma-head dot product
+      wait_d();
+      if (prof) t_a = clock64();
+      epi_stage<kFmt, true, true, kDbg>(tD_ch, wsig + 64 * ch, staged, sig_acc, d_empty, dbg_at(7, 0), skip);
+      if (prof) t_stage += clock64() - t_a;
+      wait_d();
+      if (prof) t_a = clock64();
+      epi_flush<kFmt, true, true, kDbg, false>(tD_ch, tA_ch, wsig + 128 + 64 * ch, staged, sig_acc, d_empty,
+                                               a_full, dbg_at(7, 1), skip);
+      if (prof) t_flush += clock64() - t_a;
+      {
+        const long long t_c0 = prof ? clock64() : 0;
+        // ---------------- sigma head + alpha composite (rendering.py:121-143), done by
+        // the column-half-0 warps (one thread per row); half 1 hands over its partial dot
+        if (ch == 1) {
+          M->sig_part[b][row] = sig_acc;
+          pc_arrive(7 + b);
+        } else {
+          pc_sync(7 + b);
+          sigma = softplus_ref(sig_acc + M->sig_part[b][row] + blob[kSigmaBOff]);
+          if (!raw_mode) {
+            // per-row ray state is (re)loaded here rather than carried through the layers
+            const long long ray = valid ? p / P.S : 0;
+            const int s = valid ? (int)(p - ray * P.S) : 0;
+            const float z = valid ? __ldg(P.z_vals + p) : 0.f;
+            const float delta =
+                valid ? ((s + 1 < P.S) ? __fsub_rn(__ldg(P.z_vals + p + 1), z) : 1e2f) : 0.f;
+            const float nz = (valid && P.noise) ? __ldg(P.noise + p) : 0.f;
+            const int s_first = (int)(tile_p0 % P.S);
+            const float alpha = valid ? 1.f - expf(-(delta * fmaxf(sigma + nz, 0.f))) : 0.f;
+            const float om = 1.f - alpha;
+            const int f0 = (valid && s == 0) ? 1 : 0;
+            // inclusive segmented product over the warp's 32 rows
+            float Pp = om;
+            int F = f0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const float pn = __shfl_up_sync(0xffffffffu, Pp, d);
+              const int fn = __shfl_up_sync(0xffffffffu, F, d);
+              if (lane >= d) {
+                if (!F) Pp *= pn;
+                F |= fn;
+              }
+            }
+            float Pe = __shfl_up_sync(0xffffffffu, Pp, 1);
+            int Fe = __shfl_up_sync(0xffffffffu, F, 1);
+            if (lane == 0) {
+              Pe = 1.f;
+              Fe = 0;
+            }
+            if (lane == 31) {
+              M->scan_p[b][q] = Pp;
+              M->scan_f[b][q] = F;
+            }
+            half_sync(b);
+            // carry of the ray that straddles the previous tile boundary
+            float cin_T = 1.f, cin_d = 0.f;
+            if (t > 0) {
+              const uint32_t par = b ? (uint32_t)(pair & 1) : (uint32_t)((pair - 1) & 1);
+              mbar_wait(&M->carry_a[1 - b], par, 40);
+              if (s_first != 0) {
+                cin_T = M->carry_T[1 - b];
+                cin_d = M->carry_depth[1 - b];
+              }
+            }
+            float pre = cin_T;
+            for (int w2 = 0; w2 < q; ++w2)
+              pre = M->scan_f[b][w2] ? M->scan_p[b][w2] : pre * M->scan_p[b][w2];
+            const float T = f0 ? 1.f : (Fe ? Pe : pre * Pe);
+            w_ray = alpha * T;
+            if (valid) P.weights[p] = w_ray;
+            M->wray[b][row] = w_ray;
+            // inclusive segmented sum of w*z for the depth map
+            float Sd = w_ray * z;
+            int F2 = f0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const float sn = __shfl_up_sync(0xffffffffu, Sd, d);
+              const int fn = __shfl_up_sync(0xffffffffu, F2, d);
+              if (lane >= d) {
+                if (!F2) Sd += sn;
+                F2 |= fn;
+              }
+            }
+            if (lane == 31) M->scan_d[b][q] = Sd;
+            half_sync(b);
+            float pre_d = cin_d;
+            for (int w2 = 0; w2 < q; ++w2)
+              pre_d = M->scan_f[b][w2] ? M->scan_d[b][w2] : pre_d + M->scan_d[b][w2];
+            const float D_incl = F2 ? Sd : pre_d + Sd;
+            const bool ray_end = valid && (s == P.S - 1);
+            if (ray_end) P.depth[ray] = D_incl;
+            if (row == nvalid - 1) {
+              M->carry_T[b] = ray_end ? 1.f : T * om;
+              M->carry_depth[b] = ray_end ? 0.f : D_incl;
+              mbar_arrive(&M->carry_a[b]);
+            }
+            pc_arrive(5 + b);  // wray[] is published for the half-1 warps
+          }
+        }
+        if (prof) t_comp += clock64() - t_c0;
+      }
+      // ---- xyz_encoding_final: no activation
+      wait_d();
+      if (prof) t_a = clock64();
+      epi_stage<kFmt, false, false, kDbg>(tD_ch, wsig, staged, sig_acc, d_empty, dbg_at(kLFinal, 0), skip);
+      if (prof) t_stage += clock64() - t_a;
+      wait_d();
+      if (prof) t_a = clock64();
+      epi_flush<kFmt, false, false, kDbg, false>(tD_ch, tA_ch, wsig, staged, sig_acc, d_empty, a_full,
+                                                 dbg_at(kLFinal, 1), skip);
+      if (prof) t_flush += clock64() - t_a;
+      // ---- dir layer (128 wide, ReLU): straight to A columns [0,64)
+      wait_d();
+      if (prof) t_a = clock64();
+      epi_flush<kFmt, true, false, kDbg, true>(tD_ch, tA_ch, wsig, staged, sig_acc, d_empty, a_full,
+                                               dbg_at(kLDir, 0), skip);
+      if (prof) t_flush += clock64() - t_a;
+      // ---- rgb layer
+      wait_d();
+      {
         float* dbg_row = nullptr;
         if constexpr (kDbg) {
-          if (P.dbg != nullptr && P.dbg_layer == layer && valid) dbg_row = P.dbg + p * 256 + half * 128;
+          if (P.dbg != nullptr && P.dbg_layer == kLRgb && valid) dbg_row = P.dbg + p * 256;
         }
-
-        if (layer <= kLDir) {
-          // ------------------------------------------------ 256-wide layers and the dir layer
-          const int mode = layer == kLDir ? kEpiDirect : (half == 0 ? kEpiStage : kEpiFlush);
-          if (layer == 7)
-            epi_64<kFmt, true, true, kDbg>(mode, ch, tD, tA, wsig + half * 128, staged, sig_acc,
-                                           &M->d_empty[b], dbg_row, skip);
-          else if (layer == kLFinal)
-            epi_64<kFmt, false, false, kDbg>(mode, ch, tD, tA, wsig, staged, sig_acc, &M->d_empty[b],
-                                             dbg_row, skip);
-          else
-            epi_64<kFmt, true, false, kDbg>(mode, ch, tD, tA, wsig, staged, sig_acc, &M->d_empty[b],
-                                            dbg_row, skip);
-          if (mode != kEpiStage) {
-            // A holds the next layer's full input
-            tmem_st_wait();
-            tc_fence_before_sync();
-            warp_arrive(&M->a_full[b]);
-          }
-          if (prof) {
-            const long long dt = clock64() - t_u0;
-            t_units += dt;
-            if (mode == kEpiStage) t_stage += dt; else t_flush += dt;
-          }
-
-          if (layer == 7 && half == 1) {
-            // ---------------- sigma head + alpha composite (rendering.py:121-143), done by
-            // the column-half-0 warps (one thread per row); half 1 hands over its partial dot
-            const long long t_c0 = prof ? clock64() : 0;
-            if (ch == 1) {
-              M->sig_part[b][row] = sig_acc;
-              pc_arrive(7 + b);
-            } else {
-              pc_sync(7 + b);
-              sigma = softplus_ref(sig_acc + M->sig_part[b][row] + blob[kSigmaBOff]);
-              if (!raw_mode) {
-                // per-row ray state is (re)loaded here rather than carried through the layers
-                const long long ray = valid ? p / P.S : 0;
-                const int s = valid ? (int)(p - ray * P.S) : 0;
-                const float z = valid ? __ldg(P.z_vals + p) : 0.f;
-                const float delta =
-                    valid ? ((s + 1 < P.S) ? __fsub_rn(__ldg(P.z_vals + p + 1), z) : 1e2f) : 0.f;
-                const float nz = (valid && P.noise) ? __ldg(P.noise + p) : 0.f;
-                const int s_first = (int)(tile_p0 % P.S);
-                const float alpha = valid ? 1.f - expf(-(delta * fmaxf(sigma + nz, 0.f))) : 0.f;
-                const float om = 1.f - alpha;
-                const int f0 = (valid && s == 0) ? 1 : 0;
-                // inclusive segmented product over the warp's 32 rows
-                float Pp = om;
-                int F = f0;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                  const float pn = __shfl_up_sync(0xffffffffu, Pp, d);
-                  const int fn = __shfl_up_sync(0xffffffffu, F, d);
-                  if (lane >= d) {
-                    if (!F) Pp *= pn;
-                    F |= fn;
-                  }
-                }
-                float Pe = __shfl_up_sync(0xffffffffu, Pp, 1);
-                int Fe = __shfl_up_sync(0xffffffffu, F, 1);
-                if (lane == 0) {
-                  Pe = 1.f;
-                  Fe = 0;
-                }
-                if (lane == 31) {
-                  M->scan_p[b][q] = Pp;
-                  M->scan_f[b][q] = F;
-                }
-                half_sync(b);
-                // carry of the ray that straddles the previous tile boundary
-                float cin_T = 1.f, cin_d = 0.f;
-                if (t > 0) {
-                  const uint32_t par = b ? (uint32_t)(pair & 1) : (uint32_t)((pair - 1) & 1);
-                  mbar_wait(&M->carry_a[1 - b], par, 40);
-                  if (s_first != 0) {
-                    cin_T = M->carry_T[1 - b];
-                    cin_d = M->carry_depth[1 - b];
-                  }
-                }
-                float pre = cin_T;
-                for (int w2 = 0; w2 < q; ++w2)
-                  pre = M->scan_f[b][w2] ? M->scan_p[b][w2] : pre * M->scan_p[b][w2];
-                const float T = f0 ? 1.f : (Fe ? Pe : pre * Pe);
-                w_ray = alpha * T;
-                if (valid) P.weights[p] = w_ray;
-                M->wray[b][row] = w_ray;
-                // inclusive segmented sum of w*z for the depth map
-                float Sd = w_ray * z;
-                int F2 = f0;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                  const float sn = __shfl_up_sync(0xffffffffu, Sd, d);
-                  const int fn = __shfl_up_sync(0xffffffffu, F2, d);
-                  if (lane >= d) {
-                    if (!F2) Sd += sn;
-                    F2 |= fn;
-                  }
-                }
-                if (lane == 31) M->scan_d[b][q] = Sd;
-                half_sync(b);
-                float pre_d = cin_d;
-                for (int w2 = 0; w2 < q; ++w2)
-                  pre_d = M->scan_f[b][w2] ? M->scan_d[b][w2] : pre_d + M->scan_d[b][w2];
-                const float D_incl = F2 ? Sd : pre_d + Sd;
-                const bool ray_end = valid && (s == P.S - 1);
-                if (ray_end) P.depth[ray] = D_incl;
-                if (row == nvalid - 1) {
-                  M->carry_T[b] = ray_end ? 1.f : T * om;
-                  M->carry_depth[b] = ray_end ? 0.f : D_incl;
-                  mbar_arrive(&M->carry_a[b]);
-                }
-                pc_arrive(5 + b);  // wray[] is published for the half-1 warps
-              }
-            }
-            if (prof) t_comp += clock64() - t_c0;
-          }
+        // ------------------------------------------------ rgb layer (64, sigmoid)
+        // the embedding buffer is dead (dir layer and every bias k-step of this tile have
+        // retired... except this unit's own bias k-step, which has retired too since the
+        // accumulator is complete): reuse it as the (row, channel) staging area,
+        // XOR-swizzled so both the row-wise writes and the channel-wise reads are
+        // bank-conflict free.  Each column half handles 32 of the 64 channels.
+        if (!raw_mode && ch == 1) {
+          pc_sync(5 + b);
+          w_ray = M->wray[b][row];
+        }
+        uint32_t v[32];
+        if (!skip) {
+          tmem_ld_x32(tD + 32 * ch, v);
+          tmem_ld_wait();
         } else {
-          // ------------------------------------------------ rgb layer (64, sigmoid)
-          // the embedding buffer is dead (dir layer and every bias k-step of this tile have
-          // retired... except this unit's own bias k-step, which has retired too since the
-          // accumulator is complete): reuse it as the (row, channel) staging area,
-          // XOR-swizzled so both the row-wise writes and the channel-wise reads are
-          // bank-conflict free.  Each column half handles 32 of the 64 channels.
-          if (!raw_mode && ch == 1) {
-            pc_sync(5 + b);
-            w_ray = M->wray[b][row];
-          }
-          uint32_t v[32];
-          if (!skip) {
-            tmem_ld_x32(tD + 32 * ch, v);
-            tmem_ld_wait();
-          } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0;
-          }
-          tc_fence_before_sync();
-          warp_arrive(&M->d_empty[b]);
+          for (int j = 0; j < 32; ++j) v[j] = 0;
+        }
+        tc_fence_before_sync();
+        warp_arrive(&M->d_empty[b]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float a = __uint_as_float(v[j]);
-            const float f = __fdividef(1.f, 1.f + __expf(-a));
-            const int chn = 32 * ch + j;
-            if (raw_mode) {
-              if (valid && !skip && !(P.mode & kModeSigmaOnly)) P.raw[p * 65 + chn] = f;
-            } else {
-              staging[row * 64 + (chn ^ (row & 31))] = w_ray * f;
-            }
-            if constexpr (kDbg) {
-              if (dbg_row) dbg_row[chn] = f;
-            }
-          }
+        for (int j = 0; j < 32; ++j) {
+          const float a = __uint_as_float(v[j]);
+          const float f = __fdividef(1.f, 1.f + __expf(-a));
+          const int chn = 32 * ch + j;
           if (raw_mode) {
-            if (valid && !skip && ch == 0) {
-              if (P.mode & kModeSigmaOnly)
-                P.raw[p] = sigma;
-              else
-                P.raw[p * 65 + 64] = sigma;
-            }
-            group_sync(b);  // the next tile's embedding overwrites the buffer both halves use
+            if (valid && !skip && !(P.mode & kModeSigmaOnly)) P.raw[p * 65 + chn] = f;
           } else {
-            const long long t_r0 = prof ? clock64() : 0;
-            group_sync(b);
-            const int s_first = (int)(tile_p0 % P.S);
-            const long long ray_first = tile_p0 / P.S;
-            const int n_seg = (s_first + nvalid + P.S - 1) / P.S;
-            const int cc = gtid & 63, hh = gtid >> 6;  // channel, row quarter
-            for (int sg = 0; sg < n_seg; ++sg) {
-              const int r_beg = max(0, sg * P.S - s_first);
-              const int r_end = min(nvalid, (sg + 1) * P.S - s_first);
-              const int lo = max(r_beg, 32 * hh), hi = min(r_end, 32 * hh + 32);
-              float acc = 0.f;
-              for (int r = lo; r < hi; ++r) acc += staging[r * 64 + (cc ^ (r & 31))];
-              M->part[b][hh][sg][cc] = acc;
-            }
-            group_sync(b);
-            if (hh == 0) {
-              if (t > 0) {
-                const uint32_t par = b ? (uint32_t)(pair & 1) : (uint32_t)((pair - 1) & 1);
-                mbar_wait(&M->carry_b[1 - b], par, 41);
-              }
-              float carry_out = 0.f;
-              for (int sg = 0; sg < n_seg; ++sg) {
-                float tot = (sg == 0 && s_first != 0) ? M->carry_feat[1 - b][cc] : 0.f;
-                tot += M->part[b][0][sg][cc];
-                tot += M->part[b][1][sg][cc];
-                tot += M->part[b][2][sg][cc];
-                tot += M->part[b][3][sg][cc];
-                const bool ends = ((sg + 1) * P.S - s_first) <= nvalid;
-                if (ends)
-                  P.feature[(ray_first + sg) * 64 + cc] = tot;
-                else
-                  carry_out = tot;
-              }
-              M->carry_feat[b][cc] = carry_out;
-              warp_arrive(&M->carry_b[b]);
-            }
-            if (prof) t_red += clock64() - t_r0;
+            staging[row * 64 + (chn ^ (row & 31))] = w_ray * f;
           }
+          if constexpr (kDbg) {
+            if (dbg_row) dbg_row[chn] = f;
+          }
+        }
+        if (raw_mode) {
+          if (valid && !skip && ch == 0) {
+            if (P.mode & kModeSigmaOnly)
+              P.raw[p] = sigma;
+            else
+              P.raw[p * 65 + 64] = sigma;
+          }
+          group_sync(b);  // the next tile's embedding overwrites the buffer both halves use
+        } else {
+          const long long t_r0 = prof ? clock64() : 0;
+          group_sync(b);
+          const int s_first = (int)(tile_p0 % P.S);
+          const long long ray_first = tile_p0 / P.S;
+          const int n_seg = (s_first + nvalid + P.S - 1) / P.S;
+          const int cc = gtid & 63, hh = gtid >> 6;  // channel, row quarter
+          for (int sg = 0; sg < n_seg; ++sg) {
+            const int r_beg = max(0, sg * P.S - s_first);
+            const int r_end = min(nvalid, (sg + 1) * P.S - s_first);
+            const int lo = max(r_beg, 32 * hh), hi = min(r_end, 32 * hh + 32);
+            float acc = 0.f;
+            for (int r = lo; r < hi; ++r) acc += staging[r * 64 + (cc ^ (r & 31))];
+            M->part[b][hh][sg][cc] = acc;
+          }
+          group_sync(b);
+          if (hh == 0) {
+            if (t > 0) {
+              const uint32_t par = b ? (uint32_t)(pair & 1) : (uint32_t)((pair - 1) & 1);
+              mbar_wait(&M->carry_b[1 - b], par, 41);
+            }
+            float carry_out = 0.f;
+            for (int sg = 0; sg < n_seg; ++sg) {
+              float tot = (sg == 0 && s_first != 0) ? M->carry_feat[1 - b][cc] : 0.f;
+              tot += M->part[b][0][sg][cc];
+              tot += M->part[b][1][sg][cc];
+              tot += M->part[b][2][sg][cc];
+              tot += M->part[b][3][sg][cc];
+              const bool ends = ((sg + 1) * P.S - s_first) <= nvalid;
+              if (ends)
+                P.feature[(ray_first + sg) * 64 + cc] = tot;
+              else
+                carry_out = tot;
+            }
+            M->carry_feat[b][cc] = carry_out;
+            warp_arrive(&M->carry_b[b]);
+          }
+          if (prof) t_red += clock64() - t_r0;
         }
       }
     }
@@ -816,7 +909,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       o[2] = t_emb;                // embedding phases
       o[3] = t_comp;               // sigma/alpha scan
       o[4] = t_red;                // feature reduction
-      o[5] = t_units;              // all layer epilogues (wake-up -> a_full/d_empty arrive)
+      o[5] = t_stage + t_flush;    // all layer epilogues (wake-up -> a_full/d_empty arrive)
       o[6] = t_stage;              // ... of which first halves (drain to registers)
       o[7] = t_flush;              // ... of which second halves / dir (drain + write A)
     }
@@ -1044,7 +1137,7 @@ int launch_render(const RenderArgs& a, cudaStream_t st) {
   P.dbg = g_dbg_layer >= 0 ? g_dbg_buf : nullptr;
   P.dbg_layer = g_dbg_layer;
   P.prof = g_dbg_layer <= -2 ? reinterpret_cast<long long*>(g_dbg_buf) : nullptr;
-  P.exp = g_dbg_layer <= -2 ? (-2 - g_dbg_layer) : 0;  // -2: profile, -3: exp 1, -4: exp 2, -5: both
+  P.exp = g_dbg_layer <= -2 ? (-2 - g_dbg_layer) : 0;  // -2: profile, -3: exp 1, -4: exp 2, -6: exp 4 (bit mask)
   P.n_points = a.n_points;
   P.S = a.n_samples > 0 ? a.n_samples : 1;
   P.n_freq_xyz = a.n_freq_xyz;

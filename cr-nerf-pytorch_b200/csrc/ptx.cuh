@@ -59,20 +59,22 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
 
 // Bounded wait: a protocol bug must not hang the GPU box.  On timeout the
 // waiting thread records which barrier it was stuck on and traps, which turns
-// a would-be hang into a launch failure the host reports.
-#ifndef CRNERF_WAIT_LIMIT_CYCLES
-#define CRNERF_WAIT_LIMIT_CYCLES (4000000000ll)  // ~2 s at 1.9 GHz
+// a would-be hang into a launch failure the host reports.  The bound is a spin
+// count (a failed try_wait suspends the thread for on the order of 100+ cycles,
+// so 2^24 spins is seconds); no clock reads or 64-bit math, to keep the many
+// inlined copies of this loop small - the render kernel is instruction-cache
+// sensitive.
+#ifndef CRNERF_WAIT_LIMIT_SPINS
+#define CRNERF_WAIT_LIMIT_SPINS (1u << 24)
 #endif
 __device__ unsigned int g_wait_timeout_tag = 0;
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && clock64() - t0 > CRNERF_WAIT_LIMIT_CYCLES) {
-      atomicExch(&g_wait_timeout_tag, 0x80000000u | (tag << 16) | (blockIdx.x & 0xffff));
-      __threadfence_system();
+    if (++spins == CRNERF_WAIT_LIMIT_SPINS) {
+      g_wait_timeout_tag = 0x80000000u | (tag << 16) | (blockIdx.x & 0xffff);
       __trap();
     }
   }
@@ -275,8 +277,14 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* v) {
       "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
-__device__ __forceinline__ void setmaxnreg_dec_64() { asm volatile("setmaxnreg.dec.sync.aligned.u32 64;"); }
-__device__ __forceinline__ void setmaxnreg_inc_104() { asm volatile("setmaxnreg.inc.sync.aligned.u32 104;"); }
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }

@@ -13,7 +13,9 @@ args = types.SimpleNamespace(nerf_out_dim=64, pertubeCord=False, img_wh=[64, 64]
 fine = NeRF_sigma('fine', args, in_channels_xyz=93, in_channels_dir=27).cuda()
 rays = oracle.pinhole_rays(64, 64, oracle.synthetic_pose(0)).cuda()
 EXPS = [(-2, "normal"), (-3, "EXP1: epilogue skips TMEM traffic + math"),
-        (-4, "EXP2: producer skips weight copies"), (-5, "EXP1+EXP2")]
+        (-4, "EXP2: producer skips weight copies"), (-5, "EXP1+EXP2"), (-6, "EXP4: no bias MMAs")]
+if len(sys.argv) > 1 and sys.argv[1] == "bias":
+    EXPS = [EXPS[0], EXPS[4]]
 if len(sys.argv) > 1 and sys.argv[1] == "quick":
     EXPS = EXPS[:1]
 for code, label in EXPS:
@@ -23,7 +25,7 @@ for code, label in EXPS:
     packed = fine.packed()
     for _ in range(2):
         ops.render_pass(packed, rays, z)
-    buf = torch.zeros(32, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(64, dtype=torch.int64, device="cuda")
     ops.debug_set(buf, code)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -39,7 +41,7 @@ for code, label in EXPS:
     for nm, off in (("X", 0), ("Y", 24)):
         lf = max(c[off], 1)
         print(f"   issuer {nm}: lifetime {c[off]}; blocked on " + ", ".join(
-            f"{name} {v} ({100*v/lf:.1f}%)" for name, v in zip(["emb_full", "a_full", "d_empty", "ring_full"], c[off+1:off+5])))
+            f"{name} {v} ({100*v/lf:.1f}%)" for name, v in zip(["emb_full", "a_full", "d_empty", "ring_full", "pipe_turn"], c[off+1:off+5] + [c[off+6]])) + f"; issue bursts {c[off+7]} ({100*c[off+7]/lf:.1f}%, {c[off+7]/pairs/19:.0f} cyc/unit)")
     for b in (0, 1):
         o = c[8 + 8*b: 8 + 8*b + 8]
         if o[0] == 0: continue

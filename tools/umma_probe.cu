@@ -40,9 +40,10 @@ struct Params {
   int grid;
   int commit_every;  // extra tcgen05.commit to a scratch mbarrier every n MMAs (0 = never)
   int alt;           // alternate between two accumulators every 16 MMAs
+  int acol;          // first TMEM column of the A operand (TS modes)
 };
 
-__global__ void __launch_bounds__(160, 1) probe_kernel(Params p) {
+__global__ void __launch_bounds__(672, 1) probe_kernel(Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // layout: A slabs (K/64 x 16 KB) | B slabs (K/64 x N*128 B) | barriers
   const int kslabs = p.K / 64;
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(160, 1) probe_kernel(Params p) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t a_tmem = tmem + 384;  // A operand columns (K/2 <= 128 cols)
+  const uint32_t a_tmem = tmem + p.acol;  // A operand columns (K/2 <= 128 cols)
   const uint32_t d_tmem = tmem + p.dcol;
 
   if (threadIdx.x == 0) {
@@ -138,6 +139,9 @@ __global__ void __launch_bounds__(160, 1) probe_kernel(Params p) {
       }
     }
   }
+  if (warp > 4) {  // extra pollers: spin on the "MMA done" barrier like the product kernel's epilogue warps
+    mbar_wait(&bars[1], 0, 4);
+  }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 4) tmem_dealloc<512>(tmem);
@@ -182,15 +186,18 @@ int main(int argc, char** argv) {
   int grid = argc > 7 ? atoi(argv[7]) : 1;
   int commit_every = argc > 8 ? atoi(argv[8]) : 0;
   int alt = argc > 9 ? atoi(argv[9]) : 0;
+  int acol = argc > 10 ? atoi(argv[10]) : 384;
   const int M = 128;
-  if (K % 64 || K > 256 || N % 16 || N > 256 || dcol + N > 384) {
+  if (K % 64 || K > 256 || N % 16 || N > 256 || dcol + N > 512 || acol + K / 2 > 512 ||
+      (acol < dcol + N * (alt ? 2 : 1) && dcol < acol + K / 2)) {
     printf("bad args\n");
     return 2;
   }
   srand(1234 + N + K + mode);
   std::vector<float> A(M * K), B(N * K);
-  for (auto& v : A) v = float(rand() % 9 - 4);
-  for (auto& v : B) v = float(rand() % 9 - 4) * 0.125f;
+  const int rnd = argc > 11 ? atoi(argv[11]) : 0;  // 1: dense random mantissas (power test; compare is loose)
+  for (auto& v : A) v = rnd ? float(rand() % 20001 - 10000) * 1.37e-4f : float(rand() % 9 - 4);
+  for (auto& v : B) v = rnd ? float(rand() % 20001 - 10000) * 0.93e-5f : float(rand() % 9 - 4) * 0.125f;
   std::vector<uint16_t> a_rm(M * K);
   for (int i = 0; i < M * K; ++i) a_rm[i] = to16(A[i], fmt);
   const int kslabs = K / 64;
@@ -245,9 +252,11 @@ int main(int argc, char** argv) {
   p.grid = grid;
   p.commit_every = commit_every;
   p.alt = alt;
+  p.acol = acol;
   size_t smem = kslabs * 16384 + kslabs * N * 128 + 1024;
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  probe_kernel<<<grid, 160, smem>>>(p);
+  const int pollers = argc > 12 ? atoi(argv[12]) : 0;  // extra warps spinning on an mbarrier
+  probe_kernel<<<grid, 160 + 32 * pollers, smem>>>(p);
   CK(cudaGetLastError());
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
@@ -280,8 +289,8 @@ int main(int argc, char** argv) {
     for (int i = 0; i < 48; ++i) printf(" %lld", ts[i]);
     printf("\n");
   }
-  printf("probe commit_every=%d alt=%d grid=%d mode=%d N=%d K=%d fmt=%d dcol=%d reps=%d: max_abs_err=%g mismatches=%d/%d  cycles=%lld (%.1f per MMA)  %s\n",
-         commit_every, alt, grid, mode, N, K, fmt, dcol, reps, maxerr, bad, M * N, cyc, double(cyc) / nmma,
+  printf("probe acol=%d commit_every=%d alt=%d grid=%d mode=%d N=%d K=%d fmt=%d dcol=%d reps=%d: max_abs_err=%g mismatches=%d/%d  cycles=%lld (%.1f per MMA)  %s\n",
+         acol, commit_every, alt, grid, mode, N, K, fmt, dcol, reps, maxerr, bad, M * N, cyc, double(cyc) / nmma,
          bad == 0 ? "OK" : "FAIL");
   if (bad && bad < M * N) {
     int shown = 0;
