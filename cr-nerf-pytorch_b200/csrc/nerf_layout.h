@@ -11,16 +11,17 @@
 //
 // A-operand sources of a chunk:
 //   kSrcEmb : the tile's embedding buffer in shared memory (SS MMA). 128 columns:
-//             [0,e_xyz) xyz embedding, zero pad, columns 93 and 94 hold the constant 1.0,
-//             [96,96+e_dir) dir embedding, zero pad to 128; two SW128 slabs of 64 columns.
+//             [0,e_xyz) xyz embedding, zero pad to 96, [96,96+e_dir) dir embedding, zero
+//             pad to 128; two SW128 slabs of 64 columns.
 //   kSrcAct : the previous layer's activations in TMEM (TS MMA), 2 values per column.
 //
-// Biases ride on the tensor core: every unit ends with a BIAS chunk, one 16-column
-// k-step whose A operand is embedding columns 80..95 (ones at 93, 94) and whose B
-// operand holds fp16(b) at K index 13 and fp16(b - fp16(b)) at K index 14 (zero
-// elsewhere), so D = W x + b to ~22 bits of b without a single epilogue instruction.
-// Bias chunks use the un-swizzled K-major "interleaved" layout (8x8 core matrices,
-// LBO 128 B between the two K halves, SBO 256 B between 8-row groups): rows*32 bytes.
+// Biases stay in fp32: the packer copies them into the side blob and the layer
+// epilogue adds them to the drained accumulator before the activation.  (An earlier
+// revision ran them through the tensor core as an extra 16-column k-step per unit;
+// that cost one ring slot, one weight copy, one MMA and one commit per unit - the
+// weight ring then held only 1.6 units and the issuer waited on it.  With pure
+// weight chunks a standard unit is exactly four 16 KB slabs and the 8-slot ring holds
+// two whole units.)
 //
 // build_program() is the single source of truth; host code runs it once and
 // uploads the tables to __constant__ memory for both kernels.
@@ -42,10 +43,7 @@ constexpr int kDirWidth = 128;   // W/2
 constexpr int kOutDim = 64;      // nerf_out_dim
 constexpr int kEmbCols = 128;    // embedding buffer columns (2 slabs of 64)
 constexpr int kDirCol0 = 96;     // first dir-embedding column in the buffer
-constexpr int kMaxExyz = 93, kMaxEdir = 32;
-constexpr int kOnesCol = 93;     // embedding columns kOnesCol, kOnesCol+1 are the constant 1.0
-constexpr int kBiasKstep = 5;    // k-step (16 columns) of the embedding buffer that holds them
-constexpr int kBiasKhi = kOnesCol - 16 * kBiasKstep;  // K index of fp16(b) inside a bias chunk (13)
+constexpr int kMaxExyz = 96, kMaxEdir = 32;
 
 enum LayerId : int {
   kL1 = 0,  // .. kL8 = 7
@@ -56,7 +54,7 @@ enum LayerId : int {
   kLSigma = 11  // not a tensor-core layer; index into the weight pointer array only
 };
 enum ASrc : int { kSrcEmb = 0, kSrcAct = 1 };
-enum ChunkKind : int { kKindWeights = 0, kKindBias = 1 };
+enum ChunkKind : int { kKindWeights = 0 };  // (kind 1 was the bias chunk of earlier revisions)
 
 struct Chunk {
   int32_t offset;   // byte offset in the packed image
@@ -96,10 +94,16 @@ struct Program {
   int32_t e_xyz, e_dir;
 };
 
-// fp32 side blob: sigma head weights (256) + bias; everything else is in the weight image
+// fp32 side blob: sigma head weights (256) + sigma bias, then the biases of the 11
+// tensor-core layers in LayerId order (9 x 256, 128, 64).  The kernel stages the whole blob
+// (11 KB) in shared memory: bias reads through L1 miss too often to sit in the epilogue.
 constexpr int kSigmaWOff = 0;
 constexpr int kSigmaBOff = 256;
-constexpr int kBlobFloats = 264;
+constexpr int kBiasOff = 264;
+constexpr int kBlobFloats = kBiasOff + 9 * 256 + 128 + 64;  // 2760
+CRNERF_HD inline int bias_offset(int layer) {  // float offset of a tensor-core layer's bias in the blob
+  return kBiasOff + (layer <= 8 ? 256 * layer : (layer == 9 ? 9 * 256 : 9 * 256 + 128));
+}
 
 // Index of each layer's tensors in the caller-provided pointer arrays
 // (crnerf_mlp_weights_t): xyz_encoding_1..8, xyz_encoding_final, dir_encoding,
@@ -134,22 +138,6 @@ inline void build_program(int e_xyz, int e_dir, Program* p) {
     c.a_k0 = (int16_t)a_k0;
     c.nk = (int16_t)((wcols + 15) / 16);
     c.kind = kKindWeights;
-    c.pad = 0;
-    off += c.bytes;
-  };
-  auto add_bias_chunk = [&](int layer, int row0, int rows) {
-    Chunk& c = p->chunks[nc++];
-    c.offset = off;
-    c.bytes = rows * 32;
-    c.layer = (int16_t)layer;
-    c.rows = (int16_t)rows;
-    c.row0 = (int16_t)row0;
-    c.wcol0 = 0;
-    c.wcols = 0;
-    c.a_src = (int16_t)kSrcEmb;
-    c.a_k0 = (int16_t)kBiasKstep;
-    c.nk = 1;
-    c.kind = kKindBias;
     c.pad = 0;
     off += c.bytes;
   };
@@ -193,24 +181,20 @@ inline void build_program(int e_xyz, int e_dir, Program* p) {
       } else {
         act_chunks(l, h * 128, 128, 0, kWidth);
       }
-      add_bias_chunk(l, h * 128, 128);
       end_unit();
     }
   }
   for (int h = 0; h < 2; ++h) {
     begin_unit(kLFinal, h, 128, h == 0, h == 1);
     act_chunks(kLFinal, h * 128, 128, 0, kWidth);
-    add_bias_chunk(kLFinal, h * 128, 128);
     end_unit();
   }
   begin_unit(kLDir, 0, 128, 1, 1);
   act_chunks(kLDir, 0, 128, 0, kWidth);
   emb_chunks(kLDir, 0, 128, kWidth, e_dir, kDirCol0);
-  add_bias_chunk(kLDir, 0, 128);
   end_unit();
   begin_unit(kLRgb, 0, 64, 1, 1);
   act_chunks(kLRgb, 0, 64, 0, kDirWidth);
-  add_bias_chunk(kLRgb, 0, 64);
   end_unit();
   p->n_chunks = nc;
   p->n_units = nu;

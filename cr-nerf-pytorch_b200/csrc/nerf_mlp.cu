@@ -63,7 +63,7 @@ struct Misc {
   // the issuers' copy of the program: constant-bank lookups indexed by a run-time value are
   // slow (tens to hundreds of cycles each), shared-memory loads are not
   //   unit_tab: n | first_of_layer << 8 | (layer == 0) << 9 | standard << 10 | chunk0 << 16 |
-  //             nchunks << 24; "standard" = four full activation slabs and a bias chunk
+  //             nchunks << 24; "standard" = exactly four full activation slabs
   //   meta_tab: c_meta
   uint32_t unit_tab[kMaxUnits];
   uint32_t meta_tab[kMaxChunks];
@@ -200,10 +200,9 @@ __device__ __forceinline__ bool emb_fast_ok(const EmbIn& e) {
 }
 // column c of [v, sin(2^0 v), cos(2^0 v), ...]; c is a constant after unrolling, and the
 // reduced argument of a (band, coordinate) pair is shared by its sin and cos columns (CSE)
-template <int kNFreq, bool kOnes>
+template <int kNFreq>
 __device__ __forceinline__ float emb_col(const EmbIn& e, int c) {
   if (c < 3) return e.v[c];
-  if (kOnes && (c == kOnesCol || c == kOnesCol + 1)) return 1.f;  // bias lanes (nerf_layout.h)
   if (c >= 3 + 6 * kNFreq) return 0.f;
   const int k = (c - 3) / 6, r = (c - 3) % 6, i = r % 3;
   const float sc = __int_as_float((127 + k) << 23);
@@ -213,7 +212,7 @@ __device__ __forceinline__ float emb_col(const EmbIn& e, int c) {
 }
 // 8*kNChunks consecutive columns -> kNChunks 16-byte stores into the swizzled buffer
 // embedding-column chunks [kSrc0, kSrc0+kNChunks) -> buffer chunks [kDst0, ...)
-template <int kFmt, int kNFreq, bool kOnes, int kSrc0, int kDst0, int kNChunks>
+template <int kFmt, int kNFreq, int kSrc0, int kDst0, int kNChunks>
 __device__ __forceinline__ void emb_write(uint8_t* buf, uint32_t row_off, uint32_t row_xor,
                                           const EmbIn& e) {
 #pragma unroll
@@ -221,8 +220,8 @@ __device__ __forceinline__ void emb_write(uint8_t* buf, uint32_t row_off, uint32
     uint32_t w[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      w[q] = pack2<kFmt, false>(emb_col<kNFreq, kOnes>(e, 8 * (kSrc0 + m) + 2 * q),
-                                emb_col<kNFreq, kOnes>(e, 8 * (kSrc0 + m) + 2 * q + 1));
+      w[q] = pack2<kFmt, false>(emb_col<kNFreq>(e, 8 * (kSrc0 + m) + 2 * q),
+                                emb_col<kNFreq>(e, 8 * (kSrc0 + m) + 2 * q + 1));
     const uint32_t cm = kDst0 + m;
     const uint32_t off = (cm >> 3) * 16384u + row_off + (((cm & 7u) << 4) ^ row_xor);
     *reinterpret_cast<uint4*>(buf + off) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -246,7 +245,7 @@ __device__ __noinline__ void embed3_generic(uint8_t* buf, int row, int col0, int
     }
   }
   for (int c = col0 + 3 + 6 * n_freqs; c < col_end; ++c)
-    emb_put<kFmt>(buf, row, c, (col0 == 0 && (c == kOnesCol || c == kOnesCol + 1)) ? 1.f : 0.f);
+    emb_put<kFmt>(buf, row, c, 0.f);
 }
 
 __device__ __forceinline__ float softplus_ref(float x) {
@@ -259,36 +258,45 @@ __device__ __forceinline__ float softplus_ref(float x) {
 // this warp's share of the fp32 sigma-head dot product of the layer-8 activations.
 // epi_stage / epi_flush below combine two slices into a layer-half epilogue.
 
-template <int kFmt, bool kRelu, bool kSigma, bool kDbg, int kOff, int kN>
-__device__ __forceinline__ void epi_slice32(const uint32_t (&v)[32], const float* wsig,
-                                            uint32_t (&out)[kN], float& sig_acc, float* dbg) {
-  if constexpr (kDbg) {
-    if (dbg) {
+template <int kFmt, bool kRelu, bool kSigma, bool kDbg, int kOff, int kN, int kCols = 32>
+__device__ __forceinline__ void epi_slice32(const uint32_t (&v)[kCols], const float* __restrict__ blob_g,
+                                            uint32_t boff, const float* wsig, uint32_t (&out)[kN],
+                                            float& sig_acc, float* dbg) {
+  // blob_g is the CTA's shared-memory copy of the side blob, boff an element offset
+  const float* bias = blob_g + boff;
+  // bias: consecutive fp32 values of the side blob in shared memory (same address in every
+  // lane -> one broadcast wavefront per 16 bytes), added in fp32 before the activation
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        dbg[j] = kRelu ? fmaxf(__uint_as_float(v[j]), 0.f) : __uint_as_float(v[j]);
+  for (int j = 0; j < 8; ++j) {
+    const float4 bv = *(reinterpret_cast<const float4*>(bias) + j);
+    const float x0 = __uint_as_float(v[4 * j]) + bv.x, x1 = __uint_as_float(v[4 * j + 1]) + bv.y;
+    const float x2 = __uint_as_float(v[4 * j + 2]) + bv.z, x3 = __uint_as_float(v[4 * j + 3]) + bv.w;
+    if constexpr (kDbg) {
+      if (dbg) {
+        dbg[4 * j] = kRelu ? fmaxf(x0, 0.f) : x0;
+        dbg[4 * j + 1] = kRelu ? fmaxf(x1, 0.f) : x1;
+        dbg[4 * j + 2] = kRelu ? fmaxf(x2, 0.f) : x2;
+        dbg[4 * j + 3] = kRelu ? fmaxf(x3, 0.f) : x3;
+      }
     }
-  }
-  if constexpr (kSigma) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    if constexpr (kSigma) {
       const float4 ws = *reinterpret_cast<const float4*>(wsig + 4 * j);
-      sig_acc = fmaf(fmaxf(__uint_as_float(v[4 * j]), 0.f), ws.x, sig_acc);
-      sig_acc = fmaf(fmaxf(__uint_as_float(v[4 * j + 1]), 0.f), ws.y, sig_acc);
-      sig_acc = fmaf(fmaxf(__uint_as_float(v[4 * j + 2]), 0.f), ws.z, sig_acc);
-      sig_acc = fmaf(fmaxf(__uint_as_float(v[4 * j + 3]), 0.f), ws.w, sig_acc);
+      sig_acc = fmaf(fmaxf(x0, 0.f), ws.x, sig_acc);
+      sig_acc = fmaf(fmaxf(x1, 0.f), ws.y, sig_acc);
+      sig_acc = fmaf(fmaxf(x2, 0.f), ws.z, sig_acc);
+      sig_acc = fmaf(fmaxf(x3, 0.f), ws.w, sig_acc);
     }
+    out[kOff + 2 * j] = pack2<kFmt, kRelu>(x0, x1);
+    out[kOff + 2 * j + 1] = pack2<kFmt, kRelu>(x2, x3);
   }
-#pragma unroll
-  for (int j = 0; j < 16; ++j)
-    out[kOff + j] = pack2<kFmt, kRelu>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
 }
 
 // First half of a 256-wide layer: drain this warp's 64 accumulator columns into 32 packed
 // words that stay in registers (A is still being read by the layer's second half).
 template <int kFmt, bool kRelu, bool kSigma, bool kDbg>
-__device__ __forceinline__ void epi_stage(uint32_t tD_ch, const float* wsig_ch, uint32_t (&staged)[32],
-                                          float& sig_acc, uint64_t* d_empty, float* dbg, bool skip) {
+__device__ __forceinline__ void epi_stage(uint32_t tD_ch, const float* blob_g, uint32_t boff, const float* wsig_ch,
+                                          uint32_t (&staged)[32], float& sig_acc, uint64_t* d_empty,
+                                          float* dbg, bool skip) {
   if (kDbg && skip) {
     tc_fence_before_sync();
     warp_arrive(d_empty);
@@ -298,19 +306,20 @@ __device__ __forceinline__ void epi_stage(uint32_t tD_ch, const float* wsig_ch, 
   tmem_ld_x32(tD_ch, va);
   tmem_ld_wait();
   tmem_ld_x32(tD_ch + 32, vb);  // in flight while the first slice is packed
-  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 32>(va, wsig_ch, staged, sig_acc, dbg);
+  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 32>(va, blob_g, boff, wsig_ch, staged, sig_acc, dbg);
   tmem_ld_wait();
   tc_fence_before_sync();
   warp_arrive(d_empty);  // accumulator drained: the issuer may overwrite it
-  epi_slice32<kFmt, kRelu, kSigma, kDbg, 16, 32>(vb, wsig_ch + 32, staged, sig_acc, dbg ? dbg + 32 : nullptr);
+  epi_slice32<kFmt, kRelu, kSigma, kDbg, 16, 32>(vb, blob_g, boff + 32u, wsig_ch + 32, staged, sig_acc,
+                                                 dbg ? dbg + 32 : nullptr);
 }
 
 // Second half (kDirect == false): every MMA of the layer has retired, so the staged first
 // half goes to A columns [32ch, 32ch+32) and this half's 64 columns to [64+32ch, ...).
 // kDirect (dir layer, 128 wide): this warp's 64 columns go to A columns [32ch, 32ch+32).
 template <int kFmt, bool kRelu, bool kSigma, bool kDbg, bool kDirect>
-__device__ __forceinline__ void epi_flush(uint32_t tD_ch, uint32_t tA_ch, const float* wsig_ch,
-                                          const uint32_t (&staged)[32], float& sig_acc,
+__device__ __forceinline__ void epi_flush(uint32_t tD_ch, uint32_t tA_ch, const float* blob_g, uint32_t boff,
+                                          const float* wsig_ch, const uint32_t (&staged)[32], float& sig_acc,
                                           uint64_t* d_empty, uint64_t* a_full, float* dbg, bool skip) {
   if (kDbg && skip) {
     tc_fence_before_sync();
@@ -324,12 +333,13 @@ __device__ __forceinline__ void epi_flush(uint32_t tD_ch, uint32_t tA_ch, const 
   tmem_ld_x32(tD_ch, va);
   tmem_ld_wait();
   tmem_ld_x32(tD_ch + 32, vb);
-  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 16>(va, wsig_ch, out, sig_acc, dbg);
+  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 16>(va, blob_g, boff, wsig_ch, out, sig_acc, dbg);
   tmem_st_x16p(a_dst, out);
   tmem_ld_wait();
   tc_fence_before_sync();
   warp_arrive(d_empty);  // accumulator drained: the issuer may overwrite it
-  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 16>(vb, wsig_ch + 32, out, sig_acc, dbg ? dbg + 32 : nullptr);
+  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 16>(vb, blob_g, boff + 32u, wsig_ch + 32, out, sig_acc,
+                                                dbg ? dbg + 32 : nullptr);
   tmem_st_x16p(a_dst + 16, out);
   // A holds the next layer's full input
   tmem_st_wait();
@@ -377,12 +387,11 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
   for (int i = tid; i < kBlobFloats; i += kThreads) blob[i] = P.blob[i];
   for (int i = tid; i < P.n_units; i += kThreads) {
     const Unit un = c_units[i];
-    bool standard = un.nchunks == 5;
+    bool standard = un.nchunks == 4;
     for (int j = 0; standard && j < 4; ++j) {
       const uint32_t m = c_meta[un.chunk0 + j];  // a_src | a_k0 << 8 | nk << 16 | bias flag 0x80
       standard = (m & 0xffu) == (uint32_t)kSrcAct && ((m >> 8) & 0xffu) == 4u * j && ((m >> 16) & 0xffu) == 4u;
     }
-    standard = standard && (c_meta[un.chunk0 + 4] & 0x80u) != 0;
     M->unit_tab[i] = (uint32_t)un.n | ((uint32_t)(un.first_of_layer != 0) << 8) |
                      ((uint32_t)(un.layer == 0) << 9) | ((uint32_t)standard << 10) |
                      ((uint32_t)un.chunk0 << 16) | ((uint32_t)un.nchunks << 24);
@@ -488,13 +497,9 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         const long long t_b0 = prof ? clock64() : 0;
         // ring slots are released by stream Y's commits (see ring_empty init)
         const bool release = b == 1 || solo;
-        const uint32_t a_bias = emb_lo + (uint32_t)b * (kEmbBufBytes >> 4) + (uint32_t)(kBiasKstep >> 2) * 1024u +
-                                (uint32_t)(kBiasKstep & 3) * 2u;
-        constexpr uint32_t kBiasHi = (256u >> 4) | (1u << 14);  // SBO 256 B | version | no swizzle
         if (elect_one()) {
           if (ut & 0x400u) {
-            // ---- standard unit: 16 TS MMAs over the four activation slabs + the bias k-step,
-            // straight-line
+            // ---- standard unit: 16 TS MMAs over the four activation slabs, straight-line
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t slot = (g0 + (uint32_t)j) % kSlots;
@@ -506,13 +511,6 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
               umma_ts(tD, a_t + 24u, desc(b_lo + 6u), idesc, 1u);
               if (release) umma_commit(&M->ring_empty[slot]);
             }
-            {
-              const uint32_t slot = (g0 + 4u) % kSlots;
-              const uint32_t b_lo = ring_lo + slot * (kSlotBytes >> 4);
-              const uint32_t bb_lo = (b_lo & 0xffffu) | ((128u >> 4) << 16);  // LBO 128 B
-              umma_ss(tD, desc(a_bias), (static_cast<uint64_t>(kBiasHi) << 32) | bb_lo, idesc, 1u);
-              if (release) umma_commit(&M->ring_empty[slot]);
-            }
           } else {
             // ---- embedding-fed and narrow units (layer 1, skip layer, dir, rgb): table-driven
             for (int j = 0; j < nch; ++j) {
@@ -522,13 +520,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
               const uint32_t a_k0 = (meta >> 8) & 0xffu;
               const uint32_t acc0 = j ? 1u : 0u;
               const int nk = (int)((meta >> 16) & 0xffu);
-              if (kDbg && (meta & 0x80u) && (P.exp & 4)) {
-                // profiling experiment 4: no bias MMA (results are wrong, timing only)
-              } else if (meta & 0x80u) {
-                // bias: one k-step, ones columns of the embedding x [fp16(b), fp16(b - fp16(b))]
-                const uint32_t bb_lo = (b_lo & 0xffffu) | ((128u >> 4) << 16);  // LBO 128 B
-                umma_ss(tD, desc(a_bias), (static_cast<uint64_t>(kBiasHi) << 32) | bb_lo, idesc, acc0);
-              } else if ((meta & 0x7fu) == (uint32_t)kSrcEmb) {
+              if ((meta & 0x7fu) == (uint32_t)kSrcEmb) {
                 const uint32_t a_lo = emb_lo + (uint32_t)b * (kEmbBufBytes >> 4) + (a_k0 >> 2) * 1024u +
                                       (a_k0 & 3u) * 2u;
                 for (int k = 0; k < nk; ++k)
@@ -629,11 +621,11 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         if (fast) {
           emb_prepare(ex);
           if (ch == 0) {
-            emb_write<kFmt, 15, true, 0, 0, 8>(my_emb, row_off, row_xor, ex);    // columns 0..63
+            emb_write<kFmt, 15, 0, 0, 8>(my_emb, row_off, row_xor, ex);    // columns 0..63
           } else {
             emb_prepare(ed);
-            emb_write<kFmt, 15, true, 8, 8, 4>(my_emb, row_off, row_xor, ex);    // columns 64..95
-            emb_write<kFmt, 4, false, 0, 12, 4>(my_emb, row_off, row_xor, ed);   // columns 96..127
+            emb_write<kFmt, 15, 8, 8, 4>(my_emb, row_off, row_xor, ex);    // columns 64..95
+            emb_write<kFmt, 4, 0, 12, 4>(my_emb, row_off, row_xor, ed);   // columns 96..127
           }
         } else if (ch == 0) {
           embed3_generic<kFmt>(my_emb, row, 0, kDirCol0, ex.v[0], ex.v[1], ex.v[2], P.n_freq_xyz);
@@ -645,8 +637,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         const float* xr = P.x + p * P.x_stride;
         if (ch == 0) {
           for (int c = 0; c < P.e_xyz; ++c) emb_put<kFmt>(my_emb, row, c, valid ? __ldg(xr + c) : 0.f);
-          for (int c = P.e_xyz; c < kDirCol0; ++c)
-            emb_put<kFmt>(my_emb, row, c, (c == kOnesCol || c == kOnesCol + 1) ? 1.f : 0.f);
+          for (int c = P.e_xyz; c < kDirCol0; ++c) emb_put<kFmt>(my_emb, row, c, 0.f);
         } else {
           for (int c = 0; c < P.e_dir; ++c)
             emb_put<kFmt>(my_emb, row, kDirCol0 + c,
@@ -661,6 +652,9 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       uint32_t staged[32];
       float sig_acc = 0.f, sigma = 0.f, w_ray = 0.f;
       const uint32_t tD_ch = tD + 64u * ch, tA_ch = tA + 32u * ch;
+      // this warp's first column in the blob's bias table (layer l starts at 256 l, second
+      // halves at +128; dir at 9*256, rgb at 9*256+128 - see bias_offset())
+      const uint32_t bias_ch = (uint32_t)(kBiasOff + 64 * ch);
       uint64_t* const d_full = &M->d_full[b];
       uint64_t* const d_empty = &M->d_empty[b];
       uint64_t* const a_full = &M->a_full[b];
@@ -686,23 +680,25 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       for (int layer = 0; layer < 7; ++layer) {
         wait_d();
         if (prof) t_a = clock64();
-        epi_stage<kFmt, true, false, kDbg>(tD_ch, wsig, staged, sig_acc, d_empty, dbg_at(layer, 0), skip);
+        const uint32_t bl = bias_ch + 256u * layer;
+        epi_stage<kFmt, true, false, kDbg>(tD_ch, blob, bl, wsig, staged, sig_acc, d_empty, dbg_at(layer, 0), skip);
         if (prof) t_stage += clock64() - t_a;
         wait_d();
         if (prof) t_a = clock64();
-        epi_flush<kFmt, true, false, kDbg, false>(tD_ch, tA_ch, wsig, staged, sig_acc, d_empty, a_full,
-                                                  dbg_at(layer, 1), skip);
+        epi_flush<kFmt, true, false, kDbg, false>(tD_ch, tA_ch, blob, bl + 128u, wsig, staged, sig_acc, d_empty,
+                                                  a_full, dbg_at(layer, 1), skip);
         if (prof) t_flush += clock64() - t_a;
       }
       // ---- layer 8: ReLU + this warp's share of the fp32 sigma-head dot product
       wait_d();
       if (prof) t_a = clock64();
-      epi_stage<kFmt, true, true, kDbg>(tD_ch, wsig + 64 * ch, staged, sig_acc, d_empty, dbg_at(7, 0), skip);
+      epi_stage<kFmt, true, true, kDbg>(tD_ch, blob, bias_ch + 256u * 7, wsig + 64 * ch, staged, sig_acc, d_empty,
+                                        dbg_at(7, 0), skip);
       if (prof) t_stage += clock64() - t_a;
       wait_d();
       if (prof) t_a = clock64();
-      epi_flush<kFmt, true, true, kDbg, false>(tD_ch, tA_ch, wsig + 128 + 64 * ch, staged, sig_acc, d_empty,
-                                               a_full, dbg_at(7, 1), skip);
+      epi_flush<kFmt, true, true, kDbg, false>(tD_ch, tA_ch, blob, bias_ch + 256u * 7 + 128u, wsig + 128 + 64 * ch,
+                                               staged, sig_acc, d_empty, a_full, dbg_at(7, 1), skip);
       if (prof) t_flush += clock64() - t_a;
       {
         const long long t_c0 = prof ? clock64() : 0;
@@ -799,18 +795,19 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       // ---- xyz_encoding_final: no activation
       wait_d();
       if (prof) t_a = clock64();
-      epi_stage<kFmt, false, false, kDbg>(tD_ch, wsig, staged, sig_acc, d_empty, dbg_at(kLFinal, 0), skip);
+      epi_stage<kFmt, false, false, kDbg>(tD_ch, blob, bias_ch + 256u * kLFinal, wsig, staged, sig_acc, d_empty,
+                                          dbg_at(kLFinal, 0), skip);
       if (prof) t_stage += clock64() - t_a;
       wait_d();
       if (prof) t_a = clock64();
-      epi_flush<kFmt, false, false, kDbg, false>(tD_ch, tA_ch, wsig, staged, sig_acc, d_empty, a_full,
-                                                 dbg_at(kLFinal, 1), skip);
+      epi_flush<kFmt, false, false, kDbg, false>(tD_ch, tA_ch, blob, bias_ch + 256u * kLFinal + 128u, wsig, staged,
+                                                 sig_acc, d_empty, a_full, dbg_at(kLFinal, 1), skip);
       if (prof) t_flush += clock64() - t_a;
       // ---- dir layer (128 wide, ReLU): straight to A columns [0,64)
       wait_d();
       if (prof) t_a = clock64();
-      epi_flush<kFmt, true, false, kDbg, true>(tD_ch, tA_ch, wsig, staged, sig_acc, d_empty, a_full,
-                                               dbg_at(kLDir, 0), skip);
+      epi_flush<kFmt, true, false, kDbg, true>(tD_ch, tA_ch, blob, bias_ch + 256u * 9, wsig, staged, sig_acc, d_empty,
+                                               a_full, dbg_at(kLDir, 0), skip);
       if (prof) t_flush += clock64() - t_a;
       // ---- rgb layer
       wait_d();
@@ -841,9 +838,9 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         warp_arrive(&M->d_empty[b]);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float a = __uint_as_float(v[j]);
-          const float f = __fdividef(1.f, 1.f + __expf(-a));
           const int chn = 32 * ch + j;
+          const float a = __uint_as_float(v[j]) + blob[bias_offset(kLRgb) + chn];
+          const float f = __fdividef(1.f, 1.f + __expf(-a));
           if (raw_mode) {
             if (valid && !skip && !(P.mode & kModeSigmaOnly)) P.raw[p * 65 + chn] = f;
           } else {
@@ -940,30 +937,6 @@ __global__ void pack_kernel(const __grid_constant__ PackParams P) {
     while (ci + 1 < P.n_chunks && c_chunks[ci + 1].offset <= byte) ++ci;
     const Chunk ch = c_chunks[ci];
     const int within = byte - ch.offset;
-    if (ch.kind == kKindBias) {
-      // interleaved K-major: [8-row group][K half][row in group] x 16 bytes
-      const int grp = within >> 8, khalf = (within >> 7) & 1, r = (within >> 4) & 7;
-      uint32_t out[4] = {0u, 0u, 0u, 0u};
-      if (khalf == (kBiasKhi >> 3)) {
-        const float bv = P.b[ch.layer][ch.row0 + grp * 8 + r];
-        float hi, lo;
-        if (P.fmt == 0) {
-          if (fabsf(bv) > 65504.f && P.status) atomicExch(P.status, 1);
-          hi = __half2float(__float2half_rn(fminf(fmaxf(bv, -65504.f), 65504.f)));
-          lo = __half2float(__float2half_rn(bv - hi));
-        } else {
-          hi = __bfloat162float(__float2bfloat16_rn(bv));
-          lo = __bfloat162float(__float2bfloat16_rn(bv - hi));
-        }
-        static_assert((kBiasKhi & 7) == 5, "bias hi/lo sit at elements 5 and 6 of the second K half");
-        const uint32_t w2 = P.fmt == 0 ? pack2<0, false>(0.f, hi) : pack2<1, false>(0.f, hi);  // elements 4,5
-        const uint32_t w3 = P.fmt == 0 ? pack2<0, false>(lo, 0.f) : pack2<1, false>(lo, 0.f);  // elements 6,7
-        out[2] = w2;
-        out[3] = w3;
-      }
-      *reinterpret_cast<uint4*>(P.img + byte) = make_uint4(out[0], out[1], out[2], out[3]);
-      continue;
-    }
     const int row = within >> 7;
     const int pos = (within & 127) >> 4;
     const int k0 = ((pos ^ (row & 7)) & 7) * 8;
@@ -987,10 +960,15 @@ __global__ void pack_kernel(const __grid_constant__ PackParams P) {
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kBlobFloats; i += gridDim.x * blockDim.x) {
     float v = 0.f;
-    if (i < kSigmaBOff)
+    if (i < kSigmaBOff) {
       v = P.w[kLSigma][i - kSigmaWOff];
-    else if (i == kSigmaBOff)
+    } else if (i == kSigmaBOff) {
       v = P.b[kLSigma][0];
+    } else if (i >= kBiasOff) {
+      const int k = i - kBiasOff;
+      const int layer = k < 9 * 256 ? k >> 8 : (k < 9 * 256 + 128 ? kLDir : kLRgb);
+      v = P.b[layer][i - bias_offset(layer)];
+    }
     P.blob[i] = v;
   }
 }
@@ -1017,8 +995,7 @@ int ensure_program(int e_xyz, int e_dir, cudaStream_t st, const Program** out) {
     static uint32_t meta[kMaxChunks];
     for (int i = 0; i < kMaxChunks; ++i)
       meta[i] = i < g_prog.n_chunks ? ((uint32_t)g_prog.chunks[i].a_src | ((uint32_t)g_prog.chunks[i].a_k0 << 8) |
-                                       ((uint32_t)g_prog.chunks[i].nk << 16) |
-                                       (g_prog.chunks[i].kind == kKindBias ? 0x80u : 0u))
+                                       ((uint32_t)g_prog.chunks[i].nk << 16))
                                     : 0u;
     // mark the first chunk of each run of full activation slabs inside a unit (bits 24+: run length 4 or 2)
     for (int u = 0; u < g_prog.n_units; ++u) {

@@ -38,13 +38,13 @@ def test_ctypes_binding_matches_header():
 def test_host_only_entry_points():
     from crnerf_b200 import _lib
     lib = _lib.load()
-    # weights: 77 chunks of 16 KB + 2 of 8 KB; biases: 19 chunks of 4 KB + 1 of 2 KB;
-    # + 264 fp32 side blob (sigma head)
-    assert lib.crnerf_mlp_packed_bytes(93, 27) == 77 * 16384 + 2 * 8192 + 19 * 4096 + 2048 + 264 * 4
+    # weights: 77 chunks of 16 KB + 2 of 8 KB; fp32 side blob: sigma head (264) + the biases
+    # of the 11 tensor-core layers (9*256 + 128 + 64)
+    assert lib.crnerf_mlp_packed_bytes(93, 27) == 77 * 16384 + 2 * 8192 + (264 + 2496) * 4
     assert lib.crnerf_style_scratch_floats(1024) > 296 * 1088
     buf = (ctypes.c_int32 * 4096)()
     n = lib.crnerf_debug_program(93, 27, buf, 4096)
-    assert n == 3 + 99 * 11 + 20 * 7 and buf[0] == 99 and buf[1] == 20
+    assert n == 3 + 79 * 11 + 20 * 7 and buf[0] == 79 and buf[1] == 20
     assert lib.crnerf_debug_program(200, 27, buf, 4096) < 0
     assert b"bad argument" in lib.crnerf_last_error()
 

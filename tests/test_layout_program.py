@@ -35,7 +35,6 @@ def emulate(p, x_xyz, x_dir, e_xyz, e_dir):
     emb = torch.zeros(n, 128, dtype=torch.float64)
     emb[:, :e_xyz] = x_xyz
     emb[:, 96:96 + e_dir] = x_dir
-    emb[:, 93:95] = 1.0          # the constant-one columns the bias chunks multiply
     act = torch.zeros(n, 256, dtype=torch.float64)
     acc = torch.zeros(n, 256, dtype=torch.float64)
     sigma = None
@@ -43,18 +42,9 @@ def emulate(p, x_xyz, x_dir, e_xyz, e_dir):
         key = LAYER_KEYS[u["layer"]]
         W, b = p[key + ".weight"].double(), p[key + ".bias"].double()
         d = torch.zeros(n, u["n"], dtype=torch.float64)
-        seen_bias = 0
         for c in chunks[u["chunk0"]: u["chunk0"] + u["nchunks"]]:
             assert c["layer"] == u["layer"] and c["rows"] == u["n"] and c["row0"] == u["half"] * 128
-            if c["kind"] == 1:
-                # bias chunk: one k-step over embedding columns 80..95; fp16(b) at K 13, the
-                # rounding remainder at K 14 (here: exact b at 13), ones at columns 93 / 94
-                assert c["a_src"] == 0 and c["a_k0"] == 5 and c["nk"] == 1 and c["bytes"] == c["rows"] * 32
-                wc = torch.zeros(c["rows"], 16, dtype=torch.float64)
-                wc[:, 13] = b[c["row0"]: c["row0"] + c["rows"]]
-                d += emb[:, 80:96] @ wc.t()
-                seen_bias += 1
-                continue
+            assert c["kind"] == 0      # pure weight chunks; biases live in the fp32 side blob
             assert c["nk"] == (c["wcols"] + 15) // 16 and c["bytes"] == c["rows"] * 128
             kk = c["nk"] * 16
             wc = torch.zeros(c["rows"], kk, dtype=torch.float64)
@@ -62,8 +52,8 @@ def emulate(p, x_xyz, x_dir, e_xyz, e_dir):
             src = emb if c["a_src"] == 0 else act
             a = src[:, c["a_k0"] * 16: c["a_k0"] * 16 + kk]
             d += a @ wc.t()
-        assert seen_bias == 1, "every unit carries exactly one bias chunk"
-        acc[:, u["half"] * 128: u["half"] * 128 + u["n"]] = d
+        # the layer epilogue adds the fp32 bias to the drained accumulator
+        acc[:, u["half"] * 128: u["half"] * 128 + u["n"]] = d + b[u["half"] * 128: u["half"] * 128 + u["n"]]
         if u["last"]:
             width = W.shape[0]
             y = acc[:, :width]
@@ -89,8 +79,6 @@ def test_program_covers_every_weight_once():
     for c in chunks:
         assert c["offset"] == off and c["offset"] % 16 == 0
         off += c["bytes"]
-        if c["kind"] == 1:
-            continue
         cover[c["layer"]][c["row0"]: c["row0"] + c["rows"], c["wcol0"]: c["wcol0"] + c["wcols"]] += 1
     for l, cv in enumerate(cover):
         assert int(cv.min()) == 1 and int(cv.max()) == 1, f"layer {l} not covered exactly once"
