@@ -45,6 +45,11 @@ RAY_SAMPLES_PER_STEP = N_RAYS * (NS + NI)     # 786,432
 POINTS_PER_STEP = N_RAYS * (NS + NS + NI)     # 1,048,576
 METRIC = "ray-samples/sec at 4096 rays x (64+128) samples"
 UNIT = "ray-samples/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of one fused fine-pass launch, from the committed
+# `ncu --set full` capture (bench.py cannot run ncu on itself); the kernel is tensor-bound,
+# HBM traffic is rays/z in, weights/feature/depth out plus the 1.3 MB weight image once
+NCU_DRAM_BYTES_PER_LAUNCH = 4678144
+NCU_TRAFFIC_SOURCE = "profiles/r01_ncu_fused_fine_pass_metrics.txt (dram__bytes_read.sum + dram__bytes_write.sum)"
 WORKLOAD = ("configs[1]: 4096-ray eval batches (slices of a 320x256 synthetic Brandenburg-Gate-shaped "
             "frame), 64 coarse + 128 fine samples, N_emb_xyz=15, N_emb_dir=4, nerf_out_dim=64, "
             "default-init weights seed 0")
@@ -291,7 +296,8 @@ def run_ours(args):
             pass
         roof = {"bound": "tensor", "kernel": "render_fused_kernel<fp16> fine pass, 4096x192 points",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes/launch",
+                "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src, "kernel_ms": k_ms,
                 "flop_per_launch": flop}
         if world == 1 and not args.no_cpu_baseline:
             cores = torch.get_num_threads()

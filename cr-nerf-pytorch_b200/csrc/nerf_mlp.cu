@@ -198,17 +198,57 @@ __device__ __forceinline__ void emb_prepare(EmbIn& e) {
 __device__ __forceinline__ bool emb_fast_ok(const EmbIn& e) {
   return fmaxf(fmaxf(fabsf(e.v[0]), fabsf(e.v[1])), fabsf(e.v[2])) < 1024.f;
 }
-// column c of [v, sin(2^0 v), cos(2^0 v), ...]; c is a constant after unrolling, and the
-// reduced argument of a (band, coordinate) pair is shared by its sin and cos columns (CSE)
+// sin/cos of band k, coordinate i.  Every third band is evaluated on the SFU from its own
+// reduced argument; the two bands above it come from the double-angle identities
+// (sin 2a = 2 sin a cos a, cos 2a = 1 - 2 sin^2 a: error x2 per step, <= 4e-6 after two,
+// still far below the 2^-11 operand rounding).  The SFU is quarter rate and four warps per
+// scheduler embed at the same time, so MUFU count - 114 per point without this, 48 with -
+// is what bounds the embedding phase.  k and i are constants after unrolling; the compiler
+// shares each (band, coordinate) evaluation between the columns that use it (CSE).
+template <int k>
+__device__ __forceinline__ void emb_sincos(const EmbIn& e, int i, float& s, float& c) {
+  if constexpr (k % 3 == 0) {
+    const float sc = __int_as_float((127 + k) << 23);
+    const float hk = e.hi[i] * sc, lk = e.lo[i] * sc;
+    const float a = ((hk - rintf(hk)) + lk) * 6.283185307179586f;
+    s = __sinf(a);
+    c = __cosf(a);
+  } else {
+    float s0, c0;
+    emb_sincos<k - 1>(e, i, s0, c0);
+    s = 2.f * s0 * c0;
+    c = fmaf(-2.f * s0, s0, 1.f);
+  }
+}
+template <int k>
+__device__ __forceinline__ float emb_band(const EmbIn& e, int r) {
+  float s, c;
+  emb_sincos<k>(e, r % 3, s, c);
+  return r < 3 ? s : c;
+}
+// column c of [v, sin(2^0 v), cos(2^0 v), ...]; c is a constant after unrolling
 template <int kNFreq>
 __device__ __forceinline__ float emb_col(const EmbIn& e, int c) {
   if (c < 3) return e.v[c];
   if (c >= 3 + 6 * kNFreq) return 0.f;
-  const int k = (c - 3) / 6, r = (c - 3) % 6, i = r % 3;
-  const float sc = __int_as_float((127 + k) << 23);
-  const float hk = e.hi[i] * sc, lk = e.lo[i] * sc;
-  const float a = ((hk - rintf(hk)) + lk) * 6.283185307179586f;
-  return r < 3 ? __sinf(a) : __cosf(a);
+  const int k = (c - 3) / 6, r = (c - 3) % 6;
+  switch (k) {
+    case 0: return emb_band<0>(e, r);
+    case 1: return emb_band<1>(e, r);
+    case 2: return emb_band<2>(e, r);
+    case 3: return emb_band<3>(e, r);
+    case 4: return emb_band<4>(e, r);
+    case 5: return emb_band<5>(e, r);
+    case 6: return emb_band<6>(e, r);
+    case 7: return emb_band<7>(e, r);
+    case 8: return emb_band<8>(e, r);
+    case 9: return emb_band<9>(e, r);
+    case 10: return emb_band<10>(e, r);
+    case 11: return emb_band<11>(e, r);
+    case 12: return emb_band<12>(e, r);
+    case 13: return emb_band<13>(e, r);
+    default: return emb_band<14>(e, r);
+  }
 }
 // 8*kNChunks consecutive columns -> kNChunks 16-byte stores into the swizzled buffer
 // embedding-column chunks [kSrc0, kSrc0+kNChunks) -> buffer chunks [kDst0, ...)
@@ -467,6 +507,11 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         // ---- everything this unit depends on is awaited BEFORE the pipe turn, so the turn
         // holder issues one uninterrupted burst: the tcgen05 queue is only 1-2 MMAs deep and
         // the pipe idles whenever the issuing thread does anything else for long.
+        // weight chunks first: they were requested when the partner's unit before last freed
+        // their slots and have normally landed long ago, so these waits cost nothing and are
+        // off the epilogue -> issuer critical path
+        for (int j = 0; j < nch; ++j)
+          timed_wait(&M->ring_full[(g0 + j) % kSlots], ((g0 + j) / kSlots) & 1, 5, prof, w_ring);
         if (ut & 0x100u) {
           if (ut & 0x200u) {
             timed_wait(&M->emb_full[b], (uint32_t)pair & 1, 2, prof, w_emb);
@@ -476,10 +521,6 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
           }
         }
         timed_wait(&M->d_empty[b], (ucount & 1) ^ 1, 4, prof, w_d);
-        // every weight chunk of the unit as well: they were requested when the partner's
-        // previous unit freed their slots and have normally landed by now
-        for (int j = 0; j < nch; ++j)
-          timed_wait(&M->ring_full[(g0 + j) % kSlots], ((g0 + j) / kSlots) & 1, 5, prof, w_ring);
         // Take the tensor pipe for this whole unit, strictly alternating X, Y, X, ...
         // Left alone the two streams issue MMA by MMA in lock step, finish their units
         // together and then both sit in their epilogues with the pipe idle; with unit-sized

@@ -250,7 +250,9 @@ def test_render_pass_stagewise(name):
         we, fe, de = oracle._infer(p_cpu, g["rays"][:, 0:3], g["rays"][:, 3:6], dir_emb, z,
                                    zero if nz is None else noise, 15, 8192, 64, torch.float16)
         close(f, fe, f"{name}:{typ} feature vs emulation", **EMU)
-        close(w, we, f"{name}:{typ} weights vs emulation", rtol=5e-5, atol=2e-6)
+        # the kernel's embedding differs from the emulation's by <= 4e-6 (double-angle bands), which
+        # flips a few fp16 operand roundings; the peaky sigma head (x30) amplifies a flip to ~3e-6
+        close(w, we, f"{name}:{typ} weights vs emulation", rtol=5e-5, atol=5e-6)
         close(f, g["ref"][f"feature_{typ}"], f"{name}:{typ} feature vs reference", **REF)
         close(w, g["ref"][f"weights_{typ}"], f"{name}:{typ} weights vs reference", rtol=2e-4, atol=5e-6)
         close(d, g["ref"][f"depth_{typ}"], f"{name}:{typ} depth vs reference", rtol=2e-4, atol=2e-5)
