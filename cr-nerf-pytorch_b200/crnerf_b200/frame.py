@@ -101,10 +101,11 @@ def _gather_blocks(local: torch.Tensor, n_total: int, group, dim: int) -> torch.
     shape[dim] = per
     padded = local.new_zeros(shape)
     padded.narrow(dim, 0, local.shape[dim]).copy_(local)
-    buf = local.new_empty([world] + shape)
+    # concatenated-along-dim-0 output form (accepted by both NCCL and gloo), viewed as (world, ...)
+    buf = local.new_empty([world * shape[0]] + shape[1:])
     dist.all_gather_into_tensor(buf, padded.contiguous(), group=group)
     # (world, ..., per, ...) -> (..., world*per, ...)[:n_total]
-    buf = buf.movedim(0, dim)                       # (..., world, per, ...)
+    buf = buf.reshape([world] + shape).movedim(0, dim)   # (..., world, per, ...)
     new_shape = list(local.shape)
     new_shape[dim] = world * per
     return buf.reshape(new_shape).narrow(dim, 0, n_total)

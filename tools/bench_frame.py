@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""Whole-frame render (BASELINE configs[2]/[3]): rays sharded across the ranks of one box,
+cross-ray fusion + decoder in the sharded form, one rgb all-gather at the end.
+
+  python tools/bench_frame.py [--hw 256 320] [--ns 64 --ni 128] [--reps 3]
+  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/bench_frame.py ...
+
+Prints one JSON line per run on rank 0: frame time (CUDA events, max over ranks), ray-samples/s,
+and the stand-alone timing of the cross-ray block against its HBM roofline
+(algorithmic bytes = 3 reads of the (H*W,64) fp32 feature map + 12 B/pixel of rgb + 8.6 MB of FC weights)."""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "cr-nerf-pytorch_b200"), os.path.join(ROOT, "oracle"), ROOT):
+    sys.path.insert(0, p)
+import torch
+import torch.distributed as dist
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--hw", type=int, nargs=2, default=[256, 320])
+    ap.add_argument("--ns", type=int, default=64)
+    ap.add_argument("--ni", type=int, default=128)
+    ap.add_argument("--chunk", type=int, default=16384)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--scheme", default="stats")
+    a = ap.parse_args()
+    import crnerf_oracle as oracle
+    from bench import build_models
+    from models.nerf import PosEmbedding
+    from crnerf_b200.frame import render_frame_sharded, CudaStyleBackend, fuse_decode_sharded
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    models, margs = build_models()
+    models = {k: m.to(dev) for k, m in models.items()}
+    emb = {"xyz": PosEmbedding(14, 15), "dir": PosEmbedding(3, 4)}
+    h, w = a.hw
+    rays = oracle.pinhole_rays(h, w, oracle.synthetic_pose(0)).to(dev)
+    style = torch.rand(1, 64, 32, 32, generator=torch.Generator().manual_seed(1)).to(dev)
+
+    def frame():
+        return render_frame_sharded(models, emb, rays, style, (h, w), a.ns, a.ni, chunk=a.chunk,
+                                    scheme=a.scheme, args=margs)
+    def sync():
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+    frame(); sync()
+    ts = []
+    for _ in range(a.reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync(); e0.record(); rgb = frame(); e1.record(); sync()
+        ts.append(e0.elapsed_time(e1))
+    t = torch.tensor([min(ts)], device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    # cross-ray block alone on this rank's share (features resident)
+    n = h * w
+    feat = torch.rand(-(-n // world), 64, device=dev)
+    be = CudaStyleBackend(models["decoder"])
+    fuse_decode_sharded(be, feat, style, feat.shape[0] * world); sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): fuse_decode_sharded(be, feat, style, feat.shape[0] * world)
+    e1.record(); sync()
+    cr_ms = e0.elapsed_time(e1) / 5
+    if rank == 0:
+        bytes_alg = feat.shape[0] * (3 * 256 + 12) + 8.6e6
+        peak = 6555.5
+        try: peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception: pass
+        print(json.dumps({"workload": f"{h}x{w} frame, {a.ns}+{a.ni} samples, style_net fusion+decoder, scheme {a.scheme}",
+                          "n_gpus": world, "frame_ms": ms, "ray_samples_per_s": n * (a.ns + a.ni) / (ms * 1e-3),
+                          "crossray_ms_per_rank": cr_ms, "crossray_alg_bytes_per_rank": bytes_alg,
+                          "crossray_gbs": bytes_alg / (cr_ms * 1e-3) / 1e9, "hbm_peak_gbs": peak,
+                          "crossray_frac": bytes_alg / (cr_ms * 1e-3) / 1e9 / peak,
+                          "rgb_mean": float(rgb.mean())}), flush=True)
+    if world > 1: dist.destroy_process_group()
+
+if __name__ == "__main__":
+    main()
