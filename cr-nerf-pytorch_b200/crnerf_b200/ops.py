@@ -443,3 +443,76 @@ def style_apply(sw: StyleWeightsRef, content_rows: torch.Tensor, mean: torch.Ten
                                      rgb.data_ptr(), None, _style_scratch(dev, n).data_ptr(),
                                      _stream(dev)))
     return rgb
+
+
+# --------------------------------------------------------------------------
+# Training step: forward that stores the backward's inputs, composite backward
+def render_pass_train(packed: PackedMLP, rays: torch.Tensor, z_vals: torch.Tensor,
+                      noise: Optional[torch.Tensor] = None, view_dir: Optional[torch.Tensor] = None,
+                      n_freq_xyz: int = 15, n_freq_dir: int = 4):
+    """render_pass + saved activations.  Returns (weights, feature, depth, acts, raw):
+    acts is the flat 16-bit buffer of crnerf_render_pass_train (see ``split_acts``), raw is
+    (n_points, 65) fp32 [sigmoid features | softplus sigma]."""
+    lib = _lib.load()
+    rays = _c(_need(rays, "rays", 2))
+    z_vals = _c(_need(z_vals, "z_vals", 2))
+    n, s = z_vals.shape
+    if rays.shape != (n, 8):
+        raise ValueError(f"rays must be ({n}, 8), got {tuple(rays.shape)}")
+    if 3 + 6 * n_freq_xyz != packed.e_xyz or 3 + 6 * n_freq_dir != packed.e_dir:
+        raise ValueError("weights were packed for a different embedding width")
+    if noise is not None:
+        noise = _c(_need(noise, "noise", 2))
+    if view_dir is not None:
+        view_dir = _c(_need(view_dir, "view_dir", 2))
+    dev = rays.device
+    dt = torch.float16 if packed.operand == OPERAND_FP16 else torch.bfloat16
+    with torch.cuda.device(dev):
+        weights = torch.empty((n, s), dtype=torch.float32, device=dev)
+        feature = torch.empty((n, 64), dtype=torch.float32, device=dev)
+        depth = torch.empty((n,), dtype=torch.float32, device=dev)
+        acts = torch.empty((n * s * (9 * 256 + 128),), dtype=dt, device=dev)
+        raw = torch.empty((n * s, 65), dtype=torch.float32, device=dev)
+        if n == 0:
+            return weights, feature, depth, acts, raw
+        assert acts.numel() * 2 == lib.crnerf_render_acts_bytes(n * s)
+        check(lib.crnerf_render_pass_train(packed.buf.data_ptr(), packed.operand, rays.data_ptr(),
+                                           _p(view_dir), z_vals.data_ptr(), _p(noise), n, s,
+                                           n_freq_xyz, n_freq_dir, weights.data_ptr(),
+                                           feature.data_ptr(), depth.data_ptr(), acts.data_ptr(),
+                                           raw.data_ptr(), _stream(dev)))
+    return weights, feature, depth, acts, raw
+
+
+def split_acts(acts: torch.Tensor, n_points: int):
+    """Views into the saved-activation buffer: ([h1..h8, final] each (P,256), dir_out (P,128))."""
+    trunk = acts[: 9 * n_points * 256].view(9, n_points, 256)
+    dir_out = acts[9 * n_points * 256:].view(n_points, 128)
+    return trunk, dir_out
+
+
+def composite_backward(raw: torch.Tensor, z_vals: torch.Tensor, noise: Optional[torch.Tensor],
+                       g_feature: Optional[torch.Tensor], g_weights: Optional[torch.Tensor],
+                       g_depth: Optional[torch.Tensor]):
+    """Backward of the alpha composite: -> (d_rgb_pre (P,64), d_sigma_pre (P,))."""
+    lib = _lib.load()
+    raw = _c(_need(raw, "raw", 2))
+    z_vals = _c(_need(z_vals, "z_vals", 2))
+    n, s = z_vals.shape
+    if raw.shape != (n * s, 65):
+        raise ValueError("raw must be (n_rays*n_samples, 65)")
+    opt = lambda t, name, shape: None if t is None else _c(_need(t, name).reshape(shape))
+    noise = opt(noise, "noise", (n, s))
+    g_feature = opt(g_feature, "g_feature", (n, 64))
+    g_weights = opt(g_weights, "g_weights", (n, s))
+    g_depth = opt(g_depth, "g_depth", (n,))
+    dev = raw.device
+    with torch.cuda.device(dev):
+        d_rgb = torch.empty((n * s, 64), dtype=torch.float32, device=dev)
+        d_sig = torch.empty((n * s,), dtype=torch.float32, device=dev)
+        if n == 0:
+            return d_rgb, d_sig
+        check(lib.crnerf_composite_backward(raw.data_ptr(), z_vals.data_ptr(), _p(noise), _p(g_feature),
+                                            _p(g_weights), _p(g_depth), n, s, d_rgb.data_ptr(),
+                                            d_sig.data_ptr(), _stream(dev)))
+    return d_rgb, d_sig

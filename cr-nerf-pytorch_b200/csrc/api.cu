@@ -79,6 +79,10 @@ int style_forward(const crnerf_style_weights* w, const float* content, int64_t n
                   float* transmatrix, float* fused, float* scratch, cudaStream_t st);
 int cnn_forward(const crnerf_cnn_weights* cw, const float* x, int64_t n, int64_t ps, int64_t cs,
                 float* out, float* scratch, cudaStream_t st);
+// implemented in backward.cu
+int composite_backward(const float* raw, const float* z, const float* noise, const float* g_feature,
+                       const float* g_weights, const float* g_depth, int n_rays, int n_samples,
+                       float* d_rgb_pre, float* d_sigma_pre, cudaStream_t st);
 
 }  // namespace crnerf
 
@@ -110,10 +114,47 @@ int crnerf_mlp_pack(const crnerf_mlp_weights* w, int operand, void* packed, size
   return mlp_pack(w, operand, packed, packed_bytes, status_dev, (cudaStream_t)stream);
 }
 
+static int render_pass_impl(const void* packed, int operand, const float* rays, const float* view_dir,
+                            const float* z_vals, const float* noise, int n_rays, int n_samples,
+                            int n_freq_xyz, int n_freq_dir, float* weights, float* feature,
+                            float* depth, void* acts, float* raw_save, void* stream);
+
 int crnerf_render_pass(const void* packed, int operand, const float* rays, const float* view_dir,
                        const float* z_vals, const float* noise, int n_rays, int n_samples,
                        int n_freq_xyz, int n_freq_dir, float* weights, float* feature,
                        float* depth, void* stream) {
+  return render_pass_impl(packed, operand, rays, view_dir, z_vals, noise, n_rays, n_samples, n_freq_xyz,
+                          n_freq_dir, weights, feature, depth, nullptr, nullptr, stream);
+}
+
+size_t crnerf_render_acts_bytes(int64_t n_points) {
+  return n_points <= 0 ? 0 : (size_t)n_points * (9 * 256 + 128) * sizeof(uint16_t);
+}
+
+int crnerf_render_pass_train(const void* packed, int operand, const float* rays, const float* view_dir,
+                             const float* z_vals, const float* noise, int n_rays, int n_samples,
+                             int n_freq_xyz, int n_freq_dir, float* weights, float* feature,
+                             float* depth, void* acts, float* raw, void* stream) {
+  CRNERF_REQUIRE(acts && raw, "acts and raw are required (use crnerf_render_pass for inference)");
+  CRNERF_REQUIRE((reinterpret_cast<uintptr_t>(acts) & 15) == 0, "acts must be 16-byte aligned");
+  return render_pass_impl(packed, operand, rays, view_dir, z_vals, noise, n_rays, n_samples, n_freq_xyz,
+                          n_freq_dir, weights, feature, depth, acts, raw, stream);
+}
+
+int crnerf_composite_backward(const float* raw, const float* z_vals, const float* noise,
+                              const float* g_feature, const float* g_weights, const float* g_depth,
+                              int n_rays, int n_samples, float* d_rgb_pre, float* d_sigma_pre,
+                              void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return composite_backward(raw, z_vals, noise, g_feature, g_weights, g_depth, n_rays, n_samples,
+                            d_rgb_pre, d_sigma_pre, (cudaStream_t)stream);
+}
+
+static int render_pass_impl(const void* packed, int operand, const float* rays, const float* view_dir,
+                            const float* z_vals, const float* noise, int n_rays, int n_samples,
+                            int n_freq_xyz, int n_freq_dir, float* weights, float* feature,
+                            float* depth, void* acts, float* raw_save, void* stream) {
   int rc = device_check();
   if (rc) return rc;
   CRNERF_REQUIRE(packed && rays && z_vals && weights && feature && depth, "null argument");
@@ -142,6 +183,8 @@ int crnerf_render_pass(const void* packed, int operand, const float* rays, const
   a.weights = weights;
   a.feature = feature;
   a.depth = depth;
+  a.acts = acts;
+  a.raw_save = raw_save;
   return launch_render(a, (cudaStream_t)stream);
 }
 

@@ -34,6 +34,8 @@ struct RenderArgs {
   float* feature;
   float* depth;
   float* raw;  // (n,65) or (n,1) output of mlp_forward
+  void* acts;       // training forward: saved activations (crnerf_render_acts_bytes), or nullptr
+  float* raw_save;  // training forward: (n_points, 65), or nullptr
 };
 int launch_render(const RenderArgs& a, cudaStream_t st);
 size_t mlp_packed_bytes(int e_xyz, int e_dir);

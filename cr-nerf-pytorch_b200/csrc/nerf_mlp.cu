@@ -95,6 +95,8 @@ struct RenderParams {
   float* feature;
   float* depth;
   float* raw;
+  uint16_t* acts;    // training: per-layer A-operand activations (see crnerf_render_pass_train)
+  float* raw_save;   // training: (n_points, 65) [sigmoid features | softplus sigma]
   float* dbg;
   long long* prof;  // optional cycle counters of CTA 0 (tests / profiling only)
   int exp;          // profiling experiments (debug instantiation only): 1 = epilogue skips TMEM
@@ -333,10 +335,16 @@ __device__ __forceinline__ void epi_slice32(const uint32_t (&v)[kCols], const fl
 
 // First half of a 256-wide layer: drain this warp's 64 accumulator columns into 32 packed
 // words that stay in registers (A is still being read by the layer's second half).
-template <int kFmt, bool kRelu, bool kSigma, bool kDbg>
+// 16 packed words (32 activations of one row) -> 64 contiguous bytes of the saved-activation buffer
+__device__ __forceinline__ void save16(uint4* dst, const uint32_t* w) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+
+template <int kFmt, bool kRelu, bool kSigma, bool kDbg, bool kSave>
 __device__ __forceinline__ void epi_stage(uint32_t tD_ch, const float* blob_g, uint32_t boff, const float* wsig_ch,
                                           uint32_t (&staged)[32], float& sig_acc, uint64_t* d_empty,
-                                          float* dbg, bool skip) {
+                                          float* dbg, bool skip, uint4* asave) {
   if (kDbg && skip) {
     tc_fence_before_sync();
     warp_arrive(d_empty);
@@ -352,15 +360,22 @@ __device__ __forceinline__ void epi_stage(uint32_t tD_ch, const float* blob_g, u
   warp_arrive(d_empty);  // accumulator drained: the issuer may overwrite it
   epi_slice32<kFmt, kRelu, kSigma, kDbg, 16, 32>(vb, blob_g, boff + 32u, wsig_ch + 32, staged, sig_acc,
                                                  dbg ? dbg + 32 : nullptr);
+  if constexpr (kSave) {
+    if (asave) {
+      save16(asave, staged);
+      save16(asave + 4, staged + 16);
+    }
+  }
 }
 
 // Second half (kDirect == false): every MMA of the layer has retired, so the staged first
 // half goes to A columns [32ch, 32ch+32) and this half's 64 columns to [64+32ch, ...).
 // kDirect (dir layer, 128 wide): this warp's 64 columns go to A columns [32ch, 32ch+32).
-template <int kFmt, bool kRelu, bool kSigma, bool kDbg, bool kDirect>
+template <int kFmt, bool kRelu, bool kSigma, bool kDbg, bool kDirect, bool kSave>
 __device__ __forceinline__ void epi_flush(uint32_t tD_ch, uint32_t tA_ch, const float* blob_g, uint32_t boff,
                                           const float* wsig_ch, const uint32_t (&staged)[32], float& sig_acc,
-                                          uint64_t* d_empty, uint64_t* a_full, float* dbg, bool skip) {
+                                          uint64_t* d_empty, uint64_t* a_full, float* dbg, bool skip,
+                                          uint4* asave) {
   if (kDbg && skip) {
     tc_fence_before_sync();
     warp_arrive(d_empty);
@@ -375,21 +390,31 @@ __device__ __forceinline__ void epi_flush(uint32_t tD_ch, uint32_t tA_ch, const 
   tmem_ld_x32(tD_ch + 32, vb);
   epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 16>(va, blob_g, boff, wsig_ch, out, sig_acc, dbg);
   tmem_st_x16p(a_dst, out);
+  if constexpr (kSave) {
+    if (asave) save16(asave, out);
+  }
   tmem_ld_wait();
   tc_fence_before_sync();
   warp_arrive(d_empty);  // accumulator drained: the issuer may overwrite it
   epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 16>(vb, blob_g, boff + 32u, wsig_ch + 32, out, sig_acc,
                                                 dbg ? dbg + 32 : nullptr);
   tmem_st_x16p(a_dst + 16, out);
+  if constexpr (kSave) {
+    if (asave) save16(asave + 4, out);
+  }
   // A holds the next layer's full input
   tmem_st_wait();
   tc_fence_before_sync();
   warp_arrive(a_full);
 }
 
-template <int kFmt, bool kDbg>
+// kVariant: 0 production, 1 debug/profiling instrumentation, 2 training forward (also stores
+// every layer's A-operand activations and the per-point [features | sigma] for the backward)
+template <int kFmt, int kVariant>
 __global__ void __launch_bounds__(kThreads, 1)
 render_fused_kernel(const __grid_constant__ RenderParams P) {
+  constexpr bool kDbg = kVariant == 1;
+  constexpr bool kSave = kVariant == 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem + kRingOff;
   uint8_t* emb = smem + kEmbOff;
@@ -712,6 +737,18 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         }
         return nullptr;
       };
+      // training: where this warp's 64 activations of (layer, half) go in the saved-activation
+      // buffer: slots 0..8 (trunk 1-8, final) are (n_points, 256) halves, slot 9 (dir) (n_points, 128)
+      auto save_at = [&](int layer, int half) -> uint4* {
+        if constexpr (kSave) {
+          if (P.acts != nullptr && valid) {
+            const size_t off = layer < 9 ? ((size_t)layer * P.n_points + p) * 256 + half * 128 + 64 * ch
+                                         : ((size_t)9 * P.n_points) * 256 + (size_t)p * 128 + 64 * ch;
+            return reinterpret_cast<uint4*>(P.acts + off);
+          }
+        }
+        return nullptr;
+      };
       long long t_a = 0;
 
       // ---- trunk layers 1..7: ReLU.  The layer structure is spelled out here (the issuer
@@ -722,24 +759,26 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         wait_d();
         if (prof) t_a = clock64();
         const uint32_t bl = bias_ch + 256u * layer;
-        epi_stage<kFmt, true, false, kDbg>(tD_ch, blob, bl, wsig, staged, sig_acc, d_empty, dbg_at(layer, 0), skip);
+        epi_stage<kFmt, true, false, kDbg, kSave>(tD_ch, blob, bl, wsig, staged, sig_acc, d_empty, dbg_at(layer, 0),
+                                                  skip, save_at(layer, 0));
         if (prof) t_stage += clock64() - t_a;
         wait_d();
         if (prof) t_a = clock64();
-        epi_flush<kFmt, true, false, kDbg, false>(tD_ch, tA_ch, blob, bl + 128u, wsig, staged, sig_acc, d_empty,
-                                                  a_full, dbg_at(layer, 1), skip);
+        epi_flush<kFmt, true, false, kDbg, false, kSave>(tD_ch, tA_ch, blob, bl + 128u, wsig, staged, sig_acc,
+                                                         d_empty, a_full, dbg_at(layer, 1), skip, save_at(layer, 1));
         if (prof) t_flush += clock64() - t_a;
       }
       // ---- layer 8: ReLU + this warp's share of the fp32 sigma-head dot product
       wait_d();
       if (prof) t_a = clock64();
-      epi_stage<kFmt, true, true, kDbg>(tD_ch, blob, bias_ch + 256u * 7, wsig + 64 * ch, staged, sig_acc, d_empty,
-                                        dbg_at(7, 0), skip);
+      epi_stage<kFmt, true, true, kDbg, kSave>(tD_ch, blob, bias_ch + 256u * 7, wsig + 64 * ch, staged, sig_acc,
+                                               d_empty, dbg_at(7, 0), skip, save_at(7, 0));
       if (prof) t_stage += clock64() - t_a;
       wait_d();
       if (prof) t_a = clock64();
-      epi_flush<kFmt, true, true, kDbg, false>(tD_ch, tA_ch, blob, bias_ch + 256u * 7 + 128u, wsig + 128 + 64 * ch,
-                                               staged, sig_acc, d_empty, a_full, dbg_at(7, 1), skip);
+      epi_flush<kFmt, true, true, kDbg, false, kSave>(tD_ch, tA_ch, blob, bias_ch + 256u * 7 + 128u,
+                                                      wsig + 128 + 64 * ch, staged, sig_acc, d_empty, a_full,
+                                                      dbg_at(7, 1), skip, save_at(7, 1));
       if (prof) t_flush += clock64() - t_a;
       {
         const long long t_c0 = prof ? clock64() : 0;
@@ -751,6 +790,9 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         } else {
           pc_sync(7 + b);
           sigma = softplus_ref(sig_acc + M->sig_part[b][row] + blob[kSigmaBOff]);
+          if constexpr (kSave) {
+            if (P.raw_save != nullptr && valid) P.raw_save[p * 65 + 64] = sigma;
+          }
           if (!raw_mode) {
             // per-row ray state is (re)loaded here rather than carried through the layers
             const long long ray = valid ? p / P.S : 0;
@@ -836,19 +878,20 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       // ---- xyz_encoding_final: no activation
       wait_d();
       if (prof) t_a = clock64();
-      epi_stage<kFmt, false, false, kDbg>(tD_ch, blob, bias_ch + 256u * kLFinal, wsig, staged, sig_acc, d_empty,
-                                          dbg_at(kLFinal, 0), skip);
+      epi_stage<kFmt, false, false, kDbg, kSave>(tD_ch, blob, bias_ch + 256u * kLFinal, wsig, staged, sig_acc,
+                                                 d_empty, dbg_at(kLFinal, 0), skip, save_at(kLFinal, 0));
       if (prof) t_stage += clock64() - t_a;
       wait_d();
       if (prof) t_a = clock64();
-      epi_flush<kFmt, false, false, kDbg, false>(tD_ch, tA_ch, blob, bias_ch + 256u * kLFinal + 128u, wsig, staged,
-                                                 sig_acc, d_empty, a_full, dbg_at(kLFinal, 1), skip);
+      epi_flush<kFmt, false, false, kDbg, false, kSave>(tD_ch, tA_ch, blob, bias_ch + 256u * kLFinal + 128u, wsig,
+                                                        staged, sig_acc, d_empty, a_full, dbg_at(kLFinal, 1), skip,
+                                                        save_at(kLFinal, 1));
       if (prof) t_flush += clock64() - t_a;
       // ---- dir layer (128 wide, ReLU): straight to A columns [0,64)
       wait_d();
       if (prof) t_a = clock64();
-      epi_flush<kFmt, true, false, kDbg, true>(tD_ch, tA_ch, blob, bias_ch + 256u * 9, wsig, staged, sig_acc, d_empty,
-                                               a_full, dbg_at(kLDir, 0), skip);
+      epi_flush<kFmt, true, false, kDbg, true, kSave>(tD_ch, tA_ch, blob, bias_ch + 256u * 9, wsig, staged, sig_acc,
+                                                      d_empty, a_full, dbg_at(kLDir, 0), skip, save_at(kLDir, 0));
       if (prof) t_flush += clock64() - t_a;
       // ---- rgb layer
       wait_d();
@@ -882,6 +925,9 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
           const int chn = 32 * ch + j;
           const float a = __uint_as_float(v[j]) + blob[bias_offset(kLRgb) + chn];
           const float f = __fdividef(1.f, 1.f + __expf(-a));
+          if constexpr (kSave) {
+            if (P.raw_save != nullptr && valid) P.raw_save[p * 65 + chn] = f;
+          }
           if (raw_mode) {
             if (valid && !skip && !(P.mode & kModeSigmaOnly)) P.raw[p * 65 + chn] = f;
           } else {
@@ -1182,9 +1228,13 @@ int launch_render(const RenderArgs& a, cudaStream_t st) {
     P.pts_per_cta = rpc * S;
     grid = (int)((a.n_rays + rpc - 1) / rpc);
   }
+  P.acts = static_cast<uint16_t*>(a.acts);
+  P.raw_save = a.raw_save;
   const bool dbg = P.dbg != nullptr || P.prof != nullptr;
-  auto kern = operand == 0 ? (dbg ? render_fused_kernel<0, true> : render_fused_kernel<0, false>)
-                           : (dbg ? render_fused_kernel<1, true> : render_fused_kernel<1, false>);
+  const bool save = !dbg && (a.acts != nullptr || a.raw_save != nullptr);
+  auto kern = operand == 0
+                  ? (dbg ? render_fused_kernel<0, 1> : (save ? render_fused_kernel<0, 2> : render_fused_kernel<0, 0>))
+                  : (dbg ? render_fused_kernel<1, 1> : (save ? render_fused_kernel<1, 2> : render_fused_kernel<1, 0>));
   CRNERF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   kern<<<grid, kThreads, kSmemBytes, st>>>(P);
   count_launch();

@@ -20,12 +20,44 @@ from crnerf_b200 import ops
 from models.nerf_decoder_stylenerf import NeuralRenderer
 
 
-def _no_autograd(module, *tensors):
-    if torch.is_grad_enabled() and (any(t is not None and t.requires_grad for t in tensors) or
-                                    any(p.requires_grad for p in module.parameters())):
-        raise NotImplementedError(
-            "crnerf_b200 implements the inference path (torch.no_grad()); the fused backward is "
-            "not built yet - wrap the call in torch.no_grad() or freeze the parameters")
+import torch.nn.functional as F
+
+
+def _wants_grad(module, *tensors):
+    """True when the call must be recorded for autograd (the training step's decode())."""
+    return torch.is_grad_enabled() and (any(t is not None and t.requires_grad for t in tensors) or
+                                        any(p.requires_grad for p in module.parameters()))
+
+
+# Training-mode path of the cross-ray block.  The reference trains on 32x32 patches
+# (train_mask_grid_sample.py:127-149: 1,024 pixels), where this block is a few dozen
+# launch-bound library calls whichever way it is written; it therefore runs as plain
+# differentiable tensor ops (cuBLAS / cuDNN through autograd), while inference - whole
+# frames, where the block is HBM-bound - runs the streaming kernels of csrc/crossray.cu.
+def _cnn_torch(cnn, x):
+    """CNN.forward (reference linearStyleTransfer.py:28-37) as differentiable tensor ops."""
+    y = cnn.convs(x)
+    b, c, h, w = y.shape
+    y = y.reshape(b, c, h * w)
+    gram = torch.bmm(y, y.transpose(1, 2)) / (h * w)
+    return cnn.fc(gram.reshape(b, -1))
+
+
+def _mul_layer_torch(m, cF, sF):
+    """MulLayer.forward with trans=True (reference linearStyleTransfer.py:58-90)."""
+    cb, cc, ch, cw = cF.shape
+    c_mean = cF.reshape(cb, cc, -1).mean(dim=2).reshape(cb, cc, 1, 1)
+    cFc = cF - c_mean
+    sb, sc, _, _ = sF.shape
+    s_mean = sF.reshape(sb, sc, -1).mean(dim=2).reshape(sb, sc, 1, 1)
+    sFc = sF - s_mean
+    comp = m.compress(cFc)
+    comp = comp.reshape(cb, comp.shape[1], -1)
+    c_mat = _cnn_torch(m.cnet, cFc).reshape(cb, m.matrixSize, m.matrixSize)
+    s_mat = _cnn_torch(m.snet, sFc).reshape(sb, m.matrixSize, m.matrixSize)
+    trans = torch.bmm(s_mat, c_mat)
+    y = torch.bmm(trans, comp).reshape(cb, m.matrixSize, ch, cw)
+    return m.unzip(y) + s_mean, trans
 
 
 class _StyleParamsMixin:
@@ -58,7 +90,8 @@ class CNN(nn.Module, _StyleParamsMixin):
 
     def forward(self, x):
         """(1,64,H,W) -> (1,1024), reference linearStyleTransfer.py:28-37."""
-        _no_autograd(self, x)
+        if _wants_grad(self, x):
+            return _cnn_torch(self, x)
         return ops.cnn_forward(self._style_ref([("", "multi_net.cnet.")]), "cnet", x)
 
 
@@ -79,7 +112,8 @@ class MulLayer(nn.Module, _StyleParamsMixin):
         if not trans:
             # the reference's trans=False branch returns None (bare `return`, :91-93)
             return None
-        _no_autograd(self, cF, sF)
+        if _wants_grad(self, cF, sF):
+            return _mul_layer_torch(self, cF, sF)
         sw = self._style_ref([("", "multi_net.")])
         if not sw.has_decoder:
             # stand-alone MulLayer: the kernel still needs a 64->3 head to write; use zeros
@@ -105,7 +139,11 @@ class style_net(nn.Module, _StyleParamsMixin):
     def forward(self, content_feature, style_feature, type=None):
         """content (1,64,H,W), style (1,64,32,32) or None -> rgb (1,3,H,W),
         reference linearStyleTransfer.py:284-291."""
-        _no_autograd(self, content_feature, style_feature)
+        if _wants_grad(self, content_feature, style_feature):
+            if style_feature is None and type == "content":
+                return self.decoder(content_feature)
+            fused, _ = _mul_layer_torch(self.multi_net, content_feature, style_feature)
+            return self.decoder(fused)
         sw = self._style_ref([("", "")])
         if style_feature is None and type == "content":
             return ops.style_forward(sw, content_feature, None)

@@ -102,12 +102,17 @@ class NeRF_sigma(nn.Module):
             self._packed_key = key
         return self._packed
 
+    def wants_grad(self):
+        """True when the call must be recorded for autograd (training step)."""
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
     def _no_autograd(self, x):
         if torch.is_grad_enabled() and (x.requires_grad or
                                         any(p.requires_grad for p in self.parameters())):
             raise NotImplementedError(
-                "crnerf_b200 implements the inference path (torch.no_grad()); the fused backward "
-                "is not built yet - wrap the call in torch.no_grad() or freeze the parameters")
+                "NeRF_sigma.forward on pre-embedded rows is inference-only (torch.no_grad()); the "
+                "differentiable entry is models.rendering.render_rays_cross_ray, which is what the "
+                "reference's training step calls")
 
     def forward(self, x, sigma_only=False, output_random=True):
         """(B, in_channels_xyz+in_channels_dir) -> (B, nerf_out_dim+1) = [features | sigma],

@@ -65,12 +65,11 @@ class NeuralRenderer(nn.Module):
     def forward(self, x):
         """(1,64,H,W) -> (1,3,H,W) = sigmoid(conv1x1(x)), reference :279-291."""
         conv = self.feat_2_rgb_list[0]
-        if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
-            raise NotImplementedError(
-                "crnerf_b200 implements the inference path (torch.no_grad()); wrap the call in "
-                "torch.no_grad() or freeze the parameters")
         if not self.final_actvn:
             raise NotImplementedError("final_actvn=False leaves `rgbs` undefined in the reference (:289-291)")
+        if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
+            # training step (32x32 patches): differentiable tensor ops, see linearStyleTransfer.py
+            return torch.sigmoid(conv(x))
         params = {"decoder.feat_2_rgb_list.0.weight": conv.weight,
                   "decoder.feat_2_rgb_list.0.bias": conv.bias}
         key = ops.StyleWeightsRef.version_key(params)

@@ -13,6 +13,7 @@ handed to the kernels, so seeded CUDA runs consume the generator identically.
 """
 import torch
 
+from crnerf_b200 import autograd as crnerf_autograd
 from crnerf_b200 import ops
 
 __all__ = ['render_rays_cross_ray']
@@ -51,7 +52,8 @@ def render_rays_cross_ray(models,
                           **kwargs):
     """Render rays: coarse pass, importance resampling, fine pass.
 
-    Same contract as reference models/rendering.py:50-196.  ``ts``, ``chunk``,
+    Same contract as reference models/rendering.py:50-196, including autograd with respect to
+    the models' parameters (crnerf_b200/autograd.py) when called with gradients enabled.  ``ts``, ``chunk``,
     ``white_back`` and ``test_time`` are accepted and unused, as in the reference
     (point chunking is unnecessary because no per-point tensor is
     materialised).  Returns ``weights_{typ} (N,S)``, ``feature_{typ} (N,64)``,
@@ -66,7 +68,6 @@ def render_rays_cross_ray(models,
         raise ops.CrnerfError(f"rays are on {rays.device}: crnerf_b200 renders on CUDA (sm_100) only "
                               "and has no CPU fallback")
     coarse = models['coarse']
-    coarse._no_autograd(rays)
     n_fx, n_fd = _n_freqs(embeddings['xyz']), _n_freqs(embeddings['dir'])
     rays = rays.contiguous().float()
     N_rays = rays.shape[0]
@@ -85,8 +86,12 @@ def render_rays_cross_ray(models,
     def run(model, z):
         # the reference always draws the noise tensor, even when noise_std == 0 (:125)
         noise = torch.randn(z.shape, device=dev) * noise_std
-        w, f, d = ops.render_pass(model.packed(), rays, z, noise if noise_std != 0 else None,
-                                  view_dir, n_fx, n_fd)
+        noise = noise if noise_std != 0 else None
+        if model.wants_grad():
+            # training step: same fused kernel, plus saved activations for the backward
+            w, f, d = crnerf_autograd.render_pass(model, rays, z, noise, view_dir, n_fx, n_fd)
+        else:
+            w, f, d = ops.render_pass(model.packed(), rays, z, noise, view_dir, n_fx, n_fd)
         typ = model.typ
         results[f'weights_{typ}'] = w
         results[f'feature_{typ}'] = f

@@ -95,6 +95,31 @@ int crnerf_render_pass(const void* packed, int operand, const float* rays, const
                        int n_freq_xyz, int n_freq_dir, float* weights, float* feature,
                        float* depth, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Training step (train_mask_grid_sample.py:186-197 calls render_rays_cross_ray under autograd).
+ * crnerf_render_pass_train = crnerf_render_pass that additionally stores what the backward
+ * needs, so nothing is recomputed and no (points x width) fp32 tensor is ever built:
+ *   acts  crnerf_render_acts_bytes(n_rays*n_samples) bytes, 16-bit (the operand format):
+ *         slots 0..8 = outputs of xyz_encoding_1..8 (post-ReLU) and xyz_encoding_final,
+ *         each (n_points, 256); slot 9 = dir_encoding output (post-ReLU), (n_points, 128)
+ *   raw   (n_points, 65) fp32 = [sigmoid features | softplus sigma]   (models/nerf.py:180-181)
+ * crnerf_composite_backward is the backward of rendering.py:116-143: from the gradients of
+ * feature (n_rays,64), weights (n_rays,n_samples), depth (n_rays) (each may be NULL) to the
+ * gradients of the pre-sigmoid features d_rgb_pre (n_points,64) and of the pre-softplus
+ * density d_sigma_pre (n_points).  n_samples <= 1024.  The twelve dgrad/wgrad GEMM pairs that
+ * follow are plain dense GEMMs over `acts` and are left to the caller's BLAS (the Python
+ * mirror calls cuBLAS through its tensor library, see crnerf_b200/autograd.py).
+ * ---------------------------------------------------------------------- */
+size_t crnerf_render_acts_bytes(int64_t n_points);
+int crnerf_render_pass_train(const void* packed, int operand, const float* rays, const float* view_dir,
+                             const float* z_vals, const float* noise, int n_rays, int n_samples,
+                             int n_freq_xyz, int n_freq_dir, float* weights, float* feature,
+                             float* depth, void* acts, float* raw, void* stream);
+int crnerf_composite_backward(const float* raw, const float* z_vals, const float* noise,
+                              const float* g_feature, const float* g_weights, const float* g_depth,
+                              int n_rays, int n_samples, float* d_rgb_pre, float* d_sigma_pre,
+                              void* stream);
+
 /* NeRF_sigma.forward on pre-embedded rows (models/nerf.py:157-182):
  *   x (n, x_stride) with [0,e_xyz) xyz embedding, [e_xyz, e_xyz+e_dir) dir
  *   embedding; out (n, 65) = [sigmoid features(64) | softplus sigma].
