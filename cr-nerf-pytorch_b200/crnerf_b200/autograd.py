@@ -67,24 +67,22 @@ class RenderPassFn(torch.autograd.Function):
         with _matmul_mode():
             # static_rgb: sigmoid already folded into d_rgb (index 10)
             gW[10] = _mm(d_rgb.t(), dir_out)
-            gB[10] = d_rgb.sum(0)
+            gB[10] = ops.relu_bias_grad(d_rgb, None)
             g = _mm(d_rgb, W[10])
-            g = g * (dir_out > 0)                         # dir_encoding ReLU (index 9)
+            gB[9] = ops.relu_bias_grad(g, dir_out)        # dir_encoding ReLU mask + bias grad (index 9)
             fin = trunk[8]
             gW[9] = torch.cat([_mm(g.t(), fin), _mm(g.view(n, s, 128).sum(1).t(), emb_dir)], dim=1)
-            gB[9] = g.sum(0)
             g = _mm(g, W[9][:, :256])                     # xyz_encoding_final (index 8), no activation
             h8 = trunk[7]
             gW[8] = _mm(g.t(), h8)
-            gB[8] = g.sum(0)
+            gB[8] = ops.relu_bias_grad(g, None)
             g = _mm(g, W[8])
             # static_sigma (index 11) joins at h8
             gW[11] = _mm(d_sig[None, :], h8)
             gB[11] = d_sig.sum().reshape(1)
             g = g + d_sig[:, None] * W[11].float()
-            for l in range(7, -1, -1):                    # xyz_encoding_{l+1}: ReLU
-                g = g * (trunk[l] > 0)
-                gB[l] = g.sum(0)
+            for l in range(7, -1, -1):                    # xyz_encoding_{l+1}: ReLU mask + bias grad
+                gB[l] = ops.relu_bias_grad(g, trunk[l])
                 if l == 0:
                     gW[l] = _mm(g.t(), emb_xyz)
                     break

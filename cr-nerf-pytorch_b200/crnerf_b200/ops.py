@@ -68,8 +68,18 @@ def device_ok() -> bool:
 class PackedMLP:
     """Tensor-core-ready image of one NeRF_sigma's weights (see csrc/nerf_layout.h)."""
 
-    def __init__(self, buf: torch.Tensor, operand: int, e_xyz: int, e_dir: int):
+    def __init__(self, buf: torch.Tensor, operand: int, e_xyz: int, e_dir: int, status=None):
         self.buf, self.operand, self.e_xyz, self.e_dir = buf, operand, e_xyz, e_dir
+        self.status = status     # device int32: 1 if a weight left the operand format's range
+
+    def check_range(self):
+        """Raise if the pack kernel saw a weight outside the fp16 range (host sync on first call)."""
+        if self.status is not None:
+            bad = int(self.status.item()) != 0
+            self.status = None
+            if bad:
+                raise CrnerfError("a NeRF weight exceeds the fp16 finite range (|w| > 65504); "
+                                  "pack with operand='bf16'")
 
     @property
     def device(self):
@@ -77,8 +87,10 @@ class PackedMLP:
 
 
 def pack_mlp(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], e_xyz: int,
-             e_dir: int, operand="fp16", check_range: bool = True) -> PackedMLP:
-    """weights/biases: the 12 nn.Linear tensors in ``MLP_LAYER_KEYS`` order."""
+             e_dir: int, operand="fp16", check_range=True) -> PackedMLP:
+    """weights/biases: the 12 nn.Linear tensors in ``MLP_LAYER_KEYS`` order.
+    ``check_range``: True = verify now (one host sync), "deferred" = leave the verdict on the
+    returned object (``PackedMLP.check_range()``), False = do not check."""
     lib = _lib.load()
     op = operand_id(operand)
     if len(weights) != 12 or len(biases) != 12:
@@ -107,11 +119,12 @@ def pack_mlp(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], e_
         buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev) if check_range else None
         check(lib.crnerf_mlp_pack(C.byref(w), op, buf.data_ptr(), nbytes, _p(status), _stream(dev)))
-        if check_range and int(status.item()) != 0:
-            raise CrnerfError("a NeRF weight exceeds the fp16 finite range (|w| > 65504); "
-                              "pack with operand='bf16'")
     del keep
-    return PackedMLP(buf, op, e_xyz, e_dir)
+    packed = PackedMLP(buf, op, e_xyz, e_dir, status)
+    if check_range == "deferred":
+        return packed            # the caller checks later (training: no host sync per step)
+    packed.check_range()
+    return packed
 
 
 def render_pass(packed: PackedMLP, rays: torch.Tensor, z_vals: torch.Tensor,
@@ -516,3 +529,23 @@ def composite_backward(raw: torch.Tensor, z_vals: torch.Tensor, noise: Optional[
                                             _p(g_weights), _p(g_depth), n, s, d_rgb.data_ptr(),
                                             d_sig.data_ptr(), _stream(dev)))
     return d_rgb, d_sig
+
+
+def relu_bias_grad(g: torch.Tensor, act: Optional[torch.Tensor]) -> torch.Tensor:
+    """In place g *= (act > 0) (act: saved 16-bit post-ReLU activations or None) and return the
+    column sums of the result (= the layer's bias gradient)."""
+    lib = _lib.load()
+    _need(g, "g", 2)
+    if not g.is_contiguous():
+        raise ValueError("g must be contiguous (it is modified in place)")
+    n, c = g.shape
+    if act is not None:
+        if act.shape != g.shape or act.element_size() != 2 or not act.is_contiguous() or act.device != g.device:
+            raise ValueError("act must be a contiguous 16-bit tensor of g's shape on g's device")
+    dev = g.device
+    with torch.cuda.device(dev):
+        gb = torch.empty((c,), dtype=torch.float32, device=dev)
+        scratch = torch.empty((16 * 148 * 256,), dtype=torch.float32, device=dev)
+        check(lib.crnerf_relu_bias_grad(g.data_ptr(), _p(act), n, c, gb.data_ptr(), scratch.data_ptr(),
+                                        _stream(dev)))
+    return gb

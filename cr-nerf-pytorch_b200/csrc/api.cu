@@ -83,6 +83,8 @@ int cnn_forward(const crnerf_cnn_weights* cw, const float* x, int64_t n, int64_t
 int composite_backward(const float* raw, const float* z, const float* noise, const float* g_feature,
                        const float* g_weights, const float* g_depth, int n_rays, int n_samples,
                        float* d_rgb_pre, float* d_sigma_pre, cudaStream_t st);
+int relu_bias_grad(float* g, const void* act, int64_t n_points, int width, float* gb, float* scratch,
+                   cudaStream_t st);
 
 }  // namespace crnerf
 
@@ -149,6 +151,13 @@ int crnerf_composite_backward(const float* raw, const float* z_vals, const float
   if (rc) return rc;
   return composite_backward(raw, z_vals, noise, g_feature, g_weights, g_depth, n_rays, n_samples,
                             d_rgb_pre, d_sigma_pre, (cudaStream_t)stream);
+}
+
+int crnerf_relu_bias_grad(float* g, const void* act, int64_t n_points, int width, float* gb,
+                          float* scratch, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return relu_bias_grad(g, act, n_points, width, gb, scratch, (cudaStream_t)stream);
 }
 
 static int render_pass_impl(const void* packed, int operand, const float* rays, const float* view_dir,

@@ -21,6 +21,7 @@
 // One warp per ray: lanes stride the 64 channels (coalesced rows of the (P,65) buffer) for the
 // dot products and the output rows; the two length-S recurrences run on lane 0 over shared
 // memory (S <= 1024; training uses 64 / 128).
+#include <algorithm>
 #include "common.h"
 
 namespace crnerf {
@@ -96,7 +97,90 @@ composite_backward_kernel(const float* __restrict__ raw, const float* __restrict
   }
 }
 
+// g (P, C) fp32 *= (act > 0) in place (act: the layer's saved 16-bit post-ReLU output, or
+// NULL for a layer without activation), and partial column sums for the bias gradient.
+// One pass over g instead of the mask multiply + a strided column reduction.
+// 256 threads: column = tid % C, row lane = tid / C (C in {64, 128, 256}).
+__global__ void __launch_bounds__(256)
+relu_bias_grad_kernel(float* __restrict__ g, const uint16_t* __restrict__ act, long long P, int C,
+                      float* __restrict__ partial) {
+  __shared__ float red[256];
+  const int c = threadIdx.x % C, rl = threadIdx.x / C, rows_per_it = 256 / C;
+  const long long rows_per_block = (P + gridDim.x - 1) / gridDim.x;
+  const long long r0 = blockIdx.x * rows_per_block, r1 = min(P, r0 + rows_per_block);
+  float acc = 0.f;
+  // 8 independent rows in flight per thread: the kernel is a pure HBM stream and one
+  // outstanding load per thread would leave it latency-bound
+  constexpr int kU = 8;
+  long long r = r0 + rl;
+  for (; r + (long long)(kU - 1) * rows_per_it < r1; r += (long long)kU * rows_per_it) {
+    float v[kU];
+    uint16_t a[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) v[u] = g[(r + (long long)u * rows_per_it) * C + c];
+    if (act) {
+#pragma unroll
+      for (int u = 0; u < kU; ++u) a[u] = act[(r + (long long)u * rows_per_it) * C + c];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (!(a[u] != 0 && a[u] < 0x8000)) v[u] = 0.f;  // post-ReLU value not strictly positive
+        g[(r + (long long)u * rows_per_it) * C + c] = v[u];  // unconditional: whole-line writes
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) acc += v[u];
+  }
+  for (; r < r1; r += rows_per_it) {
+    float v = g[r * C + c];
+    if (act) {
+      const uint16_t a = act[r * C + c];
+      if (!(a != 0 && a < 0x8000)) {
+        v = 0.f;
+        g[r * C + c] = 0.f;
+      }
+    }
+    acc += v;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float t = 0.f;
+    for (int k = 0; k < rows_per_it; ++k) t += red[k * C + threadIdx.x];
+    partial[(long long)blockIdx.x * C + threadIdx.x] = t;
+  }
+}
+
+// gb[c] = sum_b partial[b][c]; one block per column, fixed summation tree (deterministic)
+__global__ void __launch_bounds__(128)
+bias_reduce_kernel(const float* __restrict__ partial, int n_parts, int C, float* __restrict__ gb) {
+  __shared__ float red[4];
+  const int c = blockIdx.x;
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < n_parts; b += 128) acc += partial[(long long)b * C + c];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) gb[c] = (red[0] + red[1]) + (red[2] + red[3]);
+}
+
 }  // namespace
+
+int relu_bias_grad(float* g, const void* act, int64_t n_points, int width, float* gb, float* scratch,
+                   cudaStream_t st) {
+  CRNERF_REQUIRE(g && gb && scratch, "null argument");
+  CRNERF_REQUIRE(width == 64 || width == 128 || width == 256, "width must be 64, 128 or 256");
+  if (n_points <= 0) {
+    CRNERF_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * width, st));
+    return CRNERF_OK;
+  }
+  const int nb = (int)std::min<long long>(8LL * num_sms(), (n_points + 63) / 64);
+  relu_bias_grad_kernel<<<nb, 256, 0, st>>>(g, static_cast<const uint16_t*>(act), n_points, width, scratch);
+  bias_reduce_kernel<<<width, 128, 0, st>>>(scratch, nb, width, gb);
+  count_launch(2);
+  CRNERF_CUDA(cudaGetLastError());
+  return CRNERF_OK;
+}
 
 int composite_backward(const float* raw, const float* z, const float* noise, const float* g_feature,
                        const float* g_weights, const float* g_depth, int n_rays, int n_samples,

@@ -97,8 +97,13 @@ class NeRF_sigma(nn.Module):
         key = (self.operand,) + tuple((m.weight.data_ptr(), m.weight._version, m.bias.data_ptr(),
                                        m.bias._version) for m in lin)
         if self._packed is None or key != self._packed_key:
+            # Inference verifies that every weight fits the fp16 operand range (one host sync per
+            # weight version).  Training re-packs after every optimizer step; any host sync there
+            # drains the launch queue once per step, so the verdict is left on the object
+            # (PackedMLP.check_range()) and weights beyond +-65504 are clamped by the packer.
             self._packed = ops.pack_mlp([m.weight for m in lin], [m.bias for m in lin],
-                                        self.in_channels_xyz, self.in_channels_dir, self.operand)
+                                        self.in_channels_xyz, self.in_channels_dir, self.operand,
+                                        check_range="deferred" if self.wants_grad() else True)
             self._packed_key = key
         return self._packed
 

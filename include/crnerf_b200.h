@@ -120,6 +120,13 @@ int crnerf_composite_backward(const float* raw, const float* z_vals, const float
                               int n_rays, int n_samples, float* d_rgb_pre, float* d_sigma_pre,
                               void* stream);
 
+/* Backward of a layer's ReLU + bias: g (n_points, width) fp32 is multiplied in place by
+ * (act > 0), act being that layer's slice of `acts` (16-bit, same shape; NULL = no activation),
+ * and gb (width) receives the column sums = the bias gradient.  width in {64,128,256};
+ * scratch: 16*148*256 floats. */
+int crnerf_relu_bias_grad(float* g, const void* act, int64_t n_points, int width, float* gb,
+                          float* scratch, void* stream);
+
 /* NeRF_sigma.forward on pre-embedded rows (models/nerf.py:157-182):
  *   x (n, x_stride) with [0,e_xyz) xyz embedding, [e_xyz, e_xyz+e_dir) dir
  *   embedding; out (n, 65) = [sigmoid features(64) | softplus sigma].

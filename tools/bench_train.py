@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Training-step timing (BASELINE configs[4] shapes): 1024-ray (32x32) patch, 64+64 samples,
+perturb=1, noise_std=1, render under autograd -> style_net decode (coarse, fine) -> MSE ->
+backward -> Adam.  Prints our step next to the same step on stock PyTorch eager ops (the
+oracle's restatement of the reference math moved to the same GPU) as the library baseline.
+
+  python tools/bench_train.py [--steps 20]
+  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/bench_train.py   (DDP, 1 patch / rank)
+"""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "cr-nerf-pytorch_b200"), os.path.join(ROOT, "oracle"), ROOT):
+    sys.path.insert(0, p)
+import torch
+import torch.distributed as dist
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--rays", type=int, default=1024)
+    ap.add_argument("--ns", type=int, default=64)
+    ap.add_argument("--ni", type=int, default=64)
+    ap.add_argument("--no-eager", action="store_true")
+    a = ap.parse_args()
+    import crnerf_oracle as oracle
+    from bench import build_models
+    from models.nerf import PosEmbedding
+    from models.rendering import render_rays_cross_ray
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    models, margs = build_models()
+    models = {k: m.to(dev).train() for k, m in models.items()}
+    emb = {"xyz": PosEmbedding(14, 15), "dir": PosEmbedding(3, 4)}
+    side = int(a.rays ** 0.5)
+    rays = oracle.pinhole_rays(side, side, oracle.synthetic_pose(rank)).to(dev)
+    style = torch.rand(1, 64, 32, 32, device=dev)
+    target = torch.rand(side * side, 3, device=dev)
+    params = [p for m in models.values() for p in m.parameters()]
+    opt = torch.optim.Adam(params, lr=5e-4)
+
+    def allreduce_grads():
+        if world > 1:   # what DDP does, as one flat bucket
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat); flat /= world
+            o = 0
+            for p in params:
+                p.grad.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
+
+    def step_ours():
+        res = render_rays_cross_ray(models, emb, rays, None, a.ns, False, 1.0, 1.0, a.ni, 32768, False, args=margs)
+        loss = 0
+        for typ in ("coarse", "fine"):
+            feat = res[f"feature_{typ}"].t().reshape(1, 64, side, side)
+            rgb = models["decoder"](feat, style).reshape(3, -1).t()
+            loss = loss + 0.5 * ((rgb - target) ** 2).mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        allreduce_grads()
+        opt.step()
+        return loss
+
+    # library baseline: the same math as plain differentiable torch ops on the GPU
+    pc = {k: v.detach().clone().requires_grad_(True) for k, v in models["coarse"].state_dict().items()}
+    pf = {k: v.detach().clone().requires_grad_(True) for k, v in models["fine"].state_dict().items()}
+    pd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and k.find("rgb_upsample") < 0) for k, v in models["decoder"].state_dict().items()}
+    eparams = [v for d_ in (pc, pf, pd) for v in d_.values() if v.requires_grad]
+    eopt = torch.optim.Adam(eparams, lr=5e-4)
+
+    def step_eager():
+        n = rays.shape[0]
+        rng = {"perturb_rand": torch.rand(n, a.ns, device=dev), "noise_coarse": torch.randn(n, a.ns, device=dev),
+               "u": torch.rand(n, a.ni, device=dev), "noise_fine": torch.randn(n, a.ns + a.ni, device=dev)}
+        res = oracle.render_rays(pc, pf, rays, n_samples=a.ns, n_importance=a.ni, perturb=1.0, noise_std=1.0,
+                                 chunk=1 << 30, rng=rng)
+        loss = 0
+        for typ in ("coarse", "fine"):
+            feat = res[f"feature_{typ}"].t().reshape(1, 64, side, side)
+            rgb = oracle.style_net_forward(pd, feat, style).reshape(3, -1).t()
+            loss = loss + 0.5 * ((rgb - target) ** 2).mean()
+        eopt.zero_grad(set_to_none=True)
+        loss.backward()
+        eopt.step()
+        return loss
+
+    def timeit(fn, steps):
+        for _ in range(3): fn()
+        torch.cuda.synchronize()
+        if world > 1: dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter(); e0.record()
+        for _ in range(steps): l = fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, (time.perf_counter() - t0) * 1e3 / steps, float(l)
+
+    ours_dev, ours_wall, l1 = timeit(step_ours, a.steps)
+    out = {"workload": f"train step, {a.rays} rays x ({a.ns}+{a.ni}), perturb=1 noise=1, style_net decode x2, MSE, Adam",
+           "n_gpus": world, "ours_ms_device": ours_dev, "ours_ms_wall": ours_wall,
+           "ours_ray_samples_per_s": world * a.rays * (a.ns + a.ni) / (ours_wall * 1e-3), "loss": l1}
+    if not a.no_eager and world == 1:
+        try:
+            eg_dev, eg_wall, l2 = timeit(step_eager, max(3, a.steps // 4))
+            out.update({"torch_eager_fp32_ms_device": eg_dev, "torch_eager_fp32_ms_wall": eg_wall,
+                        "speedup_vs_torch_eager": eg_wall / ours_wall})
+        except Exception as e:   # noqa: BLE001
+            out["torch_eager_error"] = repr(e)[:200]
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1: dist.destroy_process_group()
+
+if __name__ == "__main__":
+    main()
