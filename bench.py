@@ -103,6 +103,34 @@ def cpu_reference_throughput(oracle, state, rays, reps, warm=1):
     return RAY_SAMPLES_PER_STEP / statistics.mean(times), times
 
 
+def psnr_delta(oracle, models_gpu, state_cpu, emb, margs, dev):
+    """'PSNR delta vs ref' half of the metric: one 64x64 frame (4096 rays, 64+128
+    samples) rendered + decoded by the CUDA path and by the CPU port of the reference; both are
+    scored against a pseudo ground truth T (the reference render decoded with a differently seeded
+    style feature) on the right half of the image, as eval_metric.py:89-93 does."""
+    from models.rendering import render_rays_cross_ray
+    h = w = 64
+    rays = oracle.pinhole_rays(h, w, oracle.synthetic_pose(0), 0.0, 5.0)
+    g = torch.Generator().manual_seed(1)
+    style = torch.rand(1, 64, 32, 32, generator=g)
+    style_t = torch.rand(1, 64, 32, 32, generator=g)
+    pd = {k: v.detach().cpu().clone() for k, v in models_gpu["decoder"].state_dict().items()}
+    with torch.no_grad():
+        ref = oracle.render_rays(state_cpu[0], state_cpu[1], rays, n_samples=NS, n_importance=NI, perturb=0,
+                                 noise_std=0, chunk=8192)
+        feat_ref = ref["feature_fine"].t().reshape(1, 64, h, w)
+        rgb_ref = oracle.style_net_forward(pd, feat_ref, style)
+        rgb_t = oracle.style_net_forward(pd, feat_ref, style_t)
+        res = render_rays_cross_ray(models_gpu, emb, rays.to(dev), None, NS, False, 0, 0, NI, 32768, False,
+                                    test_time=True, args=margs)
+        rgb = models_gpu["decoder"](res["feature_fine"].t().reshape(1, 64, h, w), style.to(dev)).cpu()
+    half = lambda t: t[..., w // 2:]
+    p_ours, p_ref = oracle.psnr(half(rgb), half(rgb_t)), oracle.psnr(half(rgb_ref), half(rgb_t))
+    return {"psnr_ours_vs_ref_db": oracle.psnr(rgb, rgb_ref), "psnr_ours_vs_T_db": p_ours,
+            "psnr_ref_vs_T_db": p_ref, "psnr_delta_db": abs(p_ours - p_ref),
+            "frame": "64x64, 64+128 samples, style_net decode, right half scored"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -199,10 +227,20 @@ def run_ours(args):
                                ((i * world + rank) % n_batches + 1) * N_RAYS]
     gather_buf = torch.empty(world * N_RAYS, 64, device=dev) if world > 1 else None
 
+    # the public eval API for a fixed batch shape: render_rays_cross_ray captured in a CUDA graph
+    # (crnerf_b200/graphs.py; same kernels, one launch); --no-graph times the plain call
+    graphed = None
+    if not args.no_graph:
+        from crnerf_b200.graphs import GraphedRenderer
+        graphed = GraphedRenderer(models_gpu, emb, N_RAYS, NS, NI, args=margs)
+
     def step(rays):
-        with torch.no_grad():
-            res = render_rays_cross_ray(models_gpu, emb, rays, None, NS, False, 0, 0, NI, 32768, False,
-                                        test_time=True, args=margs)
+        if graphed is not None:
+            res = graphed(rays)
+        else:
+            with torch.no_grad():
+                res = render_rays_cross_ray(models_gpu, emb, rays, None, NS, False, 0, 0, NI, 32768, False,
+                                            test_time=True, args=margs)
         if world > 1:  # the sharded frame's single collective: gather the rendered features
             dist.all_gather_into_tensor(gather_buf, res["feature_fine"])
         return res
@@ -233,6 +271,8 @@ def run_ours(args):
         e1.record()
     barrier()
     launches = ops.launch_count() - n0
+    if graphed is not None:   # replays do not pass through the library's host-side counter
+        launches = graphed.kernels_per_replay * args.steps
     dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
     t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -249,8 +289,8 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        r = host_rays[i % len(host_rays)].to(dev, non_blocking=True)
-        res = step(r)
+        r = host_rays[i % len(host_rays)]
+        res = step(r if graphed is not None else r.to(dev, non_blocking=True))   # H2D inside either way
         host_out.copy_(res["feature_fine"], non_blocking=True)
         host_depth.copy_(res["depth_fine"], non_blocking=True)
         torch.cuda.current_stream().synchronize()    # the caller consumes the result each step
@@ -306,6 +346,10 @@ def run_ours(args):
                         "sample": f"5 x one 4096-ray batch (786,432 ray-samples each), "
                                   f"{sum(times):.1f} s of CPU work on {cores} threads"}
 
+    psnr = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        psnr = psnr_delta(oracle, models_gpu, state_cpu, emb, margs, dev)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -315,6 +359,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": N_RAYS,
                        "parallelism": f"rays sharded x{world}" + (", all_gather(feature_fine)" if world > 1 else ""),
+                       "api": ("crnerf_b200.graphs.GraphedRenderer (render_rays_cross_ray captured in a CUDA graph)"
+                               if graphed is not None else "models.rendering.render_rays_cross_ray"),
                        "l2": "256 MiB buffer written between timed steps (outside the event pairs)",
                        "timing": "CUDA events per step on the launch stream, summed, max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT,
@@ -322,7 +368,7 @@ def run_ours(args):
                     "timing": "wall clock, pinned host rays -> H2D -> render -> D2H feature+depth, "
                               "stream sync every step"},
             "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu_base, "clocks": clocks,
+            "roofline": roof, "cpu_baseline": cpu_base, "psnr": psnr, "clocks": clocks,
             "points_per_step": POINTS_PER_STEP,
             "tflops_per_step_device": POINTS_PER_STEP * FLOP_PER_POINT / (dev_ms / args.steps * 1e-3) / 1e12,
         }
@@ -338,6 +384,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the plain API call instead of the graphed one")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 8:      # keep the CPU arm bounded: ~1.5-3 s per step

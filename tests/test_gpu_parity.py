@@ -367,6 +367,32 @@ def test_style_net_matches_golden():
         close(cm, want_cm, "CNN.forward", rtol=1e-4, atol=1e-6)
 
 
+def test_decoded_frame_psnr_delta_within_0p05_db():
+    """North-star bar: rendered PSNR within 0.05 dB of the reference's: our decoded
+    frame and the oracle's are scored against the same pseudo ground truth on the right image half."""
+    models, args = build_mirror_models(0)
+    p = {k: state(m) for k, m in models.items()}
+    h, w = 40, 48
+    rays = oracle.pinhole_rays(h, w, oracle.synthetic_pose(0))
+    g = torch.Generator().manual_seed(1)
+    style, style_t = torch.rand(1, 64, 32, 32, generator=g), torch.rand(1, 64, 32, 32, generator=g)
+    with torch.no_grad():
+        ref = oracle.render_rays(p["coarse"], p["fine"], rays, n_samples=32, n_importance=48, perturb=0,
+                                 noise_std=0, chunk=8192)
+        feat_ref = ref["feature_fine"].t().reshape(1, 64, h, w)
+        rgb_ref = oracle.style_net_forward(p["decoder"], feat_ref, style)
+        rgb_t = oracle.style_net_forward(p["decoder"], feat_ref, style_t)
+    models = {k: m.cuda() for k, m in models.items()}
+    res = _render(models, args, rays.cuda(), 32, 48)
+    with torch.no_grad():
+        rgb = models["decoder"](res["feature_fine"].t().reshape(1, 64, h, w), style.cuda()).cpu()
+    half = lambda t: t[..., w // 2:]
+    p_ours, p_ref = oracle.psnr(half(rgb), half(rgb_t)), oracle.psnr(half(rgb_ref), half(rgb_t))
+    print(f"PSNR ours vs ref {oracle.psnr(rgb, rgb_ref):.1f} dB; vs T: ours {p_ours:.4f} dB, ref {p_ref:.4f} dB")
+    assert oracle.psnr(rgb, rgb_ref) > 80.0
+    assert abs(p_ours - p_ref) <= 0.05
+
+
 def test_neural_renderer_standalone():
     from models.nerf_decoder_stylenerf import NeuralRenderer
     torch.manual_seed(0)
@@ -473,3 +499,21 @@ def test_native_library_is_what_ran():
     torch.cuda.synchronize()
     # pack x2, coarse_z, 2 fused passes, sample_pdf_merge
     assert o.launch_count() - before == 6
+
+
+def test_graphed_renderer_replays_identical_results():
+    """crnerf_b200.graphs.GraphedRenderer: CUDA-graph replay == the plain call, for several batches."""
+    from crnerf_b200.graphs import GraphedRenderer
+    models, args = build_mirror_models(0)
+    models = {k: m.cuda() for k, m in models.items()}
+    rays = oracle.pinhole_rays(32, 48, oracle.synthetic_pose(0)).cuda()
+    gr = GraphedRenderer(models, _embeddings(), 512, 32, 32, args=args)
+    assert gr.kernels_per_replay == 4     # coarse_z, coarse pass, sample_pdf+sort, fine pass
+    for i in range(3):
+        batch = rays[i * 512:(i + 1) * 512]
+        got = {k: v.clone() for k, v in gr(batch).items()}
+        want = _render(models, args, batch, 32, 32)
+        for k in want:
+            assert torch.equal(got[k], want[k]), k
+    with pytest.raises(ValueError):
+        gr(rays[:100])
