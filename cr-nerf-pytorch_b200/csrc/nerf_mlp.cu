@@ -57,7 +57,7 @@ constexpr int kMiscOff = kBlobOff + kBlobFloats * 4;  // 207648
 struct Misc {
   uint64_t ring_full[kSlots];
   uint64_t ring_empty[kSlots];
-  uint64_t emb_full[2], a_full[2], d_full[2], d_empty[2], carry_a[2], carry_b[2];
+  uint64_t emb_full[2], a_full[2], a_half[2], d_full[2], d_empty[2], carry_a[2], carry_b[2];
   uint32_t tmem_base;
   uint32_t pipe_turn;  // whose unit goes down the tensor pipe next (even: stream X, odd: Y)
   // the issuers' copy of the program: constant-bank lookups indexed by a run-time value are
@@ -374,11 +374,12 @@ __device__ __forceinline__ void epi_stage(uint32_t tD_ch, const float* blob_g, u
 template <int kFmt, bool kRelu, bool kSigma, bool kDbg, bool kDirect, bool kSave>
 __device__ __forceinline__ void epi_flush(uint32_t tD_ch, uint32_t tA_ch, const float* blob_g, uint32_t boff,
                                           const float* wsig_ch, const uint32_t (&staged)[32], float& sig_acc,
-                                          uint64_t* d_empty, uint64_t* a_full, float* dbg, bool skip,
-                                          uint4* asave) {
+                                          uint64_t* d_empty, uint64_t* a_full, uint64_t* a_half, float* dbg,
+                                          bool skip, uint4* asave) {
   if (kDbg && skip) {
     tc_fence_before_sync();
     warp_arrive(d_empty);
+    warp_arrive(a_half);
     warp_arrive(a_full);
     return;
   }
@@ -396,6 +397,13 @@ __device__ __forceinline__ void epi_flush(uint32_t tD_ch, uint32_t tA_ch, const 
   tmem_ld_wait();
   tc_fence_before_sync();
   warp_arrive(d_empty);  // accumulator drained: the issuer may overwrite it
+  if constexpr (!kDirect) {
+    // the staged first half (A columns 0..63 = the next layer's K 0..127) is in place: the
+    // issuer may start the next layer's first two slabs while this half is still being packed
+    tmem_st_wait();
+    tc_fence_before_sync();
+    warp_arrive(a_half);
+  }
   epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 16>(vb, blob_g, boff + 32u, wsig_ch + 32, out, sig_acc,
                                                 dbg ? dbg + 32 : nullptr);
   tmem_st_x16p(a_dst + 16, out);
@@ -405,6 +413,7 @@ __device__ __forceinline__ void epi_flush(uint32_t tD_ch, uint32_t tA_ch, const 
   // A holds the next layer's full input
   tmem_st_wait();
   tc_fence_before_sync();
+  if constexpr (kDirect) warp_arrive(a_half);
   warp_arrive(a_full);
 }
 
@@ -440,6 +449,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       // collective tcgen05.wait / __syncwarp): a 32-lane arrive is 32 serialized smem atomics
       mbar_init(&M->emb_full[b], 8);
       mbar_init(&M->a_full[b], 8);
+      mbar_init(&M->a_half[b], 8);
       mbar_init(&M->d_full[b], 1);
       mbar_init(&M->d_empty[b], 8);
       mbar_init(&M->carry_a[b], 1);
@@ -529,6 +539,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         const uint32_t idesc = make_idesc_f16(128, ut & 0xffu, kFmt);
         const int chunk0 = (int)((ut >> 16) & 0xffu), nch = (int)(ut >> 24);
         const uint32_t g0 = g_base + (uint32_t)chunk0;
+        uint32_t a_par = 0;
         // ---- everything this unit depends on is awaited BEFORE the pipe turn, so the turn
         // holder issues one uninterrupted burst: the tcgen05 queue is only 1-2 MMAs deep and
         // the pipe idles whenever the issuing thread does anything else for long.
@@ -541,7 +552,11 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
           if (ut & 0x200u) {
             timed_wait(&M->emb_full[b], (uint32_t)pair & 1, 2, prof, w_emb);
           } else {
-            timed_wait(&M->a_full[b], acount & 1, 3, prof, w_a);
+            // the previous layer's first output half (A columns 0..63) suffices to start a
+            // standard unit; its second half is awaited inside the burst, two slabs later
+            timed_wait(&M->a_half[b], acount & 1, 3, prof, w_a);
+            if (!(ut & 0x400u)) timed_wait(&M->a_full[b], acount & 1, 3, prof, w_a);
+            a_par = acount & 1;
             acount++;
           }
         }
@@ -568,6 +583,10 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
             // ---- standard unit: 16 TS MMAs over the four activation slabs, straight-line
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
+              if (j == 2 && (ut & 0x100u) && !(ut & 0x200u)) {
+                mbar_wait(&M->a_full[b], a_par, 3);   // second half of the previous layer's output
+                tc_fence_after_sync();
+              }
               const uint32_t slot = (g0 + (uint32_t)j) % kSlots;
               const uint32_t b_lo = ring_lo + slot * (kSlotBytes >> 4);
               const uint32_t a_t = tA + 32u * j;
@@ -724,6 +743,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       uint64_t* const d_full = &M->d_full[b];
       uint64_t* const d_empty = &M->d_empty[b];
       uint64_t* const a_full = &M->a_full[b];
+      uint64_t* const a_half = &M->a_half[b];
       // wait for the next accumulator of this tile (units arrive in program order)
       auto wait_d = [&]() {
         timed_wait(d_full, ud & 1, 16, prof, w_dfull);
@@ -765,7 +785,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         wait_d();
         if (prof) t_a = clock64();
         epi_flush<kFmt, true, false, kDbg, false, kSave>(tD_ch, tA_ch, blob, bl + 128u, wsig, staged, sig_acc,
-                                                         d_empty, a_full, dbg_at(layer, 1), skip, save_at(layer, 1));
+                                                         d_empty, a_full, a_half, dbg_at(layer, 1), skip, save_at(layer, 1));
         if (prof) t_flush += clock64() - t_a;
       }
       // ---- layer 8: ReLU + this warp's share of the fp32 sigma-head dot product
@@ -778,7 +798,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       if (prof) t_a = clock64();
       epi_flush<kFmt, true, true, kDbg, false, kSave>(tD_ch, tA_ch, blob, bias_ch + 256u * 7 + 128u,
                                                       wsig + 128 + 64 * ch, staged, sig_acc, d_empty, a_full,
-                                                      dbg_at(7, 1), skip, save_at(7, 1));
+                                                      a_half, dbg_at(7, 1), skip, save_at(7, 1));
       if (prof) t_flush += clock64() - t_a;
       {
         const long long t_c0 = prof ? clock64() : 0;
@@ -884,14 +904,14 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       wait_d();
       if (prof) t_a = clock64();
       epi_flush<kFmt, false, false, kDbg, false, kSave>(tD_ch, tA_ch, blob, bias_ch + 256u * kLFinal + 128u, wsig,
-                                                        staged, sig_acc, d_empty, a_full, dbg_at(kLFinal, 1), skip,
+                                                        staged, sig_acc, d_empty, a_full, a_half, dbg_at(kLFinal, 1), skip,
                                                         save_at(kLFinal, 1));
       if (prof) t_flush += clock64() - t_a;
       // ---- dir layer (128 wide, ReLU): straight to A columns [0,64)
       wait_d();
       if (prof) t_a = clock64();
       epi_flush<kFmt, true, false, kDbg, true, kSave>(tD_ch, tA_ch, blob, bias_ch + 256u * 9, wsig, staged, sig_acc,
-                                                      d_empty, a_full, dbg_at(kLDir, 0), skip, save_at(kLDir, 0));
+                                                      d_empty, a_full, a_half, dbg_at(kLDir, 0), skip, save_at(kLDir, 0));
       if (prof) t_flush += clock64() - t_a;
       // ---- rgb layer
       wait_d();
