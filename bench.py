@@ -132,44 +132,60 @@ def psnr_delta(oracle, models_gpu, state_cpu, emb, margs, dev):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md).  NVML is
+    polled from a thread every ~2 ms (the timed region of the default run is ~25 ms, too short for
+    `nvidia-smi -lms`); falls back to one `nvidia-smi` query if the NVML binding is missing."""
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self._stop, self._thr, self._h = index, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:   # noqa: BLE001
+            self._nv = None
+
+    def _poll(self):
+        nv = self._nv
+        while not self._stop:
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)))
+            except Exception:   # noqa: BLE001
+                break
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        if self._nv is not None:
+            self._thr = threading.Thread(target=self._poll, daemon=True)
+            self._thr.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        if self._nv is None:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=20).stdout.split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "samples": 1,
+                        "note": "NVML binding unavailable: one nvidia-smi sample after the timed region"}
+            except Exception:   # noqa: BLE001
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self._stop = True
+        if self._thr is not None:
+            self._thr.join(timeout=1.0)
+        nv = self._nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(n for n, bit in names.items() if any(r & bit for _, r in self.rows))
+        sm = [c for c, _ in self.rows]
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM))
+        except Exception:   # noqa: BLE001
+            mx = None
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": reasons,
                 "samples": len(sm)}
 
 

@@ -417,6 +417,29 @@ __device__ __forceinline__ void epi_flush(uint32_t tD_ch, uint32_t tA_ch, const 
   warp_arrive(a_full);
 }
 
+// Column sums over the 32 lanes of a warp for 32 values per lane, by a transposing butterfly:
+// after the step with distance h a lane keeps the half of its values whose index has bit h
+// equal to the lane's bit h, so after five steps lane L holds sum_over_lanes(v[L]).
+// 31 shuffles + 31 adds instead of a shared-memory transpose and two barriers.
+template <int kHalf>
+__device__ __forceinline__ void bfly_step(float (&v)[32], int lane) {
+  const bool up = (lane & kHalf) != 0;
+#pragma unroll
+  for (int i = 0; i < kHalf; ++i) {
+    const float send = up ? v[i] : v[i + kHalf];
+    const float keep = up ? v[i + kHalf] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, kHalf);
+  }
+}
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+  bfly_step<16>(v, lane);
+  bfly_step<8>(v, lane);
+  bfly_step<4>(v, lane);
+  bfly_step<2>(v, lane);
+  bfly_step<1>(v, lane);
+  return v[0];
+}
+
 // kVariant: 0 production, 1 debug/profiling instrumentation, 2 training forward (also stores
 // every layer's A-operand activations and the per-point [features | sigma] for the backward)
 template <int kFmt, int kVariant>
@@ -654,7 +677,6 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
     const uint32_t tA = tmem + (b ? 256u : 0u) + lane_off;
     const uint32_t tD = tmem + (b ? 384u : 128u) + lane_off;
     uint8_t* my_emb = emb + b * kEmbBufBytes;
-    float* staging = reinterpret_cast<float*>(my_emb);
     const bool ray_mode = !(P.mode & kModeEmbedded);
     const bool skip = kDbg && (P.exp & 1);
     const bool raw_mode = (P.mode & kModeRaw) != 0 || skip;
@@ -666,6 +688,78 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
     long long w_dfull = 0, t_emb = 0, t_comp = 0, t_red = 0, t_stage = 0, t_flush = 0;
     const long long t_start = clock64();
 
+    // ---- tile inputs + embedding -> smem (A operand of layers 1, 5 and dir) for tile tt of
+    // this stream.  Software-pipelined: tile t+2's embedding is produced at the end of tile t's
+    // epilogue (its buffer is free once the dir unit has retired), before the cross-warp part
+    // of tile t's feature reduction, so the issuer can start tile t+2 as soon as the rgb
+    // accumulator is drained instead of waiting for reduction + loads + sin/cos.
+    auto embed_tile = [&](int tt) {
+      const long long tile_p0 = p0 + (long long)tt * 128;
+      const int nvalid = (int)min((long long)128, p1 - tile_p0);
+      const long long p = tile_p0 + row;
+      const bool valid = row < nvalid;
+        // ---- tile inputs + embedding -> smem (A operand of layers 1, 5, dir and of every
+        // bias k-step).  Column half 0 writes buffer columns 0..63, half 1 columns 64..127.
+        const long long t_e0 = prof ? clock64() : 0;
+        if (ray_mode) {
+          EmbIn ex, ed;
+          ex.v[0] = ex.v[1] = ex.v[2] = 0.f;
+          ed.v[0] = ed.v[1] = ed.v[2] = 0.f;
+          if (valid) {
+            const long long ray = p / P.S;
+            const float z = __ldg(P.z_vals + p);
+            const float4 r0 = __ldg(reinterpret_cast<const float4*>(P.rays + ray * 8));
+            const float4 r1 = __ldg(reinterpret_cast<const float4*>(P.rays + ray * 8) + 1);
+            // xyz = o + d*z with separate roundings, as the reference's broadcast
+            // mul then add (rendering.py:178)
+            ex.v[0] = __fadd_rn(r0.x, __fmul_rn(r0.w, z));
+            ex.v[1] = __fadd_rn(r0.y, __fmul_rn(r1.x, z));
+            ex.v[2] = __fadd_rn(r0.z, __fmul_rn(r1.y, z));
+            if (P.view_dir) {
+              ed.v[0] = __ldg(P.view_dir + ray * 3 + 0);
+              ed.v[1] = __ldg(P.view_dir + ray * 3 + 1);
+              ed.v[2] = __ldg(P.view_dir + ray * 3 + 2);
+            } else {
+              ed.v[0] = r0.w;
+              ed.v[1] = r1.x;
+              ed.v[2] = r1.y;
+            }
+          }
+          // warp-uniform choice so both halves of a row agree on the path
+          const bool fast = fast_emb && __all_sync(0xffffffffu, emb_fast_ok(ex) && emb_fast_ok(ed));
+          if (fast) {
+            emb_prepare(ex);
+            if (ch == 0) {
+              emb_write<kFmt, 15, 0, 0, 8>(my_emb, row_off, row_xor, ex);    // columns 0..63
+            } else {
+              emb_prepare(ed);
+              emb_write<kFmt, 15, 8, 8, 4>(my_emb, row_off, row_xor, ex);    // columns 64..95
+              emb_write<kFmt, 4, 0, 12, 4>(my_emb, row_off, row_xor, ed);   // columns 96..127
+            }
+          } else if (ch == 0) {
+            embed3_generic<kFmt>(my_emb, row, 0, kDirCol0, ex.v[0], ex.v[1], ex.v[2], P.n_freq_xyz);
+          } else {
+            embed3_generic<kFmt>(my_emb, row, kDirCol0, kEmbCols, ed.v[0], ed.v[1], ed.v[2],
+                                 P.n_freq_dir);
+          }
+        } else {
+          const float* xr = P.x + p * P.x_stride;
+          if (ch == 0) {
+            for (int c = 0; c < P.e_xyz; ++c) emb_put<kFmt>(my_emb, row, c, valid ? __ldg(xr + c) : 0.f);
+            for (int c = P.e_xyz; c < kDirCol0; ++c) emb_put<kFmt>(my_emb, row, c, 0.f);
+          } else {
+            for (int c = 0; c < P.e_dir; ++c)
+              emb_put<kFmt>(my_emb, row, kDirCol0 + c,
+                            (valid && !(P.mode & kModeSigmaOnly)) ? __ldg(xr + P.e_xyz + c) : 0.f);
+            for (int c = kDirCol0 + P.e_dir; c < kEmbCols; ++c) emb_put<kFmt>(my_emb, row, c, 0.f);
+          }
+        }
+      fence_proxy_async_smem();
+      warp_arrive(&M->emb_full[b]);
+      if (prof) t_emb += clock64() - t_e0;
+    };
+    if (b < n_tiles) embed_tile(b);
+
     for (int pair = 0; pair < n_pairs; ++pair) {
       const int t = 2 * pair + b;
       if (t >= n_tiles) break;
@@ -673,66 +767,6 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       const int nvalid = (int)min((long long)128, p1 - tile_p0);
       const long long p = tile_p0 + row;
       const bool valid = row < nvalid;
-
-      // ---- tile inputs + embedding -> smem (A operand of layers 1, 5, dir and of every
-      // bias k-step).  Column half 0 writes buffer columns 0..63, half 1 columns 64..127.
-      const long long t_e0 = prof ? clock64() : 0;
-      if (ray_mode) {
-        EmbIn ex, ed;
-        ex.v[0] = ex.v[1] = ex.v[2] = 0.f;
-        ed.v[0] = ed.v[1] = ed.v[2] = 0.f;
-        if (valid) {
-          const long long ray = p / P.S;
-          const float z = __ldg(P.z_vals + p);
-          const float4 r0 = __ldg(reinterpret_cast<const float4*>(P.rays + ray * 8));
-          const float4 r1 = __ldg(reinterpret_cast<const float4*>(P.rays + ray * 8) + 1);
-          // xyz = o + d*z with separate roundings, as the reference's broadcast
-          // mul then add (rendering.py:178)
-          ex.v[0] = __fadd_rn(r0.x, __fmul_rn(r0.w, z));
-          ex.v[1] = __fadd_rn(r0.y, __fmul_rn(r1.x, z));
-          ex.v[2] = __fadd_rn(r0.z, __fmul_rn(r1.y, z));
-          if (P.view_dir) {
-            ed.v[0] = __ldg(P.view_dir + ray * 3 + 0);
-            ed.v[1] = __ldg(P.view_dir + ray * 3 + 1);
-            ed.v[2] = __ldg(P.view_dir + ray * 3 + 2);
-          } else {
-            ed.v[0] = r0.w;
-            ed.v[1] = r1.x;
-            ed.v[2] = r1.y;
-          }
-        }
-        // warp-uniform choice so both halves of a row agree on the path
-        const bool fast = fast_emb && __all_sync(0xffffffffu, emb_fast_ok(ex) && emb_fast_ok(ed));
-        if (fast) {
-          emb_prepare(ex);
-          if (ch == 0) {
-            emb_write<kFmt, 15, 0, 0, 8>(my_emb, row_off, row_xor, ex);    // columns 0..63
-          } else {
-            emb_prepare(ed);
-            emb_write<kFmt, 15, 8, 8, 4>(my_emb, row_off, row_xor, ex);    // columns 64..95
-            emb_write<kFmt, 4, 0, 12, 4>(my_emb, row_off, row_xor, ed);   // columns 96..127
-          }
-        } else if (ch == 0) {
-          embed3_generic<kFmt>(my_emb, row, 0, kDirCol0, ex.v[0], ex.v[1], ex.v[2], P.n_freq_xyz);
-        } else {
-          embed3_generic<kFmt>(my_emb, row, kDirCol0, kEmbCols, ed.v[0], ed.v[1], ed.v[2],
-                               P.n_freq_dir);
-        }
-      } else {
-        const float* xr = P.x + p * P.x_stride;
-        if (ch == 0) {
-          for (int c = 0; c < P.e_xyz; ++c) emb_put<kFmt>(my_emb, row, c, valid ? __ldg(xr + c) : 0.f);
-          for (int c = P.e_xyz; c < kDirCol0; ++c) emb_put<kFmt>(my_emb, row, c, 0.f);
-        } else {
-          for (int c = 0; c < P.e_dir; ++c)
-            emb_put<kFmt>(my_emb, row, kDirCol0 + c,
-                          (valid && !(P.mode & kModeSigmaOnly)) ? __ldg(xr + P.e_xyz + c) : 0.f);
-          for (int c = kDirCol0 + P.e_dir; c < kEmbCols; ++c) emb_put<kFmt>(my_emb, row, c, 0.f);
-        }
-      }
-      fence_proxy_async_smem();
-      warp_arrive(&M->emb_full[b]);
-      if (prof) t_emb += clock64() - t_e0;
 
       uint32_t staged[32];
       float sig_acc = 0.f, sigma = 0.f, w_ray = 0.f;
@@ -921,16 +955,14 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
           if (P.dbg != nullptr && P.dbg_layer == kLRgb && valid) dbg_row = P.dbg + p * 256;
         }
         // ------------------------------------------------ rgb layer (64, sigmoid)
-        // the embedding buffer is dead (dir layer and every bias k-step of this tile have
-        // retired... except this unit's own bias k-step, which has retired too since the
-        // accumulator is complete): reuse it as the (row, channel) staging area,
-        // XOR-swizzled so both the row-wise writes and the channel-wise reads are
-        // bank-conflict free.  Each column half handles 32 of the 64 channels.
+        // Each column half handles 32 of the 64 channels; w*f stays in registers and is summed
+        // over the rows of each ray segment inside the warp (warp_transpose_sum).
         if (!raw_mode && ch == 1) {
           pc_sync(5 + b);
           w_ray = M->wray[b][row];
         }
         uint32_t v[32];
+        float wf[32];
         if (!skip) {
           tmem_ld_x32(tD + 32 * ch, v);
           tmem_ld_wait();
@@ -950,9 +982,8 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
           }
           if (raw_mode) {
             if (valid && !skip && !(P.mode & kModeSigmaOnly)) P.raw[p * 65 + chn] = f;
-          } else {
-            staging[row * 64 + (chn ^ (row & 31))] = w_ray * f;
           }
+          wf[j] = w_ray * f;
           if constexpr (kDbg) {
             if (dbg_row) dbg_row[chn] = f;
           }
@@ -964,22 +995,33 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
             else
               P.raw[p * 65 + 64] = sigma;
           }
-          group_sync(b);  // the next tile's embedding overwrites the buffer both halves use
-        } else {
-          const long long t_r0 = prof ? clock64() : 0;
-          group_sync(b);
-          const int s_first = (int)(tile_p0 % P.S);
-          const long long ray_first = tile_p0 / P.S;
-          const int n_seg = (s_first + nvalid + P.S - 1) / P.S;
-          const int cc = gtid & 63, hh = gtid >> 6;  // channel, row quarter
+        }
+        const int s_first = (int)(tile_p0 % P.S);
+        const long long ray_first = tile_p0 / P.S;
+        const int n_seg = (s_first + nvalid + P.S - 1) / P.S;
+        const long long t_r0 = prof ? clock64() : 0;
+        if (!raw_mode) {
+          // per-warp partial sums of every ray segment that crosses this warp's 32 rows
           for (int sg = 0; sg < n_seg; ++sg) {
             const int r_beg = max(0, sg * P.S - s_first);
             const int r_end = min(nvalid, (sg + 1) * P.S - s_first);
-            const int lo = max(r_beg, 32 * hh), hi = min(r_end, 32 * hh + 32);
-            float acc = 0.f;
-            for (int r = lo; r < hi; ++r) acc += staging[r * 64 + (cc ^ (r & 31))];
-            M->part[b][hh][sg][cc] = acc;
+            float tot = 0.f;
+            if (r_beg < 32 * q + 32 && r_end > 32 * q) {   // warp-uniform
+              const bool in = row >= r_beg && row < r_end;
+              float m[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m[j] = in ? wf[j] : 0.f;
+              tot = warp_transpose_sum(m, lane);
+            }
+            M->part[b][q][sg][32 * ch + lane] = tot;
           }
+        }
+        if (prof) t_red += clock64() - t_r0;
+        // next tile of this stream: its embedding goes out before the cross-warp combine
+        if (t + 2 < n_tiles) embed_tile(t + 2);
+        if (!raw_mode) {
+          const long long t_r1 = prof ? clock64() : 0;
+          const int cc = gtid & 63, hh = gtid >> 6;  // channel, row quarter
           group_sync(b);
           if (hh == 0) {
             if (t > 0) {
@@ -1002,7 +1044,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
             M->carry_feat[b][cc] = carry_out;
             warp_arrive(&M->carry_b[b]);
           }
-          if (prof) t_red += clock64() - t_r0;
+          if (prof) t_red += clock64() - t_r1;
         }
       }
     }
