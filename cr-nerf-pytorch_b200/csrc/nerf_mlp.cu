@@ -822,6 +822,19 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
                                                          d_empty, a_full, a_half, dbg_at(layer, 1), skip, save_at(layer, 1));
         if (prof) t_flush += clock64() - t_a;
       }
+      // composite inputs of this row, requested now so the loads are long complete when the
+      // sigma head is (they sit on this tile's critical path: the composite runs between
+      // layer 8 and xyz_encoding_final on the same warps)
+      const int s_first = (int)(tile_p0 % P.S);
+      const long long ray_first = tile_p0 / P.S;
+      const int seg_of_row = (s_first + row) / P.S;
+      const int s_of_row = s_first + row - seg_of_row * P.S;
+      float pre_z = 0.f, pre_z1 = 0.f, pre_nz = 0.f;
+      if (!raw_mode && ch == 0 && valid) {
+        pre_z = __ldg(P.z_vals + p);
+        if (s_of_row + 1 < P.S) pre_z1 = __ldg(P.z_vals + p + 1);
+        if (P.noise) pre_nz = __ldg(P.noise + p);
+      }
       // ---- layer 8: ReLU + this warp's share of the fp32 sigma-head dot product
       wait_d();
       if (prof) t_a = clock64();
@@ -848,14 +861,11 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
             if (P.raw_save != nullptr && valid) P.raw_save[p * 65 + 64] = sigma;
           }
           if (!raw_mode) {
-            // per-row ray state is (re)loaded here rather than carried through the layers
-            const long long ray = valid ? p / P.S : 0;
-            const int s = valid ? (int)(p - ray * P.S) : 0;
-            const float z = valid ? __ldg(P.z_vals + p) : 0.f;
-            const float delta =
-                valid ? ((s + 1 < P.S) ? __fsub_rn(__ldg(P.z_vals + p + 1), z) : 1e2f) : 0.f;
-            const float nz = (valid && P.noise) ? __ldg(P.noise + p) : 0.f;
-            const int s_first = (int)(tile_p0 % P.S);
+            const long long ray = valid ? ray_first + seg_of_row : 0;
+            const int s = valid ? s_of_row : 0;
+            const float z = pre_z;
+            const float delta = valid ? ((s + 1 < P.S) ? __fsub_rn(pre_z1, z) : 1e2f) : 0.f;
+            const float nz = pre_nz;
             const float alpha = valid ? 1.f - expf(-(delta * fmaxf(sigma + nz, 0.f))) : 0.f;
             const float om = 1.f - alpha;
             const int f0 = (valid && s == 0) ? 1 : 0;
@@ -996,8 +1006,6 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
               P.raw[p * 65 + 64] = sigma;
           }
         }
-        const int s_first = (int)(tile_p0 % P.S);
-        const long long ray_first = tile_p0 / P.S;
         const int n_seg = (s_first + nvalid + P.S - 1) / P.S;
         const long long t_r0 = prof ? clock64() : 0;
         if (!raw_mode) {
