@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcrnerf_b200.so")
+# CRNERF_B200_LIB selects another build of the same ABI (A/B timing of kernel variants, tools/ab_kernel.sh)
+LIB_PATH = os.environ.get("CRNERF_B200_LIB") or os.path.join(_HERE, "libcrnerf_b200.so")
 
 c_float_p = C.c_void_p  # device pointers travel as integers
 

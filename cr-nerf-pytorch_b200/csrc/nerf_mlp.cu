@@ -617,7 +617,14 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
               umma_ts(tD, a_t + 8u, desc(b_lo + 2u), idesc, 1u);
               umma_ts(tD, a_t + 16u, desc(b_lo + 4u), idesc, 1u);
               umma_ts(tD, a_t + 24u, desc(b_lo + 6u), idesc, 1u);
-              if (release) umma_commit(&M->ring_empty[slot]);
+            }
+            // all 16 MMAs are queued: pass the pipe on before the (slow-to-issue) commits, so
+            // the partner's first MMA follows ours without a gap.  Slots are released at unit
+            // granularity - the ring holds two whole units, so nothing waits on the finer one.
+            *(volatile uint32_t*)&M->pipe_turn = my_turn + (solo ? 2u : 1u);
+            if (release) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_commit(&M->ring_empty[(g0 + (uint32_t)j) % kSlots]);
             }
           } else {
             // ---- embedding-fed and narrow units (layer 1, skip layer, dir, rgb): table-driven
@@ -646,7 +653,9 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         __syncwarp();
         if (prof) t_burst += clock64() - t_b0;
         my_turn += 2u;
-        if (lane == 0) *(volatile uint32_t*)&M->pipe_turn = my_turn - (solo ? 0u : 1u);
+        // (standard units passed the turn inside the burst; writing it again here could undo
+        // the partner's next hand-over)
+        if (!(ut & 0x400u) && lane == 0) *(volatile uint32_t*)&M->pipe_turn = my_turn - (solo ? 0u : 1u);
         ucount++;
       }
       g_base += (uint32_t)P.n_chunks;
