@@ -350,14 +350,15 @@ __device__ __forceinline__ void epi_stage(uint32_t tD_ch, const float* blob_g, u
     warp_arrive(d_empty);
     return;
   }
+  // both loads first and the "drained" signal right behind them: the issuer's next unit waits
+  // on it, the packing below does not
   uint32_t va[32], vb[32];
   tmem_ld_x32(tD_ch, va);
-  tmem_ld_wait();
-  tmem_ld_x32(tD_ch + 32, vb);  // in flight while the first slice is packed
-  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 32>(va, blob_g, boff, wsig_ch, staged, sig_acc, dbg);
+  tmem_ld_x32(tD_ch + 32, vb);
   tmem_ld_wait();
   tc_fence_before_sync();
   warp_arrive(d_empty);  // accumulator drained: the issuer may overwrite it
+  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 32>(va, blob_g, boff, wsig_ch, staged, sig_acc, dbg);
   epi_slice32<kFmt, kRelu, kSigma, kDbg, 16, 32>(vb, blob_g, boff + 32u, wsig_ch + 32, staged, sig_acc,
                                                  dbg ? dbg + 32 : nullptr);
   if constexpr (kSave) {
