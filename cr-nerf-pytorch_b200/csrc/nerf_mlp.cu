@@ -5,25 +5,29 @@
 // the 11-layer NeRF_sigma MLP (models/nerf.py:157-182) and the alpha composite
 // (rendering.py:121-143).  No (points x width) intermediate touches HBM.
 //
-// Structure (one CTA per SM, 384 threads):
-//   warp 0      producer : streams the packed weight image L2 -> smem ring with
+// Structure (one persistent CTA per SM, 640 threads = 20 warps):
+//   warp 0      producer : streams the packed weight image L2 -> 8-slot x 16 KB smem ring with
 //                          cp.async.bulk (TMA engine), mbarrier complete_tx
 //   warps 1, 3  issuers  : one per tile stream (X, Y); an elected thread issues
 //                          tcgen05.mma (kind::f16, M=128, N=128/64, K=16); activations
 //                          are the A operand read from TMEM (TS form), the embedding is
-//                          read from smem (SS form)
+//                          read from smem (SS form).  The two streams alternate whole
+//                          units (layer halves) through a shared-memory turn word; every
+//                          wait of a unit is taken before its turn, so a turn is one
+//                          uninterrupted burst of 16 MMAs.
 //   warp 2      TMEM allocator
-//   warps 4-7   epilogue group X, warps 8-11 epilogue group Y: each group owns
-//               one 128-point tile (one point per thread = one TMEM lane):
-//               embedding -> smem, per layer tcgen05.ld -> +bias -> ReLU ->
-//               cvt.f16x2 -> tcgen05.st back as next layer's A operand; sigma
-//               head as an fp32 dot in the layer-8 epilogue; segmented
-//               warp-shuffle transmittance scan; weighted feature reduction.
-// Two tiles (X, Y) are in flight per CTA and share every weight chunk; their
-// MMA streams are issued by separate warps so each stream's epilogues and
-// barrier waits run under the other stream's MMAs.  TMEM: X {A: cols 0-127, D: 128-255}, Y {A: 256-383,
-// D: 384-511}; the first output half is held in registers until the layer's
-// second half has been issued, so A needs no double buffer.
+//   warps 4-11  epilogue group X, warps 12-19 epilogue group Y (setmaxnreg 112): each group
+//               owns one 128-point tile; a warp owns a TMEM lane quarter (32 rows, one per
+//               lane) and a 64-column half of every 128-wide accumulator:
+//               embedding -> smem; per layer half tcgen05.ld -> + fp32 bias -> ReLU ->
+//               cvt.f16x2 -> (first halves wait in registers) -> tcgen05.st as the next
+//               layer's A operand; sigma head as an fp32 dot in the layer-8 epilogue;
+//               segmented warp-shuffle transmittance scan; in-warp butterfly feature sums.
+// Two tiles (X, Y) are in flight per CTA and share every weight chunk.
+// TMEM: X {A: cols 0-127, D: 128-255}, Y {A: 256-383, D: 384-511}; the first output half of
+// a layer is held in registers until the layer's second half has retired, so A needs no
+// double buffer, and the next layer may start on that half (a_half) while the second is
+// still being packed.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <algorithm>
