@@ -517,3 +517,29 @@ def test_graphed_renderer_replays_identical_results():
             assert torch.equal(got[k], want[k]), k
     with pytest.raises(ValueError):
         gr(rays[:100])
+
+
+@pytest.mark.parametrize("s", [16, 17, 64, 100, 192])
+def test_many_batch_shapes_terminate_and_agree_across_splits(s):
+    """Odd tile counts, single rays, batches smaller / larger than the SM count, sample counts that do
+    not divide the 128-row tile: every launch must terminate (turn / ring protocol) and a batch must
+    render the same whether it goes in one launch or two (tile-boundary and CTA-partition invariance)."""
+    o = ops()
+    models, _ = build_mirror_models(0)
+    fine = models["fine"].cuda()
+    packed = packed_for(fine)
+    g = torch.Generator().manual_seed(s)
+    for n in (1, 2, 3, 37, 148, 149, 1000, 4097):
+        rays = oracle.pinhole_rays(1, n, oracle.synthetic_pose(1))[:n].cuda()
+        z = torch.sort(torch.rand(n, s, generator=g) * 4.0 + 0.5, dim=1)[0].cuda()
+        w, f, d = o.render_pass(packed, rays, z)
+        torch.cuda.synchronize()
+        assert torch.isfinite(f).all() and torch.isfinite(w).all() and torch.isfinite(d).all()
+        assert float(w.sum(1).max()) <= 1.0 + 1e-5
+        if n > 1:
+            k = n // 2
+            w1, f1, d1 = o.render_pass(packed, rays[:k].contiguous(), z[:k].contiguous())
+            w2, f2, d2 = o.render_pass(packed, rays[k:].contiguous(), z[k:].contiguous())
+            assert torch.allclose(torch.cat([f1, f2]), f, rtol=1e-5, atol=1e-6)
+            assert torch.allclose(torch.cat([w1, w2]), w, rtol=1e-5, atol=1e-7)
+            assert torch.allclose(torch.cat([d1, d2]), d, rtol=1e-5, atol=1e-6)
