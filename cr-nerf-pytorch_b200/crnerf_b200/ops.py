@@ -549,3 +549,20 @@ def relu_bias_grad(g: torch.Tensor, act: Optional[torch.Tensor]) -> torch.Tensor
         check(lib.crnerf_relu_bias_grad(g.data_ptr(), _p(act), n, c, gb.data_ptr(), scratch.data_ptr(),
                                         _stream(dev)))
     return gb
+
+
+def generate_rays(height: int, width: int, K, c2w, near: float, far: float, device="cuda") -> torch.Tensor:
+    """(height*width, 8) rays [o3, d3, near, far] of a pinhole frame, built on the device
+    (reference datasets/ray_utils.py:5-52 + the row assembly of the datasets).  ``K`` is the 3x3
+    intrinsics (anything indexable as K[r][c]), ``c2w`` the 3x4 camera-to-world matrix."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise CrnerfError("generate_rays builds the rays in GPU memory; there is no CPU fallback")
+    intr = (C.c_float * 4)(float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]))
+    m = (C.c_float * 12)(*[float(c2w[r][c]) for r in range(3) for c in range(4)])
+    with torch.cuda.device(dev):
+        rays = torch.empty((height * width, 8), dtype=torch.float32, device=dev)
+        check(lib.crnerf_generate_rays(intr, m, float(near), float(far), int(height), int(width),
+                                       rays.data_ptr(), _stream(dev)))
+    return rays

@@ -79,6 +79,8 @@ int style_forward(const crnerf_style_weights* w, const float* content, int64_t n
                   float* transmatrix, float* fused, float* scratch, cudaStream_t st);
 int cnn_forward(const crnerf_cnn_weights* cw, const float* x, int64_t n, int64_t ps, int64_t cs,
                 float* out, float* scratch, cudaStream_t st);
+int generate_rays(const float* intr4_host, const float* c2w12_host, float near, float far, int H, int W,
+                  float* rays, cudaStream_t st);
 // implemented in backward.cu
 int composite_backward(const float* raw, const float* z, const float* noise, const float* g_feature,
                        const float* g_weights, const float* g_depth, int n_rays, int n_samples,
@@ -218,6 +220,13 @@ int crnerf_mlp_forward(const void* packed, int operand, int e_xyz, int e_dir, co
   a.n_samples = 1;
   a.raw = out;
   return launch_render(a, (cudaStream_t)stream);
+}
+
+int crnerf_generate_rays(const float* intrinsics_host, const float* c2w_host, float near, float far,
+                         int height, int width, float* rays, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return generate_rays(intrinsics_host, c2w_host, near, far, height, width, rays, (cudaStream_t)stream);
 }
 
 int crnerf_pos_embed(const float* x, int64_t n, int n_freqs, float* out, void* stream) {

@@ -169,6 +169,37 @@ sample_pdf_kernel(const float* __restrict__ bins_or_z, const float* __restrict__
   for (int i = lane; i < n_tot; i += 32) sorted_out[(long long)ray * n_tot + i] = buf[i];
 }
 
+// ---------------------------------------------------------------------------
+// Camera rays of a pinhole frame (reference datasets/ray_utils.py:5-52 + the (h*w, 8) row the
+// datasets build, phototourism_mask_grid_sample.py:300-307): pixel (i, j) -> camera direction
+// ((i-cx)/fx, -(j-cy)/fy, -1), rotated by c2w[:, :3], normalised; origin c2w[:, 3]; near, far.
+struct RayGenParams {
+  float fx, fy, cx, cy;
+  float c2w[12];
+  float near, far;
+  int H, W;
+};
+__global__ void generate_rays_kernel(const __grid_constant__ RayGenParams P, float* __restrict__ rays) {
+  const long long total = (long long)P.H * P.W;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx / P.W), i = (int)(idx - (long long)j * P.W);
+    const float dx = __fdiv_rn(__fsub_rn((float)i, P.cx), P.fx);
+    const float dy = -__fdiv_rn(__fsub_rn((float)j, P.cy), P.fy);
+    const float dz = -1.f;
+    float d[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)   // directions @ c2w[:, :3].T
+      d[k] = __fadd_rn(__fadd_rn(__fmul_rn(dx, P.c2w[4 * k]), __fmul_rn(dy, P.c2w[4 * k + 1])),
+                       __fmul_rn(dz, P.c2w[4 * k + 2]));
+    const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])),
+                                           __fmul_rn(d[2], d[2])));
+    float4* o = reinterpret_cast<float4*>(rays + idx * 8);
+    o[0] = make_float4(P.c2w[3], P.c2w[7], P.c2w[11], __fdiv_rn(d[0], nrm));
+    o[1] = make_float4(__fdiv_rn(d[1], nrm), __fdiv_rn(d[2], nrm), P.near, P.far);
+  }
+}
+
 int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -188,6 +219,22 @@ int pos_embed(const float* x, int64_t n, int n_freqs, float* out, cudaStream_t s
   CRNERF_REQUIRE(n_freqs >= 0 && n_freqs <= 32, "n_freqs out of range");
   if (n == 0) return CRNERF_OK;
   pos_embed_kernel<<<grid_for(n * (n_freqs + 1), 256), 256, 0, st>>>(x, n, n_freqs, out);
+  count_launch();
+  CRNERF_CUDA(cudaGetLastError());
+  return CRNERF_OK;
+}
+
+int generate_rays(const float* intr4_host, const float* c2w12_host, float near, float far, int H, int W,
+                  float* rays, cudaStream_t st) {
+  CRNERF_REQUIRE(intr4_host && c2w12_host && rays, "null argument");
+  CRNERF_REQUIRE(H >= 0 && W >= 0, "negative frame size");
+  CRNERF_REQUIRE((reinterpret_cast<uintptr_t>(rays) & 15) == 0, "rays must be 16-byte aligned");
+  if ((long long)H * W == 0) return CRNERF_OK;
+  RayGenParams P;
+  P.fx = intr4_host[0]; P.fy = intr4_host[1]; P.cx = intr4_host[2]; P.cy = intr4_host[3];
+  for (int i = 0; i < 12; ++i) P.c2w[i] = c2w12_host[i];
+  P.near = near; P.far = far; P.H = H; P.W = W;
+  generate_rays_kernel<<<grid_for((long long)H * W, 256), 256, 0, st>>>(P, rays);
   count_launch();
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;

@@ -138,6 +138,17 @@ int crnerf_mlp_forward(const void* packed, int operand, int e_xyz, int e_dir, co
  * [x, sin(2^0 x), cos(2^0 x), ...]. */
 int crnerf_pos_embed(const float* x, int64_t n, int n_freqs, float* out, void* stream);
 
+/* Camera rays of one pinhole frame, written straight into device memory as the (height*width, 8)
+ * rows [o3, d3, near, far] the renderer consumes - replaces get_ray_directions + get_rays
+ * (datasets/ray_utils.py:5-52) and the row assembly of the datasets
+ * (datasets/phototourism_mask_grid_sample.py:300-307), i.e. the per-frame CPU meshgrid and the
+ * 32 B/ray host->device copy of eval.py:279.  intrinsics_host = {fx, fy, cx, cy} (K[0,0], K[1,1],
+ * K[0,2], K[1,2]); c2w_host = the 3x4 camera-to-world matrix, row-major; both HOST pointers.
+ * Pixel (i = column, j = row) -> direction ((i-cx)/fx, -(j-cy)/fy, -1) rotated by c2w[:, :3] and
+ * normalised, origin c2w[:, 3]; row index j*width + i. */
+int crnerf_generate_rays(const float* intrinsics_host, const float* c2w_host, float near, float far,
+                         int height, int width, float* rays, void* stream);
+
 /* Coarse depths (models/rendering.py:161-176): z = near*(1-t)+far*t (or the
  * disparity form).  t_steps (n_samples) is the caller's linspace(0,1,n_samples)
  * (rendering.py:161; passed in so the grid is bit-identical to the one the

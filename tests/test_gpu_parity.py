@@ -543,3 +543,17 @@ def test_many_batch_shapes_terminate_and_agree_across_splits(s):
             assert torch.allclose(torch.cat([f1, f2]), f, rtol=1e-5, atol=1e-6)
             assert torch.allclose(torch.cat([w1, w2]), w, rtol=1e-5, atol=1e-7)
             assert torch.allclose(torch.cat([d1, d2]), d, rtol=1e-5, atol=1e-6)
+
+
+def test_generate_rays_matches_reference_ray_utils():
+    """crnerf_generate_rays vs the oracle's restatement of datasets/ray_utils.py (pinhole, fov 60 deg)."""
+    import math
+    for h, w in ((24, 40), (1, 7), (256, 320)):
+        c2w = oracle.synthetic_pose(3)
+        f = 0.5 * w / math.tan(0.5 * math.radians(60.0))
+        K = [[f, 0.0, w / 2], [0.0, f, h / 2], [0.0, 0.0, 1.0]]
+        got = ops().generate_rays(h, w, K, c2w.tolist(), 0.25, 4.5)
+        want = oracle.pinhole_rays(h, w, c2w, 0.25, 4.5)
+        assert got.shape == want.shape
+        assert torch.allclose(got.cpu(), want, rtol=2e-6, atol=2e-7)
+        assert torch.equal(got[:, 6:].cpu(), want[:, 6:]) and torch.equal(got[:, :3].cpu(), want[:, :3])
