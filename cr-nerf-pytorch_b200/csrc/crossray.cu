@@ -20,6 +20,9 @@
 #include "common.h"
 
 namespace crnerf {
+// gram_tc.cu
+int gram_tc(const crnerf_cnn_weights& cw, const float* g, int64_t n, int64_t ps, int64_t cs, const float* mean,
+            float* partial, int max_blocks, int* n_blocks, cudaStream_t st);
 namespace {
 
 constexpr int kC = 64;     // feature channels (MulLayer hard-codes 64, linearStyleTransfer.py:46-47)
@@ -409,12 +412,12 @@ int style_stats1(const float* content, int64_t n, int64_t ps, int64_t cs, float*
 int style_stats2(const crnerf_cnn_weights& cw, const float* content, int64_t n, int64_t ps,
                  int64_t cs, const float* mean, float* gram, float* partial, float scale,
                  cudaStream_t st) {
-  const int nb = blocks_for_pixels(n);
-  CRNERF_CUDA(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)sizeof(CnnSmem)));
-  gram_kernel<<<nb, 256, sizeof(CnnSmem), st>>>(content, n, ps, cs, mean, cw, partial);
+  // pixel MLP + Gram on the tensor core (gram_tc.cu), then the fixed-order sum of the per-block partials
+  int nb = 0;
+  int rc = gram_tc(cw, content, n, ps, cs, mean, partial, kMaxBlocks, &nb, st);
+  if (rc) return rc;
   reduce_partials_kernel<<<4, 256, 0, st>>>(partial, nb, 1024, scale, gram);
-  count_launch(2);
+  count_launch(1);
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;
 }
