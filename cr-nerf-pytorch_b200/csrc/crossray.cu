@@ -80,6 +80,40 @@ sums_kernel(const float* __restrict__ g, long long n, long long pix_stride, long
   if (tid < kC) partial[blockIdx.x * kC + tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
 }
 
+// Same for the renderer's row layout (a pixel's 64 channels contiguous, 16-byte aligned): a pure
+// HBM stream.  16 threads cover one pixel with float4 loads, 16 pixels per pass, 8 passes in
+// flight per thread; fixed-order block reduction.
+__global__ void __launch_bounds__(256)
+sums_rows_kernel(const float* __restrict__ g, long long n, long long pix_stride, float* __restrict__ partial) {
+  __shared__ float4 red[16][16];
+  const int c4 = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long r0 = blockIdx.x * per, r1 = min(n, r0 + per);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  long long r = r0 + rl;
+  for (; r + 7 * 16 < r1; r += 8 * 16) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(g + (r + 16 * u) * pix_stride) + c4);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+    }
+  }
+  for (; r < r1; r += 16) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g + r * pix_stride) + c4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  red[rl][c4] = acc;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    float t = 0.f;
+    for (int k = 0; k < 16; ++k) t += reinterpret_cast<const float*>(&red[k][c >> 2])[c & 3];
+    partial[blockIdx.x * kC + c] = t;
+  }
+}
+
 // out[i] = scale * sum_b partial[b][i], fixed order
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int n_parts, int len,
                                        float scale, float* __restrict__ out) {
@@ -367,6 +401,41 @@ apply_kernel(const float* __restrict__ g, long long n, long long pix_stride, lon
   }
 }
 
+// pass 3 for the row layout: one pixel per thread, the whole row requested up front
+// (16 x 16-byte loads in flight per thread), the 3x64 map broadcast from shared memory; same
+// fmaf order as apply_kernel, so both give identical bits.
+__global__ void __launch_bounds__(256)
+apply_rows_kernel(const float* __restrict__ g, long long n, long long pix_stride, const float* __restrict__ map,
+                  float* __restrict__ rgb) {
+  __shared__ float A[3][64], a0[3];
+  const int tid = threadIdx.x;
+  if (tid < 192) A[tid >> 6][tid & 63] = map[kMapA + tid];
+  if (tid < 3) a0[tid] = map[kMapA0 + tid];
+  __syncthreads();
+  const long long p = blockIdx.x * 256LL + tid;
+  if (p >= n) return;
+  float4 x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = __ldg(reinterpret_cast<const float4*>(g + p * pix_stride) + i);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      acc = fmaf(A[r][4 * i], x[i].x, acc);
+      acc = fmaf(A[r][4 * i + 1], x[i].y, acc);
+      acc = fmaf(A[r][4 * i + 2], x[i].z, acc);
+      acc = fmaf(A[r][4 * i + 3], x[i].w, acc);
+    }
+    acc += a0[r];
+    rgb[(long long)r * n + p] = 1.f / (1.f + expf(-acc));
+  }
+}
+
+static bool rows_fast(const float* g, long long ps, long long cs) {
+  return cs == 1 && (ps & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+}
+
 int blocks_for_pixels(long long n) {
   long long tiles = (n + kTP - 1) / kTP;
   long long cap = std::min<long long>(kMaxBlocks, 2LL * num_sms());
@@ -401,8 +470,13 @@ static int check_feat(const float* p, int64_t n, int64_t ps, int64_t cs, const c
 
 int style_stats1(const float* content, int64_t n, int64_t ps, int64_t cs, float* sums,
                  float* partial, cudaStream_t st) {
-  const int nb = blocks_for_pixels(n);
-  sums_kernel<<<nb, 256, 0, st>>>(content, n, ps, cs, partial);
+  int nb = blocks_for_pixels(n);
+  if (rows_fast(content, ps, cs)) {
+    nb = (int)std::max<long long>(1, std::min<long long>((n + 127) / 128, kMaxBlocks));
+    sums_rows_kernel<<<nb, 256, 0, st>>>(content, n, ps, partial);
+  } else {
+    sums_kernel<<<nb, 256, 0, st>>>(content, n, ps, cs, partial);
+  }
   reduce_partials_kernel<<<1, 64, 0, st>>>(partial, nb, 64, 1.f, sums);
   count_launch(2);
   CRNERF_CUDA(cudaGetLastError());
@@ -443,7 +517,10 @@ int style_finish(const crnerf_style_weights* w, const float* content, int64_t n,
   fc_kernel<<<256, 256, 0, st>>>(w->cnet.fc_w, w->cnet.fc_b, gram_c_normalised, w->snet.fc_w,
                                  w->snet.fc_b, gram_s, cmat, smat);
   compose_kernel<<<1, 256, 0, st>>>(cmat, smat, *w, mean_c, mean_s, map, transmatrix);
-  apply_kernel<<<blocks_for_pixels(n), 256, 0, st>>>(content, n, ps, cs, map, rgb, fused);
+  if (fused == nullptr && rows_fast(content, ps, cs))
+    apply_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(content, n, ps, map, rgb);
+  else
+    apply_kernel<<<blocks_for_pixels(n), 256, 0, st>>>(content, n, ps, cs, map, rgb, fused);
   count_launch(3);
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;
@@ -475,7 +552,10 @@ int style_forward(const crnerf_style_weights* w, const float* content, int64_t n
   float* map = scratch + kOffMap;
   if (style == nullptr) {
     content_map_kernel<<<1, 192, 0, st>>>(*w, map);
-    apply_kernel<<<blocks_for_pixels(n), 256, 0, st>>>(content, n, ps, cs, map, rgb, nullptr);
+    if (rows_fast(content, ps, cs))
+      apply_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(content, n, ps, map, rgb);
+    else
+      apply_kernel<<<blocks_for_pixels(n), 256, 0, st>>>(content, n, ps, cs, map, rgb, nullptr);
     count_launch(2);
     CRNERF_CUDA(cudaGetLastError());
     return CRNERF_OK;

@@ -27,7 +27,7 @@
 namespace crnerf {
 namespace {
 
-constexpr int kGThreads = 160;  // warps 0-3: one pixel row per thread; warp 4: MMA issuer + TMEM allocator
+constexpr int kGThreads = 288;  // warps 0-7: (lane quarter, column half) of a pixel row; warp 8: MMA issuer + TMEM allocator
 // shared memory map (bytes).  The Gram A operand is addressed as a 128-row tile although only
 // 32 rows (channels) exist: rows 32..127 alias whatever follows (the other Y^T slabs, the X
 // tile) and only feed accumulator lanes 32..127, which are never read.
@@ -83,17 +83,17 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    mbar_init(&bars[X_FULL], 4);
+    mbar_init(&bars[X_FULL], 8);
     mbar_init(&bars[D1_FULL], 1);
-    mbar_init(&bars[A1_FULL], 4);
+    mbar_init(&bars[A1_FULL], 8);
     mbar_init(&bars[D2_FULL], 1);
-    mbar_init(&bars[A2_FULL], 4);
+    mbar_init(&bars[A2_FULL], 8);
     mbar_init(&bars[D3_FULL], 1);
-    mbar_init(&bars[YT_FULL], 4);
+    mbar_init(&bars[YT_FULL], 8);
     mbar_init(&bars[G_DONE], 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc<512>(tmem_slot);
+  if (warp == 8) tmem_alloc<512>(tmem_slot);
   stage_weight(P.w.conv_w[0], 128, 64, smem + kW1Off, smem + kW1Off + 16384);
   stage_weight(P.w.conv_w[1], 64, 128, smem + kW2Off, smem + kW2Off + 16384);
   stage_weight(P.w.conv_w[2], 32, 64, smem + kW3Off, smem + kW3Off + 4096);
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
   const long long n_tiles = (P.n + 127) / 128;
   const float* b1 = fblob, *b2 = fblob + 128, *b3 = fblob + 192, *mean = fblob + 224;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 | version | SW128
     auto desc = [](uint32_t saddr) {
@@ -184,8 +184,30 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
     }
   } else {
     // ------------------------------------------------------------------ pixel rows
-    const int row = tid;  // 0..127 = TMEM lane
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    // warp w: TMEM lane quarter q = w & 3 (rows 32q..32q+31, one per lane), column half ch = w >> 2
+    const int q = warp & 3, ch = warp >> 2;
+    const int row = 32 * q + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    // this thread's half of a pixel row (32 channels) as 8 float4; the NEXT tile's values are
+    // requested while the current tile is being processed (registers are plentiful here)
+    float4 xr[8];
+    auto load_x = [&](long long t) {
+      const long long p = t * 128 + row;
+      const bool valid = t < n_tiles && p < P.n;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (valid && P.vec) {
+          xr[i] = __ldg(reinterpret_cast<const float4*>(P.g + p * P.pix_stride + 32 * ch) + i);
+        } else if (valid) {
+          const float* src = P.g + p * P.pix_stride + (long long)(32 * ch + 4 * i) * P.ch_stride;
+          xr[i] = make_float4(__ldg(src), __ldg(src + P.ch_stride), __ldg(src + 2 * P.ch_stride),
+                              __ldg(src + 3 * P.ch_stride));
+        } else {
+          xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    load_x(blockIdx.x);
     uint32_t it = 0;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const uint32_t par = it & 1;
@@ -196,25 +218,18 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
       {
         uint8_t* xh = smem + kXOff, *xl = xh + 16384;
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-          float v[8];
-          if (valid && P.vec) {
-            const float4 q0 = __ldg(reinterpret_cast<const float4*>(P.g + p * P.pix_stride + 8 * c8));
-            const float4 q1 = __ldg(reinterpret_cast<const float4*>(P.g + p * P.pix_stride + 8 * c8) + 1);
-            v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              v[j] = valid ? __ldg(P.g + p * P.pix_stride + (long long)(8 * c8 + j) * P.ch_stride) : 0.f;
-          }
+        for (int c8 = 0; c8 < 4; ++c8) {
+          const float4 q0 = xr[2 * c8], q1 = xr[2 * c8 + 1];
+          const float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+          const int c0 = 32 * ch + 8 * c8;
           uint32_t h[4], l[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float a = valid ? v[2 * j] - mean[8 * c8 + 2 * j] : 0.f;
-            const float b = valid ? v[2 * j + 1] - mean[8 * c8 + 2 * j + 1] : 0.f;
+            const float a = valid ? v[2 * j] - mean[c0 + 2 * j] : 0.f;
+            const float b = valid ? v[2 * j + 1] - mean[c0 + 2 * j + 1] : 0.f;
             split2(a, b, h[j], l[j]);
           }
-          const uint32_t off = sw128_offset(row, c8);
+          const uint32_t off = sw128_offset(row, 4 * ch + c8);
           *reinterpret_cast<uint4*>(xh + off) = make_uint4(h[0], h[1], h[2], h[3]);
           *reinterpret_cast<uint4*>(xl + off) = make_uint4(l[0], l[1], l[2], l[3]);
         }
@@ -222,20 +237,22 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[X_FULL]);
       }
+      load_x(t + gridDim.x);   // prefetch: lands under this tile's MMAs and epilogues
       // ---- epilogue 1: H1 = LeakyReLU(D1 + b1) -> A1 hi / lo (128 values = 64 + 64 columns)
       mbar_wait(&bars[D1_FULL], par, 64);
       tc_fence_after_sync();
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int qq = 0; qq < 2; ++qq) {
+        const int blk = 2 * ch + qq;
         uint32_t v[32], h[16], l[16];
-        tmem_ld_x32(lane_base + cD1 + 32 * q, v);
+        tmem_ld_x32(lane_base + cD1 + 32 * blk, v);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          split2(lrelu02(__uint_as_float(v[2 * j]) + b1[32 * q + 2 * j]),
-                 lrelu02(__uint_as_float(v[2 * j + 1]) + b1[32 * q + 2 * j + 1]), h[j], l[j]);
-        tmem_st_x16p(lane_base + cA1h + 16 * q, h);
-        tmem_st_x16p(lane_base + cA1l + 16 * q, l);
+          split2(lrelu02(__uint_as_float(v[2 * j]) + b1[32 * blk + 2 * j]),
+                 lrelu02(__uint_as_float(v[2 * j + 1]) + b1[32 * blk + 2 * j + 1]), h[j], l[j]);
+        tmem_st_x16p(lane_base + cA1h + 16 * blk, h);
+        tmem_st_x16p(lane_base + cA1l + 16 * blk, l);
       }
       tmem_st_wait();
       tc_fence_before_sync();
@@ -244,37 +261,37 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
       // ---- epilogue 2: H2 = LeakyReLU(D2 + b2) -> A2 hi / lo (64 values = 32 + 32 columns)
       mbar_wait(&bars[D2_FULL], par, 65);
       tc_fence_after_sync();
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      {
         uint32_t v[32], h[16], l[16];
-        tmem_ld_x32(lane_base + cD2 + 32 * q, v);
+        tmem_ld_x32(lane_base + cD2 + 32 * ch, v);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          split2(lrelu02(__uint_as_float(v[2 * j]) + b2[32 * q + 2 * j]),
-                 lrelu02(__uint_as_float(v[2 * j + 1]) + b2[32 * q + 2 * j + 1]), h[j], l[j]);
-        tmem_st_x16p(lane_base + cA2h + 16 * q, h);
-        tmem_st_x16p(lane_base + cA2l + 16 * q, l);
+          split2(lrelu02(__uint_as_float(v[2 * j]) + b2[32 * ch + 2 * j]),
+                 lrelu02(__uint_as_float(v[2 * j + 1]) + b2[32 * ch + 2 * j + 1]), h[j], l[j]);
+        tmem_st_x16p(lane_base + cA2h + 16 * ch, h);
+        tmem_st_x16p(lane_base + cA2l + 16 * ch, l);
       }
       tmem_st_wait();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[A2_FULL]);
       // ---- epilogue 3: Y = D3 + b3 (no activation, linearStyleTransfer.py:15), zero for pixels
-      // beyond n; Y^T hi / lo -> smem with the pixel index along K
+      // beyond n; Y^T hi / lo -> smem with the pixel index along K (this thread: 16 channels)
       mbar_wait(&bars[D3_FULL], par, 66);
       tc_fence_after_sync();
       {
-        uint32_t v[32];
-        tmem_ld_x32(lane_base + cD3, v);
+        uint32_t v[16];
+        tmem_ld_x16(lane_base + cD3 + 16 * ch, v);
         tmem_ld_wait();
         if (it > 0) mbar_wait(&bars[G_DONE], (it - 1) & 1, 67);  // previous Gram MMAs done reading Y^T
         uint8_t* yh = smem + kYtOff + (row >> 6) * kYtSlab;
         uint8_t* yl = yh + 2 * kYtSlab;
         const uint32_t kk = row & 63;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float y = valid ? __uint_as_float(v[c]) + b3[c] : 0.f;
+        for (int j = 0; j < 16; ++j) {
+          const int c = 16 * ch + j;
+          const float y = valid ? __uint_as_float(v[j]) + b3[c] : 0.f;
           const __half hi = __float2half_rn(y);
           const __half lo = __float2half_rn(y - __half2float(hi));
           const uint32_t off = sw128_offset(c, kk >> 3) + (kk & 7) * 2;
@@ -306,7 +323,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<512>(tmem);
+  if (warp == 8) tmem_dealloc<512>(tmem);
 }
 
 }  // namespace

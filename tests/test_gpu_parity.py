@@ -360,7 +360,9 @@ def test_style_net_matches_golden():
         close(rgb_c, c["rgb_content"], "rgb content-only", rtol=1e-5, atol=1e-6)
         close(fused, c["fused"], "fused feature", rtol=1e-4, atol=2e-6)
         close(trans, c["trans"], "transmatrix", rtol=1e-4, atol=1e-6)
-        assert torch.equal(rgb, rgb_nchw), "strided view and NCHW inputs must give identical results"
+        # both layouts are read in place; the row layout takes the streaming kernels, whose
+        # channel sums run in a different (still fixed) order
+        close(rgb, rgb_nchw, "strided view vs NCHW input", rtol=1e-6, atol=1e-7)
         p = state(dec.cpu())
         want_cm = oracle.cnn_forward(p, "multi_net.cnet", content.cpu())
         dec.cuda()
