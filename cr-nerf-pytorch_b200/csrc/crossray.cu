@@ -124,6 +124,20 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int n_
   out[i] = acc * scale;
 }
 
+// same result layout, for many partials: one warp per output element, lanes stride the partials
+// (independent loads in flight) and combine in a fixed shuffle tree - still deterministic
+__global__ void __launch_bounds__(256)
+reduce_partials_warp_kernel(const float* __restrict__ partial, int n_parts, int len, float scale,
+                            float* __restrict__ out) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= len) return;
+  float acc = 0.f;
+  for (int b = lane; b < n_parts; b += 32) acc += partial[(long long)b * len + i];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if (lane == 0) out[i] = acc * scale;
+}
+
 // ---------------------------------------------------------------- pass 2
 struct CnnSmem {
   float w1t[64][128];  // convs.0 transposed: [in][out]
@@ -477,7 +491,7 @@ int style_stats1(const float* content, int64_t n, int64_t ps, int64_t cs, float*
   } else {
     sums_kernel<<<nb, 256, 0, st>>>(content, n, ps, cs, partial);
   }
-  reduce_partials_kernel<<<1, 64, 0, st>>>(partial, nb, 64, 1.f, sums);
+  reduce_partials_warp_kernel<<<8, 256, 0, st>>>(partial, nb, 64, 1.f, sums);
   count_launch(2);
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;
@@ -490,7 +504,7 @@ int style_stats2(const crnerf_cnn_weights& cw, const float* content, int64_t n, 
   int nb = 0;
   int rc = gram_tc(cw, content, n, ps, cs, mean, partial, kMaxBlocks, &nb, st);
   if (rc) return rc;
-  reduce_partials_kernel<<<4, 256, 0, st>>>(partial, nb, 1024, scale, gram);
+  reduce_partials_warp_kernel<<<128, 256, 0, st>>>(partial, nb, 1024, scale, gram);
   count_launch(1);
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;

@@ -115,11 +115,11 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
       return (static_cast<uint64_t>(kHi) << 32) | (((saddr & 0x3ffffu) >> 4) | (1u << 16));
     };
     const uint32_t s0 = smem_u32(smem);
-    uint32_t it = 0;
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      const uint32_t par = it & 1;
-      // ---- layer 1: D1 = X W1^T, three split terms x 4 k-steps (SS)
-      mbar_wait(&bars[X_FULL], par, 60);
+    // layer 1 of tile i: D1 = X W1^T, three split terms x 4 k-steps (SS).  Issued one stage
+    // ahead (right after layer 2 of the previous tile): X(i) is staged as soon as D1(i-1) has
+    // been drained, so these MMAs run under the previous tile's layer-3 / Gram phases.
+    auto layer1 = [&](uint32_t i) {
+      mbar_wait(&bars[X_FULL], i & 1, 60);
       tc_fence_after_sync();
       if (elect_one()) {
         const uint32_t id = make_idesc_f16(128, 128, 0);
@@ -133,6 +133,11 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
         umma_commit(&bars[D1_FULL]);
       }
       __syncwarp();
+    };
+    uint32_t it = 0;
+    if ((long long)blockIdx.x < n_tiles) layer1(0);
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const uint32_t par = it & 1;
       // ---- layer 2: D2 = H1 W2^T, K = 128 (TS)
       mbar_wait(&bars[A1_FULL], par, 61);
       tc_fence_after_sync();
@@ -149,6 +154,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
         umma_commit(&bars[D2_FULL]);
       }
       __syncwarp();
+      if (t + gridDim.x < n_tiles) layer1(it + 1);   // A1_FULL(it) above also means D1 is drained
       // ---- layer 3: D3 = H2 W3^T, K = 64 (TS)
       mbar_wait(&bars[A2_FULL], par, 62);
       tc_fence_after_sync();
@@ -207,14 +213,9 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
         }
       }
     };
-    load_x(blockIdx.x);
-    uint32_t it = 0;
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      const uint32_t par = it & 1;
-      const long long p = t * 128 + row;
-      const bool valid = p < P.n;
-      // ---- X row -> smem (hi, lo).  The previous tile's layer-1 MMAs retired before its
-      // D1_FULL, which this thread has already waited on.
+    // X row (held in xr) of tile tt -> smem (hi, lo), then signal the issuer
+    auto stage_x = [&](long long tt) {
+      const bool valid = tt * 128 + row < P.n;
       {
         uint8_t* xh = smem + kXOff, *xl = xh + 16384;
 #pragma unroll
@@ -237,7 +238,17 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[X_FULL]);
       }
-      load_x(t + gridDim.x);   // prefetch: lands under this tile's MMAs and epilogues
+    };
+    load_x(blockIdx.x);
+    if ((long long)blockIdx.x < n_tiles) {
+      stage_x(blockIdx.x);
+      load_x(blockIdx.x + gridDim.x);
+    }
+    uint32_t it = 0;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const uint32_t par = it & 1;
+      const long long p = t * 128 + row;
+      const bool valid = p < P.n;
       // ---- epilogue 1: H1 = LeakyReLU(D1 + b1) -> A1 hi / lo (128 values = 64 + 64 columns)
       mbar_wait(&bars[D1_FULL], par, 64);
       tc_fence_after_sync();
@@ -258,6 +269,12 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[A1_FULL]);
+      // D1(t) is drained and its MMAs have retired: stage the next tile's X now, so its layer 1
+      // runs under this tile's remaining phases; then request the tile after that
+      if (t + gridDim.x < n_tiles) {
+        stage_x(t + gridDim.x);
+        load_x(t + 2 * gridDim.x);
+      }
       // ---- epilogue 2: H2 = LeakyReLU(D2 + b2) -> A2 hi / lo (64 values = 32 + 32 columns)
       mbar_wait(&bars[D2_FULL], par, 65);
       tc_fence_after_sync();
