@@ -9,7 +9,7 @@
 // where C = fc_c(Gram(cnet(x - mu_c))/HW) needs statistics over ALL pixels (the
 // "cross-ray" part) and S the same over the style feature.  So the data path is
 //   pass 1  channel sums               (read feature map once)
-//   pass 2  pixel MLP 64-128-64-32 + 32x32 Gram partials (read it again)
+//   pass 2  pixel MLP 64-128-64-32 + 32x32 Gram partials (read it again; tensor core, gram_tc.cu)
 //   tiny    partial reductions, two 1024x1024 GEMVs, compose A / a0
 //   pass 3  apply the 3x64 map + sigmoid (read it a third time, write RGB)
 // All reductions use per-block partials combined in a fixed order, so results
@@ -30,7 +30,6 @@ constexpr int kTP = 64;    // pixels per tile
 constexpr int kTPS = 68;   // padded tile row (float4-aligned)
 constexpr int kMaxBlocks = 296;
 
-__device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : 0.2f * v; }
 
 // tile loader: xin[c][px] = x[p0+px][c] - mean[c]   (zero for px beyond n)
 __device__ __forceinline__ void load_tile(const float* __restrict__ g, long long n, long long p0,
@@ -139,142 +138,7 @@ reduce_partials_warp_kernel(const float* __restrict__ partial, int n_parts, int 
 }
 
 // ---------------------------------------------------------------- pass 2
-struct CnnSmem {
-  float w1t[64][128];  // convs.0 transposed: [in][out]
-  float w2t[128][64];  // convs.2
-  float w3t[64][32];   // convs.4
-  float b1[128], b2[64], b3[32], mean[64];
-  float xin[kC][kTPS];
-  float h1[128][kTPS];
-  float h2[64][kTPS];
-  float y[32][kTPS];
-};
-
-// partial[block][i*32+j] = sum over this block's pixels of y_i y_j,
-// y = convs(x - mean)  (CNN.forward, linearStyleTransfer.py:29-34, before the /(h*w))
-__global__ void __launch_bounds__(256, 1)
-gram_kernel(const float* __restrict__ g, long long n, long long pix_stride, long long ch_stride,
-            const float* __restrict__ mean, crnerf_cnn_weights w, float* __restrict__ partial) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  CnnSmem& S = *reinterpret_cast<CnnSmem*>(smem_raw);
-  const int tid = threadIdx.x;
-  for (int i = tid; i < 128 * 64; i += 256) S.w1t[i & 63][i >> 6] = w.conv_w[0][i];  // (128,64)
-  for (int i = tid; i < 64 * 128; i += 256) S.w2t[i & 127][i >> 7] = w.conv_w[1][i];  // (64,128)
-  for (int i = tid; i < 32 * 64; i += 256) S.w3t[i & 63][i >> 6] = w.conv_w[2][i];   // (32,64)
-  if (tid < 128) S.b1[tid] = w.conv_b[0][tid];
-  if (tid < 64) S.b2[tid] = w.conv_b[1][tid];
-  if (tid < 32) S.b3[tid] = w.conv_b[2][tid];
-  if (tid < 64) S.mean[tid] = mean[tid];
-  __syncthreads();
-
-  const int tx = tid & 15, ty = tid >> 4;
-  const int px4 = 4 * tx;
-  const int gi = (tid * 4) >> 5, gj = (tid * 4) & 31;  // Gram entries (gi, gj..gj+3)
-  float gacc[4] = {0.f, 0.f, 0.f, 0.f};
-  const long long n_tiles = (n + kTP - 1) / kTP;
-
-  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const long long p0 = t * kTP;
-    load_tile(g, n, p0, pix_stride, ch_stride, S.mean, S.xin);
-    __syncthreads();
-    {  // 64 -> 128, LeakyReLU(0.2): 8 channels x 4 pixels per thread
-      float acc[8][4];
-#pragma unroll
-      for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-#pragma unroll 4
-      for (int k = 0; k < 64; ++k) {
-        const float4 xv = *reinterpret_cast<const float4*>(&S.xin[k][px4]);
-        const float4 wa = *reinterpret_cast<const float4*>(&S.w1t[k][8 * ty]);
-        const float4 wb = *reinterpret_cast<const float4*>(&S.w1t[k][8 * ty + 4]);
-        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-        for (int a = 0; a < 8; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(wv[a], xs[b], acc[a][b]);
-      }
-#pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        const float bb = S.b1[8 * ty + a];
-        *reinterpret_cast<float4*>(&S.h1[8 * ty + a][px4]) =
-            make_float4(lrelu(acc[a][0] + bb), lrelu(acc[a][1] + bb), lrelu(acc[a][2] + bb),
-                        lrelu(acc[a][3] + bb));
-      }
-    }
-    __syncthreads();
-    {  // 128 -> 64, LeakyReLU(0.2): 4 channels x 4 pixels per thread
-      float acc[4][4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-#pragma unroll 4
-      for (int k = 0; k < 128; ++k) {
-        const float4 xv = *reinterpret_cast<const float4*>(&S.h1[k][px4]);
-        const float4 wa = *reinterpret_cast<const float4*>(&S.w2t[k][4 * ty]);
-        const float wv[4] = {wa.x, wa.y, wa.z, wa.w};
-        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(wv[a], xs[b], acc[a][b]);
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const float bb = S.b2[4 * ty + a];
-        *reinterpret_cast<float4*>(&S.h2[4 * ty + a][px4]) =
-            make_float4(lrelu(acc[a][0] + bb), lrelu(acc[a][1] + bb), lrelu(acc[a][2] + bb),
-                        lrelu(acc[a][3] + bb));
-      }
-    }
-    __syncthreads();
-    {  // 64 -> 32 (no activation): 2 channels x 4 pixels per thread; mask pixels beyond n
-      float acc[2][4];
-#pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-#pragma unroll 4
-      for (int k = 0; k < 64; ++k) {
-        const float4 xv = *reinterpret_cast<const float4*>(&S.h2[k][px4]);
-        const float2 wa = *reinterpret_cast<const float2*>(&S.w3t[k][2 * ty]);
-        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          acc[0][b] = fmaf(wa.x, xs[b], acc[0][b]);
-          acc[1][b] = fmaf(wa.y, xs[b], acc[1][b]);
-        }
-      }
-#pragma unroll
-      for (int a = 0; a < 2; ++a) {
-        const float bb = S.b3[2 * ty + a];
-        float o[4];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) o[b] = (p0 + px4 + b < n) ? acc[a][b] + bb : 0.f;
-        *reinterpret_cast<float4*>(&S.y[2 * ty + a][px4]) = make_float4(o[0], o[1], o[2], o[3]);
-      }
-    }
-    __syncthreads();
-    // Gram partial: y y^T over this tile's pixels
-#pragma unroll 4
-    for (int q = 0; q < kTP / 4; ++q) {
-      const float4 a = *reinterpret_cast<const float4*>(&S.y[gi][4 * q]);
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const float4 b = *reinterpret_cast<const float4*>(&S.y[gj + jj][4 * q]);
-        gacc[jj] = fmaf(a.x, b.x, gacc[jj]);
-        gacc[jj] = fmaf(a.y, b.y, gacc[jj]);
-        gacc[jj] = fmaf(a.z, b.z, gacc[jj]);
-        gacc[jj] = fmaf(a.w, b.w, gacc[jj]);
-      }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int jj = 0; jj < 4; ++jj) partial[(long long)blockIdx.x * 1024 + tid * 4 + jj] = gacc[jj];
-}
+// pixel MLP 64 -> 128 -> 64 -> 32 + Gram partials: gram_tc.cu (tcgen05)
 
 // ---------------------------------------------------------------- tiny stage
 // rows [0,1024): cnet.fc(gram_c); rows [1024,2048): snet.fc(gram_s).  One warp per row.
