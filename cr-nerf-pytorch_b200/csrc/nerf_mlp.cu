@@ -650,6 +650,8 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
                 for (int k = 0; k < nk; ++k)
                   umma_ts(tD, a_t + 8u * k, desc(b_lo + 2u * k), idesc, k ? 1u : acc0);
               }
+              // the last chunk's MMAs are queued: hand the pipe over before its commit
+              if (j == nch - 1) *(volatile uint32_t*)&M->pipe_turn = my_turn + (solo ? 2u : 1u);
               if (release) umma_commit(&M->ring_empty[slot]);
             }
           }
@@ -658,9 +660,8 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         __syncwarp();
         if (prof) t_burst += clock64() - t_b0;
         my_turn += 2u;
-        // (standard units passed the turn inside the burst; writing it again here could undo
-        // the partner's next hand-over)
-        if (!(ut & 0x400u) && lane == 0) *(volatile uint32_t*)&M->pipe_turn = my_turn - (solo ? 0u : 1u);
+        // (the turn was passed inside the burst by the elected lane; writing it again here could
+        // undo the partner's next hand-over)
         ucount++;
       }
       g_base += (uint32_t)P.n_chunks;
