@@ -627,6 +627,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
             // the partner's first MMA follows ours without a gap.  Slots are released at unit
             // granularity - the ring holds two whole units, so nothing waits on the finer one.
             *(volatile uint32_t*)&M->pipe_turn = my_turn + (solo ? 2u : 1u);
+            umma_commit(&M->d_full[b]);   // the epilogue's wake-up first, the ring releases after it
             if (release) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) umma_commit(&M->ring_empty[(g0 + (uint32_t)j) % kSlots]);
@@ -654,8 +655,8 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
               if (j == nch - 1) *(volatile uint32_t*)&M->pipe_turn = my_turn + (solo ? 2u : 1u);
               if (release) umma_commit(&M->ring_empty[slot]);
             }
+            umma_commit(&M->d_full[b]);
           }
-          umma_commit(&M->d_full[b]);
         }
         __syncwarp();
         if (prof) t_burst += clock64() - t_b0;
