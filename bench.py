@@ -48,7 +48,7 @@ UNIT = "ray-samples/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of one fused fine-pass launch, from the committed
 # `ncu --set full` capture (bench.py cannot run ncu on itself); the kernel is tensor-bound,
 # HBM traffic is rays/z in, weights/feature/depth out plus the 1.3 MB weight image once
-NCU_DRAM_BYTES_PER_LAUNCH = 4678144
+NCU_DRAM_BYTES_PER_LAUNCH = 4676864
 NCU_TRAFFIC_SOURCE = "profiles/r01_ncu_fused_fine_pass_metrics.txt (dram__bytes_read.sum + dram__bytes_write.sum)"
 WORKLOAD = ("configs[1]: 4096-ray eval batches (slices of a 320x256 synthetic Brandenburg-Gate-shaped "
             "frame), 64 coarse + 128 fine samples, N_emb_xyz=15, N_emb_dir=4, nerf_out_dim=64, "
