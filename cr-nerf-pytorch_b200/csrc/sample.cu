@@ -147,6 +147,40 @@ sample_pdf_kernel(const float* __restrict__ bins_or_z, const float* __restrict__
 
   const int n_tot = n_coarse + n_imp;
   for (int i = lane; i < n_coarse; i += 32) buf[i] = brow[i];
+  __syncwarp();
+  // Fast path: both runs are already sorted (coarse depths always are; the new samples are
+  // whenever u is non-decreasing, e.g. the shared linspace of eval mode) -> merge by rank:
+  // an element's final position is its index in its own run plus the number of elements of
+  // the other run that precede it (ties: coarse first).  Two binary searches per lane-step
+  // instead of a 36-stage bitonic network.  Any other order of equal values would produce the
+  // same sorted row, so this is bit-identical to sort(cat(...)).
+  bool sorted_runs = true;
+  for (int i = lane; i + 1 < n_imp; i += 32) sorted_runs &= buf[n_coarse + i] <= buf[n_coarse + i + 1];
+  for (int i = lane; i + 1 < n_coarse; i += 32) sorted_runs &= buf[i] <= buf[i + 1];
+  if (__all_sync(0xffffffffu, sorted_runs)) {
+    float* orow = sorted_out + (long long)ray * n_tot;
+    const float* sc = buf;             // coarse run
+    const float* sn = buf + n_coarse;  // new samples
+    for (int i = lane; i < n_coarse; i += 32) {   // # new samples strictly below sc[i]
+      const float v = sc[i];
+      int lo = 0, hi = n_imp;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sn[mid] < v) lo = mid + 1; else hi = mid;
+      }
+      orow[i + lo] = v;
+    }
+    for (int j = lane; j < n_imp; j += 32) {      // # coarse depths not above sn[j]
+      const float v = sn[j];
+      int lo = 0, hi = n_coarse;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sc[mid] <= v) lo = mid + 1; else hi = mid;
+      }
+      orow[j + lo] = v;
+    }
+    return;
+  }
   for (int i = n_tot + lane; i < sort_pad; i += 32) buf[i] = CUDART_INF_F;
   __syncwarp();
   // bitonic sort of sort_pad (power of two) values held in shared memory
