@@ -559,3 +559,33 @@ def test_generate_rays_matches_reference_ray_utils():
         assert got.shape == want.shape
         assert torch.allclose(got.cpu(), want, rtol=2e-6, atol=2e-7)
         assert torch.equal(got[:, 6:].cpu(), want[:, 6:]) and torch.equal(got[:, :3].cpu(), want[:, :3])
+
+
+def test_full_size_4096x192_against_torch_cuda_reference():
+    """BASELINE.json's full size (4096 rays, 64+128 samples) against the reference math executed by
+    stock PyTorch CUDA ops on the same GPU (fp32, TF32 off): the oracle's functions are device
+    agnostic, so this is the reference's own library-kernel path ('CUDA-side oracle')."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        models, args = build_mirror_models(0)
+        dev = torch.device("cuda")
+        p = {k: {kk: vv.to(dev) for kk, vv in state(m).items()} for k, m in models.items() if k != "decoder"}
+        models = {k: m.cuda() for k, m in models.items()}
+        rays = oracle.pinhole_rays(64, 64, oracle.synthetic_pose(0)).to(dev)
+        rng = {"noise_coarse": torch.zeros(4096, 64, device=dev), "noise_fine": torch.zeros(4096, 192, device=dev)}
+        rec = {}
+        with torch.no_grad():
+            ref = oracle.render_rays(p["coarse"], p["fine"], rays, n_samples=64, n_importance=128, perturb=0,
+                                     noise_std=0, chunk=1 << 20, rng=rng, record=rec)
+        got = _render(models, args, rays, 64, 128)
+        for k in ("feature_coarse", "feature_fine"):
+            close(got[k], ref[k], f"end to end {k} vs torch-CUDA reference", **REF)
+            assert oracle.psnr(got[k].cpu(), ref[k].cpu()) > 95.0
+        close(got["depth_fine"], ref["depth_fine"], "depth_fine", rtol=2e-4, atol=2e-5)
+        # stage-wise at full size: the reference's own fine depths through our fused pass
+        w, f, d = ops().render_pass(packed_for(models["fine"]), rays, rec["z_fine"].contiguous())
+        close(f, ref["feature_fine"], "fine pass on the reference's depths: feature", **REF)
+        close(w, ref["weights_fine"], "fine pass on the reference's depths: weights", rtol=2e-4, atol=5e-6)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
