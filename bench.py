@@ -87,8 +87,17 @@ def cpu_state(models):
     return sd(models["coarse"]), sd(models["fine"])
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must use every host core
+    (only rank 0 runs it, so there is no oversubscription)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_reference_throughput(oracle, state, rays, reps, warm=1):
     """ray-samples/s of the CPU port on all host threads; each rep = one 4096-ray batch."""
+    use_all_host_threads()
     pc, pf = state
     times = []
     with torch.no_grad():
@@ -196,7 +205,7 @@ def run_reference(args):
     oracle = load_oracle()
     models, _ = build_models()
     rays = frame_rays(oracle)
-    cores = torch.get_num_threads()
+    cores = use_all_host_threads()
     value, times = cpu_reference_throughput(oracle, cpu_state(models), rays, reps=max(1, args.steps),
                                             warm=max(1, min(args.warmup, 2)))
     sample = f"{len(times)} x one 4096-ray batch (786,432 ray-samples each) on {cores} threads"
@@ -356,7 +365,7 @@ def run_ours(args):
                 "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src, "kernel_ms": k_ms,
                 "flop_per_launch": flop}
         if world == 1 and not args.no_cpu_baseline:
-            cores = torch.get_num_threads()
+            cores = use_all_host_threads()
             v, times = cpu_reference_throughput(oracle, state_cpu, rays_cpu, reps=5, warm=1)
             cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"5 x one 4096-ray batch (786,432 ray-samples each), "
