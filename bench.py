@@ -77,9 +77,10 @@ def build_models():
     return {"coarse": coarse.eval(), "fine": fine.eval(), "decoder": decoder.eval()}, args
 
 
-def frame_rays(oracle):
+def frame_rays():
     """A 320x256 frame = 20 batches of 4096 rays, fov 60 deg, near 0 / far 5."""
-    return oracle.pinhole_rays(256, 320, oracle.synthetic_pose(0), 0.0, 5.0)
+    from crnerf_b200.synthetic import pinhole_rays, synthetic_pose
+    return pinhole_rays(256, 320, synthetic_pose(0), 0.0, 5.0)
 
 
 def cpu_state(models):
@@ -119,7 +120,8 @@ def psnr_delta(oracle, models_gpu, state_cpu, emb, margs, dev):
     style feature) on the right half of the image, as eval_metric.py:89-93 does."""
     from models.rendering import render_rays_cross_ray
     h = w = 64
-    rays = oracle.pinhole_rays(h, w, oracle.synthetic_pose(0), 0.0, 5.0)
+    from crnerf_b200.synthetic import pinhole_rays, synthetic_pose
+    rays = pinhole_rays(h, w, synthetic_pose(0), 0.0, 5.0)
     g = torch.Generator().manual_seed(1)
     style = torch.rand(1, 64, 32, 32, generator=g)
     style_t = torch.rand(1, 64, 32, 32, generator=g)
@@ -202,9 +204,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    oracle = load_oracle()
+    oracle = load_oracle()          # the reference arm IS the CPU port
     models, _ = build_models()
-    rays = frame_rays(oracle)
+    rays = frame_rays()
     cores = use_all_host_threads()
     value, times = cpu_reference_throughput(oracle, cpu_state(models), rays, reps=max(1, args.steps),
                                             warm=max(1, min(args.warmup, 2)))
@@ -239,9 +241,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    oracle = load_oracle()
     models, margs = build_models()
-    rays_cpu = frame_rays(oracle)
+    rays_cpu = frame_rays()
     state_cpu = cpu_state(models)          # nn.Module.to() moves in place: keep a CPU copy
     models_gpu = {k: v.to(dev) for k, v in models.items()}
     emb = {"xyz": PosEmbedding(14, 15), "dir": PosEmbedding(3, 4)}
@@ -365,6 +366,7 @@ def run_ours(args):
                 "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src, "kernel_ms": k_ms,
                 "flop_per_launch": flop}
         if world == 1 and not args.no_cpu_baseline:
+            oracle = load_oracle()      # cpu_baseline / PSNR legs only: the checker, never the thing measured
             cores = use_all_host_threads()
             v, times = cpu_reference_throughput(oracle, state_cpu, rays_cpu, reps=5, warm=1)
             cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -373,7 +375,7 @@ def run_ours(args):
 
     psnr = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        psnr = psnr_delta(oracle, models_gpu, state_cpu, emb, margs, dev)
+        psnr = psnr_delta(load_oracle(), models_gpu, state_cpu, emb, margs, dev)
 
     if rank == 0:
         line = {

@@ -4,12 +4,13 @@ import os, sys, json, statistics
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (os.path.join(ROOT, "cr-nerf-pytorch_b200"), os.path.join(ROOT, "oracle"), ROOT): sys.path.insert(0, p)
 import torch
+from crnerf_b200 import synthetic
 import crnerf_oracle as oracle
 from bench import build_models
 models, _ = build_models(); dev = torch.device("cuda")
 pc = {k: v.to(dev) for k, v in models["coarse"].state_dict().items()}
 pf = {k: v.to(dev) for k, v in models["fine"].state_dict().items()}
-rays = oracle.pinhole_rays(64, 64, oracle.synthetic_pose(0)).to(dev)
+rays = synthetic.pinhole_rays(64, 64, synthetic.synthetic_pose(0)).to(dev)
 rng = {"noise_coarse": torch.zeros(4096, 64, device=dev), "noise_fine": torch.zeros(4096, 192, device=dev)}
 out = {}
 for tf32 in (False, True):

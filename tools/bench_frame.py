@@ -10,9 +10,10 @@ and the stand-alone timing of the cross-ray block against its HBM roofline
 (algorithmic bytes = 3 reads of the (H*W,64) fp32 feature map + 12 B/pixel of rgb + 8.6 MB of FC weights)."""
 import argparse, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (os.path.join(ROOT, "cr-nerf-pytorch_b200"), os.path.join(ROOT, "oracle"), ROOT):
+for p in (os.path.join(ROOT, "cr-nerf-pytorch_b200"), ROOT):
     sys.path.insert(0, p)
 import torch
+from crnerf_b200 import synthetic
 import torch.distributed as dist
 
 
@@ -25,7 +26,6 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--scheme", default="stats")
     a = ap.parse_args()
-    import crnerf_oracle as oracle
     from bench import build_models
     from models.nerf import PosEmbedding
     from crnerf_b200.frame import render_frame_sharded, CudaStyleBackend, fuse_decode_sharded
@@ -38,7 +38,7 @@ def main():
     models = {k: m.to(dev) for k, m in models.items()}
     emb = {"xyz": PosEmbedding(14, 15), "dir": PosEmbedding(3, 4)}
     h, w = a.hw
-    rays = oracle.pinhole_rays(h, w, oracle.synthetic_pose(0)).to(dev)
+    rays = synthetic.pinhole_rays(h, w, synthetic.synthetic_pose(0)).to(dev)
     style = torch.rand(1, 64, 32, 32, generator=torch.Generator().manual_seed(1)).to(dev)
 
     def frame():

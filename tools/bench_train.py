@@ -12,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (os.path.join(ROOT, "cr-nerf-pytorch_b200"), os.path.join(ROOT, "oracle"), ROOT):
     sys.path.insert(0, p)
 import torch
+from crnerf_b200 import synthetic
 import torch.distributed as dist
 
 
@@ -42,7 +43,7 @@ def main():
     models = {k: m.to(dev).train() for k, m in models.items()}
     emb = {"xyz": PosEmbedding(14, 15), "dir": PosEmbedding(3, 4)}
     side = int(a.rays ** 0.5)
-    rays = oracle.pinhole_rays(side, side, oracle.synthetic_pose(rank)).to(dev)
+    rays = synthetic.pinhole_rays(side, side, synthetic.synthetic_pose(rank)).to(dev)
     style = torch.rand(1, 64, 32, 32, device=dev)
     target = torch.rand(side * side, 3, device=dev)
     params = [p for m in models.values() for p in m.parameters()]

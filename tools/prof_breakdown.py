@@ -2,16 +2,16 @@
 thread of each tile group spend their time.  Run on a B200: python tools/prof_breakdown.py"""
 import os, sys, types
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "cr-nerf-pytorch_b200")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "cr-nerf-pytorch_b200"))
 import torch
-import crnerf_oracle as oracle
+from crnerf_b200 import synthetic
 from crnerf_b200 import ops
 from models.nerf import NeRF_sigma
 
 torch.manual_seed(0)
 args = types.SimpleNamespace(nerf_out_dim=64, pertubeCord=False, img_wh=[64, 64])
 fine = NeRF_sigma('fine', args, in_channels_xyz=93, in_channels_dir=27).cuda()
-rays = oracle.pinhole_rays(64, 64, oracle.synthetic_pose(0)).cuda()
+rays = synthetic.pinhole_rays(64, 64, synthetic.synthetic_pose(0)).cuda()
 EXPS = [(-2, "normal"), (-3, "EXP1: epilogue skips TMEM traffic + math"),
         (-4, "EXP2: producer skips weight copies"), (-5, "EXP1+EXP2"), (-6, "EXP4: no bias MMAs")]
 if len(sys.argv) > 1 and sys.argv[1] == "bias":

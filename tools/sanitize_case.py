@@ -4,9 +4,9 @@ sharded cross-ray phases, and one training forward/backward.
   compute-sanitizer --tool racecheck python tools/sanitize_case.py"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (os.path.join(ROOT, "cr-nerf-pytorch_b200"), os.path.join(ROOT, "oracle"), ROOT): sys.path.insert(0, p)
+for p in (os.path.join(ROOT, "cr-nerf-pytorch_b200"), ROOT): sys.path.insert(0, p)
 import torch
-import crnerf_oracle as oracle
+from crnerf_b200 import synthetic
 from bench import build_models
 from models.nerf import PosEmbedding
 from models.rendering import render_rays_cross_ray
@@ -14,7 +14,7 @@ from crnerf_b200.frame import CudaStyleBackend, fuse_decode_sharded
 models, margs = build_models(); dev = torch.device("cuda")
 models = {k: m.to(dev) for k, m in models.items()}
 emb = {"xyz": PosEmbedding(14, 15), "dir": PosEmbedding(3, 4)}
-rays = oracle.pinhole_rays(12, 16, oracle.synthetic_pose(0)).to(dev)
+rays = synthetic.pinhole_rays(12, 16, synthetic.synthetic_pose(0)).to(dev)
 style = torch.rand(1, 64, 32, 32, device=dev)
 with torch.no_grad():
     res = render_rays_cross_ray(models, emb, rays, None, 40, False, 0, 0, 24, 4096, False, test_time=True, args=margs)

@@ -2,15 +2,15 @@
 usage: [CRNERF_B200_LIB=path.so] python tools/time_kernel.py [reps]"""
 import os, sys, statistics
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (os.path.join(ROOT, "cr-nerf-pytorch_b200"), os.path.join(ROOT, "oracle"), ROOT): sys.path.insert(0, p)
+for p in (os.path.join(ROOT, "cr-nerf-pytorch_b200"), ROOT): sys.path.insert(0, p)
 import torch
-import crnerf_oracle as oracle
+from crnerf_b200 import synthetic
 from bench import build_models
 from crnerf_b200 import ops
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 models, _ = build_models(); dev = torch.device("cuda")
 fine = models["fine"].to(dev)
-rays = oracle.pinhole_rays(64, 64, oracle.synthetic_pose(0)).to(dev)
+rays = synthetic.pinhole_rays(64, 64, synthetic.synthetic_pose(0)).to(dev)
 z = ops.coarse_z(rays, torch.linspace(0, 1, 192, device=dev))
 packed = fine.packed()
 flush = torch.empty(64 * 1024 * 1024, device=dev)

@@ -2,7 +2,7 @@
 usage: [CRNERF_B200_LIB=path.so] python tools/time_sample.py"""
 import os, sys, statistics
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (os.path.join(ROOT, "cr-nerf-pytorch_b200"), os.path.join(ROOT, "oracle"), ROOT): sys.path.insert(0, p)
+for p in (os.path.join(ROOT, "cr-nerf-pytorch_b200"), ROOT): sys.path.insert(0, p)
 import torch
 from crnerf_b200 import ops
 dev = torch.device("cuda")
