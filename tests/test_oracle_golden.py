@@ -91,3 +91,15 @@ def test_operand_emulation_meets_tolerance():
     ref = g["ref"]["feature_fine"]
     assert torch.allclose(h["feature_fine"], ref, rtol=1e-4, atol=1e-6)
     assert not torch.allclose(b["feature_fine"], ref, rtol=1e-4, atol=1e-6)
+
+
+def test_product_synthetic_rays_equal_the_oracle_generator():
+    """bench.py / tools build their inputs with crnerf_b200.synthetic (so that the oracle is only ever
+    the checker); it must stay bit-identical to the oracle's restatement of datasets/ray_utils.py."""
+    from crnerf_b200 import synthetic
+    for seed in (0, 3):
+        assert torch.equal(synthetic.synthetic_pose(seed), oracle.synthetic_pose(seed))
+    for h, w in ((7, 9), (64, 64)):
+        a = synthetic.pinhole_rays(h, w, synthetic.synthetic_pose(1), 0.25, 4.5)
+        b = oracle.pinhole_rays(h, w, oracle.synthetic_pose(1), 0.25, 4.5)
+        assert torch.equal(a, b)
