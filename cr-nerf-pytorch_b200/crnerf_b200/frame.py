@@ -122,16 +122,24 @@ def fuse_decode_sharded(backend, feat_local: torch.Tensor, style: torch.Tensor, 
     return _gather_blocks(rgb_local, n_total, group, dim=1)
 
 
-def render_frame_sharded(models, embeddings, rays: torch.Tensor, style: Optional[torch.Tensor],
+def render_frame_sharded(models, embeddings, rays: Optional[torch.Tensor], style: Optional[torch.Tensor],
                          hw: Tuple[int, int], N_samples: int, N_importance: int, chunk: int = 4096,
                          use_disp: bool = False, scheme: str = "stats", group=None, backend=None,
-                         **kwargs) -> torch.Tensor:
+                         camera=None, **kwargs) -> torch.Tensor:
     """Render one H x W frame whose ``rays`` (H*W, 8) are known to every rank; each rank
     renders its own row block and the frame's rgb (1,3,H,W) is returned on every rank.
+    With ``rays=None`` and ``camera=(K, c2w, near, far)`` the rays are built in GPU memory
+    (``ops.generate_rays``: no per-frame host meshgrid, no 32 B/ray host-to-device copy).
 
     Equivalent single-GPU code in the reference: eval.py:279-294 (``batched_inference`` then
     ``models['decoder'](feature, a_embedded_from_img)``)."""
     h, w = hw
+    if rays is None:
+        if camera is None:
+            raise ValueError("give either rays or camera=(K, c2w, near, far)")
+        from . import ops
+        K, c2w, near, far = camera
+        rays = ops.generate_rays(h, w, K, c2w, near, far, device=next(models["coarse"].parameters()).device)
     n_total = rays.shape[0]
     if n_total != h * w:
         raise ValueError(f"rays has {n_total} rows, frame is {h}x{w}")

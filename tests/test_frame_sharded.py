@@ -140,3 +140,24 @@ def test_render_frame_sharded_single_rank_matches_two_step_path(scheme):
                                  noise_std=0, chunk=8192)
         ref_rgb = oracle.style_net_forward(p["decoder"], ref["feature_fine"].t().reshape(1, 64, h, w), style.cpu())
     assert torch.allclose(rgb.cpu(), ref_rgb, rtol=1e-4, atol=2e-6)
+
+
+@pytest.mark.gpu
+def test_render_frame_from_camera_equals_render_from_rays():
+    """rays=None + camera=(K, c2w, near, far): rays built on the device by crnerf_generate_rays."""
+    import math
+    from crnerf_b200.frame import render_frame_sharded
+    from models.nerf import PosEmbedding
+    models, args = build_mirror_models(0)
+    models = {k: m.cuda() for k, m in models.items()}
+    emb = {"xyz": PosEmbedding(14, 15), "dir": PosEmbedding(3, 4)}
+    h, w = 20, 28
+    c2w = oracle.synthetic_pose(2)
+    f = 0.5 * w / math.tan(0.5 * math.radians(60.0))
+    K = [[f, 0.0, w / 2], [0.0, f, h / 2], [0.0, 0.0, 1.0]]
+    style = torch.rand(1, 64, 32, 32, generator=torch.Generator().manual_seed(2)).cuda()
+    a = render_frame_sharded(models, emb, None, style, (h, w), 32, 32, chunk=256, camera=(K, c2w.tolist(), 0.0, 5.0),
+                             args=args)
+    b = render_frame_sharded(models, emb, oracle.pinhole_rays(h, w, c2w).cuda(), style, (h, w), 32, 32, chunk=256,
+                             args=args)
+    assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
