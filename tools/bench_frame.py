@@ -66,6 +66,18 @@ def main():
     for _ in range(5): fuse_decode_sharded(be, feat, style, feat.shape[0] * world)
     e1.record(); sync()
     cr_ms = e0.elapsed_time(e1) / 5
+    # ray generation alone (crnerf_generate_rays): 32 B written per ray, nothing read
+    import math
+    from crnerf_b200 import ops
+    fl = 0.5 * w / math.tan(math.radians(30.0))
+    Kc = [[fl, 0.0, w / 2], [0.0, fl, h / 2], [0.0, 0.0, 1.0]]
+    pose = synthetic.synthetic_pose(0).tolist()
+    ops.generate_rays(h, w, Kc, pose, 0.0, 5.0, device=dev); sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): ops.generate_rays(h, w, Kc, pose, 0.0, 5.0, device=dev)
+    e1.record(); sync()
+    rg_ms = e0.elapsed_time(e1) / 10
     if rank == 0:
         bytes_alg = feat.shape[0] * (3 * 256 + 12) + 8.6e6
         peak = 6555.5
@@ -76,6 +88,8 @@ def main():
                           "crossray_ms_per_rank": cr_ms, "crossray_alg_bytes_per_rank": bytes_alg,
                           "crossray_gbs": bytes_alg / (cr_ms * 1e-3) / 1e9, "hbm_peak_gbs": peak,
                           "crossray_frac": bytes_alg / (cr_ms * 1e-3) / 1e9 / peak,
+                          "raygen_ms": rg_ms, "raygen_gbs": n * 32 / (rg_ms * 1e-3) / 1e9,
+                          "raygen_frac": n * 32 / (rg_ms * 1e-3) / 1e9 / peak,
                           "rgb_mean": float(rgb.mean())}), flush=True)
     if world > 1: dist.destroy_process_group()
 
