@@ -61,6 +61,7 @@ SIGNATURES = {
                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "crnerf_generate_rays": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int,
                                        C.c_int, C.c_void_p, C.c_void_p]),
+    "crnerf_rgb_to_u8": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "crnerf_pos_embed": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "crnerf_coarse_z": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),

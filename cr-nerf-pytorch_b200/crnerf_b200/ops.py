@@ -566,3 +566,26 @@ def generate_rays(height: int, width: int, K, c2w, near: float, far: float, devi
         check(lib.crnerf_generate_rays(intr, m, float(near), float(far), int(height), int(width),
                                        rays.data_ptr(), _stream(dev)))
     return rays
+
+
+def rgb_to_u8(rgb: torch.Tensor) -> torch.Tensor:
+    """(1,3,H,W) or (3,n) fp32 rgb -> (H,W,3) / (n,3) uint8 = uint8(clip(x,0,1)*255), reference eval.py:295-297."""
+    lib = _lib.load()
+    _need(rgb, "rgb")
+    shape = None
+    if rgb.dim() == 4:
+        if rgb.shape[0] != 1 or rgb.shape[1] != 3:
+            raise ValueError("rgb must be (1,3,H,W) or (3,n)")
+        shape = (rgb.shape[2], rgb.shape[3], 3)
+        flat = _c(rgb).reshape(3, -1)
+    elif rgb.dim() == 2 and rgb.shape[0] == 3:
+        flat = _c(rgb)
+    else:
+        raise ValueError("rgb must be (1,3,H,W) or (3,n)")
+    n = flat.shape[1]
+    dev = rgb.device
+    with torch.cuda.device(dev):
+        out = torch.empty((n, 3), dtype=torch.uint8, device=dev)
+        if n:
+            check(lib.crnerf_rgb_to_u8(flat.data_ptr(), n, out.data_ptr(), _stream(dev)))
+    return out.reshape(shape) if shape is not None else out

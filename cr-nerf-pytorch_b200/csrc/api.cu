@@ -81,6 +81,7 @@ int cnn_forward(const crnerf_cnn_weights* cw, const float* x, int64_t n, int64_t
                 float* out, float* scratch, cudaStream_t st);
 int generate_rays(const float* intr4_host, const float* c2w12_host, float near, float far, int H, int W,
                   float* rays, cudaStream_t st);
+int rgb_to_u8(const float* rgb, int64_t n, uint8_t* out, cudaStream_t st);
 // implemented in backward.cu
 int composite_backward(const float* raw, const float* z, const float* noise, const float* g_feature,
                        const float* g_weights, const float* g_depth, int n_rays, int n_samples,
@@ -227,6 +228,12 @@ int crnerf_generate_rays(const float* intrinsics_host, const float* c2w_host, fl
   int rc = device_check();
   if (rc) return rc;
   return generate_rays(intrinsics_host, c2w_host, near, far, height, width, rays, (cudaStream_t)stream);
+}
+
+int crnerf_rgb_to_u8(const float* rgb, int64_t n_pixels, uint8_t* out, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return rgb_to_u8(rgb, n_pixels, out, (cudaStream_t)stream);
 }
 
 int crnerf_pos_embed(const float* x, int64_t n, int n_freqs, float* out, void* stream) {

@@ -234,6 +234,20 @@ __global__ void generate_rays_kernel(const __grid_constant__ RayGenParams P, flo
   }
 }
 
+// ---------------------------------------------------------------------------
+// Output stage of the eval loop (reference eval.py:295-297): rgb (3, n) planar fp32 in [0,1] ->
+// (n, 3) interleaved uint8 = uint8(clip(x, 0, 1) * 255) (truncation, as numpy's astype).
+__global__ void rgb_to_u8_kernel(const float* __restrict__ rgb, long long n, uint8_t* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = fminf(fmaxf(rgb[(long long)c * n + i], 0.f), 1.f);
+      out[i * 3 + c] = (uint8_t)(int)__fmul_rn(v, 255.f);
+    }
+  }
+}
+
 int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -253,6 +267,15 @@ int pos_embed(const float* x, int64_t n, int n_freqs, float* out, cudaStream_t s
   CRNERF_REQUIRE(n_freqs >= 0 && n_freqs <= 32, "n_freqs out of range");
   if (n == 0) return CRNERF_OK;
   pos_embed_kernel<<<grid_for(n * (n_freqs + 1), 256), 256, 0, st>>>(x, n, n_freqs, out);
+  count_launch();
+  CRNERF_CUDA(cudaGetLastError());
+  return CRNERF_OK;
+}
+
+int rgb_to_u8(const float* rgb, int64_t n, uint8_t* out, cudaStream_t st) {
+  CRNERF_REQUIRE(rgb && out, "null argument");
+  if (n <= 0) return CRNERF_OK;
+  rgb_to_u8_kernel<<<grid_for(n, 256), 256, 0, st>>>(rgb, n, out);
   count_launch();
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;

@@ -149,6 +149,11 @@ int crnerf_pos_embed(const float* x, int64_t n, int n_freqs, float* out, void* s
 int crnerf_generate_rays(const float* intrinsics_host, const float* c2w_host, float near, float far,
                          int height, int width, float* rays, void* stream);
 
+/* Output stage of the eval loop (eval.py:295-297): rgb (3, n_pixels) planar fp32 (what
+ * crnerf_style_forward writes) -> out (n_pixels, 3) interleaved uint8 = uint8(clip(x,0,1)*255),
+ * so a frame leaves the GPU as 3 B/pixel instead of 12. */
+int crnerf_rgb_to_u8(const float* rgb, int64_t n_pixels, uint8_t* out, void* stream);
+
 /* Coarse depths (models/rendering.py:161-176): z = near*(1-t)+far*t (or the
  * disparity form).  t_steps (n_samples) is the caller's linspace(0,1,n_samples)
  * (rendering.py:161; passed in so the grid is bit-identical to the one the

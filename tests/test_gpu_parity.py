@@ -589,3 +589,15 @@ def test_full_size_4096x192_against_torch_cuda_reference():
         close(w, ref["weights_fine"], "fine pass on the reference's depths: weights", rtol=2e-4, atol=5e-6)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_rgb_to_u8_matches_eval_output_stage():
+    """uint8(clip(x,0,1)*255) as eval.py:295-297 (numpy clip + astype truncation), bit exact."""
+    import numpy as np
+    g = torch.Generator().manual_seed(4)
+    rgb = torch.rand(1, 3, 17, 23, generator=g) * 1.4 - 0.2
+    rgb[0, 0, 0, :4] = torch.tensor([0.0, 1.0, 0.999999, 254.5 / 255])
+    want = (np.clip(rgb[0].permute(1, 2, 0).numpy(), 0, 1) * 255).astype(np.uint8)
+    got = ops().rgb_to_u8(rgb.cuda())
+    assert got.shape == (17, 23, 3) and got.dtype == torch.uint8
+    assert np.array_equal(got.cpu().numpy(), want)
