@@ -51,12 +51,15 @@ class RenderPassFn(torch.autograd.Function):
         w, f, d, acts, raw = ops.render_pass_train(packed, rays, z_vals, noise, view_dir, n_fx, n_fd)
         ctx.save_for_backward(rays, z_vals, noise, view_dir, acts, raw, *params)
         ctx.n_fx, ctx.n_fd = n_fx, n_fd
+        ctx.set_materialize_grads(False)   # outputs the loss does not use arrive as None, not as zeros
         return w, f, d
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_w, g_f, g_d):
         rays, z, noise, view_dir, acts, raw, *params = ctx.saved_tensors
+        if g_w is None and g_f is None and g_d is None:
+            return (None,) * (7 + len(params))
         W, B = params[:12], params[12:]
         n, s = z.shape
         P = n * s
