@@ -62,6 +62,22 @@ SIGNATURES = {
     "crnerf_generate_rays": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int,
                                        C.c_int, C.c_void_p, C.c_void_p]),
     "crnerf_rgb_to_u8": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "crnerf_ray_loss_forward": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_float, C.c_float, C.c_float,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crnerf_ray_loss_backward": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_float, C.c_float, C.c_float] +
+                                 [C.c_void_p] * 5),
+    "crnerf_pair_loss_forward": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_float),
+                                           C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crnerf_pair_loss_backward": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_float),
+                                            C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                            C.c_void_p]),
+    "crnerf_loss_scratch_floats": (C.c_size_t, []),
+    "crnerf_mask_sample_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "crnerf_mask_sample_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "crnerf_pos_embed": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "crnerf_coarse_z": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),

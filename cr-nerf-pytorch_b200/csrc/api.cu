@@ -88,6 +88,22 @@ int composite_backward(const float* raw, const float* z, const float* noise, con
                        float* d_rgb_pre, float* d_sigma_pre, cudaStream_t st);
 int relu_bias_grad(float* g, const void* act, int64_t n_points, int width, float* gb, float* scratch,
                    cudaStream_t st);
+// implemented in loss.cu
+size_t loss_scratch_floats();
+int ray_loss_forward(const float* coarse, const float* fine, const float* target, const float* mask,
+                     int64_t n_rays, float coef, float size_delta, float digit_delta, float* out4,
+                     float* scratch, cudaStream_t st);
+int ray_loss_backward(const float* coarse, const float* fine, const float* target, const float* mask,
+                      int64_t n_rays, float coef, float size_delta, float digit_delta, const float* go4,
+                      float* g_coarse, float* g_fine, float* g_mask, cudaStream_t st);
+int pair_loss_forward(int n_terms, const float* const* a, const float* const* b, const int64_t* n, const int* mode,
+                      const float* scale, float* out, float* scratch, cudaStream_t st);
+int pair_loss_backward(int n_terms, const float* const* a, const float* const* b, const int64_t* n, const int* mode,
+                       const float* scale, const float* go, float* const* ga, float* const* gb, cudaStream_t st);
+int mask_sample_forward(const float* pred, int channels, int h, int w, int H, int W, const int64_t* idx, int64_t n,
+                        float* out, cudaStream_t st);
+int mask_sample_backward(const float* g_out, int channels, int h, int w, int H, int W, const int64_t* idx, int64_t n,
+                         float* g_pred, cudaStream_t st);
 
 }  // namespace crnerf
 
@@ -234,6 +250,57 @@ int crnerf_rgb_to_u8(const float* rgb, int64_t n_pixels, uint8_t* out, void* str
   int rc = device_check();
   if (rc) return rc;
   return rgb_to_u8(rgb, n_pixels, out, (cudaStream_t)stream);
+}
+
+int crnerf_ray_loss_forward(const float* rgb_coarse, const float* rgb_fine, const float* targets,
+                            const float* mask, int64_t n_rays, float coef, float size_delta,
+                            float digit_delta, float* out4, float* scratch, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return ray_loss_forward(rgb_coarse, rgb_fine, targets, mask, n_rays, coef, size_delta, digit_delta, out4,
+                          scratch, (cudaStream_t)stream);
+}
+
+int crnerf_ray_loss_backward(const float* rgb_coarse, const float* rgb_fine, const float* targets,
+                             const float* mask, int64_t n_rays, float coef, float size_delta,
+                             float digit_delta, const float* grad_out4, float* g_rgb_coarse,
+                             float* g_rgb_fine, float* g_mask, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return ray_loss_backward(rgb_coarse, rgb_fine, targets, mask, n_rays, coef, size_delta, digit_delta,
+                           grad_out4, g_rgb_coarse, g_rgb_fine, g_mask, (cudaStream_t)stream);
+}
+
+int crnerf_pair_loss_forward(int n_terms, const float* const* a, const float* const* b,
+                             const int64_t* n, const int* mode, const float* scale, float* out,
+                             float* scratch, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return pair_loss_forward(n_terms, a, b, n, mode, scale, out, scratch, (cudaStream_t)stream);
+}
+
+int crnerf_pair_loss_backward(int n_terms, const float* const* a, const float* const* b,
+                              const int64_t* n, const int* mode, const float* scale,
+                              const float* grad_out, float* const* ga, float* const* gb, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return pair_loss_backward(n_terms, a, b, n, mode, scale, grad_out, ga, gb, (cudaStream_t)stream);
+}
+
+size_t crnerf_loss_scratch_floats(void) { return device_check() == CRNERF_OK ? loss_scratch_floats() : 0; }
+
+int crnerf_mask_sample_forward(const float* pred, int channels, int h, int w, int H, int W,
+                               const int64_t* idx, int64_t n, float* out, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return mask_sample_forward(pred, channels, h, w, H, W, idx, n, out, (cudaStream_t)stream);
+}
+
+int crnerf_mask_sample_backward(const float* g_out, int channels, int h, int w, int H, int W,
+                                const int64_t* idx, int64_t n, float* g_pred, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return mask_sample_backward(g_out, channels, h, w, H, W, idx, n, g_pred, (cudaStream_t)stream);
 }
 
 int crnerf_pos_embed(const float* x, int64_t n, int n_freqs, float* out, void* stream) {

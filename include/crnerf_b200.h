@@ -127,6 +127,51 @@ int crnerf_composite_backward(const float* raw, const float* z_vals, const float
 int crnerf_relu_bias_grad(float* g, const void* act, int64_t n_points, int width, float* gb,
                           float* scratch, void* stream);
 
+/* ---- loss + mask tail of the training step ------------------------------
+ * All pointers are device pointers unless marked HOST.  `scratch` for the two *_loss_forward
+ * calls: crnerf_loss_scratch_floats() floats whose first 16 bytes are zero before the first
+ * use (the kernels leave them zero); one scratch per stream.
+ *
+ * CRNeRFLoss.forward's per-ray terms (losses.py:62-76) in one launch:
+ *   out4[0] c_l  = coef * 0.5 * mean((1-mask) * (rgb_coarse-targets)^2)     (losses.py:63-66)
+ *   out4[1] f_l  = the same on rgb_fine (0 if rgb_fine == NULL)              (losses.py:70-74)
+ *   out4[2] r_ms = coef * size_delta * mean(mask^2)                          (mask_regularize, :80-84)
+ *   out4[3] r_md = coef * digit_delta * mean(1/((mask-0.5)^2 + 0.02))        (:86-87)
+ * rgb_* / targets (n_rays,3), mask (n_rays) or NULL (then (1-mask) = 1 and r_ms = r_md = 0). */
+int crnerf_ray_loss_forward(const float* rgb_coarse, const float* rgb_fine, const float* targets,
+                            const float* mask, int64_t n_rays, float coef, float size_delta,
+                            float digit_delta, float* out4, float* scratch, void* stream);
+/* Gradients of sum_k grad_out4[k]*out4[k] (grad_out4 == NULL: all ones).  c_l sees the mask
+ * detached (losses.py:64); g_* may be NULL to skip an output. */
+int crnerf_ray_loss_backward(const float* rgb_coarse, const float* rgb_fine, const float* targets,
+                             const float* mask, int64_t n_rays, float coef, float size_delta,
+                             float digit_delta, const float* grad_out4, float* g_rgb_coarse,
+                             float* g_rgb_fine, float* g_mask, void* stream);
+/* Up to 4 embedding terms per launch, out[k] = scale[k] * mean(f(a_k, b_k)) over n[k] elements:
+ *   mode 0: a^2           kl_a = _l2_regularize(a_embedded)                  (losses.py:53, :91-94)
+ *   mode 1: |a - b|       rec_a_random, L1 form                              (losses.py:57)
+ *   mode 2: (a - b)^2     rec_a_random MSE form / content_constraint         (losses.py:56, :68)
+ * a, b, n, mode, scale are HOST arrays of n_terms entries (a[k], b[k] device pointers). */
+int crnerf_pair_loss_forward(int n_terms, const float* const* a, const float* const* b,
+                             const int64_t* n, const int* mode, const float* scale, float* out,
+                             float* scratch, void* stream);
+/* ga[k] / gb[k] (device, n[k] floats, either may be NULL) receive grad_out[k] * d out[k] / d a_k, b_k. */
+int crnerf_pair_loss_backward(int n_terms, const float* const* a, const float* const* b,
+                              const int64_t* n, const int* mode, const float* scale,
+                              const float* grad_out, float* const* ga, float* const* gb, void* stream);
+size_t crnerf_loss_scratch_floats(void);
+
+/* The mask lookup of NeRFSystem.forward (train_mask_grid_sample.py:171-175):
+ *   interpolate(pred (1,C,h,w), size=(H,W), mode='bilinear', align_corners=False)
+ *   -> rearrange '1 n h w -> (h w) n' -> [rgb_idx]
+ * evaluated only at the n sampled pixels: out (n, C).  idx (n) int64 flat pixel indices in
+ * [0, H*W), or NULL for every pixel in order (validation; then n == H*W). */
+int crnerf_mask_sample_forward(const float* pred, int channels, int h, int w, int H, int W,
+                               const int64_t* idx, int64_t n, float* out, void* stream);
+/* g_pred (C,h,w) = the adjoint scatter of g_out (n, C) (zeroed inside, fp32 atomics). */
+int crnerf_mask_sample_backward(const float* g_out, int channels, int h, int w, int H, int W,
+                                const int64_t* idx, int64_t n, float* g_pred, void* stream);
+
 /* NeRF_sigma.forward on pre-embedded rows (models/nerf.py:157-182):
  *   x (n, x_stride) with [0,e_xyz) xyz embedding, [e_xyz, e_xyz+e_dir) dir
  *   embedding; out (n, 65) = [sigmoid features(64) | softplus sigma].

@@ -348,3 +348,49 @@ def synthetic_pose(seed: int = 0) -> Tensor:
 def psnr(a: Tensor, b: Tensor) -> float:
     """-10 log10(mse) as metrics.py:4-13."""
     return float(-10.0 * torch.log10(torch.mean((a.double() - b.double()) ** 2)))
+
+
+# --------------------------------------------------------------------------
+# f3  loss + mask tail of the training step (SURVEY.md 8f rank 3)
+#     CRNeRFLoss.forward (reference losses.py:50-89), ExponentialAnnealingWeight
+#     (losses.py:30-39), the mask lookup of NeRFSystem.forward
+#     (train_mask_grid_sample.py:171-175)
+# --------------------------------------------------------------------------
+def annealing_weight(hp, global_step: int) -> float:
+    """ExponentialAnnealingWeight.getWeight (losses.py:38-39)."""
+    return max(hp.maskrs_min, hp.maskrs_max * math.exp(-global_step * hp.maskrs_k))
+
+
+def crnerf_loss(inputs: Dict[str, Tensor], targets: Tensor, hp, global_step: int, coef: float = 1.0):
+    """Returns (dict of loss terms in the reference's key order, annealing weight)."""
+    ret = {}
+    size_delta = annealing_weight(hp, global_step)
+    if "a_embedded" in inputs:
+        ret["kl_a"] = torch.mean(inputs["a_embedded"] ** 2) * hp.weightKL                       # :53, :91-94
+        if "a_embedded_random_rec" in inputs:
+            d = inputs["a_embedded_random"].detach() - inputs["a_embedded_random_rec"]
+            ret["rec_a_random"] = ((d ** 2).mean() if hp.mse_on_appearance else d.abs().mean()) * hp.weightRecA
+    if "out_mask" in inputs:
+        mask = inputs["out_mask"]
+        ret["c_l"] = 0.5 * ((1 - mask.detach()) * (inputs["rgb_coarse"] - targets) ** 2).mean()  # :63-64
+    else:
+        ret["c_l"] = 0.5 * ((inputs["rgb_coarse"] - targets) ** 2).mean()
+    if "content_wo_a_embed" in inputs and "content_with_a_embed" in inputs:
+        ret["content_constraint"] = ((inputs["content_wo_a_embed"] - inputs["content_with_a_embed"]) ** 2
+                                     ).mean() * hp.weightcontent                                  # :67-68
+    if "rgb_fine" in inputs:
+        if "out_mask" in inputs:
+            ret["r_ms"] = torch.mean(mask ** 2) * size_delta                                      # :80-84
+            ret["r_md"] = torch.mean(1 / ((mask - 0.5) ** 2 + 0.02)) * hp.maskrd                  # :86-87
+            ret["f_l"] = 0.5 * ((1 - mask) * (inputs["rgb_fine"] - targets) ** 2).mean()          # :72
+        else:
+            ret["f_l"] = 0.5 * ((inputs["rgb_fine"] - targets) ** 2).mean()
+    return {k: coef * v for k, v in ret.items()}, size_delta
+
+
+def mask_sample(pred: Tensor, hw, idx: Optional[Tensor]) -> Tensor:
+    """pred (1,C,h,w) -> bilinear (align_corners=False) at size hw -> '(h w) c' rows -> [idx]
+    (train_mask_grid_sample.py:172-175)."""
+    up = F.interpolate(pred, size=tuple(hw), mode="bilinear", align_corners=False)
+    rows = up[0].permute(1, 2, 0).reshape(-1, pred.shape[1])
+    return rows if idx is None else rows[idx]

@@ -231,19 +231,81 @@ def case_style(nerf, lst):
     print("  style_net: pinned (3 sizes)")
 
 
+def case_loss():
+    """CRNeRFLoss (reference losses.py) and the mask lookup (train_mask_grid_sample.py:171-175,
+    restated inline from torch calls the script makes) on seeded inputs."""
+    sys.path.insert(0, REF)
+    import importlib
+    ref_losses = importlib.import_module("losses")
+    sys.path.remove(REF)
+    out = {"kind": "loss", "cases": []}
+    for ci, (n, with_mask, with_fine, with_a, with_c, mse_a, step) in enumerate([
+            (1024, True, True, True, True, False, 0), (1024, True, True, True, False, True, 1500),
+            (777, False, True, False, False, False, 10), (1024, True, False, True, False, False, 3),
+            (4096, True, True, False, True, False, 200000)]):
+        g = torch.Generator().manual_seed(100 + ci)
+        hp = types.SimpleNamespace(maskrs_max=5e-2, maskrs_min=6e-3, maskrs_k=1e-3, maskrd=0.0 if ci != 1 else 1e-3,
+                                   weightKL=1e-5, weightRecA=1e-3, weightcontent=1e-4, mse_on_appearance=mse_a)
+        inputs = {"rgb_coarse": torch.rand(n, 3, generator=g)}
+        targets = torch.rand(n, 3, generator=g)
+        if with_fine:
+            inputs["rgb_fine"] = torch.rand(n, 3, generator=g)
+        if with_mask:
+            inputs["out_mask"] = torch.rand(n, 1, generator=g)
+        if with_a:
+            inputs["a_embedded"] = torch.randn(1, 64, 8, 8, generator=g)
+            inputs["a_embedded_random"] = torch.randn(1, 64, 8, 8, generator=g)
+            inputs["a_embedded_random_rec"] = torch.randn(1, 64, 8, 8, generator=g)
+        if with_c:
+            inputs["content_wo_a_embed"] = torch.randn(1, 64, 8, 8, generator=g)
+            inputs["content_with_a_embed"] = torch.randn(1, 64, 8, 8, generator=g)
+        leaf = {k: v.clone().requires_grad_(True) for k, v in inputs.items()}
+        crit = ref_losses.loss_dict["crnerf"](hp, coef=1)
+        ref, w = crit(leaf, targets, hp, step)
+        total = sum(l for l in ref.values())
+        total.backward()
+        mine, w2 = oracle.crnerf_loss(inputs, targets, hp, step, coef=1)
+        assert list(mine) == list(ref) and w == w2
+        for k in ref:
+            assert_equal(f"loss:{k}", mine[k], ref[k].detach())
+        out["cases"].append({"inputs": inputs, "targets": targets, "hp": vars(hp), "step": step,
+                             "ref": {k: v.detach() for k, v in ref.items()}, "weight": w,
+                             "grads": {k: v.grad for k, v in leaf.items() if v.grad is not None}})
+    # mask lookup: the three torch calls of train_mask_grid_sample.py:172-175
+    from einops import rearrange
+    out["mask"] = []
+    for ci, (c, h, w, H, W, n) in enumerate([(1, 24, 32, 340, 512, 1024), (1, 33, 17, 64, 48, None),
+                                             (2, 16, 16, 16, 16, 100), (1, 50, 70, 37, 45, 500)]):
+        g = torch.Generator().manual_seed(200 + ci)
+        pred = torch.rand(1, c, h, w, generator=g)
+        idx = None if n is None else torch.randint(0, H * W, (n,), generator=g)
+        up = torch.nn.functional.interpolate(pred, size=(H, W), mode='bilinear', align_corners=False)
+        rows = rearrange(up, '1 n h w -> (h w) n')
+        ref = rows if idx is None else rows[idx]
+        assert_equal("mask_sample", oracle.mask_sample(pred, (H, W), idx), ref)
+        out["mask"].append({"pred": pred, "hw": (H, W), "idx": idx, "ref": ref.clone()})
+    torch.save(out, os.path.join(GOLD, "loss.pt"))
+    print("  CRNeRFLoss + mask lookup: pinned (5 + 4 cases)")
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.parse_args()
+    ap.add_argument("--only", choices=["loss"], help="regenerate a single fixture")
+    opt = ap.parse_args()
     if not os.path.isdir(REF):
         raise SystemExit(f"reference not found at {REF}; golden vectors can only be made in the "
                          "build container")
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
-    rendering, nerf, lst = import_reference()
     print("pinning oracle against", REF)
+    if opt.only == "loss":
+        case_loss()
+        return
+    rendering, nerf, lst = import_reference()
     case_posenc_mlp(nerf, lst)
     case_sample_pdf(rendering)
     case_style(nerf, lst)
+    case_loss()
     # config[0]-shaped (coarse only), eval and train mode, fine pass, peaky weights
     case_render(rendering, nerf, lst, "render_c64_eval", 64, 64, 0, train=False)
     case_render(rendering, nerf, lst, "render_64p128_eval", 96, 64, 128, train=False)

@@ -103,3 +103,17 @@ def test_product_synthetic_rays_equal_the_oracle_generator():
         a = synthetic.pinhole_rays(h, w, synthetic.synthetic_pose(1), 0.25, 4.5)
         b = oracle.pinhole_rays(h, w, oracle.synthetic_pose(1), 0.25, 4.5)
         assert torch.equal(a, b)
+
+
+def test_loss_and_mask_lookup_match_reference():
+    """CRNeRFLoss (losses.py:50-89) and the mask lookup (train_mask_grid_sample.py:172-175)."""
+    import types
+    g = load_golden("loss")
+    for case in g["cases"]:
+        hp = types.SimpleNamespace(**case["hp"])
+        got, w = oracle.crnerf_loss(case["inputs"], case["targets"], hp, case["step"], coef=1)
+        assert list(got) == list(case["ref"]) and w == case["weight"]
+        for k, v in case["ref"].items():
+            assert torch.equal(got[k], v), k
+    for case in g["mask"]:
+        assert torch.equal(oracle.mask_sample(case["pred"], case["hw"], case["idx"]), case["ref"])
