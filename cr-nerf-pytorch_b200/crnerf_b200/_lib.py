@@ -36,6 +36,11 @@ class StyleWeights(C.Structure):
                 ("rgb_w", C.c_void_p), ("rgb_b", C.c_void_p)]
 
 
+class EncoderWeights(C.Structure):
+    """crnerf_encoder_weights"""
+    _fields_ = [("weight", C.c_void_p * 7), ("bias", C.c_void_p * 7)]
+
+
 # name -> (restype, argtypes); must list every symbol include/crnerf_b200.h declares
 SIGNATURES = {
     "crnerf_last_error": (C.c_char_p, []),
@@ -62,6 +67,11 @@ SIGNATURES = {
     "crnerf_generate_rays": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int,
                                        C.c_int, C.c_void_p, C.c_void_p]),
     "crnerf_rgb_to_u8": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "crnerf_encoder_packed_bytes": (C.c_size_t, []),
+    "crnerf_encoder_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "crnerf_encoder_pack": (C.c_int, [C.POINTER(EncoderWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "crnerf_encoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_size_t, C.c_void_p]),
     "crnerf_ray_loss_forward": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_float, C.c_float, C.c_float,
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "crnerf_ray_loss_backward": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_float, C.c_float, C.c_float] +

@@ -589,3 +589,59 @@ def rgb_to_u8(rgb: torch.Tensor) -> torch.Tensor:
         if n:
             check(lib.crnerf_rgb_to_u8(flat.data_ptr(), n, out.data_ptr(), _stream(dev)))
     return out.reshape(shape) if shape is not None else out
+
+
+# ---- style/content encoder (csrc/encoder.cu) ------------------------------------------------------
+class PackedEncoder:
+    """Device-side weight image of an ``encoder_sameoutputsize`` (crnerf_encoder_pack)."""
+
+    def __init__(self, buf: torch.Tensor):
+        self.buf = buf
+
+
+def pack_encoder(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]) -> PackedEncoder:
+    """weights / biases: conv1..conv7 of the module, as in its state_dict (reference
+    models/linearStyleTransfer.py:213-246)."""
+    lib = _lib.load()
+    shapes = [(3, 3, 1, 1), (64, 3, 3, 3), (64, 64, 3, 3), (128, 64, 3, 3), (128, 128, 3, 3), (128, 128, 3, 3),
+              (64, 128, 1, 1)]
+    if len(weights) != 7 or len(biases) != 7:
+        raise ValueError("expected conv1..conv7")
+    w = _lib.EncoderWeights()
+    keep = []
+    for i, (wt, bt) in enumerate(zip(weights, biases)):
+        _need(wt, f"conv{i + 1}.weight")
+        _need(bt, f"conv{i + 1}.bias")
+        if tuple(wt.shape) != shapes[i] or bt.numel() != shapes[i][0]:
+            raise ValueError(f"conv{i + 1}: weight {tuple(wt.shape)} / bias {tuple(bt.shape)}; expected {shapes[i]} "
+                             "(out_channel must be 64)")
+        wc, bc = _c(wt.detach()), _c(bt.detach())
+        keep += [wc, bc]
+        w.weight[i], w.bias[i] = wc.data_ptr(), bc.data_ptr()
+    dev = keep[0].device
+    n = int(lib.crnerf_encoder_packed_bytes())
+    buf = torch.empty(n, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.crnerf_encoder_pack(C.byref(w), buf.data_ptr(), n, _stream(dev)))
+    return PackedEncoder(buf)
+
+
+def encoder_forward(packed: PackedEncoder, img: torch.Tensor) -> torch.Tensor:
+    """img (1,3,H,W) -> (1,64,32,32): encoder_sameoutputsize.forward (reference
+    models/linearStyleTransfer.py:250-276), inference only."""
+    lib = _lib.load()
+    _need(img, "img", 4)
+    if img.shape[0] != 1 or img.shape[1] != 3:
+        raise ValueError(f"img must be (1,3,H,W), got {tuple(img.shape)}")
+    h, w = int(img.shape[2]), int(img.shape[3])
+    if h < 8 or w < 8 or h > 8192 or w > 8192:
+        raise ValueError(f"image {h}x{w} unsupported (8..8192 per side)")
+    x = _c(img)
+    dev = x.device
+    nbytes = int(lib.crnerf_encoder_scratch_bytes(h, w))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = torch.empty((1, 64, 32, 32), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.crnerf_encoder_forward(packed.buf.data_ptr(), x.data_ptr(), h, w, out.data_ptr(),
+                                         scratch.data_ptr(), nbytes, _stream(dev)))
+    return out

@@ -88,6 +88,12 @@ int composite_backward(const float* raw, const float* z, const float* noise, con
                        float* d_rgb_pre, float* d_sigma_pre, cudaStream_t st);
 int relu_bias_grad(float* g, const void* act, int64_t n_points, int width, float* gb, float* scratch,
                    cudaStream_t st);
+// implemented in encoder.cu
+size_t encoder_packed_bytes();
+size_t encoder_scratch_bytes(int H, int W);
+int encoder_pack(const crnerf_encoder_weights* w, void* packed, size_t packed_bytes, cudaStream_t st);
+int encoder_forward(const void* packed, const float* img, int H, int W, float* out, void* scratch,
+                    size_t scratch_bytes, cudaStream_t st);
 // implemented in loss.cu
 size_t loss_scratch_floats();
 int ray_loss_forward(const float* coarse, const float* fine, const float* target, const float* mask,
@@ -250,6 +256,22 @@ int crnerf_rgb_to_u8(const float* rgb, int64_t n_pixels, uint8_t* out, void* str
   int rc = device_check();
   if (rc) return rc;
   return rgb_to_u8(rgb, n_pixels, out, (cudaStream_t)stream);
+}
+
+size_t crnerf_encoder_packed_bytes(void) { return encoder_packed_bytes(); }
+size_t crnerf_encoder_scratch_bytes(int height, int width) {
+  return height >= 8 && width >= 8 ? encoder_scratch_bytes(height, width) : 0;
+}
+int crnerf_encoder_pack(const crnerf_encoder_weights* w, void* packed, size_t packed_bytes, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return encoder_pack(w, packed, packed_bytes, (cudaStream_t)stream);
+}
+int crnerf_encoder_forward(const void* packed, const float* img, int height, int width, float* out,
+                           void* scratch, size_t scratch_bytes, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return encoder_forward(packed, img, height, width, out, scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
 int crnerf_ray_loss_forward(const float* rgb_coarse, const float* rgb_fine, const float* targets,

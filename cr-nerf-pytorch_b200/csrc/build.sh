@@ -9,10 +9,10 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC)
 mkdir -p "$HERE/_obj"
 pids=()
-for f in api nerf_mlp sample crossray backward gram_tc loss; do
+for f in api nerf_mlp sample crossray backward gram_tc loss encoder; do
   "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" ${CRNERF_PTXAS_V:+-Xptxas -v} &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-"$NVCC" -shared -o "$OUT" "$HERE"/_obj/{api,nerf_mlp,sample,crossray,backward,gram_tc,loss}.o -lcudart
+"$NVCC" -shared -o "$OUT" "$HERE"/_obj/{api,nerf_mlp,sample,crossray,backward,gram_tc,loss,encoder}.o -lcudart
 echo "built $OUT"

@@ -9,9 +9,9 @@ instead of ~40 library launches.  The feature map is read in place whether it is
 contiguous NCHW or the transposed view of the renderer's (N,64) rows that the
 reference's callers build.
 
-``encoder_sameoutputsize`` (:208-276, the style/content encoder ``enc_a``) sits
-outside the render path ("next"); it is provided as a plain module
-with the reference's parameter names so checkpoints load and callers run.
+``encoder_sameoutputsize`` (:208-276, the style/content encoder ``enc_a``; SURVEY.md 8f
+"next" row 1) keeps the reference's parameter names; its inference forward runs
+csrc/encoder.cu, its training forward/backward stays on library ops.
 """
 import torch
 import torch.nn as nn
@@ -153,8 +153,12 @@ class style_net(nn.Module, _StyleParamsMixin):
 class encoder_sameoutputsize(nn.Module):
     """Style/content encoder ``enc_a`` / ``enc_cont`` (reference :208-276): six
     reflection-padded 3x3 convs with LeakyReLU(0.2), two 2x2 max-pools, adaptive
-    average pool to 32x32 and a 1x1 conv.  Outside the render path (it runs once
-    per reference photo); kept as library ops - see DESIGN.md "out of scope"."""
+    average pool to 32x32 and a 1x1 conv.
+
+    Inference (no autograd, CUDA input, ``out_channel == 64``) runs csrc/encoder.cu:
+    the 3x3 convolutions as tcgen05 implicit GEMMs with fp16 hi/lo split operands
+    (fp32-class accuracy).  Under autograd - the training step back-propagates through
+    ``enc_a`` / ``enc_cont`` - it runs as differentiable library ops."""
 
     def __init__(self, out_channel=64):
         super(encoder_sameoutputsize, self).__init__()
@@ -179,8 +183,25 @@ class encoder_sameoutputsize(nn.Module):
         self.adppool = nn.AdaptiveAvgPool2d(32)
         self.conv7 = nn.Conv2d(128, out_channel, 1, 1, 0)
         self.relu7 = nn.LeakyReLU(0.2, inplace=True)
+        self._packed = None
+        self._packed_key = None
+
+    def _convs(self):
+        return [self.conv1, self.conv2, self.conv3, self.conv4, self.conv5, self.conv6, self.conv7]
+
+    def packed(self):
+        """Weight image for the kernels, rebuilt when a parameter changes."""
+        ps = [p for c in self._convs() for p in (c.weight, c.bias)]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._packed is None or key != self._packed_key:
+            self._packed = ops.pack_encoder(ps[0::2], ps[1::2])
+            self._packed_key = key
+        return self._packed
 
     def forward(self, x):
+        if x.is_cuda and self.conv7.out_channels == 64 and not _wants_grad(self, x) and x.shape[0] == 1 \
+                and min(x.shape[2:]) >= 8:
+            return ops.encoder_forward(self.packed(), x)
         h = self.relu2(self.conv2(self.reflecPad1(self.conv1(x))))
         h = self.relu3(self.conv3(self.reflecPad3(h)))
         h, _ = self.maxPool(h)

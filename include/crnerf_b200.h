@@ -289,6 +289,25 @@ int crnerf_style_apply(const crnerf_style_weights* w, const float* content, int6
                        int64_t s_pix_stride, int64_t s_ch_stride, float* rgb, float* transmatrix,
                        float* scratch, void* stream);
 
+/* ---- style/content encoder ---------------------------------------
+ * encoder_sameoutputsize.forward (models/linearStyleTransfer.py:250-276), inference only:
+ * conv1..conv7 in the module's order; weight[i] / bias[i] are the fp32 tensors of
+ * conv{i+1} exactly as its state_dict holds them ((3,3,1,1), (64,3,3,3), (64,64,3,3),
+ * (128,64,3,3), (128,128,3,3), (128,128,3,3), (64,128,1,1)). */
+typedef struct {
+  const float* weight[7];
+  const float* bias[7];
+} crnerf_encoder_weights;
+size_t crnerf_encoder_packed_bytes(void);
+/* one-time re-layout (fp16 hi/lo tensor-core images of conv3..conv6 + an fp32 blob); packed must be
+ * 128-byte aligned */
+int crnerf_encoder_pack(const crnerf_encoder_weights* w, void* packed, size_t packed_bytes, void* stream);
+size_t crnerf_encoder_scratch_bytes(int height, int width);
+/* img (3, height, width) fp32 (= the (1,3,H,W) tensor enc_a receives, eval.py:278) ->
+ * out (64, 32, 32) fp32 (= (1,64,32,32)).  height, width in [8, 8192]; scratch 256-byte aligned. */
+int crnerf_encoder_forward(const void* packed, const float* img, int height, int width, float* out,
+                           void* scratch, size_t scratch_bytes, void* stream);
+
 /* debug (tests only): dump the post-activation values of `layer` (0..10) for every
  * point of later fused launches into dbg_buf (n_points x 256 floats); NULL disables. */
 int crnerf_debug_set(float* dbg_buf, int layer);

@@ -394,3 +394,26 @@ def mask_sample(pred: Tensor, hw, idx: Optional[Tensor]) -> Tensor:
     up = F.interpolate(pred, size=tuple(hw), mode="bilinear", align_corners=False)
     rows = up[0].permute(1, 2, 0).reshape(-1, pred.shape[1])
     return rows if idx is None else rows[idx]
+
+
+# --------------------------------------------------------------------------
+# f1  encoder_sameoutputsize.forward  (reference models/linearStyleTransfer.py:250-276)
+# --------------------------------------------------------------------------
+def encoder_forward(p: Params, x: Tensor) -> Tensor:
+    """x (1,3,H,W) -> (1,out,32,32); p holds conv1..conv7 .weight/.bias under the module's keys."""
+    def conv(name, t):
+        return F.conv2d(t, p[f"{name}.weight"], p[f"{name}.bias"])
+
+    def pad(t):
+        return F.pad(t, (1, 1, 1, 1), mode="reflect")
+
+    act = lambda t: F.leaky_relu(t, 0.2)
+    h = act(conv("conv2", pad(conv("conv1", x))))
+    h = act(conv("conv3", pad(h)))
+    h = F.max_pool2d(h, 2, 2)
+    h = act(conv("conv4", pad(h)))
+    h = act(conv("conv5", pad(h)))
+    h = F.max_pool2d(h, 2, 2)
+    h = act(conv("conv6", pad(h)))
+    h = F.adaptive_avg_pool2d(h, 32)
+    return act(conv("conv7", h))

@@ -288,9 +288,25 @@ def case_loss():
     print("  CRNeRFLoss + mask lookup: pinned (5 + 4 cases)")
 
 
+def case_encoder(lst):
+    """encoder_sameoutputsize (reference linearStyleTransfer.py:208-276), default init seed 11."""
+    torch.manual_seed(11)
+    enc = lst.encoder_sameoutputsize(out_channel=64).eval()
+    p = sd(enc)
+    out = {"kind": "encoder", "seed": 11, "checksum": checksums(enc), "cases": []}
+    for i, (h, w) in enumerate([(32, 32), (40, 52), (97, 131)]):
+        x = torch.rand(1, 3, h, w, generator=torch.Generator().manual_seed(300 + i))
+        with torch.no_grad():
+            ref = enc(x)
+            assert_equal(f"encoder:{h}x{w}", oracle.encoder_forward(p, x), ref)
+        out["cases"].append({"x": x, "ref": ref})
+    torch.save(out, os.path.join(GOLD, "encoder.pt"))
+    print("  encoder_sameoutputsize: pinned (3 sizes)")
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", choices=["loss"], help="regenerate a single fixture")
+    ap.add_argument("--only", choices=["loss", "encoder"], help="regenerate a single fixture")
     opt = ap.parse_args()
     if not os.path.isdir(REF):
         raise SystemExit(f"reference not found at {REF}; golden vectors can only be made in the "
@@ -302,6 +318,10 @@ def main():
         case_loss()
         return
     rendering, nerf, lst = import_reference()
+    if opt.only == "encoder":
+        case_encoder(lst)
+        return
+    case_encoder(lst)
     case_posenc_mlp(nerf, lst)
     case_sample_pdf(rendering)
     case_style(nerf, lst)

@@ -117,3 +117,17 @@ def test_loss_and_mask_lookup_match_reference():
             assert torch.equal(got[k], v), k
     for case in g["mask"]:
         assert torch.equal(oracle.mask_sample(case["pred"], case["hw"], case["idx"]), case["ref"])
+
+
+def test_encoder_matches_reference():
+    """encoder_sameoutputsize (linearStyleTransfer.py:208-276): oracle vs golden, and the mirror
+    module's seeded default init + library-op path (the one training uses)."""
+    from models.linearStyleTransfer import encoder_sameoutputsize
+    g = load_golden("encoder")
+    torch.manual_seed(g["seed"])
+    enc = encoder_sameoutputsize(out_channel=64).eval()
+    check_checksums(enc, g["checksum"])
+    for case in g["cases"]:
+        with torch.no_grad():
+            assert torch.equal(oracle.encoder_forward(state(enc), case["x"]), case["ref"])
+            assert torch.equal(enc(case["x"]), case["ref"])
