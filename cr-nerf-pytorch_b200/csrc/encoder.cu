@@ -15,15 +15,16 @@
 // Activation layout between layers ("planes"): [C/8][H+2][W+2][8] fp16, twice (hi, lo), with the
 // reflection halo materialised.  One 16-byte element holds 8 channels of one pixel, so
 //   * a run of pixels of one channel chunk is contiguous -> the producer warp stages a tile with
-//     plain cp.async.bulk copies (3 rows x 130 pixels x 8 chunks x {hi, lo});
+//     plain cp.async.bulk copies (130 pixels x 8 chunks x {hi, lo} per tap row);
 //   * in shared memory every pixel of a chunk is 16 B after its neighbour -> the SWIZZLE_NONE
 //     K-major descriptor (LBO = chunk stride, SBO = 128 B) reads ANY 128 consecutive pixels, and a
-//     3x3 tap is a shift of the descriptor start address by (dy*130 + dx) * 16 B
+//     3x3 tap is the row slot dy with the descriptor start address shifted by dx * 16 B
 //     (validated bit-exactly by tools/nosw_probe.cu).
 // A tile is 128 consecutive positions of the flattened padded grid, so rows of any width pack
 // tiles densely (W / (W+2) useful rows); halo positions compute garbage that is not stored.
-// The convolution kernels write fp32 NHWC; enc_prep_kernel (one HBM pass) applies the optional
-// 2x2 max-pool, the hi/lo split and the reflection halo for the next layer.
+// The producer stages one tap row per ring slot (the issuer reads one row at a time, so the other
+// slots are prefetch).  Layers followed by a max-pool write fp32 NHWC and enc_prep_kernel (one HBM
+// pass) pools, splits and adds the halo; the others write the next layer's planes directly.
 #include <cuda_fp16.h>
 #include <algorithm>
 #include "common.h"
@@ -36,6 +37,46 @@ constexpr float kSlope = 0.2f;
 
 __host__ __device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 __device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : v * kSlope; }
+
+
+// hi/lo split of 8 consecutive channels of one pixel -> two 16-byte plane elements
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& h, uint4& l) {
+  uint32_t hh[4], ll[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half h0 = __float2half_rn(v[2 * j]), h1 = __float2half_rn(v[2 * j + 1]);
+    const __half l0 = __float2half_rn(v[2 * j] - __half2float(h0));
+    const __half l1 = __float2half_rn(v[2 * j + 1] - __half2float(h1));
+    hh[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    ll[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+  }
+  h = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+  l = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+}
+
+// Padded positions that hold interior pixel (yp, xp) (padded coordinates, 1-based interior) of an
+// H x W layer: itself plus its reflection-halo copies (row 0 mirrors row 2, row H+1 mirrors H-1).
+struct HaloTargets {
+  int ys[3], xs[3], ny, nx;
+  __device__ __forceinline__ HaloTargets(int yp, int xp, int H, int W) {
+    ny = nx = 0;
+    ys[ny++] = yp;
+    if (yp == 2) ys[ny++] = 0;
+    if (yp == H - 1) ys[ny++] = H + 1;
+    xs[nx++] = xp;
+    if (xp == 2) xs[nx++] = 0;
+    if (xp == W - 1) xs[nx++] = W + 1;
+  }
+};
+__device__ __forceinline__ void store_plane_elem(__half* hi, __half* lo, int Hp, int Wp, int chunk,
+                                                 const HaloTargets& t, const uint4& h, const uint4& l) {
+  for (int a = 0; a < t.ny; ++a)
+    for (int b = 0; b < t.nx; ++b) {
+      const size_t o = (((size_t)chunk * Hp + t.ys[a]) * Wp + t.xs[b]) * 8;
+      *reinterpret_cast<uint4*>(hi + o) = h;
+      *reinterpret_cast<uint4*>(lo + o) = l;
+    }
+}
 
 // ---- packed weight image ----------------------------------------------------------------------
 // [conv3 | conv4 | conv5 | conv6] tensor-core chunks, then an fp32 blob.
@@ -103,9 +144,10 @@ __global__ void enc_pack_blob_kernel(const float* w1, const float* b1, const flo
   }
 }
 
-// ---- conv1 + pad + conv2 + LeakyReLU: img (3,H,W) -> F (H,W,64) fp32 ------------------------------
+// ---- conv1 + pad + conv2 + LeakyReLU: img (3,H,W) -> planes (64 ch, H, W) hi/lo with halo ------------
 __global__ void __launch_bounds__(128)
-enc_first_kernel(const float* __restrict__ img, int H, int W, const float* __restrict__ blob, float* __restrict__ out) {
+enc_first_kernel(const float* __restrict__ img, int H, int W, const float* __restrict__ blob,
+                 __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
   __shared__ __align__(16) float s_w2t[27 * 64];
   __shared__ float s_b2[64], s_w1[9], s_b1[3];
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) s_w2t[i] = blob[Blob::w2t + i];
@@ -128,7 +170,7 @@ enc_first_kernel(const float* __restrict__ img, int H, int W, const float* __res
       for (int c = 0; c < 3; ++c)
         in[c * 9 + ky * 3 + kx] = s_b1[c] + (s_w1[c * 3] * v0 + s_w1[c * 3 + 1] * v1 + s_w1[c * 3 + 2] * v2);
     }
-  float4* o4 = reinterpret_cast<float4*>(out + (size_t)p * 64);
+  const HaloTargets tg(y + 1, x + 1, H, W);
 #pragma unroll
   for (int c0 = 0; c0 < 64; c0 += 16) {
     float acc[16];
@@ -147,9 +189,14 @@ enc_first_kernel(const float* __restrict__ img, int H, int W, const float* __res
       }
     }
 #pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4)
-      o4[c0 / 4 + j4] = make_float4(lrelu(acc[j4 * 4]), lrelu(acc[j4 * 4 + 1]), lrelu(acc[j4 * 4 + 2]),
-                                    lrelu(acc[j4 * 4 + 3]));
+    for (int h8 = 0; h8 < 2; ++h8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = lrelu(acc[h8 * 8 + j]);
+      uint4 h, l;
+      split8(v, h, l);
+      store_plane_elem(out_hi, out_lo, H + 2, W + 2, c0 / 8 + h8, tg, h, l);
+    }
   }
 }
 
@@ -186,17 +233,10 @@ enc_prep_kernel(const float* __restrict__ f, int Wi, int C, int Ho, int Wo, __ha
       const float4 a0 = *reinterpret_cast<const float4*>(s), a1 = *reinterpret_cast<const float4*>(s + 4);
       v[0] = a0.x, v[1] = a0.y, v[2] = a0.z, v[3] = a0.w, v[4] = a1.x, v[5] = a1.y, v[6] = a1.z, v[7] = a1.w;
     }
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const __half h0 = __float2half_rn(v[2 * j]), h1 = __float2half_rn(v[2 * j + 1]);
-      const __half l0 = __float2half_rn(v[2 * j] - __half2float(h0));
-      const __half l1 = __float2half_rn(v[2 * j + 1] - __half2float(h1));
-      h[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-      l[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-    }
-    *reinterpret_cast<uint4*>(hi + (size_t)i * 8) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(lo + (size_t)i * 8) = make_uint4(l[0], l[1], l[2], l[3]);
+    uint4 h, l;
+    split8(v, h, l);
+    *reinterpret_cast<uint4*>(hi + (size_t)i * 8) = h;
+    *reinterpret_cast<uint4*>(lo + (size_t)i * 8) = l;
   }
 }
 
@@ -211,36 +251,44 @@ __device__ __forceinline__ uint64_t make_sdesc_k_nosw(uint32_t smem_addr, uint32
 }
 
 constexpr int kTilePix = 128;
-constexpr int kRun = kTilePix + 2;           // pixels staged per tap row
-constexpr int kChunkStride = 3 * kRun * 16;  // bytes between K-adjacent core matrices (LBO)
-constexpr int kABytes = 8 * kChunkStride;    // one of {hi, lo}: 8 channel chunks x 3 rows x 130 pixels
-constexpr int kRing = 3;
+constexpr int kRun = kTilePix + 2;         // pixels staged per tap row
+constexpr int kChunkStride = kRun * 16;    // bytes between K-adjacent core matrices (LBO)
+constexpr int kRowHalf = 8 * kChunkStride; // one tap row, one of {hi, lo}: 8 channel chunks x 130 pixels
+constexpr int kRowBytes = 2 * kRowHalf;    // hi then lo
+constexpr int kRingW = 3;                  // weight chunks in flight
 constexpr int kConvThreads = 256;
 
+// tap rows in flight: the issuer reads one at a time, so every further slot is prefetch
+template <int COUT>
+__host__ __device__ constexpr int ring_a() {
+  return COUT == 64 ? 5 : 3;
+}
 template <int COUT>
 constexpr int conv_smem_bytes() {
-  return kRing * 2 * COUT * 128 + 2 * kABytes + 256 + 1024;
+  return kRingW * 2 * COUT * 128 + ring_a<COUT>() * kRowBytes + 256 + 1024;
 }
 
-template <int CIN, int COUT>
+// kPlanes: write the next layer's input directly (hi/lo planes with the reflection halo, same
+// H x W) instead of fp32 NHWC rows (which enc_prep_kernel then pools and splits).
+template <int CIN, int COUT, bool kPlanes>
 __global__ void __launch_bounds__(kConvThreads, 1)
 enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
                    const uint8_t* __restrict__ wimg, const float* __restrict__ bias, float* __restrict__ out,
-                   int H, int W, int n_tiles) {
+                   __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H, int W, int n_tiles) {
   constexpr int kKB = CIN / 64;
+  constexpr int kRingA = ring_a<COUT>();
   constexpr uint32_t kChunk = 2 * COUT * 128;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_ring = smem;
-  uint8_t* s_a_hi = s_ring + kRing * kChunk;
-  uint8_t* s_a_lo = s_a_hi + kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_a_lo + kABytes);
-  uint64_t* a_full = bars;
-  uint64_t* a_empty = bars + 1;
-  uint64_t* w_full = bars + 2;            // [kRing]
-  uint64_t* w_empty = bars + 2 + kRing;   // [kRing]
-  uint64_t* d_full = bars + 2 + 2 * kRing;   // [2]
-  uint64_t* d_empty = d_full + 2;            // [2]
+  uint8_t* s_rows = s_ring + kRingW * kChunk;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rows + kRingA * kRowBytes);
+  uint64_t* a_full = bars;                     // [kRingA]
+  uint64_t* a_empty = a_full + kRingA;         // [kRingA]
+  uint64_t* w_full = a_empty + kRingA;         // [kRingW]
+  uint64_t* w_empty = w_full + kRingW;         // [kRingW]
+  uint64_t* d_full = w_empty + kRingW;         // [2]
+  uint64_t* d_empty = d_full + 2;              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
   __shared__ float s_bias[COUT];
 
@@ -249,9 +297,11 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   const long long plane_len = (long long)(H + 2) * Wp;
   if (threadIdx.x < COUT) s_bias[threadIdx.x] = bias[threadIdx.x];
   if (threadIdx.x == 0) {
-    mbar_init(a_full, 1);
-    mbar_init(a_empty, 1);
-    for (int s = 0; s < kRing; ++s) {
+    for (int s = 0; s < kRingA; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < kRingW; ++s) {
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
     }
@@ -268,30 +318,26 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    // ---- A producer: 3 runs of 130 pixels x 8 channel chunks x {hi, lo} per (tile, channel block)
+    // ---- A producer: one tap row (130 pixels x 8 channel chunks x {hi, lo}) per ring slot
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long q0 = (long long)Wp + 1 + (long long)kTilePix * tile;
-        long long start[3];
-        uint32_t len[3], total = 0;
-        for (int dy = 0; dy < 3; ++dy) {
-          start[dy] = q0 + (long long)(dy - 1) * Wp - 1;
-          const long long room = plane_len - start[dy];
-          len[dy] = (uint32_t)(room < kRun ? room : kRun);
-          total += len[dy];
-        }
-        for (int kb = 0; kb < kKB; ++kb, ++it) {
-          if (it > 0) mbar_wait(a_empty, (it - 1) & 1, 11);
-          mbar_arrive_expect_tx(a_full, total * 16 * 8 * 2);
-          for (int c = 0; c < 8; ++c)
-            for (int dy = 0; dy < 3; ++dy) {
-              const size_t src = ((size_t)(kb * 8 + c) * plane_len + start[dy]) * 8;  // in halfs
-              const uint32_t dst = (c * 3 + dy) * kRun * 16;
-              bulk_g2s(s_a_hi + dst, in_hi + src, len[dy] * 16, a_full);
-              bulk_g2s(s_a_lo + dst, in_lo + src, len[dy] * 16, a_full);
+        for (int kb = 0; kb < kKB; ++kb)
+          for (int dy = 0; dy < 3; ++dy, ++it) {
+            const long long start = q0 + (long long)(dy - 1) * Wp - 1;
+            const long long room = plane_len - start;
+            const uint32_t len = (uint32_t)(room < kRun ? room : kRun);
+            const uint32_t s = it % kRingA;
+            if (it >= kRingA) mbar_wait(&a_empty[s], (it / kRingA - 1) & 1, 11);
+            mbar_arrive_expect_tx(&a_full[s], len * 16 * 8 * 2);
+            uint8_t* dst = s_rows + s * kRowBytes;
+            for (int c = 0; c < 8; ++c) {
+              const size_t src = ((size_t)(kb * 8 + c) * plane_len + start) * 8;  // in halfs
+              bulk_g2s(dst + c * kChunkStride, in_hi + src, len * 16, &a_full[s]);
+              bulk_g2s(dst + kRowHalf + c * kChunkStride, in_lo + src, len * 16, &a_full[s]);
             }
-        }
+          }
       }
     }
   } else if (warp == 1) {
@@ -301,8 +347,8 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
         for (int c = 0; c < kKB * 9; ++c, ++it) {
-          const uint32_t s = it % kRing;
-          if (it >= kRing) mbar_wait(&w_empty[s], (it / kRing - 1) & 1, 12);
+          const uint32_t s = it % kRingW;
+          if (it >= kRingW) mbar_wait(&w_empty[s], (it / kRingW - 1) & 1, 12);
           mbar_arrive_expect_tx(&w_full[s], kChunk);
           bulk_g2s_hint(s_ring + s * kChunk, wimg + (size_t)c * kChunk, kChunk, &w_full[s], policy);
         }
@@ -316,20 +362,20 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       if (local >= 2) mbar_wait(&d_empty[buf], (local / 2 - 1) & 1, 13);
       const uint32_t d_tmem = tmem + buf * COUT;
       uint32_t acc = 0;
-      for (int kb = 0; kb < kKB; ++kb, ++a_it) {
-        mbar_wait(a_full, a_it & 1, 14);
+      for (int kb = 0; kb < kKB; ++kb) {
         for (int tap = 0; tap < 9; ++tap, ++w_it) {
-          const uint32_t s = w_it % kRing;
-          mbar_wait(&w_full[s], (w_it / kRing) & 1, 15);
+          const uint32_t sa = a_it % kRingA;
+          if (tap % 3 == 0) mbar_wait(&a_full[sa], (a_it / kRingA) & 1, 14);
+          const uint32_t s = w_it % kRingW;
+          mbar_wait(&w_full[s], (w_it / kRingW) & 1, 15);
           tc_fence_after_sync();
           if (elect_one()) {
-            const uint32_t shift = ((tap / 3) * kRun + (tap % 3)) * 16;
+            const uint32_t a_hi = smem_u32(s_rows + sa * kRowBytes) + (tap % 3) * 16, a_lo = a_hi + kRowHalf;
             const uint32_t b_hi = smem_u32(s_ring + s * kChunk), b_lo = b_hi + COUT * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint32_t a_off = (2 * j) * kChunkStride + shift;
-              const uint64_t ah = make_sdesc_k_nosw(smem_u32(s_a_hi) + a_off, kChunkStride, 128);
-              const uint64_t al = make_sdesc_k_nosw(smem_u32(s_a_lo) + a_off, kChunkStride, 128);
+              const uint64_t ah = make_sdesc_k_nosw(a_hi + (2 * j) * kChunkStride, kChunkStride, 128);
+              const uint64_t al = make_sdesc_k_nosw(a_lo + (2 * j) * kChunkStride, kChunkStride, 128);
               const uint64_t bh = make_sdesc_k_sw128(b_hi + j * 32, 1024);
               const uint64_t bl = make_sdesc_k_sw128(b_lo + j * 32, 1024);
               umma_ss(d_tmem, ah, bh, idesc, acc);
@@ -338,17 +384,16 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
               umma_ss(d_tmem, ah, bl, idesc, 1);
             }
             umma_commit(&w_empty[s]);
-            if (tap == 8) {
-              umma_commit(a_empty);
-              if (kb == kKB - 1) umma_commit(&d_full[buf]);
-            }
+            if (tap % 3 == 2) umma_commit(&a_empty[sa]);
+            if (tap == 8 && kb == kKB - 1) umma_commit(&d_full[buf]);
           }
           __syncwarp();
+          if (tap % 3 == 2) ++a_it;
         }
       }
     }
   } else if (warp >= 4) {
-    // ---- epilogue: + bias, LeakyReLU, fp32 NHWC rows
+    // ---- epilogue: + bias, LeakyReLU, store
     const int quarter = warp & 3;
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
@@ -359,18 +404,31 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       const int yp = (int)(q / Wp), xp = (int)(q - (long long)yp * Wp);
       const bool valid = xp >= 1 && xp <= W && yp <= H;
       float4* o4 = reinterpret_cast<float4*>(out + ((size_t)(yp - 1) * W + (xp - 1)) * COUT);
+      const HaloTargets tg(yp, xp, H, W);
 #pragma unroll 1
       for (int c0 = 0; c0 < COUT; c0 += 32) {
         uint32_t v[32];
         tmem_ld_x32(tmem + (static_cast<uint32_t>(quarter * 32) << 16) + buf * COUT + c0, v);
         tmem_ld_wait();
         if (valid) {
+          if constexpr (kPlanes) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            o4[(c0 + j) / 4] = make_float4(lrelu(__uint_as_float(v[j]) + s_bias[c0 + j]),
-                                           lrelu(__uint_as_float(v[j + 1]) + s_bias[c0 + j + 1]),
-                                           lrelu(__uint_as_float(v[j + 2]) + s_bias[c0 + j + 2]),
-                                           lrelu(__uint_as_float(v[j + 3]) + s_bias[c0 + j + 3]));
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = lrelu(__uint_as_float(v[g * 8 + j]) + s_bias[c0 + g * 8 + j]);
+              uint4 h, l;
+              split8(f, h, l);
+              store_plane_elem(out_hi, out_lo, H + 2, Wp, c0 / 8 + g, tg, h, l);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              o4[(c0 + j) / 4] = make_float4(lrelu(__uint_as_float(v[j]) + s_bias[c0 + j]),
+                                             lrelu(__uint_as_float(v[j + 1]) + s_bias[c0 + j + 1]),
+                                             lrelu(__uint_as_float(v[j + 2]) + s_bias[c0 + j + 2]),
+                                             lrelu(__uint_as_float(v[j + 3]) + s_bias[c0 + j + 3]));
+          }
         }
       }
       tc_fence_before_sync();
@@ -405,16 +463,17 @@ enc_tail_kernel(const float* __restrict__ f, int H4, int W4, const float* __rest
   }
 }
 
-template <int CIN, int COUT>
-int launch_conv(const __half* planes, long long plane_len, const uint8_t* wimg, const float* bias, float* out, int H,
-                int W, cudaStream_t st) {
+template <int CIN, int COUT, bool kPlanes>
+int launch_conv(const __half* planes, long long plane_len, const uint8_t* wimg, const float* bias, float* out,
+                __half* out_planes, int H, int W, cudaStream_t st) {
   const long long span = (long long)(H - 1) * (W + 2) + W;
   const int n_tiles = (int)((span + kTilePix - 1) / kTilePix);
   constexpr int smem = conv_smem_bytes<COUT>();
-  CRNERF_CUDA(cudaFuncSetAttribute(enc_conv_tc_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  auto kern = enc_conv_tc_kernel<CIN, COUT, kPlanes>;
+  CRNERF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = std::min(n_tiles, num_sms());
-  enc_conv_tc_kernel<CIN, COUT><<<grid, kConvThreads, smem, st>>>(planes, planes + (size_t)CIN * plane_len, wimg, bias,
-                                                                 out, H, W, n_tiles);
+  kern<<<grid, kConvThreads, smem, st>>>(planes, planes + (size_t)CIN * plane_len, wimg, bias, out, out_planes,
+                                         out_planes ? out_planes + (size_t)COUT * plane_len : nullptr, H, W, n_tiles);
   count_launch();
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;
@@ -434,11 +493,11 @@ int launch_prep(const float* f, int Wi, int C, int Ho, int Wo, bool pool, __half
 }
 
 size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
+// scratch = [F: fp32 NHWC, largest H*W*64][Pa: planes, largest of (64, H, W) / (128, H/2, W/2)][Pb: planes (128, H/2, W/2)]
 size_t f_bytes(int H, int W) { return align256((size_t)H * W * 64 * sizeof(float)); }
-size_t p_bytes(int H, int W) {
-  const size_t full = (size_t)2 * 64 * (H + 2) * (W + 2) * sizeof(__half);
-  const size_t half = (size_t)2 * 128 * (H / 2 + 2) * (W / 2 + 2) * sizeof(__half);
-  return align256(std::max(full, half));
+size_t pb_bytes(int H, int W) { return align256((size_t)2 * 128 * (H / 2 + 2) * (W / 2 + 2) * sizeof(__half)); }
+size_t pa_bytes(int H, int W) {
+  return std::max(align256((size_t)2 * 64 * (H + 2) * (W + 2) * sizeof(__half)), pb_bytes(H, W));
 }
 
 }  // namespace
@@ -450,7 +509,7 @@ size_t encoder_packed_bytes() {
   return blob + Blob::total * sizeof(float);
 }
 
-size_t encoder_scratch_bytes(int H, int W) { return f_bytes(H, W) + p_bytes(H, W); }
+size_t encoder_scratch_bytes(int H, int W) { return f_bytes(H, W) + pa_bytes(H, W) + pb_bytes(H, W); }
 
 int encoder_pack(const crnerf_encoder_weights* w, void* packed, size_t packed_bytes, cudaStream_t st) {
   CRNERF_REQUIRE(w && packed, "null argument");
@@ -483,22 +542,29 @@ int encoder_forward(const void* packed, const float* img, int H, int W, float* o
   const uint8_t* wimg = static_cast<const uint8_t*>(packed);
   const float* blob = reinterpret_cast<const float*>(wimg + blob_off);
   float* F = static_cast<float*>(scratch);
-  __half* P = reinterpret_cast<__half*>(static_cast<uint8_t*>(scratch) + f_bytes(H, W));
+  __half* Pa = reinterpret_cast<__half*>(static_cast<uint8_t*>(scratch) + f_bytes(H, W));
+  __half* Pb = reinterpret_cast<__half*>(static_cast<uint8_t*>(scratch) + f_bytes(H, W) + pa_bytes(H, W));
   const int H2 = H / 2, W2 = W / 2, H4 = H2 / 2, W4 = W2 / 2;
   auto plane = [](int h, int w) { return (long long)(h + 2) * (w + 2); };
   int rc;
 
-  enc_first_kernel<<<(unsigned)(((long long)H * W + 127) / 128), 128, 0, st>>>(img, H, W, blob, F);
+  enc_first_kernel<<<(unsigned)(((long long)H * W + 127) / 128), 128, 0, st>>>(img, H, W, blob, Pa,
+                                                                               Pa + (size_t)64 * plane(H, W));
   count_launch();
   CRNERF_CUDA(cudaGetLastError());
-  if ((rc = launch_prep(F, W, 64, H, W, false, P, st))) return rc;
-  if ((rc = launch_conv<64, 64>(P, plane(H, W), wimg + L[0].offset, blob + Blob::b3, F, H, W, st))) return rc;
-  if ((rc = launch_prep(F, W, 64, H2, W2, true, P, st))) return rc;
-  if ((rc = launch_conv<64, 128>(P, plane(H2, W2), wimg + L[1].offset, blob + Blob::b4, F, H2, W2, st))) return rc;
-  if ((rc = launch_prep(F, W2, 128, H2, W2, false, P, st))) return rc;
-  if ((rc = launch_conv<128, 128>(P, plane(H2, W2), wimg + L[2].offset, blob + Blob::b5, F, H2, W2, st))) return rc;
-  if ((rc = launch_prep(F, W2, 128, H4, W4, true, P, st))) return rc;
-  if ((rc = launch_conv<128, 128>(P, plane(H4, W4), wimg + L[3].offset, blob + Blob::b6, F, H4, W4, st))) return rc;
+  if ((rc = launch_conv<64, 64, false>(Pa, plane(H, W), wimg + L[0].offset, blob + Blob::b3, F, nullptr, H, W, st)))
+    return rc;
+  if ((rc = launch_prep(F, W, 64, H2, W2, true, Pa, st))) return rc;
+  if ((rc = launch_conv<64, 128, true>(Pa, plane(H2, W2), wimg + L[1].offset, blob + Blob::b4, nullptr, Pb, H2, W2,
+                                       st)))
+    return rc;
+  if ((rc = launch_conv<128, 128, false>(Pb, plane(H2, W2), wimg + L[2].offset, blob + Blob::b5, F, nullptr, H2, W2,
+                                         st)))
+    return rc;
+  if ((rc = launch_prep(F, W2, 128, H4, W4, true, Pa, st))) return rc;
+  if ((rc = launch_conv<128, 128, false>(Pa, plane(H4, W4), wimg + L[3].offset, blob + Blob::b6, F, nullptr, H4, W4,
+                                         st)))
+    return rc;
   enc_tail_kernel<<<1024, 128, 0, st>>>(F, H4, W4, blob, out);
   count_launch();
   CRNERF_CUDA(cudaGetLastError());
