@@ -20,11 +20,12 @@
 //     K-major descriptor (LBO = chunk stride, SBO = 128 B) reads ANY 128 consecutive pixels, and a
 //     3x3 tap is the row slot dy with the descriptor start address shifted by dx * 16 B
 //     (validated bit-exactly by tools/nosw_probe.cu).
-// A tile is 128 consecutive positions of the flattened padded grid, so rows of any width pack
-// tiles densely (W / (W+2) useful rows); halo positions compute garbage that is not stored.
-// The producer stages one tap row per ring slot (the issuer reads one row at a time, so the other
-// slots are prefetch).  Layers followed by a max-pool write fp32 NHWC and enc_prep_kernel (one HBM
-// pass) pools, splits and adds the halo; the others write the next layer's planes directly.
+// Columns past the row end compute garbage (whatever follows in the flattened plane) that is not stored.
+// The producer stages one input row per ring slot; a step computes two vertically adjacent
+// 128-pixel tiles that share every weight chunk and three of their four input rows.  The epilogue
+// applies bias, LeakyReLU and - for conv3 / conv5 - the 2x2 max-pool in registers, and writes the
+// next layer's planes (halo included) directly: no fp32 activation ever goes to HBM except
+// conv6's small output, which the tail kernel pools.
 #include <cuda_fp16.h>
 #include <algorithm>
 #include "common.h"
@@ -200,46 +201,6 @@ enc_first_kernel(const float* __restrict__ img, int H, int W, const float* __res
   }
 }
 
-// ---- F (Hi,Wi,C) fp32 -> [maxpool 2x2] -> planes [C/8][Ho+2][Wo+2][8] hi, lo with reflection halo ----
-template <bool kPool>
-__global__ void __launch_bounds__(256)
-enc_prep_kernel(const float* __restrict__ f, int Wi, int C, int Ho, int Wo, __half* __restrict__ hi,
-                __half* __restrict__ lo) {
-  const int Hp = Ho + 2, Wp = Wo + 2;
-  const long long plane = (long long)Hp * Wp, total = plane * (C / 8);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i / plane);
-    const long long q = i - c * plane;
-    const int yp = (int)(q / Wp), xp = (int)(q - (long long)yp * Wp);
-    const int y = reflect_idx(yp - 1, Ho), x = reflect_idx(xp - 1, Wo);
-    float v[8];
-    if constexpr (kPool) {
-      const float* s = f + ((size_t)(2 * y) * Wi + 2 * x) * C + c * 8;
-      const float4 a0 = *reinterpret_cast<const float4*>(s), a1 = *reinterpret_cast<const float4*>(s + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(s + C), b1 = *reinterpret_cast<const float4*>(s + C + 4);
-      const float* t = s + (size_t)Wi * C;
-      const float4 c0 = *reinterpret_cast<const float4*>(t), c1 = *reinterpret_cast<const float4*>(t + 4);
-      const float4 d0 = *reinterpret_cast<const float4*>(t + C), d1 = *reinterpret_cast<const float4*>(t + C + 4);
-      v[0] = fmaxf(fmaxf(a0.x, b0.x), fmaxf(c0.x, d0.x));
-      v[1] = fmaxf(fmaxf(a0.y, b0.y), fmaxf(c0.y, d0.y));
-      v[2] = fmaxf(fmaxf(a0.z, b0.z), fmaxf(c0.z, d0.z));
-      v[3] = fmaxf(fmaxf(a0.w, b0.w), fmaxf(c0.w, d0.w));
-      v[4] = fmaxf(fmaxf(a1.x, b1.x), fmaxf(c1.x, d1.x));
-      v[5] = fmaxf(fmaxf(a1.y, b1.y), fmaxf(c1.y, d1.y));
-      v[6] = fmaxf(fmaxf(a1.z, b1.z), fmaxf(c1.z, d1.z));
-      v[7] = fmaxf(fmaxf(a1.w, b1.w), fmaxf(c1.w, d1.w));
-    } else {
-      const float* s = f + ((size_t)y * Wi + x) * C + c * 8;
-      const float4 a0 = *reinterpret_cast<const float4*>(s), a1 = *reinterpret_cast<const float4*>(s + 4);
-      v[0] = a0.x, v[1] = a0.y, v[2] = a0.z, v[3] = a0.w, v[4] = a1.x, v[5] = a1.y, v[6] = a1.z, v[7] = a1.w;
-    }
-    uint4 h, l;
-    split8(v, h, l);
-    *reinterpret_cast<uint4*>(hi + (size_t)i * 8) = h;
-    *reinterpret_cast<uint4*>(lo + (size_t)i * 8) = l;
-  }
-}
-
 // ---- 3x3 convolution + bias + LeakyReLU on the tensor cores ----------------------------------------
 __device__ __forceinline__ uint64_t make_sdesc_k_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -253,33 +214,39 @@ __device__ __forceinline__ uint64_t make_sdesc_k_nosw(uint32_t smem_addr, uint32
 constexpr int kTilePix = 128;
 constexpr int kRun = kTilePix + 2;         // pixels staged per tap row
 constexpr int kChunkStride = kRun * 16;    // bytes between K-adjacent core matrices (LBO)
-constexpr int kRowHalf = 8 * kChunkStride; // one tap row, one of {hi, lo}: 8 channel chunks x 130 pixels
+constexpr int kRowHalf = 8 * kChunkStride; // one input row, one of {hi, lo}: 8 channel chunks x 130 pixels
 constexpr int kRowBytes = 2 * kRowHalf;    // hi then lo
 constexpr int kRingW = 3;                  // weight chunks in flight
 constexpr int kConvThreads = 256;
 
-// tap rows in flight: the issuer reads one at a time, so every further slot is prefetch
+// input rows in flight: a tap row pair (dy, dy+1) is live, every further slot is prefetch
 template <int COUT>
 __host__ __device__ constexpr int ring_a() {
-  return COUT == 64 ? 5 : 3;
+  return COUT == 64 ? 5 : 4;
 }
 template <int COUT>
 constexpr int conv_smem_bytes() {
-  return kRingW * 2 * COUT * 128 + ring_a<COUT>() * kRowBytes + 256 + 1024;
+  return kRingW * 2 * COUT * 128 + ring_a<COUT>() * kRowBytes + 256 + COUT * 4;  // rings, barriers, bias
 }
 
-// kPlanes: write the next layer's input directly (hi/lo planes with the reflection halo, same
-// H x W) instead of fp32 NHWC rows (which enc_prep_kernel then pools and splits).
-template <int CIN, int COUT, bool kPlanes>
+enum ConvOut { kOutRows = 0, kOutPlanes = 1, kOutPoolPlanes = 2 };
+
+// One step = a "band tile": output rows 2b and 2b+1, columns [128 ct, 128 ct + 128) -> two
+// accumulators that share every weight chunk (half the L2 weight traffic per pixel) and three of
+// their four input rows.  kOut selects the epilogue:
+//   kOutRows        fp32 NHWC rows (H, W, COUT)                          (conv6 -> tail kernel)
+//   kOutPlanes      the next layer's hi/lo planes with reflection halo    (conv4 -> conv5)
+//   kOutPoolPlanes  2x2 max-pool in registers (vertical: the two accumulators, horizontal: the
+//                   neighbour lane), then planes of the pooled layer       (conv3, conv5)
+template <int CIN, int COUT, int kOut>
 __global__ void __launch_bounds__(kConvThreads, 1)
 enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
                    const uint8_t* __restrict__ wimg, const float* __restrict__ bias, float* __restrict__ out,
-                   __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H, int W, int n_tiles) {
+                   __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H, int W, int n_col, int n_tiles) {
   constexpr int kKB = CIN / 64;
   constexpr int kRingA = ring_a<COUT>();
   constexpr uint32_t kChunk = 2 * COUT * 128;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_ring = smem;
   uint8_t* s_rows = s_ring + kRingW * kChunk;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_rows + kRingA * kRowBytes);
@@ -290,7 +257,7 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   uint64_t* d_full = w_empty + kRingW;         // [2]
   uint64_t* d_empty = d_full + 2;              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
-  __shared__ float s_bias[COUT];
+  float* s_bias = reinterpret_cast<float*>(s_rows + kRingA * kRowBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Wp = W + 2;
@@ -311,31 +278,34 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<2 * COUT>(tmem_slot);
+  if (warp == 2) tmem_alloc<4 * COUT>(tmem_slot);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    // ---- A producer: one tap row (130 pixels x 8 channel chunks x {hi, lo}) per ring slot
+    // ---- A producer: input rows 2b-1 .. 2b+2 (padded 2b .. 2b+3), one per ring slot
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long q0 = (long long)Wp + 1 + (long long)kTilePix * tile;
+        const int band = tile / n_col, ct = tile - band * n_col;
+        const long long q0 = (long long)(2 * band + 1) * Wp + 1 + (long long)kTilePix * ct;
         for (int kb = 0; kb < kKB; ++kb)
-          for (int dy = 0; dy < 3; ++dy, ++it) {
-            const long long start = q0 + (long long)(dy - 1) * Wp - 1;
+          for (int r = 0; r < 4; ++r, ++it) {
+            const long long start = q0 + (long long)(r - 1) * Wp - 1;
             const long long room = plane_len - start;
-            const uint32_t len = (uint32_t)(room < kRun ? room : kRun);
+            const uint32_t len = room <= 0 ? 0u : (uint32_t)(room < kRun ? room : kRun);
             const uint32_t s = it % kRingA;
             if (it >= kRingA) mbar_wait(&a_empty[s], (it / kRingA - 1) & 1, 11);
             mbar_arrive_expect_tx(&a_full[s], len * 16 * 8 * 2);
-            uint8_t* dst = s_rows + s * kRowBytes;
-            for (int c = 0; c < 8; ++c) {
-              const size_t src = ((size_t)(kb * 8 + c) * plane_len + start) * 8;  // in halfs
-              bulk_g2s(dst + c * kChunkStride, in_hi + src, len * 16, &a_full[s]);
-              bulk_g2s(dst + kRowHalf + c * kChunkStride, in_lo + src, len * 16, &a_full[s]);
+            if (len) {
+              uint8_t* dst = s_rows + s * kRowBytes;
+              for (int c = 0; c < 8; ++c) {
+                const size_t src = ((size_t)(kb * 8 + c) * plane_len + start) * 8;  // in halfs
+                bulk_g2s(dst + c * kChunkStride, in_hi + src, len * 16, &a_full[s]);
+                bulk_g2s(dst + kRowHalf + c * kChunkStride, in_lo + src, len * 16, &a_full[s]);
+              }
             }
           }
       }
@@ -356,78 +326,125 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   } else if (warp == 2) {
     // ---- MMA issuer
     constexpr uint32_t idesc = make_idesc_f16(128, COUT, 0);
-    uint32_t a_it = 0, w_it = 0, local = 0;
+    uint32_t a_it = 0, w_it = 0, local = 0;  // a_it: sequence number of input row 0 of the current (tile, kb)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
       const uint32_t buf = local & 1;
       if (local >= 2) mbar_wait(&d_empty[buf], (local / 2 - 1) & 1, 13);
-      const uint32_t d_tmem = tmem + buf * COUT;
+      const uint32_t d0 = tmem + buf * 2 * COUT, d1 = d0 + COUT;
       uint32_t acc = 0;
-      for (int kb = 0; kb < kKB; ++kb) {
+      for (int kb = 0; kb < kKB; ++kb, a_it += 4) {
         for (int tap = 0; tap < 9; ++tap, ++w_it) {
-          const uint32_t sa = a_it % kRingA;
-          if (tap % 3 == 0) mbar_wait(&a_full[sa], (a_it / kRingA) & 1, 14);
+          const int dy = tap / 3, dx = tap - dy * 3;
+          const uint32_t r0 = a_it + dy, r1 = r0 + 1;
+          if (dx == 0) {
+            if (dy == 0) mbar_wait(&a_full[r0 % kRingA], (r0 / kRingA) & 1, 14);
+            mbar_wait(&a_full[r1 % kRingA], (r1 / kRingA) & 1, 14);
+          }
           const uint32_t s = w_it % kRingW;
           mbar_wait(&w_full[s], (w_it / kRingW) & 1, 15);
           tc_fence_after_sync();
           if (elect_one()) {
-            const uint32_t a_hi = smem_u32(s_rows + sa * kRowBytes) + (tap % 3) * 16, a_lo = a_hi + kRowHalf;
+            const uint32_t a0_hi = smem_u32(s_rows + (r0 % kRingA) * kRowBytes) + dx * 16;
+            const uint32_t a1_hi = smem_u32(s_rows + (r1 % kRingA) * kRowBytes) + dx * 16;
             const uint32_t b_hi = smem_u32(s_ring + s * kChunk), b_lo = b_hi + COUT * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint64_t ah = make_sdesc_k_nosw(a_hi + (2 * j) * kChunkStride, kChunkStride, 128);
-              const uint64_t al = make_sdesc_k_nosw(a_lo + (2 * j) * kChunkStride, kChunkStride, 128);
               const uint64_t bh = make_sdesc_k_sw128(b_hi + j * 32, 1024);
               const uint64_t bl = make_sdesc_k_sw128(b_lo + j * 32, 1024);
-              umma_ss(d_tmem, ah, bh, idesc, acc);
+              const uint64_t a0h = make_sdesc_k_nosw(a0_hi + (2 * j) * kChunkStride, kChunkStride, 128);
+              const uint64_t a0l = make_sdesc_k_nosw(a0_hi + kRowHalf + (2 * j) * kChunkStride, kChunkStride, 128);
+              const uint64_t a1h = make_sdesc_k_nosw(a1_hi + (2 * j) * kChunkStride, kChunkStride, 128);
+              const uint64_t a1l = make_sdesc_k_nosw(a1_hi + kRowHalf + (2 * j) * kChunkStride, kChunkStride, 128);
+              umma_ss(d0, a0h, bh, idesc, acc);
+              umma_ss(d1, a1h, bh, idesc, acc);
               acc = 1;
-              umma_ss(d_tmem, al, bh, idesc, 1);
-              umma_ss(d_tmem, ah, bl, idesc, 1);
+              umma_ss(d0, a0l, bh, idesc, 1);
+              umma_ss(d1, a1l, bh, idesc, 1);
+              umma_ss(d0, a0h, bl, idesc, 1);
+              umma_ss(d1, a1h, bl, idesc, 1);
             }
             umma_commit(&w_empty[s]);
-            if (tap % 3 == 2) umma_commit(&a_empty[sa]);
+            if (dx == 2) {
+              umma_commit(&a_empty[r0 % kRingA]);                 // row dy is done after tap row dy
+              if (dy == 2) umma_commit(&a_empty[r1 % kRingA]);    // and row 3 with it
+            }
             if (tap == 8 && kb == kKB - 1) umma_commit(&d_full[buf]);
           }
           __syncwarp();
-          if (tap % 3 == 2) ++a_it;
         }
       }
     }
   } else if (warp >= 4) {
-    // ---- epilogue: + bias, LeakyReLU, store
+    // ---- epilogue: + bias, LeakyReLU, (pool,) store
     const int quarter = warp & 3;
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
       const uint32_t buf = local & 1;
       mbar_wait(&d_full[buf], (local / 2) & 1, 16);
       tc_fence_after_sync();
-      const long long q = (long long)Wp + 1 + (long long)kTilePix * tile + quarter * 32 + lane;
-      const int yp = (int)(q / Wp), xp = (int)(q - (long long)yp * Wp);
-      const bool valid = xp >= 1 && xp <= W && yp <= H;
-      float4* o4 = reinterpret_cast<float4*>(out + ((size_t)(yp - 1) * W + (xp - 1)) * COUT);
-      const HaloTargets tg(yp, xp, H, W);
+      const int band = tile / n_col, ct = tile - band * n_col;
+      const int x = kTilePix * ct + quarter * 32 + lane;   // interior column
+      const int y = 2 * band;                              // interior row of accumulator 0
+      const uint32_t t0 = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 2 * COUT;
+      if constexpr (kOut == kOutPoolPlanes) {
+        const int Ho = H / 2, Wo = W / 2, xo = x >> 1;
+        const bool valid = band < Ho && xo < Wo && (lane & 1) == 0;
+        const HaloTargets tg(band + 1, xo + 1, Ho, Wo);
 #pragma unroll 1
-      for (int c0 = 0; c0 < COUT; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(tmem + (static_cast<uint32_t>(quarter * 32) << 16) + buf * COUT + c0, v);
-        tmem_ld_wait();
-        if (valid) {
-          if constexpr (kPlanes) {
+        for (int c0 = 0; c0 < COUT; c0 += 32) {
+          uint32_t v[32], u[32];
+          tmem_ld_x32(t0 + c0, v);
+          tmem_ld_x32(t0 + COUT + c0, u);
+          tmem_ld_wait();
+          float m[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float a = fmaxf(__uint_as_float(v[j]), __uint_as_float(u[j]));
+            m[j] = lrelu(fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1)) + s_bias[c0 + j]);
+          }
+          if (valid) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float f[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = lrelu(__uint_as_float(v[g * 8 + j]) + s_bias[c0 + g * 8 + j]);
+              for (int j = 0; j < 8; ++j) f[j] = m[g * 8 + j];
               uint4 h, l;
               split8(f, h, l);
-              store_plane_elem(out_hi, out_lo, H + 2, Wp, c0 / 8 + g, tg, h, l);
+              store_plane_elem(out_hi, out_lo, Ho + 2, Wo + 2, c0 / 8 + g, tg, h, l);
             }
-          } else {
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int r = 0; r < 2; ++r) {
+          const bool valid = x < W && y + r < H;
+          const HaloTargets tg(y + r + 1, x + 1, H, W);
+          float4* o4 = reinterpret_cast<float4*>(out + ((size_t)(y + r) * W + x) * COUT);
+#pragma unroll 1
+          for (int c0 = 0; c0 < COUT; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_x32(t0 + r * COUT + c0, v);
+            tmem_ld_wait();
+            if (valid) {
+              if constexpr (kOut == kOutPlanes) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              o4[(c0 + j) / 4] = make_float4(lrelu(__uint_as_float(v[j]) + s_bias[c0 + j]),
-                                             lrelu(__uint_as_float(v[j + 1]) + s_bias[c0 + j + 1]),
-                                             lrelu(__uint_as_float(v[j + 2]) + s_bias[c0 + j + 2]),
-                                             lrelu(__uint_as_float(v[j + 3]) + s_bias[c0 + j + 3]));
+                for (int g = 0; g < 4; ++g) {
+                  float f[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = lrelu(__uint_as_float(v[g * 8 + j]) + s_bias[c0 + g * 8 + j]);
+                  uint4 h, l;
+                  split8(f, h, l);
+                  store_plane_elem(out_hi, out_lo, H + 2, Wp, c0 / 8 + g, tg, h, l);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  o4[(c0 + j) / 4] = make_float4(lrelu(__uint_as_float(v[j]) + s_bias[c0 + j]),
+                                                 lrelu(__uint_as_float(v[j + 1]) + s_bias[c0 + j + 1]),
+                                                 lrelu(__uint_as_float(v[j + 2]) + s_bias[c0 + j + 2]),
+                                                 lrelu(__uint_as_float(v[j + 3]) + s_bias[c0 + j + 3]));
+              }
+            }
           }
         }
       }
@@ -438,7 +455,7 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<2 * COUT>(tmem);
+  if (warp == 2) tmem_dealloc<4 * COUT>(tmem);
 }
 
 // ---- adaptive avg-pool to 32x32 + conv7 1x1 128->64 + LeakyReLU: F (H4,W4,128) -> out (64,32,32) ----
@@ -463,42 +480,32 @@ enc_tail_kernel(const float* __restrict__ f, int H4, int W4, const float* __rest
   }
 }
 
-template <int CIN, int COUT, bool kPlanes>
-int launch_conv(const __half* planes, long long plane_len, const uint8_t* wimg, const float* bias, float* out,
-                __half* out_planes, int H, int W, cudaStream_t st) {
-  const long long span = (long long)(H - 1) * (W + 2) + W;
-  const int n_tiles = (int)((span + kTilePix - 1) / kTilePix);
+template <int CIN, int COUT, int kOut>
+int launch_conv(const __half* planes, const uint8_t* wimg, const float* bias, float* out, __half* out_planes,
+                long long out_plane_len, int H, int W, cudaStream_t st) {
+  const long long plane_len = (long long)(H + 2) * (W + 2);
+  const int n_col = (W + kTilePix - 1) / kTilePix;
+  const int n_tiles = ((H + 1) / 2) * n_col;
   constexpr int smem = conv_smem_bytes<COUT>();
-  auto kern = enc_conv_tc_kernel<CIN, COUT, kPlanes>;
+  auto kern = enc_conv_tc_kernel<CIN, COUT, kOut>;
   CRNERF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = std::min(n_tiles, num_sms());
   kern<<<grid, kConvThreads, smem, st>>>(planes, planes + (size_t)CIN * plane_len, wimg, bias, out, out_planes,
-                                         out_planes ? out_planes + (size_t)COUT * plane_len : nullptr, H, W, n_tiles);
-  count_launch();
-  CRNERF_CUDA(cudaGetLastError());
-  return CRNERF_OK;
-}
-
-int launch_prep(const float* f, int Wi, int C, int Ho, int Wo, bool pool, __half* planes, cudaStream_t st) {
-  const long long plane_len = (long long)(Ho + 2) * (Wo + 2), total = plane_len * (C / 8);
-  const int grid = (int)std::min<long long>((total + 255) / 256, 16LL * num_sms());
-  __half* lo = planes + (size_t)C * plane_len;
-  if (pool)
-    enc_prep_kernel<true><<<grid, 256, 0, st>>>(f, Wi, C, Ho, Wo, planes, lo);
-  else
-    enc_prep_kernel<false><<<grid, 256, 0, st>>>(f, Wi, C, Ho, Wo, planes, lo);
+                                         out_planes ? out_planes + (size_t)COUT * out_plane_len : nullptr, H, W,
+                                         n_col, n_tiles);
   count_launch();
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;
 }
 
 size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
-// scratch = [F: fp32 NHWC, largest H*W*64][Pa: planes, largest of (64, H, W) / (128, H/2, W/2)][Pb: planes (128, H/2, W/2)]
-size_t f_bytes(int H, int W) { return align256((size_t)H * W * 64 * sizeof(float)); }
-size_t pb_bytes(int H, int W) { return align256((size_t)2 * 128 * (H / 2 + 2) * (W / 2 + 2) * sizeof(__half)); }
-size_t pa_bytes(int H, int W) {
-  return std::max(align256((size_t)2 * 64 * (H + 2) * (W + 2) * sizeof(__half)), pb_bytes(H, W));
-}
+// scratch = [F: conv6 output, fp32 NHWC (H/4, W/4, 128)][Pa: planes (64, H, W), later (128, H/4, W/4)]
+//           [Pb: planes (64, H/2, W/2), later (128, H/2, W/2) at +Pb2]
+size_t planes_bytes(int C, int h, int w) { return align256((size_t)2 * C * (h + 2) * (w + 2) * sizeof(__half)); }
+size_t f_bytes(int H, int W) { return align256((size_t)(H / 4) * (W / 4) * 128 * sizeof(float)); }
+size_t pa_bytes(int H, int W) { return std::max(planes_bytes(64, H, W), planes_bytes(128, H / 4, W / 4)); }
+size_t pb_bytes(int H, int W) { return planes_bytes(64, H / 2, W / 2); }
+size_t pc_bytes(int H, int W) { return planes_bytes(128, H / 2, W / 2); }
 
 }  // namespace
 
@@ -509,7 +516,9 @@ size_t encoder_packed_bytes() {
   return blob + Blob::total * sizeof(float);
 }
 
-size_t encoder_scratch_bytes(int H, int W) { return f_bytes(H, W) + pa_bytes(H, W) + pb_bytes(H, W); }
+size_t encoder_scratch_bytes(int H, int W) {
+  return f_bytes(H, W) + pa_bytes(H, W) + pb_bytes(H, W) + pc_bytes(H, W);
+}
 
 int encoder_pack(const crnerf_encoder_weights* w, void* packed, size_t packed_bytes, cudaStream_t st) {
   CRNERF_REQUIRE(w && packed, "null argument");
@@ -541,29 +550,34 @@ int encoder_forward(const void* packed, const float* img, int H, int W, float* o
   tc_layers(L, blob_off);
   const uint8_t* wimg = static_cast<const uint8_t*>(packed);
   const float* blob = reinterpret_cast<const float*>(wimg + blob_off);
-  float* F = static_cast<float*>(scratch);
-  __half* Pa = reinterpret_cast<__half*>(static_cast<uint8_t*>(scratch) + f_bytes(H, W));
-  __half* Pb = reinterpret_cast<__half*>(static_cast<uint8_t*>(scratch) + f_bytes(H, W) + pa_bytes(H, W));
+  uint8_t* base = static_cast<uint8_t*>(scratch);
+  float* F = reinterpret_cast<float*>(base);
+  __half* Pa = reinterpret_cast<__half*>(base + f_bytes(H, W));
+  __half* Pb = reinterpret_cast<__half*>(base + f_bytes(H, W) + pa_bytes(H, W));
+  __half* Pc = reinterpret_cast<__half*>(base + f_bytes(H, W) + pa_bytes(H, W) + pb_bytes(H, W));
   const int H2 = H / 2, W2 = W / 2, H4 = H2 / 2, W4 = W2 / 2;
   auto plane = [](int h, int w) { return (long long)(h + 2) * (w + 2); };
   int rc;
 
+  // conv1 . pad . conv2 -> Pa (64, H, W)
   enc_first_kernel<<<(unsigned)(((long long)H * W + 127) / 128), 128, 0, st>>>(img, H, W, blob, Pa,
                                                                                Pa + (size_t)64 * plane(H, W));
   count_launch();
   CRNERF_CUDA(cudaGetLastError());
-  if ((rc = launch_conv<64, 64, false>(Pa, plane(H, W), wimg + L[0].offset, blob + Blob::b3, F, nullptr, H, W, st)))
+  // conv3 + pool: Pa -> Pb (64, H/2, W/2)
+  if ((rc = launch_conv<64, 64, kOutPoolPlanes>(Pa, wimg + L[0].offset, blob + Blob::b3, nullptr, Pb, plane(H2, W2), H,
+                                                W, st)))
     return rc;
-  if ((rc = launch_prep(F, W, 64, H2, W2, true, Pa, st))) return rc;
-  if ((rc = launch_conv<64, 128, true>(Pa, plane(H2, W2), wimg + L[1].offset, blob + Blob::b4, nullptr, Pb, H2, W2,
-                                       st)))
+  // conv4: Pb -> Pc (128, H/2, W/2)
+  if ((rc = launch_conv<64, 128, kOutPlanes>(Pb, wimg + L[1].offset, blob + Blob::b4, nullptr, Pc, plane(H2, W2), H2,
+                                             W2, st)))
     return rc;
-  if ((rc = launch_conv<128, 128, false>(Pb, plane(H2, W2), wimg + L[2].offset, blob + Blob::b5, F, nullptr, H2, W2,
-                                         st)))
+  // conv5 + pool: Pc -> Pa (128, H/4, W/4)
+  if ((rc = launch_conv<128, 128, kOutPoolPlanes>(Pc, wimg + L[2].offset, blob + Blob::b5, nullptr, Pa, plane(H4, W4),
+                                                  H2, W2, st)))
     return rc;
-  if ((rc = launch_prep(F, W2, 128, H4, W4, true, Pa, st))) return rc;
-  if ((rc = launch_conv<128, 128, false>(Pa, plane(H4, W4), wimg + L[3].offset, blob + Blob::b6, F, nullptr, H4, W4,
-                                         st)))
+  // conv6: Pa -> F (H/4, W/4, 128) fp32
+  if ((rc = launch_conv<128, 128, kOutRows>(Pa, wimg + L[3].offset, blob + Blob::b6, F, nullptr, 0, H4, W4, st)))
     return rc;
   enc_tail_kernel<<<1024, 128, 0, st>>>(F, H4, W4, blob, out);
   count_launch();
