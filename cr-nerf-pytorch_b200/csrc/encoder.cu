@@ -459,25 +459,35 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 }
 
 // ---- adaptive avg-pool to 32x32 + conv7 1x1 128->64 + LeakyReLU: F (H4,W4,128) -> out (64,32,32) ----
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 enc_tail_kernel(const float* __restrict__ f, int H4, int W4, const float* __restrict__ blob, float* __restrict__ out) {
+  __shared__ float part[4][128];
   __shared__ float pooled[128];
   const int bi = blockIdx.x / 32, bj = blockIdx.x % 32;
   // torch adaptive pooling bins: [floor(i*in/out), ceil((i+1)*in/out))
   const int y0 = (bi * H4) / 32, y1 = ((bi + 1) * H4 + 31) / 32;
   const int x0 = (bj * W4) / 32, x1 = ((bj + 1) * W4 + 31) / 32;
+  const int c = threadIdx.x & 127, g = threadIdx.x >> 7;   // 4 pixel groups x 128 channels
+  const int bw = x1 - x0, n = (y1 - y0) * bw;
   float acc = 0.f;
-  for (int y = y0; y < y1; ++y)
-    for (int x = x0; x < x1; ++x) acc += f[((size_t)y * W4 + x) * 128 + threadIdx.x];
-  pooled[threadIdx.x] = acc / (float)((y1 - y0) * (x1 - x0));
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    const float* w = blob + Blob::w7 + threadIdx.x * 128;
-    float s = blob[Blob::b7 + threadIdx.x];
-#pragma unroll 8
-    for (int c = 0; c < 128; ++c) s = fmaf(pooled[c], w[c], s);
-    out[(size_t)threadIdx.x * 1024 + blockIdx.x] = lrelu(s);
+  for (int p = g; p < n; p += 4) {
+    const int y = y0 + p / bw, x = x0 + p % bw;
+    acc += f[((size_t)y * W4 + x) * 128 + c];
   }
+  part[g][c] = acc;
+  __syncthreads();
+  if (threadIdx.x < 128) pooled[c] = ((part[0][c] + part[1][c]) + (part[2][c] + part[3][c])) / (float)n;
+  __syncthreads();
+  // conv7: 64 outputs x 128 inputs; 8 threads per output, 16 inputs each
+  const int co = threadIdx.x >> 3, k0 = (threadIdx.x & 7) * 16;
+  const float* w = blob + Blob::w7 + co * 128 + k0;
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s = fmaf(pooled[k0 + k], w[k], s);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if ((threadIdx.x & 7) == 0) out[(size_t)co * 1024 + blockIdx.x] = lrelu(s + blob[Blob::b7 + co]);
 }
 
 template <int CIN, int COUT, int kOut>
@@ -579,7 +589,7 @@ int encoder_forward(const void* packed, const float* img, int H, int W, float* o
   // conv6: Pa -> F (H/4, W/4, 128) fp32
   if ((rc = launch_conv<128, 128, kOutRows>(Pa, wimg + L[3].offset, blob + Blob::b6, F, nullptr, 0, H4, W4, st)))
     return rc;
-  enc_tail_kernel<<<1024, 128, 0, st>>>(F, H4, W4, blob, out);
+  enc_tail_kernel<<<1024, 512, 0, st>>>(F, H4, W4, blob, out);
   count_launch();
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;
