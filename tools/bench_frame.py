@@ -78,6 +78,31 @@ def main():
     for _ in range(10): ops.generate_rays(h, w, Kc, pose, 0.0, 5.0, device=dev)
     e1.record(); sync()
     rg_ms = e0.elapsed_time(e1) / 10
+    # the whole eval loop of one image (reference eval.py:275-297): enc_a(photo) -> rays built on
+    # the GPU -> render -> cross-ray fusion + decode -> uint8 -> pinned host buffer
+    from models.linearStyleTransfer import encoder_sameoutputsize
+    torch.manual_seed(1)
+    enc_a = encoder_sameoutputsize(64).to(dev).eval()
+    photo = torch.rand(1, 3, h, w, device=dev)
+    host_u8 = torch.empty((h, w, 3), dtype=torch.uint8).pin_memory()
+
+    def eval_image():
+        with torch.no_grad():
+            a_emb = enc_a(photo)
+        img = render_frame_sharded(models, emb, None, a_emb, (h, w), a.ns, a.ni, chunk=a.chunk, scheme=a.scheme,
+                                   args=margs, camera=(Kc, pose, 0.0, 5.0))
+        host_u8.copy_(ops.rgb_to_u8(img), non_blocking=True)
+    eval_image(); sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); eval_image(); e1.record(); sync()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    eval_ms = float(t.item())
+    e0.record()
+    with torch.no_grad():
+        for _ in range(5): enc_a(photo)
+    e1.record(); sync()
+    enc_ms = e0.elapsed_time(e1) / 5
     if rank == 0:
         bytes_alg = feat.shape[0] * (3 * 256 + 12) + 8.6e6
         peak = 6555.5
@@ -90,6 +115,7 @@ def main():
                           "crossray_frac": bytes_alg / (cr_ms * 1e-3) / 1e9 / peak,
                           "raygen_ms": rg_ms, "raygen_gbs": n * 32 / (rg_ms * 1e-3) / 1e9,
                           "raygen_frac": n * 32 / (rg_ms * 1e-3) / 1e9 / peak,
+                          "eval_image_ms": eval_ms, "encoder_ms": enc_ms, "u8_checksum": int(host_u8.sum()),
                           "rgb_mean": float(rgb.mean())}), flush=True)
     if world > 1: dist.destroy_process_group()
 
