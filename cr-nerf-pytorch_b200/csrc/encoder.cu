@@ -231,9 +231,11 @@ constexpr int conv_smem_bytes() {
 
 enum ConvOut { kOutRows = 0, kOutPlanes = 1, kOutPoolPlanes = 2 };
 
-// One step = a "band tile": output rows 2b and 2b+1, columns [128 ct, 128 ct + 128) -> two
-// accumulators that share every weight chunk (half the L2 weight traffic per pixel) and three of
-// their four input rows.  kOut selects the epilogue:
+// One step = a "band tile": 128 consecutive positions of the flattened (band, padded column) grid,
+// for output rows 2b and 2b+1 -> two accumulators that share every weight chunk (half the L2 weight
+// traffic per pixel) and three of their four input rows.  Runs cross band ends, so layers of any
+// width fill the 128-row MMA densely (W / (W+2)); halo columns compute garbage that is not stored.
+// kOut selects the epilogue:
 //   kOutRows        fp32 NHWC rows (H, W, COUT)                          (conv6 -> tail kernel)
 //   kOutPlanes      the next layer's hi/lo planes with reflection halo    (conv4 -> conv5)
 //   kOutPoolPlanes  2x2 max-pool in registers (vertical: the two accumulators, horizontal: the
@@ -242,7 +244,7 @@ template <int CIN, int COUT, int kOut>
 __global__ void __launch_bounds__(kConvThreads, 1)
 enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
                    const uint8_t* __restrict__ wimg, const float* __restrict__ bias, float* __restrict__ out,
-                   __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H, int W, int n_col, int n_tiles) {
+                   __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H, int W, int Ws, int n_tiles) {
   constexpr int kKB = CIN / 64;
   constexpr int kRingA = ring_a<COUT>();
   constexpr uint32_t kChunk = 2 * COUT * 128;
@@ -285,26 +287,33 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    // ---- A producer: input rows 2b-1 .. 2b+2 (padded 2b .. 2b+3), one per ring slot
+    // ---- A producer: for a step's 130 flat entries, input rows 2b .. 2b+3 (padded) of every band b the
+    // run touches, one row index per ring slot (a run that crosses a band end is filled in pieces)
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int band = tile / n_col, ct = tile - band * n_col;
-        const long long q0 = (long long)(2 * band + 1) * Wp + 1 + (long long)kTilePix * ct;
+        const long long i_lo = (long long)kTilePix * tile;   // flat index of smem entry 0
+        const int b_lo = (int)(i_lo / Ws), b_hi = (int)((i_lo + kRun - 1) / Ws);
         for (int kb = 0; kb < kKB; ++kb)
           for (int r = 0; r < 4; ++r, ++it) {
-            const long long start = q0 + (long long)(r - 1) * Wp - 1;
-            const long long room = plane_len - start;
-            const uint32_t len = room <= 0 ? 0u : (uint32_t)(room < kRun ? room : kRun);
             const uint32_t s = it % kRingA;
             if (it >= kRingA) mbar_wait(&a_empty[s], (it / kRingA - 1) & 1, 11);
-            mbar_arrive_expect_tx(&a_full[s], len * 16 * 8 * 2);
-            if (len) {
-              uint8_t* dst = s_rows + s * kRowBytes;
+            uint32_t total = 0;
+            for (int b = b_lo; b <= b_hi; ++b) {
+              const long long lo = max(i_lo, (long long)b * Ws), hi = min(i_lo + kRun, (long long)b * Ws + Wp);
+              if (hi > lo && 2 * b + r <= H + 1) total += (uint32_t)(hi - lo);
+            }
+            mbar_arrive_expect_tx(&a_full[s], total * 16 * 8 * 2);
+            uint8_t* dst = s_rows + s * kRowBytes;
+            for (int b = b_lo; b <= b_hi; ++b) {
+              const long long lo = max(i_lo, (long long)b * Ws), hi = min(i_lo + kRun, (long long)b * Ws + Wp);
+              if (hi <= lo || 2 * b + r > H + 1) continue;
+              const uint32_t bytes = (uint32_t)(hi - lo) * 16, e = (uint32_t)(lo - i_lo) * 16;
+              const long long src_px = (long long)(2 * b + r) * Wp + (lo - (long long)b * Ws);
               for (int c = 0; c < 8; ++c) {
-                const size_t src = ((size_t)(kb * 8 + c) * plane_len + start) * 8;  // in halfs
-                bulk_g2s(dst + c * kChunkStride, in_hi + src, len * 16, &a_full[s]);
-                bulk_g2s(dst + kRowHalf + c * kChunkStride, in_lo + src, len * 16, &a_full[s]);
+                const size_t src = ((size_t)(kb * 8 + c) * plane_len + src_px) * 8;  // in halfs
+                bulk_g2s(dst + c * kChunkStride + e, in_hi + src, bytes, &a_full[s]);
+                bulk_g2s(dst + kRowHalf + c * kChunkStride + e, in_lo + src, bytes, &a_full[s]);
               }
             }
           }
@@ -382,13 +391,15 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       const uint32_t buf = local & 1;
       mbar_wait(&d_full[buf], (local / 2) & 1, 16);
       tc_fence_after_sync();
-      const int band = tile / n_col, ct = tile - band * n_col;
-      const int x = kTilePix * ct + quarter * 32 + lane;   // interior column
+      const long long fi = 1 + (long long)kTilePix * tile + quarter * 32 + lane;   // flat index = band * Ws + padded column
+      const int band = (int)(fi / Ws), xp = (int)(fi - (long long)band * Ws);
+      const int x = xp - 1;                                // interior column; even x <-> even lane (Ws is even)
       const int y = 2 * band;                              // interior row of accumulator 0
+      const bool in_row = xp >= 1 && xp <= W;
       const uint32_t t0 = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 2 * COUT;
       if constexpr (kOut == kOutPoolPlanes) {
         const int Ho = H / 2, Wo = W / 2, xo = x >> 1;
-        const bool valid = band < Ho && xo < Wo && (lane & 1) == 0;
+        const bool valid = in_row && band < Ho && xo < Wo && (x & 1) == 0;
         const HaloTargets tg(band + 1, xo + 1, Ho, Wo);
 #pragma unroll 1
         for (int c0 = 0; c0 < COUT; c0 += 32) {
@@ -417,7 +428,7 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       } else {
 #pragma unroll 1
         for (int r = 0; r < 2; ++r) {
-          const bool valid = x < W && y + r < H;
+          const bool valid = in_row && y + r < H;
           const HaloTargets tg(y + r + 1, x + 1, H, W);
           float4* o4 = reinterpret_cast<float4*>(out + ((size_t)(y + r) * W + x) * COUT);
 #pragma unroll 1
@@ -494,15 +505,17 @@ template <int CIN, int COUT, int kOut>
 int launch_conv(const __half* planes, const uint8_t* wimg, const float* bias, float* out, __half* out_planes,
                 long long out_plane_len, int H, int W, cudaStream_t st) {
   const long long plane_len = (long long)(H + 2) * (W + 2);
-  const int n_col = (W + kTilePix - 1) / kTilePix;
-  const int n_tiles = ((H + 1) / 2) * n_col;
+  // flat index space: band b (output rows 2b, 2b+1) x padded column, band stride Ws (even, so that
+  // 2x2 pool partners share a lane pair); tiles are runs of 128 consecutive indices starting at 1
+  const int Ws = (W + 3) & ~1;
+  const int n_tiles = (int)((((long long)(H + 1) / 2) * Ws - 1 + kTilePix - 1) / kTilePix);
   constexpr int smem = conv_smem_bytes<COUT>();
   auto kern = enc_conv_tc_kernel<CIN, COUT, kOut>;
   CRNERF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = std::min(n_tiles, num_sms());
   kern<<<grid, kConvThreads, smem, st>>>(planes, planes + (size_t)CIN * plane_len, wimg, bias, out, out_planes,
                                          out_planes ? out_planes + (size_t)COUT * out_plane_len : nullptr, H, W,
-                                         n_col, n_tiles);
+                                         Ws, n_tiles);
   count_launch();
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;
