@@ -67,3 +67,18 @@ def test_encoder_repacks_after_update_and_trains_on_library_path():
     out = enc(x)                      # autograd on: differentiable library ops
     out.mean().backward()
     assert ops.launch_count() == n0 and enc.conv3.weight.grad is not None
+
+
+def test_encoder_full_frame_and_strided_input():
+    """An 800x800 photo (the frame size of BASELINE configs[3]) against the CPU oracle, fed once as a
+    contiguous tensor and once as a channels-last view (the wrapper must not assume NCHW strides)."""
+    enc = _encoder(7)
+    x = torch.rand(1, 3, 800, 800, generator=torch.Generator().manual_seed(42))
+    with torch.no_grad():
+        want = oracle.encoder_forward(state(enc), x)
+        enc = enc.to(DEV)
+        got = enc(x.to(DEV))
+        got_cl = enc(x.to(DEV).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2))
+    assert torch.equal(got, got_cl)
+    err = (got.cpu() - want).abs().max()
+    assert torch.allclose(got.cpu(), want, rtol=1e-4, atol=1e-5), float(err)

@@ -112,3 +112,16 @@ def test_loss_rejects_cpu_tensors():
     from crnerf_b200.ops import CrnerfError
     with pytest.raises(CrnerfError):
         loss.ray_loss(torch.rand(8, 3), None, torch.rand(8, 3), None)
+
+
+def test_loss_accepts_strided_views():
+    """rgb maps reach the loss as rearranged views (train_mask_grid_sample.py:220): same values as contiguous."""
+    from crnerf_b200 import loss
+    g = torch.Generator().manual_seed(9)
+    dev = torch.device("cuda:0")
+    c3n, f3n, t = torch.rand(3, 500, generator=g).to(dev), torch.rand(3, 500, generator=g).to(dev), \
+        torch.rand(500, 3, generator=g).to(dev)
+    m = torch.rand(500, 2, generator=g).to(dev)[:, :1]
+    a = loss.ray_loss(c3n.t(), f3n.t(), t, m, 1.0, 0.02, 1e-3)
+    b = loss.ray_loss(c3n.t().contiguous(), f3n.t().contiguous(), t, m.contiguous(), 1.0, 0.02, 1e-3)
+    assert torch.equal(a, b)
