@@ -146,6 +146,11 @@ __global__ void enc_pack_blob_kernel(const float* w1, const float* b1, const flo
 }
 
 // ---- conv1 + pad + conv2 + LeakyReLU: img (3,H,W) -> planes (64 ch, H, W) hi/lo with halo ------------
+// fp32 on the CUDA cores.  The weights are broadcast from shared memory with LDS.128 (the kernel is
+// bound by that pipe: ncu shows 72 % LSU wavefront utilisation against 38 % FMA with one pixel per
+// thread), so a thread computes kFirstPix pixels per weight load; they are 32 apart in the row so
+// that every load and store of a warp stays contiguous.
+constexpr int kFirstPix = 2;
 __global__ void __launch_bounds__(128)
 enc_first_kernel(const float* __restrict__ img, int H, int W, const float* __restrict__ blob,
                  __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
@@ -156,47 +161,64 @@ enc_first_kernel(const float* __restrict__ img, int H, int W, const float* __res
   if (threadIdx.x < 9) s_w1[threadIdx.x] = blob[Blob::w1 + threadIdx.x];
   if (threadIdx.x < 3) s_b1[threadIdx.x] = blob[Blob::b1 + threadIdx.x];
   __syncthreads();
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= (long long)H * W) return;
-  const int y = (int)(p / W), x = (int)(p - (long long)y * W);
-  float in[27];
+  // a warp covers 32 * kFirstPix consecutive pixels of one row: pixel p of lane l is x0 + l + 32 p
+  const int seg_per_row = (W + 32 * kFirstPix - 1) / (32 * kFirstPix);
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (long long)H * seg_per_row) return;
+  const int y = (int)(wid / seg_per_row), xb = (int)(wid - (long long)y * seg_per_row) * 32 * kFirstPix + (threadIdx.x & 31);
+  float in[kFirstPix][27];
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
+  for (int p = 0; p < kFirstPix; ++p) {
+    const int x = min(xb + 32 * p, W - 1);   // lanes past the row end recompute the last pixel and do not store
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int sy = reflect_idx(y + ky - 1, H), sx = reflect_idx(x + kx - 1, W);
-      const size_t o = (size_t)sy * W + sx;
-      const float v0 = img[o], v1 = img[(size_t)H * W + o], v2 = img[(size_t)2 * H * W + o];
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        in[c * 9 + ky * 3 + kx] = s_b1[c] + (s_w1[c * 3] * v0 + s_w1[c * 3 + 1] * v1 + s_w1[c * 3 + 2] * v2);
-    }
-  const HaloTargets tg(y + 1, x + 1, H, W);
+      for (int kx = 0; kx < 3; ++kx) {
+        const int sy = reflect_idx(y + ky - 1, H), sx = reflect_idx(x + kx - 1, W);
+        const size_t o = (size_t)sy * W + sx;
+        const float v0 = img[o], v1 = img[(size_t)H * W + o], v2 = img[(size_t)2 * H * W + o];
 #pragma unroll
+        for (int c = 0; c < 3; ++c)
+          in[p][c * 9 + ky * 3 + kx] = s_b1[c] + (s_w1[c * 3] * v0 + s_w1[c * 3 + 1] * v1 + s_w1[c * 3 + 2] * v2);
+      }
+  }
+#pragma unroll 1
   for (int c0 = 0; c0 < 64; c0 += 16) {
-    float acc[16];
+    float acc[kFirstPix][16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = s_b2[c0 + j];
+    for (int p = 0; p < kFirstPix; ++p)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[p][j] = s_b2[c0 + j];
 #pragma unroll
     for (int k = 0; k < 27; ++k) {
       const float4* wr = reinterpret_cast<const float4*>(s_w2t + k * 64 + c0);
 #pragma unroll
       for (int j4 = 0; j4 < 4; ++j4) {
         const float4 w = wr[j4];
-        acc[j4 * 4 + 0] = fmaf(in[k], w.x, acc[j4 * 4 + 0]);
-        acc[j4 * 4 + 1] = fmaf(in[k], w.y, acc[j4 * 4 + 1]);
-        acc[j4 * 4 + 2] = fmaf(in[k], w.z, acc[j4 * 4 + 2]);
-        acc[j4 * 4 + 3] = fmaf(in[k], w.w, acc[j4 * 4 + 3]);
+#pragma unroll
+        for (int p = 0; p < kFirstPix; ++p) {
+          acc[p][j4 * 4 + 0] = fmaf(in[p][k], w.x, acc[p][j4 * 4 + 0]);
+          acc[p][j4 * 4 + 1] = fmaf(in[p][k], w.y, acc[p][j4 * 4 + 1]);
+          acc[p][j4 * 4 + 2] = fmaf(in[p][k], w.z, acc[p][j4 * 4 + 2]);
+          acc[p][j4 * 4 + 3] = fmaf(in[p][k], w.w, acc[p][j4 * 4 + 3]);
+        }
       }
     }
 #pragma unroll
-    for (int h8 = 0; h8 < 2; ++h8) {
-      float v[8];
+    for (int p = 0; p < kFirstPix; ++p) {
+      const int x = xb + 32 * p;
+      if (x < W) {
+        const HaloTargets tg(y + 1, x + 1, H, W);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = lrelu(acc[h8 * 8 + j]);
-      uint4 h, l;
-      split8(v, h, l);
-      store_plane_elem(out_hi, out_lo, H + 2, W + 2, c0 / 8 + h8, tg, h, l);
+        for (int h8 = 0; h8 < 2; ++h8) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = lrelu(acc[p][h8 * 8 + j]);
+          uint4 h, l;
+          split8(v, h, l);
+          store_plane_elem(out_hi, out_lo, H + 2, W + 2, c0 / 8 + h8, tg, h, l);
+        }
+      }
     }
   }
 }
@@ -583,7 +605,8 @@ int encoder_forward(const void* packed, const float* img, int H, int W, float* o
   int rc;
 
   // conv1 . pad . conv2 -> Pa (64, H, W)
-  enc_first_kernel<<<(unsigned)(((long long)H * W + 127) / 128), 128, 0, st>>>(img, H, W, blob, Pa,
+  enc_first_kernel<<<(unsigned)(((long long)H * ((W + 32 * kFirstPix - 1) / (32 * kFirstPix)) * 32 + 127) / 128), 128, 0,
+                     st>>>(img, H, W, blob, Pa,
                                                                                Pa + (size_t)64 * plane(H, W));
   count_launch();
   CRNERF_CUDA(cudaGetLastError());
