@@ -375,24 +375,21 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
           mbar_wait(&w_full[s], (w_it / kRingW) & 1, 15);
           tc_fence_after_sync();
           if (elect_one()) {
-            const uint32_t a0_hi = smem_u32(s_rows + (r0 % kRingA) * kRowBytes) + dx * 16;
-            const uint32_t a1_hi = smem_u32(s_rows + (r1 % kRingA) * kRowBytes) + dx * 16;
-            const uint32_t b_hi = smem_u32(s_ring + s * kChunk), b_lo = b_hi + COUT * 128;
+            // descriptors differ only in the 14-bit address field: build one per operand and add offsets
+            const uint64_t a0h = make_sdesc_k_nosw(smem_u32(s_rows + (r0 % kRingA) * kRowBytes) + dx * 16, kChunkStride, 128);
+            const uint64_t a1h = make_sdesc_k_nosw(smem_u32(s_rows + (r1 % kRingA) * kRowBytes) + dx * 16, kChunkStride, 128);
+            const uint64_t bh = make_sdesc_k_sw128(smem_u32(s_ring + s * kChunk), 1024);
+            constexpr uint64_t kLo = kRowHalf >> 4, kBLo = (COUT * 128) >> 4;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint64_t bh = make_sdesc_k_sw128(b_hi + j * 32, 1024);
-              const uint64_t bl = make_sdesc_k_sw128(b_lo + j * 32, 1024);
-              const uint64_t a0h = make_sdesc_k_nosw(a0_hi + (2 * j) * kChunkStride, kChunkStride, 128);
-              const uint64_t a0l = make_sdesc_k_nosw(a0_hi + kRowHalf + (2 * j) * kChunkStride, kChunkStride, 128);
-              const uint64_t a1h = make_sdesc_k_nosw(a1_hi + (2 * j) * kChunkStride, kChunkStride, 128);
-              const uint64_t a1l = make_sdesc_k_nosw(a1_hi + kRowHalf + (2 * j) * kChunkStride, kChunkStride, 128);
-              umma_ss(d0, a0h, bh, idesc, acc);
-              umma_ss(d1, a1h, bh, idesc, acc);
+              const uint64_t ja = (uint64_t)((2 * j * kChunkStride) >> 4), jb = (uint64_t)((j * 32) >> 4);
+              umma_ss(d0, a0h + ja, bh + jb, idesc, acc);
+              umma_ss(d1, a1h + ja, bh + jb, idesc, acc);
               acc = 1;
-              umma_ss(d0, a0l, bh, idesc, 1);
-              umma_ss(d1, a1l, bh, idesc, 1);
-              umma_ss(d0, a0h, bl, idesc, 1);
-              umma_ss(d1, a1h, bl, idesc, 1);
+              umma_ss(d0, a0h + kLo + ja, bh + jb, idesc, 1);
+              umma_ss(d1, a1h + kLo + ja, bh + jb, idesc, 1);
+              umma_ss(d0, a0h + ja, bh + kBLo + jb, idesc, 1);
+              umma_ss(d1, a1h + ja, bh + kBLo + jb, idesc, 1);
             }
             umma_commit(&w_empty[s]);
             if (dx == 2) {
