@@ -270,6 +270,12 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   constexpr int kKB = CIN / 64;
   constexpr int kRingA = ring_a<COUT>();
   constexpr uint32_t kChunk = 2 * COUT * 128;
+  // COUT == 64: the hi and lo weight images of a chunk are adjacent, i.e. one 128-row operand, so
+  // hi*[hi; lo] is ONE N = 128 MMA whose two column halves the epilogue adds (an N = 64 MMA is bound
+  // by its shared-memory operand reads, 6 KB per 32 tensor cycles); lo*hi stays an N = 64 MMA.
+  constexpr bool kStack = COUT == 64;
+  constexpr uint32_t kDCols = kStack ? 128 : COUT;   // TMEM columns per accumulator
+  static_assert(!kStack || kOut == kOutPoolPlanes, "the stacked form is wired for the pooled epilogue only");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_ring = smem;
   uint8_t* s_rows = s_ring + kRingW * kChunk;
@@ -302,7 +308,7 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<4 * COUT>(tmem_slot);
+  if (warp == 2) tmem_alloc<4 * kDCols>(tmem_slot);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -361,7 +367,7 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
       const uint32_t buf = local & 1;
       if (local >= 2) mbar_wait(&d_empty[buf], (local / 2 - 1) & 1, 13);
-      const uint32_t d0 = tmem + buf * 2 * COUT, d1 = d0 + COUT;
+      const uint32_t d0 = tmem + buf * 2 * kDCols, d1 = d0 + kDCols;
       uint32_t acc = 0;
       for (int kb = 0; kb < kKB; ++kb, a_it += 4) {
         for (int tap = 0; tap < 9; ++tap, ++w_it) {
@@ -383,13 +389,22 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint64_t ja = (uint64_t)((2 * j * kChunkStride) >> 4), jb = (uint64_t)((j * 32) >> 4);
-              umma_ss(d0, a0h + ja, bh + jb, idesc, acc);
-              umma_ss(d1, a1h + ja, bh + jb, idesc, acc);
-              acc = 1;
-              umma_ss(d0, a0h + kLo + ja, bh + jb, idesc, 1);
-              umma_ss(d1, a1h + kLo + ja, bh + jb, idesc, 1);
-              umma_ss(d0, a0h + ja, bh + kBLo + jb, idesc, 1);
-              umma_ss(d1, a1h + ja, bh + kBLo + jb, idesc, 1);
+              if constexpr (kStack) {
+                constexpr uint32_t idesc2 = make_idesc_f16(128, 128, 0);
+                umma_ss(d0, a0h + ja, bh + jb, idesc2, acc);          // hi * [hi; lo]
+                umma_ss(d1, a1h + ja, bh + jb, idesc2, acc);
+                acc = 1;
+                umma_ss(d0, a0h + kLo + ja, bh + jb, idesc, 1);       // lo * hi
+                umma_ss(d1, a1h + kLo + ja, bh + jb, idesc, 1);
+              } else {
+                umma_ss(d0, a0h + ja, bh + jb, idesc, acc);
+                umma_ss(d1, a1h + ja, bh + jb, idesc, acc);
+                acc = 1;
+                umma_ss(d0, a0h + kLo + ja, bh + jb, idesc, 1);
+                umma_ss(d1, a1h + kLo + ja, bh + jb, idesc, 1);
+                umma_ss(d0, a0h + ja, bh + kBLo + jb, idesc, 1);
+                umma_ss(d1, a1h + ja, bh + kBLo + jb, idesc, 1);
+              }
             }
             umma_commit(&w_empty[s]);
             if (dx == 2) {
@@ -415,7 +430,7 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       const int x = xp - 1;                                // interior column; even x <-> even lane (Ws is even)
       const int y = 2 * band;                              // interior row of accumulator 0
       const bool in_row = xp >= 1 && xp <= W;
-      const uint32_t t0 = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 2 * COUT;
+      const uint32_t t0 = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 2 * kDCols;
       if constexpr (kOut == kOutPoolPlanes) {
         const int Ho = H / 2, Wo = W / 2, xo = x >> 1;
         const bool valid = in_row && band < Ho && xo < Wo && (x & 1) == 0;
@@ -424,8 +439,19 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
         for (int c0 = 0; c0 < COUT; c0 += 32) {
           uint32_t v[32], u[32];
           tmem_ld_x32(t0 + c0, v);
-          tmem_ld_x32(t0 + COUT + c0, u);
+          tmem_ld_x32(t0 + kDCols + c0, u);
           tmem_ld_wait();
+          if constexpr (kStack) {   // add the hi*lo column half
+            uint32_t v2[32], u2[32];
+            tmem_ld_x32(t0 + 64 + c0, v2);
+            tmem_ld_x32(t0 + kDCols + 64 + c0, u2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+              u[j] = __float_as_uint(__uint_as_float(u[j]) + __uint_as_float(u2[j]));
+            }
+          }
           float m[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -453,7 +479,7 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 #pragma unroll 1
           for (int c0 = 0; c0 < COUT; c0 += 32) {
             uint32_t v[32];
-            tmem_ld_x32(t0 + r * COUT + c0, v);
+            tmem_ld_x32(t0 + r * kDCols + c0, v);
             tmem_ld_wait();
             if (valid) {
               if constexpr (kOut == kOutPlanes) {
@@ -485,7 +511,7 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<4 * COUT>(tmem);
+  if (warp == 2) tmem_dealloc<4 * kDCols>(tmem);
 }
 
 // ---- adaptive avg-pool to 32x32 + conv7 1x1 128->64 + LeakyReLU: F (H4,W4,128) -> out (64,32,32) ----
