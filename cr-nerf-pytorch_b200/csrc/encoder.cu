@@ -239,7 +239,7 @@ constexpr int kChunkStride = kRun * 16;    // bytes between K-adjacent core matr
 constexpr int kRowHalf = 8 * kChunkStride; // one input row, one of {hi, lo}: 8 channel chunks x 130 pixels
 constexpr int kRowBytes = 2 * kRowHalf;    // hi then lo
 constexpr int kRingW = 3;                  // weight chunks in flight
-constexpr int kConvThreads = 256;
+constexpr int kConvThreads = 384;         // producers + issuer (warps 0-3), 8 epilogue warps (lane quarter x column half)
 
 // input rows in flight: a tap row pair (dy, dy+1) is live, every further slot is prefetch
 template <int COUT>
@@ -304,7 +304,7 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&d_full[b], 1);
-      mbar_init(&d_empty[b], 4);
+      mbar_init(&d_empty[b], 8);
     }
     fence_mbar_init();
   }
@@ -317,8 +317,12 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   if (warp == 0) {
     // ---- A producer: for a step's 130 flat entries, input rows 2b .. 2b+3 (padded) of every band b the
     // run touches, one row index per ring slot (a run that crosses a band end is filled in pieces)
-    if (lane == 0) {
+    // Lane l < 16 issues the copy of (channel chunk l & 7, hi / lo = l >> 3): a row slot is 16-32 small
+    // bulk copies, and one thread issuing them all was slower than the MMAs that consume them.
+    {
       uint32_t it = 0;
+      const int c = lane & 7;
+      const bool lo_half = (lane >> 3) & 1;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long i_lo = (long long)kTilePix * tile;   // flat index of smem entry 0
         const int b_lo = (int)(i_lo / Ws), b_hi = (int)((i_lo + kRun - 1) / Ws);
@@ -331,17 +335,17 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
               const long long lo = max(i_lo, (long long)b * Ws), hi = min(i_lo + kRun, (long long)b * Ws + Wp);
               if (hi > lo && 2 * b + r <= H + 1) total += (uint32_t)(hi - lo);
             }
-            mbar_arrive_expect_tx(&a_full[s], total * 16 * 8 * 2);
-            uint8_t* dst = s_rows + s * kRowBytes;
-            for (int b = b_lo; b <= b_hi; ++b) {
-              const long long lo = max(i_lo, (long long)b * Ws), hi = min(i_lo + kRun, (long long)b * Ws + Wp);
-              if (hi <= lo || 2 * b + r > H + 1) continue;
-              const uint32_t bytes = (uint32_t)(hi - lo) * 16, e = (uint32_t)(lo - i_lo) * 16;
-              const long long src_px = (long long)(2 * b + r) * Wp + (lo - (long long)b * Ws);
-              for (int c = 0; c < 8; ++c) {
-                const size_t src = ((size_t)(kb * 8 + c) * plane_len + src_px) * 8;  // in halfs
-                bulk_g2s(dst + c * kChunkStride + e, in_hi + src, bytes, &a_full[s]);
-                bulk_g2s(dst + kRowHalf + c * kChunkStride + e, in_lo + src, bytes, &a_full[s]);
+            if (lane == 0) mbar_arrive_expect_tx(&a_full[s], total * 16 * 8 * 2);
+            __syncwarp();
+            if (lane < 16) {
+              uint8_t* dst = s_rows + s * kRowBytes + (lo_half ? kRowHalf : 0) + c * kChunkStride;
+              const __half* srcp = lo_half ? in_lo : in_hi;
+              for (int b = b_lo; b <= b_hi; ++b) {
+                const long long lo = max(i_lo, (long long)b * Ws), hi = min(i_lo + kRun, (long long)b * Ws + Wp);
+                if (hi <= lo || 2 * b + r > H + 1) continue;
+                const uint32_t bytes = (uint32_t)(hi - lo) * 16, e = (uint32_t)(lo - i_lo) * 16;
+                const long long src_px = (long long)(2 * b + r) * Wp + (lo - (long long)b * Ws);
+                bulk_g2s(dst + e, srcp + ((size_t)(kb * 8 + c) * plane_len + src_px) * 8, bytes, &a_full[s]);
               }
             }
           }
@@ -386,26 +390,28 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
             const uint64_t a1h = make_sdesc_k_nosw(smem_u32(s_rows + (r1 % kRingA) * kRowBytes) + dx * 16, kChunkStride, 128);
             const uint64_t bh = make_sdesc_k_sw128(smem_u32(s_ring + s * kChunk), 1024);
             constexpr uint64_t kLo = kRowHalf >> 4, kBLo = (COUT * 128) >> 4;
+            // all MMAs of one accumulator back to back, then the other: alternating accumulators
+            // instruction by instruction costs ~110 cycles per MMA instead of 64 / 48
+            const uint32_t acc0 = acc;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint64_t ja = (uint64_t)((2 * j * kChunkStride) >> 4), jb = (uint64_t)((j * 32) >> 4);
-              if constexpr (kStack) {
-                constexpr uint32_t idesc2 = make_idesc_f16(128, 128, 0);
-                umma_ss(d0, a0h + ja, bh + jb, idesc2, acc);          // hi * [hi; lo]
-                umma_ss(d1, a1h + ja, bh + jb, idesc2, acc);
-                acc = 1;
-                umma_ss(d0, a0h + kLo + ja, bh + jb, idesc, 1);       // lo * hi
-                umma_ss(d1, a1h + kLo + ja, bh + jb, idesc, 1);
-              } else {
-                umma_ss(d0, a0h + ja, bh + jb, idesc, acc);
-                umma_ss(d1, a1h + ja, bh + jb, idesc, acc);
-                acc = 1;
-                umma_ss(d0, a0h + kLo + ja, bh + jb, idesc, 1);
-                umma_ss(d1, a1h + kLo + ja, bh + jb, idesc, 1);
-                umma_ss(d0, a0h + ja, bh + kBLo + jb, idesc, 1);
-                umma_ss(d1, a1h + ja, bh + kBLo + jb, idesc, 1);
+            for (int t = 0; t < 2; ++t) {
+              const uint32_t d = t ? d1 : d0;
+              const uint64_t ah = t ? a1h : a0h;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint64_t ja = (uint64_t)((2 * j * kChunkStride) >> 4), jb = (uint64_t)((j * 32) >> 4);
+                if constexpr (kStack) {
+                  constexpr uint32_t idesc2 = make_idesc_f16(128, 128, 0);
+                  umma_ss(d, ah + ja, bh + jb, idesc2, j ? 1u : acc0);   // hi * [hi; lo]
+                  umma_ss(d, ah + kLo + ja, bh + jb, idesc, 1);          // lo * hi
+                } else {
+                  umma_ss(d, ah + ja, bh + jb, idesc, j ? 1u : acc0);
+                  umma_ss(d, ah + kLo + ja, bh + jb, idesc, 1);
+                  umma_ss(d, ah + ja, bh + kBLo + jb, idesc, 1);
+                }
               }
             }
+            acc = 1;
             umma_commit(&w_empty[s]);
             if (dx == 2) {
               umma_commit(&a_empty[r0 % kRingA]);                 // row dy is done after tap row dy
@@ -418,8 +424,10 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       }
     }
   } else if (warp >= 4) {
-    // ---- epilogue: + bias, LeakyReLU, (pool,) store
-    const int quarter = warp & 3;
+    // ---- epilogue: + bias, LeakyReLU, (pool,) store.  Two warps per lane quarter, each taking every
+    // other 32-channel block: with Cout = 64 a step is only ~8 k tensor cycles and one warp per
+    // quarter (a single warp on its scheduler, nothing to hide latency) could not keep up.
+    const int quarter = warp & 3, chalf = (warp - 4) >> 2;
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
       const uint32_t buf = local & 1;
@@ -436,7 +444,7 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
         const bool valid = in_row && band < Ho && xo < Wo && (x & 1) == 0;
         const HaloTargets tg(band + 1, xo + 1, Ho, Wo);
 #pragma unroll 1
-        for (int c0 = 0; c0 < COUT; c0 += 32) {
+        for (int c0 = chalf * 32; c0 < COUT; c0 += 64) {
           uint32_t v[32], u[32];
           tmem_ld_x32(t0 + c0, v);
           tmem_ld_x32(t0 + kDCols + c0, u);
@@ -477,7 +485,7 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
           const HaloTargets tg(y + r + 1, x + 1, H, W);
           float4* o4 = reinterpret_cast<float4*>(out + ((size_t)(y + r) * W + x) * COUT);
 #pragma unroll 1
-          for (int c0 = 0; c0 < COUT; c0 += 32) {
+          for (int c0 = chalf * 32; c0 < COUT; c0 += 64) {
             uint32_t v[32];
             tmem_ld_x32(t0 + r * kDCols + c0, v);
             tmem_ld_wait();

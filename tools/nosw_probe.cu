@@ -6,7 +6,7 @@
 //
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -I cr-nerf-pytorch_b200/csrc
 //        tools/nosw_probe.cu -o tools/nosw_probe
-// run  : tools/nosw_probe <shift rows> <plane rows> <variant 0: LBO=plane stride, SBO=128  1: swapped>
+// run  : tools/nosw_probe <shift rows> <plane rows> <variant 0: LBO=plane stride, SBO=128  1: swapped> [reps: time SS MMAs]
 #include <cuda_fp16.h>
 #include <cstdio>
 #include <cstdlib>
@@ -37,7 +37,8 @@ __device__ __forceinline__ uint64_t make_sdesc_k_nosw(uint32_t smem_addr, uint32
 constexpr int K = 64, N = 128;
 
 __global__ void __launch_bounds__(160, 1)
-probe(const uint16_t* a_planes, int plane_rows, const uint8_t* b_img, int shift, int variant, float* d_out) {
+probe(const uint16_t* a_planes, int plane_rows, const uint8_t* b_img, int shift, int variant, float* d_out,
+      long long* cycles, int reps) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sB = smem;                      // N x 128 B, swizzled
   uint8_t* sA = smem + N * 128;            // [K/8][plane_rows][16 B]
@@ -73,11 +74,31 @@ probe(const uint16_t* a_planes, int plane_rows, const uint8_t* b_img, int shift,
         umma_ss(tmem, adesc, bdesc, idesc, ks > 0);
       }
       umma_commit(&bars[1]);
+      // issue-rate comparison (results discarded): N = 128 and N = 64, A no-swizzle planes vs A SWIZZLE_128B
+      if (reps > 0) {
+        mbar_wait(&bars[1], 0, 5);
+        uint32_t par = 1;
+        for (int mode = 0; mode < 4; ++mode) {
+          const uint32_t n = (mode & 1) ? 64 : 128;
+          const uint32_t id = make_idesc_f16(128, n, 0);
+          const long long t0 = clock64();
+          for (int r = 0; r < reps; ++r)
+            for (int ks = 0; ks < K / 16; ++ks) {
+              const uint64_t adesc = (mode & 2) ? make_sdesc_k_sw128(smem_u32(sA) + ks * 32, 1024)
+                                                : make_sdesc_k_nosw(smem_u32(sA) + (2 * ks) * plane, plane, 128);
+              umma_ss(tmem, adesc, make_sdesc_k_sw128(smem_u32(sB) + ks * 32, 1024), id, 1);
+            }
+          umma_commit(&bars[1]);
+          mbar_wait(&bars[1], par, 6);
+          par ^= 1;
+          cycles[mode] = clock64() - t0;
+        }
+      }
     }
     __syncwarp();
   }
   if (warp < 4) {
-    mbar_wait(&bars[1], 0, 2);
+    mbar_wait(&bars[1], 0, 2);   // (the timing rounds later overwrite D; d_out is read right here)
     tc_fence_after_sync();
     const int row = warp * 32 + lane;
     for (int c0 = 0; c0 < N; c0 += 32) {
@@ -131,7 +152,10 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(d_b, bimg.data(), bimg.size(), cudaMemcpyHostToDevice));
   const int smem = N * 128 + (K / 8) * plane_rows * 16 + 64;
   CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  probe<<<1, 160, smem>>>(d_planes, plane_rows, d_b, shift, variant, d_out);
+  const int reps = argc > 4 ? atoi(argv[4]) : 0;
+  long long* d_cyc;
+  CK(cudaMalloc(&d_cyc, 4 * sizeof(long long)));
+  probe<<<1, 160, smem>>>(d_planes, plane_rows, d_b, shift, variant, d_out, d_cyc, reps);
   CK(cudaDeviceSynchronize());
   std::vector<float> out(128 * N);
   CK(cudaMemcpy(out.data(), d_out, out.size() * 4, cudaMemcpyDeviceToHost));
@@ -142,7 +166,17 @@ int main(int argc, char** argv) {
       for (int k = 0; k < K; ++k) ref += A[(m + shift) * K + k] * B[n * K + k];
       if (ref != out[m * N + n]) ++bad;
     }
-  printf("nosw_probe shift=%d plane_rows=%d variant=%d: %s (%d / %d mismatches)\n", shift, plane_rows, variant,
-         bad ? "FAIL" : "ok", bad, 128 * N);
+  if (reps > 0) {
+    long long cyc[4];
+    CK(cudaMemcpy(cyc, d_cyc, sizeof(cyc), cudaMemcpyDeviceToHost));
+    const double n = 4.0 * reps;
+    printf("cycles per SS MMA (K16): A no-swizzle N128 %.1f  N64 %.1f | A SW128 N128 %.1f  N64 %.1f\n", cyc[0] / n,
+           cyc[1] / n, cyc[2] / n, cyc[3] / n);
+  }
+  if (reps > 0)
+    printf("nosw_probe: timing run (the timed MMAs overwrite the accumulator; run without reps to compare)\n");
+  else
+    printf("nosw_probe shift=%d plane_rows=%d variant=%d: %s (%d / %d mismatches)\n", shift, plane_rows, variant,
+           bad ? "FAIL" : "ok", bad, 128 * N);
   return 0;
 }
