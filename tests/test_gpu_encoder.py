@@ -82,3 +82,16 @@ def test_encoder_full_frame_and_strided_input():
     assert torch.equal(got, got_cl)
     err = (got.cpu() - want).abs().max()
     assert torch.allclose(got.cpu(), want, rtol=1e-4, atol=1e-5), float(err)
+
+
+def test_no_swizzle_descriptor_probe():
+    """tools/nosw_probe (built by __graft_entry__.build): the SWIZZLE_NONE K-major descriptor with a
+    row-shifted start address - what makes a 3x3 tap a pointer shift - is bit-exact on this GPU."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "nosw_probe")
+    if not os.path.exists(exe):
+        pytest.skip("tools/nosw_probe not built")
+    for shift, rows in ((0, 130), (1, 130), (2, 130), (131, 390), (262, 390)):
+        out = subprocess.run([exe, str(shift), str(rows), "0"], capture_output=True, text=True, timeout=60).stdout
+        assert ": ok (0 /" in out, out
