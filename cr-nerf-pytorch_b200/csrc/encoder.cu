@@ -1,7 +1,8 @@
 // encoder_sameoutputsize.forward (reference models/linearStyleTransfer.py:208-276; SURVEY.md 8f
 // rank 1): the style/content encoder enc_a / enc_cont, inference only.
 //
-//   conv1 1x1 3->3 . reflect-pad . conv2 3x3 3->64 . LeakyReLU           enc_first_kernel (fp32 CUDA cores, 0.9 % of the MACs)
+//   conv1 1x1 3->3 . reflect-pad                                         enc_conv1_planes_kernel (fp32)
+//   conv2 3x3 3->64 . LeakyReLU                                          enc_conv_tc_kernel<8, 64> (two taps per K = 16 step)
 //   [pad . conv3 64->64 . LReLU . maxpool2] [pad . conv4 64->128 . LReLU]
 //   [pad . conv5 128->128 . LReLU . maxpool2] [pad . conv6 128->128 . LReLU]   enc_conv_tc_kernel (tcgen05 implicit GEMM)
 //   adaptive-avg-pool 32x32 . conv7 1x1 128->64 . LeakyReLU               enc_tail_kernel
@@ -145,81 +146,40 @@ __global__ void enc_pack_blob_kernel(const float* w1, const float* b1, const flo
   }
 }
 
-// ---- conv1 + pad + conv2 + LeakyReLU: img (3,H,W) -> planes (64 ch, H, W) hi/lo with halo ------------
-// fp32 on the CUDA cores.  The weights are broadcast from shared memory with LDS.128 (the kernel is
-// bound by that pipe: ncu shows 72 % LSU wavefront utilisation against 38 % FMA with one pixel per
-// thread), so a thread computes kFirstPix pixels per weight load; they are 32 apart in the row so
-// that every load and store of a warp stays contiguous.
-constexpr int kFirstPix = 2;
-__global__ void __launch_bounds__(128)
-enc_first_kernel(const float* __restrict__ img, int H, int W, const float* __restrict__ blob,
-                 __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
-  __shared__ __align__(16) float s_w2t[27 * 64];
-  __shared__ float s_b2[64], s_w1[9], s_b1[3];
-  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) s_w2t[i] = blob[Blob::w2t + i];
-  if (threadIdx.x < 64) s_b2[threadIdx.x] = blob[Blob::b2 + threadIdx.x];
-  if (threadIdx.x < 9) s_w1[threadIdx.x] = blob[Blob::w1 + threadIdx.x];
-  if (threadIdx.x < 3) s_b1[threadIdx.x] = blob[Blob::b1 + threadIdx.x];
-  __syncthreads();
-  // a warp covers 32 * kFirstPix consecutive pixels of one row: pixel p of lane l is x0 + l + 32 p
-  const int seg_per_row = (W + 32 * kFirstPix - 1) / (32 * kFirstPix);
-  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (wid >= (long long)H * seg_per_row) return;
-  const int y = (int)(wid / seg_per_row), xb = (int)(wid - (long long)y * seg_per_row) * 32 * kFirstPix + (threadIdx.x & 31);
-  float in[kFirstPix][27];
-#pragma unroll
-  for (int p = 0; p < kFirstPix; ++p) {
-    const int x = min(xb + 32 * p, W - 1);   // lanes past the row end recompute the last pixel and do not store
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int sy = reflect_idx(y + ky - 1, H), sx = reflect_idx(x + kx - 1, W);
-        const size_t o = (size_t)sy * W + sx;
-        const float v0 = img[o], v1 = img[(size_t)H * W + o], v2 = img[(size_t)2 * H * W + o];
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          in[p][c * 9 + ky * 3 + kx] = s_b1[c] + (s_w1[c * 3] * v0 + s_w1[c * 3 + 1] * v1 + s_w1[c * 3 + 2] * v2);
-      }
+// ---- conv1 (1x1, 3 -> 3) + reflection halo: img (3,H,W) -> planes (one 8-channel chunk: 3 real + 5 zero) -----
+__global__ void __launch_bounds__(256)
+enc_conv1_planes_kernel(const float* __restrict__ img, int H, int W, const float* __restrict__ blob,
+                        __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  const int Wp = W + 2;
+  const long long total = (long long)(H + 2) * Wp;
+  const float w0 = blob[Blob::w1], w1 = blob[Blob::w1 + 1], w2 = blob[Blob::w1 + 2], w3 = blob[Blob::w1 + 3],
+              w4 = blob[Blob::w1 + 4], w5 = blob[Blob::w1 + 5], w6 = blob[Blob::w1 + 6], w7 = blob[Blob::w1 + 7],
+              w8 = blob[Blob::w1 + 8], b0 = blob[Blob::b1], b1 = blob[Blob::b1 + 1], b2 = blob[Blob::b1 + 2];
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const int yp = (int)(q / Wp), xp = (int)(q - (long long)yp * Wp);
+    const size_t o = (size_t)reflect_idx(yp - 1, H) * W + reflect_idx(xp - 1, W);
+    const float v0 = img[o], v1 = img[(size_t)H * W + o], v2 = img[(size_t)2 * H * W + o];
+    const float v[8] = {b0 + (w0 * v0 + w1 * v1 + w2 * v2), b1 + (w3 * v0 + w4 * v1 + w5 * v2),
+                        b2 + (w6 * v0 + w7 * v1 + w8 * v2), 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint4 h, l;
+    split8(v, h, l);
+    *reinterpret_cast<uint4*>(out_hi + (size_t)q * 8) = h;
+    *reinterpret_cast<uint4*>(out_lo + (size_t)q * 8) = l;
   }
-#pragma unroll 1
-  for (int c0 = 0; c0 < 64; c0 += 16) {
-    float acc[kFirstPix][16];
-#pragma unroll
-    for (int p = 0; p < kFirstPix; ++p)
-#pragma unroll
-      for (int j = 0; j < 16; ++j) acc[p][j] = s_b2[c0 + j];
-#pragma unroll
-    for (int k = 0; k < 27; ++k) {
-      const float4* wr = reinterpret_cast<const float4*>(s_w2t + k * 64 + c0);
-#pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
-        const float4 w = wr[j4];
-#pragma unroll
-        for (int p = 0; p < kFirstPix; ++p) {
-          acc[p][j4 * 4 + 0] = fmaf(in[p][k], w.x, acc[p][j4 * 4 + 0]);
-          acc[p][j4 * 4 + 1] = fmaf(in[p][k], w.y, acc[p][j4 * 4 + 1]);
-          acc[p][j4 * 4 + 2] = fmaf(in[p][k], w.z, acc[p][j4 * 4 + 2]);
-          acc[p][j4 * 4 + 3] = fmaf(in[p][k], w.w, acc[p][j4 * 4 + 3]);
-        }
-      }
-    }
-#pragma unroll
-    for (int p = 0; p < kFirstPix; ++p) {
-      const int x = xb + 32 * p;
-      if (x < W) {
-        const HaloTargets tg(y + 1, x + 1, H, W);
-#pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = lrelu(acc[p][h8 * 8 + j]);
-          uint4 h, l;
-          split8(v, h, l);
-          store_plane_elem(out_hi, out_lo, H + 2, W + 2, c0 / 8 + h8, tg, h, l);
-        }
-      }
-    }
+}
+
+// conv2 weights (64,3,3,3) -> 3 chunks (one per tap row dy) of [hi: 64 rows x 128 B, SW128][lo: same];
+// K index = dx * 8 + channel for dx = 0..3 (dx = 3 and channels 3..7 are zero), the rest of the row unused
+__global__ void enc_pack_first_kernel(const float* __restrict__ w, uint8_t* __restrict__ img) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * 64 * 64; i += gridDim.x * blockDim.x) {
+    const int k = i % 64, co = (i / 64) % 64, dy = i / 4096;
+    const int dx = k >> 3, ch = k & 7;
+    const float v = (dx < 3 && ch < 3) ? w[((co * 3 + ch) * 3 + dy) * 3 + dx] : 0.f;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    uint8_t* base = img + (size_t)dy * (2 * 64 * 128) + sw128_offset(co, k >> 3) + (k & 7) * 2;
+    *reinterpret_cast<__half*>(base) = hi;
+    *reinterpret_cast<__half*>(base + 64 * 128) = lo;
   }
 }
 
@@ -267,7 +227,14 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
                    const uint8_t* __restrict__ wimg, const float* __restrict__ bias, float* __restrict__ out,
                    __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H, int W, int Ws, int n_tiles) {
-  constexpr int kKB = CIN / 64;
+  // CIN == 8: the first 3x3 convolution (conv2, 3 real channels padded to one 8-channel chunk).  A K = 16
+  // step then spans TWO horizontally adjacent taps: the descriptor's K-chunk stride (LBO) is 16 B, i.e.
+  // the next pixel, so a tap row is 2 steps (dx = 0,1 | 2, and a phantom dx = 3 whose weights are zero).
+  constexpr bool kFirst = CIN == 8;
+  constexpr int kKB = kFirst ? 1 : CIN / 64;
+  constexpr int kTaps = kFirst ? 3 : 9;          // weight chunks per channel block
+  constexpr int kChunks = kFirst ? 1 : 8;        // 8-channel chunks per input row
+  constexpr int kRunLoad = kFirst ? kRun + 1 : kRun;
   constexpr int kRingA = ring_a<COUT>();
   constexpr uint32_t kChunk = 2 * COUT * 128;
   // COUT == 64: the hi and lo weight images of a chunk are adjacent, i.e. one 128-row operand, so
@@ -275,7 +242,7 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   // by its shared-memory operand reads, 6 KB per 32 tensor cycles); lo*hi stays an N = 64 MMA.
   constexpr bool kStack = COUT == 64;
   constexpr uint32_t kDCols = kStack ? 128 : COUT;   // TMEM columns per accumulator
-  static_assert(!kStack || kOut == kOutPoolPlanes, "the stacked form is wired for the pooled epilogue only");
+  static_assert(!kStack || kOut != kOutRows, "the stacked form is not wired for the fp32-rows epilogue");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_ring = smem;
   uint8_t* s_rows = s_ring + kRingW * kChunk;
@@ -293,6 +260,12 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   const int Wp = W + 2;
   const long long plane_len = (long long)(H + 2) * Wp;
   if (threadIdx.x < COUT) s_bias[threadIdx.x] = bias[threadIdx.x];
+  if constexpr (kFirst) {
+    // the phantom tap multiplies whatever the row slot holds by zero weights: it must be finite
+    for (int i = threadIdx.x; i < kRingA * kRowBytes / 16; i += kConvThreads)
+      reinterpret_cast<uint4*>(s_rows)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRingA; ++s) {
       mbar_init(&a_full[s], 1);
@@ -321,27 +294,27 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
     // bulk copies, and one thread issuing them all was slower than the MMAs that consume them.
     {
       uint32_t it = 0;
-      const int c = lane & 7;
-      const bool lo_half = (lane >> 3) & 1;
+      const int c = lane % kChunks;
+      const bool lo_half = (lane / kChunks) & 1;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long i_lo = (long long)kTilePix * tile;   // flat index of smem entry 0
-        const int b_lo = (int)(i_lo / Ws), b_hi = (int)((i_lo + kRun - 1) / Ws);
+        const int b_lo = (int)(i_lo / Ws), b_hi = (int)((i_lo + kRunLoad - 1) / Ws);
         for (int kb = 0; kb < kKB; ++kb)
           for (int r = 0; r < 4; ++r, ++it) {
             const uint32_t s = it % kRingA;
             if (it >= kRingA) mbar_wait(&a_empty[s], (it / kRingA - 1) & 1, 11);
             uint32_t total = 0;
             for (int b = b_lo; b <= b_hi; ++b) {
-              const long long lo = max(i_lo, (long long)b * Ws), hi = min(i_lo + kRun, (long long)b * Ws + Wp);
+              const long long lo = max(i_lo, (long long)b * Ws), hi = min(i_lo + kRunLoad, (long long)b * Ws + Wp);
               if (hi > lo && 2 * b + r <= H + 1) total += (uint32_t)(hi - lo);
             }
-            if (lane == 0) mbar_arrive_expect_tx(&a_full[s], total * 16 * 8 * 2);
+            if (lane == 0) mbar_arrive_expect_tx(&a_full[s], total * 16 * kChunks * 2);
             __syncwarp();
-            if (lane < 16) {
+            if (lane < 2 * kChunks) {
               uint8_t* dst = s_rows + s * kRowBytes + (lo_half ? kRowHalf : 0) + c * kChunkStride;
               const __half* srcp = lo_half ? in_lo : in_hi;
               for (int b = b_lo; b <= b_hi; ++b) {
-                const long long lo = max(i_lo, (long long)b * Ws), hi = min(i_lo + kRun, (long long)b * Ws + Wp);
+                const long long lo = max(i_lo, (long long)b * Ws), hi = min(i_lo + kRunLoad, (long long)b * Ws + Wp);
                 if (hi <= lo || 2 * b + r > H + 1) continue;
                 const uint32_t bytes = (uint32_t)(hi - lo) * 16, e = (uint32_t)(lo - i_lo) * 16;
                 const long long src_px = (long long)(2 * b + r) * Wp + (lo - (long long)b * Ws);
@@ -357,7 +330,7 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       const uint64_t policy = l2_policy_evict_last();
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-        for (int c = 0; c < kKB * 9; ++c, ++it) {
+        for (int c = 0; c < kKB * kTaps; ++c, ++it) {
           const uint32_t s = it % kRingW;
           if (it >= kRingW) mbar_wait(&w_empty[s], (it / kRingW - 1) & 1, 12);
           mbar_arrive_expect_tx(&w_full[s], kChunk);
@@ -374,8 +347,8 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       const uint32_t d0 = tmem + buf * 2 * kDCols, d1 = d0 + kDCols;
       uint32_t acc = 0;
       for (int kb = 0; kb < kKB; ++kb, a_it += 4) {
-        for (int tap = 0; tap < 9; ++tap, ++w_it) {
-          const int dy = tap / 3, dx = tap - dy * 3;
+        for (int tap = 0; tap < kTaps; ++tap, ++w_it) {
+          const int dy = kFirst ? tap : tap / 3, dx = kFirst ? 0 : tap - dy * 3;
           const uint32_t r0 = a_it + dy, r1 = r0 + 1;
           if (dx == 0) {
             if (dy == 0) mbar_wait(&a_full[r0 % kRingA], (r0 / kRingA) & 1, 14);
@@ -386,8 +359,9 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
           tc_fence_after_sync();
           if (elect_one()) {
             // descriptors differ only in the 14-bit address field: build one per operand and add offsets
-            const uint64_t a0h = make_sdesc_k_nosw(smem_u32(s_rows + (r0 % kRingA) * kRowBytes) + dx * 16, kChunkStride, 128);
-            const uint64_t a1h = make_sdesc_k_nosw(smem_u32(s_rows + (r1 % kRingA) * kRowBytes) + dx * 16, kChunkStride, 128);
+            constexpr uint32_t kLbo = kFirst ? 16 : kChunkStride;   // K-adjacent chunk: next pixel | next channel chunk
+            const uint64_t a0h = make_sdesc_k_nosw(smem_u32(s_rows + (r0 % kRingA) * kRowBytes) + dx * 16, kLbo, 128);
+            const uint64_t a1h = make_sdesc_k_nosw(smem_u32(s_rows + (r1 % kRingA) * kRowBytes) + dx * 16, kLbo, 128);
             const uint64_t bh = make_sdesc_k_sw128(smem_u32(s_ring + s * kChunk), 1024);
             constexpr uint64_t kLo = kRowHalf >> 4, kBLo = (COUT * 128) >> 4;
             // all MMAs of one accumulator back to back, then the other: alternating accumulators
@@ -398,8 +372,8 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
               const uint32_t d = t ? d1 : d0;
               const uint64_t ah = t ? a1h : a0h;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint64_t ja = (uint64_t)((2 * j * kChunkStride) >> 4), jb = (uint64_t)((j * 32) >> 4);
+              for (int j = 0; j < (kFirst ? 2 : 4); ++j) {
+                const uint64_t ja = (uint64_t)((2 * j * kLbo) >> 4), jb = (uint64_t)((j * 32) >> 4);
                 if constexpr (kStack) {
                   constexpr uint32_t idesc2 = make_idesc_f16(128, 128, 0);
                   umma_ss(d, ah + ja, bh + jb, idesc2, j ? 1u : acc0);   // hi * [hi; lo]
@@ -413,11 +387,11 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
             }
             acc = 1;
             umma_commit(&w_empty[s]);
-            if (dx == 2) {
+            if (dx == 2 || kFirst) {
               umma_commit(&a_empty[r0 % kRingA]);                 // row dy is done after tap row dy
               if (dy == 2) umma_commit(&a_empty[r1 % kRingA]);    // and row 3 with it
             }
-            if (tap == 8 && kb == kKB - 1) umma_commit(&d_full[buf]);
+            if (tap == kTaps - 1 && kb == kKB - 1) umma_commit(&d_full[buf]);
           }
           __syncwarp();
         }
@@ -489,6 +463,13 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
             uint32_t v[32];
             tmem_ld_x32(t0 + r * kDCols + c0, v);
             tmem_ld_wait();
+            if constexpr (kStack) {   // add the hi*lo column half
+              uint32_t v2[32];
+              tmem_ld_x32(t0 + r * kDCols + 64 + c0, v2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+            }
             if (valid) {
               if constexpr (kOut == kOutPlanes) {
 #pragma unroll
@@ -585,11 +566,15 @@ size_t pc_bytes(int H, int W) { return planes_bytes(128, H / 2, W / 2); }
 
 }  // namespace
 
+// conv2's tensor-core image (3 chunks of 16 KB) follows the fp32 blob, 128-byte aligned
+static size_t first_image_offset(size_t blob_off) { return (blob_off + Blob::total * sizeof(float) + 127) & ~size_t(127); }
+constexpr size_t kFirstImageBytes = 3 * 2 * 64 * 128;
+
 size_t encoder_packed_bytes() {
   TcLayer L[4];
   size_t blob;
   tc_layers(L, blob);
-  return blob + Blob::total * sizeof(float);
+  return first_image_offset(blob) + kFirstImageBytes;
 }
 
 size_t encoder_scratch_bytes(int H, int W) {
@@ -609,7 +594,8 @@ int encoder_pack(const crnerf_encoder_weights* w, void* packed, size_t packed_by
   enc_pack_blob_kernel<<<32, 256, 0, st>>>(w->weight[0], w->bias[0], w->weight[1], w->bias[1], w->bias[2], w->bias[3],
                                            w->bias[4], w->bias[5], w->weight[6], w->bias[6],
                                            reinterpret_cast<float*>(img + blob));
-  count_launch(5);
+  enc_pack_first_kernel<<<48, 256, 0, st>>>(w->weight[1], img + first_image_offset(blob));
+  count_launch(6);
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;
 }
@@ -635,12 +621,19 @@ int encoder_forward(const void* packed, const float* img, int H, int W, float* o
   auto plane = [](int h, int w) { return (long long)(h + 2) * (w + 2); };
   int rc;
 
-  // conv1 . pad . conv2 -> Pa (64, H, W)
-  enc_first_kernel<<<(unsigned)(((long long)H * ((W + 32 * kFirstPix - 1) / (32 * kFirstPix)) * 32 + 127) / 128), 128, 0,
-                     st>>>(img, H, W, blob, Pa,
-                                                                               Pa + (size_t)64 * plane(H, W));
-  count_launch();
-  CRNERF_CUDA(cudaGetLastError());
+  // conv1 + halo -> P0 (one 8-channel chunk, H, W; lives in Pb's region, dead before conv3 writes Pb)
+  __half* P0 = Pb;
+  {
+    const long long total = plane(H, W);
+    const int grid = (int)std::min<long long>((total + 255) / 256, 16LL * num_sms());
+    enc_conv1_planes_kernel<<<grid, 256, 0, st>>>(img, H, W, blob, P0, P0 + (size_t)8 * total);
+    count_launch();
+    CRNERF_CUDA(cudaGetLastError());
+  }
+  // conv2: P0 -> Pa (64, H, W)
+  if ((rc = launch_conv<8, 64, kOutPlanes>(P0, wimg + first_image_offset(blob_off), blob + Blob::b2, nullptr, Pa,
+                                           plane(H, W), H, W, st)))
+    return rc;
   // conv3 + pool: Pa -> Pb (64, H/2, W/2)
   if ((rc = launch_conv<64, 64, kOutPoolPlanes>(Pa, wimg + L[0].offset, blob + Blob::b3, nullptr, Pb, plane(H2, W2), H,
                                                 W, st)))

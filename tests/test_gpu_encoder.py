@@ -30,7 +30,7 @@ def test_encoder_golden():
         n0 = ops.launch_count()
         with torch.no_grad():
             got = enc(case["x"].to(DEV))
-        assert ops.launch_count() - n0 == 6, "the native encoder kernels did not run"
+        assert ops.launch_count() - n0 == 7, "the native encoder kernels did not run"
         assert got.shape == case["ref"].shape
         err = (got.cpu() - case["ref"]).abs().max()
         assert torch.allclose(got.cpu(), case["ref"], rtol=1e-4, atol=1e-5), (tuple(case["x"].shape), float(err))
