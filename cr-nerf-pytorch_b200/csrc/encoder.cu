@@ -57,27 +57,43 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& h, uint4& l) 
 }
 
 // Padded positions that hold interior pixel (yp, xp) (padded coordinates, 1-based interior) of an
-// H x W layer: itself plus its reflection-halo copies (row 0 mirrors row 2, row H+1 mirrors H-1).
+// H x W layer: itself plus its reflection-halo copies (row 0 mirrors row 2, row H+1 mirrors H-1,
+// same for columns).  Flags, not index arrays: the common interior case is one predicated-off branch.
 struct HaloTargets {
-  int ys[3], xs[3], ny, nx;
-  __device__ __forceinline__ HaloTargets(int yp, int xp, int H, int W) {
-    ny = nx = 0;
-    ys[ny++] = yp;
-    if (yp == 2) ys[ny++] = 0;
-    if (yp == H - 1) ys[ny++] = H + 1;
-    xs[nx++] = xp;
-    if (xp == 2) xs[nx++] = 0;
-    if (xp == W - 1) xs[nx++] = W + 1;
+  int yp, xp, H, W;
+  bool top, bot, left, right, any;
+  __device__ __forceinline__ HaloTargets(int yp_, int xp_, int H_, int W_) : yp(yp_), xp(xp_), H(H_), W(W_) {
+    top = yp == 2;
+    bot = yp == H - 1;
+    left = xp == 2;
+    right = xp == W - 1;
+    any = top || bot || left || right;
   }
 };
+__device__ __forceinline__ void store_plane_at(__half* hi, __half* lo, size_t plane_base, int Wp, int y, int x,
+                                               const uint4& h, const uint4& l) {
+  const size_t o = plane_base + ((size_t)y * Wp + x) * 8;
+  *reinterpret_cast<uint4*>(hi + o) = h;
+  *reinterpret_cast<uint4*>(lo + o) = l;
+}
 __device__ __forceinline__ void store_plane_elem(__half* hi, __half* lo, int Hp, int Wp, int chunk,
                                                  const HaloTargets& t, const uint4& h, const uint4& l) {
-  for (int a = 0; a < t.ny; ++a)
-    for (int b = 0; b < t.nx; ++b) {
-      const size_t o = (((size_t)chunk * Hp + t.ys[a]) * Wp + t.xs[b]) * 8;
-      *reinterpret_cast<uint4*>(hi + o) = h;
-      *reinterpret_cast<uint4*>(lo + o) = l;
+  const size_t pb = (size_t)chunk * Hp * Wp * 8;
+  store_plane_at(hi, lo, pb, Wp, t.yp, t.xp, h, l);
+  if (t.any) {
+    if (t.left) store_plane_at(hi, lo, pb, Wp, t.yp, 0, h, l);
+    if (t.right) store_plane_at(hi, lo, pb, Wp, t.yp, t.W + 1, h, l);
+    if (t.top) {
+      store_plane_at(hi, lo, pb, Wp, 0, t.xp, h, l);
+      if (t.left) store_plane_at(hi, lo, pb, Wp, 0, 0, h, l);
+      if (t.right) store_plane_at(hi, lo, pb, Wp, 0, t.W + 1, h, l);
     }
+    if (t.bot) {
+      store_plane_at(hi, lo, pb, Wp, t.H + 1, t.xp, h, l);
+      if (t.left) store_plane_at(hi, lo, pb, Wp, t.H + 1, 0, h, l);
+      if (t.right) store_plane_at(hi, lo, pb, Wp, t.H + 1, t.W + 1, h, l);
+    }
+  }
 }
 
 // ---- packed weight image ----------------------------------------------------------------------
