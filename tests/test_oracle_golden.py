@@ -131,3 +131,17 @@ def test_encoder_matches_reference():
         with torch.no_grad():
             assert torch.equal(oracle.encoder_forward(state(enc), case["x"]), case["ref"])
             assert torch.equal(enc(case["x"]), case["ref"])
+
+
+def test_losses_mirror_schedules_match_reference_weights():
+    """The `losses` module mirror (host side only here: the schedules and the key set it would emit)."""
+    import types
+    import losses
+    g = load_golden("loss")
+    for case in g["cases"]:
+        hp = types.SimpleNamespace(**case["hp"])
+        crit = losses.loss_dict["crnerf"](hp, coef=1)
+        assert crit.Annealing.getWeight(case["step"]) == case["weight"]
+    cos = losses.CosineAnnealingWeight(max=5e-2, min=6e-3, Tmax=1000)
+    assert cos.getWeight(0) == 5e-2 and abs(cos.getWeight(1000) - 6e-3) < 1e-18 and abs(cos.getWeight(500) - 0.028) < 1e-15
+    assert set(losses.loss_dict) == {"color", "crnerf"}
