@@ -19,9 +19,22 @@ evaluates the MLP at 4096*(64+192) = 1,048,576 points = 1.29306 TFLOP.
           FLOPs / duration against the measured bf16 peak of MEASURED_PEAKS.json.
   cpu_baseline : the oracle (torch-CPU port of the reference path) on the host cores.
 
-``--impl reference`` times that same CPU port alone (the reference is pure
-PyTorch; its own files cannot travel to the GPU box, the oracle is pinned
-bit-exact against them - oracle/make_golden.py).
+  sustained : >= 2 s of back-to-back steps (no L2 flush: the step's working set is the
+          1.3 MB weight images + a 131 KB ray batch), clocks sampled during the loop, against
+          MEASURED_PEAKS.json's bf16_tflops_sustained.
+  frame     : BASELINE configs[3] - ONE 800x800 frame (640,000 rays x (64+128)), rays built on
+          the GPU, ray rows sharded across the N ranks, cross-ray statistics combined with two
+          small all-reduces, rgb blocks with one all-gather (crnerf_b200/frame.py, scheme
+          "stats"); strong scaling; ``frame_check`` = max |rgb| difference between the N-rank
+          frame and rank 0 rendering the same frame alone through the unsharded style_net.
+  train     : BASELINE configs[4] - one training step of the reference's call pattern
+          (1024-ray patch x (64+64), perturb = noise = 1, decode x2, MSE, backward, Adam), one
+          patch per rank, DDP gradient all-reduce.
+
+``--impl reference`` times the reference's own CPU implementation of the path: the
+UNMODIFIED ``models/rendering.py`` + ``models/nerf.py`` staged by ``build()`` under the
+git-ignored ``oracle/_ref/`` (``kind: "reference"``); if they are absent, the pinned port
+``oracle/crnerf_oracle.py`` (``kind: "port"``, bit-exact against them - oracle/make_golden.py).
 """
 import argparse
 import json
@@ -46,11 +59,6 @@ RAY_SAMPLES_PER_STEP = N_RAYS * (NS + NI)     # 786,432
 POINTS_PER_STEP = N_RAYS * (NS + NS + NI)     # 1,048,576
 METRIC = "ray-samples/sec at 4096 rays x (64+128) samples"
 UNIT = "ray-samples/s"
-# dram__bytes_read.sum + dram__bytes_write.sum of one fused fine-pass launch, from the committed
-# `ncu --set full` capture (bench.py cannot run ncu on itself); the kernel is tensor-bound,
-# HBM traffic is rays/z in, weights/feature/depth out plus the 1.3 MB weight image once
-NCU_DRAM_BYTES_PER_LAUNCH = 4676864
-NCU_TRAFFIC_SOURCE = "profiles/r01_ncu_fused_fine_pass_metrics.txt (dram__bytes_read.sum + dram__bytes_write.sum)"
 WORKLOAD = ("configs[1]: 4096-ray eval batches (slices of a 320x256 synthetic Brandenburg-Gate-shaped "
             "frame), 64 coarse + 128 fine samples, N_emb_xyz=15, N_emb_dir=4, nerf_out_dim=64, "
             "default-init weights seed 0")
@@ -60,6 +68,32 @@ def load_oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import crnerf_oracle
     return crnerf_oracle
+
+
+class CpuPath:
+    """The CPU arm: the reference's own files when staged (oracle/_ref), else the pinned port.
+    bench.py's CPU legs are the only place outside tests/ and smoke() that touches oracle/."""
+
+    def __init__(self, state):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_loader
+        self.kind, self._ref, self._oracle, self._state = "port", None, None, state
+        if ref_loader.find_reference() is not None:
+            try:
+                self._ref = ref_loader.ReferenceRenderer(state[0], state[1])
+                self.kind = "reference"
+            except Exception as e:   # noqa: BLE001  (e.g. einops missing on the box)
+                print(f"[bench] staged reference unusable ({type(e).__name__}: {e}); using the port",
+                      file=sys.stderr)
+        if self._ref is None:
+            self._oracle = load_oracle()
+
+    def render(self, rays):
+        with torch.no_grad():
+            if self._ref is not None:
+                return self._ref.render_rays(rays, NS, NI, 8192)
+            return self._oracle.render_rays(self._state[0], self._state[1], rays, n_samples=NS,
+                                            n_importance=NI, perturb=0, noise_std=0, chunk=8192)
 
 
 def make_args():
@@ -97,20 +131,17 @@ def use_all_host_threads():
     return torch.get_num_threads()
 
 
-def cpu_reference_throughput(oracle, state, rays, reps, warm=1):
-    """ray-samples/s of the CPU port on all host threads; each rep = one 4096-ray batch."""
+def cpu_reference_throughput(cpu, rays, reps, warm=1):
+    """ray-samples/s of the CPU arm on all host threads; each rep = one 4096-ray batch."""
     use_all_host_threads()
-    pc, pf = state
     times = []
-    with torch.no_grad():
-        for i in range(warm + reps):
-            batch = rays[(i % 20) * N_RAYS:(i % 20 + 1) * N_RAYS]
-            t0 = time.perf_counter()
-            oracle.render_rays(pc, pf, batch, n_samples=NS, n_importance=NI, perturb=0, noise_std=0,
-                               chunk=8192)
-            dt = time.perf_counter() - t0
-            if i >= warm:
-                times.append(dt)
+    for i in range(warm + reps):
+        batch = rays[(i % 20) * N_RAYS:(i % 20 + 1) * N_RAYS]
+        t0 = time.perf_counter()
+        cpu.render(batch)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
     return RAY_SAMPLES_PER_STEP / statistics.mean(times), times
 
 
@@ -148,8 +179,9 @@ class ClockSampler:
     polled from a thread every ~2 ms (the timed region of the default run is ~25 ms, too short for
     `nvidia-smi -lms`); falls back to one `nvidia-smi` query if the NVML binding is missing."""
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.002):
         self.index, self.rows, self._stop, self._thr, self._h = index, [], False, None, None
+        self.period = period
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -166,7 +198,7 @@ class ClockSampler:
                                   nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)))
             except Exception:   # noqa: BLE001
                 break
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def start(self):
         if self._nv is not None:
@@ -201,30 +233,125 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def shared_config():
+    """`config` is byte-identical in both arms (same workload); per-arm details go to `detail`."""
+    return {"workload": WORKLOAD, "rays_per_step": N_RAYS, "n_coarse": NS, "n_fine": NI}
+
+
+def traffic_record():
+    """dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (bench.py cannot run ncu on itself).  profiles/ncu_traffic.json also stores a hash of the
+    kernel's sources at capture time: a mismatch with today's sources flags the number as stale
+    instead of letting a regression hide behind a constant."""
+    import hashlib
+    rec_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        rec = json.load(open(rec_path))
+    except (OSError, ValueError):
+        return None, {"traffic_source": "no committed capture"}
+    h = hashlib.sha256()
+    for rel in rec.get("sources", []):
+        try:
+            h.update(open(os.path.join(ROOT, rel), "rb").read())
+        except OSError:
+            h.update(b"missing")
+    fresh = h.hexdigest() == rec.get("sources_sha256")
+    return rec.get("dram_bytes_per_launch"), {
+        "traffic_unit": "bytes/launch", "traffic_source": rec.get("capture"),
+        "traffic_matches_current_sources": fresh}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    oracle = load_oracle()          # the reference arm IS the CPU port
     models, _ = build_models()
     rays = frame_rays()
     cores = use_all_host_threads()
-    value, times = cpu_reference_throughput(oracle, cpu_state(models), rays, reps=max(1, args.steps),
-                                            warm=max(1, min(args.warmup, 2)))
+    cpu = CpuPath(cpu_state(models))      # the reference arm IS the CPU path
+    warm = max(1, args.warmup)
+    value, times = cpu_reference_throughput(cpu, rays, reps=max(1, args.steps), warm=warm)
     sample = f"{len(times)} x one 4096-ray batch (786,432 ray-samples each) on {cores} threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(times), "warmup": max(1, min(args.warmup, 2)),
+        "steps": len(times), "warmup": warm,
         "ms_per_step": 1e3 * statistics.mean(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "device": "cpu", "chunk": 8192,
-                   "host_cpus": os.cpu_count()},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "config": shared_config(),
+        "detail": {"device": "cpu", "chunk": 8192, "host_cpus": os.cpu_count(),
+                   "code": ("unmodified reference models/rendering.py + models/nerf.py (oracle/_ref)"
+                            if cpu.kind == "reference" else "oracle/crnerf_oracle.py (pinned port)")},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": cpu.kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def frame_leg(models_gpu, emb, margs, dev, world, rank, barrier, reps=3, warm=2):
+    """BASELINE configs[3]: one 800x800 frame sharded over the ranks (see module docstring)."""
+    import math
+    import torch.distributed as dist
+    from crnerf_b200 import ops
+    from crnerf_b200.frame import batched_render, render_frame_sharded
+    from crnerf_b200.synthetic import synthetic_pose
+    h = w = 800
+    fl = 0.5 * w / math.tan(math.radians(30.0))
+    K = [[fl, 0.0, w / 2], [0.0, fl, h / 2], [0.0, 0.0, 1.0]]
+    pose = synthetic_pose(0).tolist()
+    camera = (K, pose, 0.0, 5.0)
+    style = torch.rand(1, 64, 32, 32, generator=torch.Generator().manual_seed(1)).to(dev)
+
+    def frame():
+        return render_frame_sharded(models_gpu, emb, None, style, (h, w), NS, NI, scheme="stats",
+                                    camera=camera, args=margs)
+
+    for _ in range(warm):
+        rgb = frame()
+    barrier()
+    ms = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        rgb = frame()
+        e1.record()
+        barrier()
+        ms.append(e0.elapsed_time(e1))
+    t = torch.tensor(ms, device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)        # per frame: the slowest rank
+    frame_ms = float(t.mean().item())
+    check = None
+    if rank == 0:
+        # the same frame on rank 0 alone, through the UNSHARDED public path: batched render of all
+        # 640,000 rays, then style_net.forward on the (1,64,H,W) view (reference eval.py:279-294)
+        with torch.no_grad():
+            rays = ops.generate_rays(h, w, K, pose, 0.0, 5.0, device=dev)
+            res = batched_render(models_gpu, emb, rays, NS, NI, False, None, args=margs)
+            solo = models_gpu["decoder"](res["feature_fine"].t().reshape(1, 64, h, w), style)
+        check = float((solo - rgb).abs().max().item())
+        del rays, res, solo
+    barrier()
+    return {"frame_ms": frame_ms, "frame_ray_samples_per_s": h * w * (NS + NI) / (frame_ms * 1e-3),
+            "frame_check": check, "frame_check_tolerance": 1e-5,
+            "frame": {"hw": [h, w], "rays": h * w, "samples": [NS, NI], "scheme": "stats", "reps": reps,
+                      "warmup": warm, "scaling": "strong", "rays_per_rank": -(-h * w // world),
+                      "collectives_per_frame": "all_reduce(64 f32) + all_reduce(1024 f32) + all_gather(rgb 12 B/ray)"
+                                               if world > 1 else "none",
+                      "timing": "CUDA events around the whole frame call, max over ranks per frame, mean of reps",
+                      "check": "max |rgb| diff vs rank 0 rendering the frame alone through style_net.forward"}}
+
+
+def train_leg(dev, world, rank, barrier, reps=10, warm=3):
+    """BASELINE configs[4]: tools/bench_train.py's step, one 1024-ray patch per rank."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_train
+        return bench_train.measure(dev, world, rank, barrier, reps=reps, warm=warm)
+    except Exception as e:   # noqa: BLE001  (an extra leg must not take the headline down)
+        return {"train_error": f"{type(e).__name__}: {e}"}
 
 
 def run_ours(args):
@@ -252,7 +379,11 @@ def run_ours(args):
     rays_dev = rays_cpu.to(dev)
     batch = lambda i: rays_dev[((i * world + rank) % n_batches) * N_RAYS:
                                ((i * world + rank) % n_batches + 1) * N_RAYS]
-    gather_buf = torch.empty(world * N_RAYS, 64, device=dev) if world > 1 else None
+    # the patch all-gather runs on a side stream: step i's gather overlaps step i+1's render
+    gather_bufs = [torch.empty(world * N_RAYS, 64, device=dev) for _ in range(2)] if world > 1 else None
+    gather_src = [torch.empty(N_RAYS, 64, device=dev) for _ in range(2)] if world > 1 else None
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    main_stream = torch.cuda.current_stream(dev)
 
     # the public eval API for a fixed batch shape: render_rays_cross_ray captured in a CUDA graph
     # (crnerf_b200/graphs.py; same kernels, one launch); --no-graph times the plain call
@@ -261,16 +392,50 @@ def run_ours(args):
         from crnerf_b200.graphs import GraphedRenderer
         graphed = GraphedRenderer(models_gpu, emb, N_RAYS, NS, NI, args=margs)
 
-    def step(rays):
+    def render(rays):
         if graphed is not None:
-            res = graphed(rays)
-        else:
-            with torch.no_grad():
-                res = render_rays_cross_ray(models_gpu, emb, rays, None, NS, False, 0, 0, NI, 32768, False,
-                                            test_time=True, args=margs)
-        if world > 1:  # the sharded frame's single collective: gather the rendered features
-            dist.all_gather_into_tensor(gather_buf, res["feature_fine"])
+            return graphed(rays)
+        with torch.no_grad():
+            return render_rays_cross_ray(models_gpu, emb, rays, None, NS, False, 0, 0, NI, 32768, False,
+                                         test_time=True, args=margs)
+
+    deferred = [None]     # slot whose features wait to be gathered (launched with the NEXT step)
+    pending = [None]      # completion event of the gather in flight
+
+    def launch_gather():
+        s_prev, deferred[0] = deferred[0], None
+        mark = torch.cuda.Event()
+        mark.record(main_stream)                 # inside the timed window of the step that hosts it
+        comm.wait_event(mark)
+        with torch.cuda.stream(comm):
+            dist.all_gather_into_tensor(gather_bufs[s_prev], gather_src[s_prev])
+            done = torch.cuda.Event()
+            done.record(comm)
+        pending[0] = done
+
+    def step(rays, i):
+        """One step = render of this rank's batch; with N > 1 also the patch all-gather of the
+        PREVIOUS step's features, launched on a side stream at the start of this step (never
+        earlier: it must not hide under the untimed L2 flush) and awaited before the step ends."""
+        if world > 1 and deferred[0] is not None:
+            launch_gather()
+        res = render(rays)
+        if world > 1:
+            s = i & 1
+            gather_src[s].copy_(res["feature_fine"])          # the graph's static output is reused
+            if pending[0] is not None:
+                main_stream.wait_event(pending[0])             # previous gather ends inside this step
+                pending[0] = None
+            deferred[0] = s
         return res
+
+    def drain():
+        """The last step's gather: launched and awaited on its own."""
+        if world > 1 and deferred[0] is not None:
+            launch_gather()
+        if world > 1 and pending[0] is not None:
+            main_stream.wait_event(pending[0])
+            pending[0] = None
 
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)   # > 126 MB L2
 
@@ -279,8 +444,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(3, args.warmup)):
-        step(batch(i))
+    n_warm = max(3, args.warmup)
+    for i in range(n_warm):
+        step(batch(i), i)
+    drain()
     barrier()
 
     # ---- value: device-timed steps, inputs resident, L2 flushed between steps
@@ -288,14 +455,19 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(args.steps)]
+           for _ in range(args.steps + 1)]
     n0 = ops.launch_count()
     barrier()
-    for i, (e0, e1) in enumerate(evs):
+    for i in range(args.steps):
+        e0, e1 = evs[i]
         flush.fill_(float(i))
         e0.record()
-        step(batch(i))
+        step(batch(i), i)
         e1.record()
+    e0, e1 = evs[args.steps]           # the last step's gather, timed on its own (N > 1)
+    e0.record()
+    drain()
+    e1.record()
     barrier()
     launches = ops.launch_count() - n0
     if graphed is not None:   # replays do not pass through the library's host-side counter
@@ -322,12 +494,13 @@ def run_ours(args):
     for i in range(args.steps):
         s = i & 1
         r = host_rays[i % len(host_rays)]
-        res = step(r if graphed is not None else r.to(dev, non_blocking=True))   # H2D inside either way
+        res = step(r if graphed is not None else r.to(dev, non_blocking=True), i)   # H2D inside either way
         host_out[s].copy_(res["feature_fine"], non_blocking=True)
         host_depth[s].copy_(res["depth_fine"], non_blocking=True)
         done[s].record()
         if i:
             done[s ^ 1].synchronize()    # the caller consumes step i-1's result while step i runs
+    drain()
     done[(args.steps - 1) & 1].synchronize()
     barrier()
     wall = time.perf_counter() - t0
@@ -337,9 +510,46 @@ def run_ours(args):
     e2e_value = world * RAY_SAMPLES_PER_STEP * args.steps / float(t.item())
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- sustained: >= 2 s of back-to-back steps under the power cap, clocks sampled
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(200, int(args.sustained_s * 1e3 / max(1e-3, dev_ms / args.steps)))
+        sus_sampler = ClockSampler(local, period=0.05)
+        barrier()
+        if rank == 0:
+            sus_sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_sus):
+            step(batch(i), i)
+        drain()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sus_ms = float(t.item())
+        if rank == 0:
+            sus_clocks = sus_sampler.stop()
+            sus_val = world * RAY_SAMPLES_PER_STEP * n_sus / (sus_ms * 1e-3)
+            tf = POINTS_PER_STEP * FLOP_PER_POINT * n_sus / (sus_ms * 1e-3) / 1e12     # per GPU
+            peak_s = None
+            try:
+                peak_s = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+            except (OSError, KeyError, ValueError):
+                pass
+            sustained = {"value": sus_val, "unit": UNIT, "steps": n_sus, "seconds": sus_ms * 1e-3,
+                         "ms_per_step": sus_ms / n_sus, "tflops_per_gpu": tf,
+                         "peak": peak_s, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained",
+                         "frac": (tf / peak_s) if peak_s else None, "clocks": sus_clocks,
+                         "l2": "no flush between steps (working set: 2 x 1.3 MB weight images + 131 KB of rays)",
+                         "note": "whole step (coarse + resample + fine) back to back; frac = algorithmic "
+                                 "TFLOP/s of the step / sustained cuBLAS bf16 peak"}
+
     # ---- roofline of the dominant kernel: the fused fine pass, timed alone
     roof = None
     cpu_base = None
+    cpu = None
     if rank == 0:
         with torch.no_grad():
             res = render_rays_cross_ray(models_gpu, emb, batch(0), None, NS, False, 0, 0, NI, 32768,
@@ -369,16 +579,16 @@ def run_ours(args):
             peak, peak_src = float(mp["bf16_tflops"]), "measured burst (MEASURED_PEAKS.json bf16_tflops)"
         except (OSError, KeyError, ValueError):
             pass
+        traffic, traffic_info = traffic_record()
         roof = {"bound": "tensor", "kernel": "render_fused_kernel<fp16> fine pass, 4096x192 points",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes/launch",
-                "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src, "kernel_ms": k_ms,
+                "traffic": traffic, **traffic_info, "peak_source": peak_src, "kernel_ms": k_ms,
                 "flop_per_launch": flop}
         if world == 1 and not args.no_cpu_baseline:
-            oracle = load_oracle()      # cpu_baseline / PSNR legs only: the checker, never the thing measured
+            cpu = CpuPath(state_cpu)     # cpu_baseline / PSNR legs only: the checker, never the thing measured
             cores = use_all_host_threads()
-            v, times = cpu_reference_throughput(oracle, state_cpu, rays_cpu, reps=5, warm=1)
-            cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            v, times = cpu_reference_throughput(cpu, rays_cpu, reps=5, warm=1)
+            cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": cpu.kind,
                         "sample": f"5 x one 4096-ray batch (786,432 ray-samples each), "
                                   f"{sum(times):.1f} s of CPU work on {cores} threads"}
 
@@ -386,15 +596,24 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         psnr = psnr_delta(load_oracle(), models_gpu, state_cpu, emb, margs, dev)
 
+    extra = {}
+    if not args.no_frame:
+        extra.update(frame_leg(models_gpu, emb, margs, dev, world, rank, barrier))
+    if not args.no_train:
+        extra.update(train_leg(dev, world, rank, barrier))
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": dev_ms / args.steps,
+            "warmup": n_warm, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16 operands, fp32 accumulate (tcgen05 kind::f16); fp32 everywhere else",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": N_RAYS,
-                       "parallelism": f"rays sharded x{world}" + (", all_gather(feature_fine)" if world > 1 else ""),
+            "config": shared_config(),
+            "detail": {"rays_per_gpu_per_step": N_RAYS,
+                       "parallelism": f"rays sharded x{world}" + (
+                           ", all_gather(feature_fine) of step i on a side stream under step i+1's render; "
+                           "the last gather is timed on its own" if world > 1 else ""),
                        "api": ("crnerf_b200.graphs.GraphedRenderer (render_rays_cross_ray captured in a CUDA graph)"
                                if graphed is not None else "models.rendering.render_rays_cross_ray"),
                        "l2": "256 MiB buffer written between timed steps (outside the event pairs)",
@@ -406,9 +625,11 @@ def run_ours(args):
                               "stream sync every step"},
             "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu_base, "psnr": psnr, "clocks": clocks,
+            "sustained": sustained,
             "points_per_step": POINTS_PER_STEP,
             "tflops_per_step_device": POINTS_PER_STEP * FLOP_PER_POINT / (dev_ms / args.steps * 1e-3) / 1e12,
         }
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -422,10 +643,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the plain API call instead of the graphed one")
+    ap.add_argument("--no-frame", action="store_true", help="skip the 800x800 sharded-frame leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained loop")
+    ap.add_argument("--sustained-s", type=float, default=2.5)
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.steps > 8:      # keep the CPU arm bounded: ~1.5-3 s per step
-            args.steps = 8
         run_reference(args)
     else:
         run_ours(args)

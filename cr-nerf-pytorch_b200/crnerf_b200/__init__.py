@@ -6,6 +6,7 @@ reference's ``models/`` API on top of it.  Importing this package does not load
 the shared library; the first op does, and raises if it is missing.
 """
 from . import _lib, ops  # noqa: F401
+from . import torch_ops  # noqa: F401  (registers torch.ops.crnerf.*)
 from ._lib import CrnerfError  # noqa: F401
 
 __all__ = ["ops", "CrnerfError"]

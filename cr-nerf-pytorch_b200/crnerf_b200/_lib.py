@@ -60,6 +60,7 @@ SIGNATURES = {
     "crnerf_composite_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                             C.c_void_p]),
+    "crnerf_relu_bias_grad_scratch_floats": (C.c_size_t, [C.c_int]),
     "crnerf_relu_bias_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p]),
     "crnerf_mlp_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64,

@@ -7,7 +7,7 @@ inference, which additionally stores each layer's 16-bit activations and the per
 Backward: ``crnerf_composite_backward`` (our kernel) turns the gradients of
 ``feature`` / ``weights`` / ``depth`` into the gradients of the MLP's pre-activation outputs;
 the twelve dgrad/wgrad pairs that follow are plain dense GEMMs over the saved activations and
-go to cuBLAS through ``torch.matmul`` (``BACKWARD_MATMUL``: "tf32" default, "fp32", or "bf16" = bf16
+go to cuBLAS through ``torch.matmul`` (``BACKWARD_MATMUL``: "fp32" default, "tf32", or "bf16" = bf16
 operands with fp32 accumulation and output - the pairing for ``args.crnerf_operand = 'bf16'`` models,
 BASELINE configs[4], whose saved activations are then consumed without any conversion),
 with the ReLU masks applied elementwise.  Parameter gradients land in ``param.grad`` of the
@@ -22,7 +22,10 @@ import torch
 
 from . import ops
 
-BACKWARD_MATMUL = "tf32"     # "tf32" | "fp32" | "bf16"
+# "fp32" (default: the reference trains with torch's default fp32 matmuls) | "tf32" | "bf16"
+# (explicit opt-ins; "bf16" is the pairing for args.crnerf_operand = 'bf16' models)
+BACKWARD_MATMUL = "fp32"
+DEFAULT_BACKWARD_MATMUL = BACKWARD_MATMUL
 
 
 @contextlib.contextmanager

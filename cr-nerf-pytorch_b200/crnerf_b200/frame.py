@@ -48,22 +48,31 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, min(n, lo + per)
 
 
-def batched_render(models, embeddings, rays, N_samples, N_importance, use_disp, chunk, **kwargs):
-    """The reference's ``batched_inference`` (eval.py:29-59): eval-mode render of ``rays`` in
-    chunks of ``chunk`` rays, results concatenated.  Only the keys the callers read
-    afterwards are kept on the device."""
+def batched_render(models, embeddings, rays, N_samples, N_importance, use_disp, chunk=None, **kwargs):
+    """The reference's ``batched_inference`` (eval.py:29-59): eval-mode render of ``rays``.
+
+    The reference chunks the rays (``--chunk``) because every chunk materialises
+    ``(chunk*N_samples, 256)`` activations; the fused kernels materialise no per-point tensor, so
+    with ``chunk=None`` (default) the whole block of rays is ONE call = one coarse launch, one
+    inverse-CDF launch and one fine launch, whatever its size, and nothing is concatenated.
+    An explicit ``chunk`` reproduces the reference's loop call for call."""
     from models.rendering import render_rays_cross_ray
+    n = rays.shape[0]
+    if n == 0:
+        typ = "fine" if N_importance > 0 else "coarse"
+        return {f"feature_{typ}": rays.new_zeros((0, 64)), f"depth_{typ}": rays.new_zeros((0,))}
+    if chunk is None or chunk >= n:
+        with torch.no_grad():
+            return render_rays_cross_ray(models, embeddings, rays, None, N_samples, use_disp, 0, 0,
+                                         N_importance, n, False, test_time=True, **kwargs)
     out = {}
     with torch.no_grad():
-        for i in range(0, rays.shape[0], chunk):
+        for i in range(0, n, chunk):
             res = render_rays_cross_ray(models, embeddings, rays[i:i + chunk], None, N_samples,
                                         use_disp, 0, 0, N_importance, chunk, False, test_time=True,
                                         **kwargs)
             for k, v in res.items():
                 out.setdefault(k, []).append(v)
-    if not out:
-        typ = "fine" if N_importance > 0 else "coarse"
-        return {f"feature_{typ}": rays.new_zeros((0, 64)), f"depth_{typ}": rays.new_zeros((0,))}
     return {k: torch.cat(v, 0) for k, v in out.items()}
 
 
@@ -123,7 +132,7 @@ def fuse_decode_sharded(backend, feat_local: torch.Tensor, style: torch.Tensor, 
 
 
 def render_frame_sharded(models, embeddings, rays: Optional[torch.Tensor], style: Optional[torch.Tensor],
-                         hw: Tuple[int, int], N_samples: int, N_importance: int, chunk: int = 4096,
+                         hw: Tuple[int, int], N_samples: int, N_importance: int, chunk: Optional[int] = None,
                          use_disp: bool = False, scheme: str = "stats", group=None, backend=None,
                          camera=None, **kwargs) -> torch.Tensor:
     """Render one H x W frame whose ``rays`` (H*W, 8) are known to every rank; each rank

@@ -30,12 +30,23 @@ class GraphedRenderer:
         self.rays[:, 3:6] = torch.tensor([0.0, 0.0, -1.0], device=dev)
         self.rays[:, 7] = 1.0
 
+        self._models = models
+        self._keys = ["coarse"] + (["fine"] if N_importance > 0 else [])
+        self._dev = dev
+
         def run():
             with torch.no_grad():
                 return render_rays_cross_ray(models, embeddings, self.rays, None, N_samples, use_disp, 0, 0,
                                              N_importance, n_rays, False, test_time=True, **kwargs)
 
-        # warm up on a side stream (weight packing, program tables, allocator) before capture
+        self._run = run
+        self._capture()
+
+    def _capture(self):
+        """(Re)capture.  The graph bakes in the address of each model's packed weight image, so the
+        PackedMLP objects it was captured with are kept alive here and compared on every call."""
+        dev, run = self._dev, self._run
+        # warm up on a side stream (weight packing, allocator) before capture
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         from . import ops
@@ -46,13 +57,25 @@ class GraphedRenderer:
             self.kernels_per_replay = ops.launch_count() - n0   # library kernels inside one replay
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        with torch.no_grad():
+            self._packed = [self._models[k].packed() for k in self._keys]
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.results = run()
+        with torch.no_grad():
+            if any(self._models[k].packed() is not p for k, p in zip(self._keys, self._packed)):
+                raise RuntimeError("the weight image changed during graph capture")
+        self.captures = getattr(self, "captures", 0) + 1
 
     def __call__(self, rays: torch.Tensor, non_blocking: bool = True):
         if rays.shape != self.rays.shape:
             raise ValueError(f"this graph renders batches of {tuple(self.rays.shape)}, got {tuple(rays.shape)}")
+        # weights re-packed since the capture (optimizer step, load_state_dict, invalidate_packed):
+        # the old image may be freed - capture again against the new one
+        with torch.no_grad():        # inference-mode packed(): cached, keyed on the weight version
+            stale = any(self._models[k].packed() is not p for k, p in zip(self._keys, self._packed))
+        if stale:
+            self._capture()
         self.rays.copy_(rays, non_blocking=non_blocking)     # H2D or D2D into the static input
         self.graph.replay()
         return self.results

@@ -71,6 +71,10 @@ class PackedMLP:
     def __init__(self, buf: torch.Tensor, operand: int, e_xyz: int, e_dir: int, status=None):
         self.buf, self.operand, self.e_xyz, self.e_dir = buf, operand, e_xyz, e_dir
         self.status = status     # device int32: 1 if a weight left the operand format's range
+        self._host = self._event = None
+
+    _RANGE_MSG = ("a NeRF weight exceeds the fp16 finite range (|w| > 65504) and was clamped by the "
+                  "packer; pack with operand='bf16' (args.crnerf_operand = 'bf16')")
 
     def check_range(self):
         """Raise if the pack kernel saw a weight outside the fp16 range (host sync on first call)."""
@@ -78,8 +82,24 @@ class PackedMLP:
             bad = int(self.status.item()) != 0
             self.status = None
             if bad:
-                raise CrnerfError("a NeRF weight exceeds the fp16 finite range (|w| > 65504); "
-                                  "pack with operand='bf16'")
+                raise CrnerfError(self._RANGE_MSG)
+
+    def defer_range(self):
+        """Start an asynchronous read-back of the verdict (pinned host word + event): the training
+        step must not synchronise, so the verdict is looked at by ``poll_range`` one step later."""
+        if self.status is not None:
+            self._host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._host.copy_(self.status, non_blocking=True)
+            self._event = torch.cuda.Event()
+            self._event.record(torch.cuda.current_stream(self.buf.device))
+
+    def poll_range(self):
+        """Non-blocking: raise if the deferred verdict has arrived and is bad."""
+        if self._event is not None and self._event.query():
+            bad = int(self._host[0]) != 0
+            self._event = self._host = self.status = None
+            if bad:
+                raise CrnerfError(self._RANGE_MSG)
 
     @property
     def device(self):
@@ -122,7 +142,8 @@ def pack_mlp(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], e_
     del keep
     packed = PackedMLP(buf, op, e_xyz, e_dir, status)
     if check_range == "deferred":
-        return packed            # the caller checks later (training: no host sync per step)
+        packed.defer_range()     # the caller polls later (training: no host sync per step)
+        return packed
     packed.check_range()
     return packed
 
@@ -545,7 +566,8 @@ def relu_bias_grad(g: torch.Tensor, act: Optional[torch.Tensor]) -> torch.Tensor
     dev = g.device
     with torch.cuda.device(dev):
         gb = torch.empty((c,), dtype=torch.float32, device=dev)
-        scratch = torch.empty((16 * 148 * 256,), dtype=torch.float32, device=dev)
+        scratch = torch.empty((int(lib.crnerf_relu_bias_grad_scratch_floats(c)),), dtype=torch.float32,
+                              device=dev)
         check(lib.crnerf_relu_bias_grad(g.data_ptr(), _p(act), n, c, gb.data_ptr(), scratch.data_ptr(),
                                         _stream(dev)))
     return gb

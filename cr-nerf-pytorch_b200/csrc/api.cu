@@ -178,6 +178,10 @@ int crnerf_composite_backward(const float* raw, const float* z_vals, const float
                             d_rgb_pre, d_sigma_pre, (cudaStream_t)stream);
 }
 
+size_t crnerf_relu_bias_grad_scratch_floats(int width) {
+  return (size_t)8 * (size_t)num_sms() * (size_t)(width > 0 ? width : 0);   // one row of partials per block
+}
+
 int crnerf_relu_bias_grad(float* g, const void* act, int64_t n_points, int width, float* gb,
                           float* scratch, void* stream) {
   int rc = device_check();

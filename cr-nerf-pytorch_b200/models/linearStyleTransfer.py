@@ -16,7 +16,7 @@ csrc/encoder.cu, its training forward/backward stays on library ops.
 import torch
 import torch.nn as nn
 
-from crnerf_b200 import ops
+from crnerf_b200 import ops, torch_ops
 from models.nerf_decoder_stylenerf import NeuralRenderer
 
 
@@ -135,6 +135,7 @@ class style_net(nn.Module, _StyleParamsMixin):
         self.decoder = NeuralRenderer(img_size=(args.img_wh[0], args.img_wh[1]),
                                       featmap_size=(args.img_wh[0], args.img_wh[1]),
                                       feat_nc=args.nerf_out_dim, out_dim=3, args_here=args)
+        self._style_args = None
 
     def forward(self, content_feature, style_feature, type=None):
         """content (1,64,H,W), style (1,64,32,32) or None -> rgb (1,3,H,W),
@@ -144,10 +145,16 @@ class style_net(nn.Module, _StyleParamsMixin):
                 return self.decoder(content_feature)
             fused, _ = _mul_layer_torch(self.multi_net, content_feature, style_feature)
             return self.decoder(fused)
-        sw = self._style_ref([("", "")])
+        # torch.ops.crnerf.style_forward (crnerf_b200/torch_ops.py) -> crnerf_style_forward
+        if self._style_args is None:
+            self._style_args = torch_ops.style_params(self)
         if style_feature is None and type == "content":
-            return ops.style_forward(sw, content_feature, None)
-        return ops.style_forward(sw, content_feature, style_feature)
+            return torch.ops.crnerf.style_forward(content_feature, None, self._style_args)
+        return torch.ops.crnerf.style_forward(content_feature, style_feature, self._style_args)
+
+    def _apply(self, fn, *a, **k):
+        self._style_args = None            # .to()/.cuda() may replace the parameter tensors
+        return super()._apply(fn, *a, **k)
 
 
 class encoder_sameoutputsize(nn.Module):

@@ -16,6 +16,23 @@ from torch import nn
 from crnerf_b200 import ops
 
 
+# Process-wide "some optimizer stepped" counter, part of every packed-weight cache key: optimizer
+# steps that write through ``p.data`` leave ``p._version`` untouched (reference utils/__init__.py:33-36
+# offers such optimizers), the global post-step hook sees them all.
+_weights_epoch = [0]
+
+
+def _bump_weights_epoch(optimizer, args, kwargs):
+    _weights_epoch[0] += 1
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_post_hook
+    _reg_post_hook(_bump_weights_epoch)
+except ImportError:      # very old torch: fall back to the documented invalidate_packed()
+    pass
+
+
 class PosEmbedding(nn.Module):
     def __init__(self, max_logscale, N_freqs, logscale=True):
         """x -> (x, sin(2^k x), cos(2^k x), ...), reference models/nerf.py:5-15."""
@@ -75,6 +92,8 @@ class NeRF_sigma(nn.Module):
         self.operand = getattr(args, 'crnerf_operand', 'fp16')
         self._packed = None
         self._packed_key = None
+        self._epoch = 0
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
 
     # -- kernel plumbing ---------------------------------------------------
     def _linears(self):
@@ -90,22 +109,48 @@ class NeRF_sigma(nn.Module):
                 f"D={self.D}, W={self.W}, skips={self.skips}, out_dim={self.out_dim}")
 
     def packed(self):
-        """Tensor-core-ready weight image, re-packed when any parameter changes
-        (optimizer step, load_state_dict, .to(device))."""
+        """Tensor-core-ready weight image.
+
+        Training (``wants_grad()``): re-packed on EVERY call - one 10 us kernel - so no cache key
+        can go stale whatever updated the weights (optimizers that write through ``p.data``, as
+        torch_optimizer's RAdam / Ranger do, never bump ``p._version``).  The fp16 range verdict of
+        the previous image is consumed here without a host sync (``PackedMLP.poll_range``).
+
+        Inference: cached; the key holds every parameter's ``(data_ptr, _version)`` plus two
+        epochs that catch what ``_version`` misses: a process-wide one bumped by a post-step hook
+        on every ``torch.optim.Optimizer`` (any optimizer, any update style) and a per-module one
+        bumped by ``load_state_dict`` / ``.to()`` and by ``invalidate_packed()`` - which is what
+        to call after writing weights by hand through ``.data`` (EMA, weight surgery)."""
         self._check_architecture()
         lin = self._linears()
-        key = (self.operand,) + tuple((m.weight.data_ptr(), m.weight._version, m.bias.data_ptr(),
-                                       m.bias._version) for m in lin)
-        if self._packed is None or key != self._packed_key:
-            # Inference verifies that every weight fits the fp16 operand range (one host sync per
-            # weight version).  Training re-packs after every optimizer step; any host sync there
-            # drains the launch queue once per step, so the verdict is left on the object
-            # (PackedMLP.check_range()) and weights beyond +-65504 are clamped by the packer.
+        training = self.wants_grad()
+        if training:
+            if self._packed is not None:
+                self._packed.poll_range()
             self._packed = ops.pack_mlp([m.weight for m in lin], [m.bias for m in lin],
                                         self.in_channels_xyz, self.in_channels_dir, self.operand,
-                                        check_range="deferred" if self.wants_grad() else True)
+                                        check_range="deferred")
+            self._packed_key = None
+            return self._packed
+        key = (self.operand, _weights_epoch[0], self._epoch) + tuple(
+            (m.weight.data_ptr(), m.weight._version, m.bias.data_ptr(), m.bias._version) for m in lin)
+        if self._packed is None or key != self._packed_key:
+            # inference verifies that every weight fits the fp16 operand range (one host sync per
+            # weight version)
+            self._packed = ops.pack_mlp([m.weight for m in lin], [m.bias for m in lin],
+                                        self.in_channels_xyz, self.in_channels_dir, self.operand,
+                                        check_range=True)
             self._packed_key = key
         return self._packed
+
+    def invalidate_packed(self):
+        """Force a re-pack at the next call (after in-place weight edits that bypass autograd's
+        version counter)."""
+        self._epoch += 1
+
+    def _apply(self, fn, *a, **k):
+        self._epoch += 1
+        return super()._apply(fn, *a, **k)
 
     def wants_grad(self):
         """True when the call must be recorded for autograd (training step)."""

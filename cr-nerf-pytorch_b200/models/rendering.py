@@ -15,6 +15,9 @@ import torch
 
 from crnerf_b200 import autograd as crnerf_autograd
 from crnerf_b200 import ops
+from crnerf_b200 import torch_ops  # noqa: F401  (registers torch.ops.crnerf.*)
+
+_K = torch.ops.crnerf          # the library's kernels as torch operators (crnerf_b200/torch_ops.py)
 
 __all__ = ['render_rays_cross_ray']
 
@@ -29,7 +32,7 @@ def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5):
         u = torch.linspace(0, 1, N_importance, device=bins.device)
     else:
         u = torch.rand(N_rays, N_importance, device=bins.device)
-    return ops.sample_pdf(bins, weights, u, N_importance, eps)
+    return _K.sample_pdf(bins, weights.detach(), u, N_importance, eps)
 
 
 def _n_freqs(embedding):
@@ -79,7 +82,7 @@ def render_rays_cross_ray(models,
     perturb_rand = None
     if perturb > 0:
         perturb_rand = perturb * torch.rand(N_rays, N_samples, device=dev)
-    z_vals = ops.coarse_z(rays, t_steps, perturb_rand, use_disp)
+    z_vals = _K.coarse_z(rays, t_steps, perturb_rand, bool(use_disp))
 
     results = {}
 
@@ -91,7 +94,8 @@ def render_rays_cross_ray(models,
             # training step: same fused kernel, plus saved activations for the backward
             w, f, d = crnerf_autograd.render_pass(model, rays, z, noise, view_dir, n_fx, n_fd)
         else:
-            w, f, d = ops.render_pass(model.packed(), rays, z, noise, view_dir, n_fx, n_fd)
+            pk = model.packed()
+            w, f, d = _K.render_pass(pk.buf, pk.operand, rays, z, noise, view_dir, n_fx, n_fd)
         typ = model.typ
         results[f'weights_{typ}'] = w
         results[f'feature_{typ}'] = f
@@ -108,7 +112,7 @@ def render_rays_cross_ray(models,
             u = torch.rand(N_rays, N_importance, device=dev)
         # sample_pdf on the coarse mid-points with weights_coarse[:,1:-1] (detached),
         # then sort(cat(z, z_new)) - one kernel (rendering.py:183-187)
-        z_fine = ops.sample_pdf_merge(z_vals, w_coarse, u, N_importance)
+        z_fine = _K.sample_pdf_merge(z_vals, w_coarse.detach(), u, N_importance, 1e-5)
         _, f_fine = run(fine, z_fine)
         if kwargs.get('output_random', True) and fine.encode_random:
             results['feature_fine_random'] = f_fine   # same tensor object, as the reference

@@ -123,7 +123,9 @@ int crnerf_composite_backward(const float* raw, const float* z_vals, const float
 /* Backward of a layer's ReLU + bias: g (n_points, width) fp32 is multiplied in place by
  * (act > 0), act being that layer's slice of `acts` (16-bit, same shape; NULL = no activation),
  * and gb (width) receives the column sums = the bias gradient.  width in {64,128,256};
- * scratch: 16*148*256 floats. */
+ * scratch: crnerf_relu_bias_grad_scratch_floats(width) floats (sized from the current device's
+ * SM count). */
+size_t crnerf_relu_bias_grad_scratch_floats(int width);
 int crnerf_relu_bias_grad(float* g, const void* act, int64_t n_points, int width, float* gb,
                           float* scratch, void* stream);
 

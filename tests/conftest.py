@@ -80,6 +80,23 @@ def check_checksums(module, sums):
         assert float(v.sum()) == s and float(v.abs().sum()) == a, f"init drift in {k}"
 
 
+def load_trained():
+    """The trained-like weight set of oracle/make_trained.py loaded into the product's module
+    mirror: NeRF coarse/fine entirely, style_net except its two seeded-default fc layers (whose
+    checksums the fixture carries)."""
+    t = load_golden("trained")
+    models, args = build_mirror_models(t["seed"], False)
+    models["coarse"].load_state_dict(t["coarse"], strict=True)
+    models["fine"].load_state_dict(t["fine"], strict=True)
+    missing, unexpected = models["decoder"].load_state_dict(t["decoder"], strict=False)
+    assert not unexpected and all(k.startswith(("multi_net.snet.fc.", "multi_net.cnet.fc.")) for k in missing)
+    sd = models["decoder"].state_dict()
+    for k, (s, a) in t["checksum_decoder_frozen"].items():
+        v = sd[k].double()
+        assert float(v.sum()) == s and float(v.abs().sum()) == a, f"init drift in {k}"
+    return t, models, args
+
+
 @pytest.fixture(scope="session")
 def mirror_default():
     return build_mirror_models(0, False)

@@ -16,38 +16,26 @@ from crnerf_b200 import synthetic
 import torch.distributed as dist
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--rays", type=int, default=1024)
-    ap.add_argument("--ns", type=int, default=64)
-    ap.add_argument("--ni", type=int, default=64)
-    ap.add_argument("--no-eager", action="store_true")
-    ap.add_argument("--operand", default="fp16", choices=["fp16", "bf16"], help="tensor-core operand format of the MLP")
-    ap.add_argument("--bwd", default="tf32", choices=["tf32", "fp32", "bf16"], help="backward GEMM precision")
-    a = ap.parse_args()
-    import crnerf_oracle as oracle
+def make_step(dev, world, rank, n_rays=1024, ns=64, ni=64, operand="fp16", bwd=None):
+    """Build the models + optimizer and return (step_fn, models, margs, rays, style, target, side)."""
     from bench import build_models
     from models.nerf import PosEmbedding
     from models.rendering import render_rays_cross_ray
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local); dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     from crnerf_b200 import autograd as ag
-    ag.BACKWARD_MATMUL = a.bwd
+    if bwd is not None:
+        ag.BACKWARD_MATMUL = bwd
     models, margs = build_models()
     for k in ("coarse", "fine"):
-        models[k].operand = a.operand
+        models[k].operand = operand
     models = {k: m.to(dev).train() for k, m in models.items()}
     emb = {"xyz": PosEmbedding(14, 15), "dir": PosEmbedding(3, 4)}
-    side = int(a.rays ** 0.5)
+    side = int(n_rays ** 0.5)
     rays = synthetic.pinhole_rays(side, side, synthetic.synthetic_pose(rank)).to(dev)
     style = torch.rand(1, 64, 32, 32, device=dev)
     target = torch.rand(side * side, 3, device=dev)
     params = [p for m in models.values() for p in m.parameters()]
     opt = torch.optim.Adam(params, lr=5e-4)
+    flat_n = sum(p.numel() for p in params)
 
     def allreduce_grads():
         if world > 1:   # what DDP does, as one flat bucket
@@ -58,7 +46,7 @@ def main():
                 p.grad.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
 
     def step_ours():
-        res = render_rays_cross_ray(models, emb, rays, None, a.ns, False, 1.0, 1.0, a.ni, 32768, False, args=margs)
+        res = render_rays_cross_ray(models, emb, rays, None, ns, False, 1.0, 1.0, ni, 32768, False, args=margs)
         loss = 0
         for typ in ("coarse", "fine"):
             feat = res[f"feature_{typ}"].t().reshape(1, 64, side, side)
@@ -70,6 +58,64 @@ def main():
         opt.step()
         return loss
 
+    return step_ours, models, margs, rays, style, target, side, flat_n
+
+
+def measure(dev, world, rank, barrier, reps=10, warm=3, n_rays=1024, ns=64, ni=64):
+    """bench.py's training leg: the step in both operand formats (fp16 = the 1e-4 parity mode,
+    bf16 = the configuration BASELINE configs[4] names), one patch per rank, gradient all-reduce.
+    Device-timed with CUDA events, max over ranks."""
+    from crnerf_b200 import ops
+    out = {}
+    for operand in ("fp16", "bf16"):
+        from crnerf_b200 import autograd as ag
+        default_bwd = getattr(ag, "DEFAULT_BACKWARD_MATMUL", ag.BACKWARD_MATMUL)
+        step, *_rest, flat_n = make_step(dev, world, rank, n_rays, ns, ni, operand,
+                                         default_bwd if (operand == "fp16" or default_bwd == "native") else "bf16")
+        for _ in range(warm):
+            step()
+        barrier()
+        n0 = ops.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            loss = step()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        out[f"train_step_ms_{operand}"] = ms
+        out[f"train_ray_samples_per_s_{operand}"] = world * n_rays * (ns + ni) / (ms * 1e-3)
+        out[f"train_native_launches_per_step_{operand}"] = (ops.launch_count() - n0) / reps
+        out[f"train_loss_{operand}"] = float(loss)
+    out["train"] = {"workload": f"{n_rays}-ray (32x32) patch per rank x ({ns}+{ni}) samples, perturb=1, noise_std=1, "
+                                "style_net decode of coarse and fine, MSE, backward, Adam",
+                    "parallelism": f"data parallel x{world}, one flat gradient all-reduce ({flat_n * 4} B) per step",
+                    "reps": reps, "warmup": warm, "timing": "CUDA events over the reps, max over ranks"}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--rays", type=int, default=1024)
+    ap.add_argument("--ns", type=int, default=64)
+    ap.add_argument("--ni", type=int, default=64)
+    ap.add_argument("--no-eager", action="store_true")
+    ap.add_argument("--operand", default="fp16", choices=["fp16", "bf16"], help="tensor-core operand format of the MLP")
+    ap.add_argument("--bwd", default=None, choices=["native", "tf32", "fp32", "bf16"], help="backward GEMM path")
+    a = ap.parse_args()
+    import crnerf_oracle as oracle
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    step_ours, models, margs, rays, style, target, side, _ = make_step(dev, world, rank, a.rays, a.ns, a.ni,
+                                                                    a.operand, a.bwd)
+    from crnerf_b200 import autograd as ag
     # library baseline: the same math as plain differentiable torch ops on the GPU
     pc = {k: v.detach().clone().requires_grad_(True) for k, v in models["coarse"].state_dict().items()}
     pf = {k: v.detach().clone().requires_grad_(True) for k, v in models["fine"].state_dict().items()}
@@ -105,7 +151,7 @@ def main():
 
     ours_dev, ours_wall, l1 = timeit(step_ours, a.steps)
     out = {"workload": f"train step, {a.rays} rays x ({a.ns}+{a.ni}), perturb=1 noise=1, style_net decode x2, MSE, Adam",
-           "operand": a.operand, "backward_gemm": a.bwd,
+           "operand": a.operand, "backward_gemm": ag.BACKWARD_MATMUL,
            "n_gpus": world, "ours_ms_device": ours_dev, "ours_ms_wall": ours_wall,
            "ours_ray_samples_per_s": world * a.rays * (a.ns + a.ni) / (ours_wall * 1e-3), "loss": l1}
     if not a.no_eager and world == 1:
