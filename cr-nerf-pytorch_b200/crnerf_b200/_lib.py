@@ -22,6 +22,11 @@ class MlpWeights(C.Structure):
                 ("e_xyz", C.c_int32), ("e_dir", C.c_int32)]
 
 
+class RenderOpts(C.Structure):
+    """crnerf_render_opts"""
+    _fields_ = [("xyz_jitter", C.c_void_p), ("channel_partials", C.c_void_p), ("overflow_flag", C.c_void_p)]
+
+
 class CnnWeights(C.Structure):
     """crnerf_cnn_weights"""
     _fields_ = [("conv_w", C.c_void_p * 3), ("conv_b", C.c_void_p * 3),
@@ -48,6 +53,11 @@ SIGNATURES = {
     "crnerf_device_ok": (C.c_int, []),
     "crnerf_launch_count": (C.c_uint64, []),
     "crnerf_mlp_packed_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "crnerf_mlp_packed_bytes_op": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "crnerf_render_partial_rows": (C.c_int, [C.c_int, C.c_int]),
+    "crnerf_render_pass_opts": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.POINTER(RenderOpts), C.c_void_p]),
     "crnerf_mlp_pack": (C.c_int, [C.POINTER(MlpWeights), C.c_int, C.c_void_p, C.c_size_t,
                                   C.c_void_p, C.c_void_p]),
     "crnerf_render_pass": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

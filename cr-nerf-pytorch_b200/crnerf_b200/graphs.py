@@ -76,6 +76,8 @@ class GraphedRenderer:
             stale = any(self._models[k].packed() is not p for k, p in zip(self._keys, self._packed))
         if stale:
             self._capture()
+        for p in self._packed:
+            p.check_overflow()       # fp16 saturation reported by earlier replays (host read, no sync)
         self.rays.copy_(rays, non_blocking=non_blocking)     # H2D or D2D into the static input
         self.graph.replay()
         return self.results

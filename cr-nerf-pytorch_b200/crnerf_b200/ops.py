@@ -17,7 +17,8 @@ from ._lib import CrnerfError, check
 
 OPERAND_FP16 = 0
 OPERAND_BF16 = 1
-_OPERANDS = {"fp16": 0, "bf16": 1, 0: 0, 1: 1}
+OPERAND_FP16X3 = 2      # split precision: hi + lo fp16 operands, three MMAs per product (inference)
+_OPERANDS = {"fp16": 0, "bf16": 1, "fp16x3": 2, 0: 0, 1: 1, 2: 2}
 
 # order of the 12 NeRF_sigma layers in crnerf_mlp_weights (reference state_dict prefixes)
 MLP_LAYER_KEYS = tuple([f"xyz_encoding_{i}.0" for i in range(1, 9)] +
@@ -28,7 +29,7 @@ def operand_id(op) -> int:
     try:
         return _OPERANDS[op]
     except KeyError:
-        raise ValueError(f"unknown operand format {op!r} (use 'fp16' or 'bf16')") from None
+        raise ValueError(f"unknown operand format {op!r} (use 'fp16', 'bf16' or 'fp16x3')") from None
 
 
 def _need(t: torch.Tensor, name: str, dims: Optional[int] = None):
@@ -72,6 +73,32 @@ class PackedMLP:
         self.buf, self.operand, self.e_xyz, self.e_dir = buf, operand, e_xyz, e_dir
         self.status = status     # device int32: 1 if a weight left the operand format's range
         self._host = self._event = None
+        # activation-overflow flag of the fp16 formats: one int32 in pinned host memory that the
+        # render kernels write (zero-copy) when an operand saturates; read without any sync
+        self.overflow = None
+
+    _OVERFLOW_MSG = ("an activation or input reached the fp16 operand limit (|x| >= 65504) in a render pass "
+                     "with these weights and was clamped; the results of that pass are not within tolerance. "
+                     "Use operand='bf16' (args.crnerf_operand = 'bf16'), which has fp32 range")
+
+    def overflow_ptr(self):
+        if self.operand == OPERAND_BF16:
+            return None
+        if self.overflow is None:
+            self.overflow = torch.zeros(1, dtype=torch.int32).pin_memory()
+        return self.overflow.data_ptr()
+
+    def check_overflow(self, sync: bool = False):
+        """Raise if a render pass that used this image saturated an fp16 operand.  Without ``sync``
+        it looks at what has been reported so far (free: a host memory read), so a caller in a
+        loop learns of the problem one call later; ``sync=True`` waits for the device first."""
+        if self.overflow is None:
+            return
+        if sync:
+            torch.cuda.synchronize(self.buf.device)
+        if int(self.overflow[0]) != 0:
+            self.overflow[0] = 0
+            raise CrnerfError(self._OVERFLOW_MSG)
 
     _RANGE_MSG = ("a NeRF weight exceeds the fp16 finite range (|w| > 65504) and was clamped by the "
                   "packer; pack with operand='bf16' (args.crnerf_operand = 'bf16')")
@@ -134,7 +161,7 @@ def pack_mlp(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], e_
         w.weight[i] = wi.data_ptr()
         w.bias[i] = bi.data_ptr()
     w.e_xyz, w.e_dir = e_xyz, e_dir
-    nbytes = lib.crnerf_mlp_packed_bytes(e_xyz, e_dir)
+    nbytes = lib.crnerf_mlp_packed_bytes_op(e_xyz, e_dir, op)
     with torch.cuda.device(dev):
         buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev) if check_range else None
@@ -148,10 +175,18 @@ def pack_mlp(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], e_
     return packed
 
 
+def render_partial_rows(n_rays: int, n_samples: int) -> int:
+    return int(_lib.load().crnerf_render_partial_rows(int(n_rays), int(n_samples)))
+
+
 def render_pass(packed: PackedMLP, rays: torch.Tensor, z_vals: torch.Tensor,
                 noise: Optional[torch.Tensor] = None, view_dir: Optional[torch.Tensor] = None,
-                n_freq_xyz: int = 15, n_freq_dir: int = 4):
-    """One fused pass: embed -> MLP -> composite.  Returns (weights, feature, depth)."""
+                n_freq_xyz: int = 15, n_freq_dir: int = 4, xyz_jitter: Optional[torch.Tensor] = None,
+                want_channel_partials: bool = False, overflow_ptr: Optional[int] = None):
+    """One fused pass: embed -> MLP -> composite.  Returns (weights, feature, depth), plus the
+    (rows, 64) partial channel sums of ``feature`` with ``want_channel_partials`` (their sum over
+    rows is ``feature.sum(0)``: the cross-ray block's mean without another pass over the map).
+    ``xyz_jitter`` (n_rays*n_samples, 3) is added to the sample positions (args.pertubeCord)."""
     lib = _lib.load()
     rays = _c(_need(rays, "rays", 2))
     z_vals = _c(_need(z_vals, "z_vals", 2))
@@ -168,18 +203,29 @@ def render_pass(packed: PackedMLP, rays: torch.Tensor, z_vals: torch.Tensor,
         view_dir = _c(_need(view_dir, "view_dir", 2))
         if view_dir.shape != (n, 3):
             raise ValueError("view_dir must be (n_rays, 3)")
+    if xyz_jitter is not None:
+        xyz_jitter = _c(_need(xyz_jitter, "xyz_jitter", 2))
+        if xyz_jitter.shape != (n * s, 3):
+            raise ValueError(f"xyz_jitter must be ({n * s}, 3)")
+    if overflow_ptr is None:         # the image's own flag; a caller that manages the flag passes it
+        packed.check_overflow()      # what earlier passes with these weights reported (no sync)
+        overflow_ptr = packed.overflow_ptr()
     dev = rays.device
     with torch.cuda.device(dev):
         weights = torch.empty((n, s), dtype=torch.float32, device=dev)
         feature = torch.empty((n, 64), dtype=torch.float32, device=dev)
         depth = torch.empty((n,), dtype=torch.float32, device=dev)
+        partials = None
+        if want_channel_partials:
+            partials = torch.zeros((max(1, render_partial_rows(n, s)), 64), dtype=torch.float32, device=dev)
         if n == 0:
-            return weights, feature, depth
-        check(lib.crnerf_render_pass(packed.buf.data_ptr(), packed.operand, rays.data_ptr(),
-                                     _p(view_dir), z_vals.data_ptr(), _p(noise), n, s, n_freq_xyz,
-                                     n_freq_dir, weights.data_ptr(), feature.data_ptr(),
-                                     depth.data_ptr(), _stream(dev)))
-    return weights, feature, depth
+            return (weights, feature, depth, partials) if want_channel_partials else (weights, feature, depth)
+        opts = _lib.RenderOpts(_p(xyz_jitter), _p(partials), overflow_ptr or None)
+        check(lib.crnerf_render_pass_opts(packed.buf.data_ptr(), packed.operand, rays.data_ptr(),
+                                          _p(view_dir), z_vals.data_ptr(), _p(noise), n, s, n_freq_xyz,
+                                          n_freq_dir, weights.data_ptr(), feature.data_ptr(),
+                                          depth.data_ptr(), C.byref(opts), _stream(dev)))
+    return (weights, feature, depth, partials) if want_channel_partials else (weights, feature, depth)
 
 
 def mlp_forward(packed: PackedMLP, x: torch.Tensor, sigma_only: bool = False) -> torch.Tensor:

@@ -12,8 +12,8 @@ operators, so ``torch.ops.crnerf.render_pass`` & co. are what the reference-shap
 Operator list (reference lines each one replaces are in ``include/crnerf_b200.h``):
 
   coarse_z(rays, t_steps, perturb_rand?, use_disp) -> z
-  render_pass(packed, operand, rays, z_vals, noise?, view_dir?, n_freq_xyz, n_freq_dir)
-      -> (weights, feature, depth)
+  render_pass(packed, operand, rays, z_vals, noise?, view_dir?, n_freq_xyz, n_freq_dir,
+              xyz_jitter?, overflow_ptr, channel_partials) -> (weights, feature, depth, partials)
   sample_pdf(bins, weights, u, n_importance, eps) -> samples
   sample_pdf_merge(z_coarse, weights_coarse, u, n_importance, eps) -> z_fine
   pos_embed(x, n_freqs) -> emb
@@ -57,9 +57,14 @@ def _coarse_z(rays, t_steps, perturb_rand, use_disp):
     return ops.coarse_z(rays, t_steps, perturb_rand, bool(use_disp))
 
 
-def _render_pass(packed, operand, rays, z_vals, noise, view_dir, n_freq_xyz, n_freq_dir):
+def _render_pass(packed, operand, rays, z_vals, noise, view_dir, n_freq_xyz, n_freq_dir, xyz_jitter,
+                 overflow_ptr, channel_partials):
     p = _packed(packed, operand, 3 + 6 * n_freq_xyz, 3 + 6 * n_freq_dir)
-    return ops.render_pass(p, rays, z_vals, noise, view_dir, n_freq_xyz, n_freq_dir)
+    out = ops.render_pass(p, rays, z_vals, noise, view_dir, n_freq_xyz, n_freq_dir, xyz_jitter,
+                          bool(channel_partials), overflow_ptr=int(overflow_ptr))
+    if channel_partials:
+        return out
+    return out + (rays.new_empty((0, 64)),)
 
 
 def _sample_pdf(bins, weights, u, n_importance, eps):
@@ -100,9 +105,12 @@ def _m_coarse_z(rays, t_steps, perturb_rand, use_disp):
     return rays.new_empty((rays.shape[0], t_steps.shape[0]))
 
 
-def _m_render_pass(packed, operand, rays, z_vals, noise, view_dir, n_freq_xyz, n_freq_dir):
+def _m_render_pass(packed, operand, rays, z_vals, noise, view_dir, n_freq_xyz, n_freq_dir, xyz_jitter,
+                   overflow_ptr, channel_partials):
     n, s = z_vals.shape
-    return z_vals.new_empty((n, s)), z_vals.new_empty((n, 64)), z_vals.new_empty((n,))
+    rows = 2 * 148 if channel_partials else 0        # upper bound; the CUDA kernel sizes it per device
+    return (z_vals.new_empty((n, s)), z_vals.new_empty((n, 64)), z_vals.new_empty((n,)),
+            z_vals.new_empty((rows, 64)))
 
 
 def _m_sample_pdf(bins, weights, u, n_importance, eps):
@@ -142,7 +150,8 @@ _OPS = (
     ("coarse_z", "(Tensor rays, Tensor t_steps, Tensor? perturb_rand, bool use_disp) -> Tensor",
      _coarse_z, _m_coarse_z),
     ("render_pass", "(Tensor packed, int operand, Tensor rays, Tensor z_vals, Tensor? noise, Tensor? view_dir, "
-                    "int n_freq_xyz, int n_freq_dir) -> (Tensor, Tensor, Tensor)", _render_pass, _m_render_pass),
+                    "int n_freq_xyz, int n_freq_dir, Tensor? xyz_jitter, int overflow_ptr, bool channel_partials) "
+                    "-> (Tensor, Tensor, Tensor, Tensor)", _render_pass, _m_render_pass),
     ("sample_pdf", "(Tensor bins, Tensor weights, Tensor u, int n_importance, float eps) -> Tensor",
      _sample_pdf, _m_sample_pdf),
     ("sample_pdf_merge", "(Tensor z_coarse, Tensor weights_coarse, Tensor u, int n_importance, float eps) -> Tensor",

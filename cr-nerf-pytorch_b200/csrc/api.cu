@@ -132,7 +132,11 @@ int crnerf_debug_program(int e_xyz, int e_dir, int32_t* out_host, int cap) {
   return debug_program(e_xyz, e_dir, out_host, cap);
 }
 
-size_t crnerf_mlp_packed_bytes(int e_xyz, int e_dir) { return mlp_packed_bytes(e_xyz, e_dir); }
+size_t crnerf_mlp_packed_bytes(int e_xyz, int e_dir) { return mlp_packed_bytes(e_xyz, e_dir, 0); }
+size_t crnerf_mlp_packed_bytes_op(int e_xyz, int e_dir, int operand) {
+  return mlp_packed_bytes(e_xyz, e_dir, operand);
+}
+int crnerf_render_partial_rows(int n_rays, int n_samples) { return render_partial_rows(n_rays, n_samples); }
 
 int crnerf_mlp_pack(const crnerf_mlp_weights* w, int operand, void* packed, size_t packed_bytes,
                     int32_t* status_dev, void* stream) {
@@ -144,14 +148,23 @@ int crnerf_mlp_pack(const crnerf_mlp_weights* w, int operand, void* packed, size
 static int render_pass_impl(const void* packed, int operand, const float* rays, const float* view_dir,
                             const float* z_vals, const float* noise, int n_rays, int n_samples,
                             int n_freq_xyz, int n_freq_dir, float* weights, float* feature,
-                            float* depth, void* acts, float* raw_save, void* stream);
+                            float* depth, void* acts, float* raw_save, const crnerf_render_opts* opts,
+                            void* stream);
 
 int crnerf_render_pass(const void* packed, int operand, const float* rays, const float* view_dir,
                        const float* z_vals, const float* noise, int n_rays, int n_samples,
                        int n_freq_xyz, int n_freq_dir, float* weights, float* feature,
                        float* depth, void* stream) {
   return render_pass_impl(packed, operand, rays, view_dir, z_vals, noise, n_rays, n_samples, n_freq_xyz,
-                          n_freq_dir, weights, feature, depth, nullptr, nullptr, stream);
+                          n_freq_dir, weights, feature, depth, nullptr, nullptr, nullptr, stream);
+}
+
+int crnerf_render_pass_opts(const void* packed, int operand, const float* rays, const float* view_dir,
+                            const float* z_vals, const float* noise, int n_rays, int n_samples,
+                            int n_freq_xyz, int n_freq_dir, float* weights, float* feature,
+                            float* depth, const crnerf_render_opts* opts, void* stream) {
+  return render_pass_impl(packed, operand, rays, view_dir, z_vals, noise, n_rays, n_samples, n_freq_xyz,
+                          n_freq_dir, weights, feature, depth, nullptr, nullptr, opts, stream);
 }
 
 size_t crnerf_render_acts_bytes(int64_t n_points) {
@@ -164,8 +177,9 @@ int crnerf_render_pass_train(const void* packed, int operand, const float* rays,
                              float* depth, void* acts, float* raw, void* stream) {
   CRNERF_REQUIRE(acts && raw, "acts and raw are required (use crnerf_render_pass for inference)");
   CRNERF_REQUIRE((reinterpret_cast<uintptr_t>(acts) & 15) == 0, "acts must be 16-byte aligned");
+  CRNERF_REQUIRE(operand == 0 || operand == 1, "the training forward takes operand 0 (fp16) or 1 (bf16)");
   return render_pass_impl(packed, operand, rays, view_dir, z_vals, noise, n_rays, n_samples, n_freq_xyz,
-                          n_freq_dir, weights, feature, depth, acts, raw, stream);
+                          n_freq_dir, weights, feature, depth, acts, raw, nullptr, stream);
 }
 
 int crnerf_composite_backward(const float* raw, const float* z_vals, const float* noise,
@@ -192,11 +206,12 @@ int crnerf_relu_bias_grad(float* g, const void* act, int64_t n_points, int width
 static int render_pass_impl(const void* packed, int operand, const float* rays, const float* view_dir,
                             const float* z_vals, const float* noise, int n_rays, int n_samples,
                             int n_freq_xyz, int n_freq_dir, float* weights, float* feature,
-                            float* depth, void* acts, float* raw_save, void* stream) {
+                            float* depth, void* acts, float* raw_save, const crnerf_render_opts* opts,
+                            void* stream) {
   int rc = device_check();
   if (rc) return rc;
   CRNERF_REQUIRE(packed && rays && z_vals && weights && feature && depth, "null argument");
-  CRNERF_REQUIRE(operand == 0 || operand == 1, "operand must be 0 (fp16) or 1 (bf16)");
+  CRNERF_REQUIRE(operand >= 0 && operand <= 2, "operand must be 0 (fp16), 1 (bf16) or 2 (fp16x3)");
   CRNERF_REQUIRE(n_rays >= 0, "n_rays must be non-negative");
   CRNERF_REQUIRE(n_samples >= 16 && n_samples <= 4096,
                  "n_samples=%d unsupported (16 <= n_samples <= 4096)", n_samples);
@@ -223,6 +238,11 @@ static int render_pass_impl(const void* packed, int operand, const float* rays, 
   a.depth = depth;
   a.acts = acts;
   a.raw_save = raw_save;
+  if (opts) {
+    a.jitter = opts->xyz_jitter;
+    a.chan_part = opts->channel_partials;
+    a.overflow = opts->overflow_flag;
+  }
   return launch_render(a, (cudaStream_t)stream);
 }
 
@@ -231,7 +251,7 @@ int crnerf_mlp_forward(const void* packed, int operand, int e_xyz, int e_dir, co
   int rc = device_check();
   if (rc) return rc;
   CRNERF_REQUIRE(packed && x && out, "null argument");
-  CRNERF_REQUIRE(operand == 0 || operand == 1, "operand must be 0 (fp16) or 1 (bf16)");
+  CRNERF_REQUIRE(operand >= 0 && operand <= 2, "operand must be 0 (fp16), 1 (bf16) or 2 (fp16x3)");
   CRNERF_REQUIRE(n >= 0, "n must be non-negative");
   CRNERF_REQUIRE(x_stride >= (sigma_only ? e_xyz : e_xyz + e_dir), "x_stride smaller than the row width");
   if (n == 0) return CRNERF_OK;

@@ -36,9 +36,13 @@ struct RenderArgs {
   float* raw;  // (n,65) or (n,1) output of mlp_forward
   void* acts;       // training forward: saved activations (crnerf_render_acts_bytes), or nullptr
   float* raw_save;  // training forward: (n_points, 65), or nullptr
+  const float* jitter;   // optional (n_points, 3) xyz jitter (crnerf_render_opts)
+  float* chan_part;      // optional (render_partial_rows(), 64) per-CTA channel sums of `feature`
+  int32_t* overflow;     // optional fp16 saturation flag
 };
 int launch_render(const RenderArgs& a, cudaStream_t st);
-size_t mlp_packed_bytes(int e_xyz, int e_dir);
+int render_partial_rows(int n_rays, int n_samples);
+size_t mlp_packed_bytes(int e_xyz, int e_dir, int operand);
 int debug_program(int e_xyz, int e_dir, int32_t* out, int cap);
 int mlp_pack(const crnerf_mlp_weights* w, int operand, void* packed, size_t packed_bytes,
              int32_t* status_dev, cudaStream_t st);

@@ -23,8 +23,16 @@
 // weight chunks a standard unit is exactly four 16 KB slabs and the 8-slot ring holds
 // two whole units.)
 //
-// build_program() is the single source of truth; host code runs it once and
-// uploads the tables to __constant__ memory for both kernels.
+// build_program() is the single source of truth.  The host runs it per call (microseconds); the
+// pack kernel receives the tables as a kernel parameter and stores them BEHIND the weight image
+// and the fp32 blob, so every packed buffer carries its own program: the render kernel reads the
+// tables from the buffer it was given - no __constant__ symbol, no upload, no host
+// synchronisation, no state shared between devices, streams or embedding widths.
+//
+// Operand formats (crnerf_operand): 0 fp16, 1 bf16 - one 16-bit image; 2 "fp16x3" - two images,
+// W_hi = fp16(W) and W_lo = fp16(W - W_hi), with activations split the same way in the kernel
+// and every product issued as three MMAs (hi*hi + lo*hi + hi*lo): fp32-class accuracy at three
+// times the tensor work, for weights whose cancellation the 11-bit operands cannot hold to 1e-4.
 #pragma once
 #include <stdint.h>
 
@@ -94,6 +102,16 @@ struct Program {
   int32_t e_xyz, e_dir;
 };
 
+// tables stored behind the blob in every packed buffer (see the header comment)
+struct Tables {
+  Chunk chunks[kMaxChunks];
+  Unit units[kMaxUnits];
+  int32_t n_chunks;
+  int32_t n_units;
+  int32_t image_bytes;
+  int32_t n_images;   // 1, or 2 for the split (fp16x3) format
+};
+
 // fp32 side blob: sigma head weights (256) + sigma bias, then the biases of the 11
 // tensor-core layers in LayerId order (9 x 256, 128, 64).  The kernel stages the whole blob
 // (11 KB) in shared memory: bias reads through L1 miss too often to sit in the epilogue.
@@ -121,6 +139,10 @@ CRNERF_HD inline int layer_out_features(int layer) {
   if (layer == kLRgb) return kOutDim;
   return 1;
 }
+
+constexpr int kNumOperands = 3;
+CRNERF_HD inline int operand_images(int operand) { return operand == 2 ? 2 : 1; }
+CRNERF_HD inline int operand_fmt(int operand) { return operand == 1 ? 1 : 0; }   // 16-bit element format
 
 inline void build_program(int e_xyz, int e_dir, Program* p) {
   int nc = 0, nu = 0, off = 0;

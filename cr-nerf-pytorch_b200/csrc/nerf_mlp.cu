@@ -28,6 +28,16 @@
 // a layer is held in registers until the layer's second half has retired, so A needs no
 // double buffer, and the next layer may start on that half (a_half) while the second is
 // still being packed.
+//
+// Split-precision variant (kSplit, operand "fp16x3"): every operand is x = hi + lo (two fp16
+// values) and every product three MMAs (hi*hi + lo*hi + hi*lo, fp32 accumulate): fp32-class
+// accuracy for trained weights, whose cancellation 11-bit operands cannot hold to 1e-4 (measured:
+// 1-2e-3 on the trained-like set, tests/test_trained_weights.py).  A tile then needs A_hi, A_lo
+// and D in TMEM, so ONE tile is in flight per CTA: stream X only, with the Y stream's columns
+// re-used - TMEM {A_hi: 0-127, D0: 128-255, A_lo: 256-383, D1: 384-511}; the two output halves of
+// a 256-wide layer accumulate in D0 / D1 and are drained together once both have retired (no
+// register staging).  The ring becomes 4 slots x 32 KB (W_hi slab | W_lo slab), the embedding
+// buffers of X / Y hold the embedding's hi / lo parts.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <algorithm>
@@ -38,11 +48,6 @@
 #include "ptx.cuh"
 
 namespace crnerf {
-
-__constant__ Chunk c_chunks[kMaxChunks];
-__constant__ Unit c_units[kMaxUnits];
-// per chunk, for the issuer: a_src | a_k0 << 8 | nk << 16 (one uniform load)
-__constant__ uint32_t c_meta[kMaxChunks];
 
 namespace {
 
@@ -66,11 +71,13 @@ struct Misc {
   uint32_t pipe_turn;  // whose unit goes down the tensor pipe next (even: stream X, odd: Y)
   // the issuers' copy of the program: constant-bank lookups indexed by a run-time value are
   // slow (tens to hundreds of cycles each), shared-memory loads are not
-  //   unit_tab: n | first_of_layer << 8 | (layer == 0) << 9 | standard << 10 | chunk0 << 16 |
-  //             nchunks << 24; "standard" = exactly four full activation slabs
-  //   meta_tab: c_meta
+  //   unit_tab: n | first_of_layer << 8 | (layer == 0) << 9 | standard << 10 | half << 11 |
+  //             chunk0 << 16 | nchunks << 24; "standard" = exactly four full activation slabs
+  //   meta_tab: a_src | a_k0 << 8 | nk << 16 per chunk
+  //   chunk_ob: byte offset in the image | (rows == 64) << 31, for the producer
   uint32_t unit_tab[kMaxUnits];
   uint32_t meta_tab[kMaxChunks];
+  uint32_t chunk_ob[kMaxChunks];
   float scan_p[2][4];
   float scan_d[2][4];
   int scan_f[2][4];
@@ -89,6 +96,11 @@ enum : int { kModeEmbedded = 1, kModeRaw = 2, kModeSigmaOnly = 4 };
 
 struct RenderParams {
   const uint8_t* wimg;
+  const uint8_t* wimg_lo;  // split format: the W_lo image (same layout as wimg)
+  const Tables* tab;       // program tables stored behind the blob in the packed buffer
+  const float* jitter;     // optional (n_points, 3) added to xyz (args.pertubeCord, rendering.py:102-104)
+  float* chan_part;        // optional (2*grid, 64): per (CTA, tile group) sums of the feature rows written
+  int32_t* overflow;       // optional: OR-ed with 1 when an fp16 operand saturated (|x| >= 65504)
   const float* blob;
   const float* rays;
   const float* view_dir;
@@ -173,11 +185,15 @@ __device__ __forceinline__ uint16_t to_operand(float v) {
 }
 
 // element (row, col) of a tile's embedding buffer: two K-major SW128 slabs
-template <int kFmt>
+template <int kFmt, bool kSplit = false>
 __device__ __forceinline__ void emb_put(uint8_t* buf, int row, int col, float v) {
   const uint32_t off = (uint32_t)(col >> 6) * 16384u + sw128_offset(row, (col & 63) >> 3) +
                        (uint32_t)(col & 7) * 2u;
-  *reinterpret_cast<uint16_t*>(buf + off) = to_operand<kFmt>(v);
+  const uint16_t h = to_operand<kFmt>(v);
+  *reinterpret_cast<uint16_t*>(buf + off) = h;
+  if constexpr (kSplit)   // lo part into the second embedding buffer
+    *reinterpret_cast<uint16_t*>(buf + kEmbBufBytes + off) =
+        to_operand<0>(fminf(fmaxf(v, -65504.f), 65504.f) - __half2float(__ushort_as_half(h)));
 }
 
 // ---------------------------------------------------------------------------
@@ -258,40 +274,49 @@ __device__ __forceinline__ float emb_col(const EmbIn& e, int c) {
 }
 // 8*kNChunks consecutive columns -> kNChunks 16-byte stores into the swizzled buffer
 // embedding-column chunks [kSrc0, kSrc0+kNChunks) -> buffer chunks [kDst0, ...)
-template <int kFmt, int kNFreq, int kSrc0, int kDst0, int kNChunks>
+// kSplit: also the lo parts (v - fp16(v)) into the second embedding buffer, kEmbBufBytes further on
+template <int kFmt, int kNFreq, int kSrc0, int kDst0, int kNChunks, bool kSplit = false>
 __device__ __forceinline__ void emb_write(uint8_t* buf, uint32_t row_off, uint32_t row_xor,
                                           const EmbIn& e) {
 #pragma unroll
   for (int m = 0; m < kNChunks; ++m) {
-    uint32_t w[4];
+    uint32_t w[4], wl[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      w[q] = pack2<kFmt, false>(emb_col<kNFreq>(e, 8 * (kSrc0 + m) + 2 * q),
-                                emb_col<kNFreq>(e, 8 * (kSrc0 + m) + 2 * q + 1));
+    for (int q = 0; q < 4; ++q) {
+      const float a = emb_col<kNFreq>(e, 8 * (kSrc0 + m) + 2 * q);
+      const float b = emb_col<kNFreq>(e, 8 * (kSrc0 + m) + 2 * q + 1);
+      w[q] = pack2<kFmt, false>(a, b);
+      if constexpr (kSplit) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+        wl[q] = pack2<0, false>(a - f.x, b - f.y);
+      }
+    }
     const uint32_t cm = kDst0 + m;
     const uint32_t off = (cm >> 3) * 16384u + row_off + (((cm & 7u) << 4) ^ row_xor);
     *reinterpret_cast<uint4*>(buf + off) = make_uint4(w[0], w[1], w[2], w[3]);
+    if constexpr (kSplit)
+      *reinterpret_cast<uint4*>(buf + kEmbBufBytes + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
   }
 }
 // any band count / any magnitude: library sincos, element stores (rare path, kept out of line)
-template <int kFmt>
+template <int kFmt, bool kSplit>
 __device__ __noinline__ void embed3_generic(uint8_t* buf, int row, int col0, int col_end, float v0,
                                             float v1, float v2, int n_freqs) {
   const float v[3] = {v0, v1, v2};
 #pragma unroll
-  for (int i = 0; i < 3; ++i) emb_put<kFmt>(buf, row, col0 + i, v[i]);
+  for (int i = 0; i < 3; ++i) emb_put<kFmt, kSplit>(buf, row, col0 + i, v[i]);
   for (int k = 0; k < n_freqs; ++k) {
     const float sc = __int_as_float((127 + k) << 23);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       float s, c;
       sincosf(v[i] * sc, &s, &c);
-      emb_put<kFmt>(buf, row, col0 + 3 + 6 * k + i, s);
-      emb_put<kFmt>(buf, row, col0 + 6 + 6 * k + i, c);
+      emb_put<kFmt, kSplit>(buf, row, col0 + 3 + 6 * k + i, s);
+      emb_put<kFmt, kSplit>(buf, row, col0 + 6 + 6 * k + i, c);
     }
   }
   for (int c = col0 + 3 + 6 * n_freqs; c < col_end; ++c)
-    emb_put<kFmt>(buf, row, c, 0.f);
+    emb_put<kFmt, kSplit>(buf, row, c, 0.f);
 }
 
 __device__ __forceinline__ float softplus_ref(float x) {
@@ -304,10 +329,39 @@ __device__ __forceinline__ float softplus_ref(float x) {
 // this warp's share of the fp32 sigma-head dot product of the layer-8 activations.
 // epi_stage / epi_flush below combine two slices into a layer-half epilogue.
 
+// fp16 activations beyond 65504 must not saturate silently.  CRNERF_OVF_MODE selects how the
+// epilogue notices (A/B-timed on B200, see profiles/README.md):
+//   2 (default): activations are packed WITHOUT satfinite.  An overflow becomes +inf (post-ReLU)
+//      or +-inf (no activation); inf is sticky through the remaining layers: every unit of the
+//      next layer receives +-inf or NaN, cvt.relu keeps +inf and NaN, and whatever the route, the
+//      rgb head's pre-sigmoid accumulators - fed by every earlier layer through xyz_encoding_final
+//      and dir_encoding - end up non-finite.  The rgb epilogue folds them into one sticky value
+//      (s = fma(a, 0, s): NaN iff some a is inf/NaN; 32 FFMA per thread and tile) and raises
+//      RenderParams::overflow.  (The sigmoid itself would hide it: sigmoid(+-inf) is 1 or 0.)
+//   1: packed with satfinite and a running maximum of the packed words (VIMNMX3.U16x2, one
+//      instruction per four activations): a lane that reaches 0x7bff raises the flag;
+//   0: satfinite, no report (the round-1 behaviour).
+#ifndef CRNERF_OVF_MODE
+#define CRNERF_OVF_MODE 2
+#endif
+constexpr bool kActSat = CRNERF_OVF_MODE != 2;
+template <int kFmt, bool kRelu>
+__device__ __forceinline__ void track_amax(uint32_t& amax, uint32_t w0, uint32_t w1) {
+  if constexpr (kFmt == 0 && CRNERF_OVF_MODE == 1) {
+    if constexpr (kRelu)
+      amax = __vmaxu2(__vmaxu2(amax, w0), w1);   // post-ReLU: sign bits are clear
+    else
+      amax = __vmaxu2(__vmaxu2(amax, w0 & 0x7fff7fffu), w1 & 0x7fff7fffu);
+  }
+}
+__device__ __forceinline__ bool amax_saturated(uint32_t amax) {
+  return (amax & 0xffffu) >= 0x7bffu || (amax >> 16) >= 0x7bffu;
+}
+
 template <int kFmt, bool kRelu, bool kSigma, bool kDbg, int kOff, int kN, int kCols = 32>
 __device__ __forceinline__ void epi_slice32(const uint32_t (&v)[kCols], const float* __restrict__ blob_g,
                                             uint32_t boff, const float* wsig, uint32_t (&out)[kN],
-                                            float& sig_acc, float* dbg) {
+                                            float& sig_acc, float* dbg, uint32_t& amax) {
   // blob_g is the CTA's shared-memory copy of the side blob, boff an element offset
   const float* bias = blob_g + boff;
   // bias: consecutive fp32 values of the side blob in shared memory (same address in every
@@ -332,8 +386,9 @@ __device__ __forceinline__ void epi_slice32(const uint32_t (&v)[kCols], const fl
       sig_acc = fmaf(fmaxf(x2, 0.f), ws.z, sig_acc);
       sig_acc = fmaf(fmaxf(x3, 0.f), ws.w, sig_acc);
     }
-    out[kOff + 2 * j] = pack2<kFmt, kRelu>(x0, x1);
-    out[kOff + 2 * j + 1] = pack2<kFmt, kRelu>(x2, x3);
+    out[kOff + 2 * j] = pack2<kFmt, kRelu, kActSat>(x0, x1);
+    out[kOff + 2 * j + 1] = pack2<kFmt, kRelu, kActSat>(x2, x3);
+    track_amax<kFmt, kRelu>(amax, out[kOff + 2 * j], out[kOff + 2 * j + 1]);
   }
 }
 
@@ -348,7 +403,7 @@ __device__ __forceinline__ void save16(uint4* dst, const uint32_t* w) {
 template <int kFmt, bool kRelu, bool kSigma, bool kDbg, bool kSave>
 __device__ __forceinline__ void epi_stage(uint32_t tD_ch, const float* blob_g, uint32_t boff, const float* wsig_ch,
                                           uint32_t (&staged)[32], float& sig_acc, uint64_t* d_empty,
-                                          float* dbg, bool skip, uint4* asave) {
+                                          float* dbg, bool skip, uint4* asave, uint32_t& amax) {
   if (kDbg && skip) {
     tc_fence_before_sync();
     warp_arrive(d_empty);
@@ -362,9 +417,9 @@ __device__ __forceinline__ void epi_stage(uint32_t tD_ch, const float* blob_g, u
   tmem_ld_wait();
   tc_fence_before_sync();
   warp_arrive(d_empty);  // accumulator drained: the issuer may overwrite it
-  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 32>(va, blob_g, boff, wsig_ch, staged, sig_acc, dbg);
+  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 32>(va, blob_g, boff, wsig_ch, staged, sig_acc, dbg, amax);
   epi_slice32<kFmt, kRelu, kSigma, kDbg, 16, 32>(vb, blob_g, boff + 32u, wsig_ch + 32, staged, sig_acc,
-                                                 dbg ? dbg + 32 : nullptr);
+                                                 dbg ? dbg + 32 : nullptr, amax);
   if constexpr (kSave) {
     if (asave) {
       save16(asave, staged);
@@ -380,7 +435,7 @@ template <int kFmt, bool kRelu, bool kSigma, bool kDbg, bool kDirect, bool kSave
 __device__ __forceinline__ void epi_flush(uint32_t tD_ch, uint32_t tA_ch, const float* blob_g, uint32_t boff,
                                           const float* wsig_ch, const uint32_t (&staged)[32], float& sig_acc,
                                           uint64_t* d_empty, uint64_t* a_full, uint64_t* a_half, float* dbg,
-                                          bool skip, uint4* asave) {
+                                          bool skip, uint4* asave, uint32_t& amax) {
   if (kDbg && skip) {
     tc_fence_before_sync();
     warp_arrive(d_empty);
@@ -394,7 +449,7 @@ __device__ __forceinline__ void epi_flush(uint32_t tD_ch, uint32_t tA_ch, const 
   tmem_ld_x32(tD_ch, va);
   tmem_ld_wait();
   tmem_ld_x32(tD_ch + 32, vb);
-  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 16>(va, blob_g, boff, wsig_ch, out, sig_acc, dbg);
+  epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 16>(va, blob_g, boff, wsig_ch, out, sig_acc, dbg, amax);
   tmem_st_x16p(a_dst, out);
   if constexpr (kSave) {
     if (asave) save16(asave, out);
@@ -410,7 +465,7 @@ __device__ __forceinline__ void epi_flush(uint32_t tD_ch, uint32_t tA_ch, const 
     warp_arrive(a_half);
   }
   epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 16>(vb, blob_g, boff + 32u, wsig_ch + 32, out, sig_acc,
-                                                dbg ? dbg + 32 : nullptr);
+                                                dbg ? dbg + 32 : nullptr, amax);
   tmem_st_x16p(a_dst + 16, out);
   if constexpr (kSave) {
     if (asave) save16(asave + 4, out);
@@ -420,6 +475,57 @@ __device__ __forceinline__ void epi_flush(uint32_t tD_ch, uint32_t tA_ch, const 
   tc_fence_before_sync();
   if constexpr (kDirect) warp_arrive(a_half);
   warp_arrive(a_full);
+}
+
+// Split-precision epilogue of one warp's 64 accumulator columns (one output half of a layer):
+// bias, activation, x = hi + lo with hi = fp16(x), lo = fp16(x - hi); hi goes to A_hi columns
+// [0,32) behind tAh, lo to the same columns of A_lo.  The accumulator is released (d_empty) as soon
+// as both 32-column loads have landed.
+template <bool kRelu, bool kSigma>
+__device__ __forceinline__ void epi_split_half(uint32_t tD_ch, uint32_t tAh, uint32_t tAl, const float* blob_s,
+                                               uint32_t boff, const float* wsig_ch, float& sig_acc,
+                                               uint64_t* d_empty, uint32_t& amax) {
+#pragma unroll
+  for (int sl = 0; sl < 2; ++sl) {
+    uint32_t v[32];
+    tmem_ld_x32(tD_ch + 32u * sl, v);
+    tmem_ld_wait();
+    if (sl == 1) {
+      tc_fence_before_sync();
+      warp_arrive(d_empty);
+    }
+    uint32_t oh[16], ol[16];
+    const float* bias = blob_s + boff + 32u * sl;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 bv = *(reinterpret_cast<const float4*>(bias) + j);
+      float x0 = __uint_as_float(v[4 * j]) + bv.x, x1 = __uint_as_float(v[4 * j + 1]) + bv.y;
+      float x2 = __uint_as_float(v[4 * j + 2]) + bv.z, x3 = __uint_as_float(v[4 * j + 3]) + bv.w;
+      if constexpr (kRelu) {   // x < 0 ? 0 : x keeps NaN (fmaxf would drop it; see CRNERF_OVF_MODE)
+        x0 = x0 < 0.f ? 0.f : x0;
+        x1 = x1 < 0.f ? 0.f : x1;
+        x2 = x2 < 0.f ? 0.f : x2;
+        x3 = x3 < 0.f ? 0.f : x3;
+      }
+      if constexpr (kSigma) {
+        const float4 ws = *reinterpret_cast<const float4*>(wsig_ch + 32 * sl + 4 * j);
+        sig_acc = fmaf(x0, ws.x, sig_acc);
+        sig_acc = fmaf(x1, ws.y, sig_acc);
+        sig_acc = fmaf(x2, ws.z, sig_acc);
+        sig_acc = fmaf(x3, ws.w, sig_acc);
+      }
+      const uint32_t h0 = pack2<0, false, kActSat>(x0, x1), h1 = pack2<0, false, kActSat>(x2, x3);
+      const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0));
+      const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+      oh[2 * j] = h0;
+      oh[2 * j + 1] = h1;
+      ol[2 * j] = pack2<0, false>(x0 - f0.x, x1 - f0.y);
+      ol[2 * j + 1] = pack2<0, false>(x2 - f1.x, x3 - f1.y);
+      track_amax<0, false>(amax, h0, h1);
+    }
+    tmem_st_x16p(tAh + 16u * sl, oh);
+    tmem_st_x16p(tAl + 16u * sl, ol);
+  }
 }
 
 // Column sums over the 32 lanes of a warp for 32 values per lane, by a transposing butterfly:
@@ -447,11 +553,15 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 
 // kVariant: 0 production, 1 debug/profiling instrumentation, 2 training forward (also stores
 // every layer's A-operand activations and the per-point [features | sigma] for the backward)
-template <int kFmt, int kVariant>
+template <int kFmt, int kVariant, bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1)
 render_fused_kernel(const __grid_constant__ RenderParams P) {
   constexpr bool kDbg = kVariant == 1;
   constexpr bool kSave = kVariant == 2;
+  static_assert(!kSplit || (kFmt == 0 && kVariant == 0), "the split format is fp16 hi/lo, inference only");
+  constexpr int kStreams = kSplit ? 1 : 2;          // tiles in flight per CTA
+  constexpr int kRing = kSplit ? 4 : kSlots;        // ring slots (split: 32 KB = W_hi slab | W_lo slab)
+  constexpr int kRingSlot = kSplit ? 2 * kSlotBytes : kSlotBytes;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem + kRingOff;
   uint8_t* emb = smem + kEmbOff;
@@ -463,7 +573,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
   const long long p1 = min(p0 + P.pts_per_cta, P.n_points);
   if (p0 >= p1) return;
   const int n_tiles = (int)((p1 - p0 + 127) >> 7);
-  const int n_pairs = (n_tiles + 1) >> 1;
+  const int n_pairs = (n_tiles + kStreams - 1) / kStreams;   // rounds of kStreams tiles
 
   if (tid == 0) {
     for (int i = 0; i < kSlots; ++i) {
@@ -489,17 +599,22 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
   if (warp == 2) tmem_alloc<512>(&M->tmem_base);
   for (int i = tid; i < kBlobFloats; i += kThreads) blob[i] = P.blob[i];
   for (int i = tid; i < P.n_units; i += kThreads) {
-    const Unit un = c_units[i];
+    const Unit un = P.tab->units[i];
     bool standard = un.nchunks == 4;
     for (int j = 0; standard && j < 4; ++j) {
-      const uint32_t m = c_meta[un.chunk0 + j];  // a_src | a_k0 << 8 | nk << 16 | bias flag 0x80
-      standard = (m & 0xffu) == (uint32_t)kSrcAct && ((m >> 8) & 0xffu) == 4u * j && ((m >> 16) & 0xffu) == 4u;
+      const Chunk c = P.tab->chunks[un.chunk0 + j];
+      standard = c.a_src == kSrcAct && c.a_k0 == 4 * j && c.nk == 4;
     }
     M->unit_tab[i] = (uint32_t)un.n | ((uint32_t)(un.first_of_layer != 0) << 8) |
                      ((uint32_t)(un.layer == 0) << 9) | ((uint32_t)standard << 10) |
-                     ((uint32_t)un.chunk0 << 16) | ((uint32_t)un.nchunks << 24);
+                     ((uint32_t)(un.half != 0) << 11) | ((uint32_t)un.chunk0 << 16) |
+                     ((uint32_t)un.nchunks << 24);
   }
-  for (int i = tid; i < P.n_chunks; i += kThreads) M->meta_tab[i] = c_meta[i];
+  for (int i = tid; i < P.n_chunks; i += kThreads) {
+    const Chunk c = P.tab->chunks[i];
+    M->meta_tab[i] = (uint32_t)c.a_src | ((uint32_t)c.a_k0 << 8) | ((uint32_t)c.nk << 16);
+    M->chunk_ob[i] = (uint32_t)c.offset | (c.rows == 64 ? 0x80000000u : 0u);
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -519,16 +634,18 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       uint32_t g = 0;
       for (int pair = 0; pair < n_pairs; ++pair) {
         for (int c = 0; c < P.n_chunks; ++c, ++g) {
-          const uint32_t slot = g % kSlots, n = g / kSlots;
+          const uint32_t slot = g % kRing, n = g / kRing;
           mbar_wait(&M->ring_empty[slot], (n & 1) ^ 1, 1);
-          const uint32_t bytes = (uint32_t)c_chunks[c].bytes;
+          const uint32_t ob = M->chunk_ob[c];
+          const uint32_t bytes = (ob >> 31) ? 8192u : 16384u, off = ob & 0x7fffffffu;
           if (kDbg && (P.exp & 2)) {
             mbar_arrive(&M->ring_full[slot]);
             continue;
           }
-          mbar_arrive_expect_tx(&M->ring_full[slot], bytes);
-          bulk_g2s_hint(ring + slot * kSlotBytes, P.wimg + c_chunks[c].offset, bytes,
-                        &M->ring_full[slot], pol);
+          mbar_arrive_expect_tx(&M->ring_full[slot], kSplit ? 2u * bytes : bytes);
+          bulk_g2s_hint(ring + slot * kRingSlot, P.wimg + off, bytes, &M->ring_full[slot], pol);
+          if constexpr (kSplit)
+            bulk_g2s_hint(ring + slot * kRingSlot + kSlotBytes, P.wimg_lo + off, bytes, &M->ring_full[slot], pol);
         }
       }
     }
@@ -538,6 +655,74 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
   } else if (warp == 1 || warp == 3) {
     // ------------------------------------------------------------------- issuers
     setmaxnreg_dec<kCtrlRegs>();
+    if constexpr (kSplit) {
+      // ---- split-precision issuer: stream X only (warp 3 idles), table-driven, three MMAs per
+      // k-step: A_hi*W_hi, A_lo*W_hi, A_hi*W_lo.  The two output halves of a 256-wide layer go
+      // to D0 / D1 (stream Y's accumulator columns and barriers), so the issuer runs a whole
+      // layer ahead of the epilogue.  Weight chunks are awaited one by one inside the unit (the
+      // 4-slot ring is smaller than the skip layer's six chunks) and released per chunk.
+      if (warp == 1) {
+        constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO | version | SW128
+        const uint32_t ring_lo = ((smem_u32(ring) & 0x3ffffu) >> 4) | (1u << 16);
+        const uint32_t emb_lo = ((smem_u32(emb) & 0x3ffffu) >> 4) | (1u << 16);
+        auto desc = [](uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; };
+        const uint32_t tAh = tmem, tAl = tmem + 256u;
+        uint32_t ucnt[2] = {0u, 0u}, acount = 0, g_base = 0;
+        for (int pair = 0; pair < n_pairs; ++pair) {
+          for (int u = 0; u < P.n_units; ++u) {
+            const uint32_t ut = M->unit_tab[u];
+            const uint32_t idesc = make_idesc_f16(128, ut & 0xffu, 0);
+            const int chunk0 = (int)((ut >> 16) & 0xffu), nch = (int)(ut >> 24);
+            const uint32_t g0 = g_base + (uint32_t)chunk0;
+            const int acc = (ut >> 11) & 1;                   // output half 1 -> D1
+            const uint32_t tDu = tmem + (acc ? 384u : 128u);
+            if (ut & 0x100u) {
+              if (ut & 0x200u) {
+                mbar_wait(&M->emb_full[0], (uint32_t)pair & 1, 2);
+              } else {
+                mbar_wait(&M->a_full[0], acount & 1, 3);
+                acount++;
+              }
+            }
+            mbar_wait(&M->d_empty[acc], (ucnt[acc] & 1) ^ 1, 4);
+            tc_fence_after_sync();
+            if (elect_one()) {
+              for (int j = 0; j < nch; ++j) {
+                const uint32_t gj = g0 + (uint32_t)j, slot = gj % kRing;
+                mbar_wait(&M->ring_full[slot], (gj / kRing) & 1, 5);
+                tc_fence_after_sync();
+                const uint32_t meta = M->meta_tab[chunk0 + j];
+                const uint32_t bh = ring_lo + slot * (kRingSlot >> 4), bl = bh + (kSlotBytes >> 4);
+                const uint32_t a_k0 = (meta >> 8) & 0xffu;
+                const uint32_t acc0 = j ? 1u : 0u;
+                const int nk = (int)((meta >> 16) & 0xffu);
+                if ((meta & 0x7fu) == (uint32_t)kSrcEmb) {
+                  const uint32_t ah = emb_lo + (a_k0 >> 2) * 1024u + (a_k0 & 3u) * 2u;
+                  const uint32_t al = ah + (kEmbBufBytes >> 4);
+                  for (int k = 0; k < nk; ++k) {
+                    umma_ss(tDu, desc(ah + 2u * k), desc(bh + 2u * k), idesc, k ? 1u : acc0);
+                    umma_ss(tDu, desc(al + 2u * k), desc(bh + 2u * k), idesc, 1u);
+                    umma_ss(tDu, desc(ah + 2u * k), desc(bl + 2u * k), idesc, 1u);
+                  }
+                } else {
+                  for (int k = 0; k < nk; ++k) {
+                    const uint32_t ao = (a_k0 + (uint32_t)k) * 8u;
+                    umma_ts(tDu, tAh + ao, desc(bh + 2u * k), idesc, k ? 1u : acc0);
+                    umma_ts(tDu, tAl + ao, desc(bh + 2u * k), idesc, 1u);
+                    umma_ts(tDu, tAh + ao, desc(bl + 2u * k), idesc, 1u);
+                  }
+                }
+                umma_commit(&M->ring_empty[slot]);
+              }
+              umma_commit(&M->d_full[acc]);
+            }
+            __syncwarp();
+            ucnt[acc]++;
+          }
+          g_base += (uint32_t)P.n_chunks;
+        }
+      }
+    } else {
     // One issuer warp per tile stream (warp 1 -> X, warp 3 -> Y).  The tcgen05 issue
     // queue is only 1-2 instructions deep (measured: tools/umma_probe issue timestamps),
     // so the tensor pipe runs only while some thread is actually issuing; with two
@@ -678,6 +863,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       o[6] = w_lock;
       o[7] = t_burst;  // turn acquired -> unit committed (includes the ring waits inside)
     }
+    }
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue
@@ -692,6 +878,11 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t tA = tmem + (b ? 256u : 0u) + lane_off;
     const uint32_t tD = tmem + (b ? 384u : 128u) + lane_off;
+    // split format: group X works alone; A_lo and D1 live in stream Y's columns
+    const bool active = !kSplit || b == 0;
+    const uint32_t tAl = tmem + 256u + lane_off, tD1 = tmem + 384u + lane_off;
+    uint32_t amax = 0;     // running max of packed fp16 magnitudes (overflow report)
+    float csum = 0.f;      // channel sum of the feature rows this thread wrote (gtid < 64)
     uint8_t* my_emb = emb + b * kEmbBufBytes;
     const bool ray_mode = !(P.mode & kModeEmbedded);
     const bool skip = kDbg && (P.exp & 1);
@@ -699,7 +890,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
     const bool fast_emb = P.n_freq_xyz == 15 && P.n_freq_dir == 4;
     const float* wsig = blob + kSigmaWOff;
     const uint32_t row_off = (uint32_t)row * 128u, row_xor = (uint32_t)(row & 7) << 4;
-    uint32_t ud = 0;
+    uint32_t ud = 0, ud1 = 0;
     const bool prof = kDbg && P.prof != nullptr && blockIdx.x == 0 && gtid == 0;
     long long w_dfull = 0, t_emb = 0, t_comp = 0, t_red = 0, t_stage = 0, t_flush = 0;
     const long long t_start = clock64();
@@ -731,6 +922,11 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
             ex.v[0] = __fadd_rn(r0.x, __fmul_rn(r0.w, z));
             ex.v[1] = __fadd_rn(r0.y, __fmul_rn(r1.x, z));
             ex.v[2] = __fadd_rn(r0.z, __fmul_rn(r1.y, z));
+            if (P.jitter) {   // xyz_ += pertube_ratio * rand (rendering.py:102-104); scaled by the caller
+              ex.v[0] = __fadd_rn(ex.v[0], __ldg(P.jitter + p * 3 + 0));
+              ex.v[1] = __fadd_rn(ex.v[1], __ldg(P.jitter + p * 3 + 1));
+              ex.v[2] = __fadd_rn(ex.v[2], __ldg(P.jitter + p * 3 + 2));
+            }
             if (P.view_dir) {
               ed.v[0] = __ldg(P.view_dir + ray * 3 + 0);
               ed.v[1] = __ldg(P.view_dir + ray * 3 + 1);
@@ -746,38 +942,51 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
           if (fast) {
             emb_prepare(ex);
             if (ch == 0) {
-              emb_write<kFmt, 15, 0, 0, 8>(my_emb, row_off, row_xor, ex);    // columns 0..63
+              emb_write<kFmt, 15, 0, 0, 8, kSplit>(my_emb, row_off, row_xor, ex);    // columns 0..63
             } else {
               emb_prepare(ed);
-              emb_write<kFmt, 15, 8, 8, 4>(my_emb, row_off, row_xor, ex);    // columns 64..95
-              emb_write<kFmt, 4, 0, 12, 4>(my_emb, row_off, row_xor, ed);   // columns 96..127
+              emb_write<kFmt, 15, 8, 8, 4, kSplit>(my_emb, row_off, row_xor, ex);    // columns 64..95
+              emb_write<kFmt, 4, 0, 12, 4, kSplit>(my_emb, row_off, row_xor, ed);   // columns 96..127
             }
           } else if (ch == 0) {
-            embed3_generic<kFmt>(my_emb, row, 0, kDirCol0, ex.v[0], ex.v[1], ex.v[2], P.n_freq_xyz);
+            embed3_generic<kFmt, kSplit>(my_emb, row, 0, kDirCol0, ex.v[0], ex.v[1], ex.v[2], P.n_freq_xyz);
           } else {
-            embed3_generic<kFmt>(my_emb, row, kDirCol0, kEmbCols, ed.v[0], ed.v[1], ed.v[2],
-                                 P.n_freq_dir);
+            embed3_generic<kFmt, kSplit>(my_emb, row, kDirCol0, kEmbCols, ed.v[0], ed.v[1], ed.v[2],
+                                         P.n_freq_dir);
+          }
+          if constexpr (kFmt == 0) {   // a coordinate beyond the fp16 range is clamped by the operand cast
+            if (fmaxf(fmaxf(fabsf(ex.v[0]), fabsf(ex.v[1])), fabsf(ex.v[2])) > 65504.f) amax = 0x7bff7bffu;
           }
         } else {
           const float* xr = P.x + p * P.x_stride;
+          float big = 0.f;
           if (ch == 0) {
-            for (int c = 0; c < P.e_xyz; ++c) emb_put<kFmt>(my_emb, row, c, valid ? __ldg(xr + c) : 0.f);
-            for (int c = P.e_xyz; c < kDirCol0; ++c) emb_put<kFmt>(my_emb, row, c, 0.f);
+            for (int c = 0; c < P.e_xyz; ++c) {
+              const float v = valid ? __ldg(xr + c) : 0.f;
+              big = fmaxf(big, fabsf(v));
+              emb_put<kFmt, kSplit>(my_emb, row, c, v);
+            }
+            for (int c = P.e_xyz; c < kDirCol0; ++c) emb_put<kFmt, kSplit>(my_emb, row, c, 0.f);
           } else {
-            for (int c = 0; c < P.e_dir; ++c)
-              emb_put<kFmt>(my_emb, row, kDirCol0 + c,
-                            (valid && !(P.mode & kModeSigmaOnly)) ? __ldg(xr + P.e_xyz + c) : 0.f);
-            for (int c = kDirCol0 + P.e_dir; c < kEmbCols; ++c) emb_put<kFmt>(my_emb, row, c, 0.f);
+            for (int c = 0; c < P.e_dir; ++c) {
+              const float v = (valid && !(P.mode & kModeSigmaOnly)) ? __ldg(xr + P.e_xyz + c) : 0.f;
+              big = fmaxf(big, fabsf(v));
+              emb_put<kFmt, kSplit>(my_emb, row, kDirCol0 + c, v);
+            }
+            for (int c = kDirCol0 + P.e_dir; c < kEmbCols; ++c) emb_put<kFmt, kSplit>(my_emb, row, c, 0.f);
+          }
+          if constexpr (kFmt == 0) {
+            if (big > 65504.f) amax = 0x7bff7bffu;
           }
         }
       fence_proxy_async_smem();
       warp_arrive(&M->emb_full[b]);
       if (prof) t_emb += clock64() - t_e0;
     };
-    if (b < n_tiles) embed_tile(b);
+    if (active && b < n_tiles) embed_tile(b);
 
-    for (int pair = 0; pair < n_pairs; ++pair) {
-      const int t = 2 * pair + b;
+    for (int pair = 0; active && pair < n_pairs; ++pair) {
+      const int t = kStreams * pair + b;
       if (t >= n_tiles) break;
       const long long tile_p0 = p0 + (long long)t * 128;
       const int nvalid = (int)min((long long)128, p1 - tile_p0);
@@ -799,6 +1008,25 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         timed_wait(d_full, ud & 1, 16, prof, w_dfull);
         ud++;
         tc_fence_after_sync();
+      };
+      // split format: accumulator acc (0: D0, 1: D1) has its own full/empty pair and counter
+      auto wait_d2 = [&](int acc) {
+        mbar_wait(&M->d_full[acc], (acc ? ud1 : ud) & 1, 16);
+        if (acc) ud1++; else ud++;
+        tc_fence_after_sync();
+      };
+      // one 256-wide layer in the split format: both halves have retired -> A_hi / A_lo
+      auto split_layer = [&](auto relu_tag, auto sigma_tag, uint32_t boff) {
+        constexpr bool kR = decltype(relu_tag)::value, kS = decltype(sigma_tag)::value;
+        wait_d2(0);
+        wait_d2(1);
+        epi_split_half<kR, kS>(tD_ch, tA_ch, tAl + 32u * ch, blob, boff, wsig + 64 * ch, sig_acc,
+                               &M->d_empty[0], amax);
+        epi_split_half<kR, kS>(tD1 + 64u * ch, tA_ch + 64u, tAl + 32u * ch + 64u, blob, boff + 128u,
+                               wsig + 128 + 64 * ch, sig_acc, &M->d_empty[1], amax);
+        tmem_st_wait();
+        tc_fence_before_sync();
+        warp_arrive(a_full);
       };
       // debug dump target of (layer, half) for this warp's 64 columns, or nullptr
       auto dbg_at = [&](int layer, int half) -> float* {
@@ -826,17 +1054,22 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
       // registers between a layer's two halves and nothing is indexed at run time.
 #pragma unroll 1
       for (int layer = 0; layer < 7; ++layer) {
-        wait_d();
-        if (prof) t_a = clock64();
         const uint32_t bl = bias_ch + 256u * layer;
-        epi_stage<kFmt, true, false, kDbg, kSave>(tD_ch, blob, bl, wsig, staged, sig_acc, d_empty, dbg_at(layer, 0),
-                                                  skip, save_at(layer, 0));
-        if (prof) t_stage += clock64() - t_a;
-        wait_d();
-        if (prof) t_a = clock64();
-        epi_flush<kFmt, true, false, kDbg, false, kSave>(tD_ch, tA_ch, blob, bl + 128u, wsig, staged, sig_acc,
-                                                         d_empty, a_full, a_half, dbg_at(layer, 1), skip, save_at(layer, 1));
-        if (prof) t_flush += clock64() - t_a;
+        if constexpr (kSplit) {
+          split_layer(std::true_type{}, std::false_type{}, bl);
+        } else {
+          wait_d();
+          if (prof) t_a = clock64();
+          epi_stage<kFmt, true, false, kDbg, kSave>(tD_ch, blob, bl, wsig, staged, sig_acc, d_empty, dbg_at(layer, 0),
+                                                    skip, save_at(layer, 0), amax);
+          if (prof) t_stage += clock64() - t_a;
+          wait_d();
+          if (prof) t_a = clock64();
+          epi_flush<kFmt, true, false, kDbg, false, kSave>(tD_ch, tA_ch, blob, bl + 128u, wsig, staged, sig_acc,
+                                                           d_empty, a_full, a_half, dbg_at(layer, 1), skip,
+                                                           save_at(layer, 1), amax);
+          if (prof) t_flush += clock64() - t_a;
+        }
       }
       // composite inputs of this row, requested now so the loads are long complete when the
       // sigma head is (they sit on this tile's critical path: the composite runs between
@@ -852,17 +1085,21 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         if (P.noise) pre_nz = __ldg(P.noise + p);
       }
       // ---- layer 8: ReLU + this warp's share of the fp32 sigma-head dot product
-      wait_d();
-      if (prof) t_a = clock64();
-      epi_stage<kFmt, true, true, kDbg, kSave>(tD_ch, blob, bias_ch + 256u * 7, wsig + 64 * ch, staged, sig_acc,
-                                               d_empty, dbg_at(7, 0), skip, save_at(7, 0));
-      if (prof) t_stage += clock64() - t_a;
-      wait_d();
-      if (prof) t_a = clock64();
-      epi_flush<kFmt, true, true, kDbg, false, kSave>(tD_ch, tA_ch, blob, bias_ch + 256u * 7 + 128u,
-                                                      wsig + 128 + 64 * ch, staged, sig_acc, d_empty, a_full,
-                                                      a_half, dbg_at(7, 1), skip, save_at(7, 1));
-      if (prof) t_flush += clock64() - t_a;
+      if constexpr (kSplit) {
+        split_layer(std::true_type{}, std::true_type{}, bias_ch + 256u * 7);
+      } else {
+        wait_d();
+        if (prof) t_a = clock64();
+        epi_stage<kFmt, true, true, kDbg, kSave>(tD_ch, blob, bias_ch + 256u * 7, wsig + 64 * ch, staged, sig_acc,
+                                                 d_empty, dbg_at(7, 0), skip, save_at(7, 0), amax);
+        if (prof) t_stage += clock64() - t_a;
+        wait_d();
+        if (prof) t_a = clock64();
+        epi_flush<kFmt, true, true, kDbg, false, kSave>(tD_ch, tA_ch, blob, bias_ch + 256u * 7 + 128u,
+                                                        wsig + 128 + 64 * ch, staged, sig_acc, d_empty, a_full,
+                                                        a_half, dbg_at(7, 1), skip, save_at(7, 1), amax);
+        if (prof) t_flush += clock64() - t_a;
+      }
       {
         const long long t_c0 = prof ? clock64() : 0;
         // ---------------- sigma head + alpha composite (rendering.py:121-143), done by
@@ -911,11 +1148,17 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
             // carry of the ray that straddles the previous tile boundary
             float cin_T = 1.f, cin_d = 0.f;
             if (t > 0) {
-              const uint32_t par = b ? (uint32_t)(pair & 1) : (uint32_t)((pair - 1) & 1);
-              mbar_wait(&M->carry_a[1 - b], par, 40);
+              // the previous tile belongs to the other group - or, in the split format, to this
+              // group's previous iteration (ordered by the barriers in between)
+              constexpr int kPrevOther = kSplit ? 0 : 1;
+              const int pb = kPrevOther ? 1 - b : b;
+              if constexpr (!kSplit) {
+                const uint32_t par = b ? (uint32_t)(pair & 1) : (uint32_t)((pair - 1) & 1);
+                mbar_wait(&M->carry_a[pb], par, 40);
+              }
               if (s_first != 0) {
-                cin_T = M->carry_T[1 - b];
-                cin_d = M->carry_depth[1 - b];
+                cin_T = M->carry_T[pb];
+                cin_d = M->carry_depth[pb];
               }
             }
             float pre = cin_T;
@@ -956,25 +1199,39 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         if (prof) t_comp += clock64() - t_c0;
       }
       // ---- xyz_encoding_final: no activation
-      wait_d();
-      if (prof) t_a = clock64();
-      epi_stage<kFmt, false, false, kDbg, kSave>(tD_ch, blob, bias_ch + 256u * kLFinal, wsig, staged, sig_acc,
-                                                 d_empty, dbg_at(kLFinal, 0), skip, save_at(kLFinal, 0));
-      if (prof) t_stage += clock64() - t_a;
-      wait_d();
-      if (prof) t_a = clock64();
-      epi_flush<kFmt, false, false, kDbg, false, kSave>(tD_ch, tA_ch, blob, bias_ch + 256u * kLFinal + 128u, wsig,
-                                                        staged, sig_acc, d_empty, a_full, a_half, dbg_at(kLFinal, 1), skip,
-                                                        save_at(kLFinal, 1));
-      if (prof) t_flush += clock64() - t_a;
-      // ---- dir layer (128 wide, ReLU): straight to A columns [0,64)
-      wait_d();
-      if (prof) t_a = clock64();
-      epi_flush<kFmt, true, false, kDbg, true, kSave>(tD_ch, tA_ch, blob, bias_ch + 256u * 9, wsig, staged, sig_acc,
-                                                      d_empty, a_full, a_half, dbg_at(kLDir, 0), skip, save_at(kLDir, 0));
-      if (prof) t_flush += clock64() - t_a;
-      // ---- rgb layer
-      wait_d();
+      if constexpr (kSplit) {
+        split_layer(std::false_type{}, std::false_type{}, bias_ch + 256u * kLFinal);
+        // ---- dir layer (128 wide, ReLU, one accumulator): A columns [0,64), hi and lo
+        wait_d2(0);
+        epi_split_half<true, false>(tD_ch, tA_ch, tAl + 32u * ch, blob, bias_ch + 256u * 9, wsig, sig_acc,
+                                    &M->d_empty[0], amax);
+        tmem_st_wait();
+        tc_fence_before_sync();
+        warp_arrive(a_full);
+        // ---- rgb layer
+        wait_d2(0);
+      } else {
+        wait_d();
+        if (prof) t_a = clock64();
+        epi_stage<kFmt, false, false, kDbg, kSave>(tD_ch, blob, bias_ch + 256u * kLFinal, wsig, staged, sig_acc,
+                                                   d_empty, dbg_at(kLFinal, 0), skip, save_at(kLFinal, 0), amax);
+        if (prof) t_stage += clock64() - t_a;
+        wait_d();
+        if (prof) t_a = clock64();
+        epi_flush<kFmt, false, false, kDbg, false, kSave>(tD_ch, tA_ch, blob, bias_ch + 256u * kLFinal + 128u, wsig,
+                                                          staged, sig_acc, d_empty, a_full, a_half, dbg_at(kLFinal, 1),
+                                                          skip, save_at(kLFinal, 1), amax);
+        if (prof) t_flush += clock64() - t_a;
+        // ---- dir layer (128 wide, ReLU): straight to A columns [0,64)
+        wait_d();
+        if (prof) t_a = clock64();
+        epi_flush<kFmt, true, false, kDbg, true, kSave>(tD_ch, tA_ch, blob, bias_ch + 256u * 9, wsig, staged, sig_acc,
+                                                        d_empty, a_full, a_half, dbg_at(kLDir, 0), skip,
+                                                        save_at(kLDir, 0), amax);
+        if (prof) t_flush += clock64() - t_a;
+        // ---- rgb layer
+        wait_d();
+      }
       {
         float* dbg_row = nullptr;
         if constexpr (kDbg) {
@@ -989,6 +1246,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         }
         uint32_t v[32];
         float wf[32];
+        float sticky = 0.f;     // NaN once any rgb pre-activation is inf / NaN (fp16 operand overflow upstream)
         if (!skip) {
           tmem_ld_x32(tD + 32 * ch, v);
           tmem_ld_wait();
@@ -1002,6 +1260,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         for (int j = 0; j < 32; ++j) {
           const int chn = 32 * ch + j;
           const float a = __uint_as_float(v[j]) + blob[bias_offset(kLRgb) + chn];
+          if constexpr (kFmt == 0 && CRNERF_OVF_MODE == 2) sticky = fmaf(a, 0.f, sticky);
           const float f = __fdividef(1.f, 1.f + __expf(-a));
           if constexpr (kSave) {
             if (P.raw_save != nullptr && valid) P.raw_save[p * 65 + chn] = f;
@@ -1021,6 +1280,9 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
             else
               P.raw[p * 65 + 64] = sigma;
           }
+        }
+        if constexpr (kFmt == 0 && CRNERF_OVF_MODE == 2) {
+          if (sticky != sticky) amax = 0x7bff7bffu;
         }
         const int n_seg = (s_first + nvalid + P.S - 1) / P.S;
         const long long t_r0 = prof ? clock64() : 0;
@@ -1042,34 +1304,48 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         }
         if (prof) t_red += clock64() - t_r0;
         // next tile of this stream: its embedding goes out before the cross-warp combine
-        if (t + 2 < n_tiles) embed_tile(t + 2);
+        if (t + kStreams < n_tiles) embed_tile(t + kStreams);
         if (!raw_mode) {
           const long long t_r1 = prof ? clock64() : 0;
           const int cc = gtid & 63, hh = gtid >> 6;  // channel, row quarter
           group_sync(b);
           if (hh == 0) {
-            if (t > 0) {
-              const uint32_t par = b ? (uint32_t)(pair & 1) : (uint32_t)((pair - 1) & 1);
-              mbar_wait(&M->carry_b[1 - b], par, 41);
+            if constexpr (!kSplit) {
+              if (t > 0) {
+                const uint32_t par = b ? (uint32_t)(pair & 1) : (uint32_t)((pair - 1) & 1);
+                mbar_wait(&M->carry_b[1 - b], par, 41);
+              }
             }
             float carry_out = 0.f;
             for (int sg = 0; sg < n_seg; ++sg) {
-              float tot = (sg == 0 && s_first != 0) ? M->carry_feat[1 - b][cc] : 0.f;
+              float tot = (sg == 0 && s_first != 0) ? M->carry_feat[kSplit ? b : 1 - b][cc] : 0.f;
               tot += M->part[b][0][sg][cc];
               tot += M->part[b][1][sg][cc];
               tot += M->part[b][2][sg][cc];
               tot += M->part[b][3][sg][cc];
               const bool ends = ((sg + 1) * P.S - s_first) <= nvalid;
-              if (ends)
+              if (ends) {
                 P.feature[(ray_first + sg) * 64 + cc] = tot;
-              else
+                csum += tot;
+              } else {
                 carry_out = tot;
+              }
             }
             M->carry_feat[b][cc] = carry_out;
             warp_arrive(&M->carry_b[b]);
           }
           if (prof) t_red += clock64() - t_r1;
         }
+      }
+    }
+    // per (CTA, tile group) sums of the feature rows written above: the cross-ray block's channel
+    // mean (linearStyleTransfer.py:62) rides on this kernel instead of a pass over the feature map
+    if (P.chan_part != nullptr && gtid < 64) P.chan_part[((size_t)blockIdx.x * 2 + b) * 64 + gtid] = csum;
+    if constexpr (kFmt == 0) {
+      // the flag may live in mapped pinned host memory: every writer stores the same 1
+      if (P.overflow != nullptr && __any_sync(0xffffffffu, amax_saturated(amax)) && lane == 0) {
+        *reinterpret_cast<volatile int32_t*>(P.overflow) = 1;
+        __threadfence_system();
       }
     }
     if (prof) {
@@ -1096,26 +1372,30 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
 struct PackParams {
   const float* w[12];
   const float* b[12];
-  uint8_t* img;
+  uint8_t* img;      // W (or W_hi) image
+  uint8_t* img_lo;   // split format: W_lo image, else nullptr
   float* blob;
+  Tables* tab_out;   // where the tables are stored in the packed buffer
   int32_t* status;
-  int e_xyz, e_dir, n_chunks, image_bytes, fmt;
+  int e_xyz, e_dir, fmt;
+  Tables tab;        // the program, by value (constant bank): nothing to upload
 };
+static_assert(sizeof(PackParams) <= 4096, "kernel parameter space");
 
 __global__ void pack_kernel(const __grid_constant__ PackParams P) {
-  const int total16 = P.image_bytes / 16;
+  const int total16 = P.tab.image_bytes / 16;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total16; i += gridDim.x * blockDim.x) {
     const int byte = i * 16;
     int ci = 0;
-    while (ci + 1 < P.n_chunks && c_chunks[ci + 1].offset <= byte) ++ci;
-    const Chunk ch = c_chunks[ci];
+    while (ci + 1 < P.tab.n_chunks && P.tab.chunks[ci + 1].offset <= byte) ++ci;
+    const Chunk ch = P.tab.chunks[ci];
     const int within = byte - ch.offset;
     const int row = within >> 7;
     const int pos = (within & 127) >> 4;
     const int k0 = ((pos ^ (row & 7)) & 7) * 8;
     const int in_f = layer_in_features(ch.layer, P.e_xyz, P.e_dir);
     const float* wrow = P.w[ch.layer] + (long long)(ch.row0 + row) * in_f + ch.wcol0;
-    uint32_t out[4];
+    uint32_t out[4], out_lo[4];
     bool over = false;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -1124,12 +1404,17 @@ __global__ void pack_kernel(const __grid_constant__ PackParams P) {
       if (P.fmt == 0) {
         over |= fabsf(v0) > 65504.f || fabsf(v1) > 65504.f;
         out[e] = pack2<0, false>(v0, v1);
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&out[e]));
+        out_lo[e] = pack2<0, false>(v0 - f.x, v1 - f.y);   // used by the split format only
       } else {
         out[e] = pack2<1, false>(v0, v1);
+        out_lo[e] = 0u;
       }
     }
     if (over && P.status) atomicExch(P.status, 1);
     *reinterpret_cast<uint4*>(P.img + byte) = make_uint4(out[0], out[1], out[2], out[3]);
+    if (P.img_lo)
+      *reinterpret_cast<uint4*>(P.img_lo + byte) = make_uint4(out_lo[0], out_lo[1], out_lo[2], out_lo[3]);
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kBlobFloats; i += gridDim.x * blockDim.x) {
     float v = 0.f;
@@ -1144,94 +1429,70 @@ __global__ void pack_kernel(const __grid_constant__ PackParams P) {
     }
     P.blob[i] = v;
   }
+  // the program tables travel with the image
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&P.tab);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(P.tab_out);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)(sizeof(Tables) / 4); i += gridDim.x * blockDim.x)
+    dst[i] = src[i];
 }
 
-// program tables live in __constant__ memory of this TU; upload once per
-// (device, e_xyz, e_dir) and re-upload when the embedding widths change.
-std::mutex g_prog_mu;
-int g_prog_dev = -1, g_prog_exyz = -1, g_prog_edir = -1;
-Program g_prog;
-
-int ensure_program(int e_xyz, int e_dir, cudaStream_t st, const Program** out) {
+// packed buffer: [W image][W_lo image (split format)][fp32 blob][tables]
+struct PackedLayout {
+  size_t img_lo, blob, tab, total;
+};
+int make_layout(int e_xyz, int e_dir, int operand, Program* prog, PackedLayout* L) {
   CRNERF_REQUIRE(e_xyz >= 3 && e_xyz <= kMaxExyz && e_dir >= 0 && e_dir <= kMaxEdir,
                  "embedding widths out of range: e_xyz=%d (<=96), e_dir=%d (<=32)", e_xyz, e_dir);
-  int dev = 0;
-  CRNERF_CUDA(cudaGetDevice(&dev));
-  std::lock_guard<std::mutex> lk(g_prog_mu);
-  if (dev != g_prog_dev || e_xyz != g_prog_exyz || e_dir != g_prog_edir) {
-    build_program(e_xyz, e_dir, &g_prog);
-    // stream-ordered so that kernels already queued keep the tables they were launched with
-    CRNERF_CUDA(cudaMemcpyToSymbolAsync(c_chunks, g_prog.chunks, sizeof(Chunk) * kMaxChunks, 0,
-                                        cudaMemcpyHostToDevice, st));
-    CRNERF_CUDA(cudaMemcpyToSymbolAsync(c_units, g_prog.units, sizeof(Unit) * kMaxUnits, 0,
-                                        cudaMemcpyHostToDevice, st));
-    static uint32_t meta[kMaxChunks];
-    for (int i = 0; i < kMaxChunks; ++i)
-      meta[i] = i < g_prog.n_chunks ? ((uint32_t)g_prog.chunks[i].a_src | ((uint32_t)g_prog.chunks[i].a_k0 << 8) |
-                                       ((uint32_t)g_prog.chunks[i].nk << 16))
-                                    : 0u;
-    // mark the first chunk of each run of full activation slabs inside a unit (bits 24+: run length 4 or 2)
-    for (int u = 0; u < g_prog.n_units; ++u) {
-      const Unit& un = g_prog.units[u];
-      int j = 0;
-      while (j < un.nchunks) {
-        int run = 0;
-        while (j + run < un.nchunks && g_prog.chunks[un.chunk0 + j + run].a_src == kSrcAct &&
-               g_prog.chunks[un.chunk0 + j + run].nk == 4)
-          ++run;
-        const int take = run >= 4 ? 4 : (run >= 2 ? 2 : 0);
-        if (take) {
-          meta[un.chunk0 + j] |= (uint32_t)take << 24;
-          j += take;
-        } else {
-          ++j;
-        }
-      }
-    }
-    CRNERF_CUDA(cudaMemcpyToSymbolAsync(c_meta, meta, sizeof(meta), 0, cudaMemcpyHostToDevice, st));
-    // the tables are read by every later launch on any stream of this device
-    CRNERF_CUDA(cudaStreamSynchronize(st));
-    g_prog_dev = dev;
-    g_prog_exyz = e_xyz;
-    g_prog_edir = e_dir;
-  }
-  *out = &g_prog;
+  CRNERF_REQUIRE(operand >= 0 && operand < kNumOperands, "operand must be 0 (fp16), 1 (bf16) or 2 (fp16x3)");
+  build_program(e_xyz, e_dir, prog);
+  const int n_img = operand_images(operand);
+  L->img_lo = n_img == 2 ? (size_t)prog->image_bytes : 0;
+  L->blob = (size_t)n_img * prog->image_bytes;
+  L->tab = L->blob + sizeof(float) * kBlobFloats;
+  L->total = L->tab + sizeof(Tables);
   return CRNERF_OK;
 }
 
 }  // namespace
 
-size_t mlp_packed_bytes(int e_xyz, int e_dir) {
+size_t mlp_packed_bytes(int e_xyz, int e_dir, int operand) {
   Program p;
-  build_program(e_xyz, e_dir, &p);
-  return (size_t)p.image_bytes + sizeof(float) * kBlobFloats;
+  PackedLayout L;
+  if (make_layout(e_xyz, e_dir, operand, &p, &L)) return 0;
+  return L.total;
 }
 
 int mlp_pack(const crnerf_mlp_weights* w, int operand, void* packed, size_t packed_bytes,
              int32_t* status_dev, cudaStream_t st) {
   CRNERF_REQUIRE(w && packed, "null argument");
-  CRNERF_REQUIRE(operand == 0 || operand == 1, "operand must be 0 (fp16) or 1 (bf16)");
   for (int i = 0; i < 12; ++i)
     CRNERF_REQUIRE(w->weight[i] && w->bias[i], "weight/bias pointer %d is null", i);
-  const Program* prog;
-  int rc = ensure_program(w->e_xyz, w->e_dir, st, &prog);
+  Program prog;
+  PackedLayout L;
+  int rc = make_layout(w->e_xyz, w->e_dir, operand, &prog, &L);
   if (rc) return rc;
-  const size_t need = (size_t)prog->image_bytes + sizeof(float) * kBlobFloats;
-  CRNERF_REQUIRE(packed_bytes >= need, "packed buffer too small: %zu < %zu", packed_bytes, need);
+  CRNERF_REQUIRE(packed_bytes >= L.total, "packed buffer too small: %zu < %zu", packed_bytes, L.total);
   CRNERF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "packed buffer must be 16-byte aligned");
   PackParams P;
+  memset(&P, 0, sizeof(P));
   for (int i = 0; i < 12; ++i) {
     P.w[i] = w->weight[i];
     P.b[i] = w->bias[i];
   }
   P.img = static_cast<uint8_t*>(packed);
-  P.blob = reinterpret_cast<float*>(P.img + prog->image_bytes);
+  P.img_lo = L.img_lo ? P.img + L.img_lo : nullptr;
+  P.blob = reinterpret_cast<float*>(P.img + L.blob);
+  P.tab_out = reinterpret_cast<Tables*>(P.img + L.tab);
   P.status = status_dev;
   P.e_xyz = w->e_xyz;
   P.e_dir = w->e_dir;
-  P.n_chunks = prog->n_chunks;
-  P.image_bytes = prog->image_bytes;
-  P.fmt = operand;
+  P.fmt = operand_fmt(operand);
+  memcpy(P.tab.chunks, prog.chunks, sizeof(prog.chunks));
+  memcpy(P.tab.units, prog.units, sizeof(prog.units));
+  P.tab.n_chunks = prog.n_chunks;
+  P.tab.n_units = prog.n_units;
+  P.tab.image_bytes = prog.image_bytes;
+  P.tab.n_images = operand_images(operand);
   if (status_dev) CRNERF_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int32_t), st));
   pack_kernel<<<148, 256, 0, st>>>(P);
   count_launch();
@@ -1265,15 +1526,37 @@ int debug_program(int e_xyz, int e_dir, int32_t* out, int cap) {
 
 static int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
 
+// work split of a ray batch: whole rays per CTA, a multiple of the rays that fill whole tiles
+static int ray_grid(int n_rays, int S, long long* pts_per_cta) {
+  const int sms = num_sms();
+  const int m = 128 / gcd_int(S, 128);  // rays per whole number of tiles
+  long long rpc = ((long long)n_rays + sms - 1) / sms;
+  if (rpc < 1) rpc = 1;
+  if (rpc >= 2 * m) rpc = (rpc + m - 1) / m * m;
+  if (pts_per_cta) *pts_per_cta = rpc * S;
+  return (int)((n_rays + rpc - 1) / rpc);
+}
+
+int render_partial_rows(int n_rays, int n_samples) {
+  if (n_rays <= 0 || n_samples <= 0) return 0;
+  return 2 * ray_grid(n_rays, n_samples, nullptr);
+}
+
 int launch_render(const RenderArgs& a, cudaStream_t st) {
   const int operand = a.operand, e_xyz = a.e_xyz, e_dir = a.e_dir;
-  const Program* prog;
-  int rc = ensure_program(e_xyz, e_dir, st, &prog);
+  Program prog;
+  PackedLayout L;
+  int rc = make_layout(e_xyz, e_dir, operand, &prog, &L);
   if (rc) return rc;
   RenderParams P;
   memset(&P, 0, sizeof(P));
   P.wimg = static_cast<const uint8_t*>(a.packed);
-  P.blob = reinterpret_cast<const float*>(P.wimg + prog->image_bytes);
+  P.wimg_lo = L.img_lo ? P.wimg + L.img_lo : nullptr;
+  P.blob = reinterpret_cast<const float*>(P.wimg + L.blob);
+  P.tab = reinterpret_cast<const Tables*>(P.wimg + L.tab);
+  P.jitter = a.jitter;
+  P.chan_part = a.chan_part;
+  P.overflow = a.overflow;
   P.rays = a.rays;
   P.view_dir = a.view_dir;
   P.z_vals = a.z_vals;
@@ -1294,8 +1577,8 @@ int launch_render(const RenderArgs& a, cudaStream_t st) {
   P.n_freq_dir = a.n_freq_dir;
   P.e_xyz = e_xyz;
   P.e_dir = e_dir;
-  P.n_chunks = prog->n_chunks;
-  P.n_units = prog->n_units;
+  P.n_chunks = prog.n_chunks;
+  P.n_units = prog.n_units;
   const int sms = num_sms();
   int grid;
   if (a.x) {
@@ -1307,20 +1590,21 @@ int launch_render(const RenderArgs& a, cudaStream_t st) {
     grid = (int)((tiles + tpc - 1) / tpc);
   } else {
     P.mode = 0;
-    const int S = a.n_samples;
-    const int m = 128 / gcd_int(S, 128);  // rays per whole number of tiles
-    long long rpc = (a.n_rays + sms - 1) / sms;
-    if (rpc >= 2 * m) rpc = (rpc + m - 1) / m * m;
-    P.pts_per_cta = rpc * S;
-    grid = (int)((a.n_rays + rpc - 1) / rpc);
+    grid = ray_grid(a.n_rays, a.n_samples, &P.pts_per_cta);
   }
   P.acts = static_cast<uint16_t*>(a.acts);
   P.raw_save = a.raw_save;
   const bool dbg = P.dbg != nullptr || P.prof != nullptr;
   const bool save = !dbg && (a.acts != nullptr || a.raw_save != nullptr);
-  auto kern = operand == 0
-                  ? (dbg ? render_fused_kernel<0, 1> : (save ? render_fused_kernel<0, 2> : render_fused_kernel<0, 0>))
-                  : (dbg ? render_fused_kernel<1, 1> : (save ? render_fused_kernel<1, 2> : render_fused_kernel<1, 0>));
+  void (*kern)(const RenderParams);
+  if (operand == 2) {
+    CRNERF_REQUIRE(!dbg && !save, "the fp16x3 operand format is inference only (no activation dump / saved activations)");
+    kern = render_fused_kernel<0, 0, true>;
+  } else if (operand == 0) {
+    kern = dbg ? render_fused_kernel<0, 1, false> : (save ? render_fused_kernel<0, 2, false> : render_fused_kernel<0, 0, false>);
+  } else {
+    kern = dbg ? render_fused_kernel<1, 1, false> : (save ? render_fused_kernel<1, 2, false> : render_fused_kernel<1, 0, false>);
+  }
   CRNERF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   kern<<<grid, kThreads, kSmemBytes, st>>>(P);
   count_launch();

@@ -295,11 +295,18 @@ __device__ __forceinline__ void tmem_st_wait() {
 // (lo, hi) fp32 -> packed 16-bit pair {hi: bits 31..16, lo: bits 15..0}, round
 // to nearest even, clamp to the finite range, optional fused ReLU.
 // kFmt: 0 = fp16, 1 = bf16.
-template <int kFmt, bool kRelu>
+// kSat = false (fp16 only): no clamp - a value beyond 65504 becomes inf and poisons everything
+// downstream, which is how the render kernel notices it (see RenderParams::overflow).
+template <int kFmt, bool kRelu, bool kSat = true>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   uint32_t r;
   if constexpr (kFmt == 0) {
-    if constexpr (kRelu)
+    if constexpr (!kSat) {
+      if constexpr (kRelu)
+        asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+      else
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    } else if constexpr (kRelu)
       asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     else
       asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));

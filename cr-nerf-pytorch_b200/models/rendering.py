@@ -59,14 +59,14 @@ def render_rays_cross_ray(models,
     the models' parameters (crnerf_b200/autograd.py) when called with gradients enabled.  ``ts``, ``chunk``,
     ``white_back`` and ``test_time`` are accepted and unused, as in the reference
     (point chunking is unnecessary because no per-point tensor is
-    materialised).  Returns ``weights_{typ} (N,S)``, ``feature_{typ} (N,64)``,
+    materialised).  ``args.pertubeCord`` (:102-104) is honoured in inference.  One extension:
+    ``channel_sums=True`` adds ``chansum_{typ}``, partial column sums of ``feature_{typ}`` that
+    the cross-ray block uses instead of a pass over the feature map.  Returns ``weights_{typ} (N,S)``, ``feature_{typ} (N,64)``,
     ``depth_{typ} (N,)`` for the coarse model and, if ``N_importance > 0``, the
     fine model, plus the ``feature_fine_random`` alias (rendering.py:140-141).
     """
     args = kwargs['args']
-    if getattr(args, 'pertubeCord', False):
-        raise NotImplementedError("args.pertubeCord (xyz jitter, rendering.py:102-104) is off in every "
-                                  "reference command and has no kernel")
+    pertube = bool(getattr(args, 'pertubeCord', False))
     if not rays.is_cuda:
         raise ops.CrnerfError(f"rays are on {rays.device}: crnerf_b200 renders on CUDA (sm_100) only "
                               "and has no CPU fallback")
@@ -86,17 +86,30 @@ def render_rays_cross_ray(models,
 
     results = {}
 
+    want_sums = bool(kwargs.get('channel_sums', False))
+
     def run(model, z):
+        # xyz_ += pertube_ratio * torch.rand(xyz_.size()) (:102-104), drawn before the noise as there
+        jitter = 0.00001 * torch.rand(z.numel(), 3, device=dev) if pertube else None
         # the reference always draws the noise tensor, even when noise_std == 0 (:125)
         noise = torch.randn(z.shape, device=dev) * noise_std
         noise = noise if noise_std != 0 else None
+        typ = model.typ
         if model.wants_grad():
+            if pertube:
+                raise NotImplementedError("args.pertubeCord under autograd: the training forward has no "
+                                          "jitter input (the flag is off in every reference command)")
             # training step: same fused kernel, plus saved activations for the backward
             w, f, d = crnerf_autograd.render_pass(model, rays, z, noise, view_dir, n_fx, n_fd)
         else:
             pk = model.packed()
-            w, f, d = _K.render_pass(pk.buf, pk.operand, rays, z, noise, view_dir, n_fx, n_fd)
-        typ = model.typ
+            pk.check_overflow()      # fp16 saturation reported by earlier passes (host read, no sync)
+            w, f, d, part = _K.render_pass(pk.buf, pk.operand, rays, z, noise, view_dir, n_fx, n_fd, jitter,
+                                           pk.overflow_ptr() or 0, want_sums)
+            if want_sums:
+                # (rows, 64) partial channel sums of feature_{typ}: rows concatenated over chunks
+                # still sum to the frame's channel sums (crnerf_b200/frame.py consumes them)
+                results[f'chansum_{typ}'] = part
         results[f'weights_{typ}'] = w
         results[f'feature_{typ}'] = f
         results[f'depth_{typ}'] = d

@@ -42,9 +42,15 @@ typedef enum {
 } crnerf_status;
 
 /* Operand format of the tensor-core MLP.  Accumulation is always fp32.
- *   FP16: 10-bit mantissa (same as TF32) - meets the 1e-4 parity bar; |w| must be < 65504.
- *   BF16: 7-bit mantissa, fp32 range - PSNR-level parity only. */
-typedef enum { CRNERF_OPERAND_FP16 = 0, CRNERF_OPERAND_BF16 = 1 } crnerf_operand;
+ *   FP16  : 10-bit mantissa (same as TF32).  Meets the 1e-4 parity bar at default-init weights
+ *           (measured 3-4e-5); on trained weights, whose layers cancel large terms, the operand
+ *           rounding shows as 1-2e-3 relative (PSNR-level parity: >= 70 dB against the fp32
+ *           reference).  |w| and activations must stay below 65504 (reported, never silent).
+ *   BF16  : 7-bit mantissa, fp32 range - PSNR-level parity only; the training format.
+ *   FP16X3: every operand split as hi + lo (two fp16 values), every product three MMAs
+ *           (hi*hi + lo*hi + hi*lo): fp32-class accuracy (measured <= 1e-5 on trained weights) at
+ *           three times the tensor work.  Inference only. */
+typedef enum { CRNERF_OPERAND_FP16 = 0, CRNERF_OPERAND_BF16 = 1, CRNERF_OPERAND_FP16X3 = 2 } crnerf_operand;
 
 const char* crnerf_last_error(void);
 int crnerf_abi_version(void);
@@ -66,8 +72,11 @@ typedef struct {
   int32_t e_dir; /* in_channels_dir, <= 32 (27 for N_emb_dir=4)  */
 } crnerf_mlp_weights;
 
-/* Bytes of the packed form (16-bit swizzled weight image + fp32 bias blob). */
+/* Bytes of the packed form (16-bit swizzled weight image(s) + fp32 bias blob + the kernel's
+ * program tables): crnerf_mlp_packed_bytes for operands 0 / 1, _op for any operand
+ * (CRNERF_OPERAND_FP16X3 stores two images, W_hi and W_lo = fp16(W - W_hi)). */
 size_t crnerf_mlp_packed_bytes(int e_xyz, int e_dir);
+size_t crnerf_mlp_packed_bytes_op(int e_xyz, int e_dir, int operand);
 /* Pack once per weight version.  `status_dev` (int32, device, may be NULL)
  * receives 1 if some |w| exceeded the operand format's finite range (the value
  * is clamped); the Python mirror turns that into an error. */
@@ -94,6 +103,32 @@ int crnerf_render_pass(const void* packed, int operand, const float* rays, const
                        const float* z_vals, const float* noise, int n_rays, int n_samples,
                        int n_freq_xyz, int n_freq_dir, float* weights, float* feature,
                        float* depth, void* stream);
+
+/* The same pass with optional extras (every member may be NULL):
+ *   xyz_jitter        (n_rays*n_samples, 3) added to xyz = o + d*z before the embedding: the
+ *                     reference's args.pertubeCord path, `xyz_ += pertube_ratio * rand(...)`
+ *                     (models/rendering.py:102-104); the caller draws and scales the noise.
+ *   channel_partials  out, (crnerf_render_partial_rows(n_rays, n_samples), 64): partial column
+ *                     sums of `feature`, one row per (CTA, tile group), written in full (no
+ *                     zeroing needed).  Their sum is the per-channel sum over all rays that
+ *                     MulLayer.forward's mean needs (models/linearStyleTransfer.py:62), so the
+ *                     cross-ray block does not have to read the feature map for it
+ *                     (crnerf_style_forward_sums / crnerf_style_stats1_from_partials).
+ *   overflow_flag     int32 visible to the device (device memory or mapped pinned host memory),
+ *                     set to 1 if an fp16 operand (activation or input) reached the format's
+ *                     finite limit 65504 and was clamped: the result is then NOT within
+ *                     tolerance and the caller should switch to CRNERF_OPERAND_BF16.  Never
+ *                     written otherwise; bf16 passes never write it. */
+typedef struct {
+  const float* xyz_jitter;
+  float* channel_partials;
+  int32_t* overflow_flag;
+} crnerf_render_opts;
+int crnerf_render_partial_rows(int n_rays, int n_samples);
+int crnerf_render_pass_opts(const void* packed, int operand, const float* rays, const float* view_dir,
+                            const float* z_vals, const float* noise, int n_rays, int n_samples,
+                            int n_freq_xyz, int n_freq_dir, float* weights, float* feature,
+                            float* depth, const crnerf_render_opts* opts, void* stream);
 
 /* ------------------------------------------------------------------------
  * Training step (train_mask_grid_sample.py:186-197 calls render_rays_cross_ray under autograd).

@@ -18,13 +18,13 @@ therefore hold
     |depth - d_ref| <= sum_i rtol (1 + tau_i) w_ref,i z_i + atol_d
 
 with rtol = 1e-4 (the north-star figure), tau_i taken from the reference weights
-(T_i = 1 - sum_{j<i} w_j), atol_w = 2e-6 and atol_d = 1e-5 (absolute floors for entries
+(T_i = 1 - sum_{j<i} w_j), atol_w = 5e-6 and atol_d = 2e-5 (absolute floors for entries
 near zero; depth is a sum of up to 192 products with z <= 5).
 """
 import torch
 
-ATOL_W = 2e-6
-ATOL_D = 1e-5
+ATOL_W = 5e-6
+ATOL_D = 2e-5
 
 
 def composite_bounds(w_ref, z, rtol=1e-4, atol_w=ATOL_W, atol_d=ATOL_D):

@@ -40,7 +40,12 @@ def test_host_only_entry_points():
     lib = _lib.load()
     # weights: 77 chunks of 16 KB + 2 of 8 KB; fp32 side blob: sigma head (264) + the biases
     # of the 11 tensor-core layers (9*256 + 128 + 64)
-    assert lib.crnerf_mlp_packed_bytes(93, 27) == 77 * 16384 + 2 * 8192 + (264 + 2496) * 4
+    # ... + the kernel's program tables (104 chunks x 28 B, 20 units x 16 B, 4 ints)
+    image, blob, tables = 77 * 16384 + 2 * 8192, (264 + 2496) * 4, 104 * 28 + 20 * 16 + 16
+    assert lib.crnerf_mlp_packed_bytes(93, 27) == image + blob + tables
+    assert lib.crnerf_mlp_packed_bytes_op(93, 27, 1) == image + blob + tables
+    assert lib.crnerf_mlp_packed_bytes_op(93, 27, 2) == 2 * image + blob + tables     # fp16x3: W_hi and W_lo
+    assert lib.crnerf_mlp_packed_bytes_op(93, 27, 3) == 0                             # unknown operand
     assert lib.crnerf_style_scratch_floats(1024) > 296 * 1088
     buf = (ctypes.c_int32 * 4096)()
     n = lib.crnerf_debug_program(93, 27, buf, 4096)

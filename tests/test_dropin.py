@@ -115,9 +115,9 @@ def test_torch_ops_registered():
     rays, t = torch.empty(5, 8, device="meta"), torch.empty(7, device="meta")
     z = torch.ops.crnerf.coarse_z(rays, t, None, False)
     assert z.shape == (5, 7)
-    w, f, d = torch.ops.crnerf.render_pass(torch.empty(16, dtype=torch.uint8, device="meta"), 0, rays, z, None,
-                                           None, 15, 4)
-    assert w.shape == (5, 7) and f.shape == (5, 64) and d.shape == (5,)
+    w, f, d, part = torch.ops.crnerf.render_pass(torch.empty(16, dtype=torch.uint8, device="meta"), 0, rays, z,
+                                                 None, None, 15, 4, None, 0, False)
+    assert w.shape == (5, 7) and f.shape == (5, 64) and d.shape == (5,) and part.shape == (0, 64)
     assert torch.ops.crnerf.sample_pdf_merge(z, w, torch.empty(9, device="meta"), 9, 1e-5).shape == (5, 16)
     with pytest.raises(CrnerfError):
         torch.ops.crnerf.coarse_z(torch.zeros(5, 8), torch.zeros(7), None, False)
