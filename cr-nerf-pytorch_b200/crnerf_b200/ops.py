@@ -531,7 +531,7 @@ def render_pass_train(packed: PackedMLP, rays: torch.Tensor, z_vals: torch.Tenso
                       noise: Optional[torch.Tensor] = None, view_dir: Optional[torch.Tensor] = None,
                       n_freq_xyz: int = 15, n_freq_dir: int = 4):
     """render_pass + saved activations.  Returns (weights, feature, depth, acts, raw):
-    acts is the flat 16-bit buffer of crnerf_render_pass_train (see ``split_acts``), raw is
+    acts is the byte buffer of crnerf_render_pass_train (tiled 16-bit layout, see ``untile_acts``), raw is
     (n_points, 65) fp32 [sigmoid features | softplus sigma]."""
     lib = _lib.load()
     rays = _c(_need(rays, "rays", 2))
@@ -545,17 +545,17 @@ def render_pass_train(packed: PackedMLP, rays: torch.Tensor, z_vals: torch.Tenso
         noise = _c(_need(noise, "noise", 2))
     if view_dir is not None:
         view_dir = _c(_need(view_dir, "view_dir", 2))
+    if packed.operand not in (OPERAND_FP16, OPERAND_BF16):
+        raise CrnerfError("the training forward takes fp16 or bf16 operands (fp16x3 is inference only)")
     dev = rays.device
-    dt = torch.float16 if packed.operand == OPERAND_FP16 else torch.bfloat16
     with torch.cuda.device(dev):
         weights = torch.empty((n, s), dtype=torch.float32, device=dev)
         feature = torch.empty((n, 64), dtype=torch.float32, device=dev)
         depth = torch.empty((n,), dtype=torch.float32, device=dev)
-        acts = torch.empty((n * s * (9 * 256 + 128),), dtype=dt, device=dev)
+        acts = torch.empty((int(lib.crnerf_render_acts_bytes(n * s)),), dtype=torch.uint8, device=dev)
         raw = torch.empty((n * s, 65), dtype=torch.float32, device=dev)
         if n == 0:
             return weights, feature, depth, acts, raw
-        assert acts.numel() * 2 == lib.crnerf_render_acts_bytes(n * s)
         check(lib.crnerf_render_pass_train(packed.buf.data_ptr(), packed.operand, rays.data_ptr(),
                                            _p(view_dir), z_vals.data_ptr(), _p(noise), n, s,
                                            n_freq_xyz, n_freq_dir, weights.data_ptr(),
@@ -564,11 +564,67 @@ def render_pass_train(packed: PackedMLP, rays: torch.Tensor, z_vals: torch.Tenso
     return weights, feature, depth, acts, raw
 
 
-def split_acts(acts: torch.Tensor, n_points: int):
-    """Views into the saved-activation buffer: ([h1..h8, final] each (P,256), dir_out (P,128))."""
-    trunk = acts[: 9 * n_points * 256].view(9, n_points, 256)
-    dir_out = acts[9 * n_points * 256:].view(n_points, 128)
-    return trunk, dir_out
+def untile_acts(acts: torch.Tensor, n_points: int, operand: int = OPERAND_FP16):
+    """Tests / debugging: the saved-activation buffer of ``render_pass_train`` (the backward kernels'
+    tiled, swizzled operand layout - include/crnerf_b200.h) as plain row-major tensors:
+    ``(trunk [9 x (P,256)], dir_out (P,128), emb (P,128))``."""
+    dt = torch.float16 if operand == OPERAND_FP16 else torch.bfloat16
+    T = (n_points + 127) // 128
+    dev = acts.device
+    r = torch.arange(128, device=dev)
+    src = (torch.arange(8, device=dev)[None, :] ^ (r[:, None] & 7))          # position of logical chunk c in row r
+
+    def slot(byte0, slabs):
+        blk = acts[byte0: byte0 + T * slabs * 16384].view(T, slabs, 128, 8, 16)
+        idx = src.view(1, 1, 128, 8, 1).expand(T, slabs, 128, 8, 16)
+        rows = torch.gather(blk, 3, idx).reshape(T, slabs, 128, 128)          # logical chunk order
+        vals = rows.contiguous().view(dt).reshape(T, slabs, 128, 64)
+        return vals.permute(0, 2, 1, 3).reshape(T * 128, slabs * 64)[:n_points]
+
+    trunk = [slot(k * T * 4 * 16384, 4) for k in range(9)]
+    base = 9 * T * 4 * 16384
+    return trunk, slot(base, 2), slot(base + T * 2 * 16384, 2)
+
+
+def render_backward(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], operand: int, e_xyz: int,
+                    e_dir: int, acts: torch.Tensor, raw: torch.Tensor, z_vals: torch.Tensor,
+                    noise: Optional[torch.Tensor], g_feature: Optional[torch.Tensor],
+                    g_weights: Optional[torch.Tensor], g_depth: Optional[torch.Tensor]):
+    """Backward of one render pass on the tensor cores (crnerf_render_backward): returns the 12 weight
+    and 12 bias gradients (fp32, the parameters' shapes, ``MLP_LAYER_KEYS`` order)."""
+    lib = _lib.load()
+    z_vals = _c(_need(z_vals, "z_vals", 2))
+    n, s = z_vals.shape
+    raw = _c(_need(raw, "raw", 2))
+    if raw.shape != (n * s, 65):
+        raise ValueError("raw must be (n_rays*n_samples, 65)")
+    opt = lambda t, name, shape: None if t is None else _c(_need(t, name).reshape(shape))
+    noise = opt(noise, "noise", (n, s))
+    g_feature = opt(g_feature, "g_feature", (n, 64))
+    g_weights = opt(g_weights, "g_weights", (n, s))
+    g_depth = opt(g_depth, "g_depth", (n,))
+    dev = raw.device
+    keep = []
+    w = _lib.MlpWeights()
+    for i in range(12):
+        wi, bi = _c(_need(weights[i].detach(), f"weight[{i}]", 2)), _c(_need(biases[i].detach(), f"bias[{i}]", 1))
+        keep += [wi, bi]
+        w.weight[i], w.bias[i] = wi.data_ptr(), bi.data_ptr()
+    w.e_xyz, w.e_dir = e_xyz, e_dir
+    with torch.cuda.device(dev):
+        gw = [torch.zeros_like(weights[i], dtype=torch.float32, memory_format=torch.contiguous_format) for i in range(12)]
+        gb = [torch.zeros_like(biases[i], dtype=torch.float32) for i in range(12)]
+        if n == 0:
+            return gw, gb
+        bw = torch.empty((int(lib.crnerf_render_backward_weights_bytes(e_xyz)),), dtype=torch.uint8, device=dev)
+        scratch = torch.empty((int(lib.crnerf_render_backward_scratch_bytes(n * s)),), dtype=torch.uint8, device=dev)
+        pw = (C.c_void_p * 12)(*[t.data_ptr() for t in gw])
+        pb = (C.c_void_p * 12)(*[t.data_ptr() for t in gb])
+        check(lib.crnerf_render_backward(C.byref(w), operand, acts.data_ptr(), raw.data_ptr(), z_vals.data_ptr(),
+                                         _p(noise), _p(g_feature), _p(g_weights), _p(g_depth), n, s,
+                                         bw.data_ptr(), scratch.data_ptr(), pw, pb, _stream(dev)))
+    del keep
+    return gw, gb
 
 
 def composite_backward(raw: torch.Tensor, z_vals: torch.Tensor, noise: Optional[torch.Tensor],

@@ -9,6 +9,7 @@
 
 namespace crnerf {
 
+constexpr int kMaxExyzPublic = 96;
 static thread_local char t_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
 float* g_dbg_buf = nullptr;
@@ -167,8 +168,26 @@ int crnerf_render_pass_opts(const void* packed, int operand, const float* rays, 
                           n_freq_dir, weights, feature, depth, nullptr, nullptr, opts, stream);
 }
 
-size_t crnerf_render_acts_bytes(int64_t n_points) {
-  return n_points <= 0 ? 0 : (size_t)n_points * (9 * 256 + 128) * sizeof(uint16_t);
+size_t crnerf_render_acts_bytes(int64_t n_points) { return render_acts_bytes(n_points); }
+size_t crnerf_render_backward_weights_bytes(int e_xyz) { return bwd_packed_bytes(e_xyz); }
+size_t crnerf_render_backward_scratch_bytes(int64_t n_points) { return bwd_scratch_bytes(n_points); }
+
+int crnerf_render_backward(const crnerf_mlp_weights* w, int operand, const void* acts, const float* raw,
+                           const float* z_vals, const float* noise, const float* g_feature,
+                           const float* g_weights, const float* g_depth, int n_rays, int n_samples,
+                           void* bwd_weights, void* scratch, float* const* grad_weight, float* const* grad_bias,
+                           void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  CRNERF_REQUIRE(w && acts && raw && z_vals && bwd_weights && scratch && grad_weight && grad_bias, "null argument");
+  CRNERF_REQUIRE(operand == 0 || operand == 1, "the backward takes operand 0 (fp16) or 1 (bf16)");
+  CRNERF_REQUIRE(n_rays >= 0 && n_samples >= 16 && n_samples <= 1024, "n_samples=%d unsupported (16..1024)", n_samples);
+  CRNERF_REQUIRE(w->e_xyz >= 3 && w->e_xyz <= kMaxExyzPublic && w->e_dir >= 0 && w->e_dir <= 32, "embedding widths out of range");
+  for (int i = 0; i < 12; ++i)
+    CRNERF_REQUIRE(w->weight[i] && grad_weight[i] && grad_bias[i], "weight / gradient pointer %d is null", i);
+  if (n_rays == 0) return CRNERF_OK;
+  return render_backward(w, operand, acts, raw, z_vals, noise, g_feature, g_weights, g_depth, n_rays, n_samples,
+                         bwd_weights, scratch, grad_weight, grad_bias, (cudaStream_t)stream);
 }
 
 int crnerf_render_pass_train(const void* packed, int operand, const float* rays, const float* view_dir,
@@ -178,8 +197,10 @@ int crnerf_render_pass_train(const void* packed, int operand, const float* rays,
   CRNERF_REQUIRE(acts && raw, "acts and raw are required (use crnerf_render_pass for inference)");
   CRNERF_REQUIRE((reinterpret_cast<uintptr_t>(acts) & 15) == 0, "acts must be 16-byte aligned");
   CRNERF_REQUIRE(operand == 0 || operand == 1, "the training forward takes operand 0 (fp16) or 1 (bf16)");
-  return render_pass_impl(packed, operand, rays, view_dir, z_vals, noise, n_rays, n_samples, n_freq_xyz,
-                          n_freq_dir, weights, feature, depth, acts, raw, nullptr, stream);
+  int rc = render_pass_impl(packed, operand, rays, view_dir, z_vals, noise, n_rays, n_samples, n_freq_xyz,
+                            n_freq_dir, weights, feature, depth, acts, raw, nullptr, stream);
+  if (rc) return rc;
+  return render_acts_zero_tail(acts, (int64_t)n_rays * n_samples, (cudaStream_t)stream);
 }
 
 int crnerf_composite_backward(const float* raw, const float* z_vals, const float* noise,

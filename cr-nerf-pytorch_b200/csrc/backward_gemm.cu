@@ -1,0 +1,765 @@
+// Backward of the NeRF_sigma MLP on the tensor cores (sm_100a): the 11 dgrad and 13 wgrad GEMMs of
+// one render pass of the training step (reference train_mask_grid_sample.py:186-197 under
+// autograd; the forward is models/nerf.py:157-182).  Replaces the cuBLAS calls of round 1.
+//
+// Data layout ("tiled16"): every (points x features) 16-bit operand - the activations saved by
+// the training forward and the gradients flowing down the chain - is stored per 128-point tile
+// and 64-feature slab as a 16 KB block of 128-byte rows (one per point) with the 16-byte chunks
+// XOR-swizzled by (row % 8).  Such a block is, byte for byte, both
+//   * a K-major SWIZZLE_128B tcgen05 operand with M = points, K = features     (dgrad's A), and
+//   * an MN-major SWIZZLE_128B operand with M/N = features, K = points          (wgrad's A and B;
+//     validated bit-exactly by tools/mn_probe.cu),
+// so a tile is fetched with plain bulk copies (cp.async.bulk, no tensor map) and no transpose is
+// ever materialised.
+//
+// Gradients are 16-bit in the operand format of the forward (fp16 or bf16), each stage of the
+// chain scaled by its own power of two chosen ON THE DEVICE: the kernel that produces a stage
+// measures its max magnitude (atomicMax on the bit pattern), and the kernel that produces the
+// next stage re-centres so that this max would land in [32, 64) - 2^10 of headroom for growth
+// inside one layer, 2^-20 of the max still a normal fp16 number.  (One scale for the whole chain
+// is not enough: magnitudes fall ~0.4x per layer at default init and the bottom layers end up in
+// fp16's subnormals - measured: 1e-2 relative error at layer 1 instead of 1e-3.)  Scales are
+// undone when weight and bias gradients are accumulated in fp32.  State words (device floats):
+// st[k] = max |stored value| of stage k, st[16 + k] = its scale, st[31] = max |top gradient|.
+//
+// Per layer l (top to bottom), Gm_l = dL/d(pre-activation of layer l), X_l = the layer's input:
+//   wgrad:  dW_l (out x in) += Gm_l^T X_l        M = out features, N = in features, K = points;
+//           each CTA reduces its share of the tiles in TMEM (256 x 256 fp32 = all 512 columns) and
+//           adds it to the fp32 gradient with red.global.add (.v4 where alignment allows)
+//   dgrad:  Gm_{l-1} = (Gm_l W_l) * relu'(X_l)   M = points, N = in features, K = out features;
+//           W_l^T stays resident in shared memory, the epilogue adds the sigma-head term at h8,
+//           applies the ReLU mask from the saved activation, accumulates the bias gradient of
+//           layer l-1 (column sums) and writes the 16-bit tile of the next step.
+// Both kernels are HBM-bound (134 / 200 MB per 256-wide layer at 131 k points).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <algorithm>
+#include <cstring>
+#include "common.h"
+#include "nerf_layout.h"
+#include "ptx.cuh"
+
+namespace crnerf {
+namespace {
+
+constexpr int kSlab = 16384;   // 128 rows x 128 B
+constexpr int kHalf = 8192;    // 64 rows
+
+constexpr int kStScale = 16, kStTop = 31;
+// power of two that moves a max magnitude `a` into [32, 64)
+__device__ __forceinline__ float recentre(float a) {
+  if (!(a > 0.f) || !(a < 3.0e38f)) return 1.f;
+  int e;
+  frexpf(a, &e);                 // a = m * 2^e, m in [0.5, 1)
+  e = max(-100, min(100, e));
+  return exp2f((float)(6 - e));
+}
+
+// MN-major SWIZZLE_128B descriptor: lbo = bytes between 64-feature slabs, sbo = 1024 (8-point groups)
+__device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3ffff) >> 4);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3fff) << 16;
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t idesc_mn(uint32_t M, uint32_t N, uint32_t fmt) {
+  return make_idesc_f16(M, N, fmt) | (1u << 15) | (1u << 16);
+}
+
+// one mbarrier arrival on behalf of a converged warp
+__device__ __forceinline__ void warp_arrive_bar(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+// column sums over the 32 lanes of a warp for 32 values per lane (transposing butterfly, 31
+// shuffles): lane L returns sum over lanes of v[L]
+template <int kHalfW>
+__device__ __forceinline__ void bfly(float (&v)[32], int lane) {
+  const bool up = (lane & kHalfW) != 0;
+#pragma unroll
+  for (int i = 0; i < kHalfW; ++i) {
+    const float send = up ? v[i] : v[i + kHalfW];
+    const float keep = up ? v[i + kHalfW] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, kHalfW);
+  }
+}
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+  bfly<16>(v, lane);
+  bfly<8>(v, lane);
+  bfly<4>(v, lane);
+  bfly<2>(v, lane);
+  bfly<1>(v, lane);
+  return v[0];
+}
+
+// rows [r0, 128) of one slab := 0 (the point count's tail inside the last tile)
+__global__ void zero_tail_kernel(uint8_t* base, int n_slabs, long long slab_stride, int r0) {
+  uint4* dst = reinterpret_cast<uint4*>(base + (size_t)blockIdx.x * slab_stride + (size_t)r0 * 128);
+  const int n16 = (128 - r0) * 8;
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = make_uint4(0, 0, 0, 0);
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// top of the chain: d_rgb (P,64) fp32 + d_sigma (P) fp32 -> Gm_rgb tiles (one slab, scaled) and
+// Gsig tiles (one slab whose column 0 is d_sigma, scaled); bias gradients of static_rgb / static_sigma
+// ------------------------------------------------------------------------------------------
+template <int kFmt>
+__global__ void __launch_bounds__(128) top_pack_kernel(const float* __restrict__ d_rgb, const float* __restrict__ d_sig,
+                                                       long long P, float* __restrict__ st,
+                                                       uint8_t* __restrict__ g_rgb, uint8_t* __restrict__ g_sig,
+                                                       float* __restrict__ db_rgb, float* __restrict__ db_sig) {
+  __shared__ float red[4][65];
+  const float top = st[kStTop];
+  const float S = recentre(top);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {   // stage 0 = the two top tiles
+    st[kStScale] = S;
+    st[0] = top * S;
+  }
+  const int r = threadIdx.x, warp = r >> 5, lane = r & 31;
+  const long long p = (long long)blockIdx.x * 128 + r;
+  const bool valid = p < P;
+  float v[64];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float4 t = valid ? __ldg(reinterpret_cast<const float4*>(d_rgb + p * 64) + i) : make_float4(0, 0, 0, 0);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+  const float ds = valid ? __ldg(d_sig + p) : 0.f;
+  uint4* row = reinterpret_cast<uint4*>(g_rgb + (size_t)blockIdx.x * kSlab + r * 128);
+  uint4* rows = reinterpret_cast<uint4*>(g_sig + (size_t)blockIdx.x * kSlab + r * 128);
+  const uint32_t rx = r & 7;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = pack2<kFmt, false>(v[8 * c + 2 * q] * S, v[8 * c + 2 * q + 1] * S);
+    row[(uint32_t)c ^ rx] = make_uint4(w[0], w[1], w[2], w[3]);
+    rows[(uint32_t)c ^ rx] = c == 0 ? make_uint4(pack2<kFmt, false>(ds * S, 0.f), 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  // bias gradients (unscaled fp32): column sums over the block's rows, then one atomic per column
+  float dsum = ds;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, d);
+#pragma unroll
+  for (int c = 0; c < 64; ++c) {
+    float t = v[c];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+    if (lane == 0) red[warp][c] = t;
+  }
+  if (lane == 0) red[warp][64] = dsum;
+  __syncthreads();
+  if (r < 65) {
+    const float t = (red[0][r] + red[1][r]) + (red[2][r] + red[3][r]);
+    if (r < 64)
+      atomicAdd(db_rgb + r, t);
+    else
+      atomicAdd(db_sig, t);
+  }
+}
+
+// max(|x|) of a float array into *out (non-negative floats order like their bit patterns)
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ a, long long n, float* out) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) m = fmaxf(m, fabsf(a[i]));
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m < 3.0e38f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
+}
+
+// ------------------------------------------------------------------------------------------
+// weights for dgrad: W_l^T as K-major SWIZZLE_128B slabs.  Slab j of layer l holds, for every input
+// feature k (row, 128 B), the 64 output features n = 64 j .. 64 j + 63:  element (k, n) = W[n][k0 + k]
+// ------------------------------------------------------------------------------------------
+struct BwdLayer {
+  int w_index;    // index into the 12 weight pointers
+  int n_out;      // N (64 / 128 / 256)
+  int k_in;       // rows of the image = input features that receive a gradient (128 / 256)
+  int k0;         // first such column of W
+  int ld;         // row stride of W
+  int offset;     // byte offset of the layer's image
+};
+constexpr int kBwdLayers = 10;   // layers 1..7 (trunk 2-8), final, dir, rgb; layer 0 has no dgrad
+struct BwdPackParams {
+  const float* w[12];
+  uint8_t* img;
+  BwdLayer L[kBwdLayers];
+  int fmt;
+  int total_bytes;
+};
+
+__global__ void bwd_pack_kernel(const __grid_constant__ BwdPackParams P) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.total_bytes / 16; i += gridDim.x * blockDim.x) {
+    const int byte = i * 16;
+    int li = 0;
+    while (li + 1 < kBwdLayers && P.L[li + 1].offset <= byte) ++li;
+    const BwdLayer L = P.L[li];
+    const int within = byte - L.offset;
+    const int slab_bytes = L.k_in * 128;
+    const int j = within / slab_bytes, rem = within % slab_bytes;
+    const int k = rem >> 7, pos = (rem & 127) >> 4;
+    const int n0 = 64 * j + ((pos ^ (k & 7)) & 7) * 8;
+    const float* w = P.w[L.w_index] + (size_t)(L.k0 + k);
+    uint32_t out[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float v0 = w[(size_t)(n0 + 2 * e) * L.ld], v1 = w[(size_t)(n0 + 2 * e + 1) * L.ld];
+      out[e] = P.fmt == 0 ? pack2<0, false>(v0, v1) : pack2<1, false>(v0, v1);
+    }
+    *reinterpret_cast<uint4*>(P.img + byte) = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// wgrad
+// ------------------------------------------------------------------------------------------
+struct WgradParams {
+  const uint8_t* g;     // tiled16 (P x 64*g_slabs)
+  const uint8_t* x;     // tiled16, x_slabs_total slabs per tile; the kernel reads slabs [xs0, xs0 + nxs)
+  float* dw;            // fp32 (rows x ldw), accumulated with atomics
+  const float* scale;   // scale of G's stage
+  int g_slabs, x_slabs_total, xs0, nxs;
+  int ldw, c0;          // output column of X-window column xcol0
+  int xcol0, ncols;     // valid columns of the X window
+  int nrows;            // valid rows (output features)
+  int n_tiles;
+};
+constexpr int kWgStages = 3;
+
+template <int kFmt>
+__global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ WgradParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // stage: [G half-tile: ga slabs x 8 KB][X half-tile: nxs x 8 KB]; ga = max(2, g_slabs) so that M = 128
+  // MMAs always find two slabs (the second one is zero for the 64-wide rgb gradient)
+  const int ga = P.g_slabs < 2 ? 2 : P.g_slabs;
+  const int stage_bytes = (ga + P.nxs) * kHalf;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWgStages;
+  uint64_t* done = bars + 2 * kWgStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (P.g_slabs < 2) {   // zero the phantom second G slab of every stage once
+    for (int i = threadIdx.x; i < kWgStages * (kHalf / 16); i += blockDim.x) {
+      const int st = i / (kHalf / 16), o = i % (kHalf / 16);
+      reinterpret_cast<uint4*>(smem + st * stage_bytes + kHalf)[o] = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  // this CTA's half-tiles: tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+  int my_tiles = 0;
+  for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) ++my_tiles;
+  const int n_steps = 2 * my_tiles;
+  const int m_halves = (P.g_slabs + 1) / 2;   // 128-row blocks of dW
+  const int n_mma = P.nxs * 64;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int s = 0; s < n_steps; ++s) {
+        const int st = s % kWgStages, n = s / kWgStages;
+        mbar_wait(&empty[st], (n & 1) ^ 1, 1);
+        const size_t tile = (size_t)blockIdx.x + (size_t)(s >> 1) * gridDim.x;
+        const int h = s & 1;
+        uint8_t* dst = smem + st * stage_bytes;
+        mbar_arrive_expect_tx(&full[st], (uint32_t)((P.g_slabs + P.nxs) * kHalf));
+        for (int j = 0; j < P.g_slabs; ++j)
+          bulk_g2s(dst + j * kHalf, P.g + (tile * P.g_slabs + j) * kSlab + h * kHalf, kHalf, &full[st]);
+        for (int j = 0; j < P.nxs; ++j)
+          bulk_g2s(dst + (ga + j) * kHalf, P.x + (tile * P.x_slabs_total + P.xs0 + j) * kSlab + h * kHalf, kHalf,
+                   &full[st]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    const uint32_t idesc = idesc_mn(128, (uint32_t)n_mma, kFmt);
+    for (int s = 0; s < n_steps; ++s) {
+      const int st = s % kWgStages, n = s / kWgStages;
+      mbar_wait(&full[st], n & 1, 2);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint32_t base = smem_u32(smem + st * stage_bytes);
+        for (int mh = 0; mh < m_halves; ++mh) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {   // 64 points = 4 k-steps of 16 points = 2048 B down every slab
+            const uint64_t ad = desc_mn(base + (uint32_t)(mh * 2) * kHalf + ks * 2048u, kHalf);
+            const uint64_t bd = desc_mn(base + (uint32_t)ga * kHalf + ks * 2048u, kHalf);
+            umma_ss(tmem + (uint32_t)mh * 256u, ad, bd, idesc, (s | ks) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[st]);
+        if (s == n_steps - 1) umma_commit(done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- epilogue (warps 2..5: TMEM lane quarter = warp % 4): dW += acc / S
+    if (n_steps > 0) {
+      mbar_wait(done, 0, 3);
+      tc_fence_after_sync();
+      const float inv = 1.f / *P.scale;
+      const int q = warp & 3;
+      const bool vec = (P.ldw % 4 == 0) && ((P.c0 - P.xcol0) % 4 == 0) && (P.xcol0 % 4 == 0) && (P.ncols % 4 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(P.dw) & 15) == 0);
+      for (int mh = 0; mh < m_halves; ++mh) {
+        const int rowf = mh * 128 + q * 32 + lane;
+        for (int c0 = 0; c0 < n_mma; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(tmem + (uint32_t)mh * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (rowf < P.nrows) {
+            float* drow = P.dw + (size_t)rowf * P.ldw + (P.c0 - P.xcol0);
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const int c = c0 + j;
+                if (c >= P.xcol0 && c < P.xcol0 + P.ncols)
+                  red_add_v4(drow + c, __uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv,
+                             __uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int c = c0 + j;
+                if (c >= P.xcol0 && c < P.xcol0 + P.ncols) atomicAdd(drow + c, __uint_as_float(v[j]) * inv);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
+// dgrad
+// ------------------------------------------------------------------------------------------
+struct DgradParams {
+  const uint8_t* g;      // tiled16 (P x 64*g_slabs): Gm of this layer (scaled)
+  const uint8_t* wimg;   // this layer's W^T image: g_slabs slabs of (k_in x 128 B)
+  const uint8_t* act;    // tiled16 saved activation of the layer below (ReLU mask), or nullptr
+  uint8_t* out;          // tiled16 (P x k_in): Gm of the layer below (scaled)
+  float* db;             // fp32 (k_in): bias gradient of the layer below, accumulated with atomics
+  const float* dsig;     // fp32 (P): sigma-head gradient joined at h8 (d_sigma x W_sigma), or nullptr
+  const float* wsig;     // fp32 (k_in): static_sigma weight row
+  float* st;             // scale state (see the header comment)
+  int stage;             // stage index of g; the output is stage + 1
+  long long n_points;
+  int g_slabs, k_in, act_slabs_total, act_s0;
+  int n_tiles;
+};
+constexpr int kDgStages = 3;
+constexpr int kDgStageBytes = 2 * kSlab;   // up to two 64-feature slabs of G per stage
+constexpr int kDgThreads = 320;            // producer, issuer, 8 epilogue warps
+
+template <int kFmt>
+__global__ void __launch_bounds__(kDgThreads, 1) dgrad_kernel(const __grid_constant__ DgradParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int w_bytes = P.g_slabs * P.k_in * 128;
+  uint8_t* sW = smem;
+  uint8_t* ring = smem + w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kDgStages * kDgStageBytes);
+  uint64_t* full = bars;                 // [kDgStages]
+  uint64_t* empty = bars + kDgStages;    // [kDgStages]
+  uint64_t* w_full = bars + 2 * kDgStages;
+  uint64_t* d_full = w_full + 1;         // [2]
+  uint64_t* d_empty = d_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+  float* s_wsig = reinterpret_cast<float*>(tmem_slot + 2);   // [256]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kDgStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&d_full[i], 1);
+      mbar_init(&d_empty[i], 8);
+    }
+    fence_mbar_init();
+  }
+  if (P.dsig)
+    for (int i = threadIdx.x; i < P.k_in; i += blockDim.x) s_wsig[i] = P.wsig[i];
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  int my_tiles = 0;
+  for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) ++my_tiles;
+  const int spt = (P.g_slabs + 1) / 2;           // stages per tile
+  const int slabs_last = P.g_slabs - 2 * (spt - 1);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(w_full, (uint32_t)w_bytes);
+      for (int o = 0; o < w_bytes; o += 32768) bulk_g2s(sW + o, P.wimg + o, (uint32_t)min(32768, w_bytes - o), w_full);
+      int s = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const size_t tile = (size_t)blockIdx.x + (size_t)i * gridDim.x;
+        for (int k = 0; k < spt; ++k, ++s) {
+          const int st = s % kDgStages, n = s / kDgStages;
+          mbar_wait(&empty[st], (n & 1) ^ 1, 1);
+          const int ns = k == spt - 1 ? slabs_last : 2;
+          mbar_arrive_expect_tx(&full[st], (uint32_t)(ns * kSlab));
+          bulk_g2s(ring + st * kDgStageBytes, P.g + (tile * P.g_slabs + 2 * k) * kSlab, (uint32_t)(ns * kSlab), &full[st]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_f16(128, (uint32_t)P.k_in, kFmt);
+    mbar_wait(w_full, 0, 2);
+    int s = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int buf = i & 1;
+      mbar_wait(&d_empty[buf], ((i >> 1) & 1) ^ 1, 3);
+      for (int k = 0; k < spt; ++k, ++s) {
+        const int st = s % kDgStages, n = s / kDgStages;
+        mbar_wait(&full[st], n & 1, 4);
+        tc_fence_after_sync();
+        if (elect_one()) {
+          const int ns = k == spt - 1 ? slabs_last : 2;
+          for (int j = 0; j < ns; ++j) {
+            const uint32_t a0 = smem_u32(ring + st * kDgStageBytes + j * kSlab);
+            const uint32_t b0 = smem_u32(sW + (2 * k + j) * P.k_in * 128);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ss(tmem + (uint32_t)buf * 256u, make_sdesc_k_sw128(a0 + ks * 32u, 1024), make_sdesc_k_sw128(b0 + ks * 32u, 1024),
+                      idesc, (k | j | ks) ? 1u : 0u);
+          }
+          umma_commit(&empty[st]);
+          if (k == spt - 1) umma_commit(&d_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---- epilogue: 8 warps = TMEM lane quarter (warp % 4) x column half
+    const int q = warp & 3, ch = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int cols_half = P.k_in / 2, groups = cols_half / 32;   // 32-column groups of this warp (4 or 2)
+    const float s_in = P.st[kStScale + P.stage];
+    // stored units of the input stage -> of the output stage.  The sigma-head term joined below
+    // (|d_sigma| <= the top max, st[kStTop]) must fit as well.
+    float in_max = P.st[P.stage];
+    if (P.dsig) {
+      float wm = 0.f;
+      for (int i = 0; i < P.k_in; ++i) wm = fmaxf(wm, fabsf(s_wsig[i]));
+      in_max = fmaxf(in_max, P.st[kStTop] * s_in * wm);
+    }
+    const float r = recentre(in_max);
+    if (blockIdx.x == 0 && warp == 2 && lane == 0) P.st[kStScale + P.stage + 1] = s_in * r;
+    float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
+    float amax_out = 0.f;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int buf = i & 1;
+      const size_t tile = (size_t)blockIdx.x + (size_t)i * gridDim.x;
+      const long long p = (long long)tile * 128 + row;
+      const bool valid = p < P.n_points;
+      const float ds = (P.dsig && valid) ? __ldg(P.dsig + p) * s_in : 0.f;
+      mbar_wait(&d_full[buf], (i >> 1) & 1, 5);
+      tc_fence_after_sync();
+      for (int gidx = 0; gidx < groups; gidx += 2) {
+        // two 32-column groups = one 64-column slab of the output / of the mask source
+        const int col0 = ch * cols_half + gidx * 32;
+        const int slab = col0 >> 6;
+        uint32_t va[32], vb[32];
+        tmem_ld_x32(tmem + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, va);
+        tmem_ld_x32(tmem + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)col0 + 32u, vb);
+        uint4 m[8];
+        if (P.act) {
+          const uint4* arow = reinterpret_cast<const uint4*>(
+              P.act + ((size_t)tile * P.act_slabs_total + P.act_s0 + slab) * kSlab + row * 128);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) m[c] = __ldg(arow + ((uint32_t)c ^ (uint32_t)(row & 7)));
+        }
+        tmem_ld_wait();
+        if (gidx + 2 >= groups) {   // last read of this accumulator
+          tc_fence_before_sync();
+          warp_arrive_bar(&d_empty[buf]);
+        }
+        float x[64];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          x[j] = __uint_as_float(va[j]);
+          x[32 + j] = __uint_as_float(vb[j]);
+        }
+        if (P.dsig) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) x[j] = fmaf(ds, s_wsig[col0 + j], x[j]);
+        }
+        if (P.act) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t w4[4] = {m[c].x, m[c].y, m[c].z, m[c].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t lo = w4[e] & 0xffffu, hi = w4[e] >> 16;
+              // saved post-ReLU activation strictly positive <=> the unit was active
+              if (!(lo != 0u && lo < 0x8000u)) x[8 * c + 2 * e] = 0.f;
+              if (!(hi != 0u && hi < 0x8000u)) x[8 * c + 2 * e + 1] = 0.f;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          x[j] = valid ? x[j] * r : 0.f;
+          amax_out = fmaxf(amax_out, fabsf(x[j]));
+        }
+        // 16-bit tile of the layer below
+        uint4* orow = reinterpret_cast<uint4*>(P.out + ((size_t)tile * (P.k_in / 64) + slab) * kSlab + row * 128);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) w[e] = pack2<kFmt, false>(x[8 * c + 2 * e], x[8 * c + 2 * e + 1]);
+          orow[(uint32_t)c ^ (uint32_t)(row & 7)] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        // bias gradient: column sums over the warp's 32 rows (transposing butterfly)
+        if (P.db) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float t[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = x[32 * h + j];
+            dbacc[gidx + h] += warp_colsum32(t, lane);
+          }
+        }
+      }
+    }
+    if (P.db && my_tiles > 0) {
+      const float inv = 1.f / (s_in * r);
+      for (int gidx = 0; gidx < groups; ++gidx) atomicAdd(P.db + ch * cols_half + gidx * 32 + lane, dbacc[gidx] * inv);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) amax_out = fmaxf(amax_out, __shfl_xor_sync(0xffffffffu, amax_out, d));
+    if (lane == 0 && amax_out > 0.f) {
+      amax_out = fminf(amax_out, 65504.f);
+      atomicMax(reinterpret_cast<unsigned int*>(P.st + P.stage + 1), __float_as_uint(amax_out));
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static void bwd_layers(int e_xyz, BwdLayer* L, int* total) {
+  // order: trunk layers 1..7, final (8), dir (9), rgb (10)
+  int off = 0, n = 0;
+  auto add = [&](int wi, int n_out, int k_in, int k0, int ld) {
+    L[n] = BwdLayer{wi, n_out, k_in, k0, ld, off};
+    off += (n_out / 64) * k_in * 128;
+    ++n;
+  };
+  for (int l = 1; l < 8; ++l) add(l, 256, 256, l == kSkipLayer ? e_xyz : 0, l == kSkipLayer ? e_xyz + 256 : 256);
+  add(kLFinal, 256, 256, 0, 256);
+  add(kLDir, 128, 256, 0, -1);   // ld patched by the caller (256 + e_dir)
+  add(kLRgb, 64, 128, 0, 128);
+  *total = off;
+}
+
+size_t bwd_packed_bytes(int e_xyz) {
+  BwdLayer L[kBwdLayers];
+  int total;
+  bwd_layers(e_xyz, L, &total);
+  return (size_t)total;
+}
+size_t bwd_tiled_bytes(int64_t n_points, int features) {
+  return (size_t)((n_points + 127) / 128) * (size_t)((features + 63) / 64) * kSlab;
+}
+// scratch of one backward pass: d_rgb fp32, d_sig fp32, two ping-pong gradient buffers (256 wide),
+// the rgb / sigma top tiles, the amax word
+struct BwdScratch {
+  size_t d_rgb, d_sig, g0, g1, g_rgb, g_sig, amax, total;
+};
+static BwdScratch bwd_scratch(int64_t P) {
+  BwdScratch s;
+  size_t o = 0;
+  auto take = [&](size_t b) {
+    const size_t r = o;
+    o += (b + 255) / 256 * 256;
+    return r;
+  };
+  s.d_rgb = take((size_t)P * 64 * 4);
+  s.d_sig = take((size_t)P * 4);
+  s.g0 = take(bwd_tiled_bytes(P, 256));
+  s.g1 = take(bwd_tiled_bytes(P, 256));
+  s.g_rgb = take(bwd_tiled_bytes(P, 64));
+  s.g_sig = take(bwd_tiled_bytes(P, 64));
+  s.amax = take(256);
+  s.total = o;
+  return s;
+}
+size_t bwd_scratch_bytes(int64_t n_points) { return bwd_scratch(n_points).total; }
+
+// saved-activation buffer of the training forward: slots 0..8 (256 wide), dir (128), embedding (128)
+size_t render_acts_bytes(int64_t n_points) {
+  return n_points <= 0 ? 0 : (size_t)((n_points + 127) / 128) * (9 * 4 + 2 + 2) * kSlab;
+}
+// the forward writes one row per valid point; rows past the last point inside the last tile stay
+// untouched - zero them, wgrad sums over whole tiles
+int render_acts_zero_tail(void* acts, int64_t n_points, cudaStream_t st) {
+  const int r0 = (int)(n_points % 128);
+  if (n_points <= 0 || r0 == 0) return CRNERF_OK;
+  const size_t T = (size_t)((n_points + 127) / 128);
+  uint8_t* A = static_cast<uint8_t*>(acts);
+  for (int k = 0; k < 11; ++k) {
+    const int slabs = k < 9 ? 4 : 2;
+    uint8_t* slot = A + (k < 9 ? (size_t)k * T * 4 : (size_t)9 * T * 4 + (size_t)(k - 9) * T * 2) * kSlab;
+    zero_tail_kernel<<<slabs, 128, 0, st>>>(slot + (T - 1) * slabs * kSlab, slabs, kSlab, r0);
+  }
+  count_launch(11);
+  CRNERF_CUDA(cudaGetLastError());
+  return CRNERF_OK;
+}
+
+int composite_backward(const float* raw, const float* z, const float* noise, const float* g_feature,
+                       const float* g_weights, const float* g_depth, int n_rays, int n_samples,
+                       float* d_rgb_pre, float* d_sigma_pre, cudaStream_t st);
+
+template <int kFmt>
+static int run_wgrad(const WgradParams& w, cudaStream_t st) {
+  const int ga = w.g_slabs < 2 ? 2 : w.g_slabs;
+  const size_t smem = (size_t)kWgStages * (ga + w.nxs) * kHalf + 256;
+  CRNERF_CUDA(cudaFuncSetAttribute(wgrad_kernel<kFmt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(num_sms(), w.n_tiles);
+  wgrad_kernel<kFmt><<<grid, 192, smem, st>>>(w);
+  count_launch();
+  return CRNERF_OK;
+}
+template <int kFmt>
+static int run_dgrad(const DgradParams& d, cudaStream_t st) {
+  const size_t smem = (size_t)d.g_slabs * d.k_in * 128 + kDgStages * kDgStageBytes + 256 + 1024;
+  CRNERF_CUDA(cudaFuncSetAttribute(dgrad_kernel<kFmt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(num_sms(), d.n_tiles);
+  dgrad_kernel<kFmt><<<grid, kDgThreads, smem, st>>>(d);
+  count_launch();
+  return CRNERF_OK;
+}
+
+template <int kFmt>
+static int backward_chain(const crnerf_mlp_weights* w, const void* acts, const float* raw, const float* z,
+                          const float* noise, const float* g_feature, const float* g_weights, const float* g_depth,
+                          int n_rays, int n_samples, void* bwd_weights, void* scratch, float* const* gw,
+                          float* const* gb, cudaStream_t st) {
+  const int64_t P = (int64_t)n_rays * n_samples;
+  const int T = (int)((P + 127) / 128);
+  const BwdScratch sc = bwd_scratch(P);
+  uint8_t* base = static_cast<uint8_t*>(scratch);
+  float* d_rgb = reinterpret_cast<float*>(base + sc.d_rgb);
+  float* d_sig = reinterpret_cast<float*>(base + sc.d_sig);
+  uint8_t* gbuf[2] = {base + sc.g0, base + sc.g1};
+  uint8_t* g_rgb = base + sc.g_rgb;
+  uint8_t* g_sig = base + sc.g_sig;
+  float* stw = reinterpret_cast<float*>(base + sc.amax);    // scale state words
+  const int e_xyz = w->e_xyz, e_dir = w->e_dir;
+
+  // 1. weights for dgrad (the optimizer changed them since the last step)
+  BwdPackParams bp;
+  memset(&bp, 0, sizeof(bp));
+  for (int i = 0; i < 12; ++i) bp.w[i] = w->weight[i];
+  bp.img = static_cast<uint8_t*>(bwd_weights);
+  bwd_layers(e_xyz, bp.L, &bp.total_bytes);
+  bp.L[8].ld = 256 + e_dir;
+  bp.fmt = kFmt;
+  bwd_pack_kernel<<<num_sms(), 256, 0, st>>>(bp);
+  count_launch();
+
+  // 2. composite backward -> d_rgb, d_sigma (fp32), their max magnitude, top tiles
+  int rc = composite_backward(raw, z, noise, g_feature, g_weights, g_depth, n_rays, n_samples, d_rgb, d_sig, st);
+  if (rc) return rc;
+  CRNERF_CUDA(cudaMemsetAsync(stw, 0, 32 * sizeof(float), st));
+  absmax_kernel<<<2 * num_sms(), 256, 0, st>>>(d_rgb, P * 64, stw + kStTop);
+  absmax_kernel<<<num_sms(), 256, 0, st>>>(d_sig, P, stw + kStTop);
+  top_pack_kernel<kFmt><<<T, 128, 0, st>>>(d_rgb, d_sig, P, stw, g_rgb, g_sig, gb[kLRgb], gb[kLSigma]);
+  count_launch(3);
+
+  // saved activations (tiled16): slots 0..8 (256 wide), 9 = dir (128), 10 = embedding tile (128)
+  const uint8_t* A = static_cast<const uint8_t*>(acts);
+  auto slot = [&](int k) -> const uint8_t* {
+    return A + (k < 9 ? (size_t)k * T * 4 : (size_t)9 * T * 4 + (size_t)(k - 9) * T * 2) * kSlab;
+  };
+  int stage = 0;   // stage of the gradient tiles currently at the head of the chain
+  auto wgrad = [&](const uint8_t* g, int g_slabs, const uint8_t* x, int xtot, int xs0, int nxs, float* dw, int ldw,
+                   int c0, int xcol0, int ncols, int nrows) {
+    WgradParams wp{g, x, dw, stw + kStScale + stage, g_slabs, xtot, xs0, nxs, ldw, c0, xcol0, ncols, nrows, T};
+    return run_wgrad<kFmt>(wp, st);
+  };
+  auto dgrad = [&](const uint8_t* g, int g_slabs, int layer_idx, const uint8_t* act, int atot, int as0, uint8_t* out,
+                   float* db, const float* dsig) {
+    DgradParams dp{g, static_cast<const uint8_t*>(bwd_weights) + bp.L[layer_idx].offset, act, out, db, dsig,
+                   w->weight[kLSigma], stw, stage, P, g_slabs, bp.L[layer_idx].k_in, atot, as0, T};
+    const int rc2 = run_dgrad<kFmt>(dp, st);
+    ++stage;       // the output tiles are the next stage
+    return rc2;
+  };
+#define CK_(x) do { rc = (x); if (rc) return rc; } while (0)
+  // static_sigma: dW = d_sigma^T h8 (row 0 of a 64-row product)
+  CK_(wgrad(g_sig, 1, slot(7), 4, 0, 4, gw[kLSigma], 256, 0, 0, 256, 1));
+  // static_rgb (64 x 128): X = dir_out
+  CK_(wgrad(g_rgb, 1, slot(9), 2, 0, 2, gw[kLRgb], 128, 0, 0, 128, 64));
+  CK_(dgrad(g_rgb, 1, 9, slot(9), 2, 0, gbuf[0], gb[kLDir], nullptr));                 // -> Gm_dir (P x 128)
+  // dir_encoding (128 x (256 + e_dir)): X = [final | dir embedding = columns 96.. of the embedding tile]
+  CK_(wgrad(gbuf[0], 2, slot(8), 4, 0, 4, gw[kLDir], 256 + e_dir, 0, 0, 256, 128));
+  CK_(wgrad(gbuf[0], 2, slot(10), 2, 1, 1, gw[kLDir], 256 + e_dir, 256, kDirCol0 - 64, e_dir, 128));
+  CK_(dgrad(gbuf[0], 2, 8, nullptr, 0, 0, gbuf[1], gb[kLFinal], nullptr));             // -> Gm_final (P x 256)
+  // xyz_encoding_final (256 x 256): X = h8; the sigma head joins below it
+  CK_(wgrad(gbuf[1], 4, slot(7), 4, 0, 4, gw[kLFinal], 256, 0, 0, 256, 256));
+  CK_(dgrad(gbuf[1], 4, 7, slot(7), 4, 0, gbuf[0], gb[7], d_sig));                      // -> Gm of trunk layer 8
+  int cur = 0;
+  for (int l = 7; l >= 1; --l) {
+    // trunk layer l (0-based): X = h_l (slot l-1) [+ xyz embedding in front for the skip layer]
+    const int ld = l == kSkipLayer ? e_xyz + 256 : 256, c0 = l == kSkipLayer ? e_xyz : 0;
+    CK_(wgrad(gbuf[cur], 4, slot(l - 1), 4, 0, 4, gw[l], ld, c0, 0, 256, 256));
+    if (l == kSkipLayer) CK_(wgrad(gbuf[cur], 4, slot(10), 2, 0, 2, gw[l], ld, 0, 0, e_xyz, 256));
+    CK_(dgrad(gbuf[cur], 4, l - 1, slot(l - 1), 4, 0, gbuf[cur ^ 1], gb[l - 1], nullptr));
+    cur ^= 1;
+  }
+  CK_(wgrad(gbuf[cur], 4, slot(10), 2, 0, 2, gw[0], e_xyz, 0, 0, e_xyz, 256));          // layer 0: X = xyz embedding
+#undef CK_
+  CRNERF_CUDA(cudaGetLastError());
+  return CRNERF_OK;
+}
+
+int render_backward(const crnerf_mlp_weights* w, int operand, const void* acts, const float* raw, const float* z,
+                    const float* noise, const float* g_feature, const float* g_weights, const float* g_depth,
+                    int n_rays, int n_samples, void* bwd_weights, void* scratch, float* const* gw,
+                    float* const* gb, cudaStream_t st) {
+  if (operand == 0)
+    return backward_chain<0>(w, acts, raw, z, noise, g_feature, g_weights, g_depth, n_rays, n_samples, bwd_weights,
+                             scratch, gw, gb, st);
+  return backward_chain<1>(w, acts, raw, z, noise, g_feature, g_weights, g_depth, n_rays, n_samples, bwd_weights,
+                           scratch, gw, gb, st);
+}
+
+}  // namespace crnerf

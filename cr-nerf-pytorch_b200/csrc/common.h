@@ -46,6 +46,15 @@ size_t mlp_packed_bytes(int e_xyz, int e_dir, int operand);
 int debug_program(int e_xyz, int e_dir, int32_t* out, int cap);
 int mlp_pack(const crnerf_mlp_weights* w, int operand, void* packed, size_t packed_bytes,
              int32_t* status_dev, cudaStream_t st);
+// backward_gemm.cu: the training step's backward through one render pass
+size_t render_acts_bytes(int64_t n_points);
+int render_acts_zero_tail(void* acts, int64_t n_points, cudaStream_t st);
+size_t bwd_packed_bytes(int e_xyz);
+size_t bwd_scratch_bytes(int64_t n_points);
+int render_backward(const crnerf_mlp_weights* w, int operand, const void* acts, const float* raw, const float* z,
+                    const float* noise, const float* g_feature, const float* g_weights, const float* g_depth,
+                    int n_rays, int n_samples, void* bwd_weights, void* scratch, float* const* gw,
+                    float* const* gb, cudaStream_t st);
 
 }  // namespace crnerf
 

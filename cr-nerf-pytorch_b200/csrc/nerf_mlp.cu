@@ -395,15 +395,25 @@ __device__ __forceinline__ void epi_slice32(const uint32_t (&v)[kCols], const fl
 // First half of a 256-wide layer: drain this warp's 64 accumulator columns into 32 packed
 // words that stay in registers (A is still being read by the layer's second half).
 // 16 packed words (32 activations of one row) -> 64 contiguous bytes of the saved-activation buffer
-__device__ __forceinline__ void save16(uint4* dst, const uint32_t* w) {
+// Saved activations live in the backward kernels' operand layout (csrc/backward_gemm.cu,
+// "tiled16"): per 128-point tile and 64-column slab a 16 KB block of 128-byte rows whose
+// 16-byte chunks are XOR-swizzled with (row % 8) - readable by bulk copies as a SWIZZLE_128B
+// tcgen05 operand, K-major (dgrad) and MN-major (wgrad) alike.  A thread owns one row.
+struct SaveRow {
+  uint4* base;   // the row's 128 bytes inside its slab, or nullptr
+  uint32_t rx;   // global row % 8
+};
+// 16 packed words = chunks [chunk0, chunk0 + 4) of the row
+__device__ __forceinline__ void save16(const SaveRow& r, int chunk0, const uint32_t* w) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  for (int i = 0; i < 4; ++i)
+    r.base[(uint32_t)(chunk0 + i) ^ r.rx] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
 }
 
 template <int kFmt, bool kRelu, bool kSigma, bool kDbg, bool kSave>
 __device__ __forceinline__ void epi_stage(uint32_t tD_ch, const float* blob_g, uint32_t boff, const float* wsig_ch,
                                           uint32_t (&staged)[32], float& sig_acc, uint64_t* d_empty,
-                                          float* dbg, bool skip, uint4* asave, uint32_t& amax) {
+                                          float* dbg, bool skip, const SaveRow& asave, uint32_t& amax) {
   if (kDbg && skip) {
     tc_fence_before_sync();
     warp_arrive(d_empty);
@@ -421,9 +431,9 @@ __device__ __forceinline__ void epi_stage(uint32_t tD_ch, const float* blob_g, u
   epi_slice32<kFmt, kRelu, kSigma, kDbg, 16, 32>(vb, blob_g, boff + 32u, wsig_ch + 32, staged, sig_acc,
                                                  dbg ? dbg + 32 : nullptr, amax);
   if constexpr (kSave) {
-    if (asave) {
-      save16(asave, staged);
-      save16(asave + 4, staged + 16);
+    if (asave.base) {
+      save16(asave, 0, staged);
+      save16(asave, 4, staged + 16);
     }
   }
 }
@@ -435,7 +445,7 @@ template <int kFmt, bool kRelu, bool kSigma, bool kDbg, bool kDirect, bool kSave
 __device__ __forceinline__ void epi_flush(uint32_t tD_ch, uint32_t tA_ch, const float* blob_g, uint32_t boff,
                                           const float* wsig_ch, const uint32_t (&staged)[32], float& sig_acc,
                                           uint64_t* d_empty, uint64_t* a_full, uint64_t* a_half, float* dbg,
-                                          bool skip, uint4* asave, uint32_t& amax) {
+                                          bool skip, const SaveRow& asave, uint32_t& amax) {
   if (kDbg && skip) {
     tc_fence_before_sync();
     warp_arrive(d_empty);
@@ -452,7 +462,7 @@ __device__ __forceinline__ void epi_flush(uint32_t tD_ch, uint32_t tA_ch, const 
   epi_slice32<kFmt, kRelu, kSigma, kDbg, 0, 16>(va, blob_g, boff, wsig_ch, out, sig_acc, dbg, amax);
   tmem_st_x16p(a_dst, out);
   if constexpr (kSave) {
-    if (asave) save16(asave, out);
+    if (asave.base) save16(asave, 0, out);
   }
   tmem_ld_wait();
   tc_fence_before_sync();
@@ -468,7 +478,7 @@ __device__ __forceinline__ void epi_flush(uint32_t tD_ch, uint32_t tA_ch, const 
                                                 dbg ? dbg + 32 : nullptr, amax);
   tmem_st_x16p(a_dst + 16, out);
   if constexpr (kSave) {
-    if (asave) save16(asave + 4, out);
+    if (asave.base) save16(asave, 4, out);
   }
   // A holds the next layer's full input
   tmem_st_wait();
@@ -1035,18 +1045,32 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         }
         return nullptr;
       };
-      // training: where this warp's 64 activations of (layer, half) go in the saved-activation
-      // buffer: slots 0..8 (trunk 1-8, final) are (n_points, 256) halves, slot 9 (dir) (n_points, 128)
-      auto save_at = [&](int layer, int half) -> uint4* {
+      // training: this warp's 64 activations of (layer, half) = one row of one slab of the
+      // saved-activation buffer (tiled16; slots 0..8 = trunk 1-8 + final, four slabs per tile;
+      // slot 9 = dir, two slabs; slot 10 = the embedding tile, two slabs - see save_emb)
+      auto save_at = [&](int layer, int half) -> SaveRow {
+        SaveRow r{nullptr, 0u};
         if constexpr (kSave) {
           if (P.acts != nullptr && valid) {
-            const size_t off = layer < 9 ? ((size_t)layer * P.n_points + p) * 256 + half * 128 + 64 * ch
-                                         : ((size_t)9 * P.n_points) * 256 + (size_t)p * 128 + 64 * ch;
-            return reinterpret_cast<uint4*>(P.acts + off);
+            const size_t T = (size_t)((P.n_points + 127) >> 7), tile = (size_t)(p >> 7);
+            const uint32_t rg = (uint32_t)(p & 127);
+            const size_t off = layer < 9 ? ((size_t)layer * T * 4 + tile * 4 + half * 2 + ch) * 16384
+                                         : ((size_t)9 * T * 4 + ((layer - 9) * T + tile) * 2 + ch) * 16384;
+            r.base = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(P.acts) + off + rg * 128u);
+            r.rx = rg & 7u;
           }
         }
-        return nullptr;
+        return r;
       };
+      // the tile's embedding rows (this thread wrote its own half-row in embed_tile) -> slot 10
+      if constexpr (kSave) {
+        const SaveRow er = save_at(10, 0);
+        if (er.base) {
+          const uint4* src = reinterpret_cast<const uint4*>(my_emb + ch * 16384 + row * 128);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) er.base[(uint32_t)c ^ er.rx] = src[c ^ (row & 7)];
+        }
+      }
       long long t_a = 0;
 
       // ---- trunk layers 1..7: ReLU.  The layer structure is spelled out here (the issuer

@@ -134,18 +134,34 @@ int crnerf_render_pass_opts(const void* packed, int operand, const float* rays, 
  * Training step (train_mask_grid_sample.py:186-197 calls render_rays_cross_ray under autograd).
  * crnerf_render_pass_train = crnerf_render_pass that additionally stores what the backward
  * needs, so nothing is recomputed and no (points x width) fp32 tensor is ever built:
- *   acts  crnerf_render_acts_bytes(n_rays*n_samples) bytes, 16-bit (the operand format):
- *         slots 0..8 = outputs of xyz_encoding_1..8 (post-ReLU) and xyz_encoding_final,
- *         each (n_points, 256); slot 9 = dir_encoding output (post-ReLU), (n_points, 128)
+ *   acts  crnerf_render_acts_bytes(n_rays*n_samples) bytes of 16-bit values (the operand format)
+ *         in the backward kernels' operand layout: per 128-point tile and 64-feature slab a 16 KB
+ *         block of 128-byte rows (one per point, 16-byte chunks XOR-swizzled with row % 8).
+ *         Slots: 0..8 = outputs of xyz_encoding_1..8 (post-ReLU) and xyz_encoding_final (256
+ *         wide each), 9 = dir_encoding output (post-ReLU, 128 wide), 10 = the embedding tile
+ *         (columns [0, e_xyz) xyz embedding, [96, 96 + e_dir) direction embedding).
  *   raw   (n_points, 65) fp32 = [sigmoid features | softplus sigma]   (models/nerf.py:180-181)
  * crnerf_composite_backward is the backward of rendering.py:116-143: from the gradients of
  * feature (n_rays,64), weights (n_rays,n_samples), depth (n_rays) (each may be NULL) to the
  * gradients of the pre-sigmoid features d_rgb_pre (n_points,64) and of the pre-softplus
- * density d_sigma_pre (n_points).  n_samples <= 1024.  The twelve dgrad/wgrad GEMM pairs that
- * follow are plain dense GEMMs over `acts` and are left to the caller's BLAS (the Python
- * mirror calls cuBLAS through its tensor library, see crnerf_b200/autograd.py).
+ * density d_sigma_pre (n_points).  n_samples <= 1024.
+ * crnerf_render_backward is the whole backward of one pass on the tensor cores: composite
+ * backward, then for every layer the weight gradient dW += G^T X and the input gradient
+ * G' = (G W) * relu'(X) as tcgen05 GEMMs over the saved activations (no library GEMM, no fp32
+ * (points x width) tensor).  `w` holds the CURRENT fp32 weights (their transposes are re-packed
+ * into `bwd_weights`, crnerf_render_backward_weights_bytes(e_xyz) bytes); `scratch` is
+ * crnerf_render_backward_scratch_bytes(n_points) bytes; grad_weight[i] / grad_bias[i] (fp32, the
+ * shapes of w->weight[i] / w->bias[i], i in the order of crnerf_mlp_weights) are ACCUMULATED
+ * into (zero them for a fresh gradient).  16 <= n_samples <= 1024.
  * ---------------------------------------------------------------------- */
 size_t crnerf_render_acts_bytes(int64_t n_points);
+size_t crnerf_render_backward_weights_bytes(int e_xyz);
+size_t crnerf_render_backward_scratch_bytes(int64_t n_points);
+int crnerf_render_backward(const crnerf_mlp_weights* w, int operand, const void* acts, const float* raw,
+                           const float* z_vals, const float* noise, const float* g_feature,
+                           const float* g_weights, const float* g_depth, int n_rays, int n_samples,
+                           void* bwd_weights, void* scratch, float* const* grad_weight,
+                           float* const* grad_bias, void* stream);
 int crnerf_render_pass_train(const void* packed, int operand, const float* rays, const float* view_dir,
                              const float* z_vals, const float* noise, int n_rays, int n_samples,
                              int n_freq_xyz, int n_freq_dir, float* weights, float* feature,

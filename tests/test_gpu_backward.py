@@ -5,8 +5,10 @@ Gradients are compared per parameter tensor in relative L2 norm against two refe
 
 * autograd (CPU, fp32) of the oracle's layers evaluated with the ReLU masks the kernel's own
   forward produced (read from its saved activations): this isolates the backward - composite
-  kernel, saved-activation layout, the 24 GEMMs - from forward rounding; the bar is 2e-3
-  (fp32 GEMMs) / 4e-3 (TF32), the residue being the 16-bit rounding of the saved activations;
+  kernel, saved-activation layout, the 24 tcgen05 GEMMs of csrc/backward_gemm.cu - from forward
+  rounding; the bar is 2e-3, the residue being the 16-bit rounding of the saved activations, of
+  the scaled fp16 gradient operands and of the fp16 weight transposes (all 11-bit mantissas,
+  fp32 accumulation);
 * autograd of the plain fp32 oracle (= the reference) and of its fp16-operand emulation: a
   ReLU unit whose pre-activation sits within the forward's rounding error of zero flips its
   mask, and a fraction q of flipped units costs sqrt(q) in relative L2 - around one per cent
@@ -51,17 +53,17 @@ def _masked_grads(p_cpu, rays, z, noise, g_f, g_w, g_d, masks, dir_mask):
     return {k: v.grad for k, v in p.items()}
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", 2e-3), ("tf32", 4e-3)])
+@pytest.mark.parametrize("shape", [(48, 40), (37, 16), (130, 64)])
 @pytest.mark.parametrize("peaky", [False, True])
-def test_render_pass_gradients_match_oracle_autograd(mode, tol, peaky):
+def test_render_pass_gradients_match_oracle_autograd(shape, peaky, mode="native", tol=2e-3):
     from crnerf_b200 import autograd as ag
     torch.manual_seed(0)
     models, _ = build_mirror_models(0, peaky)
     fine = models["fine"]
     p_cpu = state(fine)
     g = torch.Generator().manual_seed(11)
-    n, s = 48, 40
-    rays = oracle.pinhole_rays(6, 8, oracle.synthetic_pose(0))
+    n, s = shape          # 48 x 40 and 37 x 16 leave a partial last tile, 130 x 64 fills whole tiles
+    rays = oracle.pinhole_rays(10, 13, oracle.synthetic_pose(0))[:n].contiguous()
     z = torch.sort(torch.rand(n, s, generator=g) * 4.5 + 0.2, dim=1)[0]
     noise = torch.randn(n, s, generator=g)
     g_f, g_w, g_d = torch.randn(n, 64, generator=g), torch.randn(n, s, generator=g), torch.randn(n, generator=g)
@@ -74,9 +76,14 @@ def test_render_pass_gradients_match_oracle_autograd(mode, tol, peaky):
     from crnerf_b200 import ops
     with torch.no_grad():   # the kernel's own ReLU masks, from its saved activations
         *_, acts, _raw = ops.render_pass_train(fine.packed(), rays.cuda(), z.cuda(), noise.cuda())
-        trunk, dir_out = ops.split_acts(acts, n * s)
+        trunk, dir_out, emb_saved = ops.untile_acts(acts, n * s)
         masks = [(trunk[i] > 0).float().cpu() for i in range(8)]
         dir_mask = (dir_out > 0).float().cpu()
+        # the saved embedding tile is what the wgrad of layers 1 / 5 / dir reads
+        xyz = (rays[:, None, 0:3] + rays[:, None, 3:6] * z[:, :, None]).reshape(-1, 3)
+        assert torch.allclose(emb_saved[:, :93].float().cpu(), oracle.pos_embed(xyz, 15), rtol=0, atol=2e-3)
+        assert torch.allclose(emb_saved[:, 96:123].float().cpu(),
+                              oracle.pos_embed(rays[:, 3:6], 4).repeat_interleave(s, 0), rtol=0, atol=1e-3)
     want_mask = _masked_grads(p_cpu, rays, z, noise, g_f, g_w, g_d, masks, dir_mask)
     old = ag.BACKWARD_MATMUL
     ag.BACKWARD_MATMUL = mode
@@ -87,7 +94,9 @@ def test_render_pass_gradients_match_oracle_autograd(mode, tol, peaky):
     finally:
         ag.BACKWARD_MATMUL = old
     assert torch.allclose(f.detach().cpu(), f_ref, rtol=1e-4, atol=2e-6)
-    assert torch.allclose(w.detach().cpu(), w_ref, rtol=2e-4, atol=5e-6)
+    from parity_bounds import composite_bounds
+    bw, _ = composite_bounds(w_ref, z)      # x3 on the "peaky" stress weights, see test_ragged_sample_counts
+    assert ((w.detach().cpu().double() - w_ref.double()).abs() <= (3.0 if peaky else 1.0) * bw).all()
     errs, errs16, errs32 = {}, {}, {}
     for k, prm in fine.named_parameters():
         assert prm.grad is not None, k
@@ -166,10 +175,10 @@ def test_training_step_end_to_end_updates_parameters():
 
 
 def test_training_step_bf16_configuration():
-    """BASELINE configs[4] names bf16: bf16 tensor-core operands in the forward, bf16-operand /
-    fp32-accumulate GEMMs in the backward (saved activations consumed without conversion).  PSNR-level
-    precision only, so the check is behavioural: gradients finite, close in direction to the fp16/TF32
-    path, and the loss falls."""
+    """BASELINE configs[4] names bf16: bf16 tensor-core operands in the forward AND in the backward
+    GEMMs (saved activations, gradient tiles and weight transposes all bf16, fp32 accumulation).
+    PSNR-level precision only, so the check is behavioural: gradients finite and close in direction to
+    the fp16 path."""
     from crnerf_b200 import autograd as ag
     torch.manual_seed(0)
     models, _ = build_mirror_models(0)
@@ -180,19 +189,42 @@ def test_training_step_bf16_configuration():
     z = torch.sort(torch.rand(n, s, generator=g) * 4.5 + 0.2, dim=1)[0].cuda()
     g_f = torch.randn(n, 64, generator=g).cuda()
     grads = {}
-    for operand, mode in (("fp16", "tf32"), ("bf16", "bf16")):
+    for operand in ("fp16", "bf16"):
         fine.operand = operand
         fine.zero_grad(set_to_none=True)
-        old = ag.BACKWARD_MATMUL
-        ag.BACKWARD_MATMUL = mode
-        try:
-            w, f, d = ag.render_pass(fine, rays, z, None, None, 15, 4)
-            (f * g_f).sum().backward()
-        finally:
-            ag.BACKWARD_MATMUL = old
+        w, f, d = ag.render_pass(fine, rays, z, None, None, 15, 4)
+        (f * g_f).sum().backward()
         grads[operand] = torch.cat([p.grad.flatten() for p in fine.parameters()])
         assert torch.isfinite(grads[operand]).all()
     cos = torch.nn.functional.cosine_similarity(grads["fp16"], grads["bf16"], dim=0)
-    print(f"cosine(grad fp16/tf32, grad bf16/bf16) = {float(cos):.5f}")
+    print(f"cosine(grad fp16, grad bf16) = {float(cos):.5f}")
     assert float(cos) > 0.99
     fine.operand = "fp16"
+
+
+def test_backward_launches_no_library_gemm():
+    """The render backward is the library's own kernels: one C call, ~35 launches, and the gradients
+    of a tiny-magnitude loss survive the 16-bit gradient operands (per-pass power-of-two scale)."""
+    from crnerf_b200 import autograd as ag, ops
+    torch.manual_seed(0)
+    models, _ = build_mirror_models(0)
+    fine = models["fine"].cuda().train()
+    g = torch.Generator().manual_seed(5)
+    n, s = 64, 32
+    rays = oracle.pinhole_rays(8, 8, oracle.synthetic_pose(0)).cuda()
+    z = torch.sort(torch.rand(n, s, generator=g) * 4.5 + 0.2, dim=1)[0].cuda()
+    g_f = torch.randn(n, 64, generator=g).cuda()
+    out = {}
+    for scale in (1.0, 1e-9):
+        fine.zero_grad(set_to_none=True)
+        w, f, d = ag.render_pass(fine, rays, z, None, None, 15, 4)
+        n0 = ops.launch_count()
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+            ((f * g_f).sum() * scale).backward()
+            torch.cuda.synchronize()
+        assert 25 <= ops.launch_count() - n0 <= 60
+        names = [e.key for e in prof.key_averages()]
+        assert not any(("gemm" in k.lower() or "cutlass" in k.lower() or "cublas" in k.lower()) for k in names), names
+        out[scale] = torch.cat([p.grad.flatten() for p in fine.parameters()])
+    rel = float((out[1e-9] / 1e-9 - out[1.0]).norm() / out[1.0].norm())
+    assert rel < 1e-3, rel
