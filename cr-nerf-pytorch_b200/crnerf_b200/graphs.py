@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import torch
 
-__all__ = ["GraphedRenderer"]
+__all__ = ["GraphedRenderer", "GraphedTrainStep"]
 
 
 class GraphedRenderer:
@@ -81,3 +81,47 @@ class GraphedRenderer:
         self.rays.copy_(rays, non_blocking=non_blocking)     # H2D or D2D into the static input
         self.graph.replay()
         return self.results
+
+
+class GraphedTrainStep:
+    """One whole training step - render under autograd, decode, loss, backward, optimizer - captured
+    in a CUDA graph and replayed (the training step of train_mask_grid_sample.py:268-337 issues
+    ~340 kernels through ~1,600 tensor-library calls; at 1,024-ray patches the host, not the GPU,
+    bounds it).  Static shapes: ``step_fn()`` must read its inputs from fixed tensors (update them
+    in place between replays) and return the loss tensor; it must NOT call ``backward`` or the
+    optimizer - this class does.  The optimizer must be capturable
+    (``torch.optim.Adam(..., capturable=True)``).  Random draws inside ``step_fn`` (stratified
+    jitter, density noise) advance with every replay, as torch's graph-safe generator does.
+
+    Multi-GPU: replay the graph, then all-reduce gradients and step outside - or capture per rank
+    and keep the collective out of the graph (``optimizer=None`` skips the step inside)."""
+
+    def __init__(self, step_fn, optimizer=None, warmup: int = 3, device=None):
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.optimizer = optimizer
+
+        def whole():
+            loss = step_fn()
+            loss.backward()
+            if optimizer is not None:
+                optimizer.step()
+            return loss
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):           # eager steps: allocator warm-up, weight-range verdicts
+                if optimizer is not None:
+                    optimizer.zero_grad(set_to_none=True)
+                whole()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        if optimizer is not None:
+            optimizer.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = whole()
+
+    def __call__(self):
+        self.graph.replay()
+        return self.loss

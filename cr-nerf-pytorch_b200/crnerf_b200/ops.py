@@ -612,8 +612,21 @@ def render_backward(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tens
         w.weight[i], w.bias[i] = wi.data_ptr(), bi.data_ptr()
     w.e_xyz, w.e_dir = e_xyz, e_dir
     with torch.cuda.device(dev):
-        gw = [torch.zeros_like(weights[i], dtype=torch.float32, memory_format=torch.contiguous_format) for i in range(12)]
-        gb = [torch.zeros_like(biases[i], dtype=torch.float32) for i in range(12)]
+        # one flat buffer: weight gradients are written in full by the kernels, bias gradients are
+        # accumulated - only that tail is zeroed (one fill instead of 24)
+        nw = [int(t.numel()) for t in weights]
+        nb = [int(t.numel()) for t in biases]
+        flat = torch.empty((sum(nw) + sum(nb),), dtype=torch.float32, device=dev)
+        flat[sum(nw):].zero_()
+        if n == 0:
+            flat.zero_()
+        gw, gb, o = [], [], 0
+        for i in range(12):
+            gw.append(flat[o:o + nw[i]].view(weights[i].shape))
+            o += nw[i]
+        for i in range(12):
+            gb.append(flat[o:o + nb[i]].view(biases[i].shape))
+            o += nb[i]
         if n == 0:
             return gw, gb
         bw = torch.empty((int(lib.crnerf_render_backward_weights_bytes(e_xyz)),), dtype=torch.uint8, device=dev)

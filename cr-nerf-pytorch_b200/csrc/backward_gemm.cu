@@ -23,9 +23,11 @@
 // st[k] = max |stored value| of stage k, st[16 + k] = its scale, st[31] = max |top gradient|.
 //
 // Per layer l (top to bottom), Gm_l = dL/d(pre-activation of layer l), X_l = the layer's input:
-//   wgrad:  dW_l (out x in) += Gm_l^T X_l        M = out features, N = in features, K = points;
+//   wgrad:  dW_l (out x in) = Gm_l^T X_l         M = out features, N = in features, K = points;
 //           each CTA reduces its share of the tiles in TMEM (256 x 256 fp32 = all 512 columns) and
-//           adds it to the fp32 gradient with red.global.add (.v4 where alignment allows)
+//           stores its partial; ONE reduce kernel per pass then sums the partials of all 13
+//           products in CTA order (deterministic; atomics on 148 x 65 k addresses per layer cost
+//           more than the GEMM - measured 47 us per layer against 20 us of HBM time)
 //   dgrad:  Gm_{l-1} = (Gm_l W_l) * relu'(X_l)   M = points, N = in features, K = out features;
 //           W_l^T stays resident in shared memory, the epilogue adds the sigma-head term at h8,
 //           applies the ReLU mask from the saved activation, accumulates the bias gradient of
@@ -100,11 +102,6 @@ __global__ void zero_tail_kernel(uint8_t* base, int n_slabs, long long slab_stri
   uint4* dst = reinterpret_cast<uint4*>(base + (size_t)blockIdx.x * slab_stride + (size_t)r0 * 128);
   const int n16 = (128 - r0) * 8;
   for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = make_uint4(0, 0, 0, 0);
-}
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
-               : "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -224,14 +221,64 @@ __global__ void bwd_pack_kernel(const __grid_constant__ BwdPackParams P) {
 struct WgradParams {
   const uint8_t* g;     // tiled16 (P x 64*g_slabs)
   const uint8_t* x;     // tiled16, x_slabs_total slabs per tile; the kernel reads slabs [xs0, xs0 + nxs)
-  float* dw;            // fp32 (rows x ldw), accumulated with atomics
-  const float* scale;   // scale of G's stage
+  float* partial;       // fp32 [gridDim.x][nrows][64 * nxs]: this launch's per-CTA partial products
   int g_slabs, x_slabs_total, xs0, nxs;
-  int ldw, c0;          // output column of X-window column xcol0
-  int xcol0, ncols;     // valid columns of the X window
   int nrows;            // valid rows (output features)
   int n_tiles;
 };
+// one product's share of the reduce kernel
+struct ReduceJob {
+  const float* partial;
+  float* dw;            // fp32 (rows x ldw)
+  const float* scale;   // scale of G's stage
+  int n_parts, nrows, n_mma;
+  int ldw, c0;          // output column of X-window column xcol0
+  int xcol0, ncols;     // valid columns of the X window
+};
+constexpr int kMaxJobs = 16;
+struct ReduceParams {
+  ReduceJob job[kMaxJobs];
+  int n_jobs;
+};
+
+// dW[row][c0 + col - xcol0] = (sum over CTAs of partial[cta][row][col]) / scale, fixed order.
+// One thread per four consecutive columns (16-byte loads), eight partials in flight.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ ReduceParams P) {
+  const ReduceJob& J = P.job[blockIdx.y];
+  const int n = J.nrows * J.n_mma;
+  const int i = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (i >= n) return;
+  const int row = i / J.n_mma, col = i % J.n_mma;
+  if (col + 3 < J.xcol0 || col >= J.xcol0 + J.ncols) return;
+  const float4* p = reinterpret_cast<const float4*>(J.partial + i);
+  const size_t stride = (size_t)n / 4;
+  float4 acc[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int b = 0;
+  for (; b + 7 < J.n_parts; b += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float4 v = __ldcs(p + (size_t)(b + u) * stride);
+      acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+    }
+  }
+  for (; b < J.n_parts; ++b) {
+    const float4 v = __ldcs(p + (size_t)b * stride);
+    acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
+  }
+  const float inv = 1.f / *J.scale;
+  float r[4];
+  r[0] = ((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x)) + ((acc[4].x + acc[5].x) + (acc[6].x + acc[7].x));
+  r[1] = ((acc[0].y + acc[1].y) + (acc[2].y + acc[3].y)) + ((acc[4].y + acc[5].y) + (acc[6].y + acc[7].y));
+  r[2] = ((acc[0].z + acc[1].z) + (acc[2].z + acc[3].z)) + ((acc[4].z + acc[5].z) + (acc[6].z + acc[7].z));
+  r[3] = ((acc[0].w + acc[1].w) + (acc[2].w + acc[3].w)) + ((acc[4].w + acc[5].w) + (acc[6].w + acc[7].w));
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = col + e;
+    if (c >= J.xcol0 && c < J.xcol0 + J.ncols) J.dw[(size_t)row * J.ldw + J.c0 + (c - J.xcol0)] = r[e] * inv;
+  }
+}
 constexpr int kWgStages = 3;
 
 template <int kFmt>
@@ -313,38 +360,28 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       __syncwarp();
     }
   } else {
-    // ---- epilogue (warps 2..5: TMEM lane quarter = warp % 4): dW += acc / S
+    // ---- epilogue (warps 2..5: TMEM lane quarter = warp % 4): this CTA's partial product
+    const int q = warp & 3;
+    float* part = P.partial + (size_t)blockIdx.x * P.nrows * n_mma;
     if (n_steps > 0) {
       mbar_wait(done, 0, 3);
       tc_fence_after_sync();
-      const float inv = 1.f / *P.scale;
-      const int q = warp & 3;
-      const bool vec = (P.ldw % 4 == 0) && ((P.c0 - P.xcol0) % 4 == 0) && (P.xcol0 % 4 == 0) && (P.ncols % 4 == 0) &&
-                       ((reinterpret_cast<uintptr_t>(P.dw) & 15) == 0);
-      for (int mh = 0; mh < m_halves; ++mh) {
-        const int rowf = mh * 128 + q * 32 + lane;
-        for (int c0 = 0; c0 < n_mma; c0 += 32) {
-          uint32_t v[32];
+    }
+    for (int mh = 0; mh < m_halves; ++mh) {
+      const int rowf = mh * 128 + q * 32 + lane;
+      for (int c0 = 0; c0 < n_mma; c0 += 32) {
+        uint32_t v[32];
+        if (n_steps > 0) {
           tmem_ld_x32(tmem + (uint32_t)mh * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
           tmem_ld_wait();
-          if (rowf < P.nrows) {
-            float* drow = P.dw + (size_t)rowf * P.ldw + (P.c0 - P.xcol0);
-            if (vec) {
+        } else {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const int c = c0 + j;
-                if (c >= P.xcol0 && c < P.xcol0 + P.ncols)
-                  red_add_v4(drow + c, __uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv,
-                             __uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
-              }
-            } else {
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        if (rowf < P.nrows) {
+          uint4* dst = reinterpret_cast<uint4*>(part + (size_t)rowf * n_mma + c0);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int c = c0 + j;
-                if (c >= P.xcol0 && c < P.xcol0 + P.ncols) atomicAdd(drow + c, __uint_as_float(v[j]) * inv);
-              }
-            }
-          }
+          for (int j = 0; j < 8; ++j) dst[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
       }
     }
@@ -600,8 +637,10 @@ size_t bwd_tiled_bytes(int64_t n_points, int features) {
 // scratch of one backward pass: d_rgb fp32, d_sig fp32, two ping-pong gradient buffers (256 wide),
 // the rgb / sigma top tiles, the amax word
 struct BwdScratch {
-  size_t d_rgb, d_sig, g0, g1, g_rgb, g_sig, amax, total;
+  size_t d_rgb, d_sig, g0, g1, g_rgb, g_sig, amax, partial, total;
 };
+// floats of partial products one CTA writes over a whole pass (13 products; see backward_chain)
+constexpr size_t kPartialFloatsPerCta = 1 * 256 + 64 * 128 + 128 * 256 + 128 * 64 + 8 * 256 * 256 + 2 * 256 * 128;
 static BwdScratch bwd_scratch(int64_t P) {
   BwdScratch s;
   size_t o = 0;
@@ -617,6 +656,8 @@ static BwdScratch bwd_scratch(int64_t P) {
   s.g_rgb = take(bwd_tiled_bytes(P, 64));
   s.g_sig = take(bwd_tiled_bytes(P, 64));
   s.amax = take(256);
+  const int64_t tiles = (P + 127) / 128;
+  s.partial = take((size_t)std::min<int64_t>(num_sms(), tiles) * kPartialFloatsPerCta * sizeof(float));
   s.total = o;
   return s;
 }
@@ -710,9 +751,15 @@ static int backward_chain(const crnerf_mlp_weights* w, const void* acts, const f
     return A + (k < 9 ? (size_t)k * T * 4 : (size_t)9 * T * 4 + (size_t)(k - 9) * T * 2) * kSlab;
   };
   int stage = 0;   // stage of the gradient tiles currently at the head of the chain
+  ReduceParams red;
+  memset(&red, 0, sizeof(red));
+  const int wg_grid = std::min(num_sms(), T);
+  float* part_next = reinterpret_cast<float*>(base + sc.partial);
   auto wgrad = [&](const uint8_t* g, int g_slabs, const uint8_t* x, int xtot, int xs0, int nxs, float* dw, int ldw,
                    int c0, int xcol0, int ncols, int nrows) {
-    WgradParams wp{g, x, dw, stw + kStScale + stage, g_slabs, xtot, xs0, nxs, ldw, c0, xcol0, ncols, nrows, T};
+    WgradParams wp{g, x, part_next, g_slabs, xtot, xs0, nxs, nrows, T};
+    red.job[red.n_jobs++] = ReduceJob{part_next, dw, stw + kStScale + stage, wg_grid, nrows, nxs * 64, ldw, c0, xcol0, ncols};
+    part_next += (size_t)wg_grid * nrows * nxs * 64;
     return run_wgrad<kFmt>(wp, st);
   };
   auto dgrad = [&](const uint8_t* g, int g_slabs, int layer_idx, const uint8_t* act, int atot, int as0, uint8_t* out,
@@ -747,6 +794,9 @@ static int backward_chain(const crnerf_mlp_weights* w, const void* acts, const f
   }
   CK_(wgrad(gbuf[cur], 4, slot(10), 2, 0, 2, gw[0], e_xyz, 0, 0, e_xyz, 256));          // layer 0: X = xyz embedding
 #undef CK_
+  // all 13 weight gradients: sum the per-CTA partials (fixed order)
+  wgrad_reduce_kernel<<<dim3(64, red.n_jobs), 256, 0, st>>>(red);
+  count_launch();
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;
 }

@@ -125,11 +125,14 @@ class NeRF_sigma(nn.Module):
         lin = self._linears()
         training = self.wants_grad()
         if training:
-            if self._packed is not None:
+            # inside a CUDA-graph capture (crnerf_b200.graphs.GraphedTrainStep) nothing may touch
+            # the host: no verdict read-back there (run a few eager steps first, as the helper does)
+            capturing = torch.cuda.is_current_stream_capturing()
+            if self._packed is not None and not capturing:
                 self._packed.poll_range()
             self._packed = ops.pack_mlp([m.weight for m in lin], [m.bias for m in lin],
                                         self.in_channels_xyz, self.in_channels_dir, self.operand,
-                                        check_range="deferred")
+                                        check_range=False if capturing else "deferred")
             self._packed_key = None
             return self._packed
         key = (self.operand, _weights_epoch[0], self._epoch) + tuple(

@@ -151,8 +151,9 @@ int crnerf_render_pass_opts(const void* packed, int operand, const float* rays, 
  * (points x width) tensor).  `w` holds the CURRENT fp32 weights (their transposes are re-packed
  * into `bwd_weights`, crnerf_render_backward_weights_bytes(e_xyz) bytes); `scratch` is
  * crnerf_render_backward_scratch_bytes(n_points) bytes; grad_weight[i] / grad_bias[i] (fp32, the
- * shapes of w->weight[i] / w->bias[i], i in the order of crnerf_mlp_weights) are ACCUMULATED
- * into (zero them for a fresh gradient).  16 <= n_samples <= 1024.
+ * shapes of w->weight[i] / w->bias[i], i in the order of crnerf_mlp_weights): weight gradients are
+ * WRITTEN (every element; per-CTA partial products summed in a fixed order - run-to-run identical),
+ * bias gradients are ACCUMULATED with atomics (zero them first).  16 <= n_samples <= 1024.
  * ---------------------------------------------------------------------- */
 size_t crnerf_render_acts_bytes(int64_t n_points);
 size_t crnerf_render_backward_weights_bytes(int e_xyz);

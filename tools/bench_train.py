@@ -16,7 +16,7 @@ from crnerf_b200 import synthetic
 import torch.distributed as dist
 
 
-def make_step(dev, world, rank, n_rays=1024, ns=64, ni=64, operand="fp16", bwd=None):
+def make_step(dev, world, rank, n_rays=1024, ns=64, ni=64, operand="fp16", bwd=None, capturable=False):
     """Build the models + optimizer and return (step_fn, models, margs, rays, style, target, side)."""
     from bench import build_models
     from models.nerf import PosEmbedding
@@ -34,7 +34,7 @@ def make_step(dev, world, rank, n_rays=1024, ns=64, ni=64, operand="fp16", bwd=N
     style = torch.rand(1, 64, 32, 32, device=dev)
     target = torch.rand(side * side, 3, device=dev)
     params = [p for m in models.values() for p in m.parameters()]
-    opt = torch.optim.Adam(params, lr=5e-4)
+    opt = torch.optim.Adam(params, lr=5e-4, capturable=capturable)
     flat_n = sum(p.numel() for p in params)
 
     def allreduce_grads():
@@ -45,19 +45,24 @@ def make_step(dev, world, rank, n_rays=1024, ns=64, ni=64, operand="fp16", bwd=N
             for p in params:
                 p.grad.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
 
-    def step_ours():
+    def loss_fn():
         res = render_rays_cross_ray(models, emb, rays, None, ns, False, 1.0, 1.0, ni, 32768, False, args=margs)
         loss = 0
         for typ in ("coarse", "fine"):
             feat = res[f"feature_{typ}"].t().reshape(1, 64, side, side)
             rgb = models["decoder"](feat, style).reshape(3, -1).t()
             loss = loss + 0.5 * ((rgb - target) ** 2).mean()
+        return loss
+
+    def step_ours():
+        loss = loss_fn()
         opt.zero_grad(set_to_none=True)
         loss.backward()
         allreduce_grads()
         opt.step()
         return loss
 
+    step_ours.loss_fn, step_ours.opt = loss_fn, opt
     return step_ours, models, margs, rays, style, target, side, flat_n
 
 
@@ -90,6 +95,25 @@ def measure(dev, world, rank, barrier, reps=10, warm=3, n_rays=1024, ns=64, ni=6
         out[f"train_ray_samples_per_s_{operand}"] = world * n_rays * (ns + ni) / (ms * 1e-3)
         out[f"train_native_launches_per_step_{operand}"] = (ops.launch_count() - n0) / reps
         out[f"train_loss_{operand}"] = float(loss)
+        if world == 1:
+            # the same step replayed as one CUDA graph (crnerf_b200.graphs.GraphedTrainStep): the eager
+            # step is bound by ~1,600 host-side tensor-library calls, not by the GPU
+            try:
+                from crnerf_b200.graphs import GraphedTrainStep
+                gstep, *_r = make_step(dev, world, rank, n_rays, ns, ni, operand, None, capturable=True)
+                graphed = GraphedTrainStep(gstep.loss_fn, gstep.opt)
+                for _ in range(warm):
+                    graphed()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(reps):
+                    gl = graphed()
+                e1.record()
+                torch.cuda.synchronize()
+                out[f"train_step_ms_{operand}_graphed"] = e0.elapsed_time(e1) / reps
+                out[f"train_loss_{operand}_graphed"] = float(gl)
+            except Exception as e:   # noqa: BLE001
+                out[f"train_graph_error_{operand}"] = f"{type(e).__name__}: {e}"[:300]
     out["train"] = {"workload": f"{n_rays}-ray (32x32) patch per rank x ({ns}+{ni}) samples, perturb=1, noise_std=1, "
                                 "style_net decode of coarse and fine, MSE, backward, Adam",
                     "parallelism": f"data parallel x{world}, one flat gradient all-reduce ({flat_n * 4} B) per step",
@@ -105,7 +129,8 @@ def main():
     ap.add_argument("--ni", type=int, default=64)
     ap.add_argument("--no-eager", action="store_true")
     ap.add_argument("--operand", default="fp16", choices=["fp16", "bf16"], help="tensor-core operand format of the MLP")
-    ap.add_argument("--bwd", default=None, choices=["native", "tf32", "fp32", "bf16"], help="backward GEMM path")
+    ap.add_argument("--bwd", default=None, choices=["native"], help="(kept for old command lines)")
+    ap.add_argument("--graph", action="store_true", help="also time the step replayed as one CUDA graph")
     a = ap.parse_args()
     import crnerf_oracle as oracle
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
@@ -150,10 +175,17 @@ def main():
         return e0.elapsed_time(e1) / steps, (time.perf_counter() - t0) * 1e3 / steps, float(l)
 
     ours_dev, ours_wall, l1 = timeit(step_ours, a.steps)
+    graphed_ms = None
+    if a.graph and world == 1:
+        from crnerf_b200.graphs import GraphedTrainStep
+        gstep, *_r = make_step(dev, world, rank, a.rays, a.ns, a.ni, a.operand, None, capturable=True)
+        graphed = GraphedTrainStep(gstep.loss_fn, gstep.opt)
+        graphed_ms, _, lg = timeit(graphed, a.steps)
     out = {"workload": f"train step, {a.rays} rays x ({a.ns}+{a.ni}), perturb=1 noise=1, style_net decode x2, MSE, Adam",
            "operand": a.operand, "backward_gemm": ag.BACKWARD_MATMUL,
            "n_gpus": world, "ours_ms_device": ours_dev, "ours_ms_wall": ours_wall,
-           "ours_ray_samples_per_s": world * a.rays * (a.ns + a.ni) / (ours_wall * 1e-3), "loss": l1}
+           "ours_ray_samples_per_s": world * a.rays * (a.ns + a.ni) / (ours_wall * 1e-3), "loss": l1,
+           "ours_ms_graphed": graphed_ms}
     if not a.no_eager and world == 1:
         try:
             eg_dev, eg_wall, l2 = timeit(step_eager, max(3, a.steps // 4))
