@@ -81,6 +81,8 @@ SIGNATURES = {
                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "crnerf_generate_rays": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int,
                                        C.c_int, C.c_void_p, C.c_void_p]),
+    "crnerf_grid_patch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                    C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_float] + [C.c_void_p] * 7),
     "crnerf_rgb_to_u8": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "crnerf_encoder_packed_bytes": (C.c_size_t, []),
     "crnerf_encoder_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),

@@ -705,6 +705,40 @@ def generate_rays(height: int, width: int, K, c2w, near: float, far: float, devi
     return rays
 
 
+def grid_patch(all_rays: torch.Tensor, all_rgbs: torch.Tensor, lin_w: torch.Tensor, lin_h: torch.Tensor,
+               img_w: float, img_h: float, image_offset: float, scale: float, h_offset: float, w_offset: float,
+               status: Optional[torch.Tensor] = None):
+    """One grid-sampled training patch gathered from the device-resident ray cache (reference
+    datasets/phototourism_mask_grid_sample.py:241-275).  Returns (rays (g*g,8), ts (g*g) int64,
+    rgbs (g*g,3), rgb_idx (g*g) int64, uv_sample (g*g,2)); bit-exact with the reference, whose image
+    sizes and cache offset are fp32 values (``image_offset`` = the fp32 sum of w*h before the image)."""
+    lib = _lib.load()
+    _need(all_rays, "all_rays")
+    _need(all_rgbs, "all_rgbs")
+    if all_rays.dim() != 2 or all_rays.shape[1] != 9 or all_rgbs.shape != (all_rays.shape[0], 3):
+        raise ValueError("all_rays must be (M,9) and all_rgbs (M,3)")
+    if not (all_rays.is_contiguous() and all_rgbs.is_contiguous()):
+        raise ValueError("the ray cache must be contiguous (it is gathered in place)")
+    dev = all_rays.device
+    g = int(lin_w.numel())
+    if int(lin_h.numel()) != g:
+        raise ValueError("lin_w and lin_h must have the same length")
+    lw = lin_w.to(dev, torch.float32).contiguous()
+    lh = lin_h.to(dev, torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        rays = torch.empty((g * g, 8), dtype=torch.float32, device=dev)
+        ts = torch.empty((g * g,), dtype=torch.int64, device=dev)
+        rgbs = torch.empty((g * g, 3), dtype=torch.float32, device=dev)
+        idx = torch.empty((g * g,), dtype=torch.int64, device=dev)
+        uv = torch.empty((g * g, 2), dtype=torch.float32, device=dev)
+        check(lib.crnerf_grid_patch(lw.data_ptr(), lh.data_ptr(), g, float(img_w), float(img_h), float(scale),
+                                    float(h_offset), float(w_offset), all_rays.data_ptr(), all_rgbs.data_ptr(),
+                                    int(all_rays.shape[0]), float(image_offset), rays.data_ptr(), ts.data_ptr(),
+                                    rgbs.data_ptr(), idx.data_ptr(), uv.data_ptr(),
+                                    status.data_ptr() if status is not None else None, _stream(dev)))
+    return rays, ts, rgbs, idx, uv
+
+
 def rgb_to_u8(rgb: torch.Tensor) -> torch.Tensor:
     """(1,3,H,W) or (3,n) fp32 rgb -> (H,W,3) / (n,3) uint8 = uint8(clip(x,0,1)*255), reference eval.py:295-297."""
     lib = _lib.load()

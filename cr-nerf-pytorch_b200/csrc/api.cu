@@ -80,6 +80,10 @@ int style_forward(const crnerf_style_weights* w, const float* content, int64_t n
                   float* transmatrix, float* fused, float* scratch, cudaStream_t st);
 int cnn_forward(const crnerf_cnn_weights* cw, const float* x, int64_t n, int64_t ps, int64_t cs,
                 float* out, float* scratch, cudaStream_t st);
+int grid_patch(const float* lin_w, const float* lin_h, int g, float img_w, float img_h, float scale, float h_off,
+               float w_off, const float* all_rays, const float* all_rgbs, long long n_cache_rows,
+               float image_offset, float* rays, long long* ts, float* rgbs, long long* rgb_idx, float* uv,
+               int* status, cudaStream_t st);
 int generate_rays(const float* intr4_host, const float* c2w12_host, float near, float far, int H, int W,
                   float* rays, cudaStream_t st);
 int rgb_to_u8(const float* rgb, int64_t n, uint8_t* out, cudaStream_t st);
@@ -295,6 +299,17 @@ int crnerf_generate_rays(const float* intrinsics_host, const float* c2w_host, fl
   int rc = device_check();
   if (rc) return rc;
   return generate_rays(intrinsics_host, c2w_host, near, far, height, width, rays, (cudaStream_t)stream);
+}
+
+int crnerf_grid_patch(const float* lin_w, const float* lin_h, int grid, float img_w, float img_h, float scale,
+                      float h_offset, float w_offset, const float* all_rays, const float* all_rgbs,
+                      int64_t n_cache_rows, float image_offset, float* rays, int64_t* ts, float* rgbs,
+                      int64_t* rgb_idx, float* uv_sample, int32_t* status_dev, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return grid_patch(lin_w, lin_h, grid, img_w, img_h, scale, h_offset, w_offset, all_rays, all_rgbs,
+                    (long long)n_cache_rows, image_offset, rays, (long long*)ts, rgbs,
+                    (long long*)rgb_idx, uv_sample, status_dev, (cudaStream_t)stream);
 }
 
 int crnerf_rgb_to_u8(const float* rgb, int64_t n_pixels, uint8_t* out, void* stream) {

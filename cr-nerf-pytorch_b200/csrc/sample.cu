@@ -248,6 +248,61 @@ __global__ void rgb_to_u8_kernel(const float* __restrict__ rgb, long long n, uin
   }
 }
 
+// ---------------------------------------------------------------------------
+// Grid-sampled training patch (reference datasets/phototourism_mask_grid_sample.py:241-275): a
+// g x g lattice (g = sqrt(batch_size)) laid over one training image at a random scale / offset;
+// lattice point (i, j) - i along the width, j along the height - lands on pixel
+//   w = floor((lin_w[i]*scale + w_off) * img_w),  h = floor((lin_h[j]*scale + h_off) * img_h)
+// and output row r = j*g + i (the reference's .permute(1, 0).view(-1)) gathers that pixel's
+// cached ray row (o3 d3 near far | image id, the (N,9) ray cache) and rgb.  Every product and sum is
+// rounded separately, as torch's elementwise ops do, so indices and uv match bit for bit; the two
+// linspace vectors come from the caller (torch.linspace, as the reference builds them).
+// The reference keeps the image sizes as fp32 (all_imgs_wh is a float tensor, :197), so the
+// offset of the image inside the cache is an fp32 sum and the cache row is formed in fp32
+// (int64 index + 0-dim float tensor promotes to float32, :266): beyond 2^24 rows that rounds, and
+// the same rounded row is gathered here.
+struct GridPatchParams {
+  const float* lin_w;
+  const float* lin_h;
+  const float* all_rays;   // (M, 9)
+  const float* all_rgbs;   // (M, 3)
+  long long n_cache_rows;
+  float image_offset;      // fp32, as the reference computes it
+  float scale, h_off, w_off;
+  float img_w, img_h;
+  int g;
+  float* rays;        // (g*g, 8)
+  long long* ts;      // (g*g)
+  float* rgbs;        // (g*g, 3)
+  long long* rgb_idx; // (g*g)  index inside the image
+  float* uv;          // (g*g, 2)  [h_sb, w_sb]
+  int* status;        // set to 1 if a gathered row falls outside the cache (never silently clamped)
+};
+__global__ void grid_patch_kernel(const __grid_constant__ GridPatchParams P) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= P.g * P.g) return;
+  const int j = r / P.g, i = r - j * P.g;
+  const float h_sb = __fadd_rn(__fmul_rn(P.lin_h[j], P.scale), P.h_off);
+  const float w_sb = __fadd_rn(__fmul_rn(P.lin_w[i], P.scale), P.w_off);
+  const float h = floorf(__fmul_rn(h_sb, P.img_h));
+  const float w = floorf(__fmul_rn(w_sb, P.img_w));
+  const long long idx = (long long)__fadd_rn(w, __fmul_rn(h, P.img_w));   // fp32, then .long()
+  const long long row = (long long)__fadd_rn((float)idx, P.image_offset);  // (idx + offset_f32).long()
+  P.rgb_idx[r] = idx;
+  P.uv[2 * r] = h_sb;
+  P.uv[2 * r + 1] = w_sb;
+  if (row < 0 || row >= P.n_cache_rows) {
+    if (P.status) *P.status = 1;
+    return;
+  }
+  const float* src = P.all_rays + row * 9;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) P.rays[(long long)r * 8 + k] = src[k];
+  P.ts[r] = (long long)src[8];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) P.rgbs[(long long)r * 3 + k] = P.all_rgbs[row * 3 + k];
+}
+
 int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -332,6 +387,21 @@ int sample_pdf(const float* bins_or_z, const float* weights, const float* u, int
     sample_pdf_kernel<false><<<grid, 128, smem, st>>>(bins_or_z, weights, u, u_stride, n_rays, m,
                                                       n_imp, eps, samples, sorted, cdf_pad, sort_pad);
   }
+  count_launch();
+  CRNERF_CUDA(cudaGetLastError());
+  return CRNERF_OK;
+}
+
+int grid_patch(const float* lin_w, const float* lin_h, int g, float img_w, float img_h, float scale, float h_off,
+               float w_off, const float* all_rays, const float* all_rgbs, long long n_cache_rows,
+               float image_offset, float* rays, long long* ts, float* rgbs, long long* rgb_idx, float* uv,
+               int* status, cudaStream_t st) {
+  CRNERF_REQUIRE(lin_w && lin_h && all_rays && all_rgbs && rays && ts && rgbs && rgb_idx && uv, "null argument");
+  CRNERF_REQUIRE(g >= 1 && g <= 4096 && img_w >= 1.f && img_h >= 1.f, "bad lattice / image size");
+  CRNERF_REQUIRE(n_cache_rows >= 1 && image_offset >= 0.f, "bad ray cache extent");
+  GridPatchParams P{lin_w, lin_h, all_rays, all_rgbs, n_cache_rows, image_offset, scale, h_off, w_off,
+                    img_w, img_h, g, rays, ts, rgbs, rgb_idx, uv, status};
+  grid_patch_kernel<<<(g * g + 127) / 128, 128, 0, st>>>(P);
   count_launch();
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;

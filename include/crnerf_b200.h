@@ -248,6 +248,27 @@ int crnerf_pos_embed(const float* x, int64_t n, int n_freqs, float* out, void* s
 int crnerf_generate_rays(const float* intrinsics_host, const float* c2w_host, float near, float far,
                          int height, int width, float* rays, void* stream);
 
+/* Grid-sampled training patch (datasets/phototourism_mask_grid_sample.py:241-275): the g x g
+ * lattice (g = sqrt(batch_size)) of one training image at a random scale / offset, gathered from
+ * the ray cache resident in GPU memory - replaces the DataLoader worker's index arithmetic, the
+ * three fancy-index gathers and the per-step host->device copy of the batch.
+ *   lin_w, lin_h   (grid) device: linspace(0, 1-1/img_w, g) and linspace(0, 1-1/img_h, g) (:246-247)
+ *   scale, h_offset, w_offset    the three host-side uniform draws (:252-254)
+ *   all_rays (n_cache_rows, 9) = [o3 d3 near far image_id]  (the .npy ray cache, :204-208),
+ *   all_rgbs (n_cache_rows, 3); image_offset = sum of w*h of the images before this one (:266).
+ *   The reference holds image sizes as fp32 (:197), so img_w / img_h / image_offset are floats and
+ *   the cache row is (float(rgb_idx) + image_offset) rounded to fp32, then truncated - reproduced
+ *   as is (it only rounds once the cache exceeds 2^24 rows).
+ * Outputs, row r = j*g + i (lattice column i along the width, row j along the height):
+ *   rays (g*g, 8), ts (g*g) int64, rgbs (g*g, 3), rgb_idx (g*g) int64 (pixel index w + h*img_w
+ *   inside the image, computed in fp32 as the reference does), uv_sample (g*g, 2) = [h_sb, w_sb].
+ * Bit-exact with the reference.  status_dev (may be NULL) is set to 1 if a row index leaves the
+ * cache (inconsistent img_w/img_h/offset); such rows are left unwritten, never clamped. */
+int crnerf_grid_patch(const float* lin_w, const float* lin_h, int grid, float img_w, float img_h, float scale,
+                      float h_offset, float w_offset, const float* all_rays, const float* all_rgbs,
+                      int64_t n_cache_rows, float image_offset, float* rays, int64_t* ts, float* rgbs,
+                      int64_t* rgb_idx, float* uv_sample, int32_t* status_dev, void* stream);
+
 /* Output stage of the eval loop (eval.py:295-297): rgb (3, n_pixels) planar fp32 (what
  * crnerf_style_forward writes) -> out (n_pixels, 3) interleaved uint8 = uint8(clip(x,0,1)*255),
  * so a frame leaves the GPU as 3 B/pixel instead of 12. */

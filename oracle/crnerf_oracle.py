@@ -417,3 +417,28 @@ def encoder_forward(p: Params, x: Tensor) -> Tensor:
     h = act(conv("conv6", pad(h)))
     h = F.adaptive_avg_pool2d(h, 32)
     return act(conv("conv7", h))
+
+
+# --------------------------------------------------------------------------
+# f2  grid-sampled training patch  (reference datasets/phototourism_mask_grid_sample.py:240-275)
+# --------------------------------------------------------------------------
+def grid_patch(all_rays: Tensor, all_rgbs: Tensor, all_imgs_wh: Tensor, sample_ts: int, batch_size: int,
+               scale: Tensor, h_offset: Tensor, w_offset: Tensor) -> Dict[str, Tensor]:
+    """The lattice arithmetic and gathers of the training ``__getitem__`` for image ``sample_ts``,
+    given the three uniform draws (scale, h_offset, w_offset: (1,) fp32 tensors, :252-254).
+    ``all_imgs_wh`` is the reference's fp32 (n_img, 2) tensor (:197): sizes stay 0-dim fp32 tensors,
+    so ``1 - 1/img_w``, ``h_sb * img_h`` and the cache offset are fp32 arithmetic, as there."""
+    img_w, img_h = all_imgs_wh[sample_ts]
+    g = int(math.sqrt(batch_size))
+    w_samples, h_samples = torch.meshgrid([torch.linspace(0, 1 - 1 / img_w, g),
+                                           torch.linspace(0, 1 - 1 / img_h, g)], indexing="ij")   # :246-247
+    h_sb = h_samples * scale + h_offset                                                            # :255
+    w_sb = w_samples * scale + w_offset
+    h = (h_sb * img_h).floor()                                                                     # :257
+    w = (w_sb * img_w).floor()
+    idx = (w + h * img_w).permute(1, 0).contiguous().view(-1).long()                               # :260
+    uv = torch.cat((h_sb.permute(1, 0).contiguous().view(-1, 1),
+                    w_sb.permute(1, 0).contiguous().view(-1, 1)), -1)                              # :262
+    rows = (idx + (all_imgs_wh[:sample_ts, 0] * all_imgs_wh[:sample_ts, 1]).sum()).long()          # :264
+    return {"rays": all_rays[rows, :8], "ts": all_rays[rows, 8].long(), "rgbs": all_rgbs[rows],
+            "rgb_idx": idx, "uv_sample": uv}

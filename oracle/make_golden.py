@@ -304,9 +304,67 @@ def case_encoder(lst):
     print("  encoder_sameoutputsize: pinned (3 sizes)")
 
 
+def case_grid_patch():
+    """The training ``__getitem__`` of datasets/phototourism_mask_grid_sample.py:240-275.  The
+    dataset module itself cannot be imported here (kornia, torchvision, COLMAP readers), so the
+    method's source is cut out of the UNMODIFIED file with ``ast`` and executed as it stands against
+    a stand-in ``self`` that carries the attributes it reads."""
+    import ast
+    import math
+    import numpy as np
+    path = os.path.join(REF, "datasets", "phototourism_mask_grid_sample.py")
+    src = open(path, encoding="utf-8").read()
+    tree = ast.parse(src)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "PhototourismDataset")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "__getitem__")
+    mod = ast.Module(body=[fn], type_ignores=[])
+    gv = types.SimpleNamespace(current_epoch=0)
+    ns = {"torch": torch, "np": np, "sqrt": math.sqrt, "exp": math.exp, "global_val": gv}
+    exec(compile(mod, path, "exec"), ns)
+    getitem = ns["__getitem__"]
+
+    g = torch.Generator().manual_seed(77)
+    wh = torch.Tensor([[40, 30], [37, 53], [64, 48], [51, 29]])            # (w, h) per image, fp32 as :197
+    n_rows = int((wh[:, 0] * wh[:, 1]).sum())
+    all_rays = torch.randn(n_rows, 9, generator=g)
+    all_rays[:, 8] = torch.repeat_interleave(torch.arange(4, dtype=torch.float32) + 10, (wh[:, 0] * wh[:, 1]).long())
+    all_rgbs = torch.rand(n_rows, 3, generator=g)
+    imgs = [torch.rand(3, int(h), int(w), generator=g) for w, h in wh]
+    out = {"kind": "grid_patch", "all_rays": all_rays, "all_rgbs": all_rgbs, "all_imgs_wh": wh, "cases": []}
+    for ci, (batch, anneal, min_scale, epoch, idx) in enumerate([(1024, -1, 0.25, 0, 0), (1024, -1, 0.5, 3, 17),
+                                                                 (256, 0.0025, 0.25, 1, 5), (64, -1, 0.9, 2, 2),
+                                                                 (1024, -1, 0.25, 7, 123)]):
+        me = types.SimpleNamespace(split="train", all_imgs=imgs, all_imgs_wh=wh, batch_size=batch,
+                                   scale_anneal=anneal, min_scale=min_scale, all_rays=all_rays,
+                                   all_rgbs=all_rgbs, iterations=n_rows // batch)
+        gv.current_epoch = epoch
+        torch.manual_seed(500 + ci)
+        ref = getitem(me, idx)
+        # replay the host draws (same calls, same order) and pin the oracle's arithmetic
+        torch.manual_seed(500 + ci)
+        step = epoch * me.iterations + idx
+        np.random.seed(step)
+        ts = np.random.randint(0, len(imgs))
+        img_w, img_h = wh[ts]
+        msc = min(max(min_scale, 1. * math.exp(-step * anneal)), 0.9) if anneal > 0 else min_scale
+        scale = torch.Tensor(1).uniform_(msc, 1.)
+        h_off = torch.Tensor(1).uniform_(0, (1 - scale.item()) * (1 - 1 / img_h))
+        w_off = torch.Tensor(1).uniform_(0, (1 - scale.item()) * (1 - 1 / img_w))
+        mine = oracle.grid_patch(all_rays, all_rgbs, wh, ts, batch, scale, h_off, w_off)
+        for k in mine:
+            assert_equal(f"grid_patch:{k}", mine[k], ref[k])
+        assert ref["min_scale_cur"] == msc and torch.equal(ref["img_wh"], wh[ts]) and ref["whole_img"] is imgs[ts]
+        out["cases"].append({"batch_size": batch, "scale_anneal": anneal, "min_scale": min_scale, "epoch": epoch,
+                             "idx": idx, "torch_seed": 500 + ci, "sample_ts": int(ts), "scale": scale,
+                             "h_offset": h_off, "w_offset": w_off, "min_scale_cur": msc,
+                             "ref": {k: ref[k].clone() for k in mine}})
+    torch.save(out, os.path.join(GOLD, "grid_patch.pt"))
+    print("  grid-sampled training patch: pinned (5 cases)")
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", choices=["loss", "encoder"], help="regenerate a single fixture")
+    ap.add_argument("--only", choices=["loss", "encoder", "grid_patch", "cgnet"], help="regenerate a single fixture")
     opt = ap.parse_args()
     if not os.path.isdir(REF):
         raise SystemExit(f"reference not found at {REF}; golden vectors can only be made in the "
@@ -317,6 +375,9 @@ def main():
     if opt.only == "loss":
         case_loss()
         return
+    if opt.only == "grid_patch":
+        case_grid_patch()
+        return
     rendering, nerf, lst = import_reference()
     if opt.only == "encoder":
         case_encoder(lst)
@@ -326,6 +387,7 @@ def main():
     case_sample_pdf(rendering)
     case_style(nerf, lst)
     case_loss()
+    case_grid_patch()
     # config[0]-shaped (coarse only), eval and train mode, fine pass, peaky weights
     case_render(rendering, nerf, lst, "render_c64_eval", 64, 64, 0, train=False)
     case_render(rendering, nerf, lst, "render_64p128_eval", 96, 64, 128, train=False)

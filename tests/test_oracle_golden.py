@@ -145,3 +145,14 @@ def test_losses_mirror_schedules_match_reference_weights():
     cos = losses.CosineAnnealingWeight(max=5e-2, min=6e-3, Tmax=1000)
     assert cos.getWeight(0) == 5e-2 and abs(cos.getWeight(1000) - 6e-3) < 1e-18 and abs(cos.getWeight(500) - 0.028) < 1e-15
     assert set(losses.loss_dict) == {"color", "crnerf"}
+
+
+def test_grid_patch_matches_reference():
+    """oracle.grid_patch against the reference's own training ``__getitem__``
+    (datasets/phototourism_mask_grid_sample.py:240-275, executed unmodified by make_golden.py)."""
+    g = load_golden("grid_patch")
+    for c in g["cases"]:
+        out = oracle.grid_patch(g["all_rays"], g["all_rgbs"], g["all_imgs_wh"], c["sample_ts"], c["batch_size"],
+                                c["scale"], c["h_offset"], c["w_offset"])
+        for k, v in c["ref"].items():
+            assert out[k].dtype == v.dtype and torch.equal(out[k], v), k
