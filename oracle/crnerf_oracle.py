@@ -442,3 +442,60 @@ def grid_patch(all_rays: Tensor, all_rgbs: Tensor, all_imgs_wh: Tensor, sample_t
     rows = (idx + (all_imgs_wh[:sample_ts, 0] * all_imgs_wh[:sample_ts, 1]).sum()).long()          # :264
     return {"rays": all_rays[rows, :8], "ts": all_rays[rows, 8].long(), "rgbs": all_rgbs[rows],
             "rgb_idx": idx, "uv_sample": uv}
+
+
+# --------------------------------------------------------------------------
+# f3  Context_Guided_Network.forward  (reference models/lightweight_seg.py:271-368, built as
+#     Context_Guided_Network(classes=1, M=2, N=2, input_channel=3), train_mask_grid_sample.py:114)
+# --------------------------------------------------------------------------
+def cgnet_forward(p: Params, x: Tensor, m_blocks: int = 2, n_blocks: int = 2, train: bool = False) -> Tensor:
+    """x (B,C,H,W) -> sigmoid mask (B,classes,H,W).  ``p`` is the module's state_dict.  ``train``
+    selects BatchNorm batch statistics (as ``module.train()``; running stats are not updated here)."""
+    def bn_prelu(name_bn, name_act, t):
+        t = F.batch_norm(t, p[f"{name_bn}.running_mean"], p[f"{name_bn}.running_var"], p[f"{name_bn}.weight"],
+                         p[f"{name_bn}.bias"], training=train, momentum=0.0, eps=1e-3)       # :25,48
+        return F.prelu(t, p[f"{name_act}.weight"])
+
+    def conv(name, t, stride=1, dil=1, groups=1):
+        w = p[f"{name}.weight"]
+        pad = ((w.shape[-1] - 1) // 2) * dil
+        return F.conv2d(t, w, None, stride, pad, dil, groups)
+
+    def cbp(name, t, stride=1):                                                               # ConvBNPReLU :28-37
+        return bn_prelu(f"{name}.bn", f"{name}.act", conv(f"{name}.conv", t, stride))
+
+    def glo(name, t):                                                                         # FGlo :183-188
+        y = t.mean((2, 3))
+        y = torch.sigmoid(F.linear(F.relu(F.linear(y, p[f"{name}.fc.0.weight"], p[f"{name}.fc.0.bias"])),
+                                   p[f"{name}.fc.2.weight"], p[f"{name}.fc.2.bias"]))
+        return t * y[:, :, None, None]
+
+    def down(name, t, dil):                                                                   # :211-224
+        o = cbp(f"{name}.conv1x1", t, 2)
+        c = o.shape[1]
+        j = torch.cat([conv(f"{name}.F_loc.conv", o, groups=c), conv(f"{name}.F_sur.conv", o, dil=dil, groups=c)], 1)
+        j = bn_prelu(f"{name}.bn", f"{name}.act", j)
+        return glo(f"{name}.F_glo", conv(f"{name}.reduce.conv", j))
+
+    def block(name, t, dil):                                                                  # :244-257
+        o = cbp(f"{name}.conv1x1", t)
+        c = o.shape[1]
+        j = torch.cat([conv(f"{name}.F_loc.conv", o, groups=c), conv(f"{name}.F_sur.conv", o, dil=dil, groups=c)], 1)
+        return t + glo(f"{name}.F_glo", bn_prelu(f"{name}.bn_prelu.bn", f"{name}.bn_prelu.act", j))
+
+    pool = lambda t: F.avg_pool2d(t, 3, 2, 1)                                                 # InputInjection :263-268
+    o0 = cbp("level1_2", cbp("level1_1", cbp("level1_0", x, 2)))                              # :327-329
+    inp1 = pool(x)
+    inp2 = pool(pool(x))
+    o1_0 = down("level2_0", bn_prelu("b1.bn", "b1.act", torch.cat([o0, inp1], 1)), 2)          # :334-335
+    o1 = o1_0
+    for i in range(m_blocks - 1):
+        o1 = block(f"level2.{i}", o1, 2)
+    o2_0 = down("level3_0", bn_prelu("bn_prelu_2.bn", "bn_prelu_2.act", torch.cat([o1, o1_0, inp2], 1)), 4)
+    o2 = o2_0
+    for i in range(n_blocks - 1):
+        o2 = block(f"level3.{i}", o2, 4)
+    cat = bn_prelu("bn_prelu_3.bn", "bn_prelu_3.act", torch.cat([o2_0, o2], 1))               # :356
+    logits = conv("classifier.0.conv", cat)
+    up = F.interpolate(logits, x.shape[2:], mode="bilinear", align_corners=False)             # :365
+    return torch.sigmoid(up)

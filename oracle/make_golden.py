@@ -362,6 +362,70 @@ def case_grid_patch():
     print("  grid-sampled training patch: pinned (5 cases)")
 
 
+def ruffle_cgnet(net, g):
+    """Make BatchNorm / PReLU parameters and running statistics non-trivial, as after some training
+    (same function in tests/conftest.py)."""
+    with torch.no_grad():
+        for n_, prm in net.named_parameters():
+            if ".bn" in n_ or "b1." in n_ or ".act" in n_ or "bn_prelu" in n_:
+                prm.add_(0.1 * torch.randn(prm.shape, generator=g))
+        for n_, buf in net.named_buffers():
+            if n_.endswith("running_mean"):
+                buf.copy_(0.2 * torch.randn(buf.shape, generator=g))
+            elif n_.endswith("running_var"):
+                buf.copy_(0.5 + torch.rand(buf.shape, generator=g))
+
+
+def case_cgnet():
+    """Context_Guided_Network as the training script builds it (train_mask_grid_sample.py:114):
+    state_dict keys / shapes, seeded init, eval- and train-mode forwards, and the gradients of the
+    caller's tail (resize -> rows -> [rgb_idx], :171-175).  lightweight_seg.py imports torch only."""
+    import importlib.util
+    from einops import rearrange
+    spec = importlib.util.spec_from_file_location("_ref_lightweight_seg", os.path.join(REF, "models", "lightweight_seg.py"))
+    ref_mod = importlib.util.module_from_spec(spec)
+    import warnings
+    spec.loader.exec_module(ref_mod)
+    torch.manual_seed(21)
+    net = ref_mod.Context_Guided_Network(classes=1, M=2, N=2, input_channel=3)
+    after_init = torch.rand(1)                      # the generator position after construction
+    g = torch.Generator().manual_seed(22)
+    ruffle_cgnet(net, g)
+    # weights are not stored (1 MB): the product's mirror regenerates them from the seed + ruffle;
+    # key order, shapes and a checksum of every entry pin that
+    out = {"kind": "cgnet", "seed": 21, "after_init": after_init, "checksum": checksums(net),
+           "shapes": {k: tuple(v.shape) for k, v in net.state_dict().items()}, "cases": []}
+    for ci, (h, w, H, W, n) in enumerate([(48, 64, 48, 64, 256), (70, 52, 35, 26, 100), (33, 47, 66, 94, None)]):
+        x = torch.rand(1, 3, h, w, generator=g)
+        idx = None if n is None else torch.randint(0, H * W, (n,), generator=g)
+        rec = {"x": x, "hw": (H, W), "idx": idx}
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            net.eval()
+            with torch.no_grad():
+                rec["eval"] = net(x)
+                assert_equal("cgnet:eval", oracle.cgnet_forward(sd(net), x, 2, 2, train=False), rec["eval"])
+            net.train()
+            state_before = {k: v.clone() for k, v in net.state_dict().items()}
+            net.zero_grad()
+            y = net(x)
+            assert_equal("cgnet:train", oracle.cgnet_forward(state_before, x, 2, 2, train=True), y.detach())
+            rows = rearrange(torch.nn.functional.interpolate(y, size=(H, W), mode='bilinear', align_corners=False),
+                             '1 n h w -> (h w) n')
+            rows = rows if idx is None else rows[idx]
+            gy = torch.rand(rows.shape, generator=g)
+            (rows * gy).sum().backward()
+        grads = {k: v.grad.clone() for k, v in net.named_parameters()}
+        rec.update({"train": y.detach().clone(), "rows": rows.detach().clone(), "g_rows": gy,
+                    "grads": grads if ci == 0 else None,
+                    "grad_sums": {k: (float(v.double().sum()), float(v.double().abs().sum())) for k, v in grads.items()},
+                    "running_after": {k: v.clone() for k, v in net.named_buffers() if "running" in k}})
+        net.load_state_dict(state_before)          # every case starts from the same running statistics
+        out["cases"].append(rec)
+    torch.save(out, os.path.join(GOLD, "cgnet.pt"))
+    print("  Context_Guided_Network: pinned (3 sizes, eval + train + gradients)")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", choices=["loss", "encoder", "grid_patch", "cgnet"], help="regenerate a single fixture")
@@ -378,6 +442,9 @@ def main():
     if opt.only == "grid_patch":
         case_grid_patch()
         return
+    if opt.only == "cgnet":
+        case_cgnet()
+        return
     rendering, nerf, lst = import_reference()
     if opt.only == "encoder":
         case_encoder(lst)
@@ -388,6 +455,7 @@ def main():
     case_style(nerf, lst)
     case_loss()
     case_grid_patch()
+    case_cgnet()
     # config[0]-shaped (coarse only), eval and train mode, fine pass, peaky weights
     case_render(rendering, nerf, lst, "render_c64_eval", 64, 64, 0, train=False)
     case_render(rendering, nerf, lst, "render_64p128_eval", 96, 64, 128, train=False)

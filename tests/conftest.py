@@ -100,3 +100,28 @@ def load_trained():
 @pytest.fixture(scope="session")
 def mirror_default():
     return build_mirror_models(0, False)
+
+
+def ruffle_cgnet(net, g):
+    """Same transform as oracle/make_golden.py::ruffle_cgnet."""
+    with torch.no_grad():
+        for n_, prm in net.named_parameters():
+            if ".bn" in n_ or "b1." in n_ or ".act" in n_ or "bn_prelu" in n_:
+                prm.add_(0.1 * torch.randn(prm.shape, generator=g))
+        for n_, buf in net.named_buffers():
+            if n_.endswith("running_mean"):
+                buf.copy_(0.2 * torch.randn(buf.shape, generator=g))
+            elif n_.endswith("running_var"):
+                buf.copy_(0.5 + torch.rand(buf.shape, generator=g))
+
+
+def build_mirror_cgnet(golden):
+    """The mirror's Context_Guided_Network rebuilt the way the golden's reference network was
+    (seed, construction, ruffle); returns (net, generator positioned where the cases start)."""
+    from models.lightweight_seg import Context_Guided_Network
+    torch.manual_seed(golden["seed"])
+    net = Context_Guided_Network(classes=1, M=2, N=2, input_channel=3)
+    assert torch.equal(torch.rand(1), golden["after_init"]), "construction consumed the RNG differently"
+    g = torch.Generator().manual_seed(22)
+    ruffle_cgnet(net, g)
+    return net, g
