@@ -117,6 +117,11 @@ SIGNATURES = {
     "crnerf_style_forward": (C.c_int, [C.POINTER(StyleWeights), C.c_void_p, C.c_int64, C.c_int64,
                                        C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crnerf_style_forward_sums": (C.c_int, [C.POINTER(StyleWeights), C.c_void_p, C.c_int64, C.c_int64,
+                                            C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                            C.c_void_p, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crnerf_sum_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "crnerf_cnn_forward": (C.c_int, [C.POINTER(CnnWeights), C.c_void_p, C.c_int64, C.c_int64,
                                      C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crnerf_style_stats1": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,

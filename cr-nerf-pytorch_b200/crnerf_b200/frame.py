@@ -84,7 +84,9 @@ class CudaStyleBackend:
         self._ops = ops
         self._sw = decoder._style_ref([("", "")])
 
-    def sums(self, feat):                       # (n,64) -> (64,) channel sums
+    def sums(self, feat, parts=None):           # (n,64) -> (64,) channel sums
+        if parts is not None:                   # the render kernel's per-CTA partial sums: no pass over feat
+            return self._ops.sum_rows(parts)
         return self._ops.style_stats1(feat)
 
     def gram(self, feat, mean):                 # -> (32,32) un-normalised Gram of cnet.convs(x-mean)
@@ -121,10 +123,12 @@ def _gather_blocks(local: torch.Tensor, n_total: int, group, dim: int) -> torch.
 
 
 def fuse_decode_sharded(backend, feat_local: torch.Tensor, style: torch.Tensor, n_total: int,
-                        group=None) -> torch.Tensor:
+                        group=None, sum_parts: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Cross-ray fusion + decoder of a frame whose (n_total,64) feature rows are sharded by
-    ``shard_bounds``; returns the whole frame's rgb as (3, n_total) on every rank."""
-    sums = _all_reduce(backend.sums(feat_local), group)
+    ``shard_bounds``; returns the whole frame's rgb as (3, n_total) on every rank.  ``sum_parts``:
+    the render kernel's partial channel sums of ``feat_local`` (rows add up to its column sums)."""
+    local = backend.sums(feat_local, sum_parts) if sum_parts is not None else backend.sums(feat_local)
+    sums = _all_reduce(local, group)
     mean = sums / float(n_total)
     gram = _all_reduce(backend.gram(feat_local, mean), group)
     rgb_local = backend.apply(feat_local, mean, gram / float(n_total), style)
@@ -155,18 +159,26 @@ def render_frame_sharded(models, embeddings, rays: Optional[torch.Tensor], style
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
     lo, hi = shard_bounds(n_total, world, rank)
+    typ = "fine" if N_importance > 0 else "coarse"
+    want_sums = style is not None and "channel_sums" not in kwargs
+    if want_sums:          # the fine pass's epilogue also emits per-CTA channel sums of its features
+        kwargs = dict(kwargs, channel_sums=True)
     res = batched_render(models, embeddings, rays[lo:hi], N_samples, N_importance, use_disp, chunk,
                          **kwargs)
-    feat = res["feature_fine" if N_importance > 0 else "feature_coarse"]
+    feat = res[f"feature_{typ}"]
+    parts = res.get(f"chansum_{typ}") if want_sums and hi > lo else None
     decoder = models["decoder"]
     if scheme == "gather" or style is None:
         full = _gather_blocks(feat, n_total, group, dim=0)              # (N,64)
         content = full.t().reshape(1, 64, h, w)                         # view, read in place
         with torch.no_grad():
-            return decoder(content, style, type=None if style is not None else "content")
+            if style is None:
+                return decoder(content, None, type="content")
+            # after a gather the local partial sums no longer describe the whole map
+            return decoder(content, style, channel_sums=parts if world == 1 else None)
     if scheme != "stats":
         raise ValueError(f"unknown scheme {scheme!r}")
     if backend is None:
         backend = CudaStyleBackend(decoder)
-    rgb = fuse_decode_sharded(backend, feat, style, n_total, group)
+    rgb = fuse_decode_sharded(backend, feat, style, n_total, group, sum_parts=parts)
     return rgb.reshape(1, 3, h, w)

@@ -409,8 +409,12 @@ def _feat_strides(t: torch.Tensor, name: str):
 
 
 def style_forward(sw: StyleWeightsRef, content: torch.Tensor, style: Optional[torch.Tensor],
-                  want_trans: bool = False, want_fused: bool = False):
-    """style_net.forward: content (1,64,H,W), style (1,64,h,w) or None -> rgb (1,3,H,W)."""
+                  want_trans: bool = False, want_fused: bool = False,
+                  channel_sums: Optional[torch.Tensor] = None):
+    """style_net.forward: content (1,64,H,W), style (1,64,h,w) or None -> rgb (1,3,H,W).
+    ``channel_sums`` (rows, 64), optional: partial sums whose rows add up to the content map's
+    channel sums (``render_rays_cross_ray(..., channel_sums=True)['chansum_*']``) - saves the pass
+    over the map that would otherwise form them."""
     lib = _lib.load()
     content, n, cps, ccs = _feat_strides(content, "content")
     h, w = content.shape[2], content.shape[3]
@@ -429,9 +433,17 @@ def style_forward(sw: StyleWeightsRef, content: torch.Tensor, style: Optional[to
         trans = torch.empty((1, 32, 32), dtype=torch.float32, device=dev) if want_trans else None
         fused = torch.empty((1, 64, h, w), dtype=torch.float32, device=dev) if want_fused else None
         scratch = torch.empty(lib.crnerf_style_scratch_floats(n), dtype=torch.float32, device=dev)
-        check(lib.crnerf_style_forward(C.byref(sw.struct), content.data_ptr(), n, cps, ccs,
-                                       _p(style), ns, sps, scs, rgb.data_ptr(), _p(trans),
-                                       _p(fused), scratch.data_ptr(), _stream(dev)))
+        n_parts = 0
+        if channel_sums is not None and style is not None:
+            channel_sums = _c(_need(channel_sums, "channel_sums", 2))
+            if channel_sums.shape[1] != 64 or channel_sums.shape[0] < 1 or channel_sums.device != dev:
+                raise ValueError("channel_sums must be (rows >= 1, 64) on the content's device")
+            n_parts = int(channel_sums.shape[0])
+        check(lib.crnerf_style_forward_sums(C.byref(sw.struct), content.data_ptr(), n, cps, ccs,
+                                            _p(style), ns, sps, scs,
+                                            channel_sums.data_ptr() if n_parts else None, n_parts,
+                                            rgb.data_ptr(), _p(trans), _p(fused), scratch.data_ptr(),
+                                            _stream(dev)))
     out = [rgb]
     if want_trans:
         out.append(trans)
@@ -488,6 +500,21 @@ def style_stats1(content_rows: torch.Tensor) -> torch.Tensor:
         check(lib.crnerf_style_stats1(x.data_ptr(), n, ps, cs, sums.data_ptr(),
                                       _style_scratch(dev, n).data_ptr(), _stream(dev)))
     return sums
+
+
+def sum_rows(parts: torch.Tensor) -> torch.Tensor:
+    """(rows, len) -> (len,) column sums in a fixed order (the render kernel's per-CTA channel
+    sums -> the channel sums of this rank's block of rays)."""
+    lib = _lib.load()
+    parts = _c(_need(parts, "parts", 2))
+    dev = parts.device
+    with torch.cuda.device(dev):
+        out = torch.zeros(parts.shape[1], dtype=torch.float32, device=dev)
+        if parts.shape[0] == 0:
+            return out
+        check(lib.crnerf_sum_rows(parts.data_ptr(), int(parts.shape[0]), int(parts.shape[1]), out.data_ptr(),
+                                  _stream(dev)))
+    return out
 
 
 def style_stats2(sw: StyleWeightsRef, content_rows: torch.Tensor, mean: torch.Tensor) -> torch.Tensor:

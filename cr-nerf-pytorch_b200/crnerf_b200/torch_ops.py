@@ -18,7 +18,7 @@ Operator list (reference lines each one replaces are in ``include/crnerf_b200.h`
   sample_pdf_merge(z_coarse, weights_coarse, u, n_importance, eps) -> z_fine
   pos_embed(x, n_freqs) -> emb
   mlp_forward(packed, operand, e_xyz, e_dir, x, sigma_only) -> out
-  style_forward(content, style?, params[22]) -> rgb
+  style_forward(content, style?, params[22], channel_sums?) -> rgb
   rgb_to_u8(rgb) -> u8
 """
 from __future__ import annotations
@@ -86,14 +86,14 @@ def _mlp_forward(packed, operand, e_xyz, e_dir, x, sigma_only):
 _style_cache = {"key": None, "sw": None}     # pointer struct of the last parameter set seen
 
 
-def _style_forward(content, style, params):
+def _style_forward(content, style, params, channel_sums=None):
     if len(params) != len(STYLE_KEYS):
         raise ValueError(f"params must hold the {len(STYLE_KEYS)} style_net tensors in STYLE_KEYS order")
     key = tuple(t.data_ptr() for t in params)
     if _style_cache["key"] != key:
         _style_cache["sw"] = ops.StyleWeightsRef(dict(zip(STYLE_KEYS, params)))
         _style_cache["key"] = key
-    return ops.style_forward(_style_cache["sw"], content, style)
+    return ops.style_forward(_style_cache["sw"], content, style, channel_sums=channel_sums)
 
 
 def _rgb_to_u8(rgb):
@@ -129,7 +129,7 @@ def _m_mlp_forward(packed, operand, e_xyz, e_dir, x, sigma_only):
     return x.new_empty((x.shape[0], 1 if sigma_only else 65))
 
 
-def _m_style_forward(content, style, params):
+def _m_style_forward(content, style, params, channel_sums=None):
     return content.new_empty((1, 3, content.shape[2], content.shape[3]))
 
 
@@ -159,7 +159,7 @@ _OPS = (
     ("pos_embed", "(Tensor x, int n_freqs) -> Tensor", _pos_embed, _m_pos_embed),
     ("mlp_forward", "(Tensor packed, int operand, int e_xyz, int e_dir, Tensor x, bool sigma_only) -> Tensor",
      _mlp_forward, _m_mlp_forward),
-    ("style_forward", "(Tensor content, Tensor? style, Tensor[] params) -> Tensor", _style_forward,
+    ("style_forward", "(Tensor content, Tensor? style, Tensor[] params, Tensor? channel_sums=None) -> Tensor", _style_forward,
      _m_style_forward),
     ("rgb_to_u8", "(Tensor rgb) -> Tensor", _rgb_to_u8, _m_rgb_to_u8),
 )

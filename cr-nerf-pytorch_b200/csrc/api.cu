@@ -76,8 +76,10 @@ int style_finish(const crnerf_style_weights* w, const float* content, int64_t n,
                  const float* style, int64_t ns, int64_t sps, int64_t scs, float* rgb,
                  float* transmatrix, float* fused, float* scratch, cudaStream_t st);
 int style_forward(const crnerf_style_weights* w, const float* content, int64_t n, int64_t ps,
-                  int64_t cs, const float* style, int64_t ns, int64_t sps, int64_t scs, float* rgb,
+                  int64_t cs, const float* style, int64_t ns, int64_t sps, int64_t scs,
+                  const float* content_sum_parts, int n_parts, float* rgb,
                   float* transmatrix, float* fused, float* scratch, cudaStream_t st);
+int sum_rows(const float* parts, int n_parts, int len, float* out, cudaStream_t st);
 int cnn_forward(const crnerf_cnn_weights* cw, const float* x, int64_t n, int64_t ps, int64_t cs,
                 float* out, float* scratch, cudaStream_t st);
 int grid_patch(const float* lin_w, const float* lin_h, int g, float img_w, float img_h, float scale, float h_off,
@@ -428,8 +430,26 @@ int crnerf_style_forward(const crnerf_style_weights* w, const float* content, in
   int rc = device_check();
   if (rc) return rc;
   return style_forward(w, content, n_pixels, c_pix_stride, c_ch_stride, style, n_style_pixels,
-                       s_pix_stride, s_ch_stride, rgb, transmatrix, fused, scratch,
+                       s_pix_stride, s_ch_stride, nullptr, 0, rgb, transmatrix, fused, scratch,
                        (cudaStream_t)stream);
+}
+
+int crnerf_style_forward_sums(const crnerf_style_weights* w, const float* content, int64_t n_pixels,
+                              int64_t c_pix_stride, int64_t c_ch_stride, const float* style,
+                              int64_t n_style_pixels, int64_t s_pix_stride, int64_t s_ch_stride,
+                              const float* content_sum_partials, int n_partials, float* rgb,
+                              float* transmatrix, float* fused, float* scratch, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return style_forward(w, content, n_pixels, c_pix_stride, c_ch_stride, style, n_style_pixels,
+                       s_pix_stride, s_ch_stride, content_sum_partials, n_partials, rgb, transmatrix, fused,
+                       scratch, (cudaStream_t)stream);
+}
+
+int crnerf_sum_rows(const float* parts, int n_parts, int len, float* out, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return sum_rows(parts, n_parts, len, out, (cudaStream_t)stream);
 }
 
 int crnerf_cnn_forward(const crnerf_cnn_weights* w, const float* x, int64_t n_pixels,

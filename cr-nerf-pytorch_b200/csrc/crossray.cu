@@ -8,21 +8,25 @@
 //       = sigmoid( A x + a0 ),  A = Wr Wu (S C) Wc  (3x64)
 // where C = fc_c(Gram(cnet(x - mu_c))/HW) needs statistics over ALL pixels (the
 // "cross-ray" part) and S the same over the style feature.  So the data path is
-//   pass 1  channel sums               (read feature map once)
-//   pass 2  pixel MLP 64-128-64-32 + 32x32 Gram partials (read it again; tensor core, gram_tc.cu)
-//   tiny    partial reductions, two 1024x1024 GEMVs, compose A / a0
-//   pass 3  apply the 3x64 map + sigmoid (read it a third time, write RGB)
-// All reductions use per-block partials combined in a fixed order, so results
+//   pass 1  channel sums - normally NOT a pass: the render kernel's epilogue emits per-CTA partial
+//           sums of the features it writes (crnerf_render_pass_opts) and the Gram kernel reduces
+//           them in its prologue; sums_rows_kernel / sums_kernel exist for maps that come from
+//           elsewhere (read the feature map once)
+//   pass 2  pixel MLP 64-128-64-32 + 32x32 Gram partials, content and style map in ONE launch
+//           (tensor core, gram_tc.cu; walks the map backwards: its tail is what the producer left in L2)
+//   tiny    reduce the Gram partials (both maps, one launch), two 1024x1024 GEMVs (one launch)
+//   pass 3  compose the 3x64 map in the prologue (18 kFMA per CTA), apply it + sigmoid (second
+//           read of the map, forwards: its head is what pass 2 left in L2), write RGB
+// = 4 launches.  All reductions use per-block partials combined in a fixed order, so results
 // are deterministic run to run.  Feature maps are read in place through
 // (pixel stride, channel stride), i.e. both the renderer's (N,64) rows and
 // contiguous NCHW.
 #include <algorithm>
 #include "common.h"
 
+#include "gram_tc.h"
+
 namespace crnerf {
-// gram_tc.cu
-int gram_tc(const crnerf_cnn_weights& cw, const float* g, int64_t n, int64_t ps, int64_t cs, const float* mean,
-            float* partial, int max_blocks, int* n_blocks, cudaStream_t st);
 namespace {
 
 constexpr int kC = 64;     // feature channels (MulLayer hard-codes 64, linearStyleTransfer.py:46-47)
@@ -237,23 +241,124 @@ compose_kernel(const float* __restrict__ cmat, const float* __restrict__ smat,
   }
 }
 
-// decoder-only map (style is None and type == "content", linearStyleTransfer.py:285-287)
-__global__ void content_map_kernel(crnerf_style_weights w, float* __restrict__ map) {
-  const int tid = threadIdx.x;
-  if (tid < 192) map[kMapA + tid] = w.rgb_w[tid];
-  if (tid < 3) map[kMapA0 + tid] = w.rgb_b[tid];
+// Gram partials of both maps -> normalised Gram vectors, one launch: output e < 1024 belongs to
+// job 0, e >= 1024 to job 1 (absent when part1 == nullptr).  One warp per element, lanes stride
+// the partials (independent loads in flight), fixed shuffle tree.
+__global__ void __launch_bounds__(256)
+reduce_gram_kernel(const float* __restrict__ part0, int n0, float scale0, float* __restrict__ out0,
+                   const float* __restrict__ part1, int n1, float scale1, float* __restrict__ out1) {
+  const int e = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const bool second = e >= 1024;
+  const float* part = second ? part1 : part0;
+  if (part == nullptr) return;
+  const int n_parts = second ? n1 : n0, i = e & 1023;
+  float acc = 0.f;
+  for (int b = lane; b < n_parts; b += 32) acc += part[(long long)b * 1024 + i];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if (lane == 0) (second ? out1 : out0)[i] = acc * (second ? scale1 : scale0);
 }
 
 // ---------------------------------------------------------------- pass 3
-// rgb[r][p] = sigmoid(A[r] . x[p] + a0[r]); optional fused[o][p] = M[o] . x[p] + v[o]
+// The rgb map of the block, composed right to left so that no 64x64 matrix is ever formed:
+//   A  = Wr Wu S C Wc                      = ((((Wr Wu) S) C) Wc)                 (3x64, 18 kFMA)
+//   a0 = R3 bc + Wr (bu + mu_s) + br - A mu_c,   R3 = Wr Wu S C                   (3)
+// (MulLayer.forward :76-89 + NeuralRenderer.forward).  Every apply CTA runs this in its prologue
+// from the two FC outputs; both apply kernels share it, so they use bit-identical maps.
+struct MapSrc {
+  const float* cmat;     // cnet.fc output (1024) = C row-major; nullptr: decoder only (A = Wr, a0 = br)
+  const float* smat;     // snet.fc output = S
+  const float* mean_c;
+  const float* mean_s;
+  crnerf_style_weights w;
+  float* trans_out;      // optional (1024): T = S C, written by block 0
+};
+
+struct MapSmem {
+  float S[32][33], C[32][33], Wu[64][33], Wc[32][65], Wr[3][64];
+  float R[2][3][32];
+  float A[3][64], a0[3];
+};
+
+__device__ void compose_rgb_map(const MapSrc& m, MapSmem& sm) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (m.cmat == nullptr) {
+    for (int e = tid; e < 192; e += nt) sm.A[e >> 6][e & 63] = m.w.rgb_w[e];
+    if (tid < 3) sm.a0[tid] = m.w.rgb_b[tid];
+    __syncthreads();
+    return;
+  }
+  for (int e = tid; e < 1024; e += nt) {
+    sm.S[e >> 5][e & 31] = m.smat[e];
+    sm.C[e >> 5][e & 31] = m.cmat[e];
+  }
+  for (int e = tid; e < 2048; e += nt) {
+    sm.Wu[e >> 5][e & 31] = m.w.unzip_w[e];      // (64, 32)
+    sm.Wc[e >> 6][e & 63] = m.w.compress_w[e];   // (32, 64)
+  }
+  for (int e = tid; e < 192; e += nt) sm.Wr[e >> 6][e & 63] = m.w.rgb_w[e];
+  __syncthreads();
+  if (m.trans_out && blockIdx.x == 0) {          // transmatrix = S C (MulLayer.forward :86)
+    for (int e = tid; e < 1024; e += nt) {
+      const int i = e >> 5, j = e & 31;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) acc = fmaf(sm.S[i][k], sm.C[k][j], acc);
+      m.trans_out[e] = acc;
+    }
+  }
+  const int r = tid >> 5, i = tid & 31;          // threads 0..95: one element of a 3x32 row block
+  if (tid < 96) {                                // R1 = Wr Wu
+    float acc = 0.f;
+#pragma unroll 8
+    for (int o = 0; o < 64; ++o) acc = fmaf(sm.Wr[r][o], sm.Wu[o][i], acc);
+    sm.R[0][r][i] = acc;
+  }
+  __syncthreads();
+  if (tid < 96) {                                // R2 = R1 S
+    float acc = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) acc = fmaf(sm.R[0][r][k], sm.S[k][i], acc);
+    sm.R[1][r][i] = acc;
+  }
+  __syncthreads();
+  if (tid < 96) {                                // R3 = R2 C
+    float acc = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) acc = fmaf(sm.R[1][r][k], sm.C[k][i], acc);
+    sm.R[0][r][i] = acc;
+  }
+  __syncthreads();
+  if (tid < 192) {                               // A = R3 Wc
+    const int rr = tid >> 6, c = tid & 63;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) acc = fmaf(sm.R[0][rr][k], sm.Wc[k][c], acc);
+    sm.A[rr][c] = acc;
+  }
+  __syncthreads();
+  if (tid < 3) {
+    float acc = 0.f;
+    for (int k = 0; k < 32; ++k) acc = fmaf(sm.R[0][tid][k], m.w.compress_b[k], acc);
+    float acc2 = 0.f;
+    for (int o = 0; o < 64; ++o) acc2 = fmaf(sm.Wr[tid][o], m.w.unzip_b[o] + m.mean_s[o], acc2);
+    float acc3 = 0.f;
+    for (int c = 0; c < 64; ++c) acc3 = fmaf(sm.A[tid][c], m.mean_c[c], acc3);
+    sm.a0[tid] = ((acc + acc2) + m.w.rgb_b[tid]) - acc3;
+  }
+  __syncthreads();
+}
+
+// rgb[r][p] = sigmoid(A[r] . x[p] + a0[r]); optional fused[o][p] = M[o] . x[p] + v[o] (M, v from
+// compose_kernel's `map`).  Any layout; the row layout normally takes apply_rows_kernel.
 __global__ void __launch_bounds__(256)
 apply_kernel(const float* __restrict__ g, long long n, long long pix_stride, long long ch_stride,
-             const float* __restrict__ map, float* __restrict__ rgb, float* __restrict__ fused) {
+             const __grid_constant__ MapSrc src, const float* __restrict__ map, float* __restrict__ rgb,
+             float* __restrict__ fused) {
   __shared__ float xin[kC][kTPS];
-  __shared__ float A[3][64], a0[3];
+  __shared__ MapSmem sm;
   const int tid = threadIdx.x;
-  if (tid < 192) A[tid >> 6][tid & 63] = map[kMapA + tid];
-  if (tid < 3) a0[tid] = map[kMapA0 + tid];
+  compose_rgb_map(src, sm);
   const long long n_tiles = (n + kTP - 1) / kTP;
   for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const long long p0 = t * kTP;
@@ -264,8 +369,8 @@ apply_kernel(const float* __restrict__ g, long long n, long long pix_stride, lon
       const int r = tid / kTP, px = tid % kTP;
       float acc = 0.f;
 #pragma unroll 8
-      for (int c = 0; c < 64; ++c) acc = fmaf(A[r][c], xin[c][px], acc);
-      acc += a0[r];
+      for (int c = 0; c < 64; ++c) acc = fmaf(sm.A[r][c], xin[c][px], acc);
+      acc += sm.a0[r];
       if (p0 + px < n) rgb[(long long)r * n + p0 + px] = 1.f / (1.f + expf(-acc));
     }
     if (fused) {
@@ -279,34 +384,70 @@ apply_kernel(const float* __restrict__ g, long long n, long long pix_stride, lon
   }
 }
 
-// pass 3 for the row layout: one pixel per thread, the whole row requested up front
-// (16 x 16-byte loads in flight per thread), the 3x64 map broadcast from shared memory; same
-// fmaf order as apply_kernel, so both give identical bits.
+// pass 3 for the renderer's row layout: a pure HBM stream.  16 lanes cover one pixel with one
+// float4 load each (a warp-wide load = two whole 256-byte rows), 8 such loads in flight per
+// thread; every lane keeps its 4 channels of A in registers.  The 16 partial dot products of a
+// pixel are combined by a transposing butterfly: each exchange halves the number of (pixel, r)
+// values a lane still owns, 24 shuffles for 16 pixels x 3 outputs, fixed order.  Persistent
+// blocks sweep the map front to back.
 __global__ void __launch_bounds__(256)
-apply_rows_kernel(const float* __restrict__ g, long long n, long long pix_stride, const float* __restrict__ map,
-                  float* __restrict__ rgb) {
-  __shared__ float A[3][64], a0[3];
-  const int tid = threadIdx.x;
-  if (tid < 192) A[tid >> 6][tid & 63] = map[kMapA + tid];
-  if (tid < 3) a0[tid] = map[kMapA0 + tid];
-  __syncthreads();
-  const long long p = blockIdx.x * 256LL + tid;
-  if (p >= n) return;
-  float4 x[16];
+apply_rows_kernel(const float* __restrict__ g, long long n, long long pix_stride,
+                  const __grid_constant__ MapSrc src, float* __restrict__ rgb) {
+  __shared__ MapSmem sm;
+  compose_rgb_map(src, sm);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int l = lane & 15, half = lane >> 4;
+  float a[3][4];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) x[i] = __ldg(reinterpret_cast<const float4*>(g + p * pix_stride) + i);
+  for (int r = 0; r < 3; ++r)
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    float acc = 0.f;
+    for (int k = 0; k < 4; ++k) a[r][k] = sm.A[r][4 * l + k];
+  const float a0[3] = {sm.a0[0], sm.a0[1], sm.a0[2]};
+  const bool b3 = l & 8, b2 = l & 4, b1 = l & 2;
+  for (long long base = ((long long)blockIdx.x * 8 + warp) * 16; base < n; base += (long long)gridDim.x * 128) {
+    float4 x[8];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      acc = fmaf(A[r][4 * i], x[i].x, acc);
-      acc = fmaf(A[r][4 * i + 1], x[i].y, acc);
-      acc = fmaf(A[r][4 * i + 2], x[i].z, acc);
-      acc = fmaf(A[r][4 * i + 3], x[i].w, acc);
+    for (int u = 0; u < 8; ++u) {
+      const long long p = base + 2 * u + half;
+      x[u] = p < n ? __ldcs(reinterpret_cast<const float4*>(g + p * pix_stride) + l) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    acc += a0[r];
-    rgb[(long long)r * n + p] = 1.f / (1.f + expf(-acc));
+    float v[8][3];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        v[u][r] = fmaf(a[r][3], x[u].w, fmaf(a[r][2], x[u].z, fmaf(a[r][1], x[u].y, a[r][0] * x[u].x)));
+    // xor 8: lanes with bit 3 clear keep u 0..3, the others u 4..7
+    float w4[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float keep = b3 ? v[u + 4][r] : v[u][r], send = b3 ? v[u][r] : v[u + 4][r];
+        w4[u][r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+    float w2[2][3];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float keep = b2 ? w4[u + 2][r] : w4[u][r], send = b2 ? w4[u][r] : w4[u + 2][r];
+        w2[u][r] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+    float w1[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float keep = b1 ? w2[1][r] : w2[0][r], send = b1 ? w2[0][r] : w2[1][r];
+      w1[r] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) w1[r] += __shfl_xor_sync(0xffffffffu, w1[r], 1);
+    // this lane pair owns u = (bit3, bit2, bit1) of the lane index
+    const long long p = base + 2 * ((l >> 1) & 7) + half;
+    if ((l & 1) == 0 && p < n) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) rgb[(long long)r * n + p] = 1.f / (1.f + expf(-(w1[r] + a0[r])));
+    }
   }
 }
 
@@ -324,7 +465,7 @@ int blocks_for_pixels(long long n) {
 
 // scratch layout (floats)
 //   [0, P1)            sums partials   kMaxBlocks*64
-//   [P1, P1+P2)        gram partials   kMaxBlocks*1024
+//   [P1, P1+P2)        gram partials   kMaxBlocks*1024 (content job: first half, style job: second half)
 //   then mean_c 64 | mean_s 64 | gram_c 1024 | gram_s 1024 | cmat 1024 | smat 1024 | map 4416
 constexpr size_t kOffSumPart = 0;
 constexpr size_t kOffGramPart = kOffSumPart + (size_t)kMaxBlocks * 64;
@@ -336,6 +477,8 @@ constexpr size_t kOffCmat = kOffGramS + 1024;
 constexpr size_t kOffSmat = kOffCmat + 1024;
 constexpr size_t kOffMap = kOffSmat + 1024;
 constexpr size_t kScratchFloats = kOffMap + kMapFloats;
+constexpr int kGramBlocksPerJob = kMaxBlocks / 2;
+constexpr long long kSelfMeanMaxPixels = 4096;   // maps this small: every Gram CTA sums them itself
 
 size_t style_scratch_floats(int64_t) { return kScratchFloats; }
 
@@ -346,62 +489,126 @@ static int check_feat(const float* p, int64_t n, int64_t ps, int64_t cs, const c
   return CRNERF_OK;
 }
 
+// per-block partial channel sums of a map -> partial (n_blocks, 64); returns n_blocks
+static int sum_partials(const float* x, int64_t n, int64_t ps, int64_t cs, float* partial, int* n_blocks,
+                        cudaStream_t st, int cap = kMaxBlocks) {
+  int nb = std::min(cap, blocks_for_pixels(n));
+  if (rows_fast(x, ps, cs)) {
+    nb = (int)std::max<long long>(1, std::min<long long>((n + 127) / 128, cap));
+    sums_rows_kernel<<<nb, 256, 0, st>>>(x, n, ps, partial);
+  } else {
+    sums_kernel<<<nb, 256, 0, st>>>(x, n, ps, cs, partial);
+  }
+  count_launch();
+  CRNERF_CUDA(cudaGetLastError());
+  *n_blocks = nb;
+  return CRNERF_OK;
+}
+
 int style_stats1(const float* content, int64_t n, int64_t ps, int64_t cs, float* sums,
                  float* partial, cudaStream_t st) {
-  int nb = blocks_for_pixels(n);
-  if (rows_fast(content, ps, cs)) {
-    nb = (int)std::max<long long>(1, std::min<long long>((n + 127) / 128, kMaxBlocks));
-    sums_rows_kernel<<<nb, 256, 0, st>>>(content, n, ps, partial);
-  } else {
-    sums_kernel<<<nb, 256, 0, st>>>(content, n, ps, cs, partial);
-  }
+  int nb = 0;
+  int rc = sum_partials(content, n, ps, cs, partial, &nb, st);
+  if (rc) return rc;
   reduce_partials_warp_kernel<<<8, 256, 0, st>>>(partial, nb, 64, 1.f, sums);
-  count_launch(2);
+  count_launch();
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;
+}
+
+// sums[len] = sum of the rows of parts (n_parts, len) in a fixed order (the render kernel's
+// per-CTA channel sums -> the 64 channel sums of a rank's block of rays)
+int sum_rows(const float* parts, int n_parts, int len, float* out, cudaStream_t st) {
+  CRNERF_REQUIRE(parts && out && n_parts >= 1 && len >= 1, "bad argument");
+  reduce_partials_warp_kernel<<<(len + 7) / 8, 256, 0, st>>>(parts, n_parts, len, 1.f, out);
+  count_launch();
+  CRNERF_CUDA(cudaGetLastError());
+  return CRNERF_OK;
+}
+
+static GramJob make_job(const crnerf_cnn_weights& cw, const float* x, int64_t n, int64_t ps, int64_t cs,
+                        const float* sum_parts, int n_parts, float mean_scale, float* partial, float* mean_out,
+                        int reverse) {
+  GramJob j{};
+  j.g = x;
+  j.n = n;
+  j.pix_stride = ps;
+  j.ch_stride = cs;
+  j.sum_parts = sum_parts;
+  j.n_parts = n_parts;
+  j.mean_scale = mean_scale;
+  j.self_mean = sum_parts == nullptr;
+  j.w = cw;
+  j.partial = partial;
+  j.mean_out = mean_out;
+  j.reverse = reverse;
+  return j;
 }
 
 int style_stats2(const crnerf_cnn_weights& cw, const float* content, int64_t n, int64_t ps,
                  int64_t cs, const float* mean, float* gram, float* partial, float scale,
                  cudaStream_t st) {
   // pixel MLP + Gram on the tensor core (gram_tc.cu), then the fixed-order sum of the per-block partials
-  int nb = 0;
-  int rc = gram_tc(cw, content, n, ps, cs, mean, partial, kMaxBlocks, &nb, st);
+  GramJob j = make_job(cw, content, n, ps, cs, mean, 1, 1.f, partial, nullptr, 1);
+  int rc = gram_tc_launch(&j, 1, kGramBlocksPerJob, st);
   if (rc) return rc;
-  reduce_partials_warp_kernel<<<128, 256, 0, st>>>(partial, nb, 1024, scale, gram);
-  count_launch(1);
+  reduce_gram_kernel<<<128, 256, 0, st>>>(partial, j.n_blocks, scale, gram, nullptr, 0, 0.f, nullptr);
+  count_launch();
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;
 }
 
-// everything after the content Gram is known: style branch, FCs, compose, apply
+// FC GEMVs + the apply pass, given both normalised Gram vectors and both means
+static int fc_and_apply(const crnerf_style_weights* w, const float* content, int64_t n, int64_t ps, int64_t cs,
+                        const float* mean_c, const float* gram_c, const float* mean_s, const float* gram_s,
+                        float* rgb, float* transmatrix, float* fused, float* scratch, cudaStream_t st) {
+  float* cmat = scratch + kOffCmat;
+  float* smat = scratch + kOffSmat;
+  float* map = scratch + kOffMap;
+  fc_kernel<<<256, 256, 0, st>>>(w->cnet.fc_w, w->cnet.fc_b, gram_c, w->snet.fc_w, w->snet.fc_b, gram_s, cmat, smat);
+  count_launch();
+  MapSrc src{cmat, smat, mean_c, mean_s, *w, transmatrix};
+  if (fused == nullptr && rows_fast(content, ps, cs)) {
+    const int grid = (int)std::max<long long>(1, std::min<long long>((n + 127) / 128, 4LL * num_sms()));
+    apply_rows_kernel<<<grid, 256, 0, st>>>(content, n, ps, src, rgb);
+    count_launch();
+  } else {
+    if (fused) {   // the 64x64 map of the fused feature itself (tests / debugging output)
+      compose_kernel<<<1, 256, 0, st>>>(cmat, smat, *w, mean_c, mean_s, map, nullptr);
+      count_launch();
+    }
+    apply_kernel<<<blocks_for_pixels(n), 256, 0, st>>>(content, n, ps, cs, src, map, rgb, fused);
+    count_launch();
+  }
+  CRNERF_CUDA(cudaGetLastError());
+  return CRNERF_OK;
+}
+
+// everything after the content Gram is known (sharded path: mean and Gram were all-reduced):
+// style branch, FCs, apply
 int style_finish(const crnerf_style_weights* w, const float* content, int64_t n, int64_t ps,
                  int64_t cs, const float* mean_c, const float* gram_c_normalised,
                  const float* style, int64_t ns, int64_t sps, int64_t scs, float* rgb,
                  float* transmatrix, float* fused, float* scratch, cudaStream_t st) {
-  float* sum_part = scratch + kOffSumPart;
   float* gram_part = scratch + kOffGramPart;
   float* mean_s = scratch + kOffMeanS;
   float* gram_s = scratch + kOffGramS;
-  float* cmat = scratch + kOffCmat;
-  float* smat = scratch + kOffSmat;
-  float* map = scratch + kOffMap;
-  int rc = style_stats1(style, ns, sps, scs, mean_s, sum_part, st);
+  int rc;
+  GramJob js;
+  if (ns <= kSelfMeanMaxPixels) {
+    js = make_job(w->snet, style, ns, sps, scs, nullptr, 0, 1.f / (float)ns, gram_part, mean_s, 0);
+  } else {
+    int nb = 0;
+    rc = sum_partials(style, ns, sps, scs, scratch + kOffSumPart, &nb, st);
+    if (rc) return rc;
+    js = make_job(w->snet, style, ns, sps, scs, scratch + kOffSumPart, nb, 1.f / (float)ns, gram_part, mean_s, 1);
+  }
+  rc = gram_tc_launch(&js, 1, kGramBlocksPerJob, st);
   if (rc) return rc;
-  reduce_partials_kernel<<<1, 64, 0, st>>>(mean_s, 1, 64, 1.f / (float)ns, mean_s);
+  reduce_gram_kernel<<<128, 256, 0, st>>>(gram_part, js.n_blocks, 1.f / (float)ns, gram_s, nullptr, 0, 0.f, nullptr);
   count_launch();
-  rc = style_stats2(w->snet, style, ns, sps, scs, mean_s, gram_s, gram_part, 1.f / (float)ns, st);
-  if (rc) return rc;
-  fc_kernel<<<256, 256, 0, st>>>(w->cnet.fc_w, w->cnet.fc_b, gram_c_normalised, w->snet.fc_w,
-                                 w->snet.fc_b, gram_s, cmat, smat);
-  compose_kernel<<<1, 256, 0, st>>>(cmat, smat, *w, mean_c, mean_s, map, transmatrix);
-  if (fused == nullptr && rows_fast(content, ps, cs))
-    apply_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(content, n, ps, map, rgb);
-  else
-    apply_kernel<<<blocks_for_pixels(n), 256, 0, st>>>(content, n, ps, cs, map, rgb, fused);
-  count_launch(3);
-  CRNERF_CUDA(cudaGetLastError());
-  return CRNERF_OK;
+  return fc_and_apply(w, content, n, ps, cs, mean_c, gram_c_normalised, mean_s, gram_s, rgb, transmatrix, fused,
+                      scratch, st);
 }
 
 // CNN.forward alone (linearStyleTransfer.py:28-37): convs -> Gram/(h*w) -> fc, no mean removal
@@ -421,36 +628,63 @@ int cnn_forward(const crnerf_cnn_weights* cw, const float* x, int64_t n, int64_t
   return CRNERF_OK;
 }
 
+// style_net.forward.  content_sum_parts (n_parts, 64), optional: partial channel sums of the
+// content map whose rows add up to its channel sums (the render kernel's epilogue emits them);
+// without them the map is read once more to form them.
 int style_forward(const crnerf_style_weights* w, const float* content, int64_t n, int64_t ps,
-                  int64_t cs, const float* style, int64_t ns, int64_t sps, int64_t scs, float* rgb,
+                  int64_t cs, const float* style, int64_t ns, int64_t sps, int64_t scs,
+                  const float* content_sum_parts, int n_parts, float* rgb,
                   float* transmatrix, float* fused, float* scratch, cudaStream_t st) {
   CRNERF_REQUIRE(w && rgb && scratch, "null argument");
   int rc = check_feat(content, n, ps, cs, "content");
   if (rc) return rc;
-  float* map = scratch + kOffMap;
-  if (style == nullptr) {
-    content_map_kernel<<<1, 192, 0, st>>>(*w, map);
-    if (rows_fast(content, ps, cs))
-      apply_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(content, n, ps, map, rgb);
-    else
-      apply_kernel<<<blocks_for_pixels(n), 256, 0, st>>>(content, n, ps, cs, map, rgb, nullptr);
-    count_launch(2);
+  if (style == nullptr) {   // decoder only (type == "content", linearStyleTransfer.py:285-287)
+    MapSrc src{nullptr, nullptr, nullptr, nullptr, *w, nullptr};
+    if (rows_fast(content, ps, cs)) {
+      const int grid = (int)std::max<long long>(1, std::min<long long>((n + 127) / 128, 4LL * num_sms()));
+      apply_rows_kernel<<<grid, 256, 0, st>>>(content, n, ps, src, rgb);
+    } else {
+      apply_kernel<<<blocks_for_pixels(n), 256, 0, st>>>(content, n, ps, cs, src, nullptr, rgb, nullptr);
+    }
+    count_launch();
     CRNERF_CUDA(cudaGetLastError());
     return CRNERF_OK;
   }
   rc = check_feat(style, ns, sps, scs, "style");
   if (rc) return rc;
+  CRNERF_REQUIRE(content_sum_parts == nullptr || n_parts >= 1, "content_sum_parts without rows");
   float* mean_c = scratch + kOffMeanC;
+  float* mean_s = scratch + kOffMeanS;
   float* gram_c = scratch + kOffGramC;
-  rc = style_stats1(content, n, ps, cs, mean_c, scratch + kOffSumPart, st);
+  float* gram_s = scratch + kOffGramS;
+  float* gram_part = scratch + kOffGramPart;
+  // channel means: from the caller's partial sums, by the Gram CTAs themselves (small maps), or
+  // from one extra pass over the map
+  GramJob jobs[2];
+  int nb = 0;
+  if (content_sum_parts == nullptr && n > kSelfMeanMaxPixels) {
+    rc = sum_partials(content, n, ps, cs, scratch + kOffSumPart, &nb, st, kMaxBlocks / 2);
+    if (rc) return rc;
+    content_sum_parts = scratch + kOffSumPart;
+    n_parts = nb;
+  }
+  jobs[0] = make_job(w->cnet, content, n, ps, cs, content_sum_parts, n_parts, 1.f / (float)n, gram_part, mean_c, 1);
+  if (ns <= kSelfMeanMaxPixels) {
+    jobs[1] = make_job(w->snet, style, ns, sps, scs, nullptr, 0, 1.f / (float)ns,
+                       gram_part + (size_t)kGramBlocksPerJob * 1024, mean_s, 0);
+  } else {
+    float* sp = scratch + kOffSumPart + (size_t)(kMaxBlocks / 2) * 64;   // second half of the sums region
+    rc = sum_partials(style, ns, sps, scs, sp, &nb, st, kMaxBlocks / 2);
+    if (rc) return rc;
+    jobs[1] = make_job(w->snet, style, ns, sps, scs, sp, nb, 1.f / (float)ns,
+                       gram_part + (size_t)kGramBlocksPerJob * 1024, mean_s, 1);
+  }
+  rc = gram_tc_launch(jobs, 2, kGramBlocksPerJob, st);
   if (rc) return rc;
-  reduce_partials_kernel<<<1, 64, 0, st>>>(mean_c, 1, 64, 1.f / (float)n, mean_c);
+  reduce_gram_kernel<<<256, 256, 0, st>>>(jobs[0].partial, jobs[0].n_blocks, 1.f / (float)n, gram_c,
+                                          jobs[1].partial, jobs[1].n_blocks, 1.f / (float)ns, gram_s);
   count_launch();
-  rc = style_stats2(w->cnet, content, n, ps, cs, mean_c, gram_c, scratch + kOffGramPart,
-                    1.f / (float)n, st);
-  if (rc) return rc;
-  return style_finish(w, content, n, ps, cs, mean_c, gram_c, style, ns, sps, scs, rgb,
-                      transmatrix, fused, scratch, st);
+  return fc_and_apply(w, content, n, ps, cs, mean_c, gram_c, mean_s, gram_s, rgb, transmatrix, fused, scratch, st);
 }
 
 }  // namespace crnerf

@@ -8,40 +8,59 @@
 //
 // Per 128-pixel tile (one pixel per TMEM lane / epilogue thread):
 //   X (128x64)  -> smem, K-major SW128                                 (threads, from HBM)
-//   D1 = X  W1^T  (N=128)  -> +b1, LeakyReLU -> H1 in TMEM              tcgen05 SS
-//   D2 = H1 W2^T  (N=64)   -> +b2, LeakyReLU -> H2 in TMEM              tcgen05 TS
-//   D3 = H2 W3^T  (N=32)   -> +b3 -> Y; Y^T (32x128, pixels along K) -> smem
-//   G += Y^T Y    (M=128 with only rows 0..31 meaningful, N=32, K=128)  tcgen05 SS
-// G lives in TMEM for the CTA's whole lifetime and is written out once.
+//   D1 = X  W1^T  (N=128)  -> +b1, LeakyReLU -> H1, written IN PLACE over D1   tcgen05 SS
+//   D2 = H1 W2^T  (N=64)   -> +b2, LeakyReLU -> H2, in place over D2            tcgen05 TS
+//   D3 = H2 W3^T  (N=32)   -> +b3 -> Y; Y^T (32x128, pixels along K) -> smem    tcgen05 TS
+//   G1 += Yh^T Yh, G2 += Yh^T Yl  (M=128 with only rows 0..31 meaningful, N=32, K=128)  SS
+// G1 / G2 live in TMEM for the CTA's whole lifetime; G = G1 + G2 + G2^T is written once.
 //
-// Precision: the result feeds a 1e-4 parity bar through two 1024x1024 FCs, so 16-bit
-// operands alone are not enough.  Every operand is split into fp16 hi + fp16 lo
-// (x = hi + lo to ~2^-22) and every product is issued as three MMAs
-// (hi*hi + hi*lo + lo*hi, fp32 accumulate): fp32-class accuracy at 3x a tensor cost that is
-// still far below the pass's HBM time.
+// Two tiles ("streams") are in flight per CTA, each with its own 8 epilogue warps, operand
+// buffers and TMEM regions (2 x 224 columns + 64 for G1/G2 = all 512), so one stream's MMAs run
+// under the other's epilogues; a single issuer thread polls both streams' barriers and issues
+// whichever MMA group is ready.  In-place activations are what makes two streams fit: a 32-column
+// block of fp32 accumulators becomes 16 columns of packed fp16 hi words + 16 of lo words in the
+// same columns (each thread rewrites its own lane).
+//
+// Precision: the result feeds a 1e-4 parity bar through two 1024x1024 FCs, and on trained
+// weights the layers cancel (a CPU emulation with 16-bit activations misses the bar by 50-200x,
+// see DESIGN.md), so every operand is split into fp16 hi + fp16 lo (x = hi + lo to ~2^-22) and
+// every product issued as three MMAs (hi*hi + hi*lo + lo*hi, fp32 accumulate); the Gram uses its
+// symmetry (Yh^T Yl + Yl^T Yh = G2 + G2^T) to get by with two.
+//
+// One launch serves up to two "jobs" (the content map with cnet, the style map with snet): CTAs
+// past job 0's share work on job 1.  Each job's channel mean comes from per-block partial sums
+// (the render kernel's epilogue or sums_rows_kernel), from an explicit vector (sharded path:
+// 1 partial), or - small maps - is computed by the CTA itself.
 #include <cuda_fp16.h>
 #include <algorithm>
 #include "common.h"
 #include "ptx.cuh"
+#include "gram_tc.h"
 
 namespace crnerf {
 namespace {
 
-constexpr int kGThreads = 288;  // warps 0-7: (lane quarter, column half) of a pixel row; warp 8: MMA issuer + TMEM allocator
+constexpr int kEpiWarps = 16;                       // 2 streams x (lane quarter x column half)
+// + warp 16: MMA issuer / TMEM allocator; warps 17-19 only donate registers: the register file is
+// allocated in units of 4 warps, so 17 warps cost as much as 20, and setmaxnreg moves what the
+// four control warps do not need (4 x 64 x 32) to the 16 epilogue warps (96 -> 112 each)
+constexpr int kGThreads = (kEpiWarps + 4) * 32;
 // shared memory map (bytes).  The Gram A operand is addressed as a 128-row tile although only
 // 32 rows (channels) exist: rows 32..127 alias whatever follows (the other Y^T slabs, the X
-// tile) and only feed accumulator lanes 32..127, which are never read.
-constexpr int kYtOff = 0;       // Y^T: hi slab0, hi slab1, lo slab0, lo slab1 (32 rows x 128 B each)
+// tile) and only feed accumulator lanes that are never read.
+constexpr int kStreamBytes = 49152;   // per stream: Y^T hi slab0, hi slab1, lo slab0, lo slab1 (4 KB each) | X hi, X lo (16 KB each)
 constexpr int kYtSlab = 4096;
-constexpr int kXOff = 16384;    // X hi, X lo (128 rows x 128 B each)
-constexpr int kW1Off = 49152;   // W1 hi, lo: 128 rows x 128 B
-constexpr int kW2Off = 81920;   // W2 hi (2 slabs x 64 rows x 128 B), lo
-constexpr int kW3Off = 114688;  // W3 hi, lo: 32 rows x 128 B
-constexpr int kFOff = 122880;   // fp32: b1[128] b2[64] b3[32] mean[64]
-constexpr int kBarOff2 = kFOff + 288 * 4;  // 8 mbarriers + tmem slot
-constexpr int kGramSmem = kBarOff2 + 8 * 8 + 16;
-// TMEM columns
-constexpr uint32_t cD1 = 0, cA1h = 128, cA1l = 192, cD2 = 256, cA2h = 320, cA2l = 352, cD3 = 384, cG = 416;
+constexpr int kXOffS = 16384;
+constexpr int kW1Off = 2 * kStreamBytes;   // W1 hi, lo: 128 rows x 128 B
+constexpr int kW2Off = kW1Off + 32768;     // W2 hi (2 slabs x 64 rows x 128 B), lo
+constexpr int kW3Off = kW2Off + 32768;     // W3 hi, lo: 32 rows x 128 B
+constexpr int kFOff = kW3Off + 8192;       // fp32: b1[128] b2[64] b3[32] mean[64]
+constexpr int kRedOff = kFOff + 288 * 4;   // 8 x 64 floats (mean partials), reused as the 32 x 33 transpose tile
+constexpr int kBarOff2 = kRedOff + 33 * 32 * 4;  // 16 mbarriers + tmem slot
+constexpr int kGramSmem = kBarOff2 + 16 * 8 + 16;
+// TMEM columns: stream s at 224*s: P (128: D1 -> H1 in place), Q (64: D2 -> H2 in place), R (32: D3)
+constexpr uint32_t kStreamCols = 224, cP = 0, cQ = 128, cR = 192, cG1 = 448, cG2 = 480;
+enum { X_FULL = 0, D1_FULL, A1_FULL, D2_FULL, A2_FULL, D3_FULL, YT_FULL, G_DONE, kBarsPerStream };
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
 
@@ -50,6 +69,18 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   hi = pack2<0, false>(a, b);
   const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
   lo = pack2<0, false>(a - f.x, b - f.y);
+}
+
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
 }
 
 // fp32 row-major weight (rows x cols) -> SW128 K-major fp16 hi/lo slabs of 64 columns
@@ -66,148 +97,221 @@ __device__ void stage_weight(const float* __restrict__ w, int rows, int cols, ui
 }
 
 struct GramParams {
-  const float* g;
-  long long n, pix_stride, ch_stride;
-  const float* mean;
-  crnerf_cnn_weights w;
-  float* partial;
-  int vec;  // rows are contiguous, 16-byte aligned and a multiple of 4 floats apart: float4 loads
+  GramJob job[2];
+  int n_jobs;
 };
+
+// channel mean of the job's map -> mean[64] (shared), fixed summation order.  All threads call.
+__device__ void job_mean(const GramJob& J, float* mean, float* red) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (J.self_mean && J.ch_stride != 1) {
+    // planar / generic strides: a warp per channel, lanes along the pixels (coalesced)
+    if (warp < kEpiWarps) {
+      for (int c = warp; c < 64; c += kEpiWarps) {
+        float acc = 0.f;
+        for (long long p = lane; p < J.n; p += 32) acc += __ldg(J.g + p * J.pix_stride + (long long)c * J.ch_stride);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) mean[c] = acc * J.mean_scale;
+      }
+    }
+    return;   // caller's __syncthreads publishes mean[]
+  }
+  // rows of 64 contiguous channels: the map itself (self_mean) or per-block partial sums
+  const float* src = J.self_mean ? J.g : J.sum_parts;
+  const long long rows = J.self_mean ? J.n : (long long)J.n_parts;
+  const long long stride = J.self_mean ? J.pix_stride : 64;
+  if (tid < 512) {
+    const int c = tid & 63, rl = tid >> 6;
+    float acc = 0.f;
+    for (long long r = rl; r < rows; r += 8) acc += __ldg(src + r * stride + c);
+    red[rl * 64 + c] = acc;
+  }
+  __syncthreads();
+  if (tid < 64)
+    mean[tid] = (((red[tid] + red[64 + tid]) + (red[128 + tid] + red[192 + tid])) +
+                 ((red[256 + tid] + red[320 + tid]) + (red[384 + tid] + red[448 + tid]))) * J.mean_scale;
+}
 
 __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_constant__ GramParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   float* fblob = reinterpret_cast<float*>(smem + kFOff);
+  float* red = reinterpret_cast<float*>(smem + kRedOff);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff2);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  enum { X_FULL = 0, D1_FULL, A1_FULL, D2_FULL, A2_FULL, D3_FULL, YT_FULL, G_DONE };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kBarsPerStream);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const GramJob& J = P.job[(P.n_jobs == 2 && (int)blockIdx.x >= P.job[1].first_block) ? 1 : 0];
+  const int lb = (int)blockIdx.x - J.first_block;      // this CTA's index inside its job
 
   if (tid == 0) {
-    mbar_init(&bars[X_FULL], 8);
-    mbar_init(&bars[D1_FULL], 1);
-    mbar_init(&bars[A1_FULL], 8);
-    mbar_init(&bars[D2_FULL], 1);
-    mbar_init(&bars[A2_FULL], 8);
-    mbar_init(&bars[D3_FULL], 1);
-    mbar_init(&bars[YT_FULL], 8);
-    mbar_init(&bars[G_DONE], 1);
+    for (int s = 0; s < 2; ++s) {
+      uint64_t* b = bars + s * kBarsPerStream;
+      mbar_init(&b[X_FULL], 8);
+      mbar_init(&b[D1_FULL], 1);
+      mbar_init(&b[A1_FULL], 8);
+      mbar_init(&b[D2_FULL], 1);
+      mbar_init(&b[A2_FULL], 8);
+      mbar_init(&b[D3_FULL], 1);
+      mbar_init(&b[YT_FULL], 8);
+      mbar_init(&b[G_DONE], 1);
+    }
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc<512>(tmem_slot);
-  stage_weight(P.w.conv_w[0], 128, 64, smem + kW1Off, smem + kW1Off + 16384);
-  stage_weight(P.w.conv_w[1], 64, 128, smem + kW2Off, smem + kW2Off + 16384);
-  stage_weight(P.w.conv_w[2], 32, 64, smem + kW3Off, smem + kW3Off + 4096);
-  for (int i = tid; i < 288; i += kGThreads)
-    fblob[i] = i < 128 ? P.w.conv_b[0][i]
-                       : (i < 192 ? P.w.conv_b[1][i - 128] : (i < 224 ? P.w.conv_b[2][i - 192] : P.mean[i - 224]));
+  if (warp == kEpiWarps) tmem_alloc<512>(tmem_slot);
+  stage_weight(J.w.conv_w[0], 128, 64, smem + kW1Off, smem + kW1Off + 16384);
+  stage_weight(J.w.conv_w[1], 64, 128, smem + kW2Off, smem + kW2Off + 16384);
+  stage_weight(J.w.conv_w[2], 32, 64, smem + kW3Off, smem + kW3Off + 4096);
+  for (int i = tid; i < 224; i += kGThreads)
+    fblob[i] = i < 128 ? J.w.conv_b[0][i] : (i < 192 ? J.w.conv_b[1][i - 128] : J.w.conv_b[2][i - 192]);
+  job_mean(J, fblob + 224, red);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  const long long n_tiles = (P.n + 127) / 128;
+  const long long n_tiles = (J.n + 127) / 128;
   const float* b1 = fblob, *b2 = fblob + 128, *b3 = fblob + 192, *mean = fblob + 224;
+  if (lb == 0 && J.mean_out && tid < 64) J.mean_out[tid] = mean[tid];
+  // CTA-local tile j (stream j & 1) -> tile of the map; `reverse` walks the map from its end, so a
+  // pass that follows a forward pass over the same map starts on what is still in L2
+  const int nb = J.n_blocks;
+  auto tile_of = [&](long long j) -> long long {
+    const long long t = lb + j * (long long)nb;
+    return t < n_tiles ? (J.reverse ? n_tiles - 1 - t : t) : -1;
+  };
+  // number of tiles of stream s
+  auto count_of = [&](int s) -> uint32_t {
+    const long long mine = lb < n_tiles ? (n_tiles - 1 - lb) / nb + 1 : 0;   // tiles of this CTA
+    return (uint32_t)((mine + 1 - s) / 2);
+  };
 
-  if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 | version | SW128
-    auto desc = [](uint32_t saddr) {
-      return (static_cast<uint64_t>(kHi) << 32) | (((saddr & 0x3ffffu) >> 4) | (1u << 16));
-    };
-    const uint32_t s0 = smem_u32(smem);
-    // layer 1 of tile i: D1 = X W1^T, three split terms x 4 k-steps (SS).  Issued one stage
-    // ahead (right after layer 2 of the previous tile): X(i) is staged as soon as D1(i-1) has
-    // been drained, so these MMAs run under the previous tile's layer-3 / Gram phases.
-    auto layer1 = [&](uint32_t i) {
-      mbar_wait(&bars[X_FULL], i & 1, 60);
-      tc_fence_after_sync();
-      if (elect_one()) {
-        const uint32_t id = make_idesc_f16(128, 128, 0);
+  if (warp >= kEpiWarps) {
+    setmaxnreg_dec<32>();     // the whole warpgroup (warps 16-19) must execute the same setmaxnreg
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (warp == kEpiWarps && lane == 0) {
+      constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 | version | SW128
+      auto desc = [](uint32_t saddr) {
+        return (static_cast<uint64_t>(kHi) << 32) | (((saddr & 0x3ffffu) >> 4) | (1u << 16));
+      };
+      const uint32_t s0 = smem_u32(smem);
+      const uint32_t cnt[2] = {count_of(0), count_of(1)};
+      uint32_t l1_it[2] = {0, 0};    // next tile (stream-local) whose layer 1 is to be issued
+      uint32_t m_it[2] = {0, 0};     // tile of the main chain
+      int m_op[2] = {0, 0};          // 0: layer 2, 1: layer 3, 2: Gram
+      bool g_started = false;
+      uint32_t idle = 0;
+      while (m_it[0] < cnt[0] || m_it[1] < cnt[1]) {
+        bool progressed = false;
 #pragma unroll
-        for (int term = 0; term < 3; ++term) {
-          const uint32_t a = s0 + kXOff + (term == 2 ? 16384 : 0);    // hi, hi, lo
-          const uint32_t bq = s0 + kW1Off + (term == 1 ? 16384 : 0);  // hi, lo, hi
+        for (int s = 0; s < 2; ++s) {
+          uint64_t* b = bars + s * kBarsPerStream;
+          const uint32_t sb = s0 + s * kStreamBytes, tb = tmem + s * kStreamCols;
+          // ---- layer 1 of tile l1_it: D1 = X W1^T, three split terms x 4 k-steps (SS).  Needs the
+          // staged X and region P free (layer 2 of the previous tile, which reads H1 there, retired).
+          if (l1_it[s] < cnt[s] && mbar_test(&b[X_FULL], l1_it[s] & 1) &&
+              (l1_it[s] == 0 || mbar_test(&b[D2_FULL], (l1_it[s] - 1) & 1))) {
+            tc_fence_after_sync();
+            const uint32_t id = make_idesc_f16(128, 128, 0);
+#pragma unroll 1
+            for (int term = 0; term < 3; ++term) {
+              const uint32_t a = sb + kXOffS + (term == 2 ? 16384 : 0);   // hi, hi, lo
+              const uint32_t bq = s0 + kW1Off + (term == 1 ? 16384 : 0);  // hi, lo, hi
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tmem + cD1, desc(a + 32 * k), desc(bq + 32 * k), id, (term | k) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) umma_ss(tb + cP, desc(a + 32 * k), desc(bq + 32 * k), id, (term | k) ? 1u : 0u);
+            }
+            umma_commit(&b[D1_FULL]);
+            ++l1_it[s];
+            progressed = true;
+          }
+          if (m_it[s] >= cnt[s]) continue;
+          const uint32_t par = m_it[s] & 1;
+          if (m_op[s] == 0) {
+            // ---- layer 2: D2 = H1 W2^T, K = 128 (TS; H1 hi / lo words interleaved per 32-column block)
+            if (!mbar_test(&b[A1_FULL], par)) continue;
+            tc_fence_after_sync();
+            const uint32_t id = make_idesc_f16(128, 64, 0);
+#pragma unroll 1
+            for (int term = 0; term < 3; ++term) {
+              const uint32_t bq = s0 + kW2Off + (term == 1 ? 16384 : 0);
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                umma_ts(tb + cQ, tb + cP + 32 * (k >> 1) + 8 * (k & 1) + (term == 2 ? 16 : 0),
+                        desc(bq + (k >> 2) * 8192 + 32 * (k & 3)), id, (term | k) ? 1u : 0u);
+            }
+            umma_commit(&b[D2_FULL]);
+            m_op[s] = 1;
+            progressed = true;
+          } else if (m_op[s] == 1) {
+            // ---- layer 3: D3 = H2 W3^T, K = 64 (TS)
+            if (!mbar_test(&b[A2_FULL], par)) continue;
+            tc_fence_after_sync();
+            const uint32_t id = make_idesc_f16(128, 32, 0);
+#pragma unroll 1
+            for (int term = 0; term < 3; ++term) {
+              const uint32_t bq = s0 + kW3Off + (term == 1 ? 4096 : 0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_ts(tb + cR, tb + cQ + 32 * (k >> 1) + 8 * (k & 1) + (term == 2 ? 16 : 0), desc(bq + 32 * k), id,
+                        (term | k) ? 1u : 0u);
+            }
+            umma_commit(&b[D3_FULL]);
+            m_op[s] = 2;
+            progressed = true;
+          } else {
+            // ---- Gram: G1 += Yh^T Yh, G2 += Yh^T Yl, K = the tile's 128 pixels (SS; A rows 32..127 don't care)
+            if (!mbar_test(&b[YT_FULL], par)) continue;
+            tc_fence_after_sync();
+            const uint32_t id = make_idesc_f16(128, 32, 0);
+            const uint32_t yh = sb, yl = sb + 2 * kYtSlab;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t o = (k >> 2) * kYtSlab + 32 * (k & 3);
+              umma_ss(tmem + cG1, desc(yh + o), desc(yh + o), id, (g_started || k) ? 1u : 0u);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t o = (k >> 2) * kYtSlab + 32 * (k & 3);
+              umma_ss(tmem + cG2, desc(yh + o), desc(yl + o), id, (g_started || k) ? 1u : 0u);
+            }
+            umma_commit(&b[G_DONE]);
+            g_started = true;
+            m_op[s] = 0;
+            ++m_it[s];
+            progressed = true;
+          }
         }
-        umma_commit(&bars[D1_FULL]);
-      }
-      __syncwarp();
-    };
-    uint32_t it = 0;
-    if ((long long)blockIdx.x < n_tiles) layer1(0);
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      const uint32_t par = it & 1;
-      // ---- layer 2: D2 = H1 W2^T, K = 128 (TS)
-      mbar_wait(&bars[A1_FULL], par, 61);
-      tc_fence_after_sync();
-      if (elect_one()) {
-        const uint32_t id = make_idesc_f16(128, 64, 0);
-#pragma unroll
-        for (int term = 0; term < 3; ++term) {
-          const uint32_t a = tmem + (term == 2 ? cA1l : cA1h);
-          const uint32_t bq = s0 + kW2Off + (term == 1 ? 16384 : 0);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_ts(tmem + cD2, a + 8 * k, desc(bq + (k >> 2) * 8192 + 32 * (k & 3)), id, (term | k) ? 1u : 0u);
+        if (progressed) {
+          idle = 0;
+        } else if (++idle == (1u << 26)) {   // protocol bug: fail the launch instead of hanging the box
+          g_wait_timeout_tag = 0x80000000u | (69u << 16) | (blockIdx.x & 0xffff);
+          __trap();
         }
-        umma_commit(&bars[D2_FULL]);
       }
-      __syncwarp();
-      if (t + gridDim.x < n_tiles) layer1(it + 1);   // A1_FULL(it) above also means D1 is drained
-      // ---- layer 3: D3 = H2 W3^T, K = 64 (TS)
-      mbar_wait(&bars[A2_FULL], par, 62);
-      tc_fence_after_sync();
-      if (elect_one()) {
-        const uint32_t id = make_idesc_f16(128, 32, 0);
-#pragma unroll
-        for (int term = 0; term < 3; ++term) {
-          const uint32_t a = tmem + (term == 2 ? cA2l : cA2h);
-          const uint32_t bq = s0 + kW3Off + (term == 1 ? 4096 : 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ts(tmem + cD3, a + 8 * k, desc(bq + 32 * k), id, (term | k) ? 1u : 0u);
-        }
-        umma_commit(&bars[D3_FULL]);
-      }
-      __syncwarp();
-      // ---- Gram: G += Y^T Y, K = the tile's 128 pixels (SS; A rows 32..127 are don't-care)
-      mbar_wait(&bars[YT_FULL], par, 63);
-      tc_fence_after_sync();
-      if (elect_one()) {
-        const uint32_t id = make_idesc_f16(128, 32, 0);
-#pragma unroll
-        for (int term = 0; term < 3; ++term) {
-          const uint32_t a = s0 + kYtOff + (term == 2 ? 2 * kYtSlab : 0);
-          const uint32_t bq = s0 + kYtOff + (term == 1 ? 2 * kYtSlab : 0);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_ss(tmem + cG, desc(a + (k >> 2) * kYtSlab + 32 * (k & 3)),
-                    desc(bq + (k >> 2) * kYtSlab + 32 * (k & 3)), id, (it | term | k) ? 1u : 0u);
-        }
-        umma_commit(&bars[G_DONE]);
-      }
-      __syncwarp();
     }
+    __syncwarp();
   } else {
+    setmaxnreg_inc<112>();
     // ------------------------------------------------------------------ pixel rows
-    // warp w: TMEM lane quarter q = w & 3 (rows 32q..32q+31, one per lane), column half ch = w >> 2
-    const int q = warp & 3, ch = warp >> 2;
+    // stream s = warp / 8; inside it: TMEM lane quarter q (rows 32q..32q+31, one per lane), column half ch
+    const int s = warp >> 3, q = warp & 3, ch = (warp >> 2) & 1;
     const int row = 32 * q + lane;
-    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-    // this thread's half of a pixel row (32 channels) as 8 float4; the NEXT tile's values are
-    // requested while the current tile is being processed (registers are plentiful here)
+    uint64_t* b = bars + s * kBarsPerStream;
+    uint8_t* sbase = smem + s * kStreamBytes;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + s * kStreamCols;
+    // this thread's half of a pixel row (32 channels) as 8 float4; the stream's NEXT tile is
+    // requested while the current one is being processed
     float4 xr[8];
     auto load_x = [&](long long t) {
       const long long p = t * 128 + row;
-      const bool valid = t < n_tiles && p < P.n;
+      const bool valid = t >= 0 && p < J.n;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (valid && P.vec) {
-          xr[i] = __ldg(reinterpret_cast<const float4*>(P.g + p * P.pix_stride + 32 * ch) + i);
+        if (valid && J.vec) {
+          xr[i] = __ldg(reinterpret_cast<const float4*>(J.g + p * J.pix_stride + 32 * ch) + i);
         } else if (valid) {
-          const float* src = P.g + p * P.pix_stride + (long long)(32 * ch + 4 * i) * P.ch_stride;
-          xr[i] = make_float4(__ldg(src), __ldg(src + P.ch_stride), __ldg(src + 2 * P.ch_stride),
-                              __ldg(src + 3 * P.ch_stride));
+          const float* src = J.g + p * J.pix_stride + (long long)(32 * ch + 4 * i) * J.ch_stride;
+          xr[i] = make_float4(__ldg(src), __ldg(src + J.ch_stride), __ldg(src + 2 * J.ch_stride),
+                              __ldg(src + 3 * J.ch_stride));
         } else {
           xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -215,100 +319,97 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
     };
     // X row (held in xr) of tile tt -> smem (hi, lo), then signal the issuer
     auto stage_x = [&](long long tt) {
-      const bool valid = tt * 128 + row < P.n;
-      {
-        uint8_t* xh = smem + kXOff, *xl = xh + 16384;
+      const bool valid = tt * 128 + row < J.n;
+      uint8_t* xh = sbase + kXOffS, *xl = xh + 16384;
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          const float4 q0 = xr[2 * c8], q1 = xr[2 * c8 + 1];
-          const float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-          const int c0 = 32 * ch + 8 * c8;
-          uint32_t h[4], l[4];
+      for (int c8 = 0; c8 < 4; ++c8) {
+        const float4 q0 = xr[2 * c8], q1 = xr[2 * c8 + 1];
+        const float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        const int c0 = 32 * ch + 8 * c8;
+        uint32_t h[4], l[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float a = valid ? v[2 * j] - mean[c0 + 2 * j] : 0.f;
-            const float b = valid ? v[2 * j + 1] - mean[c0 + 2 * j + 1] : 0.f;
-            split2(a, b, h[j], l[j]);
-          }
-          const uint32_t off = sw128_offset(row, 4 * ch + c8);
-          *reinterpret_cast<uint4*>(xh + off) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(xl + off) = make_uint4(l[0], l[1], l[2], l[3]);
+        for (int j = 0; j < 4; ++j) {
+          const float a = valid ? v[2 * j] - mean[c0 + 2 * j] : 0.f;
+          const float bb = valid ? v[2 * j + 1] - mean[c0 + 2 * j + 1] : 0.f;
+          split2(a, bb, h[j], l[j]);
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[X_FULL]);
+        const uint32_t off = sw128_offset(row, 4 * ch + c8);
+        *reinterpret_cast<uint4*>(xh + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(xl + off) = make_uint4(l[0], l[1], l[2], l[3]);
       }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b[X_FULL]);
     };
-    load_x(blockIdx.x);
-    if ((long long)blockIdx.x < n_tiles) {
-      stage_x(blockIdx.x);
-      load_x(blockIdx.x + gridDim.x);
+    long long t = tile_of(s);
+    load_x(t);
+    if (t >= 0) {
+      stage_x(t);
+      load_x(tile_of(s + 2));
     }
     uint32_t it = 0;
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    for (long long j = s; t >= 0; j += 2, ++it) {
       const uint32_t par = it & 1;
-      const long long p = t * 128 + row;
-      const bool valid = p < P.n;
-      // ---- epilogue 1: H1 = LeakyReLU(D1 + b1) -> A1 hi / lo (128 values = 64 + 64 columns)
-      mbar_wait(&bars[D1_FULL], par, 64);
+      const long long t_next = tile_of(j + 2);
+      const bool valid = t * 128 + row < J.n;
+      // ---- epilogue 1: H1 = LeakyReLU(D1 + b1), fp16 hi / lo words written over the same 32 columns
+      mbar_wait(&b[D1_FULL], par, 64);
       tc_fence_after_sync();
 #pragma unroll
       for (int qq = 0; qq < 2; ++qq) {
         const int blk = 2 * ch + qq;
-        uint32_t v[32], h[16], l[16];
-        tmem_ld_x32(lane_base + cD1 + 32 * blk, v);
+        uint32_t v[32], w[32];
+        tmem_ld_x32(lane_base + cP + 32 * blk, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          split2(lrelu02(__uint_as_float(v[2 * j]) + b1[32 * blk + 2 * j]),
-                 lrelu02(__uint_as_float(v[2 * j + 1]) + b1[32 * blk + 2 * j + 1]), h[j], l[j]);
-        tmem_st_x16p(lane_base + cA1h + 16 * blk, h);
-        tmem_st_x16p(lane_base + cA1l + 16 * blk, l);
+        for (int jj = 0; jj < 16; ++jj)
+          split2(lrelu02(__uint_as_float(v[2 * jj]) + b1[32 * blk + 2 * jj]),
+                 lrelu02(__uint_as_float(v[2 * jj + 1]) + b1[32 * blk + 2 * jj + 1]), w[jj], w[16 + jj]);
+        tmem_st_x32(lane_base + cP + 32 * blk, w);
       }
       tmem_st_wait();
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[A1_FULL]);
-      // D1(t) is drained and its MMAs have retired: stage the next tile's X now, so its layer 1
-      // runs under this tile's remaining phases; then request the tile after that
-      if (t + gridDim.x < n_tiles) {
-        stage_x(t + gridDim.x);
-        load_x(t + 2 * gridDim.x);
+      if (lane == 0) mbar_arrive(&b[A1_FULL]);
+      // D1(t) is drained and its MMAs have retired (X smem is free): stage the stream's next tile now,
+      // then request the one after that
+      if (t_next >= 0) {
+        stage_x(t_next);
+        load_x(tile_of(j + 4));
       }
-      // ---- epilogue 2: H2 = LeakyReLU(D2 + b2) -> A2 hi / lo (64 values = 32 + 32 columns)
-      mbar_wait(&bars[D2_FULL], par, 65);
+      // ---- epilogue 2: H2 = LeakyReLU(D2 + b2), in place
+      mbar_wait(&b[D2_FULL], par, 65);
       tc_fence_after_sync();
       {
-        uint32_t v[32], h[16], l[16];
-        tmem_ld_x32(lane_base + cD2 + 32 * ch, v);
+        uint32_t v[32], w[32];
+        tmem_ld_x32(lane_base + cQ + 32 * ch, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          split2(lrelu02(__uint_as_float(v[2 * j]) + b2[32 * ch + 2 * j]),
-                 lrelu02(__uint_as_float(v[2 * j + 1]) + b2[32 * ch + 2 * j + 1]), h[j], l[j]);
-        tmem_st_x16p(lane_base + cA2h + 16 * ch, h);
-        tmem_st_x16p(lane_base + cA2l + 16 * ch, l);
+        for (int jj = 0; jj < 16; ++jj)
+          split2(lrelu02(__uint_as_float(v[2 * jj]) + b2[32 * ch + 2 * jj]),
+                 lrelu02(__uint_as_float(v[2 * jj + 1]) + b2[32 * ch + 2 * jj + 1]), w[jj], w[16 + jj]);
+        tmem_st_x32(lane_base + cQ + 32 * ch, w);
       }
       tmem_st_wait();
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[A2_FULL]);
+      if (lane == 0) mbar_arrive(&b[A2_FULL]);
       // ---- epilogue 3: Y = D3 + b3 (no activation, linearStyleTransfer.py:15), zero for pixels
       // beyond n; Y^T hi / lo -> smem with the pixel index along K (this thread: 16 channels)
-      mbar_wait(&bars[D3_FULL], par, 66);
+      mbar_wait(&b[D3_FULL], par, 66);
       tc_fence_after_sync();
       {
         uint32_t v[16];
-        tmem_ld_x16(lane_base + cD3 + 16 * ch, v);
+        tmem_ld_x16(lane_base + cR + 16 * ch, v);
         tmem_ld_wait();
-        if (it > 0) mbar_wait(&bars[G_DONE], (it - 1) & 1, 67);  // previous Gram MMAs done reading Y^T
-        uint8_t* yh = smem + kYtOff + (row >> 6) * kYtSlab;
+        if (it > 0) mbar_wait(&b[G_DONE], (it - 1) & 1, 67);  // the stream's previous Gram MMAs are done reading Y^T
+        uint8_t* yh = sbase + (row >> 6) * kYtSlab;
         uint8_t* yl = yh + 2 * kYtSlab;
         const uint32_t kk = row & 63;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int c = 16 * ch + j;
-          const float y = valid ? __uint_as_float(v[j]) + b3[c] : 0.f;
+        for (int jj = 0; jj < 16; ++jj) {
+          const int c = 16 * ch + jj;
+          const float y = valid ? __uint_as_float(v[jj]) + b3[c] : 0.f;
           const __half hi = __float2half_rn(y);
           const __half lo = __float2half_rn(y - __half2float(hi));
           const uint32_t off = sw128_offset(c, kk >> 3) + (kk & 7) * 2;
@@ -316,54 +417,76 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
           *reinterpret_cast<__half*>(yl + off) = lo;
         }
         fence_proxy_async_smem();
+        tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[YT_FULL]);
+        if (lane == 0) mbar_arrive(&b[YT_FULL]);
       }
+      t = t_next;
     }
-    // ---- G (rows 0..31) -> this block's partial
-    if (it > 0) {
-      mbar_wait(&bars[G_DONE], (it - 1) & 1, 68);
-      tc_fence_after_sync();
-    }
+    // ---- G = G1 + G2 + G2^T (rows 0..31) -> this block's partial
     if (warp == 0) {
-      uint32_t v[32];
-      if (it > 0) {
-        tmem_ld_x32(lane_base + cG, v);
+      const uint32_t c0 = count_of(0), c1 = count_of(1);
+      if (c0) mbar_wait(&bars[G_DONE], (c0 - 1) & 1, 68);
+      if (c1) mbar_wait(&bars[kBarsPerStream + G_DONE], (c1 - 1) & 1, 68);
+      tc_fence_after_sync();
+      uint32_t g1[32], g2[32];
+      if (c0 + c1) {
+        tmem_ld_x32(tmem + cG1, g1);
+        tmem_ld_x32(tmem + cG2, g2);
         tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
+        for (int jj = 0; jj < 32; ++jj) g1[jj] = g2[jj] = 0u;
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) P.partial[(long long)blockIdx.x * 1024 + row * 32 + j] = __uint_as_float(v[j]);
+      for (int jj = 0; jj < 32; ++jj) red[lane * 33 + jj] = __uint_as_float(g2[jj]);
+      __syncwarp();
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj)
+        J.partial[(long long)lb * 1024 + lane * 32 + jj] =
+            (__uint_as_float(g1[jj]) + __uint_as_float(g2[jj])) + red[jj * 33 + lane];
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<512>(tmem);
+  if (warp == kEpiWarps) tmem_dealloc<512>(tmem);
 }
 
 }  // namespace
 
-// partial[nb][1024] <- per-block un-normalised Gram partials; returns nb through *n_blocks
-int gram_tc(const crnerf_cnn_weights& cw, const float* g, int64_t n, int64_t ps, int64_t cs, const float* mean,
-            float* partial, int max_blocks, int* n_blocks, cudaStream_t st) {
+int gram_blocks(int64_t n, int max_blocks) {
   const long long tiles = (n + 127) / 128;
-  const int nb = (int)std::max<long long>(1, std::min<long long>(tiles, std::min(max_blocks, num_sms())));
+  return (int)std::max<long long>(1, std::min<long long>(tiles, std::min(max_blocks, num_sms())));
+}
+
+// One launch for up to two jobs.  job[i].first_block / n_blocks are filled here: when both jobs
+// together need more CTAs than there are SMs, job 1 (the small one: the style map) keeps its tile
+// count and job 0 gets the remaining SMs.
+int gram_tc_launch(GramJob* jobs, int n_jobs, int max_blocks, cudaStream_t st) {
+  CRNERF_REQUIRE(n_jobs == 1 || n_jobs == 2, "one or two Gram jobs per launch");
   GramParams P;
-  P.g = g;
-  P.n = n;
-  P.pix_stride = ps;
-  P.ch_stride = cs;
-  P.mean = mean;
-  P.w = cw;
-  P.partial = partial;
-  P.vec = cs == 1 && (ps & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+  P.n_jobs = n_jobs;
+  const int sms = num_sms();
+  int want[2] = {0, 0};
+  for (int i = 0; i < n_jobs; ++i) {
+    CRNERF_REQUIRE(jobs[i].g && jobs[i].partial && jobs[i].n >= 1, "bad Gram job");
+    CRNERF_REQUIRE(jobs[i].self_mean || (jobs[i].sum_parts && jobs[i].n_parts >= 1), "Gram job has no mean source");
+    want[i] = gram_blocks(jobs[i].n, max_blocks);
+  }
+  if (n_jobs == 2 && want[0] + want[1] > sms) want[0] = std::max(1, sms - want[1]);
+  int first = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    jobs[i].first_block = first;
+    jobs[i].n_blocks = want[i];
+    jobs[i].vec = jobs[i].ch_stride == 1 && (jobs[i].pix_stride & 3) == 0 &&
+                  (reinterpret_cast<uintptr_t>(jobs[i].g) & 15) == 0;
+    first += want[i];
+    P.job[i] = jobs[i];
+  }
   CRNERF_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSmem));
-  gram_tc_kernel<<<nb, kGThreads, kGramSmem, st>>>(P);
+  gram_tc_kernel<<<first, kGThreads, kGramSmem, st>>>(P);
   count_launch();
   CRNERF_CUDA(cudaGetLastError());
-  *n_blocks = nb;
   return CRNERF_OK;
 }
 

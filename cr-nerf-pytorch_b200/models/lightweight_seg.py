@@ -12,10 +12,13 @@ owns is
   so ``state_dict()`` keys / shapes, seeded default init (construction draws, then the
   ``kaiming_normal_`` pass over ``modules()``, lightweight_seg.py:307-317) and checkpoints are
   interchangeable (tests/test_cgnet.py pins all three against the unmodified file);
-* fp32 convolutions (cuDNN's TF32 path is switched off inside ``forward`` - the reference's CPU /
-  fp32 results are the parity bar, 1e-4) and a capture-safe forward (no host sync, no
-  data-dependent shapes), so the whole training step including this network replays as one CUDA
-  graph (``crnerf_b200.graphs.GraphedTrainStep``);
+* fp32 convolutions in the forward AND in the backward (the reference's CPU / fp32 results are the
+  parity bar, 1e-4; cuDNN's default TF32 path is off by 1e-3).  The switch is scoped, not global:
+  the conv stack runs inside one autograd node (``_Fp32Region``) that builds the inner graph under
+  ``cudnn.flags(allow_tf32=False)`` and differentiates it under the same flags, so the caller's
+  process-wide setting is never touched;
+* a capture-safe forward / backward (no host sync, no data-dependent shapes), so the whole training
+  step including this network replays as one CUDA graph (``crnerf_b200.graphs.GraphedTrainStep``);
 * ``mask_rows``: the caller's tail (train_mask_grid_sample.py:171-175 - second bilinear resize,
   ``'1 n h w -> (h w) n'``, ``[rgb_idx]``) evaluated only at the sampled pixels by
   ``crnerf_mask_sample_*`` instead of materialising the resized mask.
@@ -33,6 +36,31 @@ def _conv(n_in, n_out, k, stride=1, dilation=1, groups=1):
     pad = ((k - 1) // 2) * dilation
     return nn.Conv2d(n_in, n_out, (k, k), stride=stride, padding=(pad, pad), dilation=dilation, groups=groups,
                      bias=False)
+
+
+class _Fp32Region(torch.autograd.Function):
+    """``fn(x)`` as ONE node of the outer graph.  The inner graph (library convolutions) is recorded
+    in ``forward`` and differentiated in ``backward``, both under ``cudnn.flags(allow_tf32=False)`` -
+    a plain ``with`` block around the forward would leave the backward convolutions, which run later
+    on the autograd thread, on TF32.  ``params`` are passed as inputs only so that their gradients
+    are routed; ``fn`` reads them from the module."""
+
+    @staticmethod
+    def forward(ctx, fn, x, *params):
+        with torch.enable_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            leaf = x.detach().requires_grad_(x.requires_grad)
+            out = fn(leaf)
+        ctx.leaf, ctx.out, ctx.params = leaf, out, params
+        return out.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        wanted = [t for t in (ctx.leaf,) + tuple(ctx.params) if t.requires_grad]
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            grads = iter(torch.autograd.grad(ctx.out, wanted, g, allow_unused=True))
+        res = [next(grads) if t.requires_grad else None for t in (ctx.leaf,) + tuple(ctx.params)]
+        ctx.leaf = ctx.out = ctx.params = None
+        return (None, *res)
 
 
 class _Wrapped(nn.Module):
@@ -150,21 +178,28 @@ class Context_Guided_Network(nn.Module):
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight)
 
+    def _stack(self, x):
+        s1 = self.level1_2(self.level1_1(self.level1_0(x)))
+        inp1 = self.sample1(x)
+        inp2 = self.sample2(x)
+        s2_0 = self.level2_0(self.b1(torch.cat([s1, inp1], 1)))
+        s2 = s2_0
+        for blk in self.level2:
+            s2 = blk(s2)
+        s3_0 = self.level3_0(self.bn_prelu_2(torch.cat([s2, s2_0, inp2], 1)))
+        s3 = s3_0
+        for blk in self.level3:
+            s3 = blk(s3)
+        return self.classifier(self.bn_prelu_3(torch.cat([s3_0, s3], 1)))
+
     def logits(self, x):
         """Everything up to the 1x1 classifier: (B, classes, H/8, W/8), fp32 convolutions."""
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            s1 = self.level1_2(self.level1_1(self.level1_0(x)))
-            inp1 = self.sample1(x)
-            inp2 = self.sample2(x)
-            s2_0 = self.level2_0(self.b1(torch.cat([s1, inp1], 1)))
-            s2 = s2_0
-            for blk in self.level2:
-                s2 = blk(s2)
-            s3_0 = self.level3_0(self.bn_prelu_2(torch.cat([s2, s2_0, inp2], 1)))
-            s3 = s3_0
-            for blk in self.level3:
-                s3 = blk(s3)
-            return self.classifier(self.bn_prelu_3(torch.cat([s3_0, s3], 1)))
+        if not x.is_cuda:
+            return self._stack(x)
+        if not torch.is_grad_enabled():
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                return self._stack(x)
+        return _Fp32Region.apply(self._stack, x, *self.parameters())
 
     def forward(self, input):
         z = self.logits(input)

@@ -137,9 +137,11 @@ class style_net(nn.Module, _StyleParamsMixin):
                                       feat_nc=args.nerf_out_dim, out_dim=3, args_here=args)
         self._style_args = None
 
-    def forward(self, content_feature, style_feature, type=None):
+    def forward(self, content_feature, style_feature, type=None, channel_sums=None):
         """content (1,64,H,W), style (1,64,32,32) or None -> rgb (1,3,H,W),
-        reference linearStyleTransfer.py:284-291."""
+        reference linearStyleTransfer.py:284-291.  One extension: ``channel_sums`` (rows, 64), the
+        ``chansum_*`` entry of ``render_rays_cross_ray(..., channel_sums=True)`` for the same
+        features - the cross-ray block then reads the feature map twice instead of three times."""
         if _wants_grad(self, content_feature, style_feature):
             if style_feature is None and type == "content":
                 return self.decoder(content_feature)
@@ -150,7 +152,7 @@ class style_net(nn.Module, _StyleParamsMixin):
             self._style_args = torch_ops.style_params(self)
         if style_feature is None and type == "content":
             return torch.ops.crnerf.style_forward(content_feature, None, self._style_args)
-        return torch.ops.crnerf.style_forward(content_feature, style_feature, self._style_args)
+        return torch.ops.crnerf.style_forward(content_feature, style_feature, self._style_args, channel_sums)
 
     def _apply(self, fn, *a, **k):
         self._style_args = None            # .to()/.cuda() may replace the parameter tensors

@@ -338,6 +338,20 @@ int crnerf_style_forward(const crnerf_style_weights* w, const float* content,
                          int64_t s_ch_stride, float* rgb, float* transmatrix, float* fused,
                          float* scratch, void* stream);
 
+/* Same, with the content map's channel sums supplied as partial sums: content_sum_partials
+ * (n_partials, 64), rows adding up to the per-channel sums over all n_pixels - what
+ * crnerf_render_pass_opts writes as channel_partials (concatenate the rows of several calls).
+ * The block then reads the map twice (Gram pass, apply pass) instead of three times.  NULL / 0
+ * = crnerf_style_forward. */
+int crnerf_style_forward_sums(const crnerf_style_weights* w, const float* content, int64_t n_pixels,
+                              int64_t c_pix_stride, int64_t c_ch_stride, const float* style,
+                              int64_t n_style_pixels, int64_t s_pix_stride, int64_t s_ch_stride,
+                              const float* content_sum_partials, int n_partials, float* rgb,
+                              float* transmatrix, float* fused, float* scratch, void* stream);
+/* out (len) = column sums of parts (n_parts, len), fixed order (e.g. channel_partials -> the
+ * 64 channel sums of a rank's rays, the input of the sharded form's first all-reduce). */
+int crnerf_sum_rows(const float* parts, int n_parts, int len, float* out, void* stream);
+
 /* CNN.forward alone (models/linearStyleTransfer.py:28-37): x (n_pixels x 64) ->
  * out (1024) = fc(flatten(convs(x) convs(x)^T / n_pixels)).  Same scratch buffer. */
 int crnerf_cnn_forward(const crnerf_cnn_weights* w, const float* x, int64_t n_pixels,
