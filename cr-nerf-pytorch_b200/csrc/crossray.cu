@@ -390,7 +390,7 @@ apply_kernel(const float* __restrict__ g, long long n, long long pix_stride, lon
 // pixel are combined by a transposing butterfly: each exchange halves the number of (pixel, r)
 // values a lane still owns, 24 shuffles for 16 pixels x 3 outputs, fixed order.  Persistent
 // blocks sweep the map front to back.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 apply_rows_kernel(const float* __restrict__ g, long long n, long long pix_stride,
                   const __grid_constant__ MapSrc src, float* __restrict__ rgb) {
   __shared__ MapSmem sm;
@@ -404,13 +404,20 @@ apply_rows_kernel(const float* __restrict__ g, long long n, long long pix_stride
     for (int k = 0; k < 4; ++k) a[r][k] = sm.A[r][4 * l + k];
   const float a0[3] = {sm.a0[0], sm.a0[1], sm.a0[2]};
   const bool b3 = l & 8, b2 = l & 4, b1 = l & 2;
-  for (long long base = ((long long)blockIdx.x * 8 + warp) * 16; base < n; base += (long long)gridDim.x * 128) {
-    float4 x[8];
+  // software pipeline: the next step's 8 loads are in flight while this step's 16 pixels are reduced
+  const long long step = (long long)gridDim.x * 128;
+  auto load16 = [&](long long base, float4 (&x)[8]) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const long long p = base + 2 * u + half;
       x[u] = p < n ? __ldcs(reinterpret_cast<const float4*>(g + p * pix_stride) + l) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  };
+  long long base = ((long long)blockIdx.x * 8 + warp) * 16;
+  float4 x[8], xn[8];
+  if (base < n) load16(base, x);
+  for (; base < n; base += step) {
+    if (base + step < n) load16(base + step, xn);
     float v[8][3];
 #pragma unroll
     for (int u = 0; u < 8; ++u)
@@ -448,6 +455,8 @@ apply_rows_kernel(const float* __restrict__ g, long long n, long long pix_stride
 #pragma unroll
       for (int r = 0; r < 3; ++r) rgb[(long long)r * n + p] = 1.f / (1.f + expf(-(w1[r] + a0[r])));
     }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = xn[u];
   }
 }
 

@@ -43,7 +43,8 @@ namespace {
 constexpr int kEpiWarps = 16;                       // 2 streams x (lane quarter x column half)
 // + warp 16: MMA issuer / TMEM allocator; warps 17-19 only donate registers: the register file is
 // allocated in units of 4 warps, so 17 warps cost as much as 20, and setmaxnreg moves what the
-// four control warps do not need (4 x 64 x 32) to the 16 epilogue warps (96 -> 112 each)
+// four control warps do not need (4 x 32 x 32) to the 16 epilogue warps (96 -> 104 each); the issuer
+// keeps 64: its spills would go to L2 (the streaming loads thrash the small L1) and stall every MMA group
 constexpr int kGThreads = (kEpiWarps + 4) * 32;
 // shared memory map (bytes).  The Gram A operand is addressed as a 128-row tile although only
 // 32 rows (channels) exist: rows 32..127 alias whatever follows (the other Y^T slabs, the X
@@ -83,36 +84,74 @@ __device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
   return ok;
 }
 
-// fp32 row-major weight (rows x cols) -> SW128 K-major fp16 hi/lo slabs of 64 columns
-__device__ void stage_weight(const float* __restrict__ w, int rows, int cols, uint8_t* hi, uint8_t* lo) {
-  const int slab_bytes = rows * 128;
-  for (int e = threadIdx.x; e < rows * cols / 2; e += kGThreads) {
-    const int r = e / (cols / 2), c = 2 * (e % (cols / 2));
-    uint32_t h, l;
-    split2(w[r * cols + c], w[r * cols + c + 1], h, l);
-    const uint32_t off = (uint32_t)(c >> 6) * slab_bytes + sw128_offset(r, (c & 63) >> 3) + (c & 7) * 2;
-    *reinterpret_cast<uint32_t*>(hi + off) = h;
-    *reinterpret_cast<uint32_t*>(lo + off) = l;
+// fp32 row-major weight (rows x cols) -> SW128 K-major fp16 hi/lo slabs of 64 columns.  Each thread
+// requests all its float4s first (independent loads, one L2 round trip), then splits and stores.
+template <int kRows, int kCols>
+__device__ __forceinline__ void stage_weight(const float* __restrict__ w, uint8_t* hi, uint8_t* lo) {
+  constexpr int kQuads = kRows * kCols / 4, kIter = (kQuads + kGThreads - 1) / kGThreads, kSlab = kRows * 128;
+  float4 v[kIter];
+#pragma unroll
+  for (int i = 0; i < kIter; ++i) {
+    const int e = threadIdx.x + i * kGThreads;
+    v[i] = e < kQuads ? __ldg(reinterpret_cast<const float4*>(w) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < kIter; ++i) {
+    const int e = threadIdx.x + i * kGThreads;
+    if (e >= kQuads) break;
+    const int r = e / (kCols / 4), c = 4 * (e % (kCols / 4));
+    uint32_t h0, l0, h1, l1;
+    split2(v[i].x, v[i].y, h0, l0);
+    split2(v[i].z, v[i].w, h1, l1);
+    const uint32_t off = (uint32_t)(c >> 6) * kSlab + sw128_offset(r, (c & 63) >> 3) + (c & 7) * 2;
+    *reinterpret_cast<uint2*>(hi + off) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(lo + off) = make_uint2(l0, l1);
   }
 }
 
 struct GramParams {
   GramJob job[2];
   int n_jobs;
+  long long* ts;   // CRNERF_GRAM_TIMING builds: clock64 stamps of block 0 (tools/gram_timing.py)
 };
+
+#ifdef CRNERF_GRAM_TIMING
+#define TSTAMP(slot)                                                                   \
+  do {                                                                                 \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && P.ts) P.ts[slot] = clock64();    \
+  } while (0)
+#else
+#define TSTAMP(slot) do { } while (0)
+#endif
 
 // channel mean of the job's map -> mean[64] (shared), fixed summation order.  All threads call.
 __device__ void job_mean(const GramJob& J, float* mean, float* red) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (J.self_mean && J.ch_stride != 1) {
     // planar / generic strides: a warp per channel, lanes along the pixels (coalesced)
-    if (warp < kEpiWarps) {
-      for (int c = warp; c < 64; c += kEpiWarps) {
-        float acc = 0.f;
-        for (long long p = lane; p < J.n; p += 32) acc += __ldg(J.g + p * J.pix_stride + (long long)c * J.ch_stride);
+    if (warp < kEpiWarps) {    // 16 warps x 4 channels (warp, +16, +32, +48), 4 x 4 loads in flight per lane
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* base = J.g + (long long)warp * J.ch_stride;
+      long long p = lane;
+      for (; p + 96 < J.n; p += 128) {
+        float v[4][4];
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-        if (lane == 0) mean[c] = acc * J.mean_scale;
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[u][k] = __ldg(base + (p + 32 * u) * J.pix_stride + (long long)(16 * k) * J.ch_stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[k] += v[u][k];
+      }
+      for (; p < J.n; p += 32)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] += __ldg(base + p * J.pix_stride + (long long)(16 * k) * J.ch_stride);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
+        if (lane == 0) mean[warp + 16 * k] = acc[k] * J.mean_scale;
       }
     }
     return;   // caller's __syncthreads publishes mean[]
@@ -124,6 +163,7 @@ __device__ void job_mean(const GramJob& J, float* mean, float* red) {
   if (tid < 512) {
     const int c = tid & 63, rl = tid >> 6;
     float acc = 0.f;
+#pragma unroll 8
     for (long long r = rl; r < rows; r += 8) acc += __ldg(src + r * stride + c);
     red[rl * 64 + c] = acc;
   }
@@ -135,6 +175,7 @@ __device__ void job_mean(const GramJob& J, float* mean, float* red) {
 
 __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_constant__ GramParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0) TSTAMP(0);
   float* fblob = reinterpret_cast<float*>(smem + kFOff);
   float* red = reinterpret_cast<float*>(smem + kRedOff);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff2);
@@ -158,9 +199,10 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
     fence_mbar_init();
   }
   if (warp == kEpiWarps) tmem_alloc<512>(tmem_slot);
-  stage_weight(J.w.conv_w[0], 128, 64, smem + kW1Off, smem + kW1Off + 16384);
-  stage_weight(J.w.conv_w[1], 64, 128, smem + kW2Off, smem + kW2Off + 16384);
-  stage_weight(J.w.conv_w[2], 32, 64, smem + kW3Off, smem + kW3Off + 4096);
+  stage_weight<128, 64>(J.w.conv_w[0], smem + kW1Off, smem + kW1Off + 16384);
+  stage_weight<64, 128>(J.w.conv_w[1], smem + kW2Off, smem + kW2Off + 16384);
+  stage_weight<32, 64>(J.w.conv_w[2], smem + kW3Off, smem + kW3Off + 4096);
+  if (threadIdx.x == 0) TSTAMP(1);
   for (int i = tid; i < 224; i += kGThreads)
     fblob[i] = i < 128 ? J.w.conv_b[0][i] : (i < 192 ? J.w.conv_b[1][i - 128] : J.w.conv_b[2][i - 192]);
   job_mean(J, fblob + 224, red);
@@ -169,6 +211,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  if (threadIdx.x == 0) TSTAMP(2);
   const long long n_tiles = (J.n + 127) / 128;
   const float* b1 = fblob, *b2 = fblob + 128, *b3 = fblob + 192, *mean = fblob + 224;
   if (lb == 0 && J.mean_out && tid < 64) J.mean_out[tid] = mean[tid];
@@ -186,19 +229,26 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
   };
 
   if (warp >= kEpiWarps) {
-    setmaxnreg_dec<32>();     // the whole warpgroup (warps 16-19) must execute the same setmaxnreg
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (warp == kEpiWarps && lane == 0) {
+    setmaxnreg_dec<64>();     // the whole warpgroup (warps 16-19) must execute the same setmaxnreg
+    // ------------------------------------------------------------------ MMA issuer
+    // The whole warp runs the scheduler with warp-uniform state (barrier tests are combined by a
+    // vote, so the compiler keeps descriptors and counters in uniform registers: a thread-private
+    // scheduler pays ~20 instructions of register shuffling per MMA and becomes the bottleneck);
+    // one elected lane issues the MMAs of a burst as straight-line code.
+    if (warp == kEpiWarps) {
       constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 | version | SW128
       auto desc = [](uint32_t saddr) {
         return (static_cast<uint64_t>(kHi) << 32) | (((saddr & 0x3ffffu) >> 4) | (1u << 16));
+      };
+      auto ready = [](uint64_t* bar, uint32_t parity) -> bool {
+        return __all_sync(0xffffffffu, mbar_test(bar, parity) != 0);
       };
       const uint32_t s0 = smem_u32(smem);
       const uint32_t cnt[2] = {count_of(0), count_of(1)};
       uint32_t l1_it[2] = {0, 0};    // next tile (stream-local) whose layer 1 is to be issued
       uint32_t m_it[2] = {0, 0};     // tile of the main chain
       int m_op[2] = {0, 0};          // 0: layer 2, 1: layer 3, 2: Gram
-      bool g_started = false;
+      uint32_t g_acc = 0;            // 1 once the Gram accumulators hold something
       uint32_t idle = 0;
       while (m_it[0] < cnt[0] || m_it[1] < cnt[1]) {
         bool progressed = false;
@@ -208,18 +258,22 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
           const uint32_t sb = s0 + s * kStreamBytes, tb = tmem + s * kStreamCols;
           // ---- layer 1 of tile l1_it: D1 = X W1^T, three split terms x 4 k-steps (SS).  Needs the
           // staged X and region P free (layer 2 of the previous tile, which reads H1 there, retired).
-          if (l1_it[s] < cnt[s] && mbar_test(&b[X_FULL], l1_it[s] & 1) &&
-              (l1_it[s] == 0 || mbar_test(&b[D2_FULL], (l1_it[s] - 1) & 1))) {
+          if (l1_it[s] < cnt[s] && ready(&b[X_FULL], l1_it[s] & 1) &&
+              (l1_it[s] == 0 || ready(&b[D2_FULL], (l1_it[s] - 1) & 1))) {
             tc_fence_after_sync();
-            const uint32_t id = make_idesc_f16(128, 128, 0);
-#pragma unroll 1
-            for (int term = 0; term < 3; ++term) {
-              const uint32_t a = sb + kXOffS + (term == 2 ? 16384 : 0);   // hi, hi, lo
-              const uint32_t bq = s0 + kW1Off + (term == 1 ? 16384 : 0);  // hi, lo, hi
+            if (elect_one()) {
+              const uint32_t id = make_idesc_f16(128, 128, 0);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_ss(tb + cP, desc(a + 32 * k), desc(bq + 32 * k), id, (term | k) ? 1u : 0u);
+              for (int term = 0; term < 3; ++term) {
+                const uint32_t a = sb + kXOffS + (term == 2 ? 16384 : 0);   // hi, hi, lo
+                const uint32_t bq = s0 + kW1Off + (term == 1 ? 16384 : 0);  // hi, lo, hi
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_ss(tb + cP, desc(a + 32 * k), desc(bq + 32 * k), id, (term | k) ? 1u : 0u);
+              }
+              umma_commit(&b[D1_FULL]);
             }
-            umma_commit(&b[D1_FULL]);
+            __syncwarp();
+            if (s == 0 && l1_it[0] < 3) TSTAMP(16 + 8 * l1_it[0] + 0);
             ++l1_it[s];
             progressed = true;
           }
@@ -227,54 +281,66 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
           const uint32_t par = m_it[s] & 1;
           if (m_op[s] == 0) {
             // ---- layer 2: D2 = H1 W2^T, K = 128 (TS; H1 hi / lo words interleaved per 32-column block)
-            if (!mbar_test(&b[A1_FULL], par)) continue;
+            if (!ready(&b[A1_FULL], par)) continue;
             tc_fence_after_sync();
-            const uint32_t id = make_idesc_f16(128, 64, 0);
-#pragma unroll 1
-            for (int term = 0; term < 3; ++term) {
-              const uint32_t bq = s0 + kW2Off + (term == 1 ? 16384 : 0);
+            if (elect_one()) {
+              const uint32_t id = make_idesc_f16(128, 64, 0);
 #pragma unroll
-              for (int k = 0; k < 8; ++k)
-                umma_ts(tb + cQ, tb + cP + 32 * (k >> 1) + 8 * (k & 1) + (term == 2 ? 16 : 0),
-                        desc(bq + (k >> 2) * 8192 + 32 * (k & 3)), id, (term | k) ? 1u : 0u);
+              for (int term = 0; term < 3; ++term) {
+                const uint32_t bq = s0 + kW2Off + (term == 1 ? 16384 : 0);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                  umma_ts(tb + cQ, tb + cP + 32 * (k >> 1) + 8 * (k & 1) + (term == 2 ? 16 : 0),
+                          desc(bq + (k >> 2) * 8192 + 32 * (k & 3)), id, (term | k) ? 1u : 0u);
+              }
+              umma_commit(&b[D2_FULL]);
             }
-            umma_commit(&b[D2_FULL]);
+            __syncwarp();
+            if (s == 0 && m_it[0] < 3) TSTAMP(16 + 8 * m_it[0] + 1);
             m_op[s] = 1;
             progressed = true;
           } else if (m_op[s] == 1) {
             // ---- layer 3: D3 = H2 W3^T, K = 64 (TS)
-            if (!mbar_test(&b[A2_FULL], par)) continue;
+            if (!ready(&b[A2_FULL], par)) continue;
             tc_fence_after_sync();
-            const uint32_t id = make_idesc_f16(128, 32, 0);
-#pragma unroll 1
-            for (int term = 0; term < 3; ++term) {
-              const uint32_t bq = s0 + kW3Off + (term == 1 ? 4096 : 0);
+            if (elect_one()) {
+              const uint32_t id = make_idesc_f16(128, 32, 0);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_ts(tb + cR, tb + cQ + 32 * (k >> 1) + 8 * (k & 1) + (term == 2 ? 16 : 0), desc(bq + 32 * k), id,
-                        (term | k) ? 1u : 0u);
+              for (int term = 0; term < 3; ++term) {
+                const uint32_t bq = s0 + kW3Off + (term == 1 ? 4096 : 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_ts(tb + cR, tb + cQ + 32 * (k >> 1) + 8 * (k & 1) + (term == 2 ? 16 : 0), desc(bq + 32 * k), id,
+                          (term | k) ? 1u : 0u);
+              }
+              umma_commit(&b[D3_FULL]);
             }
-            umma_commit(&b[D3_FULL]);
+            __syncwarp();
+            if (s == 0 && m_it[0] < 3) TSTAMP(16 + 8 * m_it[0] + 2);
             m_op[s] = 2;
             progressed = true;
           } else {
             // ---- Gram: G1 += Yh^T Yh, G2 += Yh^T Yl, K = the tile's 128 pixels (SS; A rows 32..127 don't care)
-            if (!mbar_test(&b[YT_FULL], par)) continue;
+            if (!ready(&b[YT_FULL], par)) continue;
             tc_fence_after_sync();
-            const uint32_t id = make_idesc_f16(128, 32, 0);
-            const uint32_t yh = sb, yl = sb + 2 * kYtSlab;
+            if (elect_one()) {
+              const uint32_t id = make_idesc_f16(128, 32, 0);
+              const uint32_t yh = sb, yl = sb + 2 * kYtSlab;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint32_t o = (k >> 2) * kYtSlab + 32 * (k & 3);
-              umma_ss(tmem + cG1, desc(yh + o), desc(yh + o), id, (g_started || k) ? 1u : 0u);
-            }
+              for (int k = 0; k < 8; ++k) {
+                const uint32_t o = (k >> 2) * kYtSlab + 32 * (k & 3);
+                umma_ss(tmem + cG1, desc(yh + o), desc(yh + o), id, k ? 1u : g_acc);
+              }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint32_t o = (k >> 2) * kYtSlab + 32 * (k & 3);
-              umma_ss(tmem + cG2, desc(yh + o), desc(yl + o), id, (g_started || k) ? 1u : 0u);
+              for (int k = 0; k < 8; ++k) {
+                const uint32_t o = (k >> 2) * kYtSlab + 32 * (k & 3);
+                umma_ss(tmem + cG2, desc(yh + o), desc(yl + o), id, k ? 1u : g_acc);
+              }
+              umma_commit(&b[G_DONE]);
             }
-            umma_commit(&b[G_DONE]);
-            g_started = true;
+            __syncwarp();
+            if (s == 0 && m_it[0] < 3) TSTAMP(16 + 8 * m_it[0] + 3);
+            g_acc = 1;
             m_op[s] = 0;
             ++m_it[s];
             progressed = true;
@@ -288,9 +354,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
         }
       }
     }
-    __syncwarp();
   } else {
-    setmaxnreg_inc<112>();
+    setmaxnreg_inc<104>();
     // ------------------------------------------------------------------ pixel rows
     // stream s = warp / 8; inside it: TMEM lane quarter q (rows 32q..32q+31, one per lane), column half ch
     const int s = warp >> 3, q = warp & 3, ch = (warp >> 2) & 1;
@@ -304,11 +369,14 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
     auto load_x = [&](long long t) {
       const long long p = t * 128 + row;
       const bool valid = t >= 0 && p < J.n;
+      if (valid && J.vec) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ldg_stream_v8(J.g + p * J.pix_stride + 32 * ch + 8 * i, xr[2 * i], xr[2 * i + 1]);
+        return;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (valid && J.vec) {
-          xr[i] = __ldg(reinterpret_cast<const float4*>(J.g + p * J.pix_stride + 32 * ch) + i);
-        } else if (valid) {
+        if (valid) {
           const float* src = J.g + p * J.pix_stride + (long long)(32 * ch + 4 * i) * J.ch_stride;
           xr[i] = make_float4(__ldg(src), __ldg(src + J.ch_stride), __ldg(src + 2 * J.ch_stride),
                               __ldg(src + 3 * J.ch_stride));
@@ -353,8 +421,10 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
       const long long t_next = tile_of(j + 2);
       const bool valid = t * 128 + row < J.n;
       // ---- epilogue 1: H1 = LeakyReLU(D1 + b1), fp16 hi / lo words written over the same 32 columns
+      if (warp == 0 && it < 3) TSTAMP(48 + 8 * it + 0);
       mbar_wait(&b[D1_FULL], par, 64);
       tc_fence_after_sync();
+      if (warp == 0 && it < 3) TSTAMP(48 + 8 * it + 1);
 #pragma unroll
       for (int qq = 0; qq < 2; ++qq) {
         const int blk = 2 * ch + qq;
@@ -371,6 +441,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&b[A1_FULL]);
+      if (warp == 0 && it < 3) TSTAMP(48 + 8 * it + 2);
       // D1(t) is drained and its MMAs have retired (X smem is free): stage the stream's next tile now,
       // then request the one after that
       if (t_next >= 0) {
@@ -378,8 +449,10 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
         load_x(tile_of(j + 4));
       }
       // ---- epilogue 2: H2 = LeakyReLU(D2 + b2), in place
+      if (warp == 0 && it < 3) TSTAMP(48 + 8 * it + 3);
       mbar_wait(&b[D2_FULL], par, 65);
       tc_fence_after_sync();
+      if (warp == 0 && it < 3) TSTAMP(48 + 8 * it + 4);
       {
         uint32_t v[32], w[32];
         tmem_ld_x32(lane_base + cQ + 32 * ch, v);
@@ -394,10 +467,12 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&b[A2_FULL]);
+      if (warp == 0 && it < 3) TSTAMP(48 + 8 * it + 5);
       // ---- epilogue 3: Y = D3 + b3 (no activation, linearStyleTransfer.py:15), zero for pixels
       // beyond n; Y^T hi / lo -> smem with the pixel index along K (this thread: 16 channels)
       mbar_wait(&b[D3_FULL], par, 66);
       tc_fence_after_sync();
+      if (warp == 0 && it < 3) TSTAMP(48 + 8 * it + 6);
       {
         uint32_t v[16];
         tmem_ld_x16(lane_base + cR + 16 * ch, v);
@@ -421,6 +496,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&b[YT_FULL]);
       }
+      if (warp == 0 && it < 3) TSTAMP(48 + 8 * it + 7);
       t = t_next;
     }
     // ---- G = G1 + G2 + G2^T (rows 0..31) -> this block's partial
@@ -429,6 +505,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
       if (c0) mbar_wait(&bars[G_DONE], (c0 - 1) & 1, 68);
       if (c1) mbar_wait(&bars[kBarsPerStream + G_DONE], (c1 - 1) & 1, 68);
       tc_fence_after_sync();
+      TSTAMP(3);
       uint32_t g1[32], g2[32];
       if (c0 + c1) {
         tmem_ld_x32(tmem + cG1, g1);
@@ -449,6 +526,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) TSTAMP(4);
   if (warp == kEpiWarps) tmem_dealloc<512>(tmem);
 }
 
@@ -466,6 +544,11 @@ int gram_tc_launch(GramJob* jobs, int n_jobs, int max_blocks, cudaStream_t st) {
   CRNERF_REQUIRE(n_jobs == 1 || n_jobs == 2, "one or two Gram jobs per launch");
   GramParams P;
   P.n_jobs = n_jobs;
+#ifdef CRNERF_GRAM_TIMING
+  P.ts = reinterpret_cast<long long*>(g_dbg_buf);
+#else
+  P.ts = nullptr;
+#endif
   const int sms = num_sms();
   int want[2] = {0, 0};
   for (int i = 0; i < n_jobs; ++i) {

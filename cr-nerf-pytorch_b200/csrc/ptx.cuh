@@ -114,6 +114,15 @@ __device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_s
       : "memory");
 }
 
+// 32-byte streaming load (sm_100: LDG.256), read-only path, no L1 allocation: a thread takes whole
+// 32-byte sectors, and the stream does not evict what else lives in the (small, when most of the
+// SM's memory is carved out as shared) L1 - local-memory spills in particular
+__device__ __forceinline__ void ldg_stream_v8(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+
 // ----------------------------------------------------------------------------
 // tcgen05: TMEM allocation
 // ----------------------------------------------------------------------------
