@@ -14,10 +14,10 @@
 //   G1 += Yh^T Yh, G2 += Yh^T Yl  (M=128 with only rows 0..31 meaningful, N=32, K=128)  SS
 // G1 / G2 live in TMEM for the CTA's whole lifetime; G = G1 + G2 + G2^T is written once.
 //
-// Two tiles ("streams") are in flight per CTA, each with its own 8 epilogue warps, operand
-// buffers and TMEM regions (2 x 224 columns + 64 for G1/G2 = all 512), so one stream's MMAs run
-// under the other's epilogues; a single issuer thread polls both streams' barriers and issues
-// whichever MMA group is ready.  In-place activations are what makes two streams fit: a 32-column
+// Two tiles ("streams") are in flight per CTA, each with its own operand buffers and TMEM
+// regions (2 x 224 columns + 64 for G1/G2 = all 512), so one stream's MMAs run under the other's
+// epilogues; the 16 epilogue warps work through the two streams' phases alternately, and an
+// issuer warp polls both streams' barriers and issues whichever MMA group is ready.  In-place activations are what makes two streams fit: a 32-column
 // block of fp32 accumulators becomes 16 columns of packed fp16 hi words + 16 of lo words in the
 // same columns (each thread rewrites its own lane).
 //
@@ -40,7 +40,7 @@
 namespace crnerf {
 namespace {
 
-constexpr int kEpiWarps = 16;                       // 2 streams x (lane quarter x column half)
+constexpr int kEpiWarps = 16;                       // lane quarter x column quarter
 // + warp 16: MMA issuer / TMEM allocator; warps 17-19 only donate registers: the register file is
 // allocated in units of 4 warps, so 17 warps cost as much as 20, and setmaxnreg moves what the
 // four control warps do not need (4 x 32 x 32) to the 16 epilogue warps (96 -> 104 each); the issuer
@@ -63,7 +63,7 @@ constexpr int kGramSmem = kBarOff2 + 16 * 8 + 16;
 constexpr uint32_t kStreamCols = 224, cP = 0, cQ = 128, cR = 192, cG1 = 448, cG2 = 480;
 enum { X_FULL = 0, D1_FULL, A1_FULL, D2_FULL, A2_FULL, D3_FULL, YT_FULL, G_DONE, kBarsPerStream };
 
-__device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
+__device__ __forceinline__ float lrelu02(float v) { return fmaxf(v, 0.2f * v); }   // = v > 0 ? v : 0.2 v
 
 // (a, b) -> packed fp16 hi pair and packed fp16 lo pair (a = hi + lo to ~2^-22 relative)
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -82,6 +82,29 @@ __device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok;
+}
+
+// Blocking wait with a suspend-time hint: the hardware parks the warp until the phase completes (or
+// the hint expires) instead of letting it spin - a quarter of this kernel's issued instructions were
+// try_wait spin loops competing with the epilogue arithmetic for the same schedulers.  Bounded like
+// mbar_wait: a protocol bug traps instead of hanging.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t tag) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) return;
+    if (++spins == (1u << 18)) {
+      g_wait_timeout_tag = 0x80000000u | (tag << 16) | (blockIdx.x & 0xffff);
+      __trap();
+    }
+  }
 }
 
 // fp32 row-major weight (rows x cols) -> SW128 K-major fp16 hi/lo slabs of 64 columns.  Each thread
@@ -120,8 +143,21 @@ struct GramParams {
   do {                                                                                 \
     if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && P.ts) P.ts[slot] = clock64();    \
   } while (0)
+// per-warp event trace (warps 0 and 15 of block 0): (tag << 48) | clock, appended at ts[256 + 128*w + i]
+#define TRACE(tag)                                                                                   \
+  do {                                                                                               \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && P.ts && (warp == 0 || warp == 15) && trace_n < 127) \
+      P.ts[256 + 128 * (warp == 15) + trace_n++] = ((long long)(tag) << 48) | (clock64() & 0xffffffffffffLL); \
+  } while (0)
+// all-warp snapshot of one event in round 2: ts[800 + 20*k + warp]
+#define SNAP(k, it)                                                                               \
+  do {                                                                                            \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && P.ts && (it) == 2) P.ts[800 + 20 * (k) + warp] = clock64(); \
+  } while (0)
 #else
 #define TSTAMP(slot) do { } while (0)
+#define TRACE(tag) do { } while (0)
+#define SNAP(k, it) do { } while (0)
 #endif
 
 // channel mean of the job's map -> mean[64] (shared), fixed summation order.  All threads call.
@@ -187,13 +223,13 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       uint64_t* b = bars + s * kBarsPerStream;
-      mbar_init(&b[X_FULL], 8);
+      mbar_init(&b[X_FULL], 16);
       mbar_init(&b[D1_FULL], 1);
-      mbar_init(&b[A1_FULL], 8);
+      mbar_init(&b[A1_FULL], 16);
       mbar_init(&b[D2_FULL], 1);
-      mbar_init(&b[A2_FULL], 8);
+      mbar_init(&b[A2_FULL], 16);
       mbar_init(&b[D3_FULL], 1);
-      mbar_init(&b[YT_FULL], 8);
+      mbar_init(&b[YT_FULL], 16);
       mbar_init(&b[G_DONE], 1);
     }
     fence_mbar_init();
@@ -250,33 +286,22 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
       int m_op[2] = {0, 0};          // 0: layer 2, 1: layer 3, 2: Gram
       uint32_t g_acc = 0;            // 1 once the Gram accumulators hold something
       uint32_t idle = 0;
+      [[maybe_unused]] int itr_n = 0;
+#ifdef CRNERF_GRAM_TIMING
+#define ITRACE(tag)                                                                                  \
+  do {                                                                                               \
+    if (blockIdx.x == 0 && lane == 0 && P.ts && itr_n < 200)                                         \
+      P.ts[600 + itr_n++] = ((long long)(tag) << 48) | (clock64() & 0xffffffffffffLL);              \
+  } while (0)
+#else
+#define ITRACE(tag) do { } while (0)
+#endif
       while (m_it[0] < cnt[0] || m_it[1] < cnt[1]) {
         bool progressed = false;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           uint64_t* b = bars + s * kBarsPerStream;
           const uint32_t sb = s0 + s * kStreamBytes, tb = tmem + s * kStreamCols;
-          // ---- layer 1 of tile l1_it: D1 = X W1^T, three split terms x 4 k-steps (SS).  Needs the
-          // staged X and region P free (layer 2 of the previous tile, which reads H1 there, retired).
-          if (l1_it[s] < cnt[s] && ready(&b[X_FULL], l1_it[s] & 1) &&
-              (l1_it[s] == 0 || ready(&b[D2_FULL], (l1_it[s] - 1) & 1))) {
-            tc_fence_after_sync();
-            if (elect_one()) {
-              const uint32_t id = make_idesc_f16(128, 128, 0);
-#pragma unroll
-              for (int term = 0; term < 3; ++term) {
-                const uint32_t a = sb + kXOffS + (term == 2 ? 16384 : 0);   // hi, hi, lo
-                const uint32_t bq = s0 + kW1Off + (term == 1 ? 16384 : 0);  // hi, lo, hi
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_ss(tb + cP, desc(a + 32 * k), desc(bq + 32 * k), id, (term | k) ? 1u : 0u);
-              }
-              umma_commit(&b[D1_FULL]);
-            }
-            __syncwarp();
-            if (s == 0 && l1_it[0] < 3) TSTAMP(16 + 8 * l1_it[0] + 0);
-            ++l1_it[s];
-            progressed = true;
-          }
           if (m_it[s] >= cnt[s]) continue;
           const uint32_t par = m_it[s] & 1;
           if (m_op[s] == 0) {
@@ -296,11 +321,11 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
               umma_commit(&b[D2_FULL]);
             }
             __syncwarp();
-            if (s == 0 && m_it[0] < 3) TSTAMP(16 + 8 * m_it[0] + 1);
+            ITRACE(40 + 4 * s + 0);
             m_op[s] = 1;
             progressed = true;
           } else if (m_op[s] == 1) {
-            // ---- layer 3: D3 = H2 W3^T, K = 64 (TS)
+            // ---- layer 3: D3 = H2 W3^T, K = 64 (TS; H2 per 16-column group: 8 hi words | 8 lo words)
             if (!ready(&b[A2_FULL], par)) continue;
             tc_fence_after_sync();
             if (elect_one()) {
@@ -310,13 +335,13 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
                 const uint32_t bq = s0 + kW3Off + (term == 1 ? 4096 : 0);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_ts(tb + cR, tb + cQ + 32 * (k >> 1) + 8 * (k & 1) + (term == 2 ? 16 : 0), desc(bq + 32 * k), id,
+                  umma_ts(tb + cR, tb + cQ + 16 * k + (term == 2 ? 8 : 0), desc(bq + 32 * k), id,
                           (term | k) ? 1u : 0u);
               }
               umma_commit(&b[D3_FULL]);
             }
             __syncwarp();
-            if (s == 0 && m_it[0] < 3) TSTAMP(16 + 8 * m_it[0] + 2);
+            ITRACE(40 + 4 * s + 1);
             m_op[s] = 2;
             progressed = true;
           } else {
@@ -339,16 +364,47 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
               umma_commit(&b[G_DONE]);
             }
             __syncwarp();
-            if (s == 0 && m_it[0] < 3) TSTAMP(16 + 8 * m_it[0] + 3);
+            ITRACE(40 + 4 * s + 2);
             g_acc = 1;
             m_op[s] = 0;
             ++m_it[s];
             progressed = true;
           }
         }
+        // Layer 1 of a stream's NEXT tile is a prefetch with a whole tile period of slack: it is
+        // issued only when no main-chain group was ready, so it never sits in the in-order pipe
+        // ahead of a short group the epilogue warps are waiting for.
+        if (!progressed) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            uint64_t* b = bars + s * kBarsPerStream;
+            const uint32_t sb = s0 + s * kStreamBytes, tb = tmem + s * kStreamCols;
+            // ---- layer 1 of tile l1_it: D1 = X W1^T, three split terms x 4 k-steps (SS).  Needs the
+            // staged X and region P free (layer 2 of the previous tile, which reads H1 there, retired).
+            if (l1_it[s] < cnt[s] && ready(&b[X_FULL], l1_it[s] & 1) &&
+                (l1_it[s] == 0 || ready(&b[D2_FULL], (l1_it[s] - 1) & 1))) {
+              tc_fence_after_sync();
+              if (elect_one()) {
+                const uint32_t id = make_idesc_f16(128, 128, 0);
+  #pragma unroll
+                for (int term = 0; term < 3; ++term) {
+                  const uint32_t a = sb + kXOffS + (term == 2 ? 16384 : 0);   // hi, hi, lo
+                  const uint32_t bq = s0 + kW1Off + (term == 1 ? 16384 : 0);  // hi, lo, hi
+  #pragma unroll
+                  for (int k = 0; k < 4; ++k) umma_ss(tb + cP, desc(a + 32 * k), desc(bq + 32 * k), id, (term | k) ? 1u : 0u);
+                }
+                umma_commit(&b[D1_FULL]);
+              }
+              __syncwarp();
+              ITRACE(40 + 4 * s + 3);
+              ++l1_it[s];
+              progressed = true;
+            }
+          }
+        }
         if (progressed) {
           idle = 0;
-        } else if (++idle == (1u << 26)) {   // protocol bug: fail the launch instead of hanging the box
+        } else if (__nanosleep(20), ++idle == (1u << 24)) {   // protocol bug: fail the launch instead of hanging the box
           g_wait_timeout_tag = 0x80000000u | (69u << 16) | (blockIdx.x & 0xffff);
           __trap();
         }
@@ -357,43 +413,46 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
   } else {
     setmaxnreg_inc<104>();
     // ------------------------------------------------------------------ pixel rows
-    // stream s = warp / 8; inside it: TMEM lane quarter q (rows 32q..32q+31, one per lane), column half ch
-    const int s = warp >> 3, q = warp & 3, ch = (warp >> 2) & 1;
+    // All 16 warps work on ONE phase of ONE stream at a time (TMEM lane quarter q = rows 32q..32q+31,
+    // one per lane; column quarter cq) and alternate between the two streams phase by phase:
+    //   ep1(0) ep1(1) ep2(0) ep2(1) ep3(0) ep3(1) | next pair of tiles ...
+    // so every scheduler always has four warps on the same short phase while the other stream's
+    // MMAs run on the tensor pipe (with eight private warps per stream, a stream waiting for its
+    // MMAs idles half the SM and the other half runs at two warps per scheduler).
+    const int q = warp & 3, cq = warp >> 2;
     const int row = 32 * q + lane;
-    uint64_t* b = bars + s * kBarsPerStream;
-    uint8_t* sbase = smem + s * kStreamBytes;
-    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + s * kStreamCols;
-    // this thread's half of a pixel row (32 channels) as 8 float4; the stream's NEXT tile is
-    // requested while the current one is being processed
-    float4 xr[8];
-    auto load_x = [&](long long t) {
+    [[maybe_unused]] int trace_n = 0;
+    // this thread's quarter of a pixel row (16 channels) of each stream's NEXT tile, requested one
+    // tile ahead
+    float4 xr[2][4];
+    auto load_x = [&](int s, long long t) {
       const long long p = t * 128 + row;
       const bool valid = t >= 0 && p < J.n;
       if (valid && J.vec) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ldg_stream_v8(J.g + p * J.pix_stride + 32 * ch + 8 * i, xr[2 * i], xr[2 * i + 1]);
+        ldg_stream_v8(J.g + p * J.pix_stride + 16 * cq, xr[s][0], xr[s][1]);
+        ldg_stream_v8(J.g + p * J.pix_stride + 16 * cq + 8, xr[s][2], xr[s][3]);
         return;
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         if (valid) {
-          const float* src = J.g + p * J.pix_stride + (long long)(32 * ch + 4 * i) * J.ch_stride;
-          xr[i] = make_float4(__ldg(src), __ldg(src + J.ch_stride), __ldg(src + 2 * J.ch_stride),
-                              __ldg(src + 3 * J.ch_stride));
+          const float* src = J.g + p * J.pix_stride + (long long)(16 * cq + 4 * i) * J.ch_stride;
+          xr[s][i] = make_float4(__ldg(src), __ldg(src + J.ch_stride), __ldg(src + 2 * J.ch_stride),
+                                 __ldg(src + 3 * J.ch_stride));
         } else {
-          xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          xr[s][i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     };
-    // X row (held in xr) of tile tt -> smem (hi, lo), then signal the issuer
-    auto stage_x = [&](long long tt) {
+    // X row quarter (held in xr[s]) of tile tt -> smem (hi, lo), then signal the issuer
+    auto stage_x = [&](int s, long long tt) {
       const bool valid = tt * 128 + row < J.n;
-      uint8_t* xh = sbase + kXOffS, *xl = xh + 16384;
+      uint8_t* xh = smem + s * kStreamBytes + kXOffS, *xl = xh + 16384;
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        const float4 q0 = xr[2 * c8], q1 = xr[2 * c8 + 1];
+      for (int c8 = 0; c8 < 2; ++c8) {
+        const float4 q0 = xr[s][2 * c8], q1 = xr[s][2 * c8 + 1];
         const float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-        const int c0 = 32 * ch + 8 * c8;
+        const int c0 = 16 * cq + 8 * c8;
         uint32_t h[4], l[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -401,103 +460,130 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
           const float bb = valid ? v[2 * j + 1] - mean[c0 + 2 * j + 1] : 0.f;
           split2(a, bb, h[j], l[j]);
         }
-        const uint32_t off = sw128_offset(row, 4 * ch + c8);
+        const uint32_t off = sw128_offset(row, 2 * cq + c8);
         *reinterpret_cast<uint4*>(xh + off) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4*>(xl + off) = make_uint4(l[0], l[1], l[2], l[3]);
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&b[X_FULL]);
+      if (lane == 0) mbar_arrive(&bars[s * kBarsPerStream + X_FULL]);
     };
-    long long t = tile_of(s);
-    load_x(t);
-    if (t >= 0) {
-      stage_x(t);
-      load_x(tile_of(s + 2));
-    }
-    uint32_t it = 0;
-    for (long long j = s; t >= 0; j += 2, ++it) {
-      const uint32_t par = it & 1;
-      const long long t_next = tile_of(j + 2);
-      const bool valid = t * 128 + row < J.n;
-      // ---- epilogue 1: H1 = LeakyReLU(D1 + b1), fp16 hi / lo words written over the same 32 columns
-      if (warp == 0 && it < 3) TSTAMP(48 + 8 * it + 0);
-      mbar_wait(&b[D1_FULL], par, 64);
+    // ---- the three epilogues of a tile of stream s (it = the stream's tile counter)
+    // epilogue 1: H1 = LeakyReLU(D1 + b1), fp16 hi / lo words written over the same 32 columns; then
+    // (D1 drained, its MMAs retired: X smem is free) stage the stream's next tile and request the one after
+    auto ep1 = [&](int s, uint32_t it, long long t_next, long long t_after) {
+      uint64_t* b = bars + s * kBarsPerStream;
+      const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + s * kStreamCols;
+      TRACE(10 + s);
+      mbar_wait_parked(&b[D1_FULL], it & 1, 64);
       tc_fence_after_sync();
-      if (warp == 0 && it < 3) TSTAMP(48 + 8 * it + 1);
-#pragma unroll
-      for (int qq = 0; qq < 2; ++qq) {
-        const int blk = 2 * ch + qq;
+      TRACE(12 + s);
+      if (s == 0) SNAP(0, it);
+      {
         uint32_t v[32], w[32];
-        tmem_ld_x32(lane_base + cP + 32 * blk, v);
+        tmem_ld_x32(lane_base + cP + 32 * cq, v);
         tmem_ld_wait();
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj)
-          split2(lrelu02(__uint_as_float(v[2 * jj]) + b1[32 * blk + 2 * jj]),
-                 lrelu02(__uint_as_float(v[2 * jj + 1]) + b1[32 * blk + 2 * jj + 1]), w[jj], w[16 + jj]);
-        tmem_st_x32(lane_base + cP + 32 * blk, w);
+          split2(lrelu02(__uint_as_float(v[2 * jj]) + b1[32 * cq + 2 * jj]),
+                 lrelu02(__uint_as_float(v[2 * jj + 1]) + b1[32 * cq + 2 * jj + 1]), w[jj], w[16 + jj]);
+        tmem_st_x32(lane_base + cP + 32 * cq, w);
       }
       tmem_st_wait();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&b[A1_FULL]);
-      if (warp == 0 && it < 3) TSTAMP(48 + 8 * it + 2);
-      // D1(t) is drained and its MMAs have retired (X smem is free): stage the stream's next tile now,
-      // then request the one after that
+      TRACE(14 + s);
+      if (s == 0) SNAP(1, it);
       if (t_next >= 0) {
-        stage_x(t_next);
-        load_x(tile_of(j + 4));
+        stage_x(s, t_next);
+        load_x(s, t_after);
       }
-      // ---- epilogue 2: H2 = LeakyReLU(D2 + b2), in place
-      if (warp == 0 && it < 3) TSTAMP(48 + 8 * it + 3);
-      mbar_wait(&b[D2_FULL], par, 65);
+      TRACE(16 + s);
+      if (s == 0) SNAP(2, it);
+    };
+    // epilogue 2: H2 = LeakyReLU(D2 + b2), in place: 16 columns -> 8 hi words | 8 lo words
+    auto ep2 = [&](int s, uint32_t it) {
+      uint64_t* b = bars + s * kBarsPerStream;
+      const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + s * kStreamCols;
+      mbar_wait_parked(&b[D2_FULL], it & 1, 65);
       tc_fence_after_sync();
-      if (warp == 0 && it < 3) TSTAMP(48 + 8 * it + 4);
+      TRACE(20 + s);
       {
-        uint32_t v[32], w[32];
-        tmem_ld_x32(lane_base + cQ + 32 * ch, v);
+        uint32_t v[16], w[16];
+        tmem_ld_x16(lane_base + cQ + 16 * cq, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj)
-          split2(lrelu02(__uint_as_float(v[2 * jj]) + b2[32 * ch + 2 * jj]),
-                 lrelu02(__uint_as_float(v[2 * jj + 1]) + b2[32 * ch + 2 * jj + 1]), w[jj], w[16 + jj]);
-        tmem_st_x32(lane_base + cQ + 32 * ch, w);
+        for (int jj = 0; jj < 8; ++jj)
+          split2(lrelu02(__uint_as_float(v[2 * jj]) + b2[16 * cq + 2 * jj]),
+                 lrelu02(__uint_as_float(v[2 * jj + 1]) + b2[16 * cq + 2 * jj + 1]), w[jj], w[8 + jj]);
+        tmem_st_x16p(lane_base + cQ + 16 * cq, w);
       }
       tmem_st_wait();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&b[A2_FULL]);
-      if (warp == 0 && it < 3) TSTAMP(48 + 8 * it + 5);
-      // ---- epilogue 3: Y = D3 + b3 (no activation, linearStyleTransfer.py:15), zero for pixels
-      // beyond n; Y^T hi / lo -> smem with the pixel index along K (this thread: 16 channels)
-      mbar_wait(&b[D3_FULL], par, 66);
+      TRACE(22 + s);
+      if (s == 0) SNAP(3, it);
+    };
+    // epilogue 3: Y = D3 + b3 (no activation, linearStyleTransfer.py:15), zero for pixels beyond n;
+    // Y^T hi / lo -> smem with the pixel index along K (this thread: 8 channels)
+    auto ep3 = [&](int s, uint32_t it, long long tile) {
+      uint64_t* b = bars + s * kBarsPerStream;
+      const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + s * kStreamCols;
+      const bool valid = tile * 128 + row < J.n;
+      mbar_wait_parked(&b[D3_FULL], it & 1, 66);
       tc_fence_after_sync();
-      if (warp == 0 && it < 3) TSTAMP(48 + 8 * it + 6);
-      {
-        uint32_t v[16];
-        tmem_ld_x16(lane_base + cR + 16 * ch, v);
-        tmem_ld_wait();
-        if (it > 0) mbar_wait(&b[G_DONE], (it - 1) & 1, 67);  // the stream's previous Gram MMAs are done reading Y^T
-        uint8_t* yh = sbase + (row >> 6) * kYtSlab;
-        uint8_t* yl = yh + 2 * kYtSlab;
-        const uint32_t kk = row & 63;
+      TRACE(30 + s);
+      uint32_t v[8];
+      tmem_ld_x8(lane_base + cR + 8 * cq, v);
+      tmem_ld_wait();
+      if (it > 0) mbar_wait_parked(&b[G_DONE], (it - 1) & 1, 67);  // the stream's previous Gram MMAs are done reading Y^T
+      uint8_t* yh = smem + s * kStreamBytes + (row >> 6) * kYtSlab;
+      uint8_t* yl = yh + 2 * kYtSlab;
+      const uint32_t kk = row & 63;
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          const int c = 16 * ch + jj;
-          const float y = valid ? __uint_as_float(v[jj]) + b3[c] : 0.f;
-          const __half hi = __float2half_rn(y);
-          const __half lo = __float2half_rn(y - __half2float(hi));
-          const uint32_t off = sw128_offset(c, kk >> 3) + (kk & 7) * 2;
-          *reinterpret_cast<__half*>(yh + off) = hi;
-          *reinterpret_cast<__half*>(yl + off) = lo;
-        }
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&b[YT_FULL]);
+      for (int jj = 0; jj < 8; ++jj) {
+        const int c = 8 * cq + jj;
+        const float y = valid ? __uint_as_float(v[jj]) + b3[c] : 0.f;
+        const __half hi = __float2half_rn(y);
+        const __half lo = __float2half_rn(y - __half2float(hi));
+        const uint32_t off = sw128_offset(c, kk >> 3) + (kk & 7) * 2;
+        *reinterpret_cast<__half*>(yh + off) = hi;
+        *reinterpret_cast<__half*>(yl + off) = lo;
       }
-      if (warp == 0 && it < 3) TSTAMP(48 + 8 * it + 7);
-      t = t_next;
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b[YT_FULL]);
+      TRACE(32 + s);
+    };
+    long long t0 = tile_of(0), t1 = tile_of(1);
+    load_x(0, t0);
+    if (t0 >= 0) {
+      stage_x(0, t0);
+      load_x(0, tile_of(2));
+    }
+    load_x(1, t1);
+    if (t1 >= 0) {
+      stage_x(1, t1);
+      load_x(1, tile_of(3));
+    }
+    // The two streams run half a tile apart, so that each MMA group of one stream executes under an
+    // epilogue of the other:   ep1(0) | ep3(1, previous tile) | ep2(0) | ep1(1) | ep3(0) | ep2(1)
+    long long t1_prev = -1;
+    for (uint32_t r = 0; t0 >= 0 || t1_prev >= 0; ++r) {
+      const long long j = 2 * (long long)r;
+      const long long t0_next = tile_of(j + 2), t1_next = tile_of(j + 3);
+      if (t0 >= 0) ep1(0, r, t0_next, tile_of(j + 4));
+      if (t1_prev >= 0) ep3(1, r - 1, t1_prev);
+      if (t0 >= 0) ep2(0, r);
+      if (t1 >= 0) ep1(1, r, t1_next, tile_of(j + 5));
+      if (t0 >= 0) ep3(0, r, t0);
+      if (t1 >= 0) ep2(1, r);
+      t1_prev = t1;
+      t0 = t0_next;
+      t1 = t1_next;
     }
     // ---- G = G1 + G2 + G2^T (rows 0..31) -> this block's partial
     if (warp == 0) {

@@ -18,7 +18,7 @@ feat = torch.rand(n, 64, device=dev) * 0.2 + 0.4
 content = feat.t().reshape(1, 64, n // 100 if n % 100 == 0 else 1, 100 if n % 100 == 0 else n)
 style = torch.rand(1, 64, 32, 32, device=dev)
 parts = torch.stack([c.sum(0) for c in feat.chunk(min(148, n))])
-ts = torch.zeros(256, dtype=torch.int64, device=dev)
+ts = torch.zeros(1024, dtype=torch.int64, device=dev)
 with torch.no_grad():
     for _ in range(3):
         dec(content, style, channel_sums=parts)
@@ -29,9 +29,23 @@ with torch.no_grad():
     ops.debug_set(None, -1)
 t = ts.cpu().tolist()
 t0 = t[0]
-rel = lambda i: (t[i] - t0) if t[i] else None
-print("prologue: weights staged", rel(1), "| setup done", rel(2), "| G read", rel(3), "| end", rel(4))
-for tile in range(3):
-    print(f"tile {tile} (stream 0): issuer L1 {rel(16+8*tile)} L2 {rel(17+8*tile)} L3 {rel(18+8*tile)} G {rel(19+8*tile)}")
-    e = [rel(48 + 8 * tile + k) for k in range(8)]
-    print(f"   epilogue warp 0: wait D1 {e[0]} -> got {e[1]} | ep1 done {e[2]} | staged next, wait D2 {e[3]} -> got {e[4]} | ep2 done {e[5]} | got D3 {e[6]} | ep3 done {e[7]}")
+print("prologue: weights staged", t[1] - t0, "| setup done", t[2] - t0, "| G read", t[3] - t0, "| end", t[4] - t0)
+NAMES = {10: "wait D1(0)", 11: "wait D1(1)", 12: "got D1(0)", 13: "got D1(1)", 14: "ep1(0) done", 15: "ep1(1) done",
+         16: "staged(0)", 17: "staged(1)", 20: "got D2(0)", 21: "got D2(1)", 22: "ep2(0) done", 23: "ep2(1) done",
+         30: "got D3(0)", 31: "got D3(1)", 32: "ep3(0) done", 33: "ep3(1) done",
+         40: "issue L2(0)", 41: "issue L3(0)", 42: "issue G(0)", 43: "issue L1(0)",
+         44: "issue L2(1)", 45: "issue L3(1)", 46: "issue G(1)", 47: "issue L1(1)"}
+ev = []
+for who, base, cnt in (("w0 ", 256, 128), ("w15", 384, 128), ("iss", 600, 200)):
+    for v in t[base:base + cnt]:
+        if v:
+            ev.append(((v & 0xffffffffffff) - (t0 & 0xffffffffffff), who, NAMES.get(v >> 48, str(v >> 48))))
+ev.sort()
+limit = int(os.environ.get("TRACE_UNTIL", "60000"))
+for c, who, name in ev:
+    if c < limit:
+        print(f"{c:8d}  {who}  {name}")
+
+for k, name in enumerate(["got D1(0)", "ep1(0) done", "staged(0)", "ep2(0) done"]):
+    vals = [(v & 0xffffffffffff) - (t0 & 0xffffffffffff) for v in t[800 + 20 * k: 800 + 20 * k + 16]]
+    print(f"round 2, all warps, {name:12s}:", " ".join(str(v) for v in vals))
