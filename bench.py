@@ -383,6 +383,18 @@ def run_ours(args):
     gather_bufs = [torch.empty(world * N_RAYS, 64, device=dev) for _ in range(2)] if world > 1 else None
     gather_src = [torch.empty(N_RAYS, 64, device=dev) for _ in range(2)] if world > 1 else None
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    # The per-step patch gather runs on a side stream UNDER the next step's render, whose kernels are
+    # persistent (one CTA per SM): every SM the collective's kernel occupies is an SM whose render CTA
+    # starts late.  1 MB per rank is latency-bound on NVLink anyway, so its communicator gets one CTA.
+    gather_pg = None
+    if world > 1:
+        try:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = 1
+            opts.config.min_ctas = 1
+            gather_pg = dist.new_group(pg_options=opts)
+        except Exception:   # noqa: BLE001  (older torch: no per-communicator config)
+            gather_pg = None
     main_stream = torch.cuda.current_stream(dev)
 
     # the public eval API for a fixed batch shape: render_rays_cross_ray captured in a CUDA graph
@@ -408,7 +420,7 @@ def run_ours(args):
         mark.record(main_stream)                 # inside the timed window of the step that hosts it
         comm.wait_event(mark)
         with torch.cuda.stream(comm):
-            dist.all_gather_into_tensor(gather_bufs[s_prev], gather_src[s_prev])
+            dist.all_gather_into_tensor(gather_bufs[s_prev], gather_src[s_prev], group=gather_pg)
             done = torch.cuda.Event()
             done.record(comm)
         pending[0] = done
@@ -612,7 +624,7 @@ def run_ours(args):
             "config": shared_config(),
             "detail": {"rays_per_gpu_per_step": N_RAYS,
                        "parallelism": f"rays sharded x{world}" + (
-                           ", all_gather(feature_fine) of step i on a side stream under step i+1's render; "
+                           ", all_gather(feature_fine) of step i on a side stream (1-CTA communicator) under step i+1's render; "
                            "the last gather is timed on its own" if world > 1 else ""),
                        "api": ("crnerf_b200.graphs.GraphedRenderer (render_rays_cross_ray captured in a CUDA graph)"
                                if graphed is not None else "models.rendering.render_rays_cross_ray"),
