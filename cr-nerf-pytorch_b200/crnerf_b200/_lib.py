@@ -121,6 +121,16 @@ SIGNATURES = {
                                             C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                             C.c_void_p, C.c_int,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crnerf_style_aux_floats": (C.c_size_t, []),
+    "crnerf_style_backward_grads_floats": (C.c_size_t, []),
+    "crnerf_style_backward_scratch_floats": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "crnerf_style_backward_layout": (None, [C.POINTER(C.c_int64)]),
+    "crnerf_style_forward_train": (C.c_int, [C.POINTER(StyleWeights), C.c_void_p, C.c_int64, C.c_int64,
+                                             C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                             C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crnerf_style_backward": (C.c_int, [C.POINTER(StyleWeights), C.c_void_p, C.c_int64, C.c_int64,
+                                        C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64] +
+                              [C.c_void_p] * 7),
     "crnerf_sum_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "crnerf_cnn_forward": (C.c_int, [C.POINTER(CnnWeights), C.c_void_p, C.c_int64, C.c_int64,
                                      C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

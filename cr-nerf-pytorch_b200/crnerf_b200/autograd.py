@@ -51,3 +51,32 @@ def render_pass(model, rays, z_vals, noise, view_dir, n_fx, n_fd):
     lin = model._linears()
     params = [m.weight for m in lin] + [m.bias for m in lin]
     return RenderPassFn.apply(model.packed(), rays, z_vals, noise, view_dir, n_fx, n_fd, *params)
+
+
+class StyleNetFn(torch.autograd.Function):
+    """``rgb = style_net(content, style)`` under autograd (the training step's decode(),
+    train_mask_grid_sample.py:127-149): forward = the inference kernels of the cross-ray block
+    (tensor-core Gram statistics at fp32-class accuracy) plus a small ``aux`` record, backward =
+    csrc/style_backward.cu - fp32, deterministic, no library GEMM.  ``params`` are the 22 style_net
+    tensors in ``ops.STYLE_GRAD_KEYS`` order."""
+
+    @staticmethod
+    def forward(ctx, sw, content, style, channel_sums, *params):
+        rgb, aux = ops.style_forward_train(sw, content, style, channel_sums)
+        ctx.sw = sw
+        ctx.save_for_backward(content, style, aux)
+        ctx.needs = (content.requires_grad, style.requires_grad)
+        return rgb
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_rgb):
+        content, style, aux = ctx.saved_tensors
+        g_c, g_s, grads = ops.style_backward(ctx.sw, content, style, aux, g_rgb)
+        return (None, g_c if ctx.needs[0] else None, g_s if ctx.needs[1] else None, None,
+                *[grads[k] for k in ops.STYLE_GRAD_KEYS])
+
+
+def style_net_forward(module, sw, content, style, channel_sums=None):
+    named = dict(module.named_parameters())
+    return StyleNetFn.apply(sw, content, style, channel_sums, *[named[k] for k in ops.STYLE_GRAD_KEYS])

@@ -452,6 +452,76 @@ def style_forward(sw: StyleWeightsRef, content: torch.Tensor, style: Optional[to
     return out[0] if len(out) == 1 else tuple(out)
 
 
+# keys of the 22 style_net parameters in the order of crnerf_style_backward_layout's offsets
+STYLE_GRAD_KEYS = tuple(
+    [f"multi_net.{net}.{k}" for net in ("cnet", "snet")
+     for k in ("convs.0.weight", "convs.2.weight", "convs.4.weight", "convs.0.bias", "convs.2.bias",
+               "convs.4.bias", "fc.weight", "fc.bias")] +
+    ["multi_net.compress.weight", "multi_net.compress.bias", "multi_net.unzip.weight",
+     "multi_net.unzip.bias", "decoder.feat_2_rgb_list.0.weight", "decoder.feat_2_rgb_list.0.bias"])
+
+
+def style_forward_train(sw: StyleWeightsRef, content: torch.Tensor, style: torch.Tensor,
+                        channel_sums: Optional[torch.Tensor] = None):
+    """Training forward of style_net: (rgb (1,3,H,W), aux) - aux is what ``style_backward`` keeps
+    from the forward (means, Gram vectors, FC outputs, transmatrix)."""
+    lib = _lib.load()
+    content, n, cps, ccs = _feat_strides(content, "content")
+    style, ns, sps, scs = _feat_strides(style, "style")
+    h, w = content.shape[2], content.shape[3]
+    dev = content.device
+    if dev != sw.device or style.device != dev:
+        raise ValueError("content, style and style_net parameters must be on one device")
+    if not (sw.has_decoder and sw.has_fusion):
+        raise ValueError("style weights are missing the parameters this call needs")
+    with torch.cuda.device(dev):
+        rgb = torch.empty((1, 3, h, w), dtype=torch.float32, device=dev)
+        aux = torch.empty(lib.crnerf_style_aux_floats(), dtype=torch.float32, device=dev)
+        scratch = torch.empty(lib.crnerf_style_scratch_floats(n), dtype=torch.float32, device=dev)
+        n_parts = 0
+        if channel_sums is not None:
+            channel_sums = _c(_need(channel_sums, "channel_sums", 2))
+            n_parts = int(channel_sums.shape[0])
+        check(lib.crnerf_style_forward_train(C.byref(sw.struct), content.data_ptr(), n, cps, ccs, style.data_ptr(), ns,
+                                             sps, scs, channel_sums.data_ptr() if n_parts else None, n_parts,
+                                             rgb.data_ptr(), aux.data_ptr(), scratch.data_ptr(), _stream(dev)))
+    return rgb, aux
+
+
+_style_grad_layout = None
+
+
+def style_backward(sw: StyleWeightsRef, content: torch.Tensor, style: torch.Tensor, aux: torch.Tensor,
+                   g_rgb: torch.Tensor):
+    """Backward of style_net.forward: returns (g_content (1,64,H,W), g_style (1,64,h,w), {key: grad})
+    with the 22 parameter gradients as views of one flat buffer."""
+    global _style_grad_layout
+    lib = _lib.load()
+    content, n, cps, ccs = _feat_strides(content, "content")
+    style, ns, sps, scs = _feat_strides(style, "style")
+    dev = content.device
+    g_rgb = _c(_need(g_rgb, "g_rgb")).reshape(3, n)
+    if _style_grad_layout is None:
+        offs = (C.c_int64 * 22)()
+        lib.crnerf_style_backward_layout(offs)
+        _style_grad_layout = list(offs)
+    with torch.cuda.device(dev):
+        flat = torch.empty(lib.crnerf_style_backward_grads_floats(), dtype=torch.float32, device=dev)
+        g_c = torch.empty((n, 64), dtype=torch.float32, device=dev)
+        g_s = torch.empty((ns, 64), dtype=torch.float32, device=dev)
+        scratch = torch.empty(lib.crnerf_style_backward_scratch_floats(n, ns), dtype=torch.float32, device=dev)
+        check(lib.crnerf_style_backward(C.byref(sw.struct), content.data_ptr(), n, cps, ccs, style.data_ptr(), ns, sps,
+                                        scs, aux.data_ptr(), g_rgb.data_ptr(), g_c.data_ptr(), g_s.data_ptr(),
+                                        flat.data_ptr(), scratch.data_ptr(), _stream(dev)))
+    grads = {}
+    for key, off in zip(STYLE_GRAD_KEYS, _style_grad_layout):
+        t = sw.tensors[key]
+        grads[key] = flat[off:off + t.numel()].view(t.shape)
+    _, _, h, w = content.shape
+    _, _, sh, sw_ = style.shape
+    return g_c.t().reshape(1, 64, h, w), g_s.t().reshape(1, 64, sh, sw_), grads
+
+
 def cnn_forward(sw: StyleWeightsRef, which: str, x: torch.Tensor) -> torch.Tensor:
     """CNN.forward (linearStyleTransfer.py:28-37): (1,64,H,W) -> (1,1024)."""
     lib = _lib.load()

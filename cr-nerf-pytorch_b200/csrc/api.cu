@@ -80,6 +80,16 @@ int style_forward(const crnerf_style_weights* w, const float* content, int64_t n
                   const float* content_sum_parts, int n_parts, float* rgb,
                   float* transmatrix, float* fused, float* scratch, cudaStream_t st);
 int sum_rows(const float* parts, int n_parts, int len, float* out, cudaStream_t st);
+size_t style_aux_floats();
+size_t style_backward_grads_floats();
+size_t style_backward_scratch_floats(int64_t n, int64_t m);
+void style_backward_layout(int64_t* out22);
+int style_forward_train(const crnerf_style_weights* w, const float* content, int64_t n, int64_t ps, int64_t cs,
+                        const float* style, int64_t ns, int64_t sps, int64_t scs, const float* content_sum_parts,
+                        int n_parts, float* rgb, float* aux, float* scratch, cudaStream_t st);
+int style_backward(const crnerf_style_weights* w, const float* content, int64_t n, int64_t ps, int64_t cs,
+                   const float* style, int64_t m, int64_t sps, int64_t scs, const float* aux, const float* g_rgb,
+                   float* g_content, float* g_style, float* grads, float* scratch, cudaStream_t st);
 int cnn_forward(const crnerf_cnn_weights* cw, const float* x, int64_t n, int64_t ps, int64_t cs,
                 float* out, float* scratch, cudaStream_t st);
 int grid_patch(const float* lin_w, const float* lin_h, int g, float img_w, float img_h, float scale, float h_off,
@@ -444,6 +454,34 @@ int crnerf_style_forward_sums(const crnerf_style_weights* w, const float* conten
   return style_forward(w, content, n_pixels, c_pix_stride, c_ch_stride, style, n_style_pixels,
                        s_pix_stride, s_ch_stride, content_sum_partials, n_partials, rgb, transmatrix, fused,
                        scratch, (cudaStream_t)stream);
+}
+
+size_t crnerf_style_aux_floats(void) { return style_aux_floats(); }
+size_t crnerf_style_backward_grads_floats(void) { return style_backward_grads_floats(); }
+size_t crnerf_style_backward_scratch_floats(int64_t n_pixels, int64_t n_style_pixels) {
+  return style_backward_scratch_floats(n_pixels, n_style_pixels);
+}
+void crnerf_style_backward_layout(int64_t* offsets22) { style_backward_layout(offsets22); }
+
+int crnerf_style_forward_train(const crnerf_style_weights* w, const float* content, int64_t n_pixels,
+                               int64_t c_pix_stride, int64_t c_ch_stride, const float* style,
+                               int64_t n_style_pixels, int64_t s_pix_stride, int64_t s_ch_stride,
+                               const float* content_sum_partials, int n_partials, float* rgb, float* aux,
+                               float* scratch, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return style_forward_train(w, content, n_pixels, c_pix_stride, c_ch_stride, style, n_style_pixels, s_pix_stride,
+                             s_ch_stride, content_sum_partials, n_partials, rgb, aux, scratch, (cudaStream_t)stream);
+}
+
+int crnerf_style_backward(const crnerf_style_weights* w, const float* content, int64_t n_pixels,
+                          int64_t c_pix_stride, int64_t c_ch_stride, const float* style, int64_t n_style_pixels,
+                          int64_t s_pix_stride, int64_t s_ch_stride, const float* aux, const float* g_rgb,
+                          float* g_content, float* g_style, float* grads, float* scratch, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return style_backward(w, content, n_pixels, c_pix_stride, c_ch_stride, style, n_style_pixels, s_pix_stride,
+                        s_ch_stride, aux, g_rgb, g_content, g_style, grads, scratch, (cudaStream_t)stream);
 }
 
 int crnerf_sum_rows(const float* parts, int n_parts, int len, float* out, void* stream) {

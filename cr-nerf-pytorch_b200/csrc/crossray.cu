@@ -696,4 +696,21 @@ int style_forward(const crnerf_style_weights* w, const float* content, int64_t n
   return fc_and_apply(w, content, n, ps, cs, mean_c, gram_c, mean_s, gram_s, rgb, transmatrix, fused, scratch, st);
 }
 
+// Training forward of the block: style_forward + what the hand-written backward (style_backward.cu)
+// needs from it, copied out of the scratch buffer: aux = [mean_c 64 | mean_s 64 | gram_c 1024 | gram_s 1024 |
+// cmat 1024 | smat 1024] (one contiguous run of the scratch layout) | T = S C (1024).
+size_t style_aux_floats();
+int style_forward_train(const crnerf_style_weights* w, const float* content, int64_t n, int64_t ps, int64_t cs,
+                        const float* style, int64_t ns, int64_t sps, int64_t scs, const float* content_sum_parts,
+                        int n_parts, float* rgb, float* aux, float* scratch, cudaStream_t st) {
+  CRNERF_REQUIRE(aux != nullptr && style != nullptr, "the training forward needs a style map and an aux buffer");
+  static_assert(kOffMeanS == kOffMeanC + 64 && kOffGramC == kOffMeanS + 64 && kOffGramS == kOffGramC + 1024 &&
+                kOffCmat == kOffGramS + 1024 && kOffSmat == kOffCmat + 1024, "aux is one contiguous run of the scratch");
+  int rc = style_forward(w, content, n, ps, cs, style, ns, sps, scs, content_sum_parts, n_parts, rgb, aux + 4224,
+                         nullptr, scratch, st);
+  if (rc) return rc;
+  CRNERF_CUDA(cudaMemcpyAsync(aux, scratch + kOffMeanC, 4224 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return CRNERF_OK;
+}
+
 }  // namespace crnerf

@@ -23,17 +23,22 @@ from models.nerf_decoder_stylenerf import NeuralRenderer
 import torch.nn.functional as F
 
 
+# "native": style_net under autograd runs the library's own forward / backward kernels;
+# "torch": the differentiable tensor-op restatement below (kept for MulLayer / CNN used on their own
+# and as the yardstick of tests/test_gpu_style_backward.py)
+TRAIN_BACKEND = "native"
+
+
 def _wants_grad(module, *tensors):
     """True when the call must be recorded for autograd (the training step's decode())."""
     return torch.is_grad_enabled() and (any(t is not None and t.requires_grad for t in tensors) or
                                         any(p.requires_grad for p in module.parameters()))
 
 
-# Training-mode path of the cross-ray block.  The reference trains on 32x32 patches
-# (train_mask_grid_sample.py:127-149: 1,024 pixels), where this block is a few dozen
-# launch-bound library calls whichever way it is written; it therefore runs as plain
-# differentiable tensor ops (cuBLAS / cuDNN through autograd), while inference - whole
-# frames, where the block is HBM-bound - runs the streaming kernels of csrc/crossray.cu.
+# Tensor-op restatement of the cross-ray block under autograd.  ``style_net.forward`` itself - the
+# decode() of the training step (train_mask_grid_sample.py:127-149, 32x32 patches) - uses the
+# library's own kernels in both directions (crnerf_b200.autograd.StyleNetFn); these functions serve
+# ``MulLayer`` / ``CNN`` called on their own under autograd, and the tests.
 def _cnn_torch(cnn, x):
     """CNN.forward (reference linearStyleTransfer.py:28-37) as differentiable tensor ops."""
     y = cnn.convs(x)
@@ -145,6 +150,11 @@ class style_net(nn.Module, _StyleParamsMixin):
         if _wants_grad(self, content_feature, style_feature):
             if style_feature is None and type == "content":
                 return self.decoder(content_feature)
+            if content_feature.is_cuda and TRAIN_BACKEND == "native":
+                # decode() of the training step: the inference kernels forward, csrc/style_backward.cu backward
+                from crnerf_b200 import autograd as crnerf_autograd
+                return crnerf_autograd.style_net_forward(self, self._style_ref([("", "")]), content_feature,
+                                                         style_feature, channel_sums)
             fused, _ = _mul_layer_torch(self.multi_net, content_feature, style_feature)
             return self.decoder(fused)
         # torch.ops.crnerf.style_forward (crnerf_b200/torch_ops.py) -> crnerf_style_forward

@@ -352,6 +352,31 @@ int crnerf_style_forward_sums(const crnerf_style_weights* w, const float* conten
  * 64 channel sums of a rank's rays, the input of the sharded form's first all-reduce). */
 int crnerf_sum_rows(const float* parts, int n_parts, int len, float* out, void* stream);
 
+/* ---- the same block under autograd: the decode() of the training step
+ * (train_mask_grid_sample.py:127-149) ----------------------------------------------------------
+ * crnerf_style_forward_train = crnerf_style_forward_sums plus `aux`
+ * (crnerf_style_aux_floats() floats: channel means, normalised Gram vectors, the two FC outputs and
+ * transmatrix - everything the backward keeps from the forward; per-pixel activations are recomputed).
+ * crnerf_style_backward: g_rgb (3, n_pixels) planar -> g_content (n_pixels, 64) rows, g_style
+ * (n_style_pixels, 64) rows and the 22 parameter gradients in ONE flat buffer `grads`
+ * (crnerf_style_backward_grads_floats() floats; crnerf_style_backward_layout fills the 22 offsets in
+ * crnerf_style_weights order: cnet {conv_w[0..2], conv_b[0..2], fc_w, fc_b}, snet {same},
+ * compress_w, compress_b, unzip_w, unzip_b, rgb_w, rgb_b).  fp32, deterministic (per-block partials
+ * summed in block order).  scratch: crnerf_style_backward_scratch_floats(n_pixels, n_style_pixels). */
+size_t crnerf_style_aux_floats(void);
+size_t crnerf_style_backward_grads_floats(void);
+size_t crnerf_style_backward_scratch_floats(int64_t n_pixels, int64_t n_style_pixels);
+void crnerf_style_backward_layout(int64_t* offsets22);
+int crnerf_style_forward_train(const crnerf_style_weights* w, const float* content, int64_t n_pixels,
+                               int64_t c_pix_stride, int64_t c_ch_stride, const float* style,
+                               int64_t n_style_pixels, int64_t s_pix_stride, int64_t s_ch_stride,
+                               const float* content_sum_partials, int n_partials, float* rgb, float* aux,
+                               float* scratch, void* stream);
+int crnerf_style_backward(const crnerf_style_weights* w, const float* content, int64_t n_pixels,
+                          int64_t c_pix_stride, int64_t c_ch_stride, const float* style, int64_t n_style_pixels,
+                          int64_t s_pix_stride, int64_t s_ch_stride, const float* aux, const float* g_rgb,
+                          float* g_content, float* g_style, float* grads, float* scratch, void* stream);
+
 /* CNN.forward alone (models/linearStyleTransfer.py:28-37): x (n_pixels x 64) ->
  * out (1024) = fc(flatten(convs(x) convs(x)^T / n_pixels)).  Same scratch buffer. */
 int crnerf_cnn_forward(const crnerf_cnn_weights* w, const float* x, int64_t n_pixels,
