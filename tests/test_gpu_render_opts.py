@@ -131,3 +131,26 @@ def test_channel_partials_sum_to_feature_sums(n_rays, ns, ni):
         want = res[f"feature_{typ}"].double().sum(0)
         got = part.double().sum(0)
         assert torch.allclose(got, want, rtol=1e-5, atol=1e-5), float((got - want).abs().max())
+
+
+@pytest.mark.parametrize("hw", [(16, 16), (40, 52)])
+def test_style_net_with_render_channel_sums_equals_plain_call(hw):
+    """render_rays_cross_ray(..., channel_sums=True) -> style_net.forward(..., channel_sums=...): the
+    cross-ray block takes the channel means from the render epilogue's partial sums instead of a
+    pass over the feature map; the rgb must agree with the plain call to fp32 rounding
+    of the mean (different, fixed, summation orders)."""
+    from models.nerf import PosEmbedding
+    from models.rendering import render_rays_cross_ray
+    h, w = hw
+    models, args = build_mirror_models(0)
+    models = {k: m.cuda() for k, m in models.items()}
+    emb = {"xyz": PosEmbedding(14, 15), "dir": PosEmbedding(3, 4)}
+    rays = oracle.pinhole_rays(h, w, oracle.synthetic_pose(1)).cuda()
+    style = torch.rand(1, 64, 32, 32, generator=torch.Generator().manual_seed(2)).cuda()
+    with torch.no_grad():
+        res = render_rays_cross_ray(models, emb, rays, None, 32, False, 0, 0, 32, 32768, False, test_time=True,
+                                    args=args, channel_sums=True)
+        content = res["feature_fine"].t().reshape(1, 64, h, w)
+        a = models["decoder"](content, style, channel_sums=res["chansum_fine"])
+        b = models["decoder"](content, style)
+    assert float((a - b).abs().max()) <= 2e-6
