@@ -80,3 +80,30 @@ class StyleNetFn(torch.autograd.Function):
 def style_net_forward(module, sw, content, style, channel_sums=None):
     named = dict(module.named_parameters())
     return StyleNetFn.apply(sw, content, style, channel_sums, *[named[k] for k in ops.STYLE_GRAD_KEYS])
+
+
+class Fp32Region(torch.autograd.Function):
+    """``fn(x)`` as ONE node of the outer graph, for the modules that stay on library convolutions
+    under autograd (``Context_Guided_Network``, ``encoder_sameoutputsize``).  The inner graph is
+    recorded in ``forward`` and differentiated in ``backward``, both under
+    ``cudnn.flags(allow_tf32=False)`` - a plain ``with`` block around the forward would leave the
+    backward convolutions, which run later on the autograd thread, on TF32 (1e-3 off the reference's
+    fp32 results), and a global switch would change the caller's process.  ``params`` are passed as
+    inputs only so that their gradients are routed; ``fn`` reads them from the module."""
+
+    @staticmethod
+    def forward(ctx, fn, x, *params):
+        with torch.enable_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            leaf = x.detach().requires_grad_(x.requires_grad)
+            out = fn(leaf)
+        ctx.leaf, ctx.out, ctx.params = leaf, out, params
+        return out.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        wanted = [t for t in (ctx.leaf,) + tuple(ctx.params) if t.requires_grad]
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            grads = iter(torch.autograd.grad(ctx.out, wanted, g, allow_unused=True))
+        res = [next(grads) if t.requires_grad else None for t in (ctx.leaf,) + tuple(ctx.params)]
+        ctx.leaf = ctx.out = ctx.params = None
+        return (None, *res)

@@ -27,6 +27,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from crnerf_b200.autograd import Fp32Region as _Fp32Region
+
 __all__ = ["Context_Guided_Network"]
 
 _BN_EPS = 1e-3
@@ -36,31 +38,6 @@ def _conv(n_in, n_out, k, stride=1, dilation=1, groups=1):
     pad = ((k - 1) // 2) * dilation
     return nn.Conv2d(n_in, n_out, (k, k), stride=stride, padding=(pad, pad), dilation=dilation, groups=groups,
                      bias=False)
-
-
-class _Fp32Region(torch.autograd.Function):
-    """``fn(x)`` as ONE node of the outer graph.  The inner graph (library convolutions) is recorded
-    in ``forward`` and differentiated in ``backward``, both under ``cudnn.flags(allow_tf32=False)`` -
-    a plain ``with`` block around the forward would leave the backward convolutions, which run later
-    on the autograd thread, on TF32.  ``params`` are passed as inputs only so that their gradients
-    are routed; ``fn`` reads them from the module."""
-
-    @staticmethod
-    def forward(ctx, fn, x, *params):
-        with torch.enable_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            leaf = x.detach().requires_grad_(x.requires_grad)
-            out = fn(leaf)
-        ctx.leaf, ctx.out, ctx.params = leaf, out, params
-        return out.detach()
-
-    @staticmethod
-    def backward(ctx, g):
-        wanted = [t for t in (ctx.leaf,) + tuple(ctx.params) if t.requires_grad]
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            grads = iter(torch.autograd.grad(ctx.out, wanted, g, allow_unused=True))
-        res = [next(grads) if t.requires_grad else None for t in (ctx.leaf,) + tuple(ctx.params)]
-        ctx.leaf = ctx.out = ctx.params = None
-        return (None, *res)
 
 
 class _Wrapped(nn.Module):

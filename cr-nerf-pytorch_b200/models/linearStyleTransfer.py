@@ -221,6 +221,13 @@ class encoder_sameoutputsize(nn.Module):
         if x.is_cuda and self.conv7.out_channels == 64 and not _wants_grad(self, x) and x.shape[0] == 1 \
                 and min(x.shape[2:]) >= 8:
             return ops.encoder_forward(self.packed(), x)
+        if x.is_cuda and torch.is_grad_enabled():
+            # training step: library convolutions, fp32 in forward and backward (scoped, not global)
+            from crnerf_b200.autograd import Fp32Region
+            return Fp32Region.apply(self._stack, x, *self.parameters())
+        return self._stack(x)
+
+    def _stack(self, x):
         h = self.relu2(self.conv2(self.reflecPad1(self.conv1(x))))
         h = self.relu3(self.conv3(self.reflecPad3(h)))
         h, _ = self.maxPool(h)

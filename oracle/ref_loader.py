@@ -30,7 +30,9 @@ FILES = ("models/rendering.py", "models/nerf.py", "models/linearStyleTransfer.py
          # (tests/test_dropin.py: the callers' import lines and their batched_inference / decode
          # functions are executed, unmodified, against the mirror)
          "models/esrgan.py", "models/lightweight_seg.py", "models/networks.py", "models/conv_decoder.py",
-         "eval.py", "train_mask_grid_sample.py", "appearance_modification_video.py")
+         "eval.py", "train_mask_grid_sample.py", "appearance_modification_video.py",
+         # the training Dataset (its __getitem__ is cut out and executed by tests/test_training_step_replay.py)
+         "datasets/phototourism_mask_grid_sample.py")
 
 
 def find_reference() -> Optional[str]:

@@ -24,22 +24,29 @@ def test_state_dict_and_seeded_init_equal_the_reference():
     check_checksums(net, g["checksum"])                        # same values: default init + kaiming pass + ruffle
 
 
+def _same(a, b):
+    """Bit-identical on the machine that made the goldens (oracle/make_golden.py asserts torch.equal
+    there); oneDNN partitions convolutions by thread count, so another host may differ in the last
+    bits - a few ulp are allowed, nothing more."""
+    return torch.equal(a, b) or torch.allclose(a, b, rtol=2e-6, atol=2e-7)
+
+
 def test_oracle_and_mirror_forward_match_reference_on_cpu():
     g = load_golden("cgnet")
     net, _ = build_mirror_cgnet(g)
     state = {k: v.clone() for k, v in net.state_dict().items()}
     for c in g["cases"]:
         with torch.no_grad():
-            assert torch.equal(oracle.cgnet_forward(state, c["x"], 2, 2, train=False), c["eval"])
-            assert torch.equal(oracle.cgnet_forward(state, c["x"], 2, 2, train=True), c["train"])
-            assert torch.equal(net.eval()(c["x"]), c["eval"])
+            assert _same(oracle.cgnet_forward(state, c["x"], 2, 2, train=False), c["eval"])
+            assert _same(oracle.cgnet_forward(state, c["x"], 2, 2, train=True), c["train"])
+            assert _same(net.eval()(c["x"]), c["eval"])
         net.load_state_dict(state)
         net.train()
         y = net(c["x"])
-        assert torch.equal(y.detach(), c["train"])
+        assert _same(y.detach(), c["train"])
         for k, v in net.named_buffers():                       # BatchNorm running statistics advance as there
             if "running" in k:
-                assert torch.equal(v, c["running_after"][k]), k
+                assert _same(v, c["running_after"][k]), k
         net.load_state_dict(state)
 
 

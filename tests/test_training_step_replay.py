@@ -1,0 +1,66 @@
+"""The whole training step of the reference's NeRFSystem, UNMODIFIED, on the mirror.
+
+``Dataset.__getitem__`` (datasets/phototourism_mask_grid_sample.py:240-275), ``NeRFSystem.forward``
+(train_mask_grid_sample.py:150-226), ``decode`` (:127-149) and ``training_step`` (:268-337) are cut out
+of the reference's sources and executed as they stand twice: in a subprocess on the CPU with the
+reference's own ``models`` / ``losses`` / dataset code (the yardstick), and here on the GPU with this
+repo's mirror (fused render kernels under autograd, cross-ray block forward + backward kernels, loss
+kernels, mask lookup, the CGNet and encoder mirrors, the GPU grid-patch sampler).  Same seeds, same
+synthetic scene: the batch must be identical, every loss term and the gradients must agree."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import ref_loader
+from conftest import PKG
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_training_step_runs_unmodified_and_matches_the_reference(tmp_path):
+    base = ref_loader.find_reference()
+    if base is None:
+        pytest.skip("reference files neither staged (run __graft_entry__.build()) nor checked out")
+    ref = ref_loader.extract(str(tmp_path / "ref"), base)
+    if not os.path.isfile(os.path.join(ref, "datasets", "phototourism_mask_grid_sample.py")):
+        pytest.skip("staged archive predates the dataset file; re-run build()")
+    out = str(tmp_path / "ref_step.pt")
+    env = dict(os.environ, PYTHONPATH=ref, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "_training_step_driver.py"), ref, out], env=env,
+                       capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-3000:]
+    want = torch.load(out, weights_only=False)
+
+    sys.path.insert(0, HERE)
+    import _training_step_driver as drv
+    import models
+    assert os.path.realpath(models.__file__).startswith(os.path.realpath(PKG))      # the mirror, not the reference
+    from crnerf_b200 import ops
+    n0 = ops.launch_count()
+    got = drv.run("mirror", ref, "cuda")
+    assert ops.launch_count() - n0 > 50, "the native kernels did not run"
+
+    # the grid-sampled batch: bit-identical (host draws replayed, index arithmetic + gathers on the GPU)
+    for k, v in want["batch"].items():
+        assert torch.equal(got["batch"][k], v), k
+    assert got["embedding_a_slot"] == want["embedding_a_slot"]
+    # every logged scalar of training_step: lr, loss, annealing weight, each loss term, psnr
+    assert set(got["logged"]) == set(want["logged"])
+    for k, v in want["logged"].items():
+        assert got["logged"][k] == pytest.approx(v, rel=2e-3, abs=1e-7), (k, got["logged"][k], v)
+    assert got["loss"] == pytest.approx(want["loss"], rel=1e-3)
+    # gradients: relative L2 per tensor.  The NeRF MLPs run with fp16 tensor-core operands (ReLU units
+    # within rounding of zero flip their mask: a few % at the bottom layers, tests/test_gpu_backward.py);
+    # decoder, encoder and mask network are fp32 paths
+    tol = {"fine.": 5e-2, "coarse.": 8e-2, "decoder.": 5e-3, "enc_a.": 5e-3, "implicit_mask.": 5e-3}
+    errs = {}
+    for k, g_ref in want["grads"].items():
+        g = got["grads"][k]
+        errs[k] = float((g.double() - g_ref.double()).norm() / (g_ref.double().norm() + 1e-30))
+    print("relative L2 of gradients vs the reference's own CPU run:", {k: f"{v:.1e}" for k, v in errs.items()})
+    for k, e in errs.items():
+        assert e <= next(t for pre, t in tol.items() if k.startswith(pre)), (k, e)
