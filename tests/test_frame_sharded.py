@@ -26,8 +26,8 @@ class OracleStyleBackend:
     def __init__(self, p):
         self.p = p
 
-    def sums(self, feat):                        # (n,64) -> (64,)
-        return feat.sum(0)
+    def sums(self, feat, parts=None):            # (n,64) -> (64,); parts: partial sums whose rows add up to it
+        return feat.sum(0) if parts is None else parts.sum(0)
 
     def _convs(self, prefix, x):                 # x (1,64,n,1)
         h = x
@@ -65,7 +65,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, n_total, out_dir):
+def _worker(rank, world, port, n_total, out_dir, with_parts=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -77,7 +77,10 @@ def _worker(rank, world, port, n_total, out_dir):
         feat = torch.rand(n_total, 64, generator=g)
         style = torch.rand(1, 64, 32, 32, generator=g)
         lo, hi = shard_bounds(n_total, world, rank)
-        rgb = fuse_decode_sharded(OracleStyleBackend(p), feat[lo:hi].contiguous(), style, n_total)
+        local = feat[lo:hi].contiguous()
+        # the render epilogue's per-CTA partial channel sums, emulated: rows that add up to the block's sums
+        parts = torch.stack([c.sum(0) for c in local.chunk(7)]) if with_parts and hi > lo else None
+        rgb = fuse_decode_sharded(OracleStyleBackend(p), local, style, n_total, sum_parts=parts)
         torch.save(rgb, os.path.join(out_dir, f"rgb_{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -96,10 +99,10 @@ def test_shard_bounds_cover_in_order():
         shard_bounds(10, 2, 2)
 
 
-@pytest.mark.parametrize("n_total", [32 * 24, 1001])      # even split, ragged split
-def test_fuse_decode_sharded_world2_gloo_matches_unsharded(tmp_path, n_total):
+@pytest.mark.parametrize("n_total,with_parts", [(32 * 24, False), (1001, False), (1001, True)])   # even / ragged split; sums from partials
+def test_fuse_decode_sharded_world2_gloo_matches_unsharded(tmp_path, n_total, with_parts):
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), n_total, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n_total, str(tmp_path), with_parts), nprocs=world, join=True)
     models, _ = build_mirror_models(0)
     p = state(models["decoder"])
     g = torch.Generator().manual_seed(5)
