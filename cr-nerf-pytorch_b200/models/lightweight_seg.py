@@ -151,6 +151,7 @@ class Context_Guided_Network(nn.Module):
         head = _Wrapped(_conv(256, classes, 1))
         self.classifier = nn.Sequential(nn.Dropout2d(0.1, False), head) if dropout_flag else nn.Sequential(head)
         self.sigmoid = nn.Sigmoid()
+        self.conv_precision = "fp32"               # or "tf32": cuDNN's default path (see encoder_sameoutputsize)
         for m in self.modules():                   # :307-317 (same visiting order -> same RNG consumption)
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight)
@@ -171,7 +172,7 @@ class Context_Guided_Network(nn.Module):
 
     def logits(self, x):
         """Everything up to the 1x1 classifier: (B, classes, H/8, W/8), fp32 convolutions."""
-        if not x.is_cuda:
+        if not x.is_cuda or self.conv_precision != "fp32":
             return self._stack(x)
         if not torch.is_grad_enabled():
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):

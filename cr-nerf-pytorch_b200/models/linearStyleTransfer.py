@@ -204,6 +204,10 @@ class encoder_sameoutputsize(nn.Module):
         self.relu7 = nn.LeakyReLU(0.2, inplace=True)
         self._packed = None
         self._packed_key = None
+        # precision of the library convolutions under autograd: "fp32" (the reference's CPU / fp32
+        # results to 1e-4; default) or "tf32" (cuDNN's default path, what the reference itself gets on
+        # a GPU: ~3e-3 relative, about 3x faster at photo sizes - tools/bench_train_full.py)
+        self.conv_precision = "fp32"
 
     def _convs(self):
         return [self.conv1, self.conv2, self.conv3, self.conv4, self.conv5, self.conv6, self.conv7]
@@ -221,7 +225,7 @@ class encoder_sameoutputsize(nn.Module):
         if x.is_cuda and self.conv7.out_channels == 64 and not _wants_grad(self, x) and x.shape[0] == 1 \
                 and min(x.shape[2:]) >= 8:
             return ops.encoder_forward(self.packed(), x)
-        if x.is_cuda and torch.is_grad_enabled():
+        if x.is_cuda and torch.is_grad_enabled() and self.conv_precision == "fp32":
             # training step: library convolutions, fp32 in forward and backward (scoped, not global)
             from crnerf_b200.autograd import Fp32Region
             return Fp32Region.apply(self._stack, x, *self.parameters())

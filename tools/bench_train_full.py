@@ -18,6 +18,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--photo", type=int, nargs=2, default=[340, 512])
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--profile", action="store_true", help="print the top CUDA kernels of one step (torch profiler)")
+    ap.add_argument("--conv", default="fp32", choices=["fp32", "tf32"], help="precision of the library convolutions")
     a = ap.parse_args()
     import _training_step_driver as drv
     from models.nerf import NeRF_sigma, PosEmbedding
@@ -38,6 +40,7 @@ def main():
                       encode_random=True)
     mask_net = Context_Guided_Network(classes=1, M=2, N=2, input_channel=3)
     mods = [enc_a, coarse, decoder, fine, mask_net]
+    enc_a.conv_precision = mask_net.conv_precision = a.conv
     for m in mods:
         m.to(dev).train()
     models = {"coarse": coarse, "decoder": decoder, "fine": fine}
@@ -111,9 +114,16 @@ def main():
     ms = e0.elapsed_time(e1) / a.steps
     for i in range(a.steps):
         step(i, True)
+    if a.profile:
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+            step(0, False)
+            torch.cuda.synchronize()
+        rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:22]
+        for e in rows:
+            print(f"{e.device_time_total / 1e3:8.3f} ms  x{e.count:<4d} {e.key[:110]}", file=sys.stderr)
     print(json.dumps({"workload": f"whole training step, photo {H}x{W}, 1024-ray patch x (64+64), perturb=noise=1, "
                                   "enc_a + mask network + render + decode x3 + CRNeRFLoss + Adam",
-                      "ms_per_step": ms, "phases_ms": {k: v / a.steps for k, v in acc.items()}}))
+                      "library_conv_precision": a.conv, "ms_per_step": ms, "phases_ms": {k: v / a.steps for k, v in acc.items()}}))
 
 
 if __name__ == "__main__":
