@@ -383,14 +383,16 @@ def run_ours(args):
     gather_bufs = [torch.empty(world * N_RAYS, 64, device=dev) for _ in range(2)] if world > 1 else None
     gather_src = [torch.empty(N_RAYS, 64, device=dev) for _ in range(2)] if world > 1 else None
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
-    # The per-step patch gather runs on a side stream UNDER the next step's render, whose kernels are
-    # persistent (one CTA per SM): every SM the collective's kernel occupies is an SM whose render CTA
-    # starts late.  1 MB per rank is latency-bound on NVLink anyway, so its communicator gets one CTA.
+    # The per-step patch gather runs on a side stream UNDER the next step's render.  Limiting its
+    # communicator's CTAs (so that fewer SMs are taken from the persistent render kernel) was measured
+    # at 8 GPUs and LOSES: 5.93 G ray-samples/s with NCCL's default against 5.22 / 4.86 / 5.29 G with
+    # max_ctas = 2 / 4 / 8 (the gather then outlasts the step).  CRNERF_GATHER_CTAS keeps the experiment.
     gather_pg = None
-    if world > 1:
+    gather_ctas = int(os.environ.get("CRNERF_GATHER_CTAS", "0"))      # 0 = NCCL's default channel count
+    if world > 1 and gather_ctas > 0:
         try:
             opts = dist.ProcessGroupNCCL.Options()
-            opts.config.max_ctas = 1
+            opts.config.max_ctas = gather_ctas
             opts.config.min_ctas = 1
             gather_pg = dist.new_group(pg_options=opts)
         except Exception:   # noqa: BLE001  (older torch: no per-communicator config)
@@ -624,7 +626,7 @@ def run_ours(args):
             "config": shared_config(),
             "detail": {"rays_per_gpu_per_step": N_RAYS,
                        "parallelism": f"rays sharded x{world}" + (
-                           ", all_gather(feature_fine) of step i on a side stream (1-CTA communicator) under step i+1's render; "
+                           ", all_gather(feature_fine) of step i on a side stream under step i+1's render; "
                            "the last gather is timed on its own" if world > 1 else ""),
                        "api": ("crnerf_b200.graphs.GraphedRenderer (render_rays_cross_ray captured in a CUDA graph)"
                                if graphed is not None else "models.rendering.render_rays_cross_ray"),
