@@ -100,10 +100,10 @@ def make_args():
     return types.SimpleNamespace(nerf_out_dim=64, pertubeCord=False, img_wh=[320, 256])
 
 
-def build_models():
+def build_models(seed=0):
     from models.nerf import NeRF_sigma
     from models.linearStyleTransfer import style_net
-    torch.manual_seed(0)
+    torch.manual_seed(seed)
     args = make_args()
     coarse = NeRF_sigma('coarse', args, in_channels_xyz=93, in_channels_dir=27)
     decoder = style_net(args)
@@ -172,6 +172,40 @@ def psnr_delta(oracle, models_gpu, state_cpu, emb, margs, dev):
     return {"psnr_ours_vs_ref_db": oracle.psnr(rgb, rgb_ref), "psnr_ours_vs_T_db": p_ours,
             "psnr_ref_vs_T_db": p_ref, "psnr_delta_db": abs(p_ours - p_ref),
             "frame": "64x64, 64+128 samples, style_net decode, right half scored"}
+
+
+def psnr_trained(emb, margs, dev):
+    """The same metric on the TRAINED-like weight set (tests/golden/trained.pt: weights, rays and the
+    decoded frames rgb_a / rgb_t produced by the UNMODIFIED reference on CPU, oracle/make_trained.py) -
+    the regime the metric is meant for: both PSNRs against T land in 15-30 dB.  Nothing of oracle/
+    runs here; the reference side is the stored frame."""
+    from models.rendering import render_rays_cross_ray
+    path = os.path.join(ROOT, "tests", "golden", "trained.pt")
+    if not os.path.isfile(path):
+        return None
+    t = torch.load(path, map_location="cpu", weights_only=False)
+    models, _ = build_models(t["seed"])
+    models["coarse"].load_state_dict(t["coarse"], strict=True)
+    models["fine"].load_state_dict(t["fine"], strict=True)
+    models["decoder"].load_state_dict(t["decoder"], strict=False)     # its two seeded-default fc layers are not stored
+    models = {k: m.to(dev).eval() for k, m in models.items()}
+    f = t["cases"]["frame"]
+    h, w = f["hw"]
+    half = lambda x: x[..., w // 2:]
+    psnr = lambda a, b: float(-10.0 * torch.log10(torch.mean((a.double() - b.double()) ** 2)))
+    out = {"frame": f"{h}x{w}, 64+128 samples, trained-like weights, style_net decode, right half scored; "
+                    "reference side = frames stored by the unmodified reference (CPU fp32)",
+           "psnr_ref_vs_T_db": psnr(half(f["rgb_a"]), half(f["rgb_t"]))}
+    for operand in ("fp16", "fp16x3"):
+        models["coarse"].operand = models["fine"].operand = operand
+        with torch.no_grad():
+            res = render_rays_cross_ray(models, emb, f["rays"].to(dev), None, 64, False, 0, 0, 128, 32768, False,
+                                        test_time=True, args=margs)
+            rgb = models["decoder"](res["feature_fine"].t().reshape(1, 64, h, w), f["style_a"].to(dev)).cpu()
+        p = psnr(half(rgb), half(f["rgb_t"]))
+        out[operand] = {"psnr_ours_vs_T_db": p, "psnr_delta_db": abs(p - out["psnr_ref_vs_T_db"]),
+                        "psnr_ours_vs_ref_db": psnr(rgb, f["rgb_a"])}
+    return out
 
 
 class ClockSampler:
@@ -609,6 +643,12 @@ def run_ours(args):
     psnr = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         psnr = psnr_delta(load_oracle(), models_gpu, state_cpu, emb, margs, dev)
+    psnr_tr = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            psnr_tr = psnr_trained(emb, margs, dev)
+        except Exception as e:   # noqa: BLE001  (an extra record must not take the headline down)
+            psnr_tr = {"error": f"{type(e).__name__}: {e}"}
 
     extra = {}
     if not args.no_frame:
@@ -638,7 +678,7 @@ def run_ours(args):
                     "timing": "wall clock, pinned host rays -> H2D -> render -> D2H feature+depth, "
                               "stream sync every step"},
             "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu_base, "psnr": psnr, "clocks": clocks,
+            "roofline": roof, "cpu_baseline": cpu_base, "psnr": psnr, "psnr_trained": psnr_tr, "clocks": clocks,
             "sustained": sustained,
             "points_per_step": POINTS_PER_STEP,
             "tflops_per_step_device": POINTS_PER_STEP * FLOP_PER_POINT / (dev_ms / args.steps * 1e-3) / 1e12,
