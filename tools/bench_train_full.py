@@ -18,6 +18,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--photo", type=int, nargs=2, default=[340, 512])
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--graph", action="store_true", help="also time the step captured as ONE CUDA graph (GraphedTrainStep)")
     ap.add_argument("--profile", action="store_true", help="print the top CUDA kernels of one step (torch profiler)")
     ap.add_argument("--conv", default="fp32", choices=["fp32", "tf32"], help="precision of the library convolutions")
     a = ap.parse_args()
@@ -114,6 +115,44 @@ def main():
     ms = e0.elapsed_time(e1) / a.steps
     for i in range(a.steps):
         step(i, True)
+    graph_ms = None
+    if a.graph:
+        # everything after the (host-driven) patch sampler as one CUDA graph: the sampled batch is copied into
+        # static tensors, the graph holds enc_a, mask network, render, decode x3, loss, backward and Adam
+        from crnerf_b200.graphs import GraphedTrainStep
+        opt_g = torch.optim.Adam(params, lr=5e-4, capturable=True)
+        s0 = sampler.sample(0, 0)
+        static = {k: s0[k].clone() for k in ("rays", "ts", "rgbs", "rgb_idx")}
+        static["whole"] = ((s0["whole_img"].unsqueeze(0) + 1) / 2).clone()
+
+        def step_fn():
+            a_emb = enc_a(static["whole"])
+            pred_mask = mask_net.mask_rows(static["whole"], (H, W), static["rgb_idx"])
+            res = render_rays_cross_ray(models, emb, static["rays"], static["ts"], 64, False, 1.0, 1.0, 64, 32768, False,
+                                        args=hp)
+            out = dict(res)
+            for typ, key in (("coarse", "feature_coarse"), ("fine", "feature_fine"), ("fine_random", "feature_fine")):
+                img = decoder(rearrange(res[key], '(h w) c -> 1 c h w', h=32, w=32), a_emb)
+                out[f"rgb_{typ}"] = rearrange(img, '1 c h w -> (h w) c')
+                if typ == "fine_random":
+                    out["a_embedded_random_rec"] = enc_a(img)
+            out["out_mask"], out["a_embedded"], out["a_embedded_random"] = pred_mask, a_emb, a_emb
+            ld, _ = crit(out, static["rgbs"], hp, 10)
+            return sum(ld.values())
+
+        gs = GraphedTrainStep(step_fn, opt_g, warmup=3)
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for i in range(a.steps):
+            s = sampler.sample(0, i)
+            for k in ("rays", "ts", "rgbs", "rgb_idx"):
+                static[k].copy_(s[k])
+            static["whole"].copy_((s["whole_img"].unsqueeze(0) + 1) / 2)
+            gs()
+        e1.record()
+        torch.cuda.synchronize()
+        graph_ms = e0.elapsed_time(e1) / a.steps
     if a.profile:
         with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
             step(0, False)
@@ -123,7 +162,7 @@ def main():
             print(f"{e.device_time_total / 1e3:8.3f} ms  x{e.count:<4d} {e.key[:110]}", file=sys.stderr)
     print(json.dumps({"workload": f"whole training step, photo {H}x{W}, 1024-ray patch x (64+64), perturb=noise=1, "
                                   "enc_a + mask network + render + decode x3 + CRNeRFLoss + Adam",
-                      "library_conv_precision": a.conv, "ms_per_step": ms, "phases_ms": {k: v / a.steps for k, v in acc.items()}}))
+                      "library_conv_precision": a.conv, "ms_per_step": ms, "ms_per_step_graphed": graph_ms, "phases_ms": {k: v / a.steps for k, v in acc.items()}}))
 
 
 if __name__ == "__main__":
