@@ -56,7 +56,7 @@ def test_training_step_runs_unmodified_and_matches_the_reference(tmp_path):
     # gradients: relative L2 per tensor.  The NeRF MLPs run with fp16 tensor-core operands (ReLU units
     # within rounding of zero flip their mask: a few % at the bottom layers, tests/test_gpu_backward.py);
     # decoder, encoder and mask network are fp32 paths
-    tol = {"fine.": 5e-2, "coarse.": 8e-2, "decoder.": 5e-3, "enc_a.": 5e-3, "implicit_mask.": 5e-3}
+    tol = {"fine.": 5e-2, "coarse.": 8e-2, "decoder.": 3e-3, "enc_a.": 1e-4, "implicit_mask.": 1e-3}   # measured: 1.3e-2, 4.1e-2, 3.1e-4, 5e-7, 8e-6
     errs = {}
     for k, g_ref in want["grads"].items():
         g = got["grads"][k]
