@@ -4,8 +4,9 @@ Hot-path classes (reference file:line): ``CNN`` (:6-37), ``MulLayer`` (:43-94) a
 ``style_net`` (:278-291) hold the same parameters under the same names
 (``multi_net.{snet,cnet}.convs.{0,2,4}``, ``.fc``, ``multi_net.compress``,
 ``multi_net.unzip``, ``decoder.feat_2_rgb_list.0``) and run the cross-ray fusion +
-decoder as three streaming passes over the feature map (csrc/crossray.cu)
-instead of ~40 library launches.  The feature map is read in place whether it is
+decoder as four launches with two streaming passes over the feature map (csrc/crossray.cu,
+csrc/gram_tc.cu) instead of ~40 library launches; under autograd ``style_net.forward`` uses the
+same kernels forward and csrc/style_backward.cu backward (crnerf_b200.autograd.StyleNetFn).  The feature map is read in place whether it is
 contiguous NCHW or the transposed view of the renderer's (N,64) rows that the
 reference's callers build.
 
