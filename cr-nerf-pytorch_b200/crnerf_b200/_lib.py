@@ -67,6 +67,10 @@ SIGNATURES = {
     "crnerf_render_pass_train": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crnerf_render_pass_train_opts": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RenderOpts),
+                                                C.c_void_p]),
     "crnerf_render_backward_weights_bytes": (C.c_size_t, [C.c_int]),
     "crnerf_render_backward_scratch_bytes": (C.c_size_t, [C.c_int64]),
     "crnerf_render_backward": (C.c_int, [C.POINTER(MlpWeights), C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_int] +

@@ -27,8 +27,8 @@ class RenderPassFn(torch.autograd.Function):
     """(weights, feature, depth) = render_pass(rays, z, noise; 12 weights, 12 biases)."""
 
     @staticmethod
-    def forward(ctx, packed, rays, z_vals, noise, view_dir, n_fx, n_fd, *params):
-        w, f, d, acts, raw = ops.render_pass_train(packed, rays, z_vals, noise, view_dir, n_fx, n_fd)
+    def forward(ctx, packed, rays, z_vals, noise, view_dir, n_fx, n_fd, jitter, *params):
+        w, f, d, acts, raw = ops.render_pass_train(packed, rays, z_vals, noise, view_dir, n_fx, n_fd, jitter)
         ctx.save_for_backward(z_vals, noise, acts, raw, *params)
         ctx.operand, ctx.e_xyz, ctx.e_dir = packed.operand, packed.e_xyz, packed.e_dir
         ctx.set_materialize_grads(False)   # outputs the loss does not use arrive as None, not as zeros
@@ -39,18 +39,19 @@ class RenderPassFn(torch.autograd.Function):
     def backward(ctx, g_w, g_f, g_d):
         z, noise, acts, raw, *params = ctx.saved_tensors
         if g_w is None and g_f is None and g_d is None:
-            return (None,) * (7 + len(params))
+            return (None,) * (8 + len(params))
         W, B = params[:12], params[12:]
         gW, gB = ops.render_backward(W, B, ctx.operand, ctx.e_xyz, ctx.e_dir, acts, raw, z, noise, g_f, g_w, g_d)
         grads = [g.to(w.dtype) for g, w in zip(gW, W)] + [g.to(b.dtype) for g, b in zip(gB, B)]
-        return (None, None, None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, None, None, *grads)
 
 
-def render_pass(model, rays, z_vals, noise, view_dir, n_fx, n_fd):
-    """Differentiable fused pass for a ``models.nerf.NeRF_sigma``."""
+def render_pass(model, rays, z_vals, noise, view_dir, n_fx, n_fd, jitter=None):
+    """Differentiable fused pass for a ``models.nerf.NeRF_sigma``.  ``jitter`` (n_points, 3): the
+    ``args.pertubeCord`` displacement of the sample positions (no gradient, as in the reference)."""
     lin = model._linears()
     params = [m.weight for m in lin] + [m.bias for m in lin]
-    return RenderPassFn.apply(model.packed(), rays, z_vals, noise, view_dir, n_fx, n_fd, *params)
+    return RenderPassFn.apply(model.packed(), rays, z_vals, noise, view_dir, n_fx, n_fd, jitter, *params)
 
 
 class StyleNetFn(torch.autograd.Function):

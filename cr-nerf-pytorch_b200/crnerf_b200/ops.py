@@ -626,7 +626,7 @@ def style_apply(sw: StyleWeightsRef, content_rows: torch.Tensor, mean: torch.Ten
 # Training step: forward that stores the backward's inputs, composite backward
 def render_pass_train(packed: PackedMLP, rays: torch.Tensor, z_vals: torch.Tensor,
                       noise: Optional[torch.Tensor] = None, view_dir: Optional[torch.Tensor] = None,
-                      n_freq_xyz: int = 15, n_freq_dir: int = 4):
+                      n_freq_xyz: int = 15, n_freq_dir: int = 4, xyz_jitter: Optional[torch.Tensor] = None):
     """render_pass + saved activations.  Returns (weights, feature, depth, acts, raw):
     acts is the byte buffer of crnerf_render_pass_train (tiled 16-bit layout, see ``untile_acts``), raw is
     (n_points, 65) fp32 [sigmoid features | softplus sigma]."""
@@ -653,11 +653,17 @@ def render_pass_train(packed: PackedMLP, rays: torch.Tensor, z_vals: torch.Tenso
         raw = torch.empty((n * s, 65), dtype=torch.float32, device=dev)
         if n == 0:
             return weights, feature, depth, acts, raw
-        check(lib.crnerf_render_pass_train(packed.buf.data_ptr(), packed.operand, rays.data_ptr(),
-                                           _p(view_dir), z_vals.data_ptr(), _p(noise), n, s,
-                                           n_freq_xyz, n_freq_dir, weights.data_ptr(),
-                                           feature.data_ptr(), depth.data_ptr(), acts.data_ptr(),
-                                           raw.data_ptr(), _stream(dev)))
+        opts = None
+        if xyz_jitter is not None:
+            xyz_jitter = _c(_need(xyz_jitter, "xyz_jitter", 2))
+            if xyz_jitter.shape != (n * s, 3):
+                raise ValueError(f"xyz_jitter must be ({n * s}, 3)")
+            opts = C.byref(_lib.RenderOpts(_p(xyz_jitter), None, None))
+        check(lib.crnerf_render_pass_train_opts(packed.buf.data_ptr(), packed.operand, rays.data_ptr(),
+                                                _p(view_dir), z_vals.data_ptr(), _p(noise), n, s,
+                                                n_freq_xyz, n_freq_dir, weights.data_ptr(),
+                                                feature.data_ptr(), depth.data_ptr(), acts.data_ptr(),
+                                                raw.data_ptr(), opts, _stream(dev)))
     return weights, feature, depth, acts, raw
 
 

@@ -219,6 +219,20 @@ int crnerf_render_pass_train(const void* packed, int operand, const float* rays,
   return render_acts_zero_tail(acts, (int64_t)n_rays * n_samples, (cudaStream_t)stream);
 }
 
+int crnerf_render_pass_train_opts(const void* packed, int operand, const float* rays, const float* view_dir,
+                                  const float* z_vals, const float* noise, int n_rays, int n_samples,
+                                  int n_freq_xyz, int n_freq_dir, float* weights, float* feature,
+                                  float* depth, void* acts, float* raw, const crnerf_render_opts* opts,
+                                  void* stream) {
+  CRNERF_REQUIRE(acts && raw, "acts and raw are required (use crnerf_render_pass for inference)");
+  CRNERF_REQUIRE((reinterpret_cast<uintptr_t>(acts) & 15) == 0, "acts must be 16-byte aligned");
+  CRNERF_REQUIRE(operand == 0 || operand == 1, "the training forward takes operand 0 (fp16) or 1 (bf16)");
+  int rc = render_pass_impl(packed, operand, rays, view_dir, z_vals, noise, n_rays, n_samples, n_freq_xyz,
+                            n_freq_dir, weights, feature, depth, acts, raw, opts, stream);
+  if (rc) return rc;
+  return render_acts_zero_tail(acts, (int64_t)n_rays * n_samples, (cudaStream_t)stream);
+}
+
 int crnerf_composite_backward(const float* raw, const float* z_vals, const float* noise,
                               const float* g_feature, const float* g_weights, const float* g_depth,
                               int n_rays, int n_samples, float* d_rgb_pre, float* d_sigma_pre,

@@ -59,7 +59,7 @@ def render_rays_cross_ray(models,
     the models' parameters (crnerf_b200/autograd.py) when called with gradients enabled.  ``ts``, ``chunk``,
     ``white_back`` and ``test_time`` are accepted and unused, as in the reference
     (point chunking is unnecessary because no per-point tensor is
-    materialised).  ``args.pertubeCord`` (:102-104) is honoured in inference.  One extension:
+    materialised).  ``args.pertubeCord`` (:102-104) is honoured in inference and training.  One extension:
     ``channel_sums=True`` adds ``chansum_{typ}``, partial column sums of ``feature_{typ}`` that
     the cross-ray block uses instead of a pass over the feature map.  Returns ``weights_{typ} (N,S)``, ``feature_{typ} (N,64)``,
     ``depth_{typ} (N,)`` for the coarse model and, if ``N_importance > 0``, the
@@ -96,11 +96,8 @@ def render_rays_cross_ray(models,
         noise = noise if noise_std != 0 else None
         typ = model.typ
         if model.wants_grad():
-            if pertube:
-                raise NotImplementedError("args.pertubeCord under autograd: the training forward has no "
-                                          "jitter input (the flag is off in every reference command)")
             # training step: same fused kernel, plus saved activations for the backward
-            w, f, d = crnerf_autograd.render_pass(model, rays, z, noise, view_dir, n_fx, n_fd)
+            w, f, d = crnerf_autograd.render_pass(model, rays, z, noise, view_dir, n_fx, n_fd, jitter)
         else:
             pk = model.packed()
             pk.check_overflow()      # fp16 saturation reported by earlier passes (host read, no sync)

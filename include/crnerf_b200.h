@@ -167,6 +167,14 @@ int crnerf_render_pass_train(const void* packed, int operand, const float* rays,
                              const float* z_vals, const float* noise, int n_rays, int n_samples,
                              int n_freq_xyz, int n_freq_dir, float* weights, float* feature,
                              float* depth, void* acts, float* raw, void* stream);
+/* crnerf_render_pass_train with the options of crnerf_render_pass_opts (args.pertubeCord jitter of the
+ * sample positions, models/rendering.py:102-104, in the training step; the saved embedding tile is the
+ * jittered one, so the backward needs nothing else). */
+int crnerf_render_pass_train_opts(const void* packed, int operand, const float* rays, const float* view_dir,
+                                  const float* z_vals, const float* noise, int n_rays, int n_samples,
+                                  int n_freq_xyz, int n_freq_dir, float* weights, float* feature,
+                                  float* depth, void* acts, float* raw, const crnerf_render_opts* opts,
+                                  void* stream);
 int crnerf_composite_backward(const float* raw, const float* z_vals, const float* noise,
                               const float* g_feature, const float* g_weights, const float* g_depth,
                               int n_rays, int n_samples, float* d_rgb_pre, float* d_sigma_pre,

@@ -154,3 +154,33 @@ def test_style_net_with_render_channel_sums_equals_plain_call(hw):
         a = models["decoder"](content, style, channel_sums=res["chansum_fine"])
         b = models["decoder"](content, style)
     assert float((a - b).abs().max()) <= 2e-6
+
+
+def test_pertube_cord_in_the_training_step():
+    """args.pertubeCord under autograd (models/rendering.py:102-104 in the training step): the training
+    forward takes the same jitter as the inference kernel (same RNG draws in the same order), saves the
+    jittered embedding for the weight gradients of layers 1 / 5, and the backward runs."""
+    from models.nerf import PosEmbedding
+    from models.rendering import render_rays_cross_ray
+    models, args = build_mirror_models(0)
+    args.pertubeCord = True
+    models = {k: m.cuda() for k, m in models.items()}
+    emb = {"xyz": PosEmbedding(14, 15), "dir": PosEmbedding(3, 4)}
+    rays = oracle.pinhole_rays(8, 8, oracle.synthetic_pose(1)).cuda()
+    torch.manual_seed(7)
+    with torch.no_grad():
+        want = render_rays_cross_ray(models, emb, rays, None, 16, False, 1.0, 1.0, 16, 32768, False, args=args)
+    for m in models.values():
+        m.train()
+    torch.manual_seed(7)
+    got = render_rays_cross_ray(models, emb, rays, None, 16, False, 1.0, 1.0, 16, 32768, False, args=args)
+    assert got["feature_fine"].grad_fn is not None
+    for k in ("feature_coarse", "feature_fine", "weights_fine", "depth_fine"):
+        assert torch.allclose(got[k].detach(), want[k], rtol=1e-5, atol=1e-6), k
+    (got["feature_fine"].sum() + got["feature_coarse"].sum()).backward()
+    for p in list(models["coarse"].parameters()) + list(models["fine"].parameters()):
+        assert p.grad is not None and torch.isfinite(p.grad).all()
+    args.pertubeCord = False
+    torch.manual_seed(7)
+    plain = render_rays_cross_ray(models, emb, rays, None, 16, False, 1.0, 1.0, 16, 32768, False, args=args)
+    assert not torch.equal(plain["feature_fine"].detach(), got["feature_fine"].detach())   # the jitter did something
