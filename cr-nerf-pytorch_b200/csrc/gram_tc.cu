@@ -41,7 +41,7 @@ namespace crnerf {
 namespace {
 
 constexpr int kEpiWarps = 16;                       // lane quarter x column quarter
-// + warp 16: MMA issuer / TMEM allocator; warps 17-19 only donate registers: the register file is
+// + warps 16, 17: MMA issuers (16 also allocates TMEM); warps 18, 19 only donate registers: the register file is
 // allocated in units of 4 warps, so 17 warps cost as much as 20, and setmaxnreg moves what the
 // four control warps do not need (4 x 32 x 32) to the 16 epilogue warps (96 -> 104 each); the issuer
 // keeps 64: its spills would go to L2 (the streaming loads thrash the small L1) and stall every MMA group
@@ -266,42 +266,47 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
 
   if (warp >= kEpiWarps) {
     setmaxnreg_dec<64>();     // the whole warpgroup (warps 16-19) must execute the same setmaxnreg
-    // ------------------------------------------------------------------ MMA issuer
-    // The whole warp runs the scheduler with warp-uniform state (barrier tests are combined by a
-    // vote, so the compiler keeps descriptors and counters in uniform registers: a thread-private
-    // scheduler pays ~20 instructions of register shuffling per MMA and becomes the bottleneck);
-    // one elected lane issues the MMAs of a burst as straight-line code.
-    if (warp == kEpiWarps) {
-      constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 | version | SW128
-      auto desc = [](uint32_t saddr) {
-        return (static_cast<uint64_t>(kHi) << 32) | (((saddr & 0x3ffffu) >> 4) | (1u << 16));
-      };
-      auto ready = [](uint64_t* bar, uint32_t parity) -> bool {
-        return __all_sync(0xffffffffu, mbar_test(bar, parity) != 0);
-      };
-      const uint32_t s0 = smem_u32(smem);
-      const uint32_t cnt[2] = {count_of(0), count_of(1)};
-      uint32_t l1_it[2] = {0, 0};    // next tile (stream-local) whose layer 1 is to be issued
-      uint32_t m_it[2] = {0, 0};     // tile of the main chain
-      int m_op[2] = {0, 0};          // 0: layer 2, 1: layer 3, 2: Gram
-      uint32_t g_acc = 0;            // 1 once the Gram accumulators hold something
-      uint32_t idle = 0;
-      [[maybe_unused]] int itr_n = 0;
+    // ------------------------------------------------------------------ MMA issuers
+    // Two issuer warps, split by urgency rather than by stream: warp 16 issues the layer-2 / layer-3
+    // groups (what the epilogue warps are waiting for), warp 17 the layer-1 prefetch of a stream's
+    // next tile and the Gram groups (a whole tile of slack).  A burst blocks its issuer for its whole
+    // execution time (the issue queue is shallow); with one issuer a short critical group queued up
+    // behind the ISSUE of a long prefetch burst (measured: 1.2 - 2.2 k cycles from "activations
+    // ready" to "group issued"), with two the pipe interleaves them.  All Gram MMAs come from one
+    // thread, so the accumulators G1 / G2 see a single ordered stream; everything else is ordered
+    // through the barriers.  Each warp runs its scheduler with warp-uniform state (barrier tests are
+    // combined by a vote, so descriptors and counters stay in uniform registers: a thread-private
+    // scheduler pays ~20 instructions of register shuffling per MMA) and one elected lane issues a
+    // group as straight-line code.
+    constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 | version | SW128
+    auto desc = [](uint32_t saddr) {
+      return (static_cast<uint64_t>(kHi) << 32) | (((saddr & 0x3ffffu) >> 4) | (1u << 16));
+    };
+    auto ready = [](uint64_t* bar, uint32_t parity) -> bool {
+      return __all_sync(0xffffffffu, mbar_test(bar, parity) != 0);
+    };
+    const uint32_t s0 = smem_u32(smem);
+    const uint32_t cnt[2] = {count_of(0), count_of(1)};
+    [[maybe_unused]] int itr_n = 0;
 #ifdef CRNERF_GRAM_TIMING
 #define ITRACE(tag)                                                                                  \
   do {                                                                                               \
-    if (blockIdx.x == 0 && lane == 0 && P.ts && itr_n < 200)                                         \
-      P.ts[600 + itr_n++] = ((long long)(tag) << 48) | (clock64() & 0xffffffffffffLL);              \
+    if (blockIdx.x == 0 && lane == 0 && P.ts && itr_n < 100)                                         \
+      P.ts[600 + 100 * (warp - kEpiWarps) + itr_n++] = ((long long)(tag) << 48) | (clock64() & 0xffffffffffffLL); \
   } while (0)
 #else
 #define ITRACE(tag) do { } while (0)
 #endif
+    if (warp == kEpiWarps) {
+      uint32_t m_it[2] = {0, 0};     // tile of the chain
+      int m_op[2] = {0, 0};          // 0: layer 2, 1: layer 3
+      uint32_t idle = 0;
       while (m_it[0] < cnt[0] || m_it[1] < cnt[1]) {
         bool progressed = false;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           uint64_t* b = bars + s * kBarsPerStream;
-          const uint32_t sb = s0 + s * kStreamBytes, tb = tmem + s * kStreamCols;
+          const uint32_t tb = tmem + s * kStreamCols;
           if (m_it[s] >= cnt[s]) continue;
           const uint32_t par = m_it[s] & 1;
           if (m_op[s] == 0) {
@@ -324,7 +329,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
             ITRACE(40 + 4 * s + 0);
             m_op[s] = 1;
             progressed = true;
-          } else if (m_op[s] == 1) {
+          } else {
             // ---- layer 3: D3 = H2 W3^T, K = 64 (TS; H2 per 16-column group: 8 hi words | 8 lo words)
             if (!ready(&b[A2_FULL], par)) continue;
             tc_fence_after_sync();
@@ -342,11 +347,52 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
             }
             __syncwarp();
             ITRACE(40 + 4 * s + 1);
-            m_op[s] = 2;
+            m_op[s] = 0;
+            ++m_it[s];
             progressed = true;
-          } else {
-            // ---- Gram: G1 += Yh^T Yh, G2 += Yh^T Yl, K = the tile's 128 pixels (SS; A rows 32..127 don't care)
-            if (!ready(&b[YT_FULL], par)) continue;
+          }
+        }
+        if (progressed) {
+          idle = 0;
+        } else if (__nanosleep(20), ++idle == (1u << 24)) {   // protocol bug: fail the launch instead of hanging the box
+          g_wait_timeout_tag = 0x80000000u | (69u << 16) | (blockIdx.x & 0xffff);
+          __trap();
+        }
+      }
+    } else if (warp == kEpiWarps + 1) {
+      uint32_t l1_it[2] = {0, 0};    // next tile (stream-local) whose layer 1 is to be issued
+      uint32_t g_it[2] = {0, 0};     // next tile whose Gram group is to be issued
+      uint32_t g_acc = 0;            // 1 once the Gram accumulators hold something
+      uint32_t idle = 0;
+      while (g_it[0] < cnt[0] || g_it[1] < cnt[1]) {
+        bool progressed = false;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          uint64_t* b = bars + s * kBarsPerStream;
+          const uint32_t sb = s0 + s * kStreamBytes, tb = tmem + s * kStreamCols;
+          // ---- layer 1 of tile l1_it: D1 = X W1^T, three split terms x 4 k-steps (SS).  Needs the
+          // staged X and region P free (layer 2 of the previous tile, which reads H1 there, retired).
+          if (l1_it[s] < cnt[s] && ready(&b[X_FULL], l1_it[s] & 1) &&
+              (l1_it[s] == 0 || ready(&b[D2_FULL], (l1_it[s] - 1) & 1))) {
+            tc_fence_after_sync();
+            if (elect_one()) {
+              const uint32_t id = make_idesc_f16(128, 128, 0);
+#pragma unroll
+              for (int term = 0; term < 3; ++term) {
+                const uint32_t a = sb + kXOffS + (term == 2 ? 16384 : 0);   // hi, hi, lo
+                const uint32_t bq = s0 + kW1Off + (term == 1 ? 16384 : 0);  // hi, lo, hi
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_ss(tb + cP, desc(a + 32 * k), desc(bq + 32 * k), id, (term | k) ? 1u : 0u);
+              }
+              umma_commit(&b[D1_FULL]);
+            }
+            __syncwarp();
+            ITRACE(40 + 4 * s + 3);
+            ++l1_it[s];
+            progressed = true;
+          }
+          // ---- Gram: G1 += Yh^T Yh, G2 += Yh^T Yl, K = the tile's 128 pixels (SS; A rows 32..127 don't care)
+          if (g_it[s] < cnt[s] && ready(&b[YT_FULL], g_it[s] & 1)) {
             tc_fence_after_sync();
             if (elect_one()) {
               const uint32_t id = make_idesc_f16(128, 32, 0);
@@ -366,46 +412,14 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
             __syncwarp();
             ITRACE(40 + 4 * s + 2);
             g_acc = 1;
-            m_op[s] = 0;
-            ++m_it[s];
+            ++g_it[s];
             progressed = true;
-          }
-        }
-        // Layer 1 of a stream's NEXT tile is a prefetch with a whole tile period of slack: it is
-        // issued only when no main-chain group was ready, so it never sits in the in-order pipe
-        // ahead of a short group the epilogue warps are waiting for.
-        if (!progressed) {
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            uint64_t* b = bars + s * kBarsPerStream;
-            const uint32_t sb = s0 + s * kStreamBytes, tb = tmem + s * kStreamCols;
-            // ---- layer 1 of tile l1_it: D1 = X W1^T, three split terms x 4 k-steps (SS).  Needs the
-            // staged X and region P free (layer 2 of the previous tile, which reads H1 there, retired).
-            if (l1_it[s] < cnt[s] && ready(&b[X_FULL], l1_it[s] & 1) &&
-                (l1_it[s] == 0 || ready(&b[D2_FULL], (l1_it[s] - 1) & 1))) {
-              tc_fence_after_sync();
-              if (elect_one()) {
-                const uint32_t id = make_idesc_f16(128, 128, 0);
-  #pragma unroll
-                for (int term = 0; term < 3; ++term) {
-                  const uint32_t a = sb + kXOffS + (term == 2 ? 16384 : 0);   // hi, hi, lo
-                  const uint32_t bq = s0 + kW1Off + (term == 1 ? 16384 : 0);  // hi, lo, hi
-  #pragma unroll
-                  for (int k = 0; k < 4; ++k) umma_ss(tb + cP, desc(a + 32 * k), desc(bq + 32 * k), id, (term | k) ? 1u : 0u);
-                }
-                umma_commit(&b[D1_FULL]);
-              }
-              __syncwarp();
-              ITRACE(40 + 4 * s + 3);
-              ++l1_it[s];
-              progressed = true;
-            }
           }
         }
         if (progressed) {
           idle = 0;
-        } else if (__nanosleep(20), ++idle == (1u << 24)) {   // protocol bug: fail the launch instead of hanging the box
-          g_wait_timeout_tag = 0x80000000u | (69u << 16) | (blockIdx.x & 0xffff);
+        } else if (__nanosleep(20), ++idle == (1u << 24)) {
+          g_wait_timeout_tag = 0x80000000u | (70u << 16) | (blockIdx.x & 0xffff);
           __trap();
         }
       }

@@ -36,7 +36,7 @@ NAMES = {10: "wait D1(0)", 11: "wait D1(1)", 12: "got D1(0)", 13: "got D1(1)", 1
          40: "issue L2(0)", 41: "issue L3(0)", 42: "issue G(0)", 43: "issue L1(0)",
          44: "issue L2(1)", 45: "issue L3(1)", 46: "issue G(1)", 47: "issue L1(1)"}
 ev = []
-for who, base, cnt in (("w0 ", 256, 128), ("w15", 384, 128), ("iss", 600, 200)):
+for who, base, cnt in (("w0 ", 256, 128), ("w15", 384, 128), ("isC", 600, 100), ("isN", 700, 100)):
     for v in t[base:base + cnt]:
         if v:
             ev.append(((v & 0xffffffffffff) - (t0 & 0xffffffffffff), who, NAMES.get(v >> 48, str(v >> 48))))
