@@ -164,3 +164,47 @@ def test_render_frame_from_camera_equals_render_from_rays():
     b = render_frame_sharded(models, emb, oracle.pinhole_rays(h, w, c2w).cuda(), style, (h, w), 32, 32, chunk=256,
                              args=args)
     assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+
+
+def _nccl_worker(rank, world, port, hw, scheme, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from crnerf_b200.frame import render_frame_sharded
+        from models.nerf import PosEmbedding
+        models, args = build_mirror_models(0)
+        models = {k: m.to(dev) for k, m in models.items()}
+        emb = {"xyz": PosEmbedding(14, 15), "dir": PosEmbedding(3, 4)}
+        h, w = hw
+        rays = oracle.pinhole_rays(h, w, oracle.synthetic_pose(0)).to(dev)
+        style = torch.rand(1, 64, 32, 32, generator=torch.Generator().manual_seed(2)).to(dev)
+        rgb = render_frame_sharded(models, emb, rays, style, (h, w), 32, 32, scheme=scheme, args=args)
+        torch.cuda.synchronize(dev)
+        torch.save(rgb.cpu(), os.path.join(out_dir, f"rgb_{scheme}_{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scheme", ["stats", "gather"])
+def test_render_frame_sharded_two_ranks_nccl_matches_one_rank(tmp_path, scheme):
+    """The CUDA cross-ray phases under NCCL with world 2 (needs two GPUs; `bench.py --gpus N` runs the same
+    comparison at every N as `frame_check`): ragged row split, both schemes, every rank ends up with the
+    frame a single GPU renders."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from crnerf_b200.frame import render_frame_sharded
+    from models.nerf import PosEmbedding
+    hw = (23, 41)          # 943 rays: the two blocks differ in size
+    mp.spawn(_nccl_worker, args=(2, _free_port(), hw, scheme, str(tmp_path)), nprocs=2, join=True)
+    models, args = build_mirror_models(0)
+    models = {k: m.cuda() for k, m in models.items()}
+    emb = {"xyz": PosEmbedding(14, 15), "dir": PosEmbedding(3, 4)}
+    rays = oracle.pinhole_rays(*hw, oracle.synthetic_pose(0)).cuda()
+    style = torch.rand(1, 64, 32, 32, generator=torch.Generator().manual_seed(2)).cuda()
+    want = render_frame_sharded(models, emb, rays, style, hw, 32, 32, scheme=scheme, args=args).cpu()
+    for r in range(2):
+        got = torch.load(os.path.join(tmp_path, f"rgb_{scheme}_{r}.pt"))
+        assert float((got - want).abs().max()) <= 1e-5
