@@ -154,10 +154,16 @@ struct GramParams {
   do {                                                                                            \
     if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && P.ts && (it) == 2) P.ts[800 + 20 * (k) + warp] = clock64(); \
   } while (0)
+// fine-grained stamps of ONE untraced warp (5) in round 2: ts[900 + k]
+#define FINE(k, it)                                                                               \
+  do {                                                                                            \
+    if (blockIdx.x == 0 && threadIdx.x == 5 * 32 && P.ts && (it) == 2) P.ts[900 + (k)] = clock64(); \
+  } while (0)
 #else
 #define TSTAMP(slot) do { } while (0)
 #define TRACE(tag) do { } while (0)
 #define SNAP(k, it) do { } while (0)
+#define FINE(k, it) do { } while (0)
 #endif
 
 // channel mean of the job's map -> mean[64] (shared), fixed summation order.  All threads call.
@@ -489,8 +495,10 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
       uint64_t* b = bars + s * kBarsPerStream;
       const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + s * kStreamCols;
       TRACE(10 + s);
+      if (s == 0) FINE(0, it);
       mbar_wait_parked(&b[D1_FULL], it & 1, 64);
       tc_fence_after_sync();
+      if (s == 0) FINE(1, it);
       TRACE(12 + s);
       if (s == 0) SNAP(0, it);
       {
@@ -511,8 +519,10 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
       if (s == 0) SNAP(1, it);
       if (t_next >= 0) {
         stage_x(s, t_next);
+        if (s == 0) FINE(5, it);
         load_x(s, t_after);
       }
+      if (s == 0) FINE(6, it);
       TRACE(16 + s);
       if (s == 0) SNAP(2, it);
     };
@@ -546,13 +556,17 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
       uint64_t* b = bars + s * kBarsPerStream;
       const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + s * kStreamCols;
       const bool valid = tile * 128 + row < J.n;
+      if (s == 0) FINE(10, it);
       mbar_wait_parked(&b[D3_FULL], it & 1, 66);
       tc_fence_after_sync();
       TRACE(30 + s);
+      if (s == 0) FINE(11, it);
       uint32_t v[8];
       tmem_ld_x8(lane_base + cR + 8 * cq, v);
       tmem_ld_wait();
+      if (s == 0) FINE(12, it);
       if (it > 0) mbar_wait_parked(&b[G_DONE], (it - 1) & 1, 67);  // the stream's previous Gram MMAs are done reading Y^T
+      if (s == 0) FINE(13, it);
       uint8_t* yh = smem + s * kStreamBytes + (row >> 6) * kYtSlab;
       uint8_t* yl = yh + 2 * kYtSlab;
       const uint32_t kk = row & 63;
@@ -566,10 +580,12 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tc_kernel(const __grid_cons
         *reinterpret_cast<__half*>(yh + off) = hi;
         *reinterpret_cast<__half*>(yl + off) = lo;
       }
+      if (s == 0) FINE(14, it);
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&b[YT_FULL]);
+      if (s == 0) FINE(15, it);
       TRACE(32 + s);
     };
     long long t0 = tile_of(0), t1 = tile_of(1);

@@ -49,3 +49,13 @@ for c, who, name in ev:
 for k, name in enumerate(["got D1(0)", "ep1(0) done", "staged(0)", "ep2(0) done"]):
     vals = [(v & 0xffffffffffff) - (t0 & 0xffffffffffff) for v in t[800 + 20 * k: 800 + 20 * k + 16]]
     print(f"round 2, all warps, {name:12s}:", " ".join(str(v) for v in vals))
+
+fine = [(v & 0xffffffffffff) - (t0 & 0xffffffffffff) if v else None for v in t[900:916]]
+names = {0: "ep1: wait D1", 1: "got D1", 2: "ld done", 3: "math done", 4: "st + arrive done", 5: "stage_x done", 6: "load_x issued",
+         10: "ep3: wait D3", 11: "got D3", 12: "ld done", 13: "G_DONE ok", 14: "Yt stored", 15: "fence + arrive done"}
+print("warp 5, round 2, stream 0 (cycles since kernel start; deltas in brackets):")
+prev = None
+for k in sorted(names):
+    if fine[k] is not None:
+        print(f"  {names[k]:22s} {fine[k]:8d}" + (f"  [+{fine[k] - prev}]" if prev is not None else ""))
+        prev = fine[k]
