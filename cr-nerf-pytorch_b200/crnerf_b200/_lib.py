@@ -93,6 +93,13 @@ SIGNATURES = {
     "crnerf_encoder_pack": (C.c_int, [C.POINTER(EncoderWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
     "crnerf_encoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_size_t, C.c_void_p]),
+    "crnerf_encoder_tape_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "crnerf_encoder_backward_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "crnerf_encoder_forward_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                               C.c_size_t, C.c_void_p]),
+    "crnerf_encoder_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.POINTER(EncoderWeights), C.c_void_p, C.c_void_p,
+                                          C.c_size_t, C.c_void_p]),
     "crnerf_ray_loss_forward": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_float, C.c_float, C.c_float,
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "crnerf_ray_loss_backward": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_float, C.c_float, C.c_float] +

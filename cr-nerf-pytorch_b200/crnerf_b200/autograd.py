@@ -108,3 +108,28 @@ class Fp32Region(torch.autograd.Function):
         res = [next(grads) if t.requires_grad else None for t in (ctx.leaf,) + tuple(ctx.params)]
         ctx.leaf = ctx.out = ctx.params = None
         return (None, *res)
+
+
+class EncoderFn(torch.autograd.Function):
+    """``encoder_sameoutputsize.forward`` under autograd on the library's own kernels (the training
+    step back-propagates through ``enc_a``: reference train_mask_grid_sample.py, models/
+    linearStyleTransfer.py:250-276): forward = the inference tensor-core kernels with the activation
+    planes kept, backward = csrc/encoder_train.cuh (input-gradient convolutions on the forward kernel,
+    tcgen05 weight-gradient GEMMs with K = pixels, fp16 hi/lo operands, deterministic, no library
+    convolution).  ``params`` = conv1.weight, conv1.bias, ..., conv7.bias."""
+
+    @staticmethod
+    def forward(ctx, packed, x, *params):
+        out, tape = ops.encoder_forward_train(packed, x)
+        ctx.packed, ctx.tape = packed, tape
+        ctx.save_for_backward(x, out)
+        ctx.want_x = x.requires_grad
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, out = ctx.saved_tensors
+        gw, gb, gx = ops.encoder_backward(ctx.packed, x, out, ctx.tape, g, ctx.want_x)
+        ctx.packed = ctx.tape = None
+        return (None, gx, *[t for pair in zip(gw, gb) for t in pair])

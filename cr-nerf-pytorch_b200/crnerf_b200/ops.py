@@ -919,3 +919,62 @@ def encoder_forward(packed: PackedEncoder, img: torch.Tensor) -> torch.Tensor:
         check(lib.crnerf_encoder_forward(packed.buf.data_ptr(), x.data_ptr(), h, w, out.data_ptr(),
                                          scratch.data_ptr(), nbytes, _stream(dev)))
     return out
+
+
+ENCODER_SHAPES = [(3, 3, 1, 1), (64, 3, 3, 3), (64, 64, 3, 3), (128, 64, 3, 3), (128, 128, 3, 3), (128, 128, 3, 3),
+                  (64, 128, 1, 1)]
+
+
+def _encoder_img(img):
+    _need(img, "img", 4)
+    if img.shape[0] != 1 or img.shape[1] != 3:
+        raise ValueError(f"img must be (1,3,H,W), got {tuple(img.shape)}")
+    h, w = int(img.shape[2]), int(img.shape[3])
+    if h < 8 or w < 8 or h > 8192 or w > 8192:
+        raise ValueError(f"image {h}x{w} unsupported (8..8192 per side)")
+    return _c(img.detach()), h, w
+
+
+def encoder_forward_train(packed: PackedEncoder, img: torch.Tensor):
+    """Forward of the training step: ``(out (1,64,32,32), tape)`` - the kernels of ``encoder_forward``
+    with every layer's activation planes kept for ``encoder_backward`` (crnerf_encoder_forward_train)."""
+    lib = _lib.load()
+    x, h, w = _encoder_img(img)
+    dev = x.device
+    nbytes = int(lib.crnerf_encoder_tape_bytes(h, w))
+    tape = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = torch.empty((1, 64, 32, 32), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.crnerf_encoder_forward_train(packed.buf.data_ptr(), x.data_ptr(), h, w, out.data_ptr(),
+                                               tape.data_ptr(), nbytes, _stream(dev)))
+    return out, tape
+
+
+def encoder_backward(packed: PackedEncoder, img: torch.Tensor, out: torch.Tensor, tape: torch.Tensor,
+                     grad_out: torch.Tensor, want_img_grad: bool = False):
+    """Gradients of the 7 weights and 7 biases (state_dict layouts, conv1..conv7) and, optionally, of
+    ``img``: crnerf_encoder_backward (tensor-core input- and weight-gradient convolutions, deterministic)."""
+    lib = _lib.load()
+    x, h, w = _encoder_img(img)
+    dev = x.device
+    g = _c(grad_out.detach().to(torch.float32))
+    if g.numel() != 64 * 32 * 32:
+        raise ValueError(f"grad_out must be (1,64,32,32), got {tuple(grad_out.shape)}")
+    gw = [torch.empty(sh, dtype=torch.float32, device=dev) for sh in ENCODER_SHAPES]
+    gb = [torch.empty(sh[0], dtype=torch.float32, device=dev) for sh in ENCODER_SHAPES]
+    grads = _lib.EncoderWeights()
+    for i in range(7):
+        grads.weight[i], grads.bias[i] = gw[i].data_ptr(), gb[i].data_ptr()
+    g_img = torch.empty_like(x) if want_img_grad else None
+    nbytes = int(lib.crnerf_encoder_backward_scratch_bytes(h, w))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.crnerf_encoder_backward(packed.buf.data_ptr(), x.data_ptr(), h, w, _c(out).data_ptr(), g.data_ptr(),
+                                          tape.data_ptr(), C.byref(grads), g_img.data_ptr() if want_img_grad else None,
+                                          scratch.data_ptr(), nbytes, _stream(dev)))
+    if _ENCODER_DEBUG is not None:
+        _ENCODER_DEBUG["scratch"] = scratch
+    return gw, gb, g_img
+
+
+_ENCODER_DEBUG = None      # tools/enc_bwd_debug.py sets a dict to look at the backward's scratch

@@ -109,6 +109,13 @@ int relu_bias_grad(float* g, const void* act, int64_t n_points, int width, float
 size_t encoder_packed_bytes();
 size_t encoder_scratch_bytes(int H, int W);
 int encoder_pack(const crnerf_encoder_weights* w, void* packed, size_t packed_bytes, cudaStream_t st);
+size_t encoder_tape_bytes(int H, int W);
+size_t encoder_backward_scratch_bytes(int H, int W);
+int encoder_forward_train(const void* packed, const float* img, int H, int W, float* out, void* tape,
+                          size_t tape_bytes, cudaStream_t st);
+int encoder_backward(const void* packed, const float* img, int H, int W, const float* out, const float* grad_out,
+                     const void* tape, float* const* gw, float* const* gb, float* grad_img, void* scratch,
+                     size_t scratch_bytes, cudaStream_t st);
 int encoder_forward(const void* packed, const float* img, int H, int W, float* out, void* scratch,
                     size_t scratch_bytes, cudaStream_t st);
 // implemented in loss.cu
@@ -358,6 +365,27 @@ int crnerf_encoder_forward(const void* packed, const float* img, int height, int
   int rc = device_check();
   if (rc) return rc;
   return encoder_forward(packed, img, height, width, out, scratch, scratch_bytes, (cudaStream_t)stream);
+}
+size_t crnerf_encoder_tape_bytes(int height, int width) {
+  return height >= 8 && width >= 8 ? encoder_tape_bytes(height, width) : 0;
+}
+size_t crnerf_encoder_backward_scratch_bytes(int height, int width) {
+  return height >= 8 && width >= 8 ? encoder_backward_scratch_bytes(height, width) : 0;
+}
+int crnerf_encoder_forward_train(const void* packed, const float* img, int height, int width, float* out,
+                                 void* tape, size_t tape_bytes, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return encoder_forward_train(packed, img, height, width, out, tape, tape_bytes, (cudaStream_t)stream);
+}
+int crnerf_encoder_backward(const void* packed, const float* img, int height, int width, const float* out,
+                            const float* grad_out, const void* tape, const crnerf_encoder_grads* grads,
+                            float* grad_img, void* scratch, size_t scratch_bytes, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  CRNERF_REQUIRE(grads, "null argument");
+  return encoder_backward(packed, img, height, width, out, grad_out, tape, grads->weight, grads->bias, grad_img,
+                          scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
 int crnerf_ray_loss_forward(const float* rgb_coarse, const float* rgb_fine, const float* targets,

@@ -29,6 +29,7 @@
 // conv6's small output, which the tail kernel pools.
 #include <cuda_fp16.h>
 #include <algorithm>
+#include <cstdlib>
 #include "common.h"
 #include "ptx.cuh"
 
@@ -227,7 +228,7 @@ constexpr int conv_smem_bytes() {
   return kRingW * 2 * COUT * 128 + ring_a<COUT>() * kRowBytes + 256 + COUT * 4;  // rings, barriers, bias
 }
 
-enum ConvOut { kOutRows = 0, kOutPlanes = 1, kOutPoolPlanes = 2 };
+enum ConvOut { kOutRows = 0, kOutPlanes = 1, kOutPoolPlanes = 2, kOutRaw = 3 };
 
 // One step = a "band tile": 128 consecutive positions of the flattened (band, padded column) grid,
 // for output rows 2b and 2b+1 -> two accumulators that share every weight chunk (half the L2 weight
@@ -238,11 +239,14 @@ enum ConvOut { kOutRows = 0, kOutPlanes = 1, kOutPoolPlanes = 2 };
 //   kOutPlanes      the next layer's hi/lo planes with reflection halo    (conv4 -> conv5)
 //   kOutPoolPlanes  2x2 max-pool in registers (vertical: the two accumulators, horizontal: the
 //                   neighbour lane), then planes of the pooled layer       (conv3, conv5)
+//   kOutRaw         fp32 NHWC rows without bias / activation, and the launch's max |value| folded into
+//                   *maxbits (the backward's input-gradient convolutions, see "training" below)
 template <int CIN, int COUT, int kOut>
 __global__ void __launch_bounds__(kConvThreads, 1)
 enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
                    const uint8_t* __restrict__ wimg, const float* __restrict__ bias, float* __restrict__ out,
-                   __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H, int W, int Ws, int n_tiles) {
+                   __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H, int W, int Ws, int n_tiles,
+                   unsigned* __restrict__ maxbits) {
   // CIN == 8: the first 3x3 convolution (conv2, 3 real channels padded to one 8-channel chunk).  A K = 16
   // step then spans TWO horizontally adjacent taps: the descriptor's K-chunk stride (LBO) is 16 B, i.e.
   // the next pixel, so a tap row is 2 steps (dx = 0,1 | 2, and a phantom dx = 3 whose weights are zero).
@@ -258,7 +262,6 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   // by its shared-memory operand reads, 6 KB per 32 tensor cycles); lo*hi stays an N = 64 MMA.
   constexpr bool kStack = COUT == 64;
   constexpr uint32_t kDCols = kStack ? 128 : COUT;   // TMEM columns per accumulator
-  static_assert(!kStack || kOut != kOutRows, "the stacked form is not wired for the fp32-rows epilogue");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_ring = smem;
   uint8_t* s_rows = s_ring + kRingW * kChunk;
@@ -469,6 +472,7 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
           }
         }
       } else {
+        float vmax = 0.f;
 #pragma unroll 1
         for (int r = 0; r < 2; ++r) {
           const bool valid = in_row && y + r < H;
@@ -497,6 +501,14 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
                   split8(f, h, l);
                   store_plane_elem(out_hi, out_lo, H + 2, Wp, c0 / 8 + g, tg, h, l);
                 }
+              } else if constexpr (kOut == kOutRaw) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                  vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+                  o4[(c0 + j) / 4] = o;
+                }
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
@@ -507,6 +519,12 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
               }
             }
           }
+        }
+        if constexpr (kOut == kOutRaw) {
+          // non-negative floats order like their bit patterns: one atomic per warp and tile
+#pragma unroll
+          for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+          if (lane == 0 && vmax > 0.f) atomicMax(maxbits, __float_as_uint(vmax));
         }
       }
       tc_fence_before_sync();
@@ -521,7 +539,8 @@ enc_conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 
 // ---- adaptive avg-pool to 32x32 + conv7 1x1 128->64 + LeakyReLU: F (H4,W4,128) -> out (64,32,32) ----
 __global__ void __launch_bounds__(512)
-enc_tail_kernel(const float* __restrict__ f, int H4, int W4, const float* __restrict__ blob, float* __restrict__ out) {
+enc_tail_kernel(const float* __restrict__ f, int H4, int W4, const float* __restrict__ blob, float* __restrict__ out,
+                float* __restrict__ pooled_out) {
   __shared__ float part[4][128];
   __shared__ float pooled[128];
   const int bi = blockIdx.x / 32, bj = blockIdx.x % 32;
@@ -537,7 +556,10 @@ enc_tail_kernel(const float* __restrict__ f, int H4, int W4, const float* __rest
   }
   part[g][c] = acc;
   __syncthreads();
-  if (threadIdx.x < 128) pooled[c] = ((part[0][c] + part[1][c]) + (part[2][c] + part[3][c])) / (float)n;
+  if (threadIdx.x < 128) {
+    pooled[c] = ((part[0][c] + part[1][c]) + (part[2][c] + part[3][c])) / (float)n;
+    if (pooled_out) pooled_out[(size_t)blockIdx.x * 128 + c] = pooled[c];   // training: conv7's input for its weight gradient
+  }
   __syncthreads();
   // conv7: 64 outputs x 128 inputs; 8 threads per output, 16 inputs each
   const int co = threadIdx.x >> 3, k0 = (threadIdx.x & 7) * 16;
@@ -553,7 +575,7 @@ enc_tail_kernel(const float* __restrict__ f, int H4, int W4, const float* __rest
 
 template <int CIN, int COUT, int kOut>
 int launch_conv(const __half* planes, const uint8_t* wimg, const float* bias, float* out, __half* out_planes,
-                long long out_plane_len, int H, int W, cudaStream_t st) {
+                long long out_plane_len, int H, int W, cudaStream_t st, unsigned* maxbits = nullptr) {
   const long long plane_len = (long long)(H + 2) * (W + 2);
   // flat index space: band b (output rows 2b, 2b+1) x padded column, band stride Ws (even, so that
   // 2x2 pool partners share a lane pair); tiles are runs of 128 consecutive indices starting at 1
@@ -565,7 +587,7 @@ int launch_conv(const __half* planes, const uint8_t* wimg, const float* bias, fl
   const int grid = std::min(n_tiles, num_sms());
   kern<<<grid, kConvThreads, smem, st>>>(planes, planes + (size_t)CIN * plane_len, wimg, bias, out, out_planes,
                                          out_planes ? out_planes + (size_t)COUT * out_plane_len : nullptr, H, W,
-                                         Ws, n_tiles);
+                                         Ws, n_tiles, maxbits);
   count_launch();
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;
@@ -580,17 +602,30 @@ size_t pa_bytes(int H, int W) { return std::max(planes_bytes(64, H, W), planes_b
 size_t pb_bytes(int H, int W) { return planes_bytes(64, H / 2, W / 2); }
 size_t pc_bytes(int H, int W) { return planes_bytes(128, H / 2, W / 2); }
 
+#include "encoder_train.cuh"
+
 }  // namespace
 
 // conv2's tensor-core image (3 chunks of 16 KB) follows the fp32 blob, 128-byte aligned
 static size_t first_image_offset(size_t blob_off) { return (blob_off + Blob::total * sizeof(float) + 127) & ~size_t(127); }
 constexpr size_t kFirstImageBytes = 3 * 2 * 64 * 128;
 
+// training: weight images of the four input-gradient convolutions (conv3..conv6 with channels swapped and
+// taps flipped) follow conv2's image; same sizes as the forward images
+static size_t dgrad_image_offset(size_t blob_off, int i) {
+  TcLayer L[4];
+  size_t b;
+  tc_layers(L, b);
+  size_t off = (first_image_offset(blob_off) + kFirstImageBytes + 127) & ~size_t(127);
+  for (int j = 0; j < i; ++j) off += L[j].bytes();
+  return off;
+}
+
 size_t encoder_packed_bytes() {
   TcLayer L[4];
   size_t blob;
   tc_layers(L, blob);
-  return first_image_offset(blob) + kFirstImageBytes;
+  return dgrad_image_offset(blob, 4);
 }
 
 size_t encoder_scratch_bytes(int H, int W) {
@@ -611,7 +646,10 @@ int encoder_pack(const crnerf_encoder_weights* w, void* packed, size_t packed_by
                                            w->bias[4], w->bias[5], w->weight[6], w->bias[6],
                                            reinterpret_cast<float*>(img + blob));
   enc_pack_first_kernel<<<48, 256, 0, st>>>(w->weight[1], img + first_image_offset(blob));
-  count_launch(6);
+  for (int i = 0; i < 4; ++i)
+    enc_pack_tc_dgrad_kernel<<<2 * num_sms(), 256, 0, st>>>(w->weight[2 + i], L[i].cin, L[i].cout,
+                                                            img + dgrad_image_offset(blob, i));
+  count_launch(10);
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;
 }
@@ -665,9 +703,279 @@ int encoder_forward(const void* packed, const float* img, int H, int W, float* o
   // conv6: Pa -> F (H/4, W/4, 128) fp32
   if ((rc = launch_conv<128, 128, kOutRows>(Pa, wimg + L[3].offset, blob + Blob::b6, F, nullptr, 0, H4, W4, st)))
     return rc;
-  enc_tail_kernel<<<1024, 512, 0, st>>>(F, H4, W4, blob, out);
+  enc_tail_kernel<<<1024, 512, 0, st>>>(F, H4, W4, blob, out, nullptr);
   count_launch();
   CRNERF_CUDA(cudaGetLastError());
+  return CRNERF_OK;
+}
+
+}  // namespace crnerf
+
+// ======================================================================================================
+// training: forward that keeps what the backward needs, and the backward (kernels: encoder_train.cuh)
+// ======================================================================================================
+namespace crnerf {
+namespace {
+
+size_t tape_planes(int C, int h, int w) { return align256((size_t)2 * C * (h + 2) * (w + 2) * sizeof(__half) + 256); }
+struct Tape {   // byte offsets: activation planes kept by the training forward (+256 B: a K step may read past a row)
+  size_t p0, a2, a3, q3, a4, a5, q5, f, pooled, total;
+};
+Tape tape_layout(int H, int W) {
+  const int H2 = H / 2, W2 = W / 2, H4 = H2 / 2, W4 = W2 / 2;
+  Tape t;
+  size_t o = 0;
+  t.p0 = o; o += tape_planes(8, H, W);        // conv1 output (3 real channels)
+  t.a2 = o; o += tape_planes(64, H, W);       // LeakyReLU(conv2)
+  t.a3 = o; o += tape_planes(64, H, W);       // LeakyReLU(conv3), before the pool
+  t.q3 = o; o += tape_planes(64, H2, W2);     // pooled
+  t.a4 = o; o += tape_planes(128, H2, W2);
+  t.a5 = o; o += tape_planes(128, H2, W2);    // before the pool
+  t.q5 = o; o += tape_planes(128, H4, W4);
+  t.f = o; o += f_bytes(H, W);                // LeakyReLU(conv6), fp32 NHWC
+  t.pooled = o; o += align256((size_t)1024 * 128 * sizeof(float));
+  t.total = o;
+  return t;
+}
+
+size_t grad_planes(int C, int h, int w) { return align256((size_t)2 * C * (h + 4) * grad_stride(w) * sizeof(__half) + 256); }
+size_t dx_rows(int C, int h, int w) { return align256((size_t)(h + 2) * (grad_stride(w) - 2) * C * sizeof(float)); }
+constexpr int kPrepBlocks = 296;     // x-dimension of the elementwise backward grids (bias partials per chunk)
+constexpr int kFirstBlocks = 296;
+struct BwdScratch {
+  size_t ga, gb, dx, part, dpooled, dpre7, dbpart, part2, small, total;
+};
+BwdScratch bwd_layout(int H, int W) {
+  const int H2 = H / 2, W2 = W / 2, H4 = H2 / 2, W4 = W2 / 2;
+  BwdScratch s;
+  size_t o = 0;
+  s.ga = o; o += std::max({grad_planes(128, H4, W4), grad_planes(128, H2, W2), grad_planes(64, H, W)});
+  s.gb = o; o += std::max(grad_planes(128, H2, W2), grad_planes(64, H, W));
+  s.dx = o; o += std::max({dx_rows(128, H4, W4), dx_rows(128, H2, W2), dx_rows(64, H2, W2), dx_rows(64, H, W)});
+  s.part = o; o += align256(std::max((size_t)148 * 3 * 128 * 128, (size_t)kFirstBlocks * 1728) * sizeof(float));
+  s.dpooled = o; o += align256((size_t)1024 * 128 * sizeof(float));
+  s.dpre7 = o; o += align256((size_t)1024 * 64 * sizeof(float));
+  s.dbpart = o; o += align256((size_t)16 * kPrepBlocks * 8 * sizeof(float));
+  s.part2 = o; o += align256((size_t)kFirstBlocks * 12 * sizeof(float));
+  s.small = o; o += 256;                       // scales[8] floats | maxbits[8]
+  s.total = o;
+  return s;
+}
+
+template <int CIN, int COUT>
+int launch_wgrad(const __half* G, const __half* X, int h, int w, float* part, const float* scale, float* gw,
+                 cudaStream_t st) {
+  using Cfg = WgradCfg<CIN, COUT>;
+  const int Wg = grad_stride(w);
+  const long long g_plane = (long long)(h + 4) * Wg, x_plane = (long long)(h + 2) * (w + 2);
+  const int nseg = h * ((w + Cfg::kSeg - 1) / Cfg::kSeg);
+  const int grid = 3 * std::min(std::min(num_sms(), 148) / 3, nseg);
+  auto kern = enc_wgrad_tc_kernel<CIN, COUT>;
+  CRNERF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+  kern<<<grid, kWgradThreads, Cfg::kSmem, st>>>(G, G + (size_t)COUT * g_plane, g_plane, Wg, X,
+                                                X + (size_t)CIN * x_plane, x_plane, h, w, part);
+  enc_wgrad_reduce_kernel<CIN, COUT><<<(9 * COUT * CIN + 255) / 256, 256, 0, st>>>(part, grid, scale, gw);
+  count_launch(2);
+  CRNERF_CUDA(cudaGetLastError());
+  return CRNERF_OK;
+}
+
+int launch_prep(bool pool, const float* dx, int C, int hq, int wq, const __half* act, int H, int W, __half* G,
+                const unsigned* maxbits_in, const float* scale_in, float* scale_out, float* dbpart, float* gb,
+                cudaStream_t st) {
+  PrepArgs a;
+  a.dx = dx;
+  a.wdx = grad_stride(wq) - 2;
+  a.C = C;
+  a.hq = hq;
+  a.wq = wq;
+  a.act_hi = act;
+  a.act_lo = act + (size_t)C * (H + 2) * (W + 2);
+  a.H = H;
+  a.W = W;
+  a.Wg = grad_stride(W);
+  a.g_hi = G;
+  a.g_lo = G + (size_t)C * (H + 4) * a.Wg;
+  a.maxbits_in = maxbits_in;
+  a.scale_in = scale_in;
+  a.scale_out = scale_out;
+  a.db_part = dbpart;
+  CRNERF_CUDA(cudaMemsetAsync(G, 0, (size_t)2 * C * (H + 4) * a.Wg * sizeof(__half), st));
+  const int gx = (int)std::min<long long>(((long long)hq * wq + 255) / 256, kPrepBlocks);
+  const dim3 grid(gx, C / 8);
+  if (pool) enc_grad_prep_kernel<true><<<grid, 256, 0, st>>>(a);
+  else enc_grad_prep_kernel<false><<<grid, 256, 0, st>>>(a);
+  enc_db_reduce_kernel<<<(C + 127) / 128, 128, 0, st>>>(dbpart, gx, C, scale_out, gb);
+  count_launch(2);
+  CRNERF_CUDA(cudaGetLastError());
+  return CRNERF_OK;
+}
+
+}  // namespace
+
+size_t encoder_tape_bytes(int H, int W) { return tape_layout(H, W).total; }
+size_t encoder_backward_scratch_bytes(int H, int W) { return bwd_layout(H, W).total; }
+
+// forward of the training step: the same kernels, every layer's activation planes kept in `tape`
+int encoder_forward_train(const void* packed, const float* img, int H, int W, float* out, void* tape,
+                          size_t tape_bytes, cudaStream_t st) {
+  CRNERF_REQUIRE(packed && img && out && tape, "null argument");
+  CRNERF_REQUIRE(H >= 8 && W >= 8 && H <= 8192 && W <= 8192, "image %dx%d unsupported (8..8192 per side)", H, W);
+  const Tape T = tape_layout(H, W);
+  CRNERF_REQUIRE(tape_bytes >= T.total, "tape too small");
+  CRNERF_REQUIRE((reinterpret_cast<uintptr_t>(tape) & 255) == 0 && (reinterpret_cast<uintptr_t>(packed) & 127) == 0,
+                 "tape must be 256-byte and packed 128-byte aligned");
+  TcLayer L[4];
+  size_t blob_off;
+  tc_layers(L, blob_off);
+  const uint8_t* wimg = static_cast<const uint8_t*>(packed);
+  const float* blob = reinterpret_cast<const float*>(wimg + blob_off);
+  uint8_t* base = static_cast<uint8_t*>(tape);
+  auto P = [&](size_t off) { return reinterpret_cast<__half*>(base + off); };
+  const int H2 = H / 2, W2 = W / 2, H4 = H2 / 2, W4 = W2 / 2;
+  auto plane = [](int h, int w) { return (long long)(h + 2) * (w + 2); };
+  auto pool = [&](const __half* in, int C, int h, int w, __half* o) {
+    const long long total = (long long)(h / 2) * (w / 2) * (C / 8);
+    const int grid = (int)std::min<long long>((total + 255) / 256, 16LL * num_sms());
+    enc_pool_planes_kernel<<<grid, 256, 0, st>>>(in, in + (size_t)C * plane(h, w), C, h, w, o,
+                                                 o + (size_t)C * plane(h / 2, w / 2));
+    count_launch();
+  };
+  int rc;
+  {
+    const long long total = plane(H, W);
+    const int grid = (int)std::min<long long>((total + 255) / 256, 16LL * num_sms());
+    enc_conv1_planes_kernel<<<grid, 256, 0, st>>>(img, H, W, blob, P(T.p0), P(T.p0) + (size_t)8 * total);
+    count_launch();
+    CRNERF_CUDA(cudaGetLastError());
+  }
+  if ((rc = launch_conv<8, 64, kOutPlanes>(P(T.p0), wimg + first_image_offset(blob_off), blob + Blob::b2, nullptr,
+                                           P(T.a2), plane(H, W), H, W, st)))
+    return rc;
+  if ((rc = launch_conv<64, 64, kOutPlanes>(P(T.a2), wimg + L[0].offset, blob + Blob::b3, nullptr, P(T.a3), plane(H, W),
+                                            H, W, st)))
+    return rc;
+  pool(P(T.a3), 64, H, W, P(T.q3));
+  if ((rc = launch_conv<64, 128, kOutPlanes>(P(T.q3), wimg + L[1].offset, blob + Blob::b4, nullptr, P(T.a4),
+                                             plane(H2, W2), H2, W2, st)))
+    return rc;
+  if ((rc = launch_conv<128, 128, kOutPlanes>(P(T.a4), wimg + L[2].offset, blob + Blob::b5, nullptr, P(T.a5),
+                                              plane(H2, W2), H2, W2, st)))
+    return rc;
+  pool(P(T.a5), 128, H2, W2, P(T.q5));
+  float* F = reinterpret_cast<float*>(base + T.f);
+  if ((rc = launch_conv<128, 128, kOutRows>(P(T.q5), wimg + L[3].offset, blob + Blob::b6, F, nullptr, 0, H4, W4, st)))
+    return rc;
+  enc_tail_kernel<<<1024, 512, 0, st>>>(F, H4, W4, blob, out, reinterpret_cast<float*>(base + T.pooled));
+  count_launch();
+  CRNERF_CUDA(cudaGetLastError());
+  return CRNERF_OK;
+}
+
+// backward: grad_out (64,32,32) -> gradients of the 14 parameter tensors (torch layouts) and, optionally, of img
+int encoder_backward(const void* packed, const float* img, int H, int W, const float* out, const float* grad_out,
+                     const void* tape, float* const* gw, float* const* gb, float* grad_img, void* scratch,
+                     size_t scratch_bytes, cudaStream_t st) {
+  CRNERF_REQUIRE(packed && img && out && grad_out && tape && gw && gb && scratch, "null argument");
+  for (int i = 0; i < 7; ++i) CRNERF_REQUIRE(gw[i] && gb[i], "conv%d: null gradient buffer", i + 1);
+  CRNERF_REQUIRE(H >= 8 && W >= 8 && H <= 8192 && W <= 8192, "image %dx%d unsupported (8..8192 per side)", H, W);
+  const Tape T = tape_layout(H, W);
+  const BwdScratch S = bwd_layout(H, W);
+  CRNERF_REQUIRE(scratch_bytes >= S.total, "scratch too small");
+  CRNERF_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0 && (reinterpret_cast<uintptr_t>(tape) & 255) == 0,
+                 "scratch and tape must be 256-byte aligned");
+  TcLayer L[4];
+  size_t blob_off;
+  tc_layers(L, blob_off);
+  const uint8_t* wimg = static_cast<const uint8_t*>(packed);
+  const float* blob = reinterpret_cast<const float*>(wimg + blob_off);
+  const uint8_t* tb = static_cast<const uint8_t*>(tape);
+  uint8_t* sb = static_cast<uint8_t*>(scratch);
+  auto P = [&](size_t off) { return reinterpret_cast<const __half*>(tb + off); };
+  __half* Ga = reinterpret_cast<__half*>(sb + S.ga);
+  __half* Gb = reinterpret_cast<__half*>(sb + S.gb);
+  float* DX = reinterpret_cast<float*>(sb + S.dx);
+  float* part = reinterpret_cast<float*>(sb + S.part);
+  float* dpooled = reinterpret_cast<float*>(sb + S.dpooled);
+  float* dpre7 = reinterpret_cast<float*>(sb + S.dpre7);
+  float* dbpart = reinterpret_cast<float*>(sb + S.dbpart);
+  float* part2 = reinterpret_cast<float*>(sb + S.part2);
+  float* scales = reinterpret_cast<float*>(sb + S.small);           // [layer 1..7]
+  unsigned* maxbits = reinterpret_cast<unsigned*>(sb + S.small + 32);  // [stage]
+  const int H2 = H / 2, W2 = W / 2, H4 = H2 / 2, W4 = W2 / 2;
+  const float* F = reinterpret_cast<const float*>(tb + T.f);
+  const float* pooled = reinterpret_cast<const float*>(tb + T.pooled);
+  int rc;
+  CRNERF_CUDA(cudaMemsetAsync(sb + S.small, 0, 256, st));
+
+  // conv7 / pool tail
+  enc_tail_bwd_kernel<<<1024, 128, 0, st>>>(grad_out, out, blob, dpre7, dpooled, maxbits + 6);
+  enc_w7_grad_kernel<<<64, 128, 0, st>>>(dpre7, pooled, gw[6], gb[6]);
+  count_launch(2);
+  // dZ6 planes
+  {
+    auto ilog2c = [](int v) { int e = 0; while ((1 << e) < v) ++e; return e; };
+    const int fold = ilog2c((32 / H4 + 3) * (32 / W4 + 3));
+    const int Wg = grad_stride(W4);
+    CRNERF_CUDA(cudaMemsetAsync(Ga, 0, (size_t)2 * 128 * (H4 + 4) * Wg * sizeof(__half), st));
+    const int gx = (int)std::min<long long>(((long long)H4 * W4 + 255) / 256, kPrepBlocks);
+    enc_grad_top_kernel<<<dim3(gx, 16), 256, 0, st>>>(dpooled, F, H4, W4, Ga, Ga + (size_t)128 * (H4 + 4) * Wg, Wg,
+                                                      maxbits + 6, fold, scales + 6, dbpart);
+    enc_db_reduce_kernel<<<1, 128, 0, st>>>(dbpart, gx, 128, scales + 6, gb[5]);
+    count_launch(2);
+    CRNERF_CUDA(cudaGetLastError());
+  }
+  static const int stop = getenv("CRNERF_ENC_BWD_STOP") ? atoi(getenv("CRNERF_ENC_BWD_STOP")) : 0;   // debug: keep a stage's planes
+  if (stop == 1) return CRNERF_OK;
+  // conv6 (128 -> 128 at 1/4): input Q5
+  if ((rc = launch_wgrad<128, 128>(Ga, P(T.q5), H4, W4, part, scales + 6, gw[5], st))) return rc;
+  if ((rc = launch_conv<128, 128, kOutRaw>(Ga, wimg + dgrad_image_offset(blob_off, 3), blob + Blob::b6, DX, nullptr, 0,
+                                           H4 + 2, grad_stride(W4) - 2, st, maxbits + 5)))
+    return rc;
+  if ((rc = launch_prep(true, DX, 128, H4, W4, P(T.a5), H2, W2, Gb, maxbits + 5, scales + 6, scales + 5, dbpart, gb[4], st)))
+    return rc;
+  if (stop == 2) return CRNERF_OK;
+  // conv5 (128 -> 128 at 1/2): input A4
+  if ((rc = launch_wgrad<128, 128>(Gb, P(T.a4), H2, W2, part, scales + 5, gw[4], st))) return rc;
+  if ((rc = launch_conv<128, 128, kOutRaw>(Gb, wimg + dgrad_image_offset(blob_off, 2), blob + Blob::b5, DX, nullptr, 0,
+                                           H2 + 2, grad_stride(W2) - 2, st, maxbits + 4)))
+    return rc;
+  if ((rc = launch_prep(false, DX, 128, H2, W2, P(T.a4), H2, W2, Ga, maxbits + 4, scales + 5, scales + 4, dbpart, gb[3], st)))
+    return rc;
+  if (stop == 3) return CRNERF_OK;
+  // conv4 (64 -> 128 at 1/2): input Q3
+  if ((rc = launch_wgrad<64, 128>(Ga, P(T.q3), H2, W2, part, scales + 4, gw[3], st))) return rc;
+  if ((rc = launch_conv<128, 64, kOutRaw>(Ga, wimg + dgrad_image_offset(blob_off, 1), blob + Blob::b3, DX, nullptr, 0,
+                                          H2 + 2, grad_stride(W2) - 2, st, maxbits + 3)))
+    return rc;
+  if ((rc = launch_prep(true, DX, 64, H2, W2, P(T.a3), H, W, Gb, maxbits + 3, scales + 4, scales + 3, dbpart, gb[2], st)))
+    return rc;
+  if (stop == 4) return CRNERF_OK;
+  // conv3 (64 -> 64 at full resolution): input A2
+  if ((rc = launch_wgrad<64, 64>(Gb, P(T.a2), H, W, part, scales + 3, gw[2], st))) return rc;
+  if ((rc = launch_conv<64, 64, kOutRaw>(Gb, wimg + dgrad_image_offset(blob_off, 0), blob + Blob::b3, DX, nullptr, 0,
+                                         H + 2, grad_stride(W) - 2, st, maxbits + 2)))
+    return rc;
+  if ((rc = launch_prep(false, DX, 64, H, W, P(T.a2), H, W, Ga, maxbits + 2, scales + 3, scales + 2, dbpart, gb[1], st)))
+    return rc;
+  // conv2 (3 -> 64) and conv1 (1x1) on the CUDA cores
+  {
+    const int Wg = grad_stride(W);
+    const long long g_plane = (long long)(H + 4) * Wg;
+    const __half* p0 = P(T.p0);
+    const int nseg = H * ((W + kFwSeg - 1) / kFwSeg);
+    const int g1 = std::min(nseg, kFirstBlocks);
+    enc_first_wgrad_kernel<<<g1, 256, 0, st>>>(Ga, Ga + (size_t)64 * g_plane, g_plane, Wg, p0,
+                                               p0 + (size_t)8 * (H + 2) * (W + 2), H, W, part);
+    enc_part_reduce_kernel<<<(1728 + 127) / 128, 128, 0, st>>>(part, g1, 1728, 0, 1728, scales + 2, gw[1]);
+    const int g2 = (int)std::min<long long>(((long long)H * W + 255) / 256, kFirstBlocks);
+    enc_first_dgrad_kernel<<<g2, 256, 0, st>>>(Ga, Ga + (size_t)64 * g_plane, g_plane, Wg, blob, img, H, W,
+                                               scales + 2, part2, grad_img);
+    enc_part_reduce_kernel<<<1, 32, 0, st>>>(part2, g2, 12, 0, 9, scales + 2, gw[0]);
+    enc_part_reduce_kernel<<<1, 32, 0, st>>>(part2, g2, 12, 9, 3, scales + 2, gb[0]);
+    count_launch(5);
+    CRNERF_CUDA(cudaGetLastError());
+  }
   return CRNERF_OK;
 }
 

@@ -209,6 +209,9 @@ class encoder_sameoutputsize(nn.Module):
         # results to 1e-4; default) or "tf32" (cuDNN's default path, what the reference itself gets on
         # a GPU: ~3e-3 relative, about 3x faster at photo sizes - tools/bench_train_full.py)
         self.conv_precision = "fp32"
+        # under autograd: "native" = csrc/encoder.cu forward + csrc/encoder_train.cuh backward (no library
+        # convolution); "library" = differentiable torch ops at ``conv_precision`` (kept for A/B checks)
+        self.train_backend = "native"
 
     def _convs(self):
         return [self.conv1, self.conv2, self.conv3, self.conv4, self.conv5, self.conv6, self.conv7]
@@ -226,8 +229,14 @@ class encoder_sameoutputsize(nn.Module):
         if x.is_cuda and self.conv7.out_channels == 64 and not _wants_grad(self, x) and x.shape[0] == 1 \
                 and min(x.shape[2:]) >= 8:
             return ops.encoder_forward(self.packed(), x)
+        if x.is_cuda and torch.is_grad_enabled() and self.train_backend == "native" \
+                and self.conv7.out_channels == 64 and x.shape[0] == 1 and min(x.shape[2:]) >= 8:
+            # training step: the inference kernels forward (activation planes kept), csrc/encoder_train.cuh backward
+            from crnerf_b200.autograd import EncoderFn
+            self._packed = None    # weights move every step, and p.data updates do not bump _version: always re-pack
+            return EncoderFn.apply(self.packed(), x, *[p for c in self._convs() for p in (c.weight, c.bias)])
         if x.is_cuda and torch.is_grad_enabled() and self.conv_precision == "fp32":
-            # training step: library convolutions, fp32 in forward and backward (scoped, not global)
+            # library convolutions, fp32 in forward and backward (scoped, not global)
             from crnerf_b200.autograd import Fp32Region
             return Fp32Region.apply(self._stack, x, *self.parameters())
         return self._stack(x)

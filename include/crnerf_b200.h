@@ -430,6 +430,26 @@ size_t crnerf_encoder_scratch_bytes(int height, int width);
 int crnerf_encoder_forward(const void* packed, const float* img, int height, int width, float* out,
                            void* scratch, size_t scratch_bytes, void* stream);
 
+/* Training step (train_mask_grid_sample.py back-propagates through enc_a every step; the module under
+ * autograd, models/linearStyleTransfer.py:250-276).  forward_train = the same kernels, every layer's
+ * activation planes kept in `tape` (crnerf_encoder_tape_bytes, 256-byte aligned); backward = input-
+ * gradient convolutions on the forward's tensor-core kernel (flipped weight images inside `packed`),
+ * weight gradients as tcgen05 GEMMs with K = pixels, fixed-order reductions (deterministic), no library
+ * convolution.  grad_out (64,32,32); grads.weight[i] / grads.bias[i] receive the gradients of
+ * conv{i+1} in the state_dict layouts (overwritten, not accumulated); grad_img (3,H,W) or NULL.
+ * `packed` must be the image of the weights the forward ran with. */
+typedef struct {
+  float* weight[7];
+  float* bias[7];
+} crnerf_encoder_grads;
+size_t crnerf_encoder_tape_bytes(int height, int width);
+size_t crnerf_encoder_backward_scratch_bytes(int height, int width);
+int crnerf_encoder_forward_train(const void* packed, const float* img, int height, int width, float* out,
+                                 void* tape, size_t tape_bytes, void* stream);
+int crnerf_encoder_backward(const void* packed, const float* img, int height, int width, const float* out,
+                            const float* grad_out, const void* tape, const crnerf_encoder_grads* grads,
+                            float* grad_img, void* scratch, size_t scratch_bytes, void* stream);
+
 /* debug (tests only): dump the post-activation values of `layer` (0..10) for every
  * point of later fused launches into dbg_buf (n_points x 256 floats); NULL disables. */
 int crnerf_debug_set(float* dbg_buf, int layer);

@@ -51,7 +51,7 @@ def test_encoder_vs_oracle_shapes(hw):
     assert torch.allclose(got.cpu(), want, rtol=1e-4, atol=1e-5), float(err)
 
 
-def test_encoder_repacks_after_update_and_trains_on_library_path():
+def test_encoder_repacks_after_update_and_trains_on_either_path():
     from crnerf_b200 import ops
     enc = _encoder(5).to(DEV)
     x = torch.rand(1, 3, 32, 32, device=DEV)
@@ -64,9 +64,16 @@ def test_encoder_repacks_after_update_and_trains_on_library_path():
         want = oracle.encoder_forward({k: v.cpu() for k, v in state(enc).items()}, x.cpu())
     assert torch.allclose(b.cpu(), want, rtol=1e-4, atol=1e-5)
     n0 = ops.launch_count()
-    out = enc(x)                      # autograd on: differentiable library ops
+    out = enc(x)                      # autograd on: the native training path (tests/test_gpu_encoder_backward.py)
     out.mean().backward()
-    assert ops.launch_count() == n0 and enc.conv3.weight.grad is not None
+    assert ops.launch_count() > n0 and enc.conv3.weight.grad is not None
+    native = enc.conv3.weight.grad.clone()
+    enc.zero_grad()
+    enc.train_backend = "library"     # differentiable library ops, kept for A/B checks
+    n0 = ops.launch_count()
+    enc(x).mean().backward()
+    assert ops.launch_count() == n0
+    assert torch.allclose(native, enc.conv3.weight.grad, rtol=1e-3, atol=1e-7)
 
 
 def test_encoder_full_frame_and_strided_input():
