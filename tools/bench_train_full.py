@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--graph", action="store_true", help="also time the step captured as ONE CUDA graph (GraphedTrainStep)")
     ap.add_argument("--profile", action="store_true", help="print the top CUDA kernels of one step (torch profiler)")
     ap.add_argument("--conv", default="fp32", choices=["fp32", "tf32"], help="precision of the library convolutions")
+    ap.add_argument("--encoder", default="native", choices=["native", "library"],
+                    help="enc_a under autograd: csrc/encoder.cu + encoder_train.cuh, or library convolutions")
     a = ap.parse_args()
     import _training_step_driver as drv
     from models.nerf import NeRF_sigma, PosEmbedding
@@ -42,6 +44,7 @@ def main():
     mask_net = Context_Guided_Network(classes=1, M=2, N=2, input_channel=3)
     mods = [enc_a, coarse, decoder, fine, mask_net]
     enc_a.conv_precision = mask_net.conv_precision = a.conv
+    enc_a.train_backend = a.encoder
     for m in mods:
         m.to(dev).train()
     models = {"coarse": coarse, "decoder": decoder, "fine": fine}
@@ -162,7 +165,7 @@ def main():
             print(f"{e.device_time_total / 1e3:8.3f} ms  x{e.count:<4d} {e.key[:110]}", file=sys.stderr)
     print(json.dumps({"workload": f"whole training step, photo {H}x{W}, 1024-ray patch x (64+64), perturb=noise=1, "
                                   "enc_a + mask network + render + decode x3 + CRNeRFLoss + Adam",
-                      "library_conv_precision": a.conv, "ms_per_step": ms, "ms_per_step_graphed": graph_ms, "phases_ms": {k: v / a.steps for k, v in acc.items()}}))
+                      "library_conv_precision": a.conv, "encoder": a.encoder, "ms_per_step": ms, "ms_per_step_graphed": graph_ms, "phases_ms": {k: v / a.steps for k, v in acc.items()}}))
 
 
 if __name__ == "__main__":
