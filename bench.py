@@ -388,6 +388,36 @@ def train_leg(dev, world, rank, barrier, reps=10, warm=3):
         return {"train_error": f"{type(e).__name__}: {e}"}
 
 
+def encoder_train_leg(dev, reps=10, warm=3):
+    """SURVEY 8f-1 under autograd: forward + backward of enc_a on a 340x512 photo (the training step's
+    per-step encoder call), native kernels, CUDA events; the same module on library convolutions in fp32
+    beside it."""
+    try:
+        import torch
+        from models.linearStyleTransfer import encoder_sameoutputsize
+        torch.manual_seed(0)
+        enc = encoder_sameoutputsize(64).to(dev).train()
+        x = torch.rand(1, 3, 340, 512, device=dev)
+        g = torch.randn(1, 64, 32, 32, device=dev)
+        out = {}
+        for name in ("native", "library"):
+            enc.train_backend = name
+            for i in range(warm + reps):
+                if i == warm:
+                    torch.cuda.synchronize(dev)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                enc.zero_grad(set_to_none=True)
+                enc(x).backward(g)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            out[name] = e0.elapsed_time(e1) / reps
+        return {"encoder_train": {"workload": "encoder_sameoutputsize forward + backward, 340x512 photo",
+                                  "ms_native": out["native"], "ms_library_fp32": out["library"]}}
+    except Exception as e:   # noqa: BLE001  (an extra leg must not take the headline down)
+        return {"encoder_train_error": f"{type(e).__name__}: {e}"}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from models.nerf import PosEmbedding
@@ -667,6 +697,8 @@ def run_ours(args):
         extra.update(frame_leg(models_gpu, emb, margs, dev, world, rank, barrier))
     if not args.no_train:
         extra.update(train_leg(dev, world, rank, barrier))
+        if rank == 0 and world == 1:
+            extra.update(encoder_train_leg(dev))
 
     if rank == 0:
         line = {

@@ -1,5 +1,6 @@
 // encoder_sameoutputsize.forward (reference models/linearStyleTransfer.py:208-276; SURVEY.md 8f
-// rank 1): the style/content encoder enc_a / enc_cont, inference only.
+// rank 1): the style/content encoder enc_a / enc_cont.  Inference below; the training step's forward and
+// backward at the end of the file (kernels: encoder_train.cuh).
 //
 //   conv1 1x1 3->3 . reflect-pad                                         enc_conv1_planes_kernel (fp32)
 //   conv2 3x3 3->64 . LeakyReLU                                          enc_conv_tc_kernel<8, 64> (two taps per K = 16 step)

@@ -175,10 +175,11 @@ class encoder_sameoutputsize(nn.Module):
     reflection-padded 3x3 convs with LeakyReLU(0.2), two 2x2 max-pools, adaptive
     average pool to 32x32 and a 1x1 conv.
 
-    Inference (no autograd, CUDA input, ``out_channel == 64``) runs csrc/encoder.cu:
-    the 3x3 convolutions as tcgen05 implicit GEMMs with fp16 hi/lo split operands
-    (fp32-class accuracy).  Under autograd - the training step back-propagates through
-    ``enc_a`` / ``enc_cont`` - it runs as differentiable library ops."""
+    CUDA input, batch 1, ``out_channel == 64``: csrc/encoder.cu - the 3x3 convolutions as tcgen05
+    implicit GEMMs with fp16 hi/lo split operands (fp32-class accuracy).  Under autograd (the training
+    step back-propagates through ``enc_a``) the same kernels run with the activation planes kept and
+    csrc/encoder_train.cuh computes the gradients (``crnerf_b200.autograd.EncoderFn``);
+    ``train_backend = "library"`` selects differentiable library ops instead."""
 
     def __init__(self, out_channel=64):
         super(encoder_sameoutputsize, self).__init__()
