@@ -756,7 +756,7 @@ BwdScratch bwd_layout(int H, int W) {
   s.part = o; o += align256(std::max((size_t)148 * 3 * 128 * 128, (size_t)kFirstBlocks * 1728) * sizeof(float));
   s.dpooled = o; o += align256((size_t)1024 * 128 * sizeof(float));
   s.dpre7 = o; o += align256((size_t)1024 * 64 * sizeof(float));
-  s.dbpart = o; o += align256((size_t)16 * kPrepBlocks * 8 * sizeof(float));
+  s.dbpart = o; o += align256((size_t)16 * 4 * kPrepBlocks * 8 * sizeof(float));
   s.part2 = o; o += align256((size_t)kFirstBlocks * 12 * sizeof(float));
   s.small = o; o += 256;                       // scales[8] floats | maxbits[8]
   s.total = o;
@@ -802,11 +802,11 @@ int launch_prep(bool pool, const float* dx, int C, int hq, int wq, const __half*
   a.scale_out = scale_out;
   a.db_part = dbpart;
   CRNERF_CUDA(cudaMemsetAsync(G, 0, (size_t)2 * C * (H + 4) * a.Wg * sizeof(__half), st));
-  const int gx = (int)std::min<long long>(((long long)hq * wq + 255) / 256, kPrepBlocks);
-  const dim3 grid(gx, C / 8);
-  if (pool) enc_grad_prep_kernel<true><<<grid, 256, 0, st>>>(a);
-  else enc_grad_prep_kernel<false><<<grid, 256, 0, st>>>(a);
-  enc_db_reduce_kernel<<<(C + 127) / 128, 128, 0, st>>>(dbpart, gx, C, scale_out, gb);
+  const int gx = pool ? (int)std::min<long long>(((long long)hq * wq + 255) / 256, kPrepBlocks)
+                      : (int)std::min<long long>(((long long)hq * wq * (C / 8) + 255) / 256, 4 * kPrepBlocks);
+  if (pool) enc_grad_prep_kernel<true><<<dim3(gx, C / 8), 256, 0, st>>>(a);
+  else enc_grad_prep_kernel<false><<<gx, 256, 0, st>>>(a);
+  enc_db_reduce_kernel<<<(C * 32 + 255) / 256, 256, 0, st>>>(dbpart, gx, C, scale_out, gb);
   count_launch(2);
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;
@@ -911,7 +911,7 @@ int encoder_backward(const void* packed, const float* img, int H, int W, const f
 
   // conv7 / pool tail
   enc_tail_bwd_kernel<<<1024, 128, 0, st>>>(grad_out, out, blob, dpre7, dpooled, maxbits + 6);
-  enc_w7_grad_kernel<<<64, 128, 0, st>>>(dpre7, pooled, gw[6], gb[6]);
+  enc_w7_grad_kernel<<<64, 1024, 0, st>>>(dpre7, pooled, gw[6], gb[6]);
   count_launch(2);
   // dZ6 planes
   {
@@ -922,7 +922,7 @@ int encoder_backward(const void* packed, const float* img, int H, int W, const f
     const int gx = (int)std::min<long long>(((long long)H4 * W4 + 255) / 256, kPrepBlocks);
     enc_grad_top_kernel<<<dim3(gx, 16), 256, 0, st>>>(dpooled, F, H4, W4, Ga, Ga + (size_t)128 * (H4 + 4) * Wg, Wg,
                                                       maxbits + 6, fold, scales + 6, dbpart);
-    enc_db_reduce_kernel<<<1, 128, 0, st>>>(dbpart, gx, 128, scales + 6, gb[5]);
+    enc_db_reduce_kernel<<<16, 256, 0, st>>>(dbpart, gx, 128, scales + 6, gb[5]);
     count_launch(2);
     CRNERF_CUDA(cudaGetLastError());
   }
@@ -968,13 +968,17 @@ int encoder_backward(const void* packed, const float* img, int H, int W, const f
     const int g1 = std::min(nseg, kFirstBlocks);
     enc_first_wgrad_kernel<<<g1, 256, 0, st>>>(Ga, Ga + (size_t)64 * g_plane, g_plane, Wg, p0,
                                                p0 + (size_t)8 * (H + 2) * (W + 2), H, W, part);
-    enc_part_reduce_kernel<<<(1728 + 127) / 128, 128, 0, st>>>(part, g1, 1728, 0, 1728, scales + 2, gw[1]);
+    enc_part_reduce_kernel<<<1728 / 8, 256, 0, st>>>(part, g1, 1728, 0, 1728, scales + 2, gw[1]);
+    // conv2's input gradient at every padded position (fp32, in the rows buffer), then fold + conv1
+    float4* dp0 = reinterpret_cast<float4*>(DX);
+    const long long quads = (long long)(H + 2) * ((W + 2 + 3) / 4);
+    enc_first_dgrad_kernel<<<(int)std::min<long long>((quads + 127) / 128, 8LL * num_sms()), 128, 0, st>>>(
+        Ga, Ga + (size_t)64 * g_plane, g_plane, Wg, blob, H, W, dp0);
     const int g2 = (int)std::min<long long>(((long long)H * W + 255) / 256, kFirstBlocks);
-    enc_first_dgrad_kernel<<<g2, 256, 0, st>>>(Ga, Ga + (size_t)64 * g_plane, g_plane, Wg, blob, img, H, W,
-                                               scales + 2, part2, grad_img);
-    enc_part_reduce_kernel<<<1, 32, 0, st>>>(part2, g2, 12, 0, 9, scales + 2, gw[0]);
-    enc_part_reduce_kernel<<<1, 32, 0, st>>>(part2, g2, 12, 9, 3, scales + 2, gb[0]);
-    count_launch(5);
+    enc_first_finish_kernel<<<g2, 256, 0, st>>>(dp0, blob, img, H, W, scales + 2, part2, grad_img);
+    enc_part_reduce_kernel<<<2, 256, 0, st>>>(part2, g2, 12, 0, 9, scales + 2, gw[0]);
+    enc_part_reduce_kernel<<<1, 256, 0, st>>>(part2, g2, 12, 9, 3, scales + 2, gb[0]);
+    count_launch(6);
     CRNERF_CUDA(cudaGetLastError());
   }
   return CRNERF_OK;

@@ -154,27 +154,32 @@ enc_tail_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ o
   for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((t & 31) == 0 && m > 0.f) atomicMax(maxbits, __float_as_uint(m));
 }
-// dW7[co][k] = sum_bin dpre7[bin][co] pooled[bin][k], db7[co] = sum_bin dpre7[bin][co]; one block per co
-__global__ void __launch_bounds__(128)
+// dW7[co][k] = sum_bin dpre7[bin][co] pooled[bin][k], db7[co] = sum_bin dpre7[bin][co]; one block per co,
+// 8 groups of 128 bins each, combined in group order
+__global__ void __launch_bounds__(1024)
 enc_w7_grad_kernel(const float* __restrict__ dpre7, const float* __restrict__ pooled, float* __restrict__ gw7,
                    float* __restrict__ gb7) {
   __shared__ float d[1024];
-  __shared__ float red[128];
-  const int co = blockIdx.x, t = threadIdx.x;
-  float bs = 0.f;
-  for (int b = t; b < 1024; b += 128) {
-    d[b] = dpre7[(size_t)b * 64 + co];
-    bs += d[b];
-  }
-  red[t] = bs;
+  __shared__ float red[8][128];
+  const int co = blockIdx.x, t = threadIdx.x, k = t & 127, grp = t >> 7;
+  d[t] = dpre7[(size_t)t * 64 + co];
   __syncthreads();
   float s = 0.f;
-  for (int b = 0; b < 1024; ++b) s = fmaf(d[b], pooled[(size_t)b * 128 + t], s);
-  gw7[(size_t)co * 128 + t] = s;
-  if (t == 0) {
+  for (int b = grp * 128; b < grp * 128 + 128; ++b) s = fmaf(d[b], pooled[(size_t)b * 128 + k], s);
+  red[grp][k] = s;
+  __syncthreads();
+  if (t < 128) {
     float a = 0.f;
-    for (int i = 0; i < 128; ++i) a += red[i];
-    gb7[co] = a;
+#pragma unroll
+    for (int g2 = 0; g2 < 8; ++g2) a += red[g2][t];
+    gw7[(size_t)co * 128 + t] = a;
+  } else if (t < 160) {
+    const int lane = t & 31;
+    float a = 0.f;
+    for (int b = lane; b < 1024; b += 32) a += d[b];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) gb7[co] = a;
   }
 }
 
@@ -241,18 +246,24 @@ struct PrepArgs {
   float* scale_out;
   float* db_part;       // [C/8][gridDim.x][8] per-block bias-gradient partials (scaled)
 };
+// Thread mapping by what dominates the traffic.  No pool: thread = (pixel, channel chunk), chunk fastest - a pixel's
+// fp32 row of dx is one contiguous run over C/8 neighbouring lanes (grid 1-D).  Pool: the 4 + 4 plane reads and 8
+// plane writes dominate - blockIdx.y = chunk, lanes = consecutive pixels, so every plane access of a warp is one
+// contiguous run.
 template <bool kPool>
 __global__ void __launch_bounds__(256) enc_grad_prep_kernel(const PrepArgs a) {
-  __shared__ float sh[8][8];
-  const int chunk = blockIdx.y;
+  __shared__ float sh[8][16][8];
+  const int nch = kPool ? 1 : a.C >> 3;           // chunks interleaved in the thread index (8 or 16: divides the strides)
+  const int chunk = kPool ? (int)blockIdx.y : (int)(threadIdx.x & (nch - 1));
   const float sc_in = *a.scale_in;
   const float r = stage_rescale(*a.maxbits_in, 2, sc_in);   // a fold sums at most 4 entries
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.scale_out = sc_in * r;
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const long long total = (long long)a.hq * a.wq;
+  const long long total = (long long)a.hq * a.wq * nch;
   const uint4* ah = reinterpret_cast<const uint4*>(a.act_hi);
   const uint4* al = reinterpret_cast<const uint4*>(a.act_lo);
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const long long p = q / nch;
     const int yq = (int)(p / a.wq), xq = (int)(p - (long long)yq * a.wq);
     // reflection pad 1: padded row 0 mirrors interior row 1, padded row hq + 1 mirrors row hq - 2
     int ys[3], xs[3], ny = 1, nx = 1;
@@ -301,40 +312,67 @@ __global__ void __launch_bounds__(256) enc_grad_prep_kernel(const PrepArgs a) {
         const float gv = d[j] * (fw > 0.f ? 1.f : kSlope) * r;
         s[j] += gv;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) g[q][j] = q == k ? gv : 0.f;
+        for (int q2 = 0; q2 < 4; ++q2) g[q2][j] = q2 == k ? gv : 0.f;
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q2 = 0; q2 < 4; ++q2) {
         uint4 gh, gl;
-        split8(g[q], gh, gl);
-        const size_t o = (((size_t)chunk * (a.H + 4) + 2 * yq + (q >> 1) + 2) * a.Wg + 2 * xq + (q & 1) + 2) * 8;
+        split8(g[q2], gh, gl);
+        const size_t o = (((size_t)chunk * (a.H + 4) + 2 * yq + (q2 >> 1) + 2) * a.Wg + 2 * xq + (q2 & 1) + 2) * 8;
         *reinterpret_cast<uint4*>(a.g_hi + o) = gh;
         *reinterpret_cast<uint4*>(a.g_lo + o) = gl;
       }
     }
   }
-  const float t = block_sum8(s, sh);
-  if (threadIdx.x < 8) a.db_part[((size_t)chunk * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = t;
+  // bias-gradient partials: lanes of equal chunk first (fixed order), then the 8 warps
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s[j] += __shfl_xor_sync(0xffffffffu, s[j], 16);
+    if (nch <= 8) s[j] += __shfl_xor_sync(0xffffffffu, s[j], 8);
+    if (nch == 1) {
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], 4);
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], 2);
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], 1);
+    }
+  }
+  if (lane < nch) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[warp][lane][j] = s[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < nch * 8) {
+    const int c = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += sh[w][c][j];
+    a.db_part[((size_t)(kPool ? chunk : c) * gridDim.x + blockIdx.x) * 8 + j] = t;
+  }
 }
 
-// bias gradient: db[c] = (1 / scale) * sum over blocks, block order
-__global__ void enc_db_reduce_kernel(const float* __restrict__ part, int nblk, int C, const float* __restrict__ scale,
-                                     float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// bias gradient: db[c] = (1 / scale) * sum over blocks; one warp per channel, fixed order
+__global__ void __launch_bounds__(256)
+enc_db_reduce_kernel(const float* __restrict__ part, int nblk, int C, const float* __restrict__ scale,
+                     float* __restrict__ out) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   const float* p = part + (size_t)(c >> 3) * nblk * 8 + (c & 7);
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += p[(size_t)b * 8];
-  out[c] = s / *scale;
+  for (int b = lane; b < nblk; b += 32) s += p[(size_t)b * 8];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[c] = s / *scale;
 }
-// generic: out[i] = (1 / scale) * sum_b part[b * row_stride + offset + i]
-__global__ void enc_part_reduce_kernel(const float* __restrict__ part, int nblk, int row_stride, int offset, int n,
-                                       const float* __restrict__ scale, float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// generic: out[i] = (1 / scale) * sum_b part[b * row_stride + offset + i]; one warp per output, fixed order
+__global__ void __launch_bounds__(256)
+enc_part_reduce_kernel(const float* __restrict__ part, int nblk, int row_stride, int offset, int n,
+                       const float* __restrict__ scale, float* __restrict__ out) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n) return;
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += part[(size_t)b * row_stride + offset + i];
-  out[i] = s / *scale;
+  for (int b = lane; b < nblk; b += 32) s += part[(size_t)b * row_stride + offset + i];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[i] = s / *scale;
 }
 
 // ---- weight gradient of a 3x3 convolution on the tensor cores ---------------------------------------
@@ -511,17 +549,19 @@ enc_wgrad_reduce_kernel(const float* __restrict__ part, int ncta, const float* _
 }
 
 // ---- conv2 (3 -> 64) weight gradient on the CUDA cores (N = 27 is no tensor-core shape) --------------
-// block: 64-pixel row segments; thread (co = t & 63, part = t >> 6) accumulates 7 of the 27 (ci, tap) pairs
+// block: 64-pixel row segments; lane = one of the 27 (ci, tap) pairs (5 lanes idle), warp = 8 output channels:
+// per pixel a thread reads its input value once and the warp's 8 gradient values as two broadcast vectors.
+// part: [gridDim.x][64 * 27]
 constexpr int kFwSeg = 64;
 __global__ void __launch_bounds__(256)
 enc_first_wgrad_kernel(const __half* __restrict__ g_hi, const __half* __restrict__ g_lo, long long g_plane, int Wg,
                        const __half* __restrict__ p_hi, const __half* __restrict__ p_lo, int H, int W,
                        float* __restrict__ part) {
-  __shared__ float g_s[64][kFwSeg + 1];
-  __shared__ float p_s[3][3][kFwSeg + 2];
-  const int t = threadIdx.x, co = t & 63, pr = t >> 6;
-  const int c_lo = pr * 7, c_n = min(27, c_lo + 7) - c_lo;
-  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  __shared__ __align__(16) float g_s[kFwSeg][68];       // [pixel][co]; 68: consecutive pixels' 16-byte stores hit distinct banks
+  __shared__ float p_s[3][3][kFwSeg + 2];               // [ci][row][pixel]
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int cc = min(lane, 26), ci = cc / 9, tap = cc - ci * 9, ky = tap / 3, kx = tap - ky * 3;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int nseg_row = (W + kFwSeg - 1) / kFwSeg, nseg = H * nseg_row, Wp = W + 2;
   const uint4* gh = reinterpret_cast<const uint4*>(g_hi);
   const uint4* gl = reinterpret_cast<const uint4*>(g_lo);
@@ -537,8 +577,8 @@ enc_first_wgrad_kernel(const __half* __restrict__ g_hi, const __half* __restrict
         const size_t o = (size_t)ch * g_plane + (size_t)(y + 2) * Wg + sx + 2 + px;
         unpack8(gh[o], gl[o], f);
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g_s[ch * 8 + j][px] = f[j];
+      *reinterpret_cast<float4*>(&g_s[px][ch * 8]) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(&g_s[px][ch * 8 + 4]) = make_float4(f[4], f[5], f[6], f[7]);
     }
     for (int i = t; i < 3 * (kFwSeg + 2); i += 256) {
       const int px = i % (kFwSeg + 2), r = i / (kFwSeg + 2);
@@ -552,31 +592,29 @@ enc_first_wgrad_kernel(const __half* __restrict__ g_hi, const __half* __restrict
       p_s[2][r][px] = f[2];
     }
     __syncthreads();
+    const float* pp = &p_s[ci][ky][kx];
+#pragma unroll 4
     for (int p = 0; p < valid; ++p) {
-      const float g = g_s[co][p];
-#pragma unroll
-      for (int c = 0; c < 7; ++c) {
-        if (c < c_n) {
-          const int cc = c_lo + c, ci = cc / 9, tap = cc - ci * 9, ky = tap / 3, kx = tap - ky * 3;
-          acc[c] = fmaf(g, p_s[ci][ky][p + kx], acc[c]);
-        }
-      }
+      const float x = pp[p];
+      const float4 a = *reinterpret_cast<const float4*>(&g_s[p][warp * 8]);
+      const float4 b = *reinterpret_cast<const float4*>(&g_s[p][warp * 8 + 4]);
+      acc[0] = fmaf(a.x, x, acc[0]); acc[1] = fmaf(a.y, x, acc[1]); acc[2] = fmaf(a.z, x, acc[2]); acc[3] = fmaf(a.w, x, acc[3]);
+      acc[4] = fmaf(b.x, x, acc[4]); acc[5] = fmaf(b.y, x, acc[5]); acc[6] = fmaf(b.z, x, acc[6]); acc[7] = fmaf(b.w, x, acc[7]);
     }
   }
+  if (lane < 27) {
 #pragma unroll
-  for (int c = 0; c < 7; ++c)
-    if (c < c_n) part[(size_t)blockIdx.x * 1728 + co * 27 + c_lo + c] = acc[c];
+    for (int j = 0; j < 8; ++j) part[(size_t)blockIdx.x * 1728 + (warp * 8 + j) * 27 + lane] = acc[j];
+  }
 }
 
-// ---- conv2 input gradient (64 -> 3) . fold . conv1 (1x1) gradients, one thread per pixel ---------------
-// part: [gridDim.x][12] = dW1 (9, scaled) | db1 (3, scaled); gimg (3, H, W) optional, unscaled
-__global__ void __launch_bounds__(256)
+// ---- conv2 input gradient (64 -> 3) at every PADDED position, four horizontally adjacent ones per thread ---
+// dp0: [(H + 2)][(W + 2)] float4 (3 used), x scale
+__global__ void __launch_bounds__(128)
 enc_first_dgrad_kernel(const __half* __restrict__ g_hi, const __half* __restrict__ g_lo, long long g_plane, int Wg,
-                       const float* __restrict__ blob, const float* __restrict__ img, int H, int W,
-                       const float* __restrict__ scale, float* __restrict__ part, float* __restrict__ gimg) {
+                       const float* __restrict__ blob, int H, int W, float4* __restrict__ dp0) {
   __shared__ float4 w_s[9][64];       // [tap][co] -> (ci 0, 1, 2, -)
-  __shared__ float red[8][12];
-  for (int i = threadIdx.x; i < 9 * 64; i += 256) {
+  for (int i = threadIdx.x; i < 9 * 64; i += 128) {
     const int tap = i / 64, co = i % 64;
     const float* w2t = blob + Blob::w2t;    // [ci * 9 + tap][co]
     w_s[tap][co] = make_float4(w2t[(0 * 9 + tap) * 64 + co], w2t[(1 * 9 + tap) * 64 + co], w2t[(2 * 9 + tap) * 64 + co], 0.f);
@@ -584,10 +622,56 @@ enc_first_dgrad_kernel(const __half* __restrict__ g_hi, const __half* __restrict
   __syncthreads();
   const uint4* gh = reinterpret_cast<const uint4*>(g_hi);
   const uint4* gl = reinterpret_cast<const uint4*>(g_lo);
+  const int Wp = W + 2, nq = (Wp + 3) / 4;
+  const long long total = (long long)(H + 2) * nq;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const int yp = (int)(q / nq), xp0 = (int)(q - (long long)yp * nq) * 4;
+    float d[4][3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i][0] = d[i][1] = d[i][2] = 0.f;
+    // padded input (yp, xp) receives dZ2 at (yp - ky, xp - kx): gradient-plane position (yp - ky + 2, xp - kx + 2)
+#pragma unroll 1
+    for (int ky = 0; ky < 3; ++ky) {
+      const size_t row = (size_t)(yp - ky + 2) * Wg + xp0;
+#pragma unroll 1
+      for (int ch = 0; ch < 8; ++ch) {
+        float f[6][8];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) unpack8(gh[(size_t)ch * g_plane + row + c], gl[(size_t)ch * g_plane + row + c], f[c]);
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 w = w_s[ky * 3 + kx][ch * 8 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float g = f[i - kx + 2][j];
+              d[i][0] = fmaf(g, w.x, d[i][0]);
+              d[i][1] = fmaf(g, w.y, d[i][1]);
+              d[i][2] = fmaf(g, w.z, d[i][2]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (xp0 + i < Wp) dp0[(size_t)yp * Wp + xp0 + i] = make_float4(d[i][0], d[i][1], d[i][2], 0.f);
+  }
+}
+
+// ---- fold of dp0 . conv1 (1x1) gradients, one thread per pixel -----------------------------------------
+// part: [gridDim.x][12] = dW1 (9, scaled) | db1 (3, scaled); gimg (3, H, W) optional, unscaled
+__global__ void __launch_bounds__(256)
+enc_first_finish_kernel(const float4* __restrict__ dp0, const float* __restrict__ blob, const float* __restrict__ img,
+                        int H, int W, const float* __restrict__ scale, float* __restrict__ part,
+                        float* __restrict__ gimg) {
+  __shared__ float red[8][12];
   float s[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const float inv = 1.f / *scale;
   const float* w1 = blob + Blob::w1;
   const long long total = (long long)H * W;
+  const int Wp = W + 2;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
     const int y = (int)(p / W), x = (int)(p - (long long)y * W);
     int ys[3], xs[3], ny = 1, nx = 1;
@@ -600,24 +684,10 @@ enc_first_dgrad_kernel(const __half* __restrict__ g_hi, const __half* __restrict
     float d0 = 0.f, d1 = 0.f, d2 = 0.f;
     for (int iy = 0; iy < ny; ++iy)
       for (int ix = 0; ix < nx; ++ix) {
-        const int yp = ys[iy], xp = xs[ix];
-#pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          const int ky = tap / 3, kx = tap - ky * 3;
-          const size_t o = (size_t)(yp - ky + 2) * Wg + (xp - kx + 2);
-#pragma unroll 2
-          for (int ch = 0; ch < 8; ++ch) {
-            float f[8];
-            unpack8(gh[(size_t)ch * g_plane + o], gl[(size_t)ch * g_plane + o], f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 w = w_s[tap][ch * 8 + j];
-              d0 = fmaf(f[j], w.x, d0);
-              d1 = fmaf(f[j], w.y, d1);
-              d2 = fmaf(f[j], w.z, d2);
-            }
-          }
-        }
+        const float4 v = dp0[(size_t)ys[iy] * Wp + xs[ix]];
+        d0 += v.x;
+        d1 += v.y;
+        d2 += v.z;
       }
     const float v0 = img[p], v1 = img[total + p], v2 = img[2 * total + p];
     s[0] += d0 * v0; s[1] += d0 * v1; s[2] += d0 * v2;

@@ -82,7 +82,7 @@ def _rel(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-300))
 
 
-@pytest.mark.parametrize("hw", [(8, 8), (36, 52), (37, 51), (64, 200), (136, 264)])
+@pytest.mark.parametrize("hw", [(8, 8), (36, 52), (37, 51), (64, 200), (136, 264), (340, 512)])
 def test_encoder_gradients_match_float64_autograd(hw):
     from crnerf_b200 import ops
     from crnerf_b200.autograd import EncoderFn

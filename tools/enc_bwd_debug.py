@@ -55,7 +55,7 @@ ga = max(gp(128, H4, W4), gp(128, H2, W2), gp(64, H, W))
 gb = max(gp(128, H2, W2), gp(64, H, W))
 dxb = max(al((h + 2) * (gs(w) - 2) * C * 4) for C, h, w in [(128, H4, W4), (128, H2, W2), (64, H2, W2), (64, H, W)])
 part = al(max(148 * 3 * 128 * 128, 296 * 1728) * 4)
-small = ga + gb + dxb + part + al(1024 * 128 * 4) + al(1024 * 64 * 4) + al(16 * 296 * 8 * 4) + al(296 * 12 * 4)
+small = ga + gb + dxb + part + al(1024 * 128 * 4) + al(1024 * 64 * 4) + al(16 * 4 * 296 * 8 * 4) + al(296 * 12 * 4)
 scales = scratch[small:small + 32].view(torch.float32)
 maxbits = scratch[small + 32:small + 64].view(torch.int32)
 print("scales", scales.tolist(), "max", maxbits.view(torch.float32).tolist())

@@ -13,7 +13,7 @@
 //
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -I cr-nerf-pytorch_b200/csrc
 //        tools/mn_nosw_probe.cu -o tools/mn_nosw_probe
-// run  : tools/mn_nosw_probe [N=128] [variant=0] [shift_a=0] [shift_b=0]
+// run  : tools/mn_nosw_probe [N=128] [variant=0] [shift_a=0] [shift_b=0] [reps: time 16 x reps MMAs]
 #include <cuda_fp16.h>
 #include <cstdio>
 #include <cstdlib>
@@ -44,7 +44,8 @@ __device__ __forceinline__ uint64_t desc_mn_nosw(uint32_t addr, uint32_t lbo, ui
 }
 
 __global__ void __launch_bounds__(160, 1)
-probe_kernel(const uint8_t* a_img, const uint8_t* b_img, float* d_out, int N, int variant, int sa, int sb) {
+probe_kernel(const uint8_t* a_img, const uint8_t* b_img, float* d_out, int N, int variant, int sa, int sb, int reps,
+             long long* cycles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t a_bytes = 16 * kRun * 16, b_bytes = (N / 8) * kRun * 16;
   uint8_t* sA = smem;
@@ -55,9 +56,10 @@ probe_kernel(const uint8_t* a_img, const uint8_t* b_img, float* d_out, int N, in
   if (threadIdx.x == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc<256>(tmem_slot);
+  if (warp == 4) tmem_alloc<512>(tmem_slot);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -80,6 +82,19 @@ probe_kernel(const uint8_t* a_img, const uint8_t* b_img, float* d_out, int N, in
         umma_ss(tmem, ad, bd, idesc, ks ? 1u : 0u);
       }
       umma_commit(&bars[1]);
+      // issue rate of the MN-major no-swizzle form (results discarded): `reps` x 16 MMAs back to back
+      if (reps > 0) {
+        mbar_wait(&bars[1], 0, 5);
+        const uint64_t ad = desc_mn_nosw(smem_u32(sA), lbo, sbo), bd = desc_mn_nosw(smem_u32(sB), lbo, sbo);
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) umma_ss(tmem + 128, ad + (uint64_t)((j & 3) * 16), bd + (uint64_t)((j & 3) * 16 + (j >> 2)), idesc, 1u);
+        }
+        umma_commit(&bars[2]);
+        mbar_wait(&bars[2], 0, 6);
+        cycles[0] = clock64() - t0;
+      }
     }
     __syncwarp();
   }
@@ -97,13 +112,14 @@ probe_kernel(const uint8_t* a_img, const uint8_t* b_img, float* d_out, int N, in
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<256>(tmem);
+  if (warp == 4) tmem_dealloc<512>(tmem);
 }
 
 int main(int argc, char** argv) {
   const int N = argc > 1 ? atoi(argv[1]) : 128;
   const int variant = argc > 2 ? atoi(argv[2]) : 0;
   const int sa = argc > 3 ? atoi(argv[3]) : 0, sb = argc > 4 ? atoi(argv[4]) : 0;
+  const int reps = argc > 5 ? atoi(argv[5]) : 0;
   const int M = 128;
   if (N % 16 || N > 256 || sa < 0 || sb < 0 || sa + kPix > kRun || sb + kPix > kRun) {
     printf("bad args\n");
@@ -140,7 +156,10 @@ int main(int argc, char** argv) {
   CK(cudaMemset(dd, 0xff, M * N * 4));
   const size_t smem = a_img.size() + b_img.size() + 1024;
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  probe_kernel<<<1, 160, smem>>>(da, db, dd, N, variant, sa, sb);
+  long long* dcyc;
+  CK(cudaMalloc(&dcyc, 8));
+  CK(cudaMemset(dcyc, 0, 8));
+  probe_kernel<<<1, 160, smem>>>(da, db, dd, N, variant, sa, sb, reps, dcyc);
   CK(cudaGetLastError());
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
@@ -153,6 +172,12 @@ int main(int argc, char** argv) {
   for (int i = 0; i < M * N; ++i) bad += out[i] != ref[i];
   printf("mn_nosw_probe N=%d variant=%d shift_a=%d shift_b=%d: mismatches=%d/%d %s\n", N, variant, sa, sb, bad, M * N,
          bad == 0 ? "OK" : "FAIL");
+  if (reps > 0) {
+    long long cyc = 0;
+    CK(cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost));
+    printf("   MN-major no-swizzle SS MMA M=128 N=%d K=16: %.1f cycles per MMA (%d back to back)\n", N,
+           double(cyc) / (16.0 * reps), 16 * reps);
+  }
   if (bad) {
     int shown = 0;
     for (int i = 0; i < M * N && shown < 6; ++i)
