@@ -419,6 +419,13 @@ enc_wgrad_tc_kernel(const __half* __restrict__ g_hi, const __half* __restrict__ 
   uint64_t* d_full = empty + kStages;    // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#if defined(CRNERF_WGRAD_DIAG) && CRNERF_WGRAD_DIAG == 3
+  __shared__ long long ts[8];
+#define WSTAMP(k) do { if (lane == 0) ts[k] = clock64(); } while (0)
+  if (threadIdx.x == 0) ts[0] = clock64();
+#else
+#define WSTAMP(k) do { } while (0)
+#endif
   // stale shared memory may hold NaN patterns; operands past a row's end are multiplied by zero gradients
   for (int i = threadIdx.x; i < kStages * Cfg::kStageBytes / 16; i += kWgradThreads)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -436,6 +443,7 @@ enc_wgrad_tc_kernel(const __half* __restrict__ g_hi, const __half* __restrict__ 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  if (warp == 3) WSTAMP(1);
 
   const int ky = blockIdx.x % 3, grp = blockIdx.x / 3, ngrp = gridDim.x / 3;
   const int nseg_row = (W + Cfg::kSeg - 1) / Cfg::kSeg, nseg = H * nseg_row;
@@ -451,6 +459,12 @@ enc_wgrad_tc_kernel(const __half* __restrict__ g_hi, const __half* __restrict__ 
       // the X run stops at the row's end: entries past it keep stale (finite) data and meet zero gradients
       const uint32_t gbytes = (uint32_t)nks * 256, xbytes = (uint32_t)min(nks * 16 + 2, Wp - sx) * 16;
       uint8_t* stage = smem + st * Cfg::kStageBytes;
+#if defined(CRNERF_WGRAD_DIAG) && CRNERF_WGRAD_DIAG == 1   // diagnostic: no operand traffic after the first ring fill
+      if (it >= (uint32_t)kStages) {
+        if (lane == 0) mbar_arrive(&full[st]);
+        continue;
+      }
+#endif
       if (lane == 0) mbar_arrive_expect_tx(&full[st], Cfg::kGChunks * gbytes + Cfg::kXChunks * xbytes);
       __syncwarp();
       for (int c = lane; c < Cfg::kGChunks; c += 32) {
@@ -471,6 +485,7 @@ enc_wgrad_tc_kernel(const __half* __restrict__ g_hi, const __half* __restrict__ 
       const uint32_t st = it % kStages;
       mbar_wait(&full[st], (it / kStages) & 1, 22);
       tc_fence_after_sync();
+      if (it == 0) WSTAMP(2);
       const int y = sg / nseg_row, sx = (sg - y * nseg_row) * Cfg::kSeg;
       const int nks = (min(Cfg::kSeg, W - sx) + 15) >> 4;
       if (elect_one()) {
@@ -480,6 +495,9 @@ enc_wgrad_tc_kernel(const __half* __restrict__ g_hi, const __half* __restrict__ 
         constexpr uint64_t kALo = (uint64_t)((COUT / 8) * Cfg::kGStride) >> 4;
         constexpr uint64_t kXLo = (uint64_t)((CIN / 8) * Cfg::kXStride) >> 4;
         // all MMAs of one accumulator back to back (alternating accumulators per instruction is slower)
+#if defined(CRNERF_WGRAD_DIAG) && CRNERF_WGRAD_DIAG == 2   // diagnostic: operand traffic only
+        if (false)
+#endif
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           const uint32_t d = tmem + kx * CIN;
@@ -500,6 +518,7 @@ enc_wgrad_tc_kernel(const __half* __restrict__ g_hi, const __half* __restrict__ 
       }
       __syncwarp();
     }
+    WSTAMP(3);
     if (elect_one()) umma_commit(d_full);
     __syncwarp();
   } else if (warp >= 4) {
@@ -507,6 +526,7 @@ enc_wgrad_tc_kernel(const __half* __restrict__ g_hi, const __half* __restrict__ 
     const bool any = grp < nseg;      // a CTA without segments has issued nothing: its partial is zero
     mbar_wait(d_full, 0, 23);
     tc_fence_after_sync();
+    if (warp == 4) WSTAMP(4);
     const int row = quarter * 32 + lane;
 #pragma unroll 1
     for (int kx = 0; kx < 3; ++kx) {
@@ -528,9 +548,15 @@ enc_wgrad_tc_kernel(const __half* __restrict__ g_hi, const __half* __restrict__ 
       }
     }
   }
+  if (warp == 4) WSTAMP(5);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 2) tmem_dealloc<512>(tmem);
+#if defined(CRNERF_WGRAD_DIAG) && CRNERF_WGRAD_DIAG == 3
+  if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 100))
+    printf("wgrad<%d,%d> cta %d (%d x %d): prologue %lld | first operands +%lld | issue loop end +%lld | accumulators done +%lld | epilogue +%lld | total %lld\n",
+           CIN, COUT, (int)blockIdx.x, H, W, ts[1] - ts[0], ts[2] - ts[1], ts[3] - ts[2], ts[4] - ts[3], ts[5] - ts[4], clock64() - ts[0]);
+#endif
 }
 
 // dW[co][ci][ky][kx] = (1 / scale) * sum over the CTAs of kernel row ky (CTA order) of their partials
