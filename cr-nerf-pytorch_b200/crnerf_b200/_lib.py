@@ -153,6 +153,9 @@ SIGNATURES = {
                                      C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),
+    "crnerf_adam_step": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
+                                   C.c_double, C.c_int, C.c_void_p]),
     "crnerf_debug_set": (C.c_int, [C.c_void_p, C.c_int]),
     "crnerf_debug_program": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int]),
 }

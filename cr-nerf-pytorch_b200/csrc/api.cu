@@ -105,6 +105,10 @@ int composite_backward(const float* raw, const float* z, const float* noise, con
                        float* d_rgb_pre, float* d_sigma_pre, cudaStream_t st);
 int relu_bias_grad(float* g, const void* act, int64_t n_points, int width, float* gb, float* scratch,
                    cudaStream_t st);
+// implemented in optim.cu
+int adam_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+              float* const* exp_avg_sq, const int64_t* numel, const float* step, const float* lr_dev, double lr,
+              double beta1, double beta2, double eps, double weight_decay, int maximize, cudaStream_t st);
 // implemented in encoder.cu
 size_t encoder_packed_bytes();
 size_t encoder_scratch_bytes(int H, int W);
@@ -248,6 +252,16 @@ int crnerf_composite_backward(const float* raw, const float* z_vals, const float
   if (rc) return rc;
   return composite_backward(raw, z_vals, noise, g_feature, g_weights, g_depth, n_rays, n_samples,
                             d_rgb_pre, d_sigma_pre, (cudaStream_t)stream);
+}
+
+int crnerf_adam_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                     float* const* exp_avg_sq, const int64_t* numel, const float* step, const float* lr_dev,
+                     double lr, double beta1, double beta2, double eps, double weight_decay, int maximize,
+                     void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  return adam_step(n_tensors, params, grads, exp_avg, exp_avg_sq, numel, step, lr_dev, lr, beta1, beta2, eps,
+                   weight_decay, maximize, (cudaStream_t)stream);
 }
 
 size_t crnerf_relu_bias_grad_scratch_floats(int width) {

@@ -18,9 +18,11 @@
 // z, noise and rays receive no gradient (the reference detaches the importance samples,
 // rendering.py:184, and its inputs do not require grad).
 //
-// One warp per ray: lanes stride the 64 channels (coalesced rows of the (P,65) buffer) for the
-// dot products and the output rows; the two length-S recurrences run on lane 0 over shared
-// memory (S <= 1024; training uses 64 / 128).
+// One warp per ray.  Dot products: 32 rows of the (P,65) buffer at a time, lanes over the channels
+// (coalesced 256-byte rows, 64 independent loads in flight per lane), then a transposing butterfly
+// (31 shuffles for 32 rows) leaves row r's dot product on lane r, so everything per sample -
+// z, noise, sigma, the exponentials - runs with lanes over samples.  Only the two length-S
+// recurrences are serial (lane 0 over shared memory; S <= 1024, training uses 64 / 128).
 #include <algorithm>
 #include "common.h"
 
@@ -28,8 +30,9 @@ namespace crnerf {
 namespace {
 
 constexpr int kMaxS = 1024;
+constexpr int kCbWarps = 2;   // rays per block
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * kCbWarps)
 composite_backward_kernel(const float* __restrict__ raw, const float* __restrict__ z,
                           const float* __restrict__ noise, const float* __restrict__ g_feature,
                           const float* __restrict__ g_weights, const float* __restrict__ g_depth,
@@ -37,31 +40,48 @@ composite_backward_kernel(const float* __restrict__ raw, const float* __restrict
                           float* __restrict__ d_sigma_pre) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ray = blockIdx.x * 4 + warp;
+  const int ray = blockIdx.x * kCbWarps + warp;
   if (ray >= n_rays) return;
-  float* gw = sm + warp * 4 * S;  // dL/dw_s, later dL/dalpha_s
+  float* gw = sm + warp * 5 * S;  // dL/dw_s, later (dL/dalpha_s) / T_s
   float* al = gw + S;             // alpha_s
   float* wt = al + S;             // w_s
-  float* dl = wt + S;             // delta_s (1 - alpha_s) [x_s > 0]
+  float* dl = wt + S;             // delta_s (1 - alpha_s) [x_s > 0], later times T_s
+  float* sg = dl + S;             // 1 - exp(-sigma_s)
   const long long p0 = (long long)ray * S;
   const float g0 = g_feature ? g_feature[(long long)ray * 64 + lane] : 0.f;
   const float g1 = g_feature ? g_feature[(long long)ray * 64 + 32 + lane] : 0.f;
   const float gd = g_depth ? g_depth[ray] : 0.f;
 
-  // pass 1 (parallel over samples in groups of one row per iteration): dL/dw_s and alpha_s
-  for (int s = 0; s < S; ++s) {
-    const float* row = raw + (p0 + s) * 65;
-    float dot = g0 * row[lane] + g1 * row[32 + lane];
+  // pass 1: dL/dw_s, alpha_s and the per-sample factors, 32 samples per iteration
+  for (int s0 = 0; s0 < S; s0 += 32) {
+    float p[32];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d);
-    if (lane == 0) {
+    for (int r = 0; r < 32; ++r) {
+      const int s = min(s0 + r, S - 1);  // rows past the end repeat the last one; their lanes write nothing
+      const float* row = raw + (p0 + s) * 65;
+      p[r] = g0 * __ldg(row + lane) + g1 * __ldg(row + 32 + lane);
+    }
+    // after the step with distance d, bit log2(d) of the row a lane still carries equals that bit of the lane
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      const bool up = (lane & d) != 0;
+#pragma unroll
+      for (int i = 0; i < d; ++i) {
+        const float keep = up ? p[i + d] : p[i], send = up ? p[i] : p[i + d];
+        p[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+      }
+    }
+    const int s = s0 + lane;
+    if (s < S) {
       const float zs = z[p0 + s];
       const float delta = s + 1 < S ? __fsub_rn(z[p0 + s + 1], zs) : 1e2f;
-      const float x = row[64] + (noise ? noise[p0 + s] : 0.f);
+      const float sigma = __ldg(raw + (p0 + s) * 65 + 64);
+      const float x = sigma + (noise ? noise[p0 + s] : 0.f);
       const float e = expf(-(delta * fmaxf(x, 0.f)));  // 1 - alpha
       al[s] = 1.f - e;
       dl[s] = x > 0.f ? delta * e : 0.f;
-      gw[s] = dot + (g_weights ? g_weights[p0 + s] : 0.f) + gd * zs;
+      sg[s] = 1.f - expf(-sigma);
+      gw[s] = p[0] + (g_weights ? g_weights[p0 + s] : 0.f) + gd * zs;
     }
   }
   __syncwarp();
@@ -82,18 +102,16 @@ composite_backward_kernel(const float* __restrict__ raw, const float* __restrict
     }
   }
   __syncwarp();
-  // pass 3: outputs
+  // pass 3: outputs (the rows come from L1 / L2 this time)
+  for (int s = lane; s < S; s += 32) d_sigma_pre[p0 + s] = gw[s] * dl[s] * sg[s];
+#pragma unroll 8
   for (int s = 0; s < S; ++s) {
     const float* row = raw + (p0 + s) * 65;
     const float w = wt[s];
-    const float f0 = row[lane], f1 = row[32 + lane];
+    const float f0 = __ldg(row + lane), f1 = __ldg(row + 32 + lane);
     float* o = d_rgb_pre + (p0 + s) * 64;
     o[lane] = w * g0 * f0 * (1.f - f0);
     o[32 + lane] = w * g1 * f1 * (1.f - f1);
-    if (lane == 0) {
-      const float sigma = row[64];
-      d_sigma_pre[p0 + s] = gw[s] * dl[s] * (1.f - expf(-sigma));
-    }
   }
 }
 
@@ -189,11 +207,11 @@ int composite_backward(const float* raw, const float* z, const float* noise, con
   CRNERF_REQUIRE(n_samples >= 1 && n_samples <= kMaxS, "n_samples=%d unsupported by the backward (<= %d)",
                  n_samples, kMaxS);
   if (n_rays == 0) return CRNERF_OK;
-  const size_t smem = (size_t)4 * 4 * n_samples * sizeof(float);
+  const size_t smem = (size_t)kCbWarps * 5 * n_samples * sizeof(float);
   if (smem > 48 * 1024)
     CRNERF_CUDA(cudaFuncSetAttribute(composite_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
-  composite_backward_kernel<<<(n_rays + 3) / 4, 128, smem, st>>>(raw, z, noise, g_feature, g_weights, g_depth,
+  composite_backward_kernel<<<(n_rays + kCbWarps - 1) / kCbWarps, 32 * kCbWarps, smem, st>>>(raw, z, noise, g_feature, g_weights, g_depth,
                                                                  n_rays, n_samples, d_rgb_pre, d_sigma_pre);
   count_launch();
   CRNERF_CUDA(cudaGetLastError());

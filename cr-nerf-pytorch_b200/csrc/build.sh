@@ -10,10 +10,10 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC)
 mkdir -p "$OBJ"
 pids=()
-for f in api nerf_mlp sample crossray style_backward backward backward_gemm gram_tc loss encoder; do
+for f in api nerf_mlp sample crossray style_backward backward backward_gemm gram_tc loss encoder optim; do
   "$NVCC" "${FLAGS[@]}" ${CRNERF_DEFS:-} -c "$HERE/$f.cu" -o "$OBJ/$f.o" ${CRNERF_PTXAS_V:+-Xptxas -v} &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-"$NVCC" -shared -o "$OUT" "$OBJ"/{api,nerf_mlp,sample,crossray,style_backward,backward,backward_gemm,gram_tc,loss,encoder}.o -lcudart
+"$NVCC" -shared -o "$OUT" "$OBJ"/{api,nerf_mlp,sample,crossray,style_backward,backward,backward_gemm,gram_tc,loss,encoder,optim}.o -lcudart
 echo "built $OUT"

@@ -10,7 +10,7 @@
 // Per pixel the block is two dense chains over the centred features xc = x - mean:
 //   head : xc -Wc,bc-> comp(32) -T-> z(32) -Wu,bu+mu_s-> u(64) -Wr,br-> sigmoid -> rgb(3)
 //   cnn  : xc -W1,b1-> lrelu(128) -W2,b2-> lrelu(64) -W3,b3-> y(32);  G = sum_p y y^T / n
-// chain_backward_kernel runs either one on 16-pixel tiles: forward recompute into shared memory,
+// chain_backward_kernel runs either one on 8-pixel tiles: forward recompute into shared memory,
 // then top-down input gradients and outer-product weight gradients, accumulated into the CTA's own
 // slot of a partial buffer (plain read-modify-write, no atomics; a fixed-order reduction follows).
 // Between the two chains sit the 32x32 algebra (dS = dT C^T, dC = S^T dT) and the two FC layers
@@ -23,7 +23,8 @@
 namespace crnerf {
 namespace {
 
-constexpr int kTP = 16;        // pixels per tile
+constexpr int kTP = 8;         // pixels per tile: a 32x32 training patch spreads over 128 CTAs per map (the kernel is
+                               // latency-bound per tile: 16-pixel tiles on 64 CTAs took 1.9x as long)
 constexpr int kActStride = 297;  // floats per pixel of the activation stash (>= 64+128+64+32, odd: no bank conflicts)
 constexpr int kGStride = 129;
 constexpr int kMaxLayers = 4;
@@ -108,7 +109,7 @@ chain_backward_kernel(const __grid_constant__ ChainParams P) {
         if (L.b2) acc += L.b2[j];
         const float* w = L.W + (long long)j * L.K;
         const float* in = acts + p * kActStride + off[l];
-#pragma unroll 4
+#pragma unroll 8
         for (int k = 0; k < L.K; ++k) acc = fmaf(w[k], in[k], acc);
         acts[p * kActStride + off[l + 1] + j] = act_fn(acc, L.act);
       }
@@ -158,7 +159,7 @@ chain_backward_kernel(const __grid_constant__ ChainParams P) {
         const int p = e % kTP, k = e / kTP;
         float acc = 0.f;
         const float* w = L.W + k;
-#pragma unroll 4
+#pragma unroll 8
         for (int j = 0; j < L.N; ++j) acc = fmaf(w[(long long)j * L.K], g_out[p * kGStride + j], acc);
         g_in[p * kGStride + k] = acc;
       }

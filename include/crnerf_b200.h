@@ -450,6 +450,22 @@ int crnerf_encoder_backward(const void* packed, const float* img, int height, in
                             const float* grad_out, const void* tape, const crnerf_encoder_grads* grads,
                             float* grad_img, void* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- optimizer update of the training step ----------------------------------------------
+ * The Adam optimizer as the reference builds it (utils/__init__.py:33-34 `Adam(parameters, lr=hparams.lr,
+ * eps=eps, weight_decay=hparams.weight_decay)`, stepped once per batch by the training loop of
+ * train_mask_grid_sample.py) over a table of tensors: one launch per 48 tensors.  params / grads /
+ * exp_avg / exp_avg_sq / numel are HOST arrays of n_tensors entries holding device pointers (fp32,
+ * contiguous) and element counts; `step` is a DEVICE float holding the number of steps already taken
+ * (the update uses *step + 1; the caller increments it afterwards, so the call can be captured in a CUDA
+ * graph); lr_dev, when non-NULL, is a DEVICE float that overrides `lr` (a scheduler can change it
+ * between graph replays).  Element-wise fp32 math of the PyTorch optimizer with amsgrad = False
+ * (m += (1-b1)(g-m); v = b2 v + (1-b2) g g; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)), bias
+ * corrections in double. */
+int crnerf_adam_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                     float* const* exp_avg_sq, const int64_t* numel, const float* step, const float* lr_dev,
+                     double lr, double beta1, double beta2, double eps, double weight_decay, int maximize,
+                     void* stream);
+
 /* debug (tests only): dump the post-activation values of `layer` (0..10) for every
  * point of later fused launches into dbg_buf (n_points x 256 floats); NULL disables. */
 int crnerf_debug_set(float* dbg_buf, int layer);

@@ -16,6 +16,9 @@ from crnerf_b200 import synthetic
 import torch.distributed as dist
 
 
+OPTIMIZER = os.environ.get("CRNERF_BENCH_OPTIMIZER", "native")   # "native": crnerf_b200.optim.Adam, "torch": torch.optim.Adam
+
+
 def make_step(dev, world, rank, n_rays=1024, ns=64, ni=64, operand="fp16", bwd=None, capturable=False):
     """Build the models + optimizer and return (step_fn, models, margs, rays, style, target, side)."""
     from bench import build_models
@@ -34,7 +37,11 @@ def make_step(dev, world, rank, n_rays=1024, ns=64, ni=64, operand="fp16", bwd=N
     style = torch.rand(1, 64, 32, 32, device=dev)
     target = torch.rand(side * side, 3, device=dev)
     params = [p for m in models.values() for p in m.parameters()]
-    opt = torch.optim.Adam(params, lr=5e-4, capturable=capturable)
+    if OPTIMIZER == "native":
+        from crnerf_b200.optim import Adam      # one launch per 48 tensors (csrc/optim.cu), always capturable
+        opt = Adam(params, lr=5e-4)
+    else:
+        opt = torch.optim.Adam(params, lr=5e-4, capturable=capturable)
     flat_n = sum(p.numel() for p in params)
 
     def allreduce_grads():

@@ -64,7 +64,8 @@ def main():
                                batch_size=1024, device=dev)
     crit = loss_dict["crnerf"](hp, coef=1)
     params = [p for m in mods for p in m.parameters()]
-    opt = torch.optim.Adam(params, lr=5e-4)
+    from crnerf_b200.optim import Adam   # torch.optim.Adam's update as one launch per 48 tensors (csrc/optim.cu)
+    opt = Adam(params, lr=5e-4)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     acc = {}
 
@@ -123,7 +124,7 @@ def main():
         # everything after the (host-driven) patch sampler as one CUDA graph: the sampled batch is copied into
         # static tensors, the graph holds enc_a, mask network, render, decode x3, loss, backward and Adam
         from crnerf_b200.graphs import GraphedTrainStep
-        opt_g = torch.optim.Adam(params, lr=5e-4, capturable=True)
+        opt_g = Adam(params, lr=5e-4)
         s0 = sampler.sample(0, 0)
         static = {k: s0[k].clone() for k in ("rays", "ts", "rgbs", "rgb_idx")}
         static["whole"] = ((s0["whole_img"].unsqueeze(0) + 1) / 2).clone()
