@@ -134,12 +134,13 @@ __global__ void __launch_bounds__(128) top_pack_kernel(const float* __restrict__
   uint4* rows = reinterpret_cast<uint4*>(g_sig + (size_t)blockIdx.x * kSlab + r * 128);
   const uint32_t rx = r & 7;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    uint32_t w[4];
+  for (int k = 0; k < 4; ++k) {
+    uint32_t w[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) w[q] = pack2<kFmt, false>(v[8 * c + 2 * q] * S, v[8 * c + 2 * q + 1] * S);
-    row[(uint32_t)c ^ rx] = make_uint4(w[0], w[1], w[2], w[3]);
-    rows[(uint32_t)c ^ rx] = c == 0 ? make_uint4(pack2<kFmt, false>(ds * S, 0.f), 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    for (int q = 0; q < 8; ++q) w[q] = pack2<kFmt, false>(v[16 * k + 2 * q] * S, v[16 * k + 2 * q + 1] * S);
+    stg_row_pair(row, (uint32_t)k, rx, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
+    stg_row_pair(rows, (uint32_t)k, rx, k == 0 ? make_uint4(pack2<kFmt, false>(ds * S, 0.f), 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u),
+                 make_uint4(0u, 0u, 0u, 0u));
   }
   // bias gradients (unscaled fp32): column sums over the block's rows, then one atomic per column
   float dsum = ds;
@@ -381,7 +382,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
         if (rowf < P.nrows) {
           uint4* dst = reinterpret_cast<uint4*>(part + (size_t)rowf * n_mma + c0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 4; ++j)
+            stg_v8(dst + 2 * j, make_uint4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
+                   make_uint4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]));
         }
       }
     }
@@ -533,7 +536,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_kernel(const __grid_const
           const uint4* arow = reinterpret_cast<const uint4*>(
               P.act + ((size_t)tile * P.act_slabs_total + P.act_s0 + slab) * kSlab + row * 128);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) m[c] = __ldg(arow + ((uint32_t)c ^ (uint32_t)(row & 7)));
+          for (int k = 0; k < 4; ++k) ldg_row_pair(arow, (uint32_t)k, (uint32_t)(row & 7), m[2 * k], m[2 * k + 1]);
         }
         tmem_ld_wait();
         if (gidx + 2 >= groups) {   // last read of this accumulator
@@ -571,11 +574,11 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_kernel(const __grid_const
         // 16-bit tile of the layer below
         uint4* orow = reinterpret_cast<uint4*>(P.out + ((size_t)tile * (P.k_in / 64) + slab) * kSlab + row * 128);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint32_t w[4];
+        for (int k = 0; k < 4; ++k) {
+          uint32_t w[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) w[e] = pack2<kFmt, false>(x[8 * c + 2 * e], x[8 * c + 2 * e + 1]);
-          orow[(uint32_t)c ^ (uint32_t)(row & 7)] = make_uint4(w[0], w[1], w[2], w[3]);
+          for (int e = 0; e < 8; ++e) w[e] = pack2<kFmt, false>(x[16 * k + 2 * e], x[16 * k + 2 * e + 1]);
+          stg_row_pair(orow, (uint32_t)k, (uint32_t)(row & 7), make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
         }
         // bias gradient: column sums over the warp's 32 rows (transposing butterfly)
         if (P.db) {

@@ -406,8 +406,9 @@ struct SaveRow {
 // 16 packed words = chunks [chunk0, chunk0 + 4) of the row
 __device__ __forceinline__ void save16(const SaveRow& r, int chunk0, const uint32_t* w) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    r.base[(uint32_t)(chunk0 + i) ^ r.rx] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  for (int i = 0; i < 2; ++i)   // whole 32-byte sectors per thread (STG.256, see stg_v8)
+    stg_row_pair(r.base, (uint32_t)(chunk0 >> 1) + i, r.rx, make_uint4(w[8 * i], w[8 * i + 1], w[8 * i + 2], w[8 * i + 3]),
+                 make_uint4(w[8 * i + 4], w[8 * i + 5], w[8 * i + 6], w[8 * i + 7]));
 }
 
 template <int kFmt, bool kRelu, bool kSigma, bool kDbg, bool kSave>
@@ -1068,7 +1069,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         if (er.base) {
           const uint4* src = reinterpret_cast<const uint4*>(my_emb + ch * 16384 + row * 128);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) er.base[(uint32_t)c ^ er.rx] = src[c ^ (row & 7)];
+          for (int k = 0; k < 4; ++k) stg_row_pair(er.base, (uint32_t)k, er.rx, src[(2 * k) ^ (row & 7)], src[(2 * k + 1) ^ (row & 7)]);
         }
       }
       long long t_a = 0;

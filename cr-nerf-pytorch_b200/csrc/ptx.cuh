@@ -123,6 +123,34 @@ __device__ __forceinline__ void ldg_stream_v8(const float* p, float4& a, float4&
                : "l"(p));
 }
 
+// 32-byte accesses of 16-bit operand rows (sm_100: LDG.256 / STG.256).  The "tiled16" rows of the training
+// path are written / read one row per thread, 128 B apart across a warp: with 16-byte accesses every
+// request touches 32 half-filled sectors and the L1 -> L2 sector rate bounds the kernel (ncu: 32 sectors per
+// request, l1tex and lts at 50-65 %); a thread that moves whole 32-byte sectors halves both counts.
+__device__ __forceinline__ void stg_v8(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void ldg_nc_v8(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+// One 128-byte row of a SWIZZLE_128B block (16-byte chunk c sits at position c ^ rx, rx = row % 8): chunks 2k and
+// 2k + 1 share the aligned 32-byte sector at position 2k ^ (rx & 6), in swapped order when rx is odd.
+__device__ __forceinline__ void stg_row_pair(uint4* row, uint32_t k, uint32_t rx, const uint4& c_even, const uint4& c_odd) {
+  const bool sw = (rx & 1u) != 0u;
+  stg_v8(row + ((2u * k) ^ (rx & 6u)), sw ? c_odd : c_even, sw ? c_even : c_odd);
+}
+__device__ __forceinline__ void ldg_row_pair(const uint4* row, uint32_t k, uint32_t rx, uint4& c_even, uint4& c_odd) {
+  uint4 a, b;
+  ldg_nc_v8(row + ((2u * k) ^ (rx & 6u)), a, b);
+  const bool sw = (rx & 1u) != 0u;
+  c_even = sw ? b : a;
+  c_odd = sw ? a : b;
+}
+
 // ----------------------------------------------------------------------------
 // tcgen05: TMEM allocation
 // ----------------------------------------------------------------------------
