@@ -629,7 +629,7 @@ def render_pass_train(packed: PackedMLP, rays: torch.Tensor, z_vals: torch.Tenso
                       n_freq_xyz: int = 15, n_freq_dir: int = 4, xyz_jitter: Optional[torch.Tensor] = None):
     """render_pass + saved activations.  Returns (weights, feature, depth, acts, raw):
     acts is the byte buffer of crnerf_render_pass_train (tiled 16-bit layout, see ``untile_acts``), raw is
-    (n_points, 65) fp32 [sigmoid features | softplus sigma]."""
+    65*n_points fp32: the sigmoid features as (n_points, 64) rows, then the n_points softplus sigmas."""
     lib = _lib.load()
     rays = _c(_need(rays, "rays", 2))
     z_vals = _c(_need(z_vals, "z_vals", 2))
@@ -650,7 +650,7 @@ def render_pass_train(packed: PackedMLP, rays: torch.Tensor, z_vals: torch.Tenso
         feature = torch.empty((n, 64), dtype=torch.float32, device=dev)
         depth = torch.empty((n,), dtype=torch.float32, device=dev)
         acts = torch.empty((int(lib.crnerf_render_acts_bytes(n * s)),), dtype=torch.uint8, device=dev)
-        raw = torch.empty((n * s, 65), dtype=torch.float32, device=dev)
+        raw = torch.empty((n * s * 65,), dtype=torch.float32, device=dev)   # (n*s, 64) features, then n*s sigmas
         if n == 0:
             return weights, feature, depth, acts, raw
         opts = None
@@ -698,9 +698,9 @@ def render_backward(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tens
     lib = _lib.load()
     z_vals = _c(_need(z_vals, "z_vals", 2))
     n, s = z_vals.shape
-    raw = _c(_need(raw, "raw", 2))
-    if raw.shape != (n * s, 65):
-        raise ValueError("raw must be (n_rays*n_samples, 65)")
+    raw = _c(_need(raw, "raw"))
+    if raw.numel() != n * s * 65:
+        raise ValueError("raw must be the 65*n_rays*n_samples floats render_pass_train saved")
     opt = lambda t, name, shape: None if t is None else _c(_need(t, name).reshape(shape))
     noise = opt(noise, "noise", (n, s))
     g_feature = opt(g_feature, "g_feature", (n, 64))

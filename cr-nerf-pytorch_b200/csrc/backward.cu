@@ -18,11 +18,12 @@
 // z, noise and rays receive no gradient (the reference detaches the importance samples,
 // rendering.py:184, and its inputs do not require grad).
 //
-// One warp per ray.  Dot products: 32 rows of the (P,65) buffer at a time, lanes over the channels
-// (coalesced 256-byte rows, 64 independent loads in flight per lane), then a transposing butterfly
-// (31 shuffles for 32 rows) leaves row r's dot product on lane r, so everything per sample -
-// z, noise, sigma, the exponentials - runs with lanes over samples.  Only the two length-S
-// recurrences are serial (lane 0 over shared memory; S <= 1024, training uses 64 / 128).
+// One block of four warps per ray, 32 samples per warp and pass.  Dot products: a warp's 32 rows at a time,
+// lanes over the channels (coalesced 256-byte rows, 64 independent loads in flight per lane), then a
+// transposing butterfly (31 shuffles for 32 rows) leaves row r's dot product on lane r, so everything per
+// sample - z, noise, sigma, the exponentials - runs with lanes over samples.  Only the two length-S
+// recurrences are serial (one thread over shared memory; S <= 1024, training uses 64 / 128).  For
+// S <= 128 (kKeep) a warp's rows stay in registers between the passes: the features are read once.
 #include <algorithm>
 #include "common.h"
 
@@ -30,37 +31,48 @@ namespace crnerf {
 namespace {
 
 constexpr int kMaxS = 1024;
-constexpr int kCbWarps = 2;   // rays per block
+constexpr int kCbWarps = 4;   // warps per ray
 
+template <bool kKeep>
 __global__ void __launch_bounds__(32 * kCbWarps)
 composite_backward_kernel(const float* __restrict__ raw, const float* __restrict__ z,
                           const float* __restrict__ noise, const float* __restrict__ g_feature,
                           const float* __restrict__ g_weights, const float* __restrict__ g_depth,
-                          int n_rays, int S, float* __restrict__ d_rgb_pre,
+                          int n_rays, int S, int split, float* __restrict__ d_rgb_pre,
                           float* __restrict__ d_sigma_pre) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ray = blockIdx.x * kCbWarps + warp;
-  if (ray >= n_rays) return;
-  float* gw = sm + warp * 5 * S;  // dL/dw_s, later (dL/dalpha_s) / T_s
-  float* al = gw + S;             // alpha_s
-  float* wt = al + S;             // w_s
-  float* dl = wt + S;             // delta_s (1 - alpha_s) [x_s > 0], later times T_s
-  float* sg = dl + S;             // 1 - exp(-sigma_s)
+  const int ray = blockIdx.x;
+  float* gw = sm;       // dL/dw_s, later (dL/dalpha_s) / T_s
+  float* al = gw + S;   // alpha_s
+  float* wt = al + S;   // w_s
+  float* dl = wt + S;   // delta_s (1 - alpha_s) [x_s > 0], later times T_s
+  float* sg = dl + S;   // 1 - exp(-sigma_s)
   const long long p0 = (long long)ray * S;
+  // split: the training forward's layout ((P,64) feature rows, then P sigmas: aligned rows, whole-sector stores);
+  // otherwise (P,65) interleaved rows as NeRF_sigma.forward returns them
+  const int rs = split ? 64 : 65;
+  const float* sig = split ? raw + (long long)n_rays * S * 64 : raw + 64;
+  const int ss = split ? 1 : 65;
   const float g0 = g_feature ? g_feature[(long long)ray * 64 + lane] : 0.f;
   const float g1 = g_feature ? g_feature[(long long)ray * 64 + 32 + lane] : 0.f;
   const float gd = g_depth ? g_depth[ray] : 0.f;
+  const int n_chunks = (S + 31) >> 5;
 
-  // pass 1: dL/dw_s, alpha_s and the per-sample factors, 32 samples per iteration
-  for (int s0 = 0; s0 < S; s0 += 32) {
+  // pass 1: dL/dw_s, alpha_s and the per-sample factors
+  float f0[32], f1[32];
+  for (int c = warp; c < n_chunks; c += kCbWarps) {
+    const int s0 = c * 32;
     float p[32];
 #pragma unroll
     for (int r = 0; r < 32; ++r) {
       const int s = min(s0 + r, S - 1);  // rows past the end repeat the last one; their lanes write nothing
-      const float* row = raw + (p0 + s) * 65;
-      p[r] = g0 * __ldg(row + lane) + g1 * __ldg(row + 32 + lane);
+      const float* row = raw + (p0 + s) * rs;
+      f0[r] = __ldg(row + lane);
+      f1[r] = __ldg(row + 32 + lane);
     }
+#pragma unroll
+    for (int r = 0; r < 32; ++r) p[r] = g0 * f0[r] + g1 * f1[r];
     // after the step with distance d, bit log2(d) of the row a lane still carries equals that bit of the lane
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
@@ -75,7 +87,7 @@ composite_backward_kernel(const float* __restrict__ raw, const float* __restrict
     if (s < S) {
       const float zs = z[p0 + s];
       const float delta = s + 1 < S ? __fsub_rn(z[p0 + s + 1], zs) : 1e2f;
-      const float sigma = __ldg(raw + (p0 + s) * 65 + 64);
+      const float sigma = __ldg(sig + (p0 + s) * ss);
       const float x = sigma + (noise ? noise[p0 + s] : 0.f);
       const float e = expf(-(delta * fmaxf(x, 0.f)));  // 1 - alpha
       al[s] = 1.f - e;
@@ -84,9 +96,9 @@ composite_backward_kernel(const float* __restrict__ raw, const float* __restrict
       gw[s] = p[0] + (g_weights ? g_weights[p0 + s] : 0.f) + gd * zs;
     }
   }
-  __syncwarp();
-  // pass 2 (lane 0): T_s forward, R_s backward
-  if (lane == 0) {
+  __syncthreads();
+  // pass 2 (one thread): T_s forward, R_s backward
+  if (threadIdx.x == 0) {
     float T = 1.f;
     for (int s = 0; s < S; ++s) {
       wt[s] = al[s] * T;
@@ -101,17 +113,27 @@ composite_backward_kernel(const float* __restrict__ raw, const float* __restrict
       R = gws * al[s] + (1.f - al[s]) * R;
     }
   }
-  __syncwarp();
-  // pass 3: outputs (the rows come from L1 / L2 this time)
-  for (int s = lane; s < S; s += 32) d_sigma_pre[p0 + s] = gw[s] * dl[s] * sg[s];
-#pragma unroll 8
-  for (int s = 0; s < S; ++s) {
-    const float* row = raw + (p0 + s) * 65;
-    const float w = wt[s];
-    const float f0 = __ldg(row + lane), f1 = __ldg(row + 32 + lane);
-    float* o = d_rgb_pre + (p0 + s) * 64;
-    o[lane] = w * g0 * f0 * (1.f - f0);
-    o[32 + lane] = w * g1 * f1 * (1.f - f1);
+  __syncthreads();
+  // pass 3: outputs
+  for (int s = threadIdx.x; s < S; s += 32 * kCbWarps) d_sigma_pre[p0 + s] = gw[s] * dl[s] * sg[s];
+  for (int c = warp; c < n_chunks; c += kCbWarps) {
+    const int s0 = c * 32;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const int s = s0 + r;
+      if (s < S) {
+        float a0 = f0[r], a1 = f1[r];
+        if (!kKeep) {   // more than one chunk per warp: the registers hold the last one only
+          const float* row = raw + (p0 + s) * rs;
+          a0 = __ldg(row + lane);
+          a1 = __ldg(row + 32 + lane);
+        }
+        const float w = wt[s];
+        float* o = d_rgb_pre + (p0 + s) * 64;
+        o[lane] = w * g0 * a0 * (1.f - a0);
+        o[32 + lane] = w * g1 * a1 * (1.f - a1);
+      }
+    }
   }
 }
 
@@ -202,17 +224,18 @@ int relu_bias_grad(float* g, const void* act, int64_t n_points, int width, float
 
 int composite_backward(const float* raw, const float* z, const float* noise, const float* g_feature,
                        const float* g_weights, const float* g_depth, int n_rays, int n_samples,
-                       float* d_rgb_pre, float* d_sigma_pre, cudaStream_t st) {
+                       float* d_rgb_pre, float* d_sigma_pre, cudaStream_t st, int split) {
   CRNERF_REQUIRE(raw && z && d_rgb_pre && d_sigma_pre, "null argument");
   CRNERF_REQUIRE(n_samples >= 1 && n_samples <= kMaxS, "n_samples=%d unsupported by the backward (<= %d)",
                  n_samples, kMaxS);
   if (n_rays == 0) return CRNERF_OK;
-  const size_t smem = (size_t)kCbWarps * 5 * n_samples * sizeof(float);
-  if (smem > 48 * 1024)
-    CRNERF_CUDA(cudaFuncSetAttribute(composite_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-  composite_backward_kernel<<<(n_rays + kCbWarps - 1) / kCbWarps, 32 * kCbWarps, smem, st>>>(raw, z, noise, g_feature, g_weights, g_depth,
-                                                                 n_rays, n_samples, d_rgb_pre, d_sigma_pre);
+  const size_t smem = (size_t)5 * n_samples * sizeof(float);   // <= 20 KB
+  if (n_samples <= 32 * kCbWarps)
+    composite_backward_kernel<true><<<n_rays, 32 * kCbWarps, smem, st>>>(raw, z, noise, g_feature, g_weights, g_depth,
+                                                                        n_rays, n_samples, split, d_rgb_pre, d_sigma_pre);
+  else
+    composite_backward_kernel<false><<<n_rays, 32 * kCbWarps, smem, st>>>(raw, z, noise, g_feature, g_weights, g_depth,
+                                                                         n_rays, n_samples, split, d_rgb_pre, d_sigma_pre);
   count_launch();
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;

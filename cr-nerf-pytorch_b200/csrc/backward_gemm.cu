@@ -689,7 +689,7 @@ int render_acts_zero_tail(void* acts, int64_t n_points, cudaStream_t st) {
 
 int composite_backward(const float* raw, const float* z, const float* noise, const float* g_feature,
                        const float* g_weights, const float* g_depth, int n_rays, int n_samples,
-                       float* d_rgb_pre, float* d_sigma_pre, cudaStream_t st);
+                       float* d_rgb_pre, float* d_sigma_pre, cudaStream_t st, int split);
 
 template <int kFmt>
 static int run_wgrad(const WgradParams& w, cudaStream_t st) {
@@ -740,7 +740,7 @@ static int backward_chain(const crnerf_mlp_weights* w, const void* acts, const f
   count_launch();
 
   // 2. composite backward -> d_rgb, d_sigma (fp32), their max magnitude, top tiles
-  int rc = composite_backward(raw, z, noise, g_feature, g_weights, g_depth, n_rays, n_samples, d_rgb, d_sig, st);
+  int rc = composite_backward(raw, z, noise, g_feature, g_weights, g_depth, n_rays, n_samples, d_rgb, d_sig, st, 1);
   if (rc) return rc;
   CRNERF_CUDA(cudaMemsetAsync(stw, 0, 32 * sizeof(float), st));
   absmax_kernel<<<2 * num_sms(), 256, 0, st>>>(d_rgb, P * 64, stw + kStTop);

@@ -112,7 +112,7 @@ struct RenderParams {
   float* depth;
   float* raw;
   uint16_t* acts;    // training: per-layer A-operand activations (see crnerf_render_pass_train)
-  float* raw_save;   // training: (n_points, 65) [sigmoid features | softplus sigma]
+  float* raw_save;   // training: (n_points, 64) sigmoid features, then the n_points softplus sigmas
   float* dbg;
   long long* prof;  // optional cycle counters of CTA 0 (tests / profiling only)
   int exp;          // profiling experiments (debug instantiation only): 1 = epilogue skips TMEM
@@ -1136,7 +1136,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
           pc_sync(7 + b);
           sigma = softplus_ref(sig_acc + M->sig_part[b][row] + blob[kSigmaBOff]);
           if constexpr (kSave) {
-            if (P.raw_save != nullptr && valid) P.raw_save[p * 65 + 64] = sigma;
+            if (P.raw_save != nullptr && valid) P.raw_save[(long long)P.n_points * 64 + p] = sigma;   // sigmas behind the feature rows
           }
           if (!raw_mode) {
             const long long ray = valid ? ray_first + seg_of_row : 0;
@@ -1271,6 +1271,7 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
         }
         uint32_t v[32];
         float wf[32];
+        [[maybe_unused]] float fsave[8];
         float sticky = 0.f;     // NaN once any rgb pre-activation is inf / NaN (fp16 operand overflow upstream)
         if (!skip) {
           tmem_ld_x32(tD + 32 * ch, v);
@@ -1288,7 +1289,12 @@ render_fused_kernel(const __grid_constant__ RenderParams P) {
           if constexpr (kFmt == 0 && CRNERF_OVF_MODE == 2) sticky = fmaf(a, 0.f, sticky);
           const float f = __fdividef(1.f, 1.f + __expf(-a));
           if constexpr (kSave) {
-            if (P.raw_save != nullptr && valid) P.raw_save[p * 65 + chn] = f;
+            // saved features: (n_points, 64) rows, this warp's 32 channels as four whole 32-byte sectors
+            fsave[j & 7] = f;
+            if ((j & 7) == 7 && P.raw_save != nullptr && valid)
+              stg_v8(P.raw_save + p * 64 + (chn - 7),
+                     make_uint4(__float_as_uint(fsave[0]), __float_as_uint(fsave[1]), __float_as_uint(fsave[2]), __float_as_uint(fsave[3])),
+                     make_uint4(__float_as_uint(fsave[4]), __float_as_uint(fsave[5]), __float_as_uint(fsave[6]), __float_as_uint(fsave[7])));
           }
           if (raw_mode) {
             if (valid && !skip && !(P.mode & kModeSigmaOnly)) P.raw[p * 65 + chn] = f;

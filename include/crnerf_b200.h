@@ -140,8 +140,11 @@ int crnerf_render_pass_opts(const void* packed, int operand, const float* rays, 
  *         Slots: 0..8 = outputs of xyz_encoding_1..8 (post-ReLU) and xyz_encoding_final (256
  *         wide each), 9 = dir_encoding output (post-ReLU, 128 wide), 10 = the embedding tile
  *         (columns [0, e_xyz) xyz embedding, [96, 96 + e_dir) direction embedding).
- *   raw   (n_points, 65) fp32 = [sigmoid features | softplus sigma]   (models/nerf.py:180-181)
- * crnerf_composite_backward is the backward of rendering.py:116-143: from the gradients of
+ *   raw   65 * n_points fp32: the sigmoid features as (n_points, 64) rows, then the n_points softplus
+ *         sigmas (models/nerf.py:180-181's columns, split so that a point's features are whole
+ *         32-byte sectors); consumed by crnerf_render_backward only
+ * crnerf_composite_backward is the backward of rendering.py:116-143 (raw here = (n_points, 65) rows
+ * [features | sigma] as NeRF_sigma.forward returns them): from the gradients of
  * feature (n_rays,64), weights (n_rays,n_samples), depth (n_rays) (each may be NULL) to the
  * gradients of the pre-sigmoid features d_rgb_pre (n_points,64) and of the pre-softplus
  * density d_sigma_pre (n_points).  n_samples <= 1024.
