@@ -226,6 +226,7 @@ struct WgradParams {
   int g_slabs, x_slabs_total, xs0, nxs;
   int nrows;            // valid rows (output features)
   int n_tiles;
+  int x_dead;           // no later kernel of this pass reads these X slabs: stream them through the L2
 };
 // one product's share of the reduce kernel
 struct ReduceJob {
@@ -324,18 +325,27 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
 
   if (warp == 0) {
     if (elect_one()) {
+      // Tiles in DESCENDING order: the dgrad kernel that ran just before this one wrote G in ascending order, so
+      // the highest tiles are what the L2 still holds; the dgrad that follows re-reads G and X from the low end,
+      // where this kernel ends (G + X of one 256-wide layer at 131 k points = 134 MB against 126 MB of L2).
+      // x_dead: no later kernel reads these X slabs (evict-first).
+      const uint64_t pol_x = P.x_dead ? l2_policy_evict_first() : 0;
       for (int s = 0; s < n_steps; ++s) {
         const int st = s % kWgStages, n = s / kWgStages;
         mbar_wait(&empty[st], (n & 1) ^ 1, 1);
-        const size_t tile = (size_t)blockIdx.x + (size_t)(s >> 1) * gridDim.x;
+        const size_t tile = (size_t)P.n_tiles - 1 - ((size_t)blockIdx.x + (size_t)(s >> 1) * gridDim.x);
         const int h = s & 1;
         uint8_t* dst = smem + st * stage_bytes;
         mbar_arrive_expect_tx(&full[st], (uint32_t)((P.g_slabs + P.nxs) * kHalf));
         for (int j = 0; j < P.g_slabs; ++j)
           bulk_g2s(dst + j * kHalf, P.g + (tile * P.g_slabs + j) * kSlab + h * kHalf, kHalf, &full[st]);
-        for (int j = 0; j < P.nxs; ++j)
-          bulk_g2s(dst + (ga + j) * kHalf, P.x + (tile * P.x_slabs_total + P.xs0 + j) * kSlab + h * kHalf, kHalf,
-                   &full[st]);
+        for (int j = 0; j < P.nxs; ++j) {
+          const uint8_t* src = P.x + (tile * P.x_slabs_total + P.xs0 + j) * kSlab + h * kHalf;
+          if (P.x_dead)
+            bulk_g2s_hint(dst + (ga + j) * kHalf, src, kHalf, &full[st], pol_x);
+          else
+            bulk_g2s(dst + (ga + j) * kHalf, src, kHalf, &full[st]);
+        }
       }
     }
     __syncwarp();
@@ -383,8 +393,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
           uint4* dst = reinterpret_cast<uint4*>(part + (size_t)rowf * n_mma + c0);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            stg_v8(dst + 2 * j, make_uint4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
-                   make_uint4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]));
+            stg_v8_cs(dst + 2 * j, make_uint4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),   // read once, by the
+                      make_uint4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]));               // pass's last kernel
         }
       }
     }
@@ -458,6 +468,9 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_kernel(const __grid_const
     if (elect_one()) {
       mbar_arrive_expect_tx(w_full, (uint32_t)w_bytes);
       for (int o = 0; o < w_bytes; o += 32768) bulk_g2s(sW + o, P.wimg + o, (uint32_t)min(32768, w_bytes - o), w_full);
+      // G is dead after this kernel (its wgrad ran before), and so is the mask source: evict-first, so that what
+      // stays in the L2 is the output tiles, which the next wgrad reads from the high end, where this kernel ends
+      const uint64_t pol_g = l2_policy_evict_first();
       int s = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const size_t tile = (size_t)blockIdx.x + (size_t)i * gridDim.x;
@@ -466,7 +479,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_kernel(const __grid_const
           mbar_wait(&empty[st], (n & 1) ^ 1, 1);
           const int ns = k == spt - 1 ? slabs_last : 2;
           mbar_arrive_expect_tx(&full[st], (uint32_t)(ns * kSlab));
-          bulk_g2s(ring + st * kDgStageBytes, P.g + (tile * P.g_slabs + 2 * k) * kSlab, (uint32_t)(ns * kSlab), &full[st]);
+          bulk_g2s_hint(ring + st * kDgStageBytes, P.g + (tile * P.g_slabs + 2 * k) * kSlab, (uint32_t)(ns * kSlab), &full[st],
+                        pol_g);
         }
       }
     }
@@ -516,6 +530,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_kernel(const __grid_const
     if (blockIdx.x == 0 && warp == 2 && lane == 0) P.st[kStScale + P.stage + 1] = s_in * r;
     float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
     float amax_out = 0.f;
+    const uint64_t pol_dead = l2_policy_evict_first();   // the mask source's last reader (its wgrad ran before)
     for (int i = 0; i < my_tiles; ++i) {
       const int buf = i & 1;
       const size_t tile = (size_t)blockIdx.x + (size_t)i * gridDim.x;
@@ -536,7 +551,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_kernel(const __grid_const
           const uint4* arow = reinterpret_cast<const uint4*>(
               P.act + ((size_t)tile * P.act_slabs_total + P.act_s0 + slab) * kSlab + row * 128);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ldg_row_pair(arow, (uint32_t)k, (uint32_t)(row & 7), m[2 * k], m[2 * k + 1]);
+          for (int k = 0; k < 4; ++k) ldg_row_pair(arow, (uint32_t)k, (uint32_t)(row & 7), m[2 * k], m[2 * k + 1], pol_dead);
         }
         tmem_ld_wait();
         if (gidx + 2 >= groups) {   // last read of this accumulator
@@ -759,8 +774,8 @@ static int backward_chain(const crnerf_mlp_weights* w, const void* acts, const f
   const int wg_grid = std::min(num_sms(), T);
   float* part_next = reinterpret_cast<float*>(base + sc.partial);
   auto wgrad = [&](const uint8_t* g, int g_slabs, const uint8_t* x, int xtot, int xs0, int nxs, float* dw, int ldw,
-                   int c0, int xcol0, int ncols, int nrows) {
-    WgradParams wp{g, x, part_next, g_slabs, xtot, xs0, nxs, nrows, T};
+                   int c0, int xcol0, int ncols, int nrows, int x_dead = 0) {
+    WgradParams wp{g, x, part_next, g_slabs, xtot, xs0, nxs, nrows, T, x_dead};
     red.job[red.n_jobs++] = ReduceJob{part_next, dw, stw + kStScale + stage, wg_grid, nrows, nxs * 64, ldw, c0, xcol0, ncols};
     part_next += (size_t)wg_grid * nrows * nxs * 64;
     return run_wgrad<kFmt>(wp, st);
@@ -780,7 +795,7 @@ static int backward_chain(const crnerf_mlp_weights* w, const void* acts, const f
   CK_(wgrad(g_rgb, 1, slot(9), 2, 0, 2, gw[kLRgb], 128, 0, 0, 128, 64));
   CK_(dgrad(g_rgb, 1, 9, slot(9), 2, 0, gbuf[0], gb[kLDir], nullptr));                 // -> Gm_dir (P x 128)
   // dir_encoding (128 x (256 + e_dir)): X = [final | dir embedding = columns 96.. of the embedding tile]
-  CK_(wgrad(gbuf[0], 2, slot(8), 4, 0, 4, gw[kLDir], 256 + e_dir, 0, 0, 256, 128));
+  CK_(wgrad(gbuf[0], 2, slot(8), 4, 0, 4, gw[kLDir], 256 + e_dir, 0, 0, 256, 128, 1));
   CK_(wgrad(gbuf[0], 2, slot(10), 2, 1, 1, gw[kLDir], 256 + e_dir, 256, kDirCol0 - 64, e_dir, 128));
   CK_(dgrad(gbuf[0], 2, 8, nullptr, 0, 0, gbuf[1], gb[kLFinal], nullptr));             // -> Gm_final (P x 256)
   // xyz_encoding_final (256 x 256): X = h8; the sigma head joins below it
@@ -795,7 +810,7 @@ static int backward_chain(const crnerf_mlp_weights* w, const void* acts, const f
     CK_(dgrad(gbuf[cur], 4, l - 1, slot(l - 1), 4, 0, gbuf[cur ^ 1], gb[l - 1], nullptr));
     cur ^= 1;
   }
-  CK_(wgrad(gbuf[cur], 4, slot(10), 2, 0, 2, gw[0], e_xyz, 0, 0, e_xyz, 256));          // layer 0: X = xyz embedding
+  CK_(wgrad(gbuf[cur], 4, slot(10), 2, 0, 2, gw[0], e_xyz, 0, 0, e_xyz, 256, 1));       // layer 0: X = xyz embedding
 #undef CK_
   // all 13 weight gradients: sum the per-CTA partials (fixed order)
   wgrad_reduce_kernel<<<dim3(64, red.n_jobs), 256, 0, st>>>(red);

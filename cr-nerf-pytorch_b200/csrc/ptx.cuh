@@ -99,6 +99,12 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// L2 policy for data that is dead after this read (streams that must not displace what the next kernel re-reads)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 // same, with an L2 cache-policy hint (weights are re-read by every CTA: keep)
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t pol;
@@ -132,6 +138,12 @@ __device__ __forceinline__ void stg_v8(void* p, const uint4& a, const uint4& b) 
                "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
                : "memory");
 }
+// streaming form (evict-first in L2): written once, read once much later
+__device__ __forceinline__ void stg_v8_cs(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 __device__ __forceinline__ void ldg_nc_v8(const void* p, uint4& a, uint4& b) {
   asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
@@ -143,9 +155,15 @@ __device__ __forceinline__ void stg_row_pair(uint4* row, uint32_t k, uint32_t rx
   const bool sw = (rx & 1u) != 0u;
   stg_v8(row + ((2u * k) ^ (rx & 6u)), sw ? c_odd : c_even, sw ? c_even : c_odd);
 }
-__device__ __forceinline__ void ldg_row_pair(const uint4* row, uint32_t k, uint32_t rx, uint4& c_even, uint4& c_odd) {
+__device__ __forceinline__ void ldg_nc_v8_hint(const void* p, uint4& a, uint4& b, uint64_t policy) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p), "l"(policy));
+}
+__device__ __forceinline__ void ldg_row_pair(const uint4* row, uint32_t k, uint32_t rx, uint4& c_even, uint4& c_odd,
+                                             uint64_t policy) {
   uint4 a, b;
-  ldg_nc_v8(row + ((2u * k) ^ (rx & 6u)), a, b);
+  ldg_nc_v8_hint(row + ((2u * k) ^ (rx & 6u)), a, b, policy);
   const bool sw = (rx & 1u) != 0u;
   c_even = sw ? b : a;
   c_odd = sw ? a : b;
