@@ -250,7 +250,12 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant
   const int n = J.nrows * J.n_mma;
   const int i = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (i >= n) return;
-  const int row = i / J.n_mma, col = i % J.n_mma;
+  int row = i / J.n_mma, col = i % J.n_mma;
+  if (J.nrows % 128 == 0) {   // tiled partial (wgrad_kernel's staged epilogue): [128-row block][4-column group][row][4]
+    const int f4 = i >> 2, blk = (J.n_mma / 4) * 128, rem = f4 % blk;
+    row = (f4 / blk) * 128 + rem % 128;
+    col = (rem / 128) * 4;
+  }
   if (col + 3 < J.xcol0 || col >= J.xcol0 + J.ncols) return;
   const float4* p = reinterpret_cast<const float4*>(J.partial + i);
   const size_t stride = (size_t)n / 4;
@@ -378,6 +383,40 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       mbar_wait(done, 0, 3);
       tc_fence_after_sync();
     }
+    if (P.nrows == m_halves * 128) {
+      // Whole 128-row blocks: staged through the (now idle) operand ring and written with bulk copies.  A chunk =
+      // 32 columns of one block = 16 KB laid out [4-column group (8)][row (128)][16 B]: a lane's stores are 16 B
+      // apart (conflict-free) and the chunk leaves as full-line writes (a thread-per-row store to the 1 KB rows of
+      // a plain [row][column] partial touches 32 lines per request: 9 us of a 29 us kernel).  The partial keeps this
+      // tiled order, [block][4-column group][row][4]; wgrad_reduce_kernel decodes it.  Four buffers in rotation.
+      const int trow = q * 32 + lane;
+      const bool issuer = warp == 2 && lane == 0;
+      int ci = 0;
+      for (int mh = 0; mh < m_halves; ++mh) {
+        for (int c0 = 0; c0 < n_mma; c0 += 32, ++ci) {
+          uint32_t v[32];
+          if (n_steps > 0) {
+            tmem_ld_x32(tmem + (uint32_t)mh * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
+          uint8_t* buf = smem + (ci & 3) * 16384;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(buf + j * 2048 + trow * 16) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_proxy_async_smem();
+          if (issuer) bulk_wait_group_read<2>();   // the buffer of chunk ci + 1 (written after this barrier) has drained
+          named_bar_sync(1, 128);
+          if (issuer) {
+            bulk_s2g(part + ((size_t)mh * (n_mma / 4) + c0 / 4) * 512, buf, 16384);
+            bulk_commit_group();
+          }
+        }
+      }
+      if (issuer) bulk_wait_group_all();
+    } else
     for (int mh = 0; mh < m_halves; ++mh) {
       const int rowf = mh * 128 + q * 32 + lane;
       for (int c0 = 0; c0 < n_mma; c0 += 32) {

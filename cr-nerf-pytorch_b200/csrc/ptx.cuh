@@ -99,6 +99,26 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// shared -> global bulk copy (SASS UBLKCP.G.S): the store half of the TMA-style epilogue - threads fill a shared
+// staging buffer (conflict-free), fence_proxy_async_smem(), a barrier, then ONE thread moves the whole block as
+// full-line writes.  Completion is tracked per thread in bulk groups.
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most kPending of this thread's bulk groups still READING their shared-memory source
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// named barrier among `threads` threads (a multiple of 32) of the CTA
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // L2 policy for data that is dead after this read (streams that must not displace what the next kernel re-reads)
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t pol;
