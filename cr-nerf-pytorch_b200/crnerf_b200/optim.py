@@ -70,6 +70,15 @@ class Adam(torch.optim.Optimizer):
         self._group_step[gi] = shared
         return shared
 
+    def state_dict(self):
+        """torch.optim.Adam's layout.  The live state shares ONE step counter per group; a consumer that
+        increments every parameter's ``step`` (torch.optim.Adam after ``load_state_dict``, which keeps the
+        tensors it is given) must receive separate tensors."""
+        sd = super().state_dict()
+        sd["state"] = {k: ({**v, "step": v["step"].clone()} if isinstance(v.get("step"), torch.Tensor) else v)
+                       for k, v in sd["state"].items()}
+        return sd
+
     def _table(self, gi: int, plist):
         st = [self.state[p] for p in plist]
         key = tuple((p.data_ptr(), p.grad.data_ptr(), s["exp_avg"].data_ptr(), s["exp_avg_sq"].data_ptr(), p.numel())

@@ -246,6 +246,7 @@ struct ReduceParams {
 // dW[row][c0 + col - xcol0] = (sum over CTAs of partial[cta][row][col]) / scale, fixed order.
 // One thread per four consecutive columns (16-byte loads), eight partials in flight.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ ReduceParams P) {
+  pdl_wait();   // the last wgrad of the pass (and, through the chain, every kernel before it)
   const ReduceJob& J = P.job[blockIdx.y];
   const int n = J.nrows * J.n_mma;
   const int i = (blockIdx.x * 256 + threadIdx.x) * 4;
@@ -321,6 +322,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();      // everything above overlapped the previous kernel's tail
+  pdl_trigger();
   // this CTA's half-tiles: tiles blockIdx.x, blockIdx.x + gridDim.x, ...
   int my_tiles = 0;
   for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) ++my_tiles;
@@ -498,6 +501,15 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_kernel(const __grid_const
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  // the weight image was packed at the head of the pass (several kernels ago): its load, like everything above,
+  // overlaps the previous kernel's tail
+  if (warp == 0 && elect_one()) {
+    mbar_arrive_expect_tx(w_full, (uint32_t)w_bytes);
+    for (int o = 0; o < w_bytes; o += 32768) bulk_g2s(sW + o, P.wimg + o, (uint32_t)min(32768, w_bytes - o), w_full);
+  }
+  __syncwarp();
+  pdl_wait();
+  pdl_trigger();
   int my_tiles = 0;
   for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) ++my_tiles;
   const int spt = (P.g_slabs + 1) / 2;           // stages per tile
@@ -505,8 +517,6 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_kernel(const __grid_const
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_arrive_expect_tx(w_full, (uint32_t)w_bytes);
-      for (int o = 0; o < w_bytes; o += 32768) bulk_g2s(sW + o, P.wimg + o, (uint32_t)min(32768, w_bytes - o), w_full);
       // G is dead after this kernel (its wgrad ran before), and so is the mask source: evict-first, so that what
       // stays in the L2 is the output tiles, which the next wgrad reads from the high end, where this kernel ends
       const uint64_t pol_g = l2_policy_evict_first();
@@ -745,13 +755,29 @@ int composite_backward(const float* raw, const float* z, const float* noise, con
                        const float* g_weights, const float* g_depth, int n_rays, int n_samples,
                        float* d_rgb_pre, float* d_sigma_pre, cudaStream_t st, int split);
 
+// launch with programmatic stream serialization (the kernel calls pdl_wait() before its first dependent access)
+template <typename Kern, typename Params>
+static cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Params& p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
 template <int kFmt>
 static int run_wgrad(const WgradParams& w, cudaStream_t st) {
   const int ga = w.g_slabs < 2 ? 2 : w.g_slabs;
   const size_t smem = (size_t)kWgStages * (ga + w.nxs) * kHalf + 256;
   CRNERF_CUDA(cudaFuncSetAttribute(wgrad_kernel<kFmt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(num_sms(), w.n_tiles);
-  wgrad_kernel<kFmt><<<grid, 192, smem, st>>>(w);
+  CRNERF_CUDA(launch_pdl(wgrad_kernel<kFmt>, dim3(grid), dim3(192), smem, st, w));
   count_launch();
   return CRNERF_OK;
 }
@@ -760,7 +786,7 @@ static int run_dgrad(const DgradParams& d, cudaStream_t st) {
   const size_t smem = (size_t)d.g_slabs * d.k_in * 128 + kDgStages * kDgStageBytes + 256 + 1024;
   CRNERF_CUDA(cudaFuncSetAttribute(dgrad_kernel<kFmt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(num_sms(), d.n_tiles);
-  dgrad_kernel<kFmt><<<grid, kDgThreads, smem, st>>>(d);
+  CRNERF_CUDA(launch_pdl(dgrad_kernel<kFmt>, dim3(grid), dim3(kDgThreads), smem, st, d));
   count_launch();
   return CRNERF_OK;
 }
@@ -852,7 +878,7 @@ static int backward_chain(const crnerf_mlp_weights* w, const void* acts, const f
   CK_(wgrad(gbuf[cur], 4, slot(10), 2, 0, 2, gw[0], e_xyz, 0, 0, e_xyz, 256, 1));       // layer 0: X = xyz embedding
 #undef CK_
   // all 13 weight gradients: sum the per-CTA partials (fixed order)
-  wgrad_reduce_kernel<<<dim3(64, red.n_jobs), 256, 0, st>>>(red);
+  CRNERF_CUDA(launch_pdl(wgrad_reduce_kernel, dim3(64, red.n_jobs), dim3(256), 0, st, red));
   count_launch();
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;

@@ -119,6 +119,15 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start (prologue: barrier init, TMEM allocation, loads of data no recent kernel wrote) while its predecessor
+// drains; pdl_wait() returns once the predecessor grid has completed and its writes are visible, pdl_trigger()
+// lets the successor's CTAs be scheduled as this grid's CTAs retire.  Every kernel of such a chain calls
+// pdl_wait() before its first dependent access and pdl_trigger() only after it, so that past its own wait a kernel
+// sees ALL earlier kernels complete, and before it everything but the immediate predecessor.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // L2 policy for data that is dead after this read (streams that must not displace what the next kernel re-reads)
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t pol;

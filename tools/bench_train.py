@@ -124,6 +124,8 @@ def measure(dev, world, rank, barrier, reps=10, warm=3, n_rays=1024, ns=64, ni=6
     out["train"] = {"workload": f"{n_rays}-ray (32x32) patch per rank x ({ns}+{ni}) samples, perturb=1, noise_std=1, "
                                 "style_net decode of coarse and fine, MSE, backward, Adam",
                     "parallelism": f"data parallel x{world}, one flat gradient all-reduce ({flat_n * 4} B) per step",
+                    "optimizer": "crnerf_b200.optim.Adam (csrc/optim.cu, torch.optim.Adam's update as one launch per 48 tensors)"
+                                 if OPTIMIZER == "native" else "torch.optim.Adam",
                     "reps": reps, "warmup": warm, "timing": "CUDA events over the reps, max over ranks"}
     return out
 
