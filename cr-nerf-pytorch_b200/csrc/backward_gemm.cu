@@ -465,7 +465,7 @@ struct DgradParams {
 };
 constexpr int kDgStages = 3;
 constexpr int kDgStageBytes = 2 * kSlab;   // up to two 64-feature slabs of G per stage
-constexpr int kDgThreads = 320;            // producer, issuer, 8 epilogue warps
+constexpr int kDgThreads = 576;            // producer, issuer, 16 epilogue warps (4 lane quarters x 4 output slabs)
 
 template <int kFmt>
 __global__ void __launch_bounds__(kDgThreads, 1) dgrad_kernel(const __grid_constant__ DgradParams P) {
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_kernel(const __grid_const
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&d_full[i], 1);
-      mbar_init(&d_empty[i], 8);
+      mbar_init(&d_empty[i], (uint32_t)(4 * (P.k_in / 64)));   // epilogue warps that own a slab
     }
     fence_mbar_init();
   }
@@ -562,10 +562,14 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_kernel(const __grid_const
       }
     }
   } else {
-    // ---- epilogue: 8 warps = TMEM lane quarter (warp % 4) x column half
-    const int q = warp & 3, ch = (warp - 2) >> 2;
+    // ---- epilogue: 16 warps = TMEM lane quarter (warp % 4) x 64-column slab of the output (4 for a 256-wide
+    // layer below, 2 for a 128-wide one: the other warps idle).  A warp walks its slab in two 32-column halves, so
+    // that 18 warps fit the register file (112 registers each); with 8 warps x two slabs the epilogue - a
+    // dependent chain accumulator -> mask rows (an L2 / HBM round trip) -> mask, rescale, pack -> store per slab -
+    // was what bounded the kernel (~5.5 us per tile against 1.1 us of MMAs).
+    const int q = warp & 3, slab = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const int cols_half = P.k_in / 2, groups = cols_half / 32;   // 32-column groups of this warp (4 or 2)
+    if (slab < P.k_in / 64) {
     const float s_in = P.st[kStScale + P.stage];
     // stored units of the input stage -> of the output stage.  The sigma-head term joined below
     // (|d_sigma| <= the top max, st[kStTop]) must fit as well.
@@ -577,50 +581,49 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_kernel(const __grid_const
     }
     const float r = recentre(in_max);
     if (blockIdx.x == 0 && warp == 2 && lane == 0) P.st[kStScale + P.stage + 1] = s_in * r;
-    float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
+    float dbacc[2] = {0.f, 0.f};
     float amax_out = 0.f;
     const uint64_t pol_dead = l2_policy_evict_first();   // the mask source's last reader (its wgrad ran before)
+    const uint32_t rx = (uint32_t)(row & 7);
     for (int i = 0; i < my_tiles; ++i) {
       const int buf = i & 1;
       const size_t tile = (size_t)blockIdx.x + (size_t)i * gridDim.x;
       const long long p = (long long)tile * 128 + row;
       const bool valid = p < P.n_points;
       const float ds = (P.dsig && valid) ? __ldg(P.dsig + p) * s_in : 0.f;
+      // the mask rows do not depend on the MMAs: requested before the wait for the accumulator
+      uint4 m[8];
+      if (P.act) {
+        const uint4* arow = reinterpret_cast<const uint4*>(
+            P.act + ((size_t)tile * P.act_slabs_total + P.act_s0 + slab) * kSlab + row * 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ldg_row_pair(arow, (uint32_t)k, rx, m[2 * k], m[2 * k + 1], pol_dead);
+      }
+      uint4* orow = reinterpret_cast<uint4*>(P.out + ((size_t)tile * (P.k_in / 64) + slab) * kSlab + row * 128);
       mbar_wait(&d_full[buf], (i >> 1) & 1, 5);
       tc_fence_after_sync();
-      for (int gidx = 0; gidx < groups; gidx += 2) {
-        // two 32-column groups = one 64-column slab of the output / of the mask source
-        const int col0 = ch * cols_half + gidx * 32;
-        const int slab = col0 >> 6;
-        uint32_t va[32], vb[32];
-        tmem_ld_x32(tmem + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, va);
-        tmem_ld_x32(tmem + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)col0 + 32u, vb);
-        uint4 m[8];
-        if (P.act) {
-          const uint4* arow = reinterpret_cast<const uint4*>(
-              P.act + ((size_t)tile * P.act_slabs_total + P.act_s0 + slab) * kSlab + row * 128);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ldg_row_pair(arow, (uint32_t)k, (uint32_t)(row & 7), m[2 * k], m[2 * k + 1], pol_dead);
-        }
+      for (int h = 0; h < 2; ++h) {
+        const int col0 = slab * 64 + h * 32;
+        uint32_t v[32];
+        tmem_ld_x32(tmem + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
         tmem_ld_wait();
-        if (gidx + 2 >= groups) {   // last read of this accumulator
+        if (h == 1) {   // last read of this accumulator
           tc_fence_before_sync();
           warp_arrive_bar(&d_empty[buf]);
         }
-        float x[64];
+        float x[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          x[j] = __uint_as_float(va[j]);
-          x[32 + j] = __uint_as_float(vb[j]);
-        }
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
         if (P.dsig) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) x[j] = fmaf(ds, s_wsig[col0 + j], x[j]);
+          for (int j = 0; j < 32; ++j) x[j] = fmaf(ds, s_wsig[col0 + j], x[j]);
         }
         if (P.act) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint32_t w4[4] = {m[c].x, m[c].y, m[c].z, m[c].w};
+          for (int c = 0; c < 4; ++c) {
+            const uint4 mc = m[4 * h + c];
+            const uint32_t w4[4] = {mc.x, mc.y, mc.z, mc.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const uint32_t lo = w4[e] & 0xffffu, hi = w4[e] >> 16;
@@ -631,40 +634,33 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_kernel(const __grid_const
           }
         }
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
+        for (int j = 0; j < 32; ++j) {
           x[j] = valid ? x[j] * r : 0.f;
           amax_out = fmaxf(amax_out, fabsf(x[j]));
         }
         // 16-bit tile of the layer below
-        uint4* orow = reinterpret_cast<uint4*>(P.out + ((size_t)tile * (P.k_in / 64) + slab) * kSlab + row * 128);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 2; ++k) {
           uint32_t w[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) w[e] = pack2<kFmt, false>(x[16 * k + 2 * e], x[16 * k + 2 * e + 1]);
-          stg_row_pair(orow, (uint32_t)k, (uint32_t)(row & 7), make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
+          stg_row_pair(orow, (uint32_t)(2 * h + k), rx, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
         }
-        // bias gradient: column sums over the warp's 32 rows (transposing butterfly)
-        if (P.db) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float t[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) t[j] = x[32 * h + j];
-            dbacc[gidx + h] += warp_colsum32(t, lane);
-          }
-        }
+        // bias gradient: column sums over the warp's 32 rows (transposing butterfly, in place)
+        if (P.db) dbacc[h] += warp_colsum32(x, lane);
       }
     }
     if (P.db && my_tiles > 0) {
       const float inv = 1.f / (s_in * r);
-      for (int gidx = 0; gidx < groups; ++gidx) atomicAdd(P.db + ch * cols_half + gidx * 32 + lane, dbacc[gidx] * inv);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) atomicAdd(P.db + slab * 64 + h * 32 + lane, dbacc[h] * inv);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) amax_out = fmaxf(amax_out, __shfl_xor_sync(0xffffffffu, amax_out, d));
     if (lane == 0 && amax_out > 0.f) {
       amax_out = fminf(amax_out, 65504.f);
       atomicMax(reinterpret_cast<unsigned int*>(P.st + P.stage + 1), __float_as_uint(amax_out));
+    }
     }
   }
   tc_fence_before_sync();
