@@ -88,6 +88,20 @@ chain_backward_kernel(const __grid_constant__ ChainParams P) {
   int off[kMaxLayers + 1];
   off[0] = 0;
   for (int l = 0; l < nl; ++l) off[l + 1] = off[l] + J.L[l].K;   // input of layer l at off[l]; final output at off[nl]
+  // The chain's weights, staged once: a CTA touches every weight only twice per tile (forward, input gradient), so
+  // from global memory each of those reads was a cold L2 round trip inside a dependent FMA chain - the kernel ran at
+  // L2 latency.  Rows padded to K + 1 floats: the forward's four rows per warp land in different banks.
+  extern __shared__ float wsm[];
+  int woff[kMaxLayers];
+  {
+    int o = 0;
+    for (int l = 0; l < nl; ++l) {
+      woff[l] = o;
+      const ChainLayer& L = J.L[l];
+      for (int e = tid; e < L.N * L.K; e += 256) wsm[o + (e / L.K) * (L.K + 1) + e % L.K] = __ldg(L.W + e);
+      o += L.N * (L.K + 1);
+    }
+  }
   const long long n_tiles = (J.n + kTP - 1) / kTP;
   bool first = true;
   for (long long t = lb; t < n_tiles; t += J.n_blocks, first = false) {
@@ -107,7 +121,7 @@ chain_backward_kernel(const __grid_constant__ ChainParams P) {
         const int p = e % kTP, j = e / kTP;
         float acc = L.b ? L.b[j] : 0.f;
         if (L.b2) acc += L.b2[j];
-        const float* w = L.W + (long long)j * L.K;
+        const float* w = wsm + woff[l] + j * (L.K + 1);
         const float* in = acts + p * kActStride + off[l];
 #pragma unroll 8
         for (int k = 0; k < L.K; ++k) acc = fmaf(w[k], in[k], acc);
@@ -158,9 +172,9 @@ chain_backward_kernel(const __grid_constant__ ChainParams P) {
       for (int e = tid; e < kTP * L.K; e += 256) {   // g_in[p][k] = sum_j W[j][k] g[p][j]
         const int p = e % kTP, k = e / kTP;
         float acc = 0.f;
-        const float* w = L.W + k;
+        const float* w = wsm + woff[l] + k;
 #pragma unroll 8
-        for (int j = 0; j < L.N; ++j) acc = fmaf(w[(long long)j * L.K], g_out[p * kGStride + j], acc);
+        for (int j = 0; j < L.N; ++j) acc = fmaf(w[j * (L.K + 1)], g_out[p * kGStride + j], acc);
         g_in[p * kGStride + k] = acc;
       }
       __syncthreads();
@@ -181,16 +195,21 @@ chain_backward_kernel(const __grid_constant__ ChainParams P) {
   }
 }
 
-// out[i] = sum_b partial[b][i], fixed order: one warp per element, lanes stride the slots
-__global__ void __launch_bounds__(256)
+// out[i] = sum_b partial[b][i], fixed order: one thread per element (coalesced across the block), eight slots in
+// flight per thread, partial sums combined in a fixed tree
+__global__ void __launch_bounds__(128)
 reduce_slots_kernel(const float* __restrict__ partial, int n_slots, int len, float* __restrict__ out) {
-  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 128 + threadIdx.x;
   if (i >= len) return;
-  float acc = 0.f;
-  for (int b = lane; b < n_slots; b += 32) acc += partial[(long long)b * len + i];
+  const float* p = partial + i;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int b = 0;
+  for (; b + 7 < n_slots; b += 8) {
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-  if (lane == 0) out[i] = acc;
+    for (int u = 0; u < 8; ++u) acc[u] += __ldcs(p + (long long)(b + u) * len);
+  }
+  for (; b < n_slots; ++b) acc[0] += __ldcs(p + (long long)b * len);
+  out[i] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
 }
 
 // dS = dT C^T, dC = S^T dT  (T = S C, MulLayer.forward :86); also the fc bias gradients (= dc, ds)
@@ -323,11 +342,20 @@ size_t style_backward_scratch_floats(int64_t n, int64_t m) {
   return bwd_off_gx() + (size_t)(2 * n + m) * 64;
 }
 
+// dynamic shared memory of chain_backward_kernel: the job's weights with rows padded by one float
+static size_t chain_wsm_bytes(const ChainJob& j) {
+  size_t f = 0;
+  for (int l = 0; l < j.n_layers; ++l) f += (size_t)j.L[l].N * (j.L[l].K + 1);
+  return f * sizeof(float);
+}
+
 int style_backward(const crnerf_style_weights* w, const float* content, int64_t n, int64_t ps, int64_t cs,
                    const float* style, int64_t m, int64_t sps, int64_t scs, const float* aux, const float* g_rgb,
                    float* g_content, float* g_style, float* grads, float* scratch, cudaStream_t st) {
   CRNERF_REQUIRE(w && content && style && aux && g_rgb && g_content && g_style && grads && scratch, "null argument");
   CRNERF_REQUIRE(n >= 1 && m >= 1, "empty map");
+  // 22 KB static + up to 75 KB of staged weights: two CTAs per SM
+  CRNERF_CUDA(cudaFuncSetAttribute(chain_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
   float* partA = scratch;
   float* partB = scratch + bwd_off_partB();
   float* fcpart = scratch + bwd_off_fcpart();
@@ -361,14 +389,14 @@ int style_backward(const crnerf_style_weights* w, const float* content, int64_t 
   ja.colsum_off = kA_colsum;
   ja.first_block = 0;
   ja.n_blocks = blocks_for(n);
-  chain_backward_kernel<<<ja.n_blocks, 256, 0, st>>>(A);
-  reduce_slots_kernel<<<(kA_len + 7) / 8, 256, 0, st>>>(partA, ja.n_blocks, kA_len, grads + kG_head);
+  chain_backward_kernel<<<ja.n_blocks, 256, chain_wsm_bytes(ja), st>>>(A);
+  reduce_slots_kernel<<<(kA_len + 127) / 128, 128, 0, st>>>(partA, ja.n_blocks, kA_len, grads + kG_head);
   // ---- 32x32 algebra and the FC layers
   float* head = grads + kG_head;
   style_mid_kernel<<<1, 256, 0, st>>>(head + kA_dT, aux + kAuxC, aux + kAuxS, dC, dS, grads + kG_dfbc, grads + kG_dfbs);
   style_fc_backward_kernel<<<dim3(32, 2), 256, 0, st>>>(w->cnet.fc_w, w->snet.fc_w, dC, dS, aux + kAuxGramC,
                                                         aux + kAuxGramS, grads + kG_dFc, grads + kG_dFs, fcpart);
-  reduce_slots_kernel<<<2048 / 8, 256, 0, st>>>(fcpart, 32, 2048, dvecg);
+  reduce_slots_kernel<<<2048 / 128, 128, 0, st>>>(fcpart, 32, 2048, dvecg);
   // ---- pixel-MLP chains: content with cnet, style with snet, one launch
   ChainParams B{};
   B.n_jobs = 2;
@@ -394,9 +422,9 @@ int style_backward(const crnerf_style_weights* w, const float* content, int64_t 
     jb.n_blocks = blocks_for(jb.n);
     jb.first_block = net ? B.job[0].n_blocks : 0;
   }
-  chain_backward_kernel<<<B.job[0].n_blocks + B.job[1].n_blocks, 256, 0, st>>>(B);
-  reduce_slots_kernel<<<(kB_len + 7) / 8, 256, 0, st>>>(B.job[0].partial, B.job[0].n_blocks, kB_len, grads + kG_cnet);
-  reduce_slots_kernel<<<(kB_len + 7) / 8, 256, 0, st>>>(B.job[1].partial, B.job[1].n_blocks, kB_len, grads + kG_snet);
+  chain_backward_kernel<<<B.job[0].n_blocks + B.job[1].n_blocks, 256, chain_wsm_bytes(B.job[0]), st>>>(B);
+  reduce_slots_kernel<<<(kB_len + 127) / 128, 128, 0, st>>>(B.job[0].partial, B.job[0].n_blocks, kB_len, grads + kG_cnet);
+  reduce_slots_kernel<<<(kB_len + 127) / 128, 128, 0, st>>>(B.job[1].partial, B.job[1].n_blocks, kB_len, grads + kG_snet);
   // ---- mean-subtraction backward; the style mean also enters through the unzip bias (d mu_s = d bu)
   const int gc = (int)std::max<int64_t>(1, std::min<int64_t>((n * 64 + 255) / 256, 4 * num_sms()));
   const int gs = (int)std::max<int64_t>(1, std::min<int64_t>((m * 64 + 255) / 256, 4 * num_sms()));
