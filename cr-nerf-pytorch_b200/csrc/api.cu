@@ -102,7 +102,7 @@ int rgb_to_u8(const float* rgb, int64_t n, uint8_t* out, cudaStream_t st);
 // implemented in backward.cu
 int composite_backward(const float* raw, const float* z, const float* noise, const float* g_feature,
                        const float* g_weights, const float* g_depth, int n_rays, int n_samples,
-                       float* d_rgb_pre, float* d_sigma_pre, cudaStream_t st, int split = 0);
+                       float* d_rgb_pre, float* d_sigma_pre, cudaStream_t st, int split = 0, float* amax = nullptr);
 int relu_bias_grad(float* g, const void* act, int64_t n_points, int width, float* gb, float* scratch,
                    cudaStream_t st);
 // implemented in optim.cu

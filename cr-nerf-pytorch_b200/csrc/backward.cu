@@ -39,7 +39,7 @@ composite_backward_kernel(const float* __restrict__ raw, const float* __restrict
                           const float* __restrict__ noise, const float* __restrict__ g_feature,
                           const float* __restrict__ g_weights, const float* __restrict__ g_depth,
                           int n_rays, int S, int split, float* __restrict__ d_rgb_pre,
-                          float* __restrict__ d_sigma_pre) {
+                          float* __restrict__ d_sigma_pre, float* __restrict__ amax) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ray = blockIdx.x;
@@ -115,7 +115,12 @@ composite_backward_kernel(const float* __restrict__ raw, const float* __restrict
   }
   __syncthreads();
   // pass 3: outputs
-  for (int s = threadIdx.x; s < S; s += 32 * kCbWarps) d_sigma_pre[p0 + s] = gw[s] * dl[s] * sg[s];
+  float am = 0.f;   // max magnitude of everything this thread writes (the backward chain's first scale)
+  for (int s = threadIdx.x; s < S; s += 32 * kCbWarps) {
+    const float v = gw[s] * dl[s] * sg[s];
+    d_sigma_pre[p0 + s] = v;
+    am = fmaxf(am, fabsf(v));
+  }
   for (int c = warp; c < n_chunks; c += kCbWarps) {
     const int s0 = c * 32;
 #pragma unroll
@@ -130,10 +135,17 @@ composite_backward_kernel(const float* __restrict__ raw, const float* __restrict
         }
         const float w = wt[s];
         float* o = d_rgb_pre + (p0 + s) * 64;
-        o[lane] = w * g0 * a0 * (1.f - a0);
-        o[32 + lane] = w * g1 * a1 * (1.f - a1);
+        const float o0 = w * g0 * a0 * (1.f - a0), o1 = w * g1 * a1 * (1.f - a1);
+        o[lane] = o0;
+        o[32 + lane] = o1;
+        am = fmaxf(am, fmaxf(fabsf(o0), fabsf(o1)));
       }
     }
+  }
+  if (amax != nullptr) {   // non-negative floats order like their bit patterns; NaN / inf are left out like absmax_kernel's
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, d));
+    if (lane == 0 && am > 0.f && am < 3.0e38f) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(am));
   }
 }
 
@@ -224,7 +236,7 @@ int relu_bias_grad(float* g, const void* act, int64_t n_points, int width, float
 
 int composite_backward(const float* raw, const float* z, const float* noise, const float* g_feature,
                        const float* g_weights, const float* g_depth, int n_rays, int n_samples,
-                       float* d_rgb_pre, float* d_sigma_pre, cudaStream_t st, int split) {
+                       float* d_rgb_pre, float* d_sigma_pre, cudaStream_t st, int split, float* amax) {
   CRNERF_REQUIRE(raw && z && d_rgb_pre && d_sigma_pre, "null argument");
   CRNERF_REQUIRE(n_samples >= 1 && n_samples <= kMaxS, "n_samples=%d unsupported by the backward (<= %d)",
                  n_samples, kMaxS);
@@ -232,10 +244,10 @@ int composite_backward(const float* raw, const float* z, const float* noise, con
   const size_t smem = (size_t)5 * n_samples * sizeof(float);   // <= 20 KB
   if (n_samples <= 32 * kCbWarps)
     composite_backward_kernel<true><<<n_rays, 32 * kCbWarps, smem, st>>>(raw, z, noise, g_feature, g_weights, g_depth,
-                                                                        n_rays, n_samples, split, d_rgb_pre, d_sigma_pre);
+                                                                        n_rays, n_samples, split, d_rgb_pre, d_sigma_pre, amax);
   else
     composite_backward_kernel<false><<<n_rays, 32 * kCbWarps, smem, st>>>(raw, z, noise, g_feature, g_weights, g_depth,
-                                                                         n_rays, n_samples, split, d_rgb_pre, d_sigma_pre);
+                                                                         n_rays, n_samples, split, d_rgb_pre, d_sigma_pre, amax);
   count_launch();
   CRNERF_CUDA(cudaGetLastError());
   return CRNERF_OK;

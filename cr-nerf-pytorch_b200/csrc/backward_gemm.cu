@@ -164,15 +164,6 @@ __global__ void __launch_bounds__(128) top_pack_kernel(const float* __restrict__
   }
 }
 
-// max(|x|) of a float array into *out (non-negative floats order like their bit patterns)
-__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ a, long long n, float* out) {
-  float m = 0.f;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) m = fmaxf(m, fabsf(a[i]));
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
-  if ((threadIdx.x & 31) == 0 && m > 0.f && m < 3.0e38f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
-}
-
 // ------------------------------------------------------------------------------------------
 // weights for dgrad: W_l^T as K-major SWIZZLE_128B slabs.  Slab j of layer l holds, for every input
 // feature k (row, 128 B), the 64 output features n = 64 j .. 64 j + 63:  element (k, n) = W[n][k0 + k]
@@ -324,10 +315,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   const uint32_t tmem = *tmem_slot;
   pdl_wait();      // everything above overlapped the previous kernel's tail
   pdl_trigger();
-  // this CTA's half-tiles: tiles blockIdx.x, blockIdx.x + gridDim.x, ...
-  int my_tiles = 0;
-  for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) ++my_tiles;
-  const int n_steps = 2 * my_tiles;
+  // this CTA's half-tiles (64 points each): blockIdx.x, blockIdx.x + gridDim.x, ... of the 2 * n_tiles - halves, not
+  // tiles, are dealt out, so that 512 tiles over 148 CTAs cost 7 steps per CTA instead of 8
+  int n_steps = 0;
+  for (int t = blockIdx.x; t < 2 * P.n_tiles; t += gridDim.x) ++n_steps;
   const int m_halves = (P.g_slabs + 1) / 2;   // 128-row blocks of dW
   const int n_mma = P.nxs * 64;
 
@@ -341,8 +332,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       for (int s = 0; s < n_steps; ++s) {
         const int st = s % kWgStages, n = s / kWgStages;
         mbar_wait(&empty[st], (n & 1) ^ 1, 1);
-        const size_t tile = (size_t)P.n_tiles - 1 - ((size_t)blockIdx.x + (size_t)(s >> 1) * gridDim.x);
-        const int h = s & 1;
+        const size_t half = (size_t)2 * P.n_tiles - 1 - ((size_t)blockIdx.x + (size_t)s * gridDim.x);
+        const size_t tile = half >> 1;
+        const int h = (int)(half & 1);
         uint8_t* dst = smem + st * stage_bytes;
         mbar_arrive_expect_tx(&full[st], (uint32_t)((P.g_slabs + P.nxs) * kHalf));
         for (int j = 0; j < P.g_slabs; ++j)
@@ -749,7 +741,7 @@ int render_acts_zero_tail(void* acts, int64_t n_points, cudaStream_t st) {
 
 int composite_backward(const float* raw, const float* z, const float* noise, const float* g_feature,
                        const float* g_weights, const float* g_depth, int n_rays, int n_samples,
-                       float* d_rgb_pre, float* d_sigma_pre, cudaStream_t st, int split);
+                       float* d_rgb_pre, float* d_sigma_pre, cudaStream_t st, int split, float* amax);
 
 // launch with programmatic stream serialization (the kernel calls pdl_wait() before its first dependent access)
 template <typename Kern, typename Params>
@@ -816,13 +808,13 @@ static int backward_chain(const crnerf_mlp_weights* w, const void* acts, const f
   count_launch();
 
   // 2. composite backward -> d_rgb, d_sigma (fp32), their max magnitude, top tiles
-  int rc = composite_backward(raw, z, noise, g_feature, g_weights, g_depth, n_rays, n_samples, d_rgb, d_sig, st, 1);
-  if (rc) return rc;
+  //    (the composite kernel also measures the max magnitude of what it writes: the chain's first scale)
   CRNERF_CUDA(cudaMemsetAsync(stw, 0, 32 * sizeof(float), st));
-  absmax_kernel<<<2 * num_sms(), 256, 0, st>>>(d_rgb, P * 64, stw + kStTop);
-  absmax_kernel<<<num_sms(), 256, 0, st>>>(d_sig, P, stw + kStTop);
+  int rc = composite_backward(raw, z, noise, g_feature, g_weights, g_depth, n_rays, n_samples, d_rgb, d_sig, st, 1,
+                              stw + kStTop);
+  if (rc) return rc;
   top_pack_kernel<kFmt><<<T, 128, 0, st>>>(d_rgb, d_sig, P, stw, g_rgb, g_sig, gb[kLRgb], gb[kLSigma]);
-  count_launch(3);
+  count_launch(1);
 
   // saved activations (tiled16): slots 0..8 (256 wide), 9 = dir (128), 10 = embedding tile (128)
   const uint8_t* A = static_cast<const uint8_t*>(acts);
