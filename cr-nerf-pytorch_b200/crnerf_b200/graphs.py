@@ -93,12 +93,26 @@ class GraphedTrainStep:
     (``torch.optim.Adam(..., capturable=True)``).  Random draws inside ``step_fn`` (stratified
     jitter, density noise) advance with every replay, as torch's graph-safe generator does.
 
-    Multi-GPU: replay the graph, then all-reduce gradients and step outside - or capture per rank
-    and keep the collective out of the graph (``optimizer=None`` skips the step inside)."""
+    Multi-GPU: capture forward + backward per rank (``optimizer=None, parameters=<the trained parameters>``),
+    replay, exchange the gradients (``crnerf_b200.ddp.allreduce_gradients``: one all-reduce per flat
+    gradient buffer) and step the optimizer outside.  ``parameters`` are needed in that form so that their
+    gradients are unset before the capture: the captured backward then WRITES static gradient tensors on
+    every replay instead of accumulating into whatever the warm-up left."""
 
-    def __init__(self, step_fn, optimizer=None, warmup: int = 3, device=None):
+    def __init__(self, step_fn, optimizer=None, warmup: int = 3, device=None, parameters=None):
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.optimizer = optimizer
+        if optimizer is None and parameters is None:
+            raise ValueError("GraphedTrainStep(optimizer=None) needs parameters=: their gradients must be unset "
+                             "before the capture, or every replay would accumulate into the warm-up's")
+        self.parameters = list(parameters) if parameters is not None else None
+
+        def unset_grads():
+            if optimizer is not None:
+                optimizer.zero_grad(set_to_none=True)
+            if self.parameters is not None:
+                for p in self.parameters:
+                    p.grad = None
 
         def whole():
             loss = step_fn()
@@ -111,13 +125,11 @@ class GraphedTrainStep:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):           # eager steps: allocator warm-up, weight-range verdicts
-                if optimizer is not None:
-                    optimizer.zero_grad(set_to_none=True)
+                unset_grads()
                 whole()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        if optimizer is not None:
-            optimizer.zero_grad(set_to_none=True)
+        unset_grads()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = whole()

@@ -45,12 +45,9 @@ def make_step(dev, world, rank, n_rays=1024, ns=64, ni=64, operand="fp16", bwd=N
     flat_n = sum(p.numel() for p in params)
 
     def allreduce_grads():
-        if world > 1:   # what DDP does, as one flat bucket
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat); flat /= world
-            o = 0
-            for p in params:
-                p.grad.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
+        if world > 1:   # one in-place all-reduce per gradient storage (24 for the 68 tensors)
+            from crnerf_b200.ddp import allreduce_gradients
+            allreduce_gradients(params)
 
     def loss_fn():
         res = render_rays_cross_ray(models, emb, rays, None, ns, False, 1.0, 1.0, ni, 32768, False, args=margs)
@@ -69,7 +66,7 @@ def make_step(dev, world, rank, n_rays=1024, ns=64, ni=64, operand="fp16", bwd=N
         opt.step()
         return loss
 
-    step_ours.loss_fn, step_ours.opt = loss_fn, opt
+    step_ours.loss_fn, step_ours.opt, step_ours.params = loss_fn, opt, params
     return step_ours, models, margs, rays, style, target, side, flat_n
 
 
@@ -102,6 +99,34 @@ def measure(dev, world, rank, barrier, reps=10, warm=3, n_rays=1024, ns=64, ni=6
         out[f"train_ray_samples_per_s_{operand}"] = world * n_rays * (ns + ni) / (ms * 1e-3)
         out[f"train_native_launches_per_step_{operand}"] = (ops.launch_count() - n0) / reps
         out[f"train_loss_{operand}"] = float(loss)
+        if world > 1:
+            # forward + backward replayed as one CUDA graph per rank, gradient exchange and optimizer outside it
+            try:
+                from crnerf_b200.graphs import GraphedTrainStep
+                from crnerf_b200.ddp import allreduce_gradients
+                gstep, *_r = make_step(dev, world, rank, n_rays, ns, ni, operand, None, capturable=True)
+                graphed = GraphedTrainStep(gstep.loss_fn, optimizer=None, parameters=gstep.params)
+
+                def dstep():
+                    gl = graphed()
+                    allreduce_gradients(gstep.params)
+                    gstep.opt.step()
+                    return gl
+                for _ in range(warm):
+                    dstep()
+                barrier()
+                e0.record()
+                for _ in range(reps):
+                    gl = dstep()
+                e1.record()
+                barrier()
+                t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                out[f"train_step_ms_{operand}_graphed"] = float(t.item())
+                out[f"train_ray_samples_per_s_{operand}_graphed"] = world * n_rays * (ns + ni) / (float(t.item()) * 1e-3)
+                out[f"train_loss_{operand}_graphed"] = float(gl)
+            except Exception as e:   # noqa: BLE001
+                out[f"train_graph_error_{operand}"] = f"{type(e).__name__}: {e}"[:300]
         if world == 1:
             # the same step replayed as one CUDA graph (crnerf_b200.graphs.GraphedTrainStep): the eager
             # step is bound by ~1,600 host-side tensor-library calls, not by the GPU
@@ -123,7 +148,9 @@ def measure(dev, world, rank, barrier, reps=10, warm=3, n_rays=1024, ns=64, ni=6
                 out[f"train_graph_error_{operand}"] = f"{type(e).__name__}: {e}"[:300]
     out["train"] = {"workload": f"{n_rays}-ray (32x32) patch per rank x ({ns}+{ni}) samples, perturb=1, noise_std=1, "
                                 "style_net decode of coarse and fine, MSE, backward, Adam",
-                    "parallelism": f"data parallel x{world}, one flat gradient all-reduce ({flat_n * 4} B) per step",
+                    "parallelism": f"data parallel x{world}, {flat_n * 4} B of gradients per step exchanged as one in-place all-reduce per "
+                                   "gradient storage (crnerf_b200.ddp: 24 collectives for 68 tensors); _graphed = forward + backward as one CUDA graph per rank, "
+                                   "exchange and optimizer outside it",
                     "optimizer": "crnerf_b200.optim.Adam (csrc/optim.cu, torch.optim.Adam's update as one launch per 48 tensors)"
                                  if OPTIMIZER == "native" else "torch.optim.Adam",
                     "reps": reps, "warmup": warm, "timing": "CUDA events over the reps, max over ranks"}

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Instruction histogram per kernel of libcrnerf_b200.so (cuobjdump -sass): the mnemonics that show
 which hardware paths a kernel uses - UTCHMMA (tcgen05.mma), LDTM/STTM (tcgen05.ld/st), UTCBAR
-(tcgen05.commit), UBLKCP (cp.async.bulk), UTMALDG/UTMASTG (tensor-map TMA, not used: every bulk copy
+(tcgen05.commit), UBLKCP (cp.async.bulk, either direction), UTMALDG/UTMASTG (tensor-map TMA, not used: every bulk copy
 here is a 1-D pre-swizzled image), SYNCS (mbarrier), LDG/STG widths, USETMAXREG.
 
   python tools/sass_summary.py > profiles/r02_sass_summary.txt"""
@@ -10,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "cr-nerf-pytorch_b200", "crnerf_b200", "libcrnerf_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
 KEYS = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTCATOMSWS", "UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "USETMAXREG",
-        "LDG.E.256", "LDG.E.128", "LDG", "STG.E.128", "STG", "LDS", "STS", "LDL", "STL", "SHFL", "F2FP", "MUFU", "FFMA", "HFMA2", "BAR"]
+        "LDG.256", "LDG.E.128", "LDG", "STG.256", "STG.E.128", "STG", "LDS", "STS", "LDL", "STL", "SHFL", "F2FP", "MUFU", "FFMA",
+        "HFMA2", "BAR"]
 kern, hist, total = None, {}, {}
 for line in sass.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)
@@ -27,6 +28,9 @@ for line in sass.splitlines():
     if m and kern:
         op = m.group(1)
         total[kern] += 1
+        if op.startswith(("LDG", "STG")) and ".256" in op:   # e.g. LDG.E.NA.ENL2.256.CONSTANT, STG.E.EF.ENL2.256
+            hist[kern][op[:3] + ".256"] += 1
+            continue
         for k in KEYS:
             if op.startswith(k):
                 hist[kern][k] += 1
