@@ -49,7 +49,8 @@ def _worker(rank, world, port, out_dir):
         from crnerf_b200.ddp import allreduce_gradients, gradient_buffers
         params = _make(rank)
         assert len(gradient_buffers(params)) == 3
-        n = allreduce_gradients(params)
+        # the 19-float flat buffer travels alone, the 12-float one and the stand-alone gradient are packed together
+        n = allreduce_gradients(params, pack_below_bytes=64)
         torch.save({"n": n, "grads": [None if p.grad is None else p.grad.clone() for p in params]},
                    os.path.join(out_dir, f"g_{rank}.pt"))
     finally:
@@ -62,7 +63,7 @@ def test_allreduce_gradients_world2_gloo(tmp_path):
     want = [None if a.grad is None else (a.grad + b.grad) / 2 for a, b in zip(_make(0), _make(1))]
     for r in range(world):
         got = torch.load(os.path.join(tmp_path, f"g_{r}.pt"))
-        assert got["n"] == 3          # two flat buffers + the stand-alone gradient: not one collective per tensor
+        assert got["n"] == 2          # one flat buffer on its own + one packed collective: not one per tensor
         for g, w in zip(got["grads"], want):
             assert (g is None) == (w is None)
             if g is not None:
