@@ -142,7 +142,7 @@ composite_backward_kernel(const float* __restrict__ raw, const float* __restrict
       }
     }
   }
-  if (amax != nullptr) {   // non-negative floats order like their bit patterns; NaN / inf are left out like absmax_kernel's
+  if (amax != nullptr) {   // non-negative floats order like their bit patterns; NaN / inf are left out
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, d));
     if (lane == 0 && am > 0.f && am < 3.0e38f) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(am));
