@@ -112,3 +112,22 @@ def test_graphed_forward_backward_without_optimizer_writes_fresh_gradients():
     opt = Adam(g.params, lr=1e-3)
     opt.step()      # views of the flat buffers are what the optimizer consumes
     assert float(opt.state[g.params[0]]["step"]) == 1.0
+
+
+def test_native_adam_refuses_what_it_cannot_update_without_a_gpu():
+    """Host logic of crnerf_b200.optim.Adam: constructor validation like torch.optim.Adam's, and no fallback
+    update for parameters the kernel cannot take (raised before any CUDA call)."""
+    from crnerf_b200.optim import Adam
+    w = torch.nn.Parameter(torch.zeros(4))
+    with pytest.raises(NotImplementedError):
+        Adam([w], amsgrad=True)
+    for bad in (dict(lr=-1.0), dict(eps=-1e-8), dict(betas=(1.0, 0.999)), dict(betas=(0.9, -0.1)), dict(weight_decay=-1.0)):
+        with pytest.raises(ValueError):
+            Adam([w], **bad)
+    opt = Adam([w], lr=1e-3)
+    assert opt.step() is None                      # no gradients: nothing to do, no library call
+    w.grad = torch.ones(4)
+    with pytest.raises(RuntimeError, match="no fallback"):
+        opt.step()
+    assert opt.state_dict()["param_groups"][0]["lr"] == 1e-3 and opt.state_dict()["state"] == {}
+
