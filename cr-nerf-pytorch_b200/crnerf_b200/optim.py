@@ -1,7 +1,7 @@
 """Adam for the training step on the library's own kernel (``csrc/optim.cu``).
 
 The reference builds ``torch.optim.Adam(parameters, lr=hparams.lr, eps=1e-8, weight_decay=...)``
-(utils/__init__.py:33-34) and steps it once per batch.  In its graph-capturable form the tensor
+(utils/__init__.py:31-32) and steps it once per batch.  In its graph-capturable form the tensor
 library's Adam is ~160 launches per step for the 68 parameter tensors of this model (0.45 ms of a
 3.5 ms step); :class:`Adam` is the same update as ONE launch per 48 tensors plus the step counter's
 increment, capturable as is.

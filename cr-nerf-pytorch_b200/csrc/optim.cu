@@ -1,4 +1,4 @@
-// Adam update of the training step (reference utils/__init__.py:33-34: torch.optim.Adam(parameters,
+// Adam update of the training step (reference utils/__init__.py:31-32: torch.optim.Adam(parameters,
 // lr, eps=1e-8, weight_decay) stepped once per batch by train_mask_grid_sample.py's optimizer) as
 // ONE launch per 48 parameter tensors instead of the tensor library's ~160 (21 multi-tensor launches
 // plus two scalar pow kernels per parameter in its graph-capturable form).

@@ -454,7 +454,7 @@ int crnerf_encoder_backward(const void* packed, const float* img, int height, in
                             float* grad_img, void* scratch, size_t scratch_bytes, void* stream);
 
 /* ---- optimizer update of the training step ----------------------------------------------
- * The Adam optimizer as the reference builds it (utils/__init__.py:33-34 `Adam(parameters, lr=hparams.lr,
+ * The Adam optimizer as the reference builds it (utils/__init__.py:31-32 `Adam(parameters, lr=hparams.lr,
  * eps=eps, weight_decay=hparams.weight_decay)`, stepped once per batch by the training loop of
  * train_mask_grid_sample.py) over a table of tensors: one launch per 48 tensors.  params / grads /
  * exp_avg / exp_avg_sq / numel are HOST arrays of n_tensors entries holding device pointers (fp32,

@@ -1,5 +1,5 @@
 """crnerf_b200.optim.Adam (csrc/optim.cu) against torch.optim.Adam, the optimizer the reference
-builds in utils/__init__.py:33-34 (`Adam(parameters, lr, eps=1e-8, weight_decay)`)."""
+builds in utils/__init__.py:31-32 (`Adam(parameters, lr, eps=1e-8, weight_decay)`)."""
 import copy
 import os
 import sys
