@@ -47,6 +47,10 @@ class Adam(torch.optim.Optimizer):
         self._group_step = {}  # group index -> shared device step counter
         self._lr_keepalive = {}
 
+    def __setstate__(self, state):
+        super().__setstate__(state)       # unpickled / deep-copied: the launch-table caches are rebuilt on demand
+        self._tables, self._group_step, self._lr_keepalive = {}, {}, {}
+
     # ---- state ---------------------------------------------------------------------------
     def _shared_step(self, gi: int, plist) -> torch.Tensor:
         """One device counter per group, shared by the `step` entries of its parameters' state (all

@@ -130,4 +130,8 @@ def test_native_adam_refuses_what_it_cannot_update_without_a_gpu():
     with pytest.raises(RuntimeError, match="no fallback"):
         opt.step()
     assert opt.state_dict()["param_groups"][0]["lr"] == 1e-3 and opt.state_dict()["state"] == {}
+    import copy
+    import pickle
+    for clone in (copy.deepcopy(opt), pickle.loads(pickle.dumps(opt))):     # caches are not part of the pickled state
+        assert clone._tables == {} and clone._group_step == {} and clone.param_groups[0]["lr"] == 1e-3
 
