@@ -24,7 +24,7 @@ namespace crnerf {
 namespace {
 
 constexpr int kTP = 8;         // pixels per tile: a 32x32 training patch spreads over 128 CTAs per map (the kernel is
-                               // latency-bound per tile: 16-pixel tiles on 64 CTAs took 1.9x as long)
+                               // latency-bound per tile: 16-pixel tiles on 64 CTAs took 1.8x as long)
 constexpr int kActStride = 297;  // floats per pixel of the activation stash (>= 64+128+64+32, odd: no bank conflicts)
 constexpr int kGStride = 129;
 constexpr int kMaxLayers = 4;
